@@ -1,0 +1,57 @@
+/* TEST INFRASTRUCTURE ONLY (oracle/).  Not part of the product: only tests/, __graft_entry__.smoke() and the
+ * cpu_baseline / --impl reference legs of bench.py may load libvoforacle.so.
+ *
+ * Plain-C restatement of dune-vof's per-timestep hot path on an axis-aligned Cartesian
+ * grid.  Every function cites the reference file:line it restates.  Pinned bit-for-bit against the reference's
+ * own templates (oracle/_ref/libvofref.so, built from /root/reference) by tests/test_oracle_vs_reference.py and
+ * against the golden vectors in tests/golden.  The only third-party arithmetic (dune-common FieldMatrix::solve,
+ * dune-spgrid cell coordinates) is restated from the published closed forms: parity is UNPINNED at those two
+ * boundaries.
+ *
+ * Conventions: cell index x-fastest; cell lower corner = origin + i*h; centre = lower + 0.5*h;
+ * faces ordered x-,x+,y-,y+,z-,z+; half-space stored as (n[dim], d), fluid side n.x + d > 0;
+ * flags 0 empty, 1 mixed, 2 mixedfull, 3 full, 99 nan (flagset.hh:18-24).
+ */
+#ifndef VOF_ORACLE_H
+#define VOF_ORACLE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct
+{
+  int dim;
+  int n[3];
+  double origin[3];
+  double h[3];
+} vo_grid;
+
+enum { VO_RECON_YOUNGS = 0, VO_RECON_HF = 1, VO_RECON_SWARTZ = 2 };
+enum { VO_PROB_ROTATING_CIRCLE = 0, VO_PROB_SFLOW = 1, VO_PROB_SLOTTED_CYLINDER = 2, VO_PROB_LINEAR_WALL = 3, VO_PROB_LEVEQUE = 4 };
+
+/* operators */
+int vo_flag ( const vo_grid *g, const double *u, double eps, uint8_t *flags );
+int vo_reconstruct ( const vo_grid *g, int kind, const double *u, const uint8_t *flags, double *hs, int max_iterations );
+int vo_evolve ( const vo_grid *g, const double *hs, const uint8_t *flags, int problem, double time, double dt, double *update, double *dt_est );
+int vo_curvature ( const vo_grid *g, const double *u, const double *hs, const uint8_t *flags, double *kappa, uint8_t *valid );
+int vo_init ( const vo_grid *g, int problem, double time, double *u );
+int vo_face_velocity ( const vo_grid *g, int problem, double time, int64_t cell, int face, double *v );
+int vo_run ( const vo_grid *g, int kind, int problem, double eps, double cfl, int max_iterations, int passes,
+             double *u, double *time_io, double *dt_io, double *phase_seconds, int64_t *mixed_cell_steps );
+
+/* geometry primitives on one axis-aligned cell */
+int vo_locate ( int dim, const double *lo, const double *h, const double *normal, double fraction, double *out );
+int vo_volume_fraction ( int dim, const double *lo, const double *h, const double *hs, double *out );
+int vo_flux ( int dim, const double *lo, const double *h, int face, const double *v, const double *hs, double *out );
+int vo_interface ( int dim, const double *lo, const double *h, const double *hs, int *nverts, double *verts, double *centroid, double *measure );
+double vo_brent_cubic ( double A, double B, double C, double target, double a, double b, double tol );
+double vo_det_cospi ( double s );
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* VOF_ORACLE_H */
