@@ -1,0 +1,1033 @@
+// vofx: implementation of the C ABI in include/vofx.h (host side: context, velocity tables, launches, staging).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -shared -Xcompiler -fPIC
+//   -fmad=false: the parity contract of vofx_math.cuh (no FMA contraction in the device arithmetic).
+#include "../../include/vofx.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "vofx_kernels.cuh"
+
+using namespace vofx;
+
+namespace
+{
+
+  thread_local std::string g_lastError;
+
+  int fail ( int status, const std::string &msg )
+  {
+    g_lastError = msg;
+    return status;
+  }
+
+#define VOFX_CUDA( call )                                                                                       \
+  do                                                                                                            \
+  {                                                                                                             \
+    const cudaError_t vofx_err_ = ( call );                                                                     \
+    if( vofx_err_ != cudaSuccess )                                                                              \
+      return fail( VOFX_ERR_CUDA, std::string( #call ) + ": " + cudaGetErrorString( vofx_err_ ) );              \
+  } while( 0 )
+
+  constexpr int kSMs = 148;   // B200: grids are sized in multiples of the SM count
+
+} // namespace
+
+struct vofx_ctx
+{
+  vofx_grid_desc desc;
+  Grid grid;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int numSMs = kSMs;
+
+  // scratch owned by the context
+  int capacity = 0;
+  int *mixedList = nullptr;
+  int *slot = nullptr;
+  FluxRecord *records = nullptr;
+  StepState *state = nullptr;
+  double *curv1 = nullptr;
+  unsigned char *ok1 = nullptr;
+  double *scalars = nullptr;        // [0] time override, [1] dt override (operator-level evolve)
+
+  // velocity
+  Velocity velHost;                 // device pointers inside
+  Velocity *velDev = nullptr;
+  std::vector< double * > velTables;
+  bool velocitySet = false;
+
+  // staging for the host-buffer variants
+  void *pinned = nullptr;
+  size_t pinnedBytes = 0;
+  double *dU = nullptr, *dHs = nullptr, *dUpd = nullptr, *dKappa = nullptr;
+  unsigned char *dFlags = nullptr, *dValid = nullptr;
+
+  long long launches = 0;
+};
+
+namespace
+{
+
+  int setDevice ( const vofx_ctx *ctx )
+  {
+    VOFX_CUDA( cudaSetDevice( ctx->device ) );
+    return VOFX_OK;
+  }
+
+  int gridBlocks ( const vofx_ctx *ctx, long long items, int threads, int blocksPerSM )
+  {
+    long long need = ( items + threads - 1 ) / threads;
+    const long long cap = (long long) ctx->numSMs * blocksPerSM;
+    if( need > cap )
+      need = cap;
+    if( need < 1 )
+      need = 1;
+    return (int) need;
+  }
+
+  int checkLaunch ( vofx_ctx *ctx, const char *what )
+  {
+    ctx->launches++;
+    const cudaError_t e = cudaGetLastError();
+    if( e != cudaSuccess )
+      return fail( VOFX_ERR_CUDA, std::string( what ) + ": " + cudaGetErrorString( e ) );
+    return VOFX_OK;
+  }
+
+  template< class T >
+  int ensureDevice ( T *&p, size_t count )
+  {
+    if( p )
+      return VOFX_OK;
+    VOFX_CUDA( cudaMalloc( (void **) &p, count * sizeof( T ) ) );
+    return VOFX_OK;
+  }
+
+  int ensurePinned ( vofx_ctx *ctx, size_t bytes )
+  {
+    if( ctx->pinnedBytes >= bytes )
+      return VOFX_OK;
+    if( ctx->pinned )
+      cudaFreeHost( ctx->pinned );
+    ctx->pinned = nullptr;
+    ctx->pinnedBytes = 0;
+    VOFX_CUDA( cudaMallocHost( &ctx->pinned, bytes ) );
+    ctx->pinnedBytes = bytes;
+    return VOFX_OK;
+  }
+
+  // ---- launches -------------------------------------------------------------------------------------------------
+
+  int launchFlag ( vofx_ctx *ctx, const double *u, double eps, unsigned char *flags, bool compact )
+  {
+    const Grid &g = ctx->grid;
+    const long long quads = ( g.cells + 3 ) / 4;
+    const int blocks = gridBlocks( ctx, quads, 256, 8 );
+    if( g.dim == 2 )
+      k_flag_compact< 2 ><<< blocks, 256, 0, ctx->stream >>>( g, u, eps, flags, ctx->mixedList, ctx->slot, ctx->capacity, ctx->state, compact ? 1 : 0 );
+    else
+      k_flag_compact< 3 ><<< blocks, 256, 0, ctx->stream >>>( g, u, eps, flags, ctx->mixedList, ctx->slot, ctx->capacity, ctx->state, compact ? 1 : 0 );
+    return checkLaunch( ctx, "k_flag_compact" );
+  }
+
+  int launchResetCounters ( vofx_ctx *ctx )
+  {
+    k_reset_counters<<< 1, 1, 0, ctx->stream >>>( ctx->state );
+    return checkLaunch( ctx, "k_reset_counters" );
+  }
+
+  int launchCompactFlags ( vofx_ctx *ctx, const unsigned char *flags )
+  {
+    const Grid &g = ctx->grid;
+    const int blocks = gridBlocks( ctx, g.cells, 256, 8 );
+    if( g.dim == 2 )
+      k_compact_flags< 2 ><<< blocks, 256, 0, ctx->stream >>>( g, flags, ctx->mixedList, ctx->slot, ctx->capacity, ctx->state );
+    else
+      k_compact_flags< 3 ><<< blocks, 256, 0, ctx->stream >>>( g, flags, ctx->mixedList, ctx->slot, ctx->capacity, ctx->state );
+    return checkLaunch( ctx, "k_compact_flags" );
+  }
+
+  int launchReconstruct ( vofx_ctx *ctx, int kind, const double *u, const unsigned char *flags, double *hs, int maxIterations )
+  {
+    const Grid &g = ctx->grid;
+    const int blocks = ctx->numSMs * 8;
+    if( g.dim == 2 )
+      k_youngs< 2 ><<< blocks, 128, 0, ctx->stream >>>( g, u, ctx->mixedList, ctx->state, ctx->capacity, hs );
+    else
+      k_youngs< 3 ><<< blocks, 128, 0, ctx->stream >>>( g, u, ctx->mixedList, ctx->state, ctx->capacity, hs );
+    int rc = checkLaunch( ctx, "k_youngs" );
+    if( rc )
+      return rc;
+    if( kind == VOFX_RECON_HF )
+    {
+      if( g.dim == 2 )
+        k_hf< 2 ><<< blocks, 128, 0, ctx->stream >>>( g, u, ctx->mixedList, ctx->state, ctx->capacity, hs );
+      else
+        k_hf< 3 ><<< blocks, 128, 0, ctx->stream >>>( g, u, ctx->mixedList, ctx->state, ctx->capacity, hs );
+      rc = checkLaunch( ctx, "k_hf" );
+    }
+    else if( kind == VOFX_RECON_SWARTZ )
+    {
+      if( g.dim == 2 )
+        k_swartz< 2 ><<< ctx->numSMs * 16, 64, 0, ctx->stream >>>( g, u, flags, ctx->mixedList, ctx->state, ctx->capacity, hs, maxIterations );
+      else
+        k_swartz< 3 ><<< ctx->numSMs * 16, 64, 0, ctx->stream >>>( g, u, flags, ctx->mixedList, ctx->state, ctx->capacity, hs, maxIterations );
+      rc = checkLaunch( ctx, "k_swartz" );
+    }
+    else if( kind != VOFX_RECON_YOUNGS )
+      return fail( VOFX_ERR_ARGUMENT, "unknown reconstruction kind" );
+    return rc;
+  }
+
+  int launchFlux ( vofx_ctx *ctx, const double *hs, const unsigned char *flags, const double *timeOverride, const double *dtOverride )
+  {
+    const Grid &g = ctx->grid;
+    const int blocks = ctx->numSMs * 8;
+    if( g.dim == 2 )
+      k_flux< 2 ><<< blocks, 128, 0, ctx->stream >>>( g, ctx->velDev, hs, flags, ctx->mixedList, ctx->state, ctx->capacity, ctx->records, timeOverride, dtOverride );
+    else
+      k_flux< 3 ><<< blocks, 128, 0, ctx->stream >>>( g, ctx->velDev, hs, flags, ctx->mixedList, ctx->state, ctx->capacity, ctx->records, timeOverride, dtOverride );
+    return checkLaunch( ctx, "k_flux" );
+  }
+
+  int launchUpdate ( vofx_ctx *ctx, const unsigned char *flags, double *target, bool accumulate )
+  {
+    const Grid &g = ctx->grid;
+    const int blocks = ctx->numSMs * 8;
+    if( g.dim == 2 )
+      k_update< 2 ><<< blocks, 128, 0, ctx->stream >>>( g, flags, ctx->mixedList, ctx->slot, ctx->state, ctx->capacity, ctx->records, target, accumulate ? 1 : 0 );
+    else
+      k_update< 3 ><<< blocks, 128, 0, ctx->stream >>>( g, flags, ctx->mixedList, ctx->slot, ctx->state, ctx->capacity, ctx->records, target, accumulate ? 1 : 0 );
+    return checkLaunch( ctx, "k_update" );
+  }
+
+  int launchCurvature ( vofx_ctx *ctx, const double *u, const double *hs, const unsigned char *flags, double *kappa, unsigned char *valid )
+  {
+    const Grid &g = ctx->grid;
+    const int blocks = ctx->numSMs * 8;
+    // curvature[ entity ] = 0 and satisfiesConstraint_[ entity ] = 0 for all cells, cartesianheightfunctioncurvature.hh:57-60
+    VOFX_CUDA( cudaMemsetAsync( kappa, 0, sizeof( double ) * (size_t) g.cells, ctx->stream ) );
+    if( valid )
+      VOFX_CUDA( cudaMemsetAsync( valid, 0, (size_t) g.cells, ctx->stream ) );
+    if( g.dim == 2 )
+      k_curvature_local< 2 ><<< blocks, 128, 0, ctx->stream >>>( g, u, hs, ctx->mixedList, ctx->state, ctx->capacity, ctx->curv1, ctx->ok1 );
+    else
+      k_curvature_local< 3 ><<< blocks, 128, 0, ctx->stream >>>( g, u, hs, ctx->mixedList, ctx->state, ctx->capacity, ctx->curv1, ctx->ok1 );
+    int rc = checkLaunch( ctx, "k_curvature_local" );
+    if( rc )
+      return rc;
+    if( g.dim == 2 )
+      k_curvature_average< 2 ><<< blocks, 128, 0, ctx->stream >>>( g, flags, ctx->mixedList, ctx->slot, ctx->state, ctx->capacity, ctx->curv1, ctx->ok1, kappa, valid );
+    else
+      k_curvature_average< 3 ><<< blocks, 128, 0, ctx->stream >>>( g, flags, ctx->mixedList, ctx->slot, ctx->state, ctx->capacity, ctx->curv1, ctx->ok1, kappa, valid );
+    return checkLaunch( ctx, "k_curvature_average" );
+  }
+
+  int checkOverflow ( vofx_ctx *ctx, const StepState &s )
+  {
+    if( s.overflow )
+      return fail( VOFX_ERR_STATE, "mixed-cell list overflow: more than " + std::to_string( ctx->capacity ) + " mixed cells" );
+    return VOFX_OK;
+  }
+
+  int readState ( vofx_ctx *ctx, StepState &s )
+  {
+    VOFX_CUDA( cudaMemcpyAsync( &s, ctx->state, sizeof( StepState ), cudaMemcpyDeviceToHost, ctx->stream ) );
+    VOFX_CUDA( cudaStreamSynchronize( ctx->stream ) );
+    return checkOverflow( ctx, s );
+  }
+
+  // ---- built-in velocity tables ---------------------------------------------------------------------------------
+
+  typedef double ( *Factor ) ( double );
+  double fOne ( double ) { return 1.0; }
+  double fMinusHalf ( double x ) { return x - 0.5; }                 // c = x - 0.5
+  double fHalfMinus ( double x ) { return 0.5 - x; }
+  double fNegMinusHalf ( double x ) { return -( x - 0.5 ); }
+  double fSflowLin ( double x ) { return 4 * x - 2; }
+  double fSflowCube ( double x ) { const double y = 4 * x - 2; return y * y * y; }
+  double fSinSq ( double x ) { const double s = std::sin( M_PI * x ); return s * s; }
+  double fTwoSinSq ( double x ) { return 2.0 * fSinSq( x ); }
+  double fSinTwo ( double x ) { return std::sin( 2.0 * M_PI * x ); }
+  double fNegSinTwo ( double x ) { return -std::sin( 2.0 * M_PI * x ); }
+
+  int setFactor ( vofx_ctx *ctx, int component, int term, int axis, Factor f )
+  {
+    const vofx_grid_desc &d = ctx->desc;
+    const int n = d.n_global[ axis ];
+    std::vector< double > centre( n ), lower( n ), upper( n );
+    for( int i = 0; i < n; ++i )
+    {
+      const double lo = d.origin[ axis ] + i * d.h[ axis ];
+      lower[ i ] = f( lo );
+      upper[ i ] = f( lo + d.h[ axis ] );
+      centre[ i ] = f( lo + 0.5 * d.h[ axis ] );
+    }
+    return vofx_velocity_set_factor( ctx, component, term, axis, centre.data(), lower.data(), upper.data() );
+  }
+
+  int setTerm ( vofx_ctx *ctx, int component, int term, Factor fx, Factor fy, Factor fz )
+  {
+    int rc = setFactor( ctx, component, term, 0, fx );
+    rc = rc ? rc : setFactor( ctx, component, term, 1, fy );
+    if( ctx->desc.dim == 3 )
+      rc = rc ? rc : setFactor( ctx, component, term, 2, fz );
+    return rc;
+  }
+
+  int uploadVelocity ( vofx_ctx *ctx )
+  {
+    VOFX_CUDA( cudaMemcpyAsync( ctx->velDev, &ctx->velHost, sizeof( Velocity ), cudaMemcpyHostToDevice, ctx->stream ) );
+    VOFX_CUDA( cudaStreamSynchronize( ctx->stream ) );
+    return VOFX_OK;
+  }
+
+  int requireVelocity ( vofx_ctx *ctx )
+  {
+    if( !ctx->velocitySet )
+      return fail( VOFX_ERR_STATE, "no velocity set (vofx_velocity_builtin / vofx_velocity_set_*)" );
+    return VOFX_OK;
+  }
+
+} // namespace
+
+
+extern "C"
+{
+
+  const char *vofx_last_error ( void ) { return g_lastError.c_str(); }
+
+  int vofx_create ( const vofx_grid_desc *desc, int device, vofx_ctx **out )
+  {
+    if( !desc || !out )
+      return fail( VOFX_ERR_ARGUMENT, "null argument" );
+    if( desc->dim != 2 && desc->dim != 3 )
+      return fail( VOFX_ERR_ARGUMENT, "dim must be 2 or 3" );
+    if( desc->halo < 0 )
+      return fail( VOFX_ERR_ARGUMENT, "negative halo" );
+    for( int d = 0; d < desc->dim; ++d )
+    {
+      if( desc->n_global[ d ] < 1 || desc->n_local[ d ] < 1 || desc->lo[ d ] < 0 || desc->lo[ d ] + desc->n_local[ d ] > desc->n_global[ d ] )
+        return fail( VOFX_ERR_ARGUMENT, "inconsistent grid extents" );
+      if( !( desc->h[ d ] > 0.0 ) )
+        return fail( VOFX_ERR_ARGUMENT, "mesh width must be positive" );
+      if( d != desc->dim - 1 && ( desc->lo[ d ] != 0 || desc->n_local[ d ] != desc->n_global[ d ] ) )
+        return fail( VOFX_ERR_ARGUMENT, "only the last axis may be decomposed (slabs)" );
+    }
+
+    int count = 0;
+    if( cudaGetDeviceCount( &count ) != cudaSuccess || count == 0 )
+      return fail( VOFX_ERR_CUDA, "no CUDA device: vofx has no CPU fallback" );
+    if( device < 0 )
+      VOFX_CUDA( cudaGetDevice( &device ) );
+    if( device >= count )
+      return fail( VOFX_ERR_ARGUMENT, "device index out of range" );
+    VOFX_CUDA( cudaSetDevice( device ) );
+
+    vofx_ctx *ctx = new vofx_ctx();
+    ctx->desc = *desc;
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if( cudaGetDeviceProperties( &prop, device ) == cudaSuccess )
+      ctx->numSMs = prop.multiProcessorCount;
+
+    Grid &g = ctx->grid;
+    g.dim = desc->dim;
+    const int la = desc->dim - 1;
+    g.cells = 1;
+    for( int d = 0; d < 3; ++d )
+    {
+      const bool used = d < desc->dim;
+      g.ns[ d ] = used ? desc->n_local[ d ] + ( d == la ? 2 * desc->halo : 0 ) : 1;
+      g.g0[ d ] = used ? desc->lo[ d ] - ( d == la ? desc->halo : 0 ) : 0;
+      g.ng[ d ] = used ? desc->n_global[ d ] : 1;
+      g.origin[ d ] = used ? desc->origin[ d ] : 0.0;
+      g.h[ d ] = used ? desc->h[ d ] : 1.0;
+      g.cells *= g.ns[ d ];
+    }
+    if( g.cells >= ( 1LL << 31 ) )
+    {
+      delete ctx;
+      return fail( VOFX_ERR_ARGUMENT, "more than 2^31 cells per context" );
+    }
+    g.own0 = desc->halo;
+    g.own1 = desc->halo + desc->n_local[ la ];
+    // mixed cells one layer beyond the owned box are reconstructed too (their fluxes enter owned cells)
+    const int dom0 = ( -g.g0[ la ] > 0 ) ? -g.g0[ la ] : 0;
+    const int dom1 = ( g.ng[ la ] - g.g0[ la ] < g.ns[ la ] ) ? g.ng[ la ] - g.g0[ la ] : g.ns[ la ];
+    g.list0 = ( g.own0 - 1 > dom0 ) ? g.own0 - 1 : dom0;
+    g.list1 = ( g.own1 + 1 < dom1 ) ? g.own1 + 1 : dom1;
+
+    // capacity of the mixed-cell list: every cell on small grids, an eighth of the cells (>= 2^20) on large ones
+    long long cap = g.cells / 8;
+    if( cap < ( 1LL << 20 ) )
+      cap = 1LL << 20;
+    if( cap > g.cells )
+      cap = g.cells;
+    ctx->capacity = (int) cap;
+
+    int rc = VOFX_OK;
+    auto alloc = [ & ] ( void **p, size_t bytes ) {
+      if( rc == VOFX_OK && cudaMalloc( p, bytes ) != cudaSuccess )
+        rc = fail( VOFX_ERR_CUDA, "cudaMalloc of context scratch failed" );
+    };
+    alloc( (void **) &ctx->mixedList, sizeof( int ) * (size_t) ctx->capacity );
+    alloc( (void **) &ctx->slot, sizeof( int ) * (size_t) g.cells );
+    alloc( (void **) &ctx->records, sizeof( FluxRecord ) * (size_t) ctx->capacity );
+    alloc( (void **) &ctx->state, sizeof( StepState ) );
+    alloc( (void **) &ctx->curv1, sizeof( double ) * (size_t) ctx->capacity );
+    alloc( (void **) &ctx->ok1, (size_t) ctx->capacity );
+    alloc( (void **) &ctx->scalars, sizeof( double ) * 4 );
+    alloc( (void **) &ctx->velDev, sizeof( Velocity ) );
+    if( rc != VOFX_OK )
+    {
+      vofx_destroy( ctx );
+      return rc;
+    }
+    StepState init;
+    std::memset( &init, 0, sizeof( init ) );
+    init.dtEst = DBL_MAX;
+    cudaMemcpy( ctx->state, &init, sizeof( init ), cudaMemcpyHostToDevice );
+    std::memset( &ctx->velHost, 0, sizeof( Velocity ) );
+    *out = ctx;
+    return VOFX_OK;
+  }
+
+  void vofx_destroy ( vofx_ctx *ctx )
+  {
+    if( !ctx )
+      return;
+    cudaSetDevice( ctx->device );
+    cudaFree( ctx->mixedList );
+    cudaFree( ctx->slot );
+    cudaFree( ctx->records );
+    cudaFree( ctx->state );
+    cudaFree( ctx->curv1 );
+    cudaFree( ctx->ok1 );
+    cudaFree( ctx->scalars );
+    cudaFree( ctx->velDev );
+    for( double *t : ctx->velTables )
+      cudaFree( t );
+    cudaFree( ctx->dU );
+    cudaFree( ctx->dHs );
+    cudaFree( ctx->dUpd );
+    cudaFree( ctx->dKappa );
+    cudaFree( ctx->dFlags );
+    cudaFree( ctx->dValid );
+    if( ctx->pinned )
+      cudaFreeHost( ctx->pinned );
+    delete ctx;
+  }
+
+  int vofx_set_stream ( vofx_ctx *ctx, void *cuda_stream )
+  {
+    if( !ctx )
+      return fail( VOFX_ERR_ARGUMENT, "null context" );
+    ctx->stream = (cudaStream_t) cuda_stream;
+    return VOFX_OK;
+  }
+
+  int64_t vofx_cells ( const vofx_ctx *ctx ) { return ctx ? (int64_t) ctx->grid.cells : 0; }
+
+  int64_t vofx_launch_count ( const vofx_ctx *ctx ) { return ctx ? (int64_t) ctx->launches : 0; }
+
+  // ---- velocity -----------------------------------------------------------------------------------------------------
+
+  int vofx_velocity_clear ( vofx_ctx *ctx )
+  {
+    if( !ctx )
+      return fail( VOFX_ERR_ARGUMENT, "null context" );
+    int rc = setDevice( ctx );
+    if( rc )
+      return rc;
+    VOFX_CUDA( cudaStreamSynchronize( ctx->stream ) );
+    for( double *t : ctx->velTables )
+      cudaFree( t );
+    ctx->velTables.clear();
+    std::memset( &ctx->velHost, 0, sizeof( Velocity ) );
+    ctx->velocitySet = false;
+    return uploadVelocity( ctx );
+  }
+
+  int vofx_velocity_set_component ( vofx_ctx *ctx, int component, int nterms, double coef, int time_factor, double period )
+  {
+    if( !ctx || component < 0 || component >= ctx->desc.dim || nterms < 0 || nterms > 2 )
+      return fail( VOFX_ERR_ARGUMENT, "bad velocity component description" );
+    if( time_factor != VOFX_TIME_CONST && time_factor != VOFX_TIME_COSPI )
+      return fail( VOFX_ERR_ARGUMENT, "unknown time factor" );
+    int rc = setDevice( ctx );
+    if( rc )
+      return rc;
+    ctx->velHost.nterms[ component ] = nterms;
+    ctx->velHost.coef[ component ] = coef;
+    ctx->velHost.timeKind[ component ] = time_factor;
+    ctx->velHost.period[ component ] = period;
+    ctx->velocitySet = true;
+    return uploadVelocity( ctx );
+  }
+
+  int vofx_velocity_set_factor ( vofx_ctx *ctx, int component, int term, int axis, const double *at_centre, const double *at_lower_face, const double *at_upper_face )
+  {
+    if( !ctx || component < 0 || component >= ctx->desc.dim || term < 0 || term > 1 || axis < 0 || axis >= ctx->desc.dim
+        || !at_centre || !at_lower_face || !at_upper_face )
+      return fail( VOFX_ERR_ARGUMENT, "bad velocity factor description" );
+    int rc = setDevice( ctx );
+    if( rc )
+      return rc;
+    const size_t n = (size_t) ctx->desc.n_global[ axis ];
+    const double *src[ 3 ] = { at_centre, at_lower_face, at_upper_face };
+    for( int k = 0; k < 3; ++k )
+    {
+      double *dev = nullptr;
+      VOFX_CUDA( cudaMalloc( (void **) &dev, n * sizeof( double ) ) );
+      ctx->velTables.push_back( dev );
+      VOFX_CUDA( cudaMemcpy( dev, src[ k ], n * sizeof( double ), cudaMemcpyHostToDevice ) );
+      ctx->velHost.tab[ component ][ term ][ axis ][ k ] = dev;
+    }
+    return uploadVelocity( ctx );
+  }
+
+  int vofx_velocity_builtin ( vofx_ctx *ctx, int problem )
+  {
+    if( !ctx )
+      return fail( VOFX_ERR_ARGUMENT, "null context" );
+    int rc = vofx_velocity_clear( ctx );
+    if( rc )
+      return rc;
+    const int dim = ctx->desc.dim;
+    const double omega = 2 * M_PI / 10;
+    switch( problem )
+    {
+    case VOFX_PROB_ROTATING_CIRCLE:
+      // 2D rotatingcircle.hh:45-52: r = ( x1 - c1, c0 - x0 ) * omega ; 3D :92-101: rot = ( c1, -c0, 0 ) * omega with c = x - 0.5
+      rc = vofx_velocity_set_component( ctx, 0, 1, omega, VOFX_TIME_CONST, 1.0 );
+      rc = rc ? rc : setTerm( ctx, 0, 0, fOne, fMinusHalf, fOne );
+      rc = rc ? rc : vofx_velocity_set_component( ctx, 1, 1, omega, VOFX_TIME_CONST, 1.0 );
+      rc = rc ? rc : setTerm( ctx, 1, 0, dim == 2 ? fHalfMinus : fNegMinusHalf, fOne, fOne );
+      if( dim == 3 )
+        rc = rc ? rc : vofx_velocity_set_component( ctx, 2, 0, 0.0, VOFX_TIME_CONST, 1.0 );
+      return rc;
+    case VOFX_PROB_SFLOW:
+      // sflow.hh:35-42,73-82: v = ( 0.25*( y0 + y1^3 ), -0.25*( y1 + y0^3 ) [, 0] ), y = 4x - 2
+      rc = vofx_velocity_set_component( ctx, 0, 2, 0.25, VOFX_TIME_CONST, 1.0 );
+      rc = rc ? rc : setTerm( ctx, 0, 0, fSflowLin, fOne, fOne );
+      rc = rc ? rc : setTerm( ctx, 0, 1, fOne, fSflowCube, fOne );
+      rc = rc ? rc : vofx_velocity_set_component( ctx, 1, 2, -0.25, VOFX_TIME_CONST, 1.0 );
+      rc = rc ? rc : setTerm( ctx, 1, 0, fOne, fSflowLin, fOne );
+      rc = rc ? rc : setTerm( ctx, 1, 1, fSflowCube, fOne, fOne );
+      if( dim == 3 )
+        rc = rc ? rc : vofx_velocity_set_component( ctx, 2, 0, 0.0, VOFX_TIME_CONST, 1.0 );
+      return rc;
+    case VOFX_PROB_SLOTTED_CYLINDER:
+      if( dim != 2 )
+        return fail( VOFX_ERR_ARGUMENT, "SlottedCylinder is a 2D problem" );
+      // slottedcylinder.hh:47-55: rot = ( x1 - 0.5, -( x0 - 0.5 ) ) * omega
+      rc = vofx_velocity_set_component( ctx, 0, 1, omega, VOFX_TIME_CONST, 1.0 );
+      rc = rc ? rc : setTerm( ctx, 0, 0, fOne, fMinusHalf, fOne );
+      rc = rc ? rc : vofx_velocity_set_component( ctx, 1, 1, omega, VOFX_TIME_CONST, 1.0 );
+      rc = rc ? rc : setTerm( ctx, 1, 0, fNegMinusHalf, fOne, fOne );
+      return rc;
+    case VOFX_PROB_LINEAR_WALL:
+      // linearwall.hh:27-31: ( 0.02, 0 [, 0] )
+      rc = vofx_velocity_set_component( ctx, 0, 1, 0.02, VOFX_TIME_CONST, 1.0 );
+      rc = rc ? rc : setTerm( ctx, 0, 0, fOne, fOne, fOne );
+      for( int a = 1; a < dim; ++a )
+        rc = rc ? rc : vofx_velocity_set_component( ctx, a, 0, 0.0, VOFX_TIME_CONST, 1.0 );
+      return rc;
+    case VOFX_PROB_LEVEQUE:
+      if( dim == 2 )
+      {
+        // single vortex: ( sin^2(pi x) sin(2 pi y), -sin(2 pi x) sin^2(pi y) ) cos(pi t/8)
+        rc = vofx_velocity_set_component( ctx, 0, 1, 1.0, VOFX_TIME_COSPI, 8.0 );
+        rc = rc ? rc : setTerm( ctx, 0, 0, fSinSq, fSinTwo, fOne );
+        rc = rc ? rc : vofx_velocity_set_component( ctx, 1, 1, 1.0, VOFX_TIME_COSPI, 8.0 );
+        rc = rc ? rc : setTerm( ctx, 1, 0, fNegSinTwo, fSinSq, fOne );
+      }
+      else
+      {
+        // deformation field: ( 2 sin^2(pi x) sin(2 pi y) sin(2 pi z), -sin(2 pi x) sin^2(pi y) sin(2 pi z),
+        //                      -sin(2 pi x) sin(2 pi y) sin^2(pi z) ) cos(pi t/3)
+        rc = vofx_velocity_set_component( ctx, 0, 1, 1.0, VOFX_TIME_COSPI, 3.0 );
+        rc = rc ? rc : setTerm( ctx, 0, 0, fTwoSinSq, fSinTwo, fSinTwo );
+        rc = rc ? rc : vofx_velocity_set_component( ctx, 1, 1, 1.0, VOFX_TIME_COSPI, 3.0 );
+        rc = rc ? rc : setTerm( ctx, 1, 0, fNegSinTwo, fSinSq, fSinTwo );
+        rc = rc ? rc : vofx_velocity_set_component( ctx, 2, 1, 1.0, VOFX_TIME_COSPI, 3.0 );
+        rc = rc ? rc : setTerm( ctx, 2, 0, fNegSinTwo, fSinTwo, fSinSq );
+      }
+      return rc;
+    }
+    return fail( VOFX_ERR_ARGUMENT, "unknown built-in problem" );
+  }
+
+  int vofx_face_velocity ( vofx_ctx *ctx, double time, int64_t cell, int face, double *v_host )
+  {
+    if( !ctx || !v_host || cell < 0 || cell >= ctx->grid.cells || face < 0 || face >= 2 * ctx->desc.dim )
+      return fail( VOFX_ERR_ARGUMENT, "bad argument" );
+    int rc = setDevice( ctx );
+    rc = rc ? rc : requireVelocity( ctx );
+    if( rc )
+      return rc;
+    k_test_face_velocity<<< 1, 1, 0, ctx->stream >>>( ctx->grid, ctx->velDev, time, cell, face, ctx->scalars );
+    rc = checkLaunch( ctx, "k_test_face_velocity" );
+    if( rc )
+      return rc;
+    double v[ 3 ];
+    VOFX_CUDA( cudaMemcpyAsync( v, ctx->scalars, sizeof( v ), cudaMemcpyDeviceToHost, ctx->stream ) );
+    VOFX_CUDA( cudaStreamSynchronize( ctx->stream ) );
+    for( int d = 0; d < ctx->desc.dim; ++d )
+      v_host[ d ] = v[ d ];
+    return VOFX_OK;
+  }
+
+  // ---- operators on device arrays -------------------------------------------------------------------------------------
+
+  int vofx_flag ( vofx_ctx *ctx, const double *u, double eps, uint8_t *flags )
+  {
+    if( !ctx || !u || !flags )
+      return fail( VOFX_ERR_ARGUMENT, "null argument" );
+    int rc = setDevice( ctx );
+    return rc ? rc : launchFlag( ctx, u, eps, flags, false );
+  }
+
+  int vofx_reconstruct ( vofx_ctx *ctx, int kind, const double *u, const uint8_t *flags, double *halfspaces, int max_iterations )
+  {
+    if( !ctx || !u || !flags || !halfspaces )
+      return fail( VOFX_ERR_ARGUMENT, "null argument" );
+    int rc = setDevice( ctx );
+    if( rc )
+      return rc;
+    // reconstructions.clear(), modifiedyoungs.hh:65
+    VOFX_CUDA( cudaMemsetAsync( halfspaces, 0, sizeof( double ) * (size_t) ctx->grid.cells * ( ctx->desc.dim + 1 ), ctx->stream ) );
+    rc = launchResetCounters( ctx );
+    rc = rc ? rc : launchCompactFlags( ctx, flags );
+    rc = rc ? rc : launchReconstruct( ctx, kind, u, flags, halfspaces, max_iterations );
+    if( rc )
+      return rc;
+    StepState s;
+    return readState( ctx, s );
+  }
+
+  int vofx_evolve ( vofx_ctx *ctx, const double *halfspaces, const uint8_t *flags, double time, double dt, double *update, double *dt_est )
+  {
+    if( !ctx || !halfspaces || !flags || !update || !dt_est )
+      return fail( VOFX_ERR_ARGUMENT, "null argument" );
+    int rc = setDevice( ctx );
+    rc = rc ? rc : requireVelocity( ctx );
+    if( rc )
+      return rc;
+    const double td[ 2 ] = { time, dt };
+    VOFX_CUDA( cudaMemcpyAsync( ctx->scalars, td, sizeof( td ), cudaMemcpyHostToDevice, ctx->stream ) );
+    // update.clear(), evolution/evolution.hh:62
+    VOFX_CUDA( cudaMemsetAsync( update, 0, sizeof( double ) * (size_t) ctx->grid.cells, ctx->stream ) );
+    rc = launchResetCounters( ctx );
+    rc = rc ? rc : launchCompactFlags( ctx, flags );
+    rc = rc ? rc : launchFlux( ctx, halfspaces, flags, ctx->scalars, ctx->scalars + 1 );
+    rc = rc ? rc : launchUpdate( ctx, flags, update, false );
+    if( rc )
+      return rc;
+    StepState s;
+    rc = readState( ctx, s );
+    *dt_est = s.dtEst;
+    return rc;
+  }
+
+  int vofx_axpy ( vofx_ctx *ctx, double *u, double a, const double *x )
+  {
+    if( !ctx || !u || !x )
+      return fail( VOFX_ERR_ARGUMENT, "null argument" );
+    int rc = setDevice( ctx );
+    if( rc )
+      return rc;
+    k_axpy<<< gridBlocks( ctx, ctx->grid.cells, 256, 8 ), 256, 0, ctx->stream >>>( ctx->grid.cells, u, a, x );
+    return checkLaunch( ctx, "k_axpy" );
+  }
+
+  int vofx_curvature ( vofx_ctx *ctx, const double *u, const double *halfspaces, const uint8_t *flags, double *kappa, uint8_t *valid )
+  {
+    if( !ctx || !u || !halfspaces || !flags || !kappa )
+      return fail( VOFX_ERR_ARGUMENT, "null argument" );
+    int rc = setDevice( ctx );
+    rc = rc ? rc : launchResetCounters( ctx );
+    rc = rc ? rc : launchCompactFlags( ctx, flags );
+    rc = rc ? rc : launchCurvature( ctx, u, halfspaces, flags, kappa, valid );
+    if( rc )
+      return rc;
+    StepState s;
+    return readState( ctx, s );
+  }
+
+  // ---- fused time loop ---------------------------------------------------------------------------------------------------
+
+  int vofx_step_begin ( vofx_ctx *ctx, double time, double dt )
+  {
+    if( !ctx )
+      return fail( VOFX_ERR_ARGUMENT, "null context" );
+    int rc = setDevice( ctx );
+    if( rc )
+      return rc;
+    StepState init;
+    std::memset( &init, 0, sizeof( init ) );
+    init.time = time;
+    init.dt = dt;
+    init.dtEst = DBL_MAX;
+    VOFX_CUDA( cudaMemcpyAsync( ctx->state, &init, sizeof( init ), cudaMemcpyHostToDevice, ctx->stream ) );
+    VOFX_CUDA( cudaStreamSynchronize( ctx->stream ) );
+    return VOFX_OK;
+  }
+
+  int vofx_step_local ( vofx_ctx *ctx, const vofx_step_params *p, double *u, uint8_t *flags, double *halfspaces, double *kappa )
+  {
+    if( !ctx || !p || !u || !flags || !halfspaces || ( p->with_curvature && !kappa ) )
+      return fail( VOFX_ERR_ARGUMENT, "null argument" );
+    int rc = setDevice( ctx );
+    rc = rc ? rc : requireVelocity( ctx );
+    // algorithm.hh:75-83: flagOperator, reconstructionOperator, evolutionOperator, uh.axpy( 1.0, update )
+    rc = rc ? rc : launchFlag( ctx, u, p->eps, flags, true );
+    rc = rc ? rc : launchReconstruct( ctx, p->reconstruction, u, flags, halfspaces, p->max_iterations );
+    if( !rc && p->with_curvature )
+      rc = launchCurvature( ctx, u, halfspaces, flags, kappa, nullptr );
+    rc = rc ? rc : launchFlux( ctx, halfspaces, flags, nullptr, nullptr );
+    rc = rc ? rc : launchUpdate( ctx, flags, u, true );
+    return rc;
+  }
+
+  int vofx_step_finish ( vofx_ctx *ctx, const vofx_step_params *p )
+  {
+    if( !ctx || !p )
+      return fail( VOFX_ERR_ARGUMENT, "null argument" );
+    int rc = setDevice( ctx );
+    if( rc )
+      return rc;
+    k_finalize<<< 1, 1, 0, ctx->stream >>>( ctx->state, p->cfl );
+    return checkLaunch( ctx, "k_finalize" );
+  }
+
+  int vofx_step ( vofx_ctx *ctx, const vofx_step_params *p, double *u, uint8_t *flags, double *halfspaces, double *kappa )
+  {
+    int rc = vofx_step_local( ctx, p, u, flags, halfspaces, kappa );
+    return rc ? rc : vofx_step_finish( ctx, p );
+  }
+
+  double *vofx_dt_est_device ( vofx_ctx *ctx ) { return ctx ? &ctx->state->dtEst : nullptr; }
+
+  int vofx_step_state ( vofx_ctx *ctx, double *time, double *dt, double *dt_est, int64_t *mixed_cells )
+  {
+    if( !ctx )
+      return fail( VOFX_ERR_ARGUMENT, "null context" );
+    int rc = setDevice( ctx );
+    if( rc )
+      return rc;
+    StepState s;
+    rc = readState( ctx, s );
+    if( time )
+      *time = s.time;
+    if( dt )
+      *dt = s.dt;
+    if( dt_est )
+      *dt_est = s.dtEstLast;
+    if( mixed_cells )
+      *mixed_cells = s.mixedCountLast;
+    return rc;
+  }
+
+  // ---- host-buffer variants ---------------------------------------------------------------------------------------------
+
+  static int stageIn ( vofx_ctx *ctx, void *dev, const void *host, size_t bytes )
+  {
+    int rc = ensurePinned( ctx, bytes );
+    if( rc )
+      return rc;
+    std::memcpy( ctx->pinned, host, bytes );
+    VOFX_CUDA( cudaMemcpyAsync( dev, ctx->pinned, bytes, cudaMemcpyHostToDevice, ctx->stream ) );
+    VOFX_CUDA( cudaStreamSynchronize( ctx->stream ) );
+    return VOFX_OK;
+  }
+
+  static int stageOut ( vofx_ctx *ctx, void *host, const void *dev, size_t bytes )
+  {
+    int rc = ensurePinned( ctx, bytes );
+    if( rc )
+      return rc;
+    VOFX_CUDA( cudaMemcpyAsync( ctx->pinned, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream ) );
+    VOFX_CUDA( cudaStreamSynchronize( ctx->stream ) );
+    std::memcpy( host, ctx->pinned, bytes );
+    return VOFX_OK;
+  }
+
+  static int ensureMirrors ( vofx_ctx *ctx )
+  {
+    const size_t N = (size_t) ctx->grid.cells;
+    int rc = setDevice( ctx );
+    rc = rc ? rc : ensureDevice( ctx->dU, N );
+    rc = rc ? rc : ensureDevice( ctx->dFlags, N );
+    rc = rc ? rc : ensureDevice( ctx->dHs, N * ( ctx->desc.dim + 1 ) );
+    return rc;
+  }
+
+  int vofx_flag_host ( vofx_ctx *ctx, const double *u, double eps, uint8_t *flags )
+  {
+    if( !ctx || !u || !flags )
+      return fail( VOFX_ERR_ARGUMENT, "null argument" );
+    const size_t N = (size_t) ctx->grid.cells;
+    int rc = ensureMirrors( ctx );
+    rc = rc ? rc : stageIn( ctx, ctx->dU, u, N * sizeof( double ) );
+    rc = rc ? rc : vofx_flag( ctx, ctx->dU, eps, ctx->dFlags );
+    return rc ? rc : stageOut( ctx, flags, ctx->dFlags, N );
+  }
+
+  int vofx_reconstruct_host ( vofx_ctx *ctx, int kind, const double *u, const uint8_t *flags, double *halfspaces, int max_iterations )
+  {
+    if( !ctx || !u || !flags || !halfspaces )
+      return fail( VOFX_ERR_ARGUMENT, "null argument" );
+    const size_t N = (size_t) ctx->grid.cells;
+    int rc = ensureMirrors( ctx );
+    rc = rc ? rc : stageIn( ctx, ctx->dU, u, N * sizeof( double ) );
+    rc = rc ? rc : stageIn( ctx, ctx->dFlags, flags, N );
+    rc = rc ? rc : vofx_reconstruct( ctx, kind, ctx->dU, ctx->dFlags, ctx->dHs, max_iterations );
+    return rc ? rc : stageOut( ctx, halfspaces, ctx->dHs, N * ( ctx->desc.dim + 1 ) * sizeof( double ) );
+  }
+
+  int vofx_evolve_host ( vofx_ctx *ctx, const double *halfspaces, const uint8_t *flags, double time, double dt, double *update, double *dt_est )
+  {
+    if( !ctx || !halfspaces || !flags || !update || !dt_est )
+      return fail( VOFX_ERR_ARGUMENT, "null argument" );
+    const size_t N = (size_t) ctx->grid.cells;
+    int rc = ensureMirrors( ctx );
+    rc = rc ? rc : ensureDevice( ctx->dUpd, N );
+    rc = rc ? rc : stageIn( ctx, ctx->dHs, halfspaces, N * ( ctx->desc.dim + 1 ) * sizeof( double ) );
+    rc = rc ? rc : stageIn( ctx, ctx->dFlags, flags, N );
+    rc = rc ? rc : vofx_evolve( ctx, ctx->dHs, ctx->dFlags, time, dt, ctx->dUpd, dt_est );
+    return rc ? rc : stageOut( ctx, update, ctx->dUpd, N * sizeof( double ) );
+  }
+
+  int vofx_curvature_host ( vofx_ctx *ctx, const double *u, const double *halfspaces, const uint8_t *flags, double *kappa, uint8_t *valid )
+  {
+    if( !ctx || !u || !halfspaces || !flags || !kappa )
+      return fail( VOFX_ERR_ARGUMENT, "null argument" );
+    const size_t N = (size_t) ctx->grid.cells;
+    int rc = ensureMirrors( ctx );
+    rc = rc ? rc : ensureDevice( ctx->dKappa, N );
+    rc = rc ? rc : ensureDevice( ctx->dValid, N );
+    rc = rc ? rc : stageIn( ctx, ctx->dU, u, N * sizeof( double ) );
+    rc = rc ? rc : stageIn( ctx, ctx->dHs, halfspaces, N * ( ctx->desc.dim + 1 ) * sizeof( double ) );
+    rc = rc ? rc : stageIn( ctx, ctx->dFlags, flags, N );
+    rc = rc ? rc : vofx_curvature( ctx, ctx->dU, ctx->dHs, ctx->dFlags, ctx->dKappa, ctx->dValid );
+    rc = rc ? rc : stageOut( ctx, kappa, ctx->dKappa, N * sizeof( double ) );
+    if( !rc && valid )
+      rc = stageOut( ctx, valid, ctx->dValid, N );
+    return rc;
+  }
+
+  int vofx_step_host ( vofx_ctx *ctx, const vofx_step_params *p, double *u, uint8_t *flags )
+  {
+    if( !ctx || !p || !u )
+      return fail( VOFX_ERR_ARGUMENT, "null argument" );
+    const size_t N = (size_t) ctx->grid.cells;
+    int rc = ensureMirrors( ctx );
+    if( !rc && p->with_curvature )
+      rc = ensureDevice( ctx->dKappa, N );
+    // u may be caller-pinned memory: copy directly, no staging copy
+    if( rc )
+      return rc;
+    VOFX_CUDA( cudaMemcpyAsync( ctx->dU, u, N * sizeof( double ), cudaMemcpyHostToDevice, ctx->stream ) );
+    rc = vofx_step( ctx, p, ctx->dU, ctx->dFlags, ctx->dHs, ctx->dKappa );
+    if( rc )
+      return rc;
+    VOFX_CUDA( cudaMemcpyAsync( u, ctx->dU, N * sizeof( double ), cudaMemcpyDeviceToHost, ctx->stream ) );
+    if( flags )
+      VOFX_CUDA( cudaMemcpyAsync( flags, ctx->dFlags, N, cudaMemcpyDeviceToHost, ctx->stream ) );
+    VOFX_CUDA( cudaStreamSynchronize( ctx->stream ) );
+    return VOFX_OK;
+  }
+
+  // ---- initial data -------------------------------------------------------------------------------------------------------
+
+  int vofx_init ( vofx_ctx *ctx, int problem, double time, double *u )
+  {
+    if( !ctx || !u )
+      return fail( VOFX_ERR_ARGUMENT, "null argument" );
+    int rc = setDevice( ctx );
+    if( rc )
+      return rc;
+    const int dim = ctx->desc.dim;
+    Indicator I;
+    std::memset( &I, 0, sizeof( I ) );
+    I.dim = dim;
+    switch( problem )
+    {
+    case VOFX_PROB_ROTATING_CIRCLE:
+      if( dim != 3 )
+        return fail( VOFX_ERR_ARGUMENT, "the 2D RotatingCircle is initialised by the exact circle average on the host (test/average.hh:82-101)" );
+      {
+        // rotatingcircle.hh:81-90
+        double c[ 3 ] = { 0.5, 0.5, 0.5 };
+        const double a[ 3 ] = { 0.0, 0.25, 0.0 }, b[ 3 ] = { 0.25, 0.0, 0.0 }, z[ 3 ] = { 0.0, 0.0, 0.0 };
+        const double cs = std::cos( ( 2 * M_PI / 10 ) * time ), sn = std::sin( ( 2 * M_PI / 10 ) * time ), msn = -std::sin( ( 2 * M_PI / 10 ) * time );
+        for( int k = 0; k < 3; ++k )
+        {
+          c[ k ] += cs * a[ k ];
+          c[ k ] += sn * b[ k ];
+          c[ k ] += msn * z[ k ];
+          I.c[ k ] = c[ k ];
+        }
+        I.kind = 0;
+        I.r = 0.15;
+      }
+      break;
+    case VOFX_PROB_SFLOW:
+      I.kind = 1;
+      I.c[ 0 ] = I.c[ 1 ] = I.c[ 2 ] = 0.5;
+      I.r = 0.25;
+      break;
+    case VOFX_PROB_SLOTTED_CYLINDER:
+      if( dim != 2 )
+        return fail( VOFX_ERR_ARGUMENT, "SlottedCylinder is a 2D problem" );
+      I.kind = 2;
+      I.cs = std::cos( ( 2.0 * M_PI / 10.0 ) * time );
+      I.sn = std::sin( ( 2.0 * M_PI / 10.0 ) * time );
+      break;
+    case VOFX_PROB_LINEAR_WALL:
+      I.kind = 3;
+      I.c[ 0 ] = 0.3 + time * 0.02;
+      break;
+    case VOFX_PROB_LEVEQUE:
+      I.kind = 0;
+      I.r = 0.15;
+      if( dim == 2 )
+      {
+        I.c[ 0 ] = 0.5;
+        I.c[ 1 ] = 0.75;
+      }
+      else
+        I.c[ 0 ] = I.c[ 1 ] = I.c[ 2 ] = 0.35;
+      break;
+    default:
+      return fail( VOFX_ERR_ARGUMENT, "unknown built-in problem" );
+    }
+    const int blocks = gridBlocks( ctx, ctx->grid.cells, 128, 16 );
+    if( dim == 2 )
+      k_init< 2 ><<< blocks, 128, 0, ctx->stream >>>( ctx->grid, I, u );
+    else
+      k_init< 3 ><<< blocks, 128, 0, ctx->stream >>>( ctx->grid, I, u );
+    return checkLaunch( ctx, "k_init" );
+  }
+
+  // ---- primitives (tests) ----------------------------------------------------------------------------------------------------
+
+  namespace
+  {
+    struct DevBuf
+    {
+      void *p = nullptr;
+      ~DevBuf () { cudaFree( p ); }
+      int alloc ( size_t bytes )
+      {
+        VOFX_CUDA( cudaMalloc( &p, bytes ? bytes : 1 ) );
+        return VOFX_OK;
+      }
+      int upload ( const void *src, size_t bytes )
+      {
+        int rc = alloc( bytes );
+        if( rc )
+          return rc;
+        VOFX_CUDA( cudaMemcpy( p, src, bytes, cudaMemcpyHostToDevice ) );
+        return VOFX_OK;
+      }
+    };
+
+    int requireDevice ()
+    {
+      int count = 0;
+      if( cudaGetDeviceCount( &count ) != cudaSuccess || count == 0 )
+        return fail( VOFX_ERR_CUDA, "no CUDA device: vofx has no CPU fallback" );
+      return VOFX_OK;
+    }
+  } // namespace
+
+  int vofx_test_locate ( int dim, int64_t count, const double *lo, const double *h, const double *normal, const double *fraction, double *halfspaces )
+  {
+    if( ( dim != 2 && dim != 3 ) || count < 0 || !lo || !h || !normal || !fraction || !halfspaces )
+      return fail( VOFX_ERR_ARGUMENT, "bad argument" );
+    int rc = requireDevice();
+    if( rc )
+      return rc;
+    DevBuf dLo, dH, dN, dF, dOut;
+    const size_t n = (size_t) count;
+    rc = dLo.upload( lo, n * dim * 8 );
+    rc = rc ? rc : dH.upload( h, n * dim * 8 );
+    rc = rc ? rc : dN.upload( normal, n * dim * 8 );
+    rc = rc ? rc : dF.upload( fraction, n * 8 );
+    rc = rc ? rc : dOut.alloc( n * ( dim + 1 ) * 8 );
+    if( rc )
+      return rc;
+    const int blocks = (int) ( ( n + 63 ) / 64 ) > 0 ? (int) ( ( n + 63 ) / 64 ) : 1;
+    if( dim == 2 )
+      k_test_locate< 2 ><<< blocks, 64 >>>( count, (double *) dLo.p, (double *) dH.p, (double *) dN.p, (double *) dF.p, (double *) dOut.p );
+    else
+      k_test_locate< 3 ><<< blocks, 64 >>>( count, (double *) dLo.p, (double *) dH.p, (double *) dN.p, (double *) dF.p, (double *) dOut.p );
+    VOFX_CUDA( cudaGetLastError() );
+    VOFX_CUDA( cudaMemcpy( halfspaces, dOut.p, n * ( dim + 1 ) * 8, cudaMemcpyDeviceToHost ) );
+    return VOFX_OK;
+  }
+
+  int vofx_test_flux ( int dim, int64_t count, const double *lo, const double *h, const int32_t *face, const double *v, const double *halfspaces, double *flux )
+  {
+    if( ( dim != 2 && dim != 3 ) || count < 0 || !lo || !h || !face || !v || !halfspaces || !flux )
+      return fail( VOFX_ERR_ARGUMENT, "bad argument" );
+    int rc = requireDevice();
+    if( rc )
+      return rc;
+    DevBuf dLo, dH, dFace, dV, dHs, dOut;
+    const size_t n = (size_t) count;
+    rc = dLo.upload( lo, n * dim * 8 );
+    rc = rc ? rc : dH.upload( h, n * dim * 8 );
+    rc = rc ? rc : dFace.upload( face, n * 4 );
+    rc = rc ? rc : dV.upload( v, n * dim * 8 );
+    rc = rc ? rc : dHs.upload( halfspaces, n * ( dim + 1 ) * 8 );
+    rc = rc ? rc : dOut.alloc( n * 8 );
+    if( rc )
+      return rc;
+    const int blocks = (int) ( ( n + 63 ) / 64 ) > 0 ? (int) ( ( n + 63 ) / 64 ) : 1;
+    if( dim == 2 )
+      k_test_flux< 2 ><<< blocks, 64 >>>( count, (double *) dLo.p, (double *) dH.p, (int *) dFace.p, (double *) dV.p, (double *) dHs.p, (double *) dOut.p );
+    else
+      k_test_flux< 3 ><<< blocks, 64 >>>( count, (double *) dLo.p, (double *) dH.p, (int *) dFace.p, (double *) dV.p, (double *) dHs.p, (double *) dOut.p );
+    VOFX_CUDA( cudaGetLastError() );
+    VOFX_CUDA( cudaMemcpy( flux, dOut.p, n * 8, cudaMemcpyDeviceToHost ) );
+    return VOFX_OK;
+  }
+
+  int vofx_test_interface ( int dim, int64_t count, const double *lo, const double *h, const double *halfspaces, int32_t *nverts, double *centroid, double *measure )
+  {
+    if( ( dim != 2 && dim != 3 ) || count < 0 || !lo || !h || !halfspaces || !nverts || !centroid || !measure )
+      return fail( VOFX_ERR_ARGUMENT, "bad argument" );
+    int rc = requireDevice();
+    if( rc )
+      return rc;
+    DevBuf dLo, dH, dHs, dNv, dCen, dMeas;
+    const size_t n = (size_t) count;
+    rc = dLo.upload( lo, n * dim * 8 );
+    rc = rc ? rc : dH.upload( h, n * dim * 8 );
+    rc = rc ? rc : dHs.upload( halfspaces, n * ( dim + 1 ) * 8 );
+    rc = rc ? rc : dNv.alloc( n * 4 );
+    rc = rc ? rc : dCen.alloc( n * dim * 8 );
+    rc = rc ? rc : dMeas.alloc( n * 8 );
+    if( rc )
+      return rc;
+    const int blocks = (int) ( ( n + 63 ) / 64 ) > 0 ? (int) ( ( n + 63 ) / 64 ) : 1;
+    if( dim == 2 )
+      k_test_interface< 2 ><<< blocks, 64 >>>( count, (double *) dLo.p, (double *) dH.p, (double *) dHs.p, (int *) dNv.p, (double *) dCen.p, (double *) dMeas.p );
+    else
+      k_test_interface< 3 ><<< blocks, 64 >>>( count, (double *) dLo.p, (double *) dH.p, (double *) dHs.p, (int *) dNv.p, (double *) dCen.p, (double *) dMeas.p );
+    VOFX_CUDA( cudaGetLastError() );
+    VOFX_CUDA( cudaMemcpy( nverts, dNv.p, n * 4, cudaMemcpyDeviceToHost ) );
+    VOFX_CUDA( cudaMemcpy( centroid, dCen.p, n * dim * 8, cudaMemcpyDeviceToHost ) );
+    VOFX_CUDA( cudaMemcpy( measure, dMeas.p, n * 8, cudaMemcpyDeviceToHost ) );
+    return VOFX_OK;
+  }
+
+} // extern "C"

@@ -1,0 +1,211 @@
+// vofx 2D geometry device functions: polygon clip, plane-constant solve, swept-face flux, interface segment.
+// Restates (operation for operation, see vofx_math.cuh) dune/vof/geometry/2d/{polygon,intersect,upwindpolygon}.hh
+// and the Polygon overload of locateHalfSpace (geometry/algorithm.hh:68-111) for axis-aligned cells, with
+// fixed-size register arrays instead of std::vector.
+#pragma once
+
+#include "vofx_math.cuh"
+
+namespace vofx
+{
+
+  // a convex polygon with at most 8 vertices (a clipped quadrilateral has at most 5)
+  struct Poly2
+  {
+    int n;
+    double x[ 8 ], y[ 8 ];
+  };
+
+  // half-space in 2D: (nx, ny, d), fluid side nx*x + ny*y + d > 0; valid iff |n|^2 > 0.5 (geometry/halfspace.hh:104-107)
+  struct Hs2
+  {
+    double nx, ny, d;
+  };
+
+  VOFX_INLINE bool hs_valid ( const Hs2 &h ) { return dot2( h.nx, h.ny, h.nx, h.ny ) > 0.5; }
+  VOFX_INLINE double level_set ( const Hs2 &h, double x, double y ) { return dot2( h.nx, h.ny, x, y ) + h.d; }
+
+  // signed area, 2d/polygon.hh:99-106
+  VOFX_HD inline double poly_volume ( const Poly2 &p )
+  {
+    double sum = 0.0;
+    const int n = p.n;
+    for( int i = 0; i < n; ++i )
+    {
+      const int j = ( i + 1 == n ) ? 0 : i + 1;
+      sum += ( p.y[ i ] + p.y[ j ] ) * ( p.x[ i ] - p.x[ j ] );
+    }
+    return sum / 2.0;
+  }
+
+  // Sutherland-Hodgman against one half-space, 2d/intersect.hh:67-99: inside iff levelSet > 0 (strict),
+  // cut point = (-l1/(l0-l1))*v0 + (l0/(l0-l1))*v1 accumulated from zero
+  VOFX_HD inline void poly_clip ( const Poly2 &p, const Hs2 &hs, Poly2 &out )
+  {
+    out.n = 0;
+    if( !hs_valid( hs ) )
+      return;
+    const int n = p.n;
+    for( int i = 0; i < n; ++i )
+    {
+      const int j = ( i + 1 == n ) ? 0 : i + 1;
+      const double l0 = level_set( hs, p.x[ i ], p.y[ i ] );
+      const double l1 = level_set( hs, p.x[ j ], p.y[ j ] );
+      if( l0 > 0.0 )
+      {
+        out.x[ out.n ] = p.x[ i ];
+        out.y[ out.n ] = p.y[ i ];
+        out.n++;
+      }
+      if( ( l0 > 0.0 ) != ( l1 > 0.0 ) )
+      {
+        const double a = -l1 / ( l0 - l1 );
+        const double b = l0 / ( l0 - l1 );
+        double cx = 0.0, cy = 0.0;
+        cx += a * p.x[ i ]; cx += b * p.x[ j ];
+        cy += a * p.y[ i ]; cy += b * p.y[ j ];
+        out.x[ out.n ] = cx;
+        out.y[ out.n ] = cy;
+        out.n++;
+      }
+    }
+  }
+
+  // getVolumeFraction, geometry/algorithm.hh:31-37
+  VOFX_HD inline double volume_fraction ( const Poly2 &p, const Hs2 &hs )
+  {
+    Poly2 c;
+    poly_clip( p, hs, c );
+    return poly_volume( c ) / poly_volume( p );
+  }
+
+  // makePolygon of a quadrilateral cell, 2d/polygon.hh:230-241: corners 0,1,3,2; upper corner = lower + h
+  VOFX_HD inline void make_cell ( double lox, double loy, double hx, double hy, Poly2 &p )
+  {
+    const double x1 = lox + hx, y1 = loy + hy;
+    p.n = 4;
+    p.x[ 0 ] = lox; p.y[ 0 ] = loy;
+    p.x[ 1 ] = x1;  p.y[ 1 ] = loy;
+    p.x[ 2 ] = x1;  p.y[ 2 ] = y1;
+    p.x[ 3 ] = lox; p.y[ 3 ] = y1;
+  }
+
+  struct VfResidual2
+  {
+    const Poly2 *p;
+    double nx, ny, fraction;
+    VOFX_HD double operator() ( double dist ) const
+    {
+      const Hs2 hs = { nx, ny, dist };
+      return volume_fraction( *p, hs ) - fraction;
+    }
+  };
+
+  // locateHalfSpace( Polygon, normal, fraction ), geometry/algorithm.hh:68-111: bracket by the planes through the
+  // vertices, degenerate returns, else Brent on the plane constant with absolute tolerance 1e-12
+  VOFX_HD inline double locate ( const Poly2 &polygon, double nx, double ny, double fraction )
+  {
+    double pMin = 0.0, pMax = 0.0;
+    double volMin = -DBL_MAX, volMax = DBL_MAX;
+    for( int i = 0; i < polygon.n; ++i )
+    {
+      const double dist = -( dot2( nx, ny, polygon.x[ i ], polygon.y[ i ] ) );
+      const Hs2 hs = { nx, ny, dist };
+      const double volume = volume_fraction( polygon, hs );
+      if( ( volume <= volMax ) && ( volume >= fraction ) )
+      {
+        pMax = dist;
+        volMax = volume;
+      }
+      if( ( volume >= volMin ) && ( volume <= fraction ) )
+      {
+        pMin = dist;
+        volMin = volume;
+      }
+    }
+    if( volMax == DBL_MAX )
+      return pMin;
+    if( volMin == -DBL_MAX )
+      return pMax;
+    if( volMin == volMax )
+      return pMin;
+    const VfResidual2 f = { &polygon, nx, ny, fraction };
+    return brent( f, pMin, pMax, 1e-12 );
+  }
+
+  // truncVolume( upwindPolygon2d( face, v ), hs ): 2d/upwindpolygon.hh:24-30, geometry/upwindpolygon.hh:58-62.
+  // face = 2*axis+side of the cell with lower corner (lox,loy); the face's corners are its lower corner and
+  // that corner + h along the spanned axis; the swept region is the face translated by -v.
+  VOFX_HD inline double flux ( double lox, double loy, double hx, double hy, int face, double vx, double vy, const Hs2 &hs )
+  {
+    const int axis = face >> 1;
+    double c0x = lox, c0y = loy;
+    if( face & 1 )
+    {
+      if( axis == 0 ) c0x += hx; else c0y += hy;
+    }
+    double c1x = c0x, c1y = c0y;
+    if( axis == 0 ) c1y += hy; else c1x += hx;
+    const double dx = c1x - c0x, dy = c1y - c0y;
+    Poly2 up, cl;
+    up.n = 4;
+    if( dot2( -dy, dx, vx, vy ) < 0.0 )   // generalizedCrossProduct( c1 - c0 ) * v, geometry/utility.hh:82-85
+    {
+      up.x[ 0 ] = c0x; up.y[ 0 ] = c0y;
+      up.x[ 1 ] = c1x; up.y[ 1 ] = c1y;
+      up.x[ 2 ] = c1x - vx; up.y[ 2 ] = c1y - vy;
+      up.x[ 3 ] = c0x - vx; up.y[ 3 ] = c0y - vy;
+    }
+    else
+    {
+      up.x[ 0 ] = c1x; up.y[ 0 ] = c1y;
+      up.x[ 1 ] = c0x; up.y[ 1 ] = c0y;
+      up.x[ 2 ] = c0x - vx; up.y[ 2 ] = c0y - vy;
+      up.x[ 3 ] = c1x - vx; up.y[ 3 ] = c1y - vy;
+    }
+    poly_clip( up, hs, cl );
+    return poly_volume( cl );
+  }
+
+  // intersect( Polygon, HyperPlane ) -> Line, 2d/intersect.hh:110-148.  Returns false (and a zero line) if empty.
+  VOFX_HD inline bool plane_cut ( const Poly2 &p, const Hs2 &hs, double lx[ 2 ], double ly[ 2 ] )
+  {
+    lx[ 0 ] = lx[ 1 ] = ly[ 0 ] = ly[ 1 ] = 0.0;
+    if( !hs_valid( hs ) )
+      return false;
+    int j = 0;
+    const int n = p.n;
+    for( int i = 0; i < n; ++i )
+    {
+      if( j == 2 )
+        break;
+      const int k = ( i + 1 == n ) ? 0 : i + 1;
+      const double l0 = level_set( hs, p.x[ i ], p.y[ i ] );
+      const double l1 = level_set( hs, p.x[ k ], p.y[ k ] );
+      if( ( l0 > 0.0 && l1 < 0.0 ) || ( l0 < 0.0 && l1 > 0.0 ) )
+      {
+        const double a = -l1 / ( l0 - l1 );
+        const double b = l0 / ( l0 - l1 );
+        double cx = 0.0, cy = 0.0;
+        cx += a * p.x[ i ]; cx += b * p.x[ k ];
+        cy += a * p.y[ i ]; cy += b * p.y[ k ];
+        lx[ j ] = cx; ly[ j ] = cy;
+        j++;
+      }
+      else if( fabs( l0 ) < kEps )
+      {
+        lx[ j ] = p.x[ i ]; ly[ j ] = p.y[ i ];
+        j++;
+      }
+    }
+    if( j == 0 )
+      return false;
+    if( j == 1 )
+    {
+      lx[ 1 ] = lx[ 0 ];
+      ly[ 1 ] = ly[ 0 ];
+    }
+    return true;
+  }
+
+} // namespace vofx

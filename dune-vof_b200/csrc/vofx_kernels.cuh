@@ -1,0 +1,1366 @@
+// vofx: CUDA kernels of the per-timestep VoF hot path (sm_100a).
+//
+// Step structure (DESIGN.md "Kernels"):
+//   k_flag_compact   dense, HBM-bound: u -> flags (1 B/cell) + compacted list of mixed cells         (F1)
+//   k_youngs         band: least-squares normal + plane-constant solve per mixed cell                 (R1, G1/G2)
+//   k_hf / k_swartz  band: height-function / iterative Swartz normals on top of Young's                (R2, R3)
+//   k_flux           band: one lane per (mixed cell, face): face velocity, swept-box clip, flux record (E1, G5, G7)
+//   k_update         band: owner-computes gather of the flux records in the reference's summation order,
+//                    u += du in place (the dense update.clear()/axpy passes of the reference vanish)   (E1, U1)
+//   k_finalize       one thread: time += dt, dt = cfl * dtEst, reset counters                          (T1)
+// No tensor cores: nothing here is a contraction.  Arithmetic order follows the reference (vofx_math.cuh).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "vofx_geom2d.cuh"
+#include "vofx_geom3d.cuh"
+#include "vofx_grid.cuh"
+
+namespace vofx
+{
+
+  // device-resident loop state (Algorithm::operator() locals, algorithm.hh:61)
+  struct StepState
+  {
+    double time;
+    double dt;
+    double dtEst;               // running MIN of the current step (bits compared as unsigned: values are >= 0)
+    double dtEstLast;           // estimate of the last finished step
+    int mixedCount;             // entries in the mixed list
+    int mixedCountLast;
+    int overflow;               // mixed list capacity exceeded
+    int pad;
+  };
+
+  // per mixed cell: what it adds to its own update and to each face neighbour's update (Appendix C of SURVEY.md)
+  struct FluxRecord
+  {
+    double self[ 6 ];
+    double nb[ 6 ];
+    unsigned char selfMask, nbMask;
+    unsigned char pad[ 6 ];
+  };
+
+  // ------------------------------------------------------------------------------------------------------------
+  // F1: flags + compaction.  Each thread owns 4 consecutive cells (two 16-byte loads, one 4-byte flag store).
+  // ------------------------------------------------------------------------------------------------------------
+
+  template< int DIM >
+  __device__ __forceinline__ unsigned char flag_of ( const Grid &g, const double *__restrict__ u, double eps, double colorEn, const int *ijk )
+  {
+    // flagging.hh:46-64
+    if( colorEn < eps )
+      return 0;
+    if( colorEn <= ( 1 - eps ) )
+      return 1;
+    if( colorEn != colorEn )
+      return 99;
+    unsigned char flag = 3;
+#pragma unroll
+    for( int face = 0; face < 2 * DIM; ++face )
+    {
+      int nb[ 3 ] = { ijk[ 0 ], ijk[ 1 ], ijk[ 2 ] };
+      nb[ face >> 1 ] += ( face & 1 ) ? 1 : -1;
+      if( cell_exists( g, nb ) && __ldg( u + cell_index( g, nb ) ) < eps )
+      {
+        flag = 2;
+        break;
+      }
+    }
+    return flag;
+  }
+
+  template< int DIM >
+  __global__ void __launch_bounds__( 256 ) k_flag_compact ( Grid g, const double *__restrict__ u, double eps, unsigned char *__restrict__ flags,
+                                                             int *__restrict__ mixedList, int *__restrict__ slot, int capacity, StepState *state, int compact )
+  {
+    const long long nQuads = ( g.cells + 3 ) >> 2;
+    const int lane = threadIdx.x & 31;
+    for( long long q = blockIdx.x * (long long) blockDim.x + threadIdx.x; q < ( ( nQuads + 31 ) & ~31LL ); q += (long long) gridDim.x * blockDim.x )
+    {
+      const long long c0 = q << 2;
+      double uu[ 4 ] = { 0.0, 0.0, 0.0, 0.0 };
+      unsigned char ff[ 4 ] = { 0, 0, 0, 0 };
+      int nMixed = 0;
+      unsigned mixedBits = 0;
+      const bool full4 = ( q < nQuads ) && ( c0 + 3 < g.cells );
+      if( full4 )
+      {
+        const double2 a = __ldg( reinterpret_cast< const double2 * >( u + c0 ) );
+        const double2 b = __ldg( reinterpret_cast< const double2 * >( u + c0 + 2 ) );
+        uu[ 0 ] = a.x; uu[ 1 ] = a.y; uu[ 2 ] = b.x; uu[ 3 ] = b.y;
+      }
+      else if( q < nQuads )
+        for( int k = 0; k < 4; ++k )
+          if( c0 + k < g.cells )
+            uu[ k ] = u[ c0 + k ];
+
+      if( q < nQuads )
+      {
+        int ijk[ 3 ];
+        cell_ijk( g, c0, ijk );
+#pragma unroll
+        for( int k = 0; k < 4; ++k )
+        {
+          if( c0 + k < g.cells )
+          {
+            ff[ k ] = flag_of< DIM >( g, u, eps, uu[ k ], ijk );
+            const int la = ijk[ DIM - 1 ];
+            if( is_mixed( ff[ k ] ) && la >= g.list0 && la < g.list1 && in_domain( g, ijk ) )
+            {
+              mixedBits |= 1u << k;
+              nMixed++;
+            }
+          }
+          // advance the multi-index with carry
+          if( ++ijk[ 0 ] == g.ns[ 0 ] )
+          {
+            ijk[ 0 ] = 0;
+            if( ++ijk[ 1 ] == g.ns[ 1 ] )
+            {
+              ijk[ 1 ] = 0;
+              ++ijk[ 2 ];
+            }
+          }
+        }
+        if( full4 )
+          *reinterpret_cast< uchar4 * >( flags + c0 ) = make_uchar4( ff[ 0 ], ff[ 1 ], ff[ 2 ], ff[ 3 ] );
+        else
+          for( int k = 0; k < 4; ++k )
+            if( c0 + k < g.cells )
+              flags[ c0 + k ] = ff[ k ];
+      }
+
+      if( compact )
+      {
+        // warp-aggregated append: one atomic per warp that holds any mixed cell
+        int incl = nMixed;
+#pragma unroll
+        for( int o = 1; o < 32; o <<= 1 )
+        {
+          const int t = __shfl_up_sync( 0xffffffffu, incl, o );
+          if( lane >= o )
+            incl += t;
+        }
+        const int total = __shfl_sync( 0xffffffffu, incl, 31 );
+        if( total > 0 )
+        {
+          int base = 0;
+          if( lane == 31 )
+            base = atomicAdd( &state->mixedCount, total );
+          base = __shfl_sync( 0xffffffffu, base, 31 );
+          int pos = base + incl - nMixed;
+          for( int k = 0; k < 4; ++k )
+            if( mixedBits & ( 1u << k ) )
+            {
+              if( pos < capacity )
+              {
+                mixedList[ pos ] = int( c0 + k );
+                slot[ c0 + k ] = pos;
+              }
+              else
+                state->overflow = 1;
+              pos++;
+            }
+        }
+      }
+    }
+  }
+
+  // mixed list from given flags (operator-level API: the caller supplies the flags)
+  template< int DIM >
+  __global__ void __launch_bounds__( 256 ) k_compact_flags ( Grid g, const unsigned char *__restrict__ flags, int *__restrict__ mixedList,
+                                                              int *__restrict__ slot, int capacity, StepState *state )
+  {
+    const int lane = threadIdx.x & 31;
+    const long long nRound = ( g.cells + 31 ) & ~31LL;
+    for( long long c = blockIdx.x * (long long) blockDim.x + threadIdx.x; c < nRound; c += (long long) gridDim.x * blockDim.x )
+    {
+      bool m = false;
+      if( c < g.cells && is_mixed( flags[ c ] ) )
+      {
+        int ijk[ 3 ];
+        cell_ijk( g, c, ijk );
+        const int la = ijk[ DIM - 1 ];
+        m = la >= g.list0 && la < g.list1 && in_domain( g, ijk );
+      }
+      const unsigned ballot = __ballot_sync( 0xffffffffu, m );
+      if( ballot )
+      {
+        int base = 0;
+        if( lane == 0 )
+          base = atomicAdd( &state->mixedCount, __popc( ballot ) );
+        base = __shfl_sync( 0xffffffffu, base, 0 );
+        if( m )
+        {
+          const int pos = base + __popc( ballot & ( ( 1u << lane ) - 1 ) );
+          if( pos < capacity )
+          {
+            mixedList[ pos ] = int( c );
+            slot[ c ] = pos;
+          }
+          else
+            state->overflow = 1;
+        }
+      }
+    }
+  }
+
+  __device__ __forceinline__ int mixed_count ( const StepState *state, int capacity )
+  {
+    const int n = state->mixedCount;
+    return n < capacity ? n : capacity;
+  }
+
+  // ------------------------------------------------------------------------------------------------------------
+  // plane-constant solve for the cell ijk with a given unit normal: locateHalfSpace( makePolytope( geometry ), n, u )
+  // ------------------------------------------------------------------------------------------------------------
+
+  template< int DIM >
+  __device__ __forceinline__ double locate_cell ( const Grid &g, const int *ijk, const double *normal, double fraction )
+  {
+    if( DIM == 2 )
+    {
+      Poly2 p;
+      make_cell( cell_lower( g, 0, ijk[ 0 ] ), cell_lower( g, 1, ijk[ 1 ] ), g.h[ 0 ], g.h[ 1 ], p );
+      return locate( p, normal[ 0 ], normal[ 1 ], fraction );
+    }
+    const double lo[ 3 ] = { cell_lower( g, 0, ijk[ 0 ] ), cell_lower( g, 1, ijk[ 1 ] ), cell_lower( g, 2, ijk[ 2 ] ) };
+    Hex c;
+    make_cell( lo, g.h, c );
+    return locate( c, normal, fraction );
+  }
+
+  // ------------------------------------------------------------------------------------------------------------
+  // R1: modified Young's, reconstruction/modifiedyoungs.hh:90-134.  One thread per mixed cell.
+  // ------------------------------------------------------------------------------------------------------------
+
+  template< int DIM >
+  __device__ __forceinline__ void ls_accumulate ( double *d, double colorDiff, double AtA[ 3 ][ 3 ], double *Atb )
+  {
+    double n2 = 0.0;
+#pragma unroll
+    for( int k = 0; k < DIM; ++k )
+      n2 += d[ k ] * d[ k ];
+    const double weight = 1.0 / n2;
+#pragma unroll
+    for( int k = 0; k < DIM; ++k )
+      d[ k ] *= weight;
+#pragma unroll
+    for( int i = 0; i < DIM; ++i )
+#pragma unroll
+      for( int j = 0; j < DIM; ++j )
+      {
+        double m = 0.0;          // outerProduct: axpy onto a zero matrix, geometry/utility.hh:161-169
+        m += d[ i ] * d[ j ];
+        AtA[ i ][ j ] += m;
+      }
+    const double w = weight * colorDiff;
+#pragma unroll
+    for( int k = 0; k < DIM; ++k )
+      Atb[ k ] += w * d[ k ];
+  }
+
+  // FieldMatrix::solve closed forms (dune-common 2.6 densematrix.hh; third party, see DESIGN.md "parity unpinned")
+  template< int DIM >
+  __device__ __forceinline__ void solve_small ( const double M[ 3 ][ 3 ], const double *b, double *x )
+  {
+    if( DIM == 2 )
+    {
+      double detinv = M[ 0 ][ 0 ] * M[ 1 ][ 1 ] - M[ 0 ][ 1 ] * M[ 1 ][ 0 ];
+      detinv = 1.0 / detinv;
+      x[ 0 ] = detinv * ( M[ 1 ][ 1 ] * b[ 0 ] - M[ 0 ][ 1 ] * b[ 1 ] );
+      x[ 1 ] = detinv * ( M[ 0 ][ 0 ] * b[ 1 ] - M[ 1 ][ 0 ] * b[ 0 ] );
+      x[ 2 ] = 0.0;
+      return;
+    }
+    const double t4 = M[ 0 ][ 0 ] * M[ 1 ][ 1 ];
+    const double t6 = M[ 0 ][ 0 ] * M[ 1 ][ 2 ];
+    const double t8 = M[ 0 ][ 1 ] * M[ 1 ][ 0 ];
+    const double t10 = M[ 0 ][ 2 ] * M[ 1 ][ 0 ];
+    const double t12 = M[ 0 ][ 1 ] * M[ 2 ][ 0 ];
+    const double t14 = M[ 0 ][ 2 ] * M[ 2 ][ 0 ];
+    const double d = ( t4 * M[ 2 ][ 2 ] - t6 * M[ 2 ][ 1 ] - t8 * M[ 2 ][ 2 ] + t10 * M[ 2 ][ 1 ] + t12 * M[ 1 ][ 2 ] - t14 * M[ 1 ][ 1 ] );
+    x[ 0 ] = ( b[ 0 ] * M[ 1 ][ 1 ] * M[ 2 ][ 2 ] - b[ 0 ] * M[ 2 ][ 1 ] * M[ 1 ][ 2 ]
+               - b[ 1 ] * M[ 0 ][ 1 ] * M[ 2 ][ 2 ] + b[ 1 ] * M[ 2 ][ 1 ] * M[ 0 ][ 2 ]
+               + b[ 2 ] * M[ 0 ][ 1 ] * M[ 1 ][ 2 ] - b[ 2 ] * M[ 1 ][ 1 ] * M[ 0 ][ 2 ] ) / d;
+    x[ 1 ] = ( M[ 0 ][ 0 ] * b[ 1 ] * M[ 2 ][ 2 ] - M[ 0 ][ 0 ] * b[ 2 ] * M[ 1 ][ 2 ]
+               - M[ 1 ][ 0 ] * b[ 0 ] * M[ 2 ][ 2 ] + M[ 1 ][ 0 ] * b[ 2 ] * M[ 0 ][ 2 ]
+               + M[ 2 ][ 0 ] * b[ 0 ] * M[ 1 ][ 2 ] - M[ 2 ][ 0 ] * b[ 1 ] * M[ 0 ][ 2 ] ) / d;
+    x[ 2 ] = ( M[ 0 ][ 0 ] * M[ 1 ][ 1 ] * b[ 2 ] - M[ 0 ][ 0 ] * M[ 2 ][ 1 ] * b[ 1 ]
+               - M[ 1 ][ 0 ] * M[ 0 ][ 1 ] * b[ 2 ] + M[ 1 ][ 0 ] * M[ 2 ][ 1 ] * b[ 0 ]
+               + M[ 2 ][ 0 ] * M[ 0 ][ 1 ] * b[ 1 ] - M[ 2 ][ 0 ] * M[ 1 ][ 1 ] * b[ 0 ] ) / d;
+  }
+
+  // returns false if the normal degenerates (the reconstruction stays the zero half-space, :128-129)
+  template< int DIM >
+  __device__ bool youngs_normal ( const Grid &g, const double *__restrict__ u, const int *ijk, double colorEn, double *normal )
+  {
+    double center[ 3 ] = { 0.0, 0.0, 0.0 }, lower[ 3 ] = { 0.0, 0.0, 0.0 };
+#pragma unroll
+    for( int d = 0; d < DIM; ++d )
+    {
+      lower[ d ] = cell_lower( g, d, ijk[ d ] );
+      center[ d ] = lower[ d ] + 0.5 * g.h[ d ];
+    }
+    double AtA[ 3 ][ 3 ] = { { 0.0, 0.0, 0.0 }, { 0.0, 0.0, 0.0 }, { 0.0, 0.0, 0.0 } };
+    double Atb[ 3 ] = { 0.0, 0.0, 0.0 };
+
+    // vertex-neighbour stencil in ascending cell index, self excluded (stencil/vertexneighborsstencil.hh:52-94)
+    for( int dz = ( DIM == 3 ? -1 : 0 ); dz <= ( DIM == 3 ? 1 : 0 ); ++dz )
+      for( int dy = -1; dy <= 1; ++dy )
+        for( int dx = -1; dx <= 1; ++dx )
+        {
+          if( dx == 0 && dy == 0 && dz == 0 )
+            continue;
+          const int nb[ 3 ] = { ijk[ 0 ] + dx, ijk[ 1 ] + dy, ijk[ 2 ] + dz };
+          if( !cell_exists( g, nb ) )
+            continue;
+          const double colorNb = clamp01( __ldg( u + cell_index( g, nb ) ) );
+          double d[ 3 ];
+#pragma unroll
+          for( int k = 0; k < DIM; ++k )
+            d[ k ] = ( cell_lower( g, k, nb[ k ] ) + 0.5 * g.h[ k ] ) - center[ k ];
+          ls_accumulate< DIM >( d, colorNb - colorEn, AtA, Atb );
+        }
+
+    // domain-boundary faces get a ghost with colour 0.5 at twice the face-centre distance, :112-124
+    for( int face = 0; face < 2 * DIM; ++face )
+    {
+      int nb[ 3 ] = { ijk[ 0 ], ijk[ 1 ], ijk[ 2 ] };
+      nb[ face >> 1 ] += ( face & 1 ) ? 1 : -1;
+      if( in_domain( g, nb ) )
+        continue;
+      double d[ 3 ];
+#pragma unroll
+      for( int k = 0; k < DIM; ++k )
+      {
+        double fc = lower[ k ];
+        if( k == ( face >> 1 ) )
+        {
+          if( face & 1 )
+            fc += g.h[ k ];
+        }
+        else
+          fc += 0.5 * g.h[ k ];
+        d[ k ] = fc - center[ k ];
+        d[ k ] *= 2.0;
+      }
+      ls_accumulate< DIM >( d, 0.5 - colorEn, AtA, Atb );
+    }
+
+    normal[ 0 ] = normal[ 1 ] = normal[ 2 ] = 0.0;
+    solve_small< DIM >( AtA, Atb, normal );
+    double n2 = 0.0;
+#pragma unroll
+    for( int k = 0; k < DIM; ++k )
+      n2 += normal[ k ] * normal[ k ];
+    if( n2 < kEps )
+      return false;
+    const double nrm = sqrt( n2 );
+#pragma unroll
+    for( int k = 0; k < DIM; ++k )
+      normal[ k ] /= nrm;
+    return true;
+  }
+
+  template< int DIM >
+  __global__ void __launch_bounds__( 128 ) k_youngs ( Grid g, const double *__restrict__ u, const int *__restrict__ mixedList,
+                                                       const StepState *state, int capacity, double *__restrict__ hs )
+  {
+    const int count = mixed_count( state, capacity );
+    for( int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < count; idx += gridDim.x * blockDim.x )
+    {
+      const long long c = mixedList[ idx ];
+      int ijk[ 3 ];
+      cell_ijk( g, c, ijk );
+      const double colorEn = u[ c ];
+      double normal[ 3 ];
+      double *out = hs + c * ( DIM + 1 );
+      if( !youngs_normal< DIM >( g, u, ijk, colorEn, normal ) )
+      {
+#pragma unroll
+        for( int k = 0; k <= DIM; ++k )
+          out[ k ] = 0.0;
+        continue;
+      }
+      const double dist = locate_cell< DIM >( g, ijk, normal, colorEn );
+#pragma unroll
+      for( int k = 0; k < DIM; ++k )
+        out[ k ] = normal[ k ];
+      out[ DIM ] = dist;
+    }
+  }
+
+  // ------------------------------------------------------------------------------------------------------------
+  // S2 + R2: Cartesian height functions, stencil/heightfunctionstencil.hh:22-107, reconstruction/heightfunction.hh:101-259
+  // ------------------------------------------------------------------------------------------------------------
+
+  // getOrientation, heightfunction.hh:126-144
+  template< int DIM >
+  __device__ __forceinline__ void hf_orientation ( const double *normal, int &dir, int &sign )
+  {
+    dir = 0;
+    double max = DBL_MIN;
+#pragma unroll
+    for( int i = 0; i < DIM; ++i )
+      if( fabs( normal[ i ] ) > max )
+      {
+        dir = i;
+        max = fabs( normal[ i ] );
+      }
+    if( fabs( max - 1.0 / sqrt( 2.0 ) ) < 1e-3 )
+      dir = DIM - 1;
+    sign = ( normal[ dir ] > 0 ) ? -1 : 1;
+  }
+
+  // getMultiIndex in cell-index units, heightfunctionstencil.hh:69-100 (the reference works on SPGrid ids 2*i+1)
+  template< int DIM >
+  __device__ __forceinline__ void hf_offset ( int i, int j, int c, int t, int *m )
+  {
+    m[ 0 ] = m[ 1 ] = m[ 2 ] = 0;
+    if( DIM == 2 )
+    {
+      m[ 1 - i ] += ( c - 1 ) * ( i == 0 ? -1 : 1 );
+      m[ i ] += t;
+      m[ 0 ] *= j;
+      m[ 1 ] *= j;
+    }
+    else
+    {
+      m[ i ] += j * t;
+      m[ ( i + 1 ) % 3 ] += ( ( c % 3 ) - 1 ) * -j;
+      m[ ( i + 2 ) % 3 ] += ( ( c / 3 ) - 1 );
+    }
+  }
+
+  // the stencil cell (c,t) or -1 if it is outside (valid(), heightfunctionstencil.hh:63-66)
+  template< int DIM >
+  __device__ __forceinline__ long long hf_cell ( const Grid &g, const int *ijk, int i, int j, int c, int t )
+  {
+    int m[ 3 ];
+    hf_offset< DIM >( i, j, c, t, m );
+    const int nb[ 3 ] = { ijk[ 0 ] + m[ 0 ], ijk[ 1 ] + m[ 1 ], ijk[ 2 ] + m[ 2 ] };
+    return cell_exists( g, nb ) ? cell_index( g, nb ) : -1;
+  }
+
+  // getHeightValues, heightfunction.hh:147-196
+  template< int DIM >
+  __device__ void hf_heights ( const Grid &g, const double *__restrict__ u, const int *ijk, int i, int j, int tup, double *heights )
+  {
+    constexpr int noc = ( DIM == 2 ) ? 3 : 9;
+    const double TOL = 1e-10;
+    for( int c = 0; c < noc; ++c )
+    {
+      heights[ c ] = 0.0;
+      long long cell = hf_cell< DIM >( g, ijk, i, j, c, 0 );
+      if( cell < 0 )
+        continue;
+      const double u0 = clamp01( __ldg( u + cell ) );
+      heights[ c ] += u0;
+      double lastU = u0;
+      for( int t = 1; t <= tup; ++t )
+      {
+        cell = hf_cell< DIM >( g, ijk, i, j, c, t );
+        if( cell < 0 )
+          break;
+        const double uu = clamp01( __ldg( u + cell ) );
+        if( uu > lastU - TOL && !( uu > 1.0 - TOL ) )
+          break;
+        heights[ c ] += uu;
+        lastU = uu;
+      }
+      lastU = u0;
+      for( int t = -1; t >= -tup; --t )
+      {
+        cell = hf_cell< DIM >( g, ijk, i, j, c, t );
+        if( cell < 0 )
+          break;
+        double uu = clamp01( __ldg( u + cell ) );
+        if( uu < lastU + TOL && !( uu < TOL ) )
+          uu = 1.0;
+        heights[ c ] += uu;
+        lastU = uu;
+      }
+    }
+  }
+
+  // computeNormal, heightfunction.hh:200-226 (2D) / :229-259 (3D)
+  template< int DIM >
+  __device__ __forceinline__ void hf_normal ( const double *heights, int i, int j, double *n )
+  {
+    if( DIM == 2 )
+    {
+      double Hx;
+      if( fabs( heights[ 0 ] ) < kEps )
+        Hx = ( heights[ 2 ] - heights[ 1 ] );
+      else if( fabs( heights[ 2 ] ) < kEps )
+        Hx = ( heights[ 1 ] - heights[ 0 ] );
+      else
+        Hx = ( heights[ 2 ] - heights[ 0 ] ) / 2.0;
+      n[ 0 ] = Hx;
+      n[ 1 ] = -1.0;
+      n[ 2 ] = 0.0;
+      const double nrm = norm2( n[ 0 ], n[ 1 ] );
+      n[ 0 ] /= nrm;
+      n[ 1 ] /= nrm;
+      if( ( i == 0 && j == 1 ) || ( i == 1 && j == -1 ) )
+      {
+        n[ 0 ] *= -1.0;
+        n[ 1 ] *= -1.0;
+      }
+      if( i == 0 )
+      {
+        const double a = -n[ 1 ], b = n[ 0 ];
+        n[ 0 ] = a;
+        n[ 1 ] = b;
+      }
+      return;
+    }
+    double Hx, Hy;
+    if( heights[ 5 ] == 0.0 )
+      Hx = ( heights[ 4 ] - heights[ 3 ] );
+    else if( heights[ 3 ] == 0.0 )
+      Hx = ( heights[ 5 ] - heights[ 4 ] );
+    else
+      Hx = ( heights[ 5 ] - heights[ 3 ] ) / 2.0;
+    if( heights[ 7 ] == 0.0 )
+      Hy = ( heights[ 4 ] - heights[ 1 ] );
+    else if( heights[ 1 ] == 0.0 )
+      Hy = ( heights[ 7 ] - heights[ 4 ] );
+    else
+      Hy = ( heights[ 7 ] - heights[ 1 ] ) / 2.0;
+    n[ 0 ] = n[ 1 ] = n[ 2 ] = 0.0;
+    n[ i ] = -j;
+    n[ ( i + 1 ) % 3 ] = Hx * -j;
+    n[ ( i + 2 ) % 3 ] = Hy;
+    const double nrm = norm3( n );
+#pragma unroll
+    for( int k = 0; k < 3; ++k )
+      n[ k ] /= nrm;
+  }
+
+  // HeightFunctionReconstruction::applyLocal on top of the Young's planes already in hs, heightfunction.hh:101-123
+  template< int DIM >
+  __global__ void __launch_bounds__( 128 ) k_hf ( Grid g, const double *__restrict__ u, const int *__restrict__ mixedList,
+                                                   const StepState *state, int capacity, double *__restrict__ hs )
+  {
+    const int count = mixed_count( state, capacity );
+    for( int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < count; idx += gridDim.x * blockDim.x )
+    {
+      const long long c = mixedList[ idx ];
+      int ijk[ 3 ];
+      cell_ijk( g, c, ijk );
+      double *rec = hs + c * ( DIM + 1 );
+      double youngs[ 3 ] = { rec[ 0 ], rec[ 1 ], DIM == 3 ? rec[ 2 ] : 0.0 };
+      int dir, sign;
+      hf_orientation< DIM >( youngs, dir, sign );
+      double heights[ 9 ], newNormal[ 3 ];
+      hf_heights< DIM >( g, u, ijk, dir, sign, 3, heights );
+      hf_normal< DIM >( heights, dir, sign, newNormal );
+      const double dist = locate_cell< DIM >( g, ijk, newNormal, u[ c ] );
+#pragma unroll
+      for( int k = 0; k < DIM; ++k )
+        rec[ k ] = newNormal[ k ];
+      rec[ DIM ] = dist;
+    }
+  }
+
+  // ------------------------------------------------------------------------------------------------------------
+  // R3: modified Swartz, reconstruction/modifiedswartz.hh:102-243.  One thread per mixed cell; the neighbours'
+  // interface centroids depend only on (neighbour, oldNormal) and are computed once per iteration.
+  // ------------------------------------------------------------------------------------------------------------
+
+  template< int DIM >
+  __device__ void interface_centroid ( const Grid &g, const int *ijk, const double *normal, double color, double *centroid )
+  {
+    const double dist = locate_cell< DIM >( g, ijk, normal, color );
+    if( DIM == 2 )
+    {
+      Poly2 p;
+      make_cell( cell_lower( g, 0, ijk[ 0 ] ), cell_lower( g, 1, ijk[ 1 ] ), g.h[ 0 ], g.h[ 1 ], p );
+      const Hs2 H = { normal[ 0 ], normal[ 1 ], dist };
+      double lx[ 2 ], ly[ 2 ];
+      plane_cut( p, H, lx, ly );
+      centroid[ 0 ] = ( lx[ 0 ] + lx[ 1 ] ) * 0.5;
+      centroid[ 1 ] = ( ly[ 0 ] + ly[ 1 ] ) * 0.5;
+      centroid[ 2 ] = 0.0;
+      return;
+    }
+    const double lo[ 3 ] = { cell_lower( g, 0, ijk[ 0 ] ), cell_lower( g, 1, ijk[ 1 ] ), cell_lower( g, 2, ijk[ 2 ] ) };
+    Hex cell;
+    make_cell( lo, g.h, cell );
+    const Hs3 H = { { normal[ 0 ], normal[ 1 ], normal[ 2 ] }, dist };
+    Face3 f;
+    plane_cut( cell, H, f );
+    face_centroid( f, centroid );
+  }
+
+  template< int DIM >
+  __global__ void __launch_bounds__( 64 ) k_swartz ( Grid g, const double *__restrict__ u, const unsigned char *__restrict__ flags,
+                                                      const int *__restrict__ mixedList, const StepState *state, int capacity,
+                                                      double *__restrict__ hs, int maxIterations )
+  {
+    constexpr int maxNb = ( DIM == 3 ) ? 26 : 8;
+    const int count = mixed_count( state, capacity );
+    for( int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < count; idx += gridDim.x * blockDim.x )
+    {
+      const long long c = mixedList[ idx ];
+      int ijk[ 3 ];
+      cell_ijk( g, c, ijk );
+      double *rec = hs + c * ( DIM + 1 );
+      const double colorEn = u[ c ];
+
+      // mixed vertex neighbours, ascending index; packed offsets (dx+1) | (dy+1)<<2 | (dz+1)<<4
+      unsigned char nbOff[ maxNb ];
+      int nNb = 0;
+      for( int dz = ( DIM == 3 ? -1 : 0 ); dz <= ( DIM == 3 ? 1 : 0 ); ++dz )
+        for( int dy = -1; dy <= 1; ++dy )
+          for( int dx = -1; dx <= 1; ++dx )
+          {
+            if( dx == 0 && dy == 0 && dz == 0 )
+              continue;
+            const int nb[ 3 ] = { ijk[ 0 ] + dx, ijk[ 1 ] + dy, ijk[ 2 ] + dz };
+            if( !cell_exists( g, nb ) )
+              continue;
+            if( !is_mixed( flags[ cell_index( g, nb ) ] ) )
+              continue;
+            nbOff[ nNb++ ] = (unsigned char) ( ( dx + 1 ) | ( ( dy + 1 ) << 2 ) | ( ( dz + 1 ) << 4 ) );
+          }
+
+      double normal[ 3 ] = { rec[ 0 ], rec[ 1 ], DIM == 3 ? rec[ 2 ] : 0.0 };
+      int iterations = 0;
+      double residuum = 0.0;
+      do
+      {
+        const double oldNormal[ 3 ] = { normal[ 0 ], normal[ 1 ], normal[ 2 ] };
+        normal[ 0 ] = normal[ 1 ] = normal[ 2 ] = 0.0;
+
+        double cEn[ 3 ];
+        interface_centroid< DIM >( g, ijk, oldNormal, colorEn, cEn );
+
+        double cNb[ maxNb ][ 3 ];
+        for( int a = 0; a < nNb; ++a )
+        {
+          const int nb[ 3 ] = { ijk[ 0 ] + ( nbOff[ a ] & 3 ) - 1, ijk[ 1 ] + ( ( nbOff[ a ] >> 2 ) & 3 ) - 1, ijk[ 2 ] + ( ( nbOff[ a ] >> 4 ) & 3 ) - 1 };
+          interface_centroid< DIM >( g, nb, oldNormal, u[ cell_index( g, nb ) ], cNb[ a ] );
+        }
+
+        if( DIM == 2 )
+        {
+          for( int a = 0; a < nNb; ++a )
+          {
+            const double dx = cNb[ a ][ 0 ] - cEn[ 0 ], dy = cNb[ a ][ 1 ] - cEn[ 1 ];
+            double cx = -dy, cy = dx;
+            if( dot2( cx, cy, oldNormal[ 0 ], oldNormal[ 1 ] ) < 0 )
+            {
+              cx *= -1.0;
+              cy *= -1.0;
+            }
+            const double nrm = norm2( cx, cy );
+            cx /= nrm;
+            cy /= nrm;
+            normal[ 0 ] += 1.0 * cx;
+            normal[ 1 ] += 1.0 * cy;
+          }
+        }
+        else
+        {
+          for( int a = 0; a < nNb; ++a )
+            for( int b = 0; b < nNb; ++b )
+            {
+              if( a == b )
+                continue;
+              double d1[ 3 ], d2[ 3 ], cn[ 3 ];
+#pragma unroll
+              for( int k = 0; k < 3; ++k )
+              {
+                d1[ k ] = cNb[ a ][ k ] - cEn[ k ];
+                d2[ k ] = cNb[ b ][ k ] - cEn[ k ];
+              }
+              cross3( d1, d2, cn );
+              if( norm3( cn ) < 1e-12 )
+                continue;
+              if( dot3( cn, oldNormal ) < 0 )
+              {
+#pragma unroll
+                for( int k = 0; k < 3; ++k )
+                  cn[ k ] *= -1.0;
+              }
+              const double nrm = norm3( cn );
+#pragma unroll
+              for( int k = 0; k < 3; ++k )
+              {
+                cn[ k ] /= nrm;
+                normal[ k ] += 1.0 * cn[ k ];
+              }
+            }
+        }
+
+        double n2 = 0.0;
+#pragma unroll
+        for( int k = 0; k < DIM; ++k )
+          n2 += normal[ k ] * normal[ k ];
+        const double nrm = sqrt( n2 );
+        if( nrm < 0.5 )
+          break;   // "return": keep the last reconstruction, modifiedswartz.hh:140-141,231-232
+#pragma unroll
+        for( int k = 0; k < DIM; ++k )
+          normal[ k ] /= nrm;
+
+        const double dist = locate_cell< DIM >( g, ijk, normal, colorEn );
+#pragma unroll
+        for( int k = 0; k < DIM; ++k )
+          rec[ k ] = normal[ k ];
+        rec[ DIM ] = dist;
+
+        double dotp = 0.0;
+#pragma unroll
+        for( int k = 0; k < DIM; ++k )
+          dotp += normal[ k ] * oldNormal[ k ];
+        residuum = 1.0 - dotp;
+        ++iterations;
+      }
+      while( residuum > 1e-12 && iterations < maxIterations );
+    }
+  }
+
+  // ------------------------------------------------------------------------------------------------------------
+  // E1: geometric fluxes, evolution/evolution.hh:90-174.  LANES lanes per mixed cell, one per face.
+  // ------------------------------------------------------------------------------------------------------------
+
+  __device__ __forceinline__ void atomic_min_positive ( double *addr, double value )
+  {
+    // std::min( dtEst, value ) for value >= 0 (NaN never wins, as in std::min): the bit patterns of non-negative
+    // doubles are ordered like unsigned integers
+    if( value == value )
+      atomicMin( reinterpret_cast< unsigned long long * >( addr ), (unsigned long long) __double_as_longlong( value ) );
+  }
+
+  template< int DIM >
+  __global__ void __launch_bounds__( 128 ) k_flux ( Grid g, const Velocity *__restrict__ velocity, const double *__restrict__ hs,
+                                                     const unsigned char *__restrict__ flags, const int *__restrict__ mixedList,
+                                                     StepState *state, int capacity, FluxRecord *__restrict__ records,
+                                                     const double *timeOverride, const double *dtOverride )
+  {
+    constexpr int LANES = ( DIM == 3 ) ? 8 : 4;
+    constexpr int NFACES = 2 * DIM;
+    const int count = mixed_count( state, capacity );
+    const double time = timeOverride ? *timeOverride : state->time;
+    const double dt = dtOverride ? *dtOverride : state->dt;
+    const double volume = cell_volume( g );
+    const int groupsPerBlock = blockDim.x / LANES;
+    const int lane = threadIdx.x % LANES;
+    const int laneInWarp = threadIdx.x & 31;
+    const int groupBase = laneInWarp - lane;
+    // all groups of a warp iterate the same number of times so that the shuffles below see full warps
+    const int nGroupsRounded = ( ( count + 32 / LANES - 1 ) / ( 32 / LANES ) ) * ( 32 / LANES );
+    for( int idx = blockIdx.x * groupsPerBlock + threadIdx.x / LANES; idx < nGroupsRounded; idx += gridDim.x * groupsPerBlock )
+    {
+      const bool active = idx < count;
+      double sf = 0.0, selfc = 0.0, nbc = 0.0;
+      bool hasNb = false, hasSelf = false, hasNbc = false;
+      long long c = 0;
+      if( active && lane < NFACES )
+      {
+        c = mixedList[ idx ];
+        int ijk[ 3 ];
+        cell_ijk( g, c, ijk );
+        const int face = lane;
+        int nb[ 3 ] = { ijk[ 0 ], ijk[ 1 ], ijk[ 2 ] };
+        nb[ face >> 1 ] += ( face & 1 ) ? 1 : -1;
+        // a face has a neighbour iff the neighbour is inside the global domain (intersection.neighbor(), :102-103)
+        if( in_domain( g, nb ) )
+        {
+          hasNb = true;
+          const unsigned char flagNb = cell_exists( g, nb ) ? flags[ cell_index( g, nb ) ] : (unsigned char) 99;
+          double outerNormal[ 3 ] = { 0.0, 0.0, 0.0 };
+          outerNormal[ face >> 1 ] = ( face & 1 ) ? 1.0 : -1.0;
+          double v[ 3 ];
+          face_velocity( g, *velocity, ijk, face, time, v );
+          const double faceVol = face_measure_of( g, face );
+          double nv = 0.0;
+#pragma unroll
+          for( int k = 0; k < DIM; ++k )
+            nv += outerNormal[ k ] * v[ k ];
+          sf = faceVol * fabs( nv );
+#pragma unroll
+          for( int k = 0; k < DIM; ++k )
+            v[ k ] *= dt;
+          double vn = 0.0, vN = 0.0;
+#pragma unroll
+          for( int k = 0; k < DIM; ++k )
+          {
+            vn += v[ k ] * outerNormal[ k ];
+            vN += v[ k ] * ( outerNormal[ k ] * faceVol );   // v * integrationOuterNormal
+          }
+          if( vn > 0 )
+          {
+            double flux;
+            const double *rec = hs + c * ( DIM + 1 );
+            if( DIM == 2 )
+            {
+              const Hs2 H = { rec[ 0 ], rec[ 1 ], rec[ 2 ] };
+              flux = vofx::flux( cell_lower( g, 0, ijk[ 0 ] ), cell_lower( g, 1, ijk[ 1 ] ), g.h[ 0 ], g.h[ 1 ], face, v[ 0 ], v[ 1 ], H );
+            }
+            else
+            {
+              const Hs3 H = { { rec[ 0 ], rec[ 1 ], rec[ 2 ] }, rec[ 3 ] };
+              const double lo[ 3 ] = { cell_lower( g, 0, ijk[ 0 ] ), cell_lower( g, 1, ijk[ 1 ] ), cell_lower( g, 2, ijk[ 2 ] ) };
+              flux = vofx::flux( lo, g.h, face, v, H );
+            }
+            hasSelf = true;
+            selfc = -( flux / volume );                          // update[ entity ] -= flux / volume
+            if( flagNb == 3 )
+            {
+              hasNbc = true;
+              nbc = -( ( vN - flux ) / volume );                 // update[ neighbor ] -= ( v*N - flux ) / volume
+            }
+            else if( flagNb == 0 || is_mixed( flagNb ) )
+            {
+              hasNbc = true;
+              nbc = flux / volume;                               // update[ neighbor ] += flux / volume
+            }
+          }
+          if( flagNb == 3 && vn < 0 )
+          {
+            hasSelf = true;
+            selfc = -( vN / volume );                            // inflow from a full neighbour
+          }
+        }
+      }
+
+      // time-step estimate: volume / sum of |F| |n.v| over the faces in face order, :113,144
+      double sumFluxes = 0.0;
+#pragma unroll
+      for( int f = 0; f < NFACES; ++f )
+      {
+        const double sff = __shfl_sync( 0xffffffffu, sf, groupBase + f );
+        const int has = __shfl_sync( 0xffffffffu, (int) hasNb, groupBase + f );
+        if( has )
+          sumFluxes += sff;
+      }
+      const unsigned selfBits = __ballot_sync( 0xffffffffu, hasSelf ) >> groupBase;
+      const unsigned nbBits = __ballot_sync( 0xffffffffu, hasNbc ) >> groupBase;
+
+      if( active )
+      {
+        FluxRecord *r = records + idx;
+        if( lane < NFACES )
+        {
+          r->self[ lane ] = selfc;
+          r->nb[ lane ] = nbc;
+        }
+        if( lane == 0 )
+        {
+          r->selfMask = (unsigned char) ( selfBits & ( ( 1u << NFACES ) - 1 ) );
+          r->nbMask = (unsigned char) ( nbBits & ( ( 1u << NFACES ) - 1 ) );
+          // only cells this rank owns enter the estimate (every cell is owned by exactly one rank)
+          int ijk[ 3 ];
+          cell_ijk( g, c, ijk );
+          const int la = ijk[ DIM - 1 ];
+          if( la >= g.own0 && la < g.own1 )
+            atomic_min_positive( &state->dtEst, volume / sumFluxes );
+        }
+      }
+    }
+  }
+
+  // ------------------------------------------------------------------------------------------------------------
+  // E1 + U1: owner-computes gather.  LANES lanes per mixed cell: lane 0 = the cell itself,
+  // lanes 1..2*DIM = its face neighbours; a non-mixed neighbour X is handled by its first mixed face neighbour in
+  // the order z-,y-,x-,x+,y+,z+.  The contributions are summed in the order the reference's scatter loop produces:
+  // mixed neighbours with smaller index, the cell's own faces in face order, mixed neighbours with larger index.
+  // ------------------------------------------------------------------------------------------------------------
+
+  template< int DIM >
+  __device__ __forceinline__ int gather_face ( int k )
+  {
+    // k-th entry of the order z-,y-,x-,x+,y+,z+ as a face number of X (2D: y-,x-,x+,y+)
+    if( DIM == 3 )
+    {
+      const int order[ 6 ] = { 4, 2, 0, 1, 3, 5 };
+      return order[ k ];
+    }
+    const int order[ 4 ] = { 2, 0, 1, 3 };
+    return order[ k ];
+  }
+
+  template< int DIM >
+  __global__ void __launch_bounds__( 128 ) k_update ( Grid g, const unsigned char *__restrict__ flags, const int *__restrict__ mixedList,
+                                                       const int *__restrict__ slot, const StepState *state, int capacity,
+                                                       const FluxRecord *__restrict__ records, double *__restrict__ target, int accumulate )
+  {
+    constexpr int LANES = ( DIM == 3 ) ? 8 : 8;
+    constexpr int NFACES = 2 * DIM;
+    const int count = mixed_count( state, capacity );
+    const int groupsPerBlock = blockDim.x / LANES;
+    const int lane = threadIdx.x % LANES;
+    for( int idx = blockIdx.x * groupsPerBlock + threadIdx.x / LANES; idx < count; idx += gridDim.x * groupsPerBlock )
+    {
+      if( lane > NFACES )
+        continue;
+      const long long m = mixedList[ idx ];
+      int mijk[ 3 ];
+      cell_ijk( g, m, mijk );
+      int x[ 3 ] = { mijk[ 0 ], mijk[ 1 ], mijk[ 2 ] };
+      if( lane > 0 )
+      {
+        const int face = lane - 1;
+        x[ face >> 1 ] += ( face & 1 ) ? 1 : -1;
+        if( !cell_exists( g, x ) )
+          continue;
+      }
+      const int la = x[ DIM - 1 ];
+      if( la < g.own0 || la >= g.own1 )
+        continue;                                  // not owned: another rank updates it
+      const long long X = cell_index( g, x );
+      const unsigned char flagX = flags[ X ];
+      if( lane > 0 )
+      {
+        if( is_mixed( flagX ) )
+          continue;                                // a mixed cell gathers for itself (lane 0 of its own group)
+        // is m the first mixed neighbour of X in gather order?
+        bool first = true;
+        for( int k = 0; k < NFACES; ++k )
+        {
+          const int f = gather_face< DIM >( k );
+          int y[ 3 ] = { x[ 0 ], x[ 1 ], x[ 2 ] };
+          y[ f >> 1 ] += ( f & 1 ) ? 1 : -1;
+          if( !cell_exists( g, y ) )
+            continue;
+          const long long Y = cell_index( g, y );
+          if( Y == m )
+            break;
+          const int ly = y[ DIM - 1 ];
+          if( is_mixed( flags[ Y ] ) && ly >= g.list0 && ly < g.list1 )
+          {
+            first = false;
+            break;
+          }
+        }
+        if( !first )
+          continue;
+      }
+
+      double acc = 0.0;
+      // mixed neighbours with smaller index: z-, y-, x-
+      for( int k = 0; k < DIM; ++k )
+      {
+        const int f = gather_face< DIM >( k );
+        int y[ 3 ] = { x[ 0 ], x[ 1 ], x[ 2 ] };
+        y[ f >> 1 ] -= 1;
+        if( !cell_exists( g, y ) )
+          continue;
+        const long long Y = cell_index( g, y );
+        if( !is_mixed( flags[ Y ] ) )
+          continue;
+        const FluxRecord &r = records[ slot[ Y ] ];
+        const int toward = f + 1;                  // Y's face towards X is the upper face of the same axis
+        if( r.nbMask & ( 1u << toward ) )
+          acc += r.nb[ toward ];
+      }
+      if( is_mixed( flagX ) )
+      {
+        const FluxRecord &r = records[ slot[ X ] ];
+        for( int f = 0; f < NFACES; ++f )
+          if( r.selfMask & ( 1u << f ) )
+            acc += r.self[ f ];
+      }
+      for( int k = DIM; k < NFACES; ++k )
+      {
+        const int f = gather_face< DIM >( k );
+        int y[ 3 ] = { x[ 0 ], x[ 1 ], x[ 2 ] };
+        y[ f >> 1 ] += 1;
+        if( !cell_exists( g, y ) )
+          continue;
+        const long long Y = cell_index( g, y );
+        if( !is_mixed( flags[ Y ] ) )
+          continue;
+        const FluxRecord &r = records[ slot[ Y ] ];
+        const int toward = f - 1;                  // Y's lower face of the same axis
+        if( r.nbMask & ( 1u << toward ) )
+          acc += r.nb[ toward ];
+      }
+
+      if( accumulate )
+        target[ X ] += 1.0 * acc;                  // uh.axpy( 1.0, update ), colorfunction.hh:31-37
+      else
+        target[ X ] = acc;                         // the dense `update` of the operator-level API
+    }
+  }
+
+  // T1: algorithm.hh:85-93
+  __global__ void k_finalize ( StepState *state, double cfl )
+  {
+    if( state->dt > 0.0 )
+      state->time += state->dt;
+    state->dt = state->dtEst * cfl;
+    state->dtEstLast = state->dtEst;
+    state->dtEst = DBL_MAX;
+    state->mixedCountLast = state->mixedCount;
+    state->mixedCount = 0;
+  }
+
+  __global__ void k_reset_counters ( StepState *state )
+  {
+    state->mixedCount = 0;
+    state->dtEst = DBL_MAX;
+  }
+
+  // U1 (operator-level API): ColorFunction::axpy, colorfunction.hh:31-37
+  __global__ void __launch_bounds__( 256 ) k_axpy ( long long n, double *__restrict__ u, double a, const double *__restrict__ x )
+  {
+    for( long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x; i < n; i += (long long) gridDim.x * blockDim.x )
+      u[ i ] += a * x[ i ];
+  }
+
+} // namespace vofx
+
+namespace vofx
+{
+
+  // ------------------------------------------------------------------------------------------------------------
+  // C1: height-function curvature, curvature/cartesianheightfunctioncurvature.hh:54-187
+  // ------------------------------------------------------------------------------------------------------------
+
+  // effectiveTdown, heightfunctionstencil.hh:47-53
+  template< int DIM >
+  __device__ __forceinline__ int hf_effective_tdown ( const Grid &g, const int *ijk, int i, int j, int tup )
+  {
+    constexpr int noc = ( DIM == 2 ) ? 3 : 9;
+    for( int t = -1; t >= -tup; --t )
+      if( hf_cell< DIM >( g, ijk, i, j, ( noc - 1 ) / 2, t ) < 0 )
+        return -1 - t;
+    return tup;
+  }
+
+  // pass 1 (applyLocal, :94-123): per mixed cell the raw curvature and whether the stencil satisfies the constraint
+  template< int DIM >
+  __global__ void __launch_bounds__( 128 ) k_curvature_local ( Grid g, const double *__restrict__ u, const double *__restrict__ hs,
+                                                                const int *__restrict__ mixedList, const StepState *state, int capacity,
+                                                                double *__restrict__ curv1, unsigned char *__restrict__ ok1 )
+  {
+    constexpr int noc = ( DIM == 2 ) ? 3 : 9;
+    const int count = mixed_count( state, capacity );
+    for( int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < count; idx += gridDim.x * blockDim.x )
+    {
+      const long long c = mixedList[ idx ];
+      int ijk[ 3 ];
+      cell_ijk( g, c, ijk );
+      const double *rec = hs + c * ( DIM + 1 );
+      const double normal[ 3 ] = { rec[ 0 ], rec[ 1 ], DIM == 3 ? rec[ 2 ] : 0.0 };
+      int dir, sign;
+      hf_orientation< DIM >( normal, dir, sign );
+      double heights[ 9 ];
+      hf_heights< DIM >( g, u, ijk, dir, sign, 1, heights );
+
+      double kappa = 0.0;
+      unsigned char ok = 0;
+      const double uMid = heights[ ( noc - 1 ) / 2 ];
+      const int effTdown = hf_effective_tdown< DIM >( g, ijk, dir, sign, 1 );
+      if( !( uMid < effTdown || uMid > effTdown + 1 ) )
+      {
+        const double deltaX = g.h[ DIM - dir - 1 ];   // jacobianTransposed[dim-o-1][dim-o-1], :111-113
+        bool anyZero = false;
+        for( int i = 0; i < noc; ++i )
+          if( heights[ i ] == 0.0 )
+            anyZero = true;
+        if( !anyZero )
+        {
+          ok = 1;
+          if( DIM == 2 )
+          {
+            const double Hx = ( heights[ 2 ] - heights[ 0 ] ) / 2.0;
+            const double Hxx = ( heights[ 2 ] - 2 * heights[ 1 ] + heights[ 0 ] ) / deltaX;
+            kappa = -Hxx / pow( 1.0 + Hx * Hx, 3.0 / 2.0 );
+          }
+          else
+          {
+            const double Hx = ( heights[ 5 ] - heights[ 3 ] ) / 2.0;
+            const double Hy = ( heights[ 7 ] - heights[ 1 ] ) / 2.0;
+            const double Hxx = ( heights[ 5 ] - 2.0 * heights[ 4 ] + heights[ 3 ] ) / deltaX;
+            const double Hyy = ( heights[ 7 ] - 2.0 * heights[ 4 ] + heights[ 1 ] ) / deltaX;
+            const double Hxy = ( heights[ 8 ] - heights[ 2 ] - heights[ 6 ] + heights[ 0 ] ) / ( 4.0 * deltaX );
+            kappa = -( Hxx + Hyy + Hxx * Hy * Hy + Hyy * Hx * Hx - 2.0 * Hxy * Hx * Hy ) / ( pow( 1.0 + Hx * Hx + Hy * Hy, 3.0 / 2.0 ) );
+          }
+        }
+      }
+      curv1[ idx ] = kappa;
+      ok1[ idx ] = ok;
+    }
+  }
+
+  // pass 2 (averageCurvature with firstTurn, :156-187): keep the own value if valid, else the mean over the valid
+  // mixed vertex neighbours (ascending index order)
+  template< int DIM >
+  __global__ void __launch_bounds__( 128 ) k_curvature_average ( Grid g, const unsigned char *__restrict__ flags, const int *__restrict__ mixedList,
+                                                                  const int *__restrict__ slot, const StepState *state, int capacity,
+                                                                  const double *__restrict__ curv1, const unsigned char *__restrict__ ok1,
+                                                                  double *__restrict__ kappa, unsigned char *__restrict__ valid )
+  {
+    const int count = mixed_count( state, capacity );
+    for( int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < count; idx += gridDim.x * blockDim.x )
+    {
+      const long long c = mixedList[ idx ];
+      if( valid )
+        valid[ c ] = ok1[ idx ];
+      if( ok1[ idx ] )
+      {
+        kappa[ c ] = curv1[ idx ];
+        continue;
+      }
+      int ijk[ 3 ];
+      cell_ijk( g, c, ijk );
+      double sum = 0.0;
+      int n = 0;
+      for( int dz = ( DIM == 3 ? -1 : 0 ); dz <= ( DIM == 3 ? 1 : 0 ); ++dz )
+        for( int dy = -1; dy <= 1; ++dy )
+          for( int dx = -1; dx <= 1; ++dx )
+          {
+            if( dx == 0 && dy == 0 && dz == 0 )
+              continue;
+            const int nb[ 3 ] = { ijk[ 0 ] + dx, ijk[ 1 ] + dy, ijk[ 2 ] + dz };
+            if( !cell_exists( g, nb ) )
+              continue;
+            const long long cn = cell_index( g, nb );
+            const int ln = nb[ DIM - 1 ];
+            if( !is_mixed( flags[ cn ] ) || ln < g.list0 || ln >= g.list1 )
+              continue;
+            const int s = slot[ cn ];
+            if( ok1[ s ] )
+            {
+              sum += curv1[ s ];
+              n++;
+            }
+          }
+      if( n > 0 )
+        sum /= (double) n;
+      kappa[ c ] = sum;
+    }
+  }
+
+  // ------------------------------------------------------------------------------------------------------------
+  // initial data: RecursiveInterpolationCube depth 3 (interpolation/recursiveinterpolationcube.hh:33-82) of the
+  // built-in problems' indicator functions (test/problems, Problem::evaluate).  Transcendental time factors are
+  // evaluated on the host and passed in, so the device only does + - * sqrt and comparisons.
+  // ------------------------------------------------------------------------------------------------------------
+
+  struct Indicator
+  {
+    int kind;          // 0 ball |x-c| < r, 1 ball |x-c|^2 <= r^2, 2 slotted cylinder, 3 half space x0 <= pos
+    int dim;
+    double c[ 3 ];     // centre (kinds 0,1) / wall position in c[0] (kind 3)
+    double r;
+    double cs, sn;     // slotted cylinder: cos/sin of the rotation angle
+  };
+
+  __device__ __forceinline__ int indicator_eval ( const Indicator &I, const double *x )
+  {
+    double uu = 0.0;
+    if( I.kind == 0 )
+    {
+      // rotatingcircle.hh:81-90, LeVeque (oracle/problems_extra.hh): ( x - center ).two_norm() < r
+      double s = 0.0;
+      for( int k = 0; k < I.dim; ++k )
+      {
+        const double d = x[ k ] - I.c[ k ];
+        s += d * d;
+      }
+      uu = ( sqrt( s ) < I.r ) ? 1.0 : 0.0;
+    }
+    else if( I.kind == 1 )
+    {
+      // sflow.hh:26-33,63-71: y = c - x; y.two_norm2() <= r*r
+      double s = 0.0;
+      for( int k = 0; k < I.dim; ++k )
+      {
+        const double d = I.c[ k ] - x[ k ];
+        s += d * d;
+      }
+      uu = ( s <= I.r * I.r ) ? 1.0 : 0.0;
+    }
+    else if( I.kind == 2 )
+    {
+      // slottedcylinder.hh:22-45
+      const double cx = 0.5, cy = 0.5;
+      double xpx = cx, xpy = cy;
+      const double tx = x[ 0 ] - cx, ty = x[ 1 ] - cy;
+      xpx += I.cs * tx;
+      xpy += I.cs * ty;
+      const double r0 = -ty, r1 = tx;
+      xpx += I.sn * r0;
+      xpy += I.sn * r1;
+      const double slotWidth = 0.075;
+      double dx = xpx - cx, dy = xpy - cy;
+      if( norm2( dx, dy ) < 0.4 )
+        uu = 1.0;
+      const double ccx = cx + 0.0, ccy = cy + slotWidth;
+      dx = xpx - ccx;
+      dy = xpy - ccy;
+      if( norm2( dx, dy ) < slotWidth )
+        uu = 0.0;
+      if( xpy > cy + slotWidth && fabs( xpx - cx ) < slotWidth )
+        uu = 0.0;
+    }
+    else
+      uu = ( x[ 0 ] <= I.c[ 0 ] ) ? 1.0 : 0.0;   // linearwall.hh:17-20
+    return (int) ( uu + 0.3 );
+  }
+
+  // LEVEL is a template parameter so that the recursion depth (3) is static: no device call stack needed
+  template< int DIM, int LEVEL >
+  __device__ double recursive_evaluation ( const Grid &g, const Indicator &I, const double *cellLo, const double *origin, double h )
+  {
+    constexpr int corners = 1 << DIM;
+    int sum = 0;
+    for( int i = 0; i < corners; ++i )
+    {
+      double x[ 3 ] = { 0.0, 0.0, 0.0 };
+      for( int j = 0; j < DIM; ++j )
+      {
+        double corner = origin[ j ];
+        corner += h * (double) ( ( i >> j ) & 1 );
+        x[ j ] = cellLo[ j ];
+        x[ j ] += corner * g.h[ j ];
+      }
+      sum += indicator_eval( I, x );
+    }
+    double vol = 1.0;
+    for( int i = 0; i < DIM; ++i )
+      vol *= h;
+    if( LEVEL == 0 )
+      return vol * ( (double) sum / (double) corners );
+    if( sum == corners )
+      return vol;
+    if( sum == 0 )
+      return 0.0;
+    h /= 2;
+    double value = 0.0;
+    for( int i = 0; i < corners; ++i )
+    {
+      double childOrigin[ 3 ] = { 0.0, 0.0, 0.0 };
+      for( int j = 0; j < DIM; ++j )
+      {
+        childOrigin[ j ] = origin[ j ];
+        childOrigin[ j ] += h * (double) ( ( i >> j ) & 1 );
+      }
+      value += recursive_evaluation< DIM, ( LEVEL > 0 ? LEVEL - 1 : 0 ) >( g, I, cellLo, childOrigin, h );
+    }
+    return value;
+  }
+
+  template< int DIM >
+  __global__ void __launch_bounds__( 128 ) k_init ( Grid g, Indicator I, double *__restrict__ u )
+  {
+    for( long long c = blockIdx.x * (long long) blockDim.x + threadIdx.x; c < g.cells; c += (long long) gridDim.x * blockDim.x )
+    {
+      int ijk[ 3 ];
+      cell_ijk( g, c, ijk );
+      if( !in_domain( g, ijk ) )
+      {
+        u[ c ] = 0.0;
+        continue;
+      }
+      double lo[ 3 ] = { 0.0, 0.0, 0.0 };
+      for( int d = 0; d < DIM; ++d )
+        lo[ d ] = cell_lower( g, d, ijk[ d ] );
+      const double origin[ 3 ] = { 0.0, 0.0, 0.0 };
+      u[ c ] = recursive_evaluation< DIM, 3 >( g, I, lo, origin, 1.0 );
+    }
+  }
+
+  // ------------------------------------------------------------------------------------------------------------
+  // single-cell primitives on small batches (parity tests of G1/G2/G5/G6/G7 on the device)
+  // ------------------------------------------------------------------------------------------------------------
+
+  template< int DIM >
+  __global__ void k_test_locate ( long long count, const double *lo, const double *h, const double *normal, const double *fraction, double *out )
+  {
+    for( long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x; i < count; i += (long long) gridDim.x * blockDim.x )
+    {
+      double d;
+      if( DIM == 2 )
+      {
+        Poly2 p;
+        make_cell( lo[ 2 * i ], lo[ 2 * i + 1 ], h[ 2 * i ], h[ 2 * i + 1 ], p );
+        d = locate( p, normal[ 2 * i ], normal[ 2 * i + 1 ], fraction[ i ] );
+      }
+      else
+      {
+        Hex c;
+        make_cell( lo + 3 * i, h + 3 * i, c );
+        d = locate( c, normal + 3 * i, fraction[ i ] );
+      }
+      for( int k = 0; k < DIM; ++k )
+        out[ ( DIM + 1 ) * i + k ] = normal[ DIM * i + k ];
+      out[ ( DIM + 1 ) * i + DIM ] = d;
+    }
+  }
+
+  template< int DIM >
+  __global__ void k_test_flux ( long long count, const double *lo, const double *h, const int *face, const double *v, const double *hs, double *out )
+  {
+    for( long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x; i < count; i += (long long) gridDim.x * blockDim.x )
+    {
+      if( DIM == 2 )
+      {
+        const Hs2 H = { hs[ 3 * i ], hs[ 3 * i + 1 ], hs[ 3 * i + 2 ] };
+        out[ i ] = flux( lo[ 2 * i ], lo[ 2 * i + 1 ], h[ 2 * i ], h[ 2 * i + 1 ], face[ i ], v[ 2 * i ], v[ 2 * i + 1 ], H );
+      }
+      else
+      {
+        const Hs3 H = { { hs[ 4 * i ], hs[ 4 * i + 1 ], hs[ 4 * i + 2 ] }, hs[ 4 * i + 3 ] };
+        out[ i ] = flux( lo + 3 * i, h + 3 * i, face[ i ], v + 3 * i, H );
+      }
+    }
+  }
+
+  template< int DIM >
+  __global__ void k_test_interface ( long long count, const double *lo, const double *h, const double *hs, int *nverts, double *centroid, double *measure )
+  {
+    for( long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x; i < count; i += (long long) gridDim.x * blockDim.x )
+    {
+      if( DIM == 2 )
+      {
+        Poly2 p;
+        make_cell( lo[ 2 * i ], lo[ 2 * i + 1 ], h[ 2 * i ], h[ 2 * i + 1 ], p );
+        const Hs2 H = { hs[ 3 * i ], hs[ 3 * i + 1 ], hs[ 3 * i + 2 ] };
+        double lx[ 2 ], ly[ 2 ];
+        plane_cut( p, H, lx, ly );
+        nverts[ i ] = 2;
+        centroid[ 2 * i ] = ( lx[ 0 ] + lx[ 1 ] ) * 0.5;
+        centroid[ 2 * i + 1 ] = ( ly[ 0 ] + ly[ 1 ] ) * 0.5;
+        measure[ i ] = norm2( lx[ 0 ] - lx[ 1 ], ly[ 0 ] - ly[ 1 ] );
+      }
+      else
+      {
+        Hex c;
+        make_cell( lo + 3 * i, h + 3 * i, c );
+        const Hs3 H = { { hs[ 4 * i ], hs[ 4 * i + 1 ], hs[ 4 * i + 2 ] }, hs[ 4 * i + 3 ] };
+        Face3 f;
+        plane_cut( c, H, f );
+        nverts[ i ] = f.n;
+        if( f.n > 2 )
+        {
+          face_centroid( f, centroid + 3 * i );
+          measure[ i ] = face_measure( f );
+        }
+        else
+        {
+          centroid[ 3 * i ] = centroid[ 3 * i + 1 ] = centroid[ 3 * i + 2 ] = 0.0;
+          measure[ i ] = 0.0;
+        }
+      }
+    }
+  }
+
+  __global__ void k_test_face_velocity ( Grid g, const Velocity *velocity, double time, long long cell, int face, double *out )
+  {
+    int ijk[ 3 ];
+    cell_ijk( g, cell, ijk );
+    face_velocity( g, *velocity, ijk, face, time, out );
+  }
+
+} // namespace vofx

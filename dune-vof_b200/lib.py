@@ -1,0 +1,115 @@
+"""ctypes binding of the vofx C ABI (include/vofx.h) and the in-tree build of dune-vof_b200/libvofx.so.
+
+There is no fallback: if the shared library is missing or no CUDA device is present every entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+LIB_PATH = os.path.join(HERE, "libvofx.so")
+CSRC = os.path.join(HERE, "csrc")
+
+RECON_YOUNGS, RECON_HF, RECON_SWARTZ = 0, 1, 2
+PROB_ROTATING_CIRCLE, PROB_SFLOW, PROB_SLOTTED_CYLINDER, PROB_LINEAR_WALL, PROB_LEVEQUE = 0, 1, 2, 3, 4
+TIME_CONST, TIME_COSPI = 0, 1
+
+# every symbol include/vofx.h declares
+SYMBOLS = [
+    "vofx_last_error", "vofx_create", "vofx_destroy", "vofx_set_stream", "vofx_cells", "vofx_velocity_clear",
+    "vofx_velocity_set_component", "vofx_velocity_set_factor", "vofx_velocity_builtin", "vofx_face_velocity",
+    "vofx_flag", "vofx_reconstruct", "vofx_evolve", "vofx_axpy", "vofx_curvature", "vofx_step_begin", "vofx_step",
+    "vofx_step_state", "vofx_step_local", "vofx_step_finish", "vofx_dt_est_device", "vofx_flag_host",
+    "vofx_reconstruct_host", "vofx_evolve_host", "vofx_curvature_host", "vofx_step_host", "vofx_init",
+    "vofx_test_locate", "vofx_test_flux", "vofx_test_interface", "vofx_launch_count",
+]
+
+
+class GridDesc(C.Structure):
+    _fields_ = [("dim", C.c_int32), ("n_global", C.c_int32 * 3), ("origin", C.c_double * 3), ("h", C.c_double * 3),
+                ("lo", C.c_int32 * 3), ("n_local", C.c_int32 * 3), ("halo", C.c_int32)]
+
+
+class StepParams(C.Structure):
+    _fields_ = [("reconstruction", C.c_int32), ("max_iterations", C.c_int32), ("eps", C.c_double), ("cfl", C.c_double),
+                ("with_curvature", C.c_int32)]
+
+
+class VofxError(RuntimeError):
+    pass
+
+
+def sources():
+    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))] + \
+           [os.path.join(ROOT, "include", "vofx.h")]
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false ... -> dune-vof_b200/libvofx.so (in-tree)."""
+    newest = max(os.path.getmtime(s) for s in sources())
+    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < newest:
+        cmd = ["make", "-f", os.path.join(CSRC, "Makefile")]
+        if force:
+            cmd.append("-B")
+        subprocess.check_call(cmd, cwd=ROOT, stdout=None if verbose else subprocess.DEVNULL)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def load():
+    """Load libvofx.so and declare the prototypes.  Raises if the library has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise VofxError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(vofx has no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, dp, bp, ip = C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p   # raw addresses (device or host)
+    L.vofx_last_error.restype = C.c_char_p
+    L.vofx_create.argtypes = [C.POINTER(GridDesc), C.c_int, C.POINTER(C.c_void_p)]
+    L.vofx_destroy.argtypes = [vp]
+    L.vofx_destroy.restype = None
+    L.vofx_set_stream.argtypes = [vp, vp]
+    L.vofx_cells.argtypes = [vp]
+    L.vofx_cells.restype = C.c_int64
+    L.vofx_launch_count.argtypes = [vp]
+    L.vofx_launch_count.restype = C.c_int64
+    L.vofx_velocity_clear.argtypes = [vp]
+    L.vofx_velocity_set_component.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_int, C.c_double]
+    L.vofx_velocity_set_factor.argtypes = [vp, C.c_int, C.c_int, C.c_int, dp, dp, dp]
+    L.vofx_velocity_builtin.argtypes = [vp, C.c_int]
+    L.vofx_face_velocity.argtypes = [vp, C.c_double, C.c_int64, C.c_int, dp]
+    L.vofx_flag.argtypes = [vp, dp, C.c_double, bp]
+    L.vofx_reconstruct.argtypes = [vp, C.c_int, dp, bp, dp, C.c_int]
+    L.vofx_evolve.argtypes = [vp, dp, bp, C.c_double, C.c_double, dp, C.POINTER(C.c_double)]
+    L.vofx_axpy.argtypes = [vp, dp, C.c_double, dp]
+    L.vofx_curvature.argtypes = [vp, dp, dp, bp, dp, bp]
+    L.vofx_step_begin.argtypes = [vp, C.c_double, C.c_double]
+    L.vofx_step.argtypes = [vp, C.POINTER(StepParams), dp, bp, dp, dp]
+    L.vofx_step_local.argtypes = [vp, C.POINTER(StepParams), dp, bp, dp, dp]
+    L.vofx_step_finish.argtypes = [vp, C.POINTER(StepParams)]
+    L.vofx_dt_est_device.argtypes = [vp]
+    L.vofx_dt_est_device.restype = C.c_void_p
+    L.vofx_step_state.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+    L.vofx_flag_host.argtypes = [vp, dp, C.c_double, bp]
+    L.vofx_reconstruct_host.argtypes = [vp, C.c_int, dp, bp, dp, C.c_int]
+    L.vofx_evolve_host.argtypes = [vp, dp, bp, C.c_double, C.c_double, dp, C.POINTER(C.c_double)]
+    L.vofx_curvature_host.argtypes = [vp, dp, dp, bp, dp, bp]
+    L.vofx_step_host.argtypes = [vp, C.POINTER(StepParams), dp, bp]
+    L.vofx_init.argtypes = [vp, C.c_int, C.c_double, dp]
+    L.vofx_test_locate.argtypes = [C.c_int, C.c_int64, dp, dp, dp, dp, dp]
+    L.vofx_test_flux.argtypes = [C.c_int, C.c_int64, dp, dp, ip, dp, dp, dp]
+    L.vofx_test_interface.argtypes = [C.c_int, C.c_int64, dp, dp, dp, ip, dp, dp]
+    _lib = L
+    return L
+
+
+def check(status: int) -> None:
+    if status != 0:
+        raise VofxError(f"vofx status {status}: {load().vofx_last_error().decode()}")

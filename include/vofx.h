@@ -1,0 +1,182 @@
+/* vofx -- C ABI of the B200-native volume-of-fluid step.
+ *
+ * This is the drop-in boundary for dune-vof's per-timestep hot path.  Each entry point
+ * names the reference interface it replaces (paths relative to the reference's dune/vof/).  The header adaptor in
+ * include/dune/vofx/ wraps these calls in classes with the reference's operator names and signatures;
+ * INTEGRATION.md shows the binding a dune-vof maintainer would add.
+ *
+ * Plain C: pointers and sizes only, no C++/torch types.  All functions return 0 on success and a non-zero status
+ * otherwise (never throw across the boundary); vofx_last_error() describes the last failure of the calling thread.
+ * There is NO CPU fallback: every entry point needs a CUDA device and fails with VOFX_ERR_CUDA without one.
+ *
+ * Grid convention (defined here so that host and device generate bit-identical coordinates):
+ *   structured Cartesian grid, global cell multi-index (i,j,k), cell index x-fastest;
+ *   cell lower corner x_lo[d] = origin[d] + i[d]*h[d]; upper corner x_lo[d] + h[d]; centre x_lo[d] + 0.5*h[d];
+ *   faces are numbered x-,x+,y-,y+,z-,z+ (dune-grid's cube numbering).
+ * Slab decomposition (multi-GPU): a context owns the cells [lo, lo+n_local) and stores `halo` extra layers on
+ *   either side along the LAST axis only; every per-cell array passed to a context has
+ *   n_local[0] * n_local[1] * (n_local[2] + 2*halo) entries in 3D (n_local[0] * (n_local[1] + 2*halo) in 2D).
+ *   With halo == 0 and lo == 0, n_local == n_global this is the plain single-GPU layout.
+ *
+ * Data layout:
+ *   colour u       double[cells]            (dune-vof ColorFunction, colorfunction.hh:20-52)
+ *   flags          uint8_t[cells]           values of enum Flag (flagset.hh:18-24): 0 empty, 1 mixed, 2 mixedfull, 3 full, 99 nan
+ *   half-spaces    double[cells*(dim+1)]    per cell (n[0..dim), d); fluid side n.x + d > 0 (geometry/halfspace.hh:32-112);
+ *                                           the zero normal means "no reconstruction"
+ *   curvature      double[cells], validity uint8_t[cells]
+ */
+#ifndef VOFX_H
+#define VOFX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VOFX_VERSION 1
+
+enum vofx_status
+{
+  VOFX_OK = 0,
+  VOFX_ERR_ARGUMENT = 1,   /* bad descriptor / null pointer / unsupported combination */
+  VOFX_ERR_CUDA = 2,       /* CUDA runtime error, or no device */
+  VOFX_ERR_STATE = 3       /* call sequence error (e.g. step without velocity) */
+};
+
+enum vofx_flag_value { VOFX_FLAG_EMPTY = 0, VOFX_FLAG_MIXED = 1, VOFX_FLAG_MIXEDFULL = 2, VOFX_FLAG_FULL = 3, VOFX_FLAG_NAN = 99 };
+
+/* reconstruction operators of the reference */
+enum vofx_reconstruction
+{
+  VOFX_RECON_YOUNGS = 0,   /* ModifiedYoungsReconstruction,              reconstruction/modifiedyoungs.hh:63-134 */
+  VOFX_RECON_HF = 1,       /* HeightFunctionReconstruction< Youngs >,    reconstruction/heightfunction.hh:70-259 (the default factory, reconstruction.hh:29-37) */
+  VOFX_RECON_SWARTZ = 2    /* ModifiedSwartzReconstruction< Youngs >,    reconstruction/modifiedswartz.hh:70-243 */
+};
+
+typedef struct
+{
+  int32_t dim;             /* 2 or 3 */
+  int32_t n_global[3];     /* cells per axis of the whole grid */
+  double origin[3];        /* lower corner of the whole grid */
+  double h[3];             /* mesh widths */
+  int32_t lo[3];           /* global multi-index of the first owned cell */
+  int32_t n_local[3];      /* owned cells per axis */
+  int32_t halo;            /* halo layers stored along the last axis (0 on a single GPU) */
+} vofx_grid_desc;
+
+typedef struct vofx_ctx vofx_ctx;
+
+const char *vofx_last_error ( void );
+
+/* replaces: construction of the operators + VertexNeighborsStencil in Algorithm's constructor (algorithm.hh:46-51).
+ * device < 0 selects the current device.  The context owns device scratch (mixed-cell list, flux records, tables);
+ * callers own all per-cell arrays. */
+int vofx_create ( const vofx_grid_desc *grid, int device, vofx_ctx **out );
+void vofx_destroy ( vofx_ctx *ctx );
+
+/* run all work of this context on the given cudaStream_t (default: the legacy default stream) */
+int vofx_set_stream ( vofx_ctx *ctx, void *cuda_stream );
+
+/* number of cells of a per-cell array of this context (including halo layers) */
+int64_t vofx_cells ( const vofx_ctx *ctx );
+
+/* ---- velocity (replaces Velocity< Problem, GridView >, velocity.hh:5-33, evaluated at face centres) ------------
+ * Separable description: component a at a face centre x and time t is
+ *     v_a = coef_a * c_a(t) * sum_{r < nterms_a} ( f_{a,r,0}(x_0) * f_{a,r,1}(x_1) ) * f_{a,r,2}(x_2)
+ * (2D: the product of two factors) with the products and sums associated exactly as written, left to right.
+ * Every factor is a table over the cells of its axis, sampled at the three coordinates a face centre can have
+ * in that axis when seen from cell i: the cell centre, its lower face and its upper face (n_global[axis] entries
+ * each, HOST pointers, copied).  c_a(t) is 1 (VOFX_TIME_CONST) or cos(pi t/period) (VOFX_TIME_COSPI) evaluated by
+ * the fixed polynomial documented in DESIGN.md, so that time can live on the device.
+ * All dune-vof test problems (rigid rotations, SFlow, LinearWall) and the LeVeque fields are of this form.       */
+enum vofx_time_factor { VOFX_TIME_CONST = 0, VOFX_TIME_COSPI = 1 };
+
+int vofx_velocity_clear ( vofx_ctx *ctx );
+int vofx_velocity_set_component ( vofx_ctx *ctx, int component, int nterms, double coef, int time_factor, double period );
+int vofx_velocity_set_factor ( vofx_ctx *ctx, int component, int term, int axis,
+                               const double *at_centre, const double *at_lower_face, const double *at_upper_face );
+
+/* built-in problems (tables generated on the host with libm from the coordinates defined above):
+ * 0 RotatingCircle (test/problems/rotatingcircle.hh:45-52,92-101), 1 SFlow (sflow.hh:35-42,73-82),
+ * 2 SlottedCylinder (slottedcylinder.hh:47-55, 2D), 3 LinearWall (linearwall.hh:27-31), 4 LeVeque deformation field */
+enum vofx_problem { VOFX_PROB_ROTATING_CIRCLE = 0, VOFX_PROB_SFLOW = 1, VOFX_PROB_SLOTTED_CYLINDER = 2, VOFX_PROB_LINEAR_WALL = 3, VOFX_PROB_LEVEQUE = 4 };
+int vofx_velocity_builtin ( vofx_ctx *ctx, int problem );
+
+/* velocity at the centre of `face` of the cell with LOCAL storage index `cell` at time t (for tests) */
+int vofx_face_velocity ( vofx_ctx *ctx, double time, int64_t cell, int face, double *v_host );
+
+/* ---- operators on DEVICE arrays ---------------------------------------------------------------------------------*/
+
+/* replaces FlagOperator::operator()( color, flags ), flagging.hh:35-70 */
+int vofx_flag ( vofx_ctx *ctx, const double *u, double eps, uint8_t *flags );
+
+/* replaces {ModifiedYoungs,HeightFunction,ModifiedSwartz}Reconstruction::operator()( color, reconstructions, flags ):
+ * clears `halfspaces`, then reconstructs every mixed cell.  max_iterations: Swartz only (reference default 10). */
+int vofx_reconstruct ( vofx_ctx *ctx, int kind, const double *u, const uint8_t *flags, double *halfspaces, int max_iterations );
+
+/* replaces Evolution::operator()( reconstructions, flags, velocity, deltaT, update ), evolution/evolution.hh:58-76:
+ * clears `update`, accumulates the geometric fluxes, returns the time-step estimate (min over mixed cells) in *dt_est
+ * (host pointer). */
+int vofx_evolve ( vofx_ctx *ctx, const double *halfspaces, const uint8_t *flags, double time, double dt, double *update, double *dt_est );
+
+/* replaces ColorFunction::axpy( a, x ), colorfunction.hh:31-37 */
+int vofx_axpy ( vofx_ctx *ctx, double *u, double a, const double *x );
+
+/* replaces CartesianHeightFunctionCurvature::operator()( color, reconstructions, flags, curvature ),
+ * curvature/cartesianheightfunctioncurvature.hh:54-87.  `valid` (may be NULL) receives satisfiesConstraint_. */
+int vofx_curvature ( vofx_ctx *ctx, const double *u, const double *halfspaces, const uint8_t *flags, double *kappa, uint8_t *valid );
+
+/* ---- fused time loop on a DEVICE-resident colour function (replaces the loop body of Algorithm::operator(),
+ * algorithm.hh:68-95, without l1error/output) -------------------------------------------------------------------
+ * State (time, dt) lives on the device; no host synchronisation per step.  vofx_step_begin sets (time, dt = 0):
+ * as in the reference the first step is a dry run that only produces the time-step estimate. */
+typedef struct
+{
+  int32_t reconstruction;   /* enum vofx_reconstruction */
+  int32_t max_iterations;   /* Swartz */
+  double eps;               /* flag tolerance (scheme.eps) */
+  double cfl;               /* dt = cfl * dtEst */
+  int32_t with_curvature;   /* also evaluate the height-function curvature each step (into kappa) */
+} vofx_step_params;
+
+int vofx_step_begin ( vofx_ctx *ctx, double time, double dt );
+/* one loop pass: flag -> reconstruct -> evolve -> u += update -> time += dt -> dt = cfl*dtEst.
+ * flags / halfspaces / kappa are outputs (kappa may be NULL unless with_curvature). */
+int vofx_step ( vofx_ctx *ctx, const vofx_step_params *params, double *u, uint8_t *flags, double *halfspaces, double *kappa );
+/* copy the device-resident (time, dt, last dtEst, number of mixed cells of the last step) to the host; synchronises */
+int vofx_step_state ( vofx_ctx *ctx, double *time, double *dt, double *dt_est, int64_t *mixed_cells );
+/* multi-GPU: address of the device scalar holding the last local dtEst, for a MIN all-reduce between
+ * vofx_step_local() and vofx_step_finish() (see dune_vof_b200/host/decomposition.py) */
+int vofx_step_local ( vofx_ctx *ctx, const vofx_step_params *params, double *u, uint8_t *flags, double *halfspaces, double *kappa );
+int vofx_step_finish ( vofx_ctx *ctx, const vofx_step_params *params );
+double *vofx_dt_est_device ( vofx_ctx *ctx );
+
+/* ---- HOST-buffer variants: what the DUNE-side containers (std::vector based DataSet, dataset.hh:26-87) bind to.
+ * They stage through pinned memory, copy to the device, run the operator and copy the results back. */
+int vofx_flag_host ( vofx_ctx *ctx, const double *u, double eps, uint8_t *flags );
+int vofx_reconstruct_host ( vofx_ctx *ctx, int kind, const double *u, const uint8_t *flags, double *halfspaces, int max_iterations );
+int vofx_evolve_host ( vofx_ctx *ctx, const double *halfspaces, const uint8_t *flags, double time, double dt, double *update, double *dt_est );
+int vofx_curvature_host ( vofx_ctx *ctx, const double *u, const double *halfspaces, const uint8_t *flags, double *kappa, uint8_t *valid );
+/* one full loop pass on a host colour function: H2D u, step, D2H u (and flags if non-NULL) */
+int vofx_step_host ( vofx_ctx *ctx, const vofx_step_params *params, double *u, uint8_t *flags );
+
+/* ---- initial data on the device (replaces Average< Problem >, test/average.hh:28-54, i.e.
+ * RecursiveInterpolationCube depth 3, interpolation/recursiveinterpolationcube.hh:33-82, for the built-in problems) */
+int vofx_init ( vofx_ctx *ctx, int problem, double time, double *u );
+
+/* ---- geometry primitives on single cells (DEVICE work on small batches; for parity tests) ---------------------
+ * arrays are HOST pointers of `count` items: lo[count*dim], h[count*dim], ... */
+int vofx_test_locate ( int dim, int64_t count, const double *lo, const double *h, const double *normal, const double *fraction, double *halfspaces );
+int vofx_test_flux ( int dim, int64_t count, const double *lo, const double *h, const int32_t *face, const double *v, const double *halfspaces, double *flux );
+int vofx_test_interface ( int dim, int64_t count, const double *lo, const double *h, const double *halfspaces, int32_t *nverts, double *centroid, double *measure );
+
+/* counters of kernel launches issued by this context since creation (bench.py reports them as gpu_launches) */
+int64_t vofx_launch_count ( const vofx_ctx *ctx );
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* VOFX_H */

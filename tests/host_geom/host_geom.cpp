@@ -1,0 +1,107 @@
+// TEST-ONLY host build of the product's DEVICE geometry headers (dune-vof_b200/csrc/vofx_geom{2d,3d}.cuh).
+// The same functions run on the GPU in the product; compiling them with g++ lets the CPU test-suite check their
+// logic bit-for-bit against the oracle where no GPU exists.  The product never loads this library.
+#include <cstdint>
+
+#include "vofx_geom2d.cuh"
+#include "vofx_geom3d.cuh"
+
+using namespace vofx;
+
+extern "C"
+{
+
+  int hg_locate ( int dim, const double *lo, const double *h, const double *normal, double fraction, double *out )
+  {
+    if( dim == 2 )
+    {
+      Poly2 p;
+      make_cell( lo[ 0 ], lo[ 1 ], h[ 0 ], h[ 1 ], p );
+      out[ 0 ] = normal[ 0 ];
+      out[ 1 ] = normal[ 1 ];
+      out[ 2 ] = locate( p, normal[ 0 ], normal[ 1 ], fraction );
+      return 0;
+    }
+    Hex c;
+    make_cell( lo, h, c );
+    for( int k = 0; k < 3; ++k )
+      out[ k ] = normal[ k ];
+    out[ 3 ] = locate( c, normal, fraction );
+    return 0;
+  }
+
+  int hg_volume_fraction ( int dim, const double *lo, const double *h, const double *hs, double *out )
+  {
+    if( dim == 2 )
+    {
+      Poly2 p;
+      make_cell( lo[ 0 ], lo[ 1 ], h[ 0 ], h[ 1 ], p );
+      const Hs2 H = { hs[ 0 ], hs[ 1 ], hs[ 2 ] };
+      *out = volume_fraction( p, H );
+      return 0;
+    }
+    Hex c;
+    make_cell( lo, h, c );
+    const Hs3 H = { { hs[ 0 ], hs[ 1 ], hs[ 2 ] }, hs[ 3 ] };
+    *out = volume_fraction( c, H );
+    return 0;
+  }
+
+  int hg_flux ( int dim, const double *lo, const double *h, int face, const double *v, const double *hs, double *out )
+  {
+    if( dim == 2 )
+    {
+      const Hs2 H = { hs[ 0 ], hs[ 1 ], hs[ 2 ] };
+      *out = flux( lo[ 0 ], lo[ 1 ], h[ 0 ], h[ 1 ], face, v[ 0 ], v[ 1 ], H );
+      return 0;
+    }
+    const Hs3 H = { { hs[ 0 ], hs[ 1 ], hs[ 2 ] }, hs[ 3 ] };
+    *out = flux( lo, h, face, v, H );
+    return 0;
+  }
+
+  int hg_interface ( int dim, const double *lo, const double *h, const double *hs, int *nverts, double *verts, double *centroid, double *measure )
+  {
+    if( dim == 2 )
+    {
+      Poly2 p;
+      make_cell( lo[ 0 ], lo[ 1 ], h[ 0 ], h[ 1 ], p );
+      const Hs2 H = { hs[ 0 ], hs[ 1 ], hs[ 2 ] };
+      double lx[ 2 ], ly[ 2 ];
+      plane_cut( p, H, lx, ly );
+      *nverts = 2;
+      for( int i = 0; i < 2; ++i )
+      {
+        verts[ 2 * i ] = lx[ i ];
+        verts[ 2 * i + 1 ] = ly[ i ];
+      }
+      centroid[ 0 ] = ( lx[ 0 ] + lx[ 1 ] ) * 0.5;
+      centroid[ 1 ] = ( ly[ 0 ] + ly[ 1 ] ) * 0.5;
+      *measure = norm2( lx[ 0 ] - lx[ 1 ], ly[ 0 ] - ly[ 1 ] );
+      return 0;
+    }
+    Hex c;
+    make_cell( lo, h, c );
+    const Hs3 H = { { hs[ 0 ], hs[ 1 ], hs[ 2 ] }, hs[ 3 ] };
+    Face3 f;
+    plane_cut( c, H, f );
+    *nverts = f.n;
+    for( int i = 0; i < f.n && i < 8; ++i )
+      for( int d = 0; d < 3; ++d )
+        verts[ 3 * i + d ] = f.v[ i ][ d ];
+    if( f.n > 2 )
+    {
+      face_centroid( f, centroid );
+      *measure = face_measure( f );
+    }
+    else
+    {
+      centroid[ 0 ] = centroid[ 1 ] = centroid[ 2 ] = 0.0;
+      *measure = 0.0;
+    }
+    return 0;
+  }
+
+  double hg_det_cospi ( double s ) { return det_cospi( s ); }
+
+} // extern "C"

@@ -1,0 +1,112 @@
+"""The product's DEVICE geometry functions (dune-vof_b200/csrc/vofx_geom{2d,3d}.cuh), compiled for the host by
+tests/host_geom (test-only), against the oracle: bit-exact on seeded inputs incl. degenerate normals.
+This checks the kernels' logic where no GPU exists; the GPU tests repeat it on the device.  CPU only."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import oraclelib as O
+from util import ROOT, same_bits
+
+HG = os.path.join(ROOT, "tests", "host_geom")
+
+
+@pytest.fixture(scope="module")
+def hg():
+    subprocess.check_call(["make", "-s", "-f", os.path.join(HG, "Makefile")], cwd=ROOT)
+    L = C.CDLL(os.path.join(HG, "libhostgeom.so"))
+    L.hg_det_cospi.restype = C.c_double
+    L.hg_det_cospi.argtypes = [C.c_double]
+    return L
+
+
+def _d(a):
+    return C.c_void_p(a.ctypes.data)
+
+
+def _v(x):
+    return np.ascontiguousarray(np.asarray(x, dtype=np.float64))
+
+
+def hg_locate(L, lo, h, n, f):
+    lo, h, n = _v(lo), _v(h), _v(n)
+    out = np.empty(len(lo) + 1)
+    L.hg_locate(len(lo), _d(lo), _d(h), _d(n), C.c_double(f), _d(out))
+    return out
+
+
+def hg_flux(L, lo, h, face, vel, hs):
+    lo, h, vel, hs = _v(lo), _v(h), _v(vel), _v(hs)
+    out = C.c_double(0)
+    L.hg_flux(len(lo), _d(lo), _d(h), int(face), _d(vel), _d(hs), C.byref(out))
+    return out.value
+
+
+def hg_vf(L, lo, h, hs):
+    lo, h, hs = _v(lo), _v(h), _v(hs)
+    out = C.c_double(0)
+    L.hg_volume_fraction(len(lo), _d(lo), _d(h), _d(hs), C.byref(out))
+    return out.value
+
+
+def hg_iface(L, lo, h, hs):
+    lo, h, hs = _v(lo), _v(h), _v(hs)
+    dim = len(lo)
+    nv = C.c_int(0)
+    verts = np.zeros(16 * dim)
+    cen = np.zeros(dim)
+    m = C.c_double(0)
+    L.hg_interface(dim, _d(lo), _d(h), _d(hs), C.byref(nv), _d(verts), _d(cen), C.byref(m))
+    return nv.value, verts.reshape(16, dim)[: min(nv.value, 8)].copy(), cen, m.value
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_geometry_bit_exact(hg, dim):
+    rng = np.random.default_rng(70 + dim)
+    for it in range(6000):
+        res = int(rng.choice([64, 128, 512, 1024, 4096, 100, 37]))
+        h = np.full(dim, 1.0 / res)
+        lo = rng.integers(0, res, dim) * h
+        n = rng.normal(size=dim)
+        mode = it % 12
+        if mode == 1:
+            n[rng.integers(0, dim)] = 0
+        if mode == 2:
+            n[rng.integers(0, dim)] *= 1e-9
+        if mode == 3:
+            k = rng.integers(0, dim); n[:] = 0; n[k] = rng.choice([-1.0, 1.0])
+        if mode == 4:
+            n = rng.choice([-1.0, 1.0], size=dim)
+        if mode == 6 and dim == 3:   # SURVEY.md hard part 1(iii): nearly axis-aligned normals
+            k = rng.integers(0, 3); n[:] = 0; n[k] = rng.choice([-1, 1])
+            n[(k + 1) % 3] = rng.choice([-1, 1]) * 10.0 ** rng.uniform(-17, -5)
+            if it % 2:
+                n[(k + 2) % 3] = rng.choice([-1, 1]) * 10.0 ** rng.uniform(-17, -5)
+        n /= np.linalg.norm(n)
+        f = rng.random()
+        if mode == 5:
+            f = float(rng.choice([0.0, 1.0, 1e-7, 1 - 1e-7, 1e-6, 0.5, 1.2, -0.1]))
+        a = O.locate(lo, h, n, f)
+        assert same_bits(a, hg_locate(hg, lo, h, n, f)), (dim, mode, lo, h, n, f)
+        hs = a.copy()
+        if np.isnan(hs[-1]):
+            hs[-1] = -np.dot(n, lo + 0.5 * h)
+        if it % 5 == 0:
+            hs[-1] += rng.normal() * h[0]
+        face = int(rng.integers(0, 2 * dim))
+        vel = rng.normal(size=dim) * h[0] * 0.5
+        if it % 11 == 3:
+            vel[rng.integers(0, dim)] = 0
+        assert same_bits(O.flux(lo, h, face, vel, hs), hg_flux(hg, lo, h, face, vel, hs))
+        assert same_bits(O.volume_fraction(lo, h, hs), hg_vf(hg, lo, h, hs))
+        na, va, ca, ma = O.interface(lo, h, hs)
+        nb, vb, cb, mb = hg_iface(hg, lo, h, hs)
+        assert na == nb and same_bits(va, vb) and same_bits(ca, cb) and same_bits(ma, mb)
+
+
+def test_det_cospi_matches_oracle(hg):
+    for s in np.linspace(-2.0, 5.0, 2001):
+        assert hg.hg_det_cospi(float(s)) == O.det_cospi(float(s))
