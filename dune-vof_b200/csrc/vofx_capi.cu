@@ -67,6 +67,14 @@ struct vofx_ctx
   unsigned char *dFlags = nullptr, *dValid = nullptr;
 
   long long launches = 0;
+
+  // optional per-kernel timing (vofx_profile_*): one CUDA event pair per launch, on the launching stream
+  bool profiling = false;
+  std::vector< cudaEvent_t > eventPool;
+  size_t eventsUsed = 0;
+  struct ProfEntry { const char *name; cudaEvent_t begin, end; };
+  std::vector< ProfEntry > profEntries;
+  cudaEvent_t pendingBegin = nullptr;
 };
 
 namespace
@@ -89,9 +97,42 @@ namespace
     return (int) need;
   }
 
+  cudaEvent_t takeEvent ( vofx_ctx *ctx )
+  {
+    if( ctx->eventsUsed == ctx->eventPool.size() )
+    {
+      cudaEvent_t e = nullptr;
+      if( cudaEventCreate( &e ) != cudaSuccess )
+        return nullptr;
+      ctx->eventPool.push_back( e );
+    }
+    return ctx->eventPool[ ctx->eventsUsed++ ];
+  }
+
+  // call directly before a kernel launch; checkLaunch() closes the pair
+  void profBegin ( vofx_ctx *ctx )
+  {
+    ctx->pendingBegin = nullptr;
+    if( !ctx->profiling )
+      return;
+    ctx->pendingBegin = takeEvent( ctx );
+    if( ctx->pendingBegin )
+      cudaEventRecord( ctx->pendingBegin, ctx->stream );
+  }
+
   int checkLaunch ( vofx_ctx *ctx, const char *what )
   {
     ctx->launches++;
+    if( ctx->profiling && ctx->pendingBegin )
+    {
+      cudaEvent_t end = takeEvent( ctx );
+      if( end )
+      {
+        cudaEventRecord( end, ctx->stream );
+        ctx->profEntries.push_back( { what, ctx->pendingBegin, end } );
+      }
+      ctx->pendingBegin = nullptr;
+    }
     const cudaError_t e = cudaGetLastError();
     if( e != cudaSuccess )
       return fail( VOFX_ERR_CUDA, std::string( what ) + ": " + cudaGetErrorString( e ) );
@@ -127,6 +168,7 @@ namespace
     const Grid &g = ctx->grid;
     const long long quads = ( g.cells + 3 ) / 4;
     const int blocks = gridBlocks( ctx, quads, 256, 8 );
+    profBegin( ctx );
     if( g.dim == 2 )
       k_flag_compact< 2 ><<< blocks, 256, 0, ctx->stream >>>( g, u, eps, flags, ctx->mixedList, ctx->slot, ctx->capacity, ctx->state, compact ? 1 : 0 );
     else
@@ -136,6 +178,7 @@ namespace
 
   int launchResetCounters ( vofx_ctx *ctx )
   {
+    profBegin( ctx );
     k_reset_counters<<< 1, 1, 0, ctx->stream >>>( ctx->state );
     return checkLaunch( ctx, "k_reset_counters" );
   }
@@ -144,6 +187,7 @@ namespace
   {
     const Grid &g = ctx->grid;
     const int blocks = gridBlocks( ctx, g.cells, 256, 8 );
+    profBegin( ctx );
     if( g.dim == 2 )
       k_compact_flags< 2 ><<< blocks, 256, 0, ctx->stream >>>( g, flags, ctx->mixedList, ctx->slot, ctx->capacity, ctx->state );
     else
@@ -155,6 +199,7 @@ namespace
   {
     const Grid &g = ctx->grid;
     const int blocks = ctx->numSMs * 8;
+    profBegin( ctx );
     if( g.dim == 2 )
       k_youngs< 2 ><<< blocks, 128, 0, ctx->stream >>>( g, u, ctx->mixedList, ctx->state, ctx->capacity, hs );
     else
@@ -164,6 +209,7 @@ namespace
       return rc;
     if( kind == VOFX_RECON_HF )
     {
+      profBegin( ctx );
       if( g.dim == 2 )
         k_hf< 2 ><<< blocks, 128, 0, ctx->stream >>>( g, u, ctx->mixedList, ctx->state, ctx->capacity, hs );
       else
@@ -172,6 +218,7 @@ namespace
     }
     else if( kind == VOFX_RECON_SWARTZ )
     {
+      profBegin( ctx );
       if( g.dim == 2 )
         k_swartz< 2 ><<< ctx->numSMs * 16, 64, 0, ctx->stream >>>( g, u, flags, ctx->mixedList, ctx->state, ctx->capacity, hs, maxIterations );
       else
@@ -187,6 +234,7 @@ namespace
   {
     const Grid &g = ctx->grid;
     const int blocks = ctx->numSMs * 8;
+    profBegin( ctx );
     if( g.dim == 2 )
       k_flux< 2 ><<< blocks, 128, 0, ctx->stream >>>( g, ctx->velDev, hs, flags, ctx->mixedList, ctx->state, ctx->capacity, ctx->records, timeOverride, dtOverride );
     else
@@ -198,6 +246,7 @@ namespace
   {
     const Grid &g = ctx->grid;
     const int blocks = ctx->numSMs * 8;
+    profBegin( ctx );
     if( g.dim == 2 )
       k_update< 2 ><<< blocks, 128, 0, ctx->stream >>>( g, flags, ctx->mixedList, ctx->slot, ctx->state, ctx->capacity, ctx->records, target, accumulate ? 1 : 0 );
     else
@@ -213,6 +262,7 @@ namespace
     VOFX_CUDA( cudaMemsetAsync( kappa, 0, sizeof( double ) * (size_t) g.cells, ctx->stream ) );
     if( valid )
       VOFX_CUDA( cudaMemsetAsync( valid, 0, (size_t) g.cells, ctx->stream ) );
+    profBegin( ctx );
     if( g.dim == 2 )
       k_curvature_local< 2 ><<< blocks, 128, 0, ctx->stream >>>( g, u, hs, ctx->mixedList, ctx->state, ctx->capacity, ctx->curv1, ctx->ok1 );
     else
@@ -220,6 +270,7 @@ namespace
     int rc = checkLaunch( ctx, "k_curvature_local" );
     if( rc )
       return rc;
+    profBegin( ctx );
     if( g.dim == 2 )
       k_curvature_average< 2 ><<< blocks, 128, 0, ctx->stream >>>( g, flags, ctx->mixedList, ctx->slot, ctx->state, ctx->capacity, ctx->curv1, ctx->ok1, kappa, valid );
     else
@@ -420,6 +471,8 @@ extern "C"
     cudaFree( ctx->dValid );
     if( ctx->pinned )
       cudaFreeHost( ctx->pinned );
+    for( cudaEvent_t e : ctx->eventPool )
+      cudaEventDestroy( e );
     delete ctx;
   }
 
@@ -434,6 +487,52 @@ extern "C"
   int64_t vofx_cells ( const vofx_ctx *ctx ) { return ctx ? (int64_t) ctx->grid.cells : 0; }
 
   int64_t vofx_launch_count ( const vofx_ctx *ctx ) { return ctx ? (int64_t) ctx->launches : 0; }
+
+  int vofx_profile_enable ( vofx_ctx *ctx, int enable )
+  {
+    if( !ctx )
+      return fail( VOFX_ERR_ARGUMENT, "null context" );
+    ctx->profiling = enable != 0;
+    ctx->profEntries.clear();
+    ctx->eventsUsed = 0;
+    return VOFX_OK;
+  }
+
+  int vofx_profile_read ( vofx_ctx *ctx, int max_entries, char *names, double *total_ms, int64_t *launches, int *n_entries )
+  {
+    if( !ctx || !names || !total_ms || !launches || !n_entries || max_entries < 1 )
+      return fail( VOFX_ERR_ARGUMENT, "bad argument" );
+    int rc = setDevice( ctx );
+    if( rc )
+      return rc;
+    VOFX_CUDA( cudaStreamSynchronize( ctx->stream ) );
+    int n = 0;
+    for( const auto &entry : ctx->profEntries )
+    {
+      float ms = 0.0f;
+      VOFX_CUDA( cudaEventElapsedTime( &ms, entry.begin, entry.end ) );
+      int k = 0;
+      for( ; k < n; ++k )
+        if( std::strncmp( names + 48 * k, entry.name, 47 ) == 0 )
+          break;
+      if( k == n )
+      {
+        if( n == max_entries )
+          continue;
+        std::strncpy( names + 48 * k, entry.name, 47 );
+        names[ 48 * k + 47 ] = 0;
+        total_ms[ k ] = 0.0;
+        launches[ k ] = 0;
+        n++;
+      }
+      total_ms[ k ] += ms;
+      launches[ k ]++;
+    }
+    *n_entries = n;
+    ctx->profEntries.clear();
+    ctx->eventsUsed = 0;
+    return VOFX_OK;
+  }
 
   // ---- velocity -----------------------------------------------------------------------------------------------------
 
@@ -642,6 +741,7 @@ extern "C"
     int rc = setDevice( ctx );
     if( rc )
       return rc;
+    profBegin( ctx );
     k_axpy<<< gridBlocks( ctx, ctx->grid.cells, 256, 8 ), 256, 0, ctx->stream >>>( ctx->grid.cells, u, a, x );
     return checkLaunch( ctx, "k_axpy" );
   }
@@ -702,6 +802,7 @@ extern "C"
     int rc = setDevice( ctx );
     if( rc )
       return rc;
+    profBegin( ctx );
     k_finalize<<< 1, 1, 0, ctx->stream >>>( ctx->state, p->cfl );
     return checkLaunch( ctx, "k_finalize" );
   }

@@ -24,7 +24,8 @@ SYMBOLS = [
     "vofx_flag", "vofx_reconstruct", "vofx_evolve", "vofx_axpy", "vofx_curvature", "vofx_step_begin", "vofx_step",
     "vofx_step_state", "vofx_step_local", "vofx_step_finish", "vofx_dt_est_device", "vofx_flag_host",
     "vofx_reconstruct_host", "vofx_evolve_host", "vofx_curvature_host", "vofx_step_host", "vofx_init",
-    "vofx_test_locate", "vofx_test_flux", "vofx_test_interface", "vofx_launch_count",
+    "vofx_test_locate", "vofx_test_flux", "vofx_test_interface", "vofx_launch_count", "vofx_profile_enable",
+    "vofx_profile_read",
 ]
 
 
@@ -103,6 +104,8 @@ def load():
     L.vofx_curvature_host.argtypes = [vp, dp, dp, bp, dp, bp]
     L.vofx_step_host.argtypes = [vp, C.POINTER(StepParams), dp, bp]
     L.vofx_init.argtypes = [vp, C.c_int, C.c_double, dp]
+    L.vofx_profile_enable.argtypes = [vp, C.c_int]
+    L.vofx_profile_read.argtypes = [vp, C.c_int, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int)]
     L.vofx_test_locate.argtypes = [C.c_int, C.c_int64, dp, dp, dp, dp, dp]
     L.vofx_test_flux.argtypes = [C.c_int, C.c_int64, dp, dp, ip, dp, dp, dp]
     L.vofx_test_interface.argtypes = [C.c_int, C.c_int64, dp, dp, dp, ip, dp, dp]

@@ -175,6 +175,12 @@ int vofx_test_interface ( int dim, int64_t count, const double *lo, const double
 /* counters of kernel launches issued by this context since creation (bench.py reports them as gpu_launches) */
 int64_t vofx_launch_count ( const vofx_ctx *ctx );
 
+/* per-kernel device timing for the roofline report: while enabled, every kernel launch of the context is bracketed
+ * by a CUDA event pair on the launching stream.  vofx_profile_read synchronises and returns, per kernel name
+ * (names: max_entries rows of 48 chars), the summed duration in ms and the number of launches, then clears. */
+int vofx_profile_enable ( vofx_ctx *ctx, int enable );
+int vofx_profile_read ( vofx_ctx *ctx, int max_entries, char *names, double *total_ms, int64_t *launches, int *n_entries );
+
 #ifdef __cplusplus
 }
 #endif

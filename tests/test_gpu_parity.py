@@ -35,12 +35,14 @@ def test_primitives_against_golden(dim):
     n = len(g["fraction"])
     lo, h = np.ascontiguousarray(g["lo"]), np.ascontiguousarray(g["h"])
     out = np.empty((n, dim + 1))
-    vlib.check(L.vofx_test_locate(dim, n, _p(lo), _p(h), _p(np.ascontiguousarray(g["normal"])), _p(np.ascontiguousarray(g["fraction"])), _p(out)))
+    normal, fraction = np.ascontiguousarray(g["normal"]), np.ascontiguousarray(g["fraction"])   # keep alive across the call
+    vlib.check(L.vofx_test_locate(dim, n, _p(lo), _p(h), _p(normal), _p(fraction), _p(out)))
     assert n_mismatch(out, g["hs_located"]) == 0
     hs = np.ascontiguousarray(g["hs"])
     flux = np.empty(n)
     face = np.ascontiguousarray(g["face"], dtype=np.int32)
-    vlib.check(L.vofx_test_flux(dim, n, _p(lo), _p(h), _p(face), _p(np.ascontiguousarray(g["v"])), _p(hs), _p(flux)))
+    vel = np.ascontiguousarray(g["v"])
+    vlib.check(L.vofx_test_flux(dim, n, _p(lo), _p(h), _p(face), _p(vel), _p(hs), _p(flux)))
     assert n_mismatch(flux, g["flux"]) == 0
     nv = np.empty(n, dtype=np.int32); cen = np.empty((n, dim)); meas = np.empty(n)
     vlib.check(L.vofx_test_interface(dim, n, _p(lo), _p(h), _p(hs), _p(nv), _p(cen), _p(meas)))
