@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py -- VoF cell-steps/sec of the per-timestep hot path (flag -> reconstruct -> flux/evolve -> update).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl vofx|reference]
+    (N > 1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...)
+
+Workload (BASELINE.json `metric`, configs[2]): 3D sphere (R = 0.15) in the LeVeque deformation field on a 512^3
+Cartesian grid, Young's reconstruction, eps 1e-6, cfl 0.5, fp64.  A step is one pass of the time loop
+(dune/vof/algorithm.hh:68-95 without l1error/output) over the whole grid.  N > 1 is WEAK scaling: every GPU owns one
+512 x 512 x 512 slab of a 512 x 512 x 512N grid (z-slabs, 2-layer colour halos over NCCL, one MIN all-reduce); the
+LeVeque field is 1-periodic in z and every slab starts with its own sphere, so all GPUs carry the same band load.
+
+Prints ONE JSON line (rank 0).  `value` = cells x steps / device time (inputs resident in HBM), `e2e` = the same
+through the host-buffer C-ABI call with H2D/D2H copies of the colour function inside the timed region,
+`roofline` for the dominant kernel (dense flag/compact pass), `cpu_baseline` = the reference's own CPU templates
+(oracle/_ref, or the plain-C port if that is absent) on this box's host cores on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_SIDE = int(os.environ.get("VOFX_BENCH_N", "512"))          # cells per axis of one slab
+CPU_SAMPLE_N = int(os.environ.get("VOFX_BENCH_CPU_N", "128"))  # the reference needs >= 624 B/cell: 512^3 does not fit any host
+EPS, CFL = 1e-6, 0.5
+SURVEY_BYTES_PER_CELL_STEP = 17      # read u (8) + write u' (8) + write flag (1)
+FLAG_KERNEL_BYTES_PER_CELL = 9       # what the dense kernel itself must move: read u (8) + write flag (1)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """polls SM clock and throttle reasons through NVML while the timed region runs"""
+
+    def __init__(self, index, period=0.005):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2.0)
+
+    def report(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def cpu_reference_run(passes, warm, n_side=CPU_SAMPLE_N):
+    """the reference's own CPU implementation (oracle/_ref = /root/reference's templates, 1 thread: the reference has no
+    threading and MPI is absent), or the plain-C port when the prebuilt harness is absent.  Returns (value, info)."""
+    from oracle import oraclelib as O
+    from oracle import reflib as R
+    n = (n_side,) * 3
+    if R.available():
+        kind, grid, mod = "reference", R.RefGrid(n), R
+    else:
+        kind, grid, mod = "port", O.OracleGrid(n), O
+    u = grid.init(mod.PROB_LEVEQUE)
+    t = dt = 0.0
+    if warm > 0:
+        u, t, dt, _, _ = grid.run(mod.RECON_YOUNGS, mod.PROB_LEVEQUE, EPS, CFL, warm, u, t, dt)
+    t0 = time.perf_counter()
+    u, t, dt, phases, mixed = grid.run(mod.RECON_YOUNGS, mod.PROB_LEVEQUE, EPS, CFL, passes, u, t, dt)
+    wall = time.perf_counter() - t0
+    cells = n_side ** 3
+    value = cells * passes / wall
+    info = {"value": value, "unit": "cell-steps/s", "cores": 1, "kind": kind,
+            "sample": f"{n_side}^3 grid of the same problem (sphere in LeVeque field, Young's), {passes} loop passes after "
+                      f"{warm} warm-up passes; the reference stores >= 624 B/cell of stencil entities, so 512^3 does not fit a host",
+            "host_cores_available": os.cpu_count(), "seconds": wall, "mixed_cells_per_step": mixed / max(passes, 1),
+            "phase_seconds": {"flag": phases[0], "reconstruct": phases[1], "evolve": phases[2], "axpy": phases[3]}}
+    return value, info
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    steps = min(args.steps, 40)
+    warm = max(1, min(args.warmup, 5))
+    value, info = cpu_reference_run(steps, warm)
+    line = {
+        "impl": "reference",
+        "metric": "VoF cell-steps/sec (reconstruct+advect)", "value": value, "unit": "cell-steps/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": 1e3 * info["seconds"] / steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "3D sphere in LeVeque deformation field, Young's reconstruction, eps 1e-6, cfl 0.5 "
+                               f"(configs[2]); CPU sample on {CPU_SAMPLE_N}^3 per step",
+                   "grid": [CPU_SAMPLE_N] * 3},
+        "cpu_baseline": info,
+        "e2e": {"value": value, "unit": "cell-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="vofx", choices=["vofx", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device: vofx has no CPU fallback"}))
+        return 2
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    import dune_vof_b200.operators as ops
+    from dune_vof_b200.decomposition import SlabAlgorithm
+    from dune_vof_b200 import lib as vlib
+
+    W = max(3, args.warmup)
+    K = max(1, args.steps)
+    n_global = (N_SIDE, N_SIDE, N_SIDE * world)
+    h = (1.0 / N_SIDE,) * 3
+    slab = SlabAlgorithm(n_global, rank, world, CFL, EPS, ops.RECON_YOUNGS, h=h, device=local_rank)
+    grid = slab.grid
+    grid.set_velocity_builtin(ops.PROB_LEVEQUE)
+    grid.use_current_stream()
+
+    # initial data: every slab is a copy of the unit-cube problem (sphere at (0.35,0.35,0.35) + k e_z)
+    unit = ops.CartesianGrid((N_SIDE,) * 3, h=h, device=local_rank)
+    u_unit = unit.init(ops.PROB_LEVEQUE)
+    uh = grid.empty("color")
+    slab.owned(uh).copy_(u_unit.view(N_SIDE, -1))
+    del u_unit
+    unit.close()
+    cells_per_gpu = N_SIDE ** 3
+    total_cells = cells_per_gpu * world
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    slab.begin(0.0, 0.0)
+    for _ in range(W):
+        slab.step(uh)
+    sync_all()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = grid.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    ev0.record()
+    for _ in range(K):
+        slab.step(uh)
+    ev1.record()
+    sync_all()
+    ms = ev0.elapsed_time(ev1)
+    launches = grid.launch_count - launches0
+    state = slab.state()
+
+    # per-kernel device times of the same workload (separate pass: the event pairs perturb the headline slightly)
+    L = grid._L
+    vlib.check(L.vofx_profile_enable(grid._ctx, 1))
+    KP = min(K, 50)
+    for _ in range(KP):
+        slab.step(uh)
+    names = C.create_string_buffer(48 * 32)
+    tot = (C.c_double * 32)()
+    cnt = (C.c_int64 * 32)()
+    nent = C.c_int(0)
+    vlib.check(L.vofx_profile_read(grid._ctx, 32, names, tot, cnt, C.byref(nent)))
+    vlib.check(L.vofx_profile_enable(grid._ctx, 0))
+    sampler.stop()
+    kernels = {}
+    for i in range(nent.value):
+        nm = names.raw[48 * i:48 * (i + 1)].split(b"\0", 1)[0].decode()
+        kernels[nm] = {"avg_ms": tot[i] / max(cnt[i], 1), "launches_per_step": cnt[i] / KP}
+    step_ms_profiled = sum(k["avg_ms"] * k["launches_per_step"] for k in kernels.values())
+    for k in kernels.values():
+        k["share"] = (k["avg_ms"] * k["launches_per_step"]) / step_ms_profiled if step_ms_profiled > 0 else None
+
+    if world > 1:
+        tms = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+        ln = torch.tensor([launches], dtype=torch.float64, device="cuda")
+        dist.all_reduce(ln, op=dist.ReduceOp.SUM)
+        launches = int(ln.item())
+    value = total_cells * K / (ms * 1e-3)
+
+    # end to end through the host-buffer C ABI: H2D colour, one loop pass, D2H colour, every step
+    e2e = None
+    if world == 1:
+        host_u = torch.empty(grid.cells, dtype=torch.float64).pin_memory()
+        host_u.copy_(uh)
+        torch.cuda.synchronize()
+        p = slab.alg.params
+        KE = max(1, args.e2e_steps)
+        vlib.check(L.vofx_step_host(grid._ctx, C.byref(p), C.c_void_p(host_u.data_ptr()), None))   # warm-up (allocates mirrors)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(KE):
+            vlib.check(L.vofx_step_host(grid._ctx, C.byref(p), C.c_void_p(host_u.data_ptr()), None))
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        e2e = {"value": total_cells * KE / wall, "unit": "cell-steps/s", "h2d_bytes_per_step": 8 * grid.cells,
+               "d2h_bytes_per_step": 8 * grid.cells, "steps": KE, "ms_per_step": 1e3 * wall / KE,
+               "api": "vofx_step_host (pinned host colour function in, colour function out)"}
+    else:
+        e2e = {"value": None, "unit": "cell-steps/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
+               "note": "measured at N=1 only"}
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = measured_peaks()
+    flag = kernels.get("k_flag_compact")
+    roofline = None
+    if flag:
+        achieved = FLAG_KERNEL_BYTES_PER_CELL * cells_per_gpu / (flag["avg_ms"] * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "k_flag_compact", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_cell": FLAG_KERNEL_BYTES_PER_CELL,
+                    "kernel_avg_ms": flag["avg_ms"], "kernel_share_of_step": flag["share"],
+                    "note": "dense pass reads u (8 B) and writes the flag (1 B); the u' write of SURVEY 8(d)'s 17 B/cell-step "
+                            "is elided by the in-place band update (k_update)",
+                    "whole_step_equivalent_frac_at_17B": (value / world) * SURVEY_BYTES_PER_CELL_STEP / 1e9 / peak}
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            _, cpu_baseline = cpu_reference_run(passes=12, warm=2)
+        except Exception as exc:   # the checker must never take the bench down
+            cpu_baseline = {"value": None, "error": repr(exc)}
+
+    line = {
+        "metric": "VoF cell-steps/sec (reconstruct+advect)", "value": value, "unit": "cell-steps/s",
+        "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "3D sphere (R=0.15) in LeVeque deformation field, Young's reconstruction, eps 1e-6, cfl 0.5 (configs[2])",
+                   "grid": list(n_global), "cells_per_gpu": cells_per_gpu, "decomposition": f"z-slabs x{world}",
+                   "l2": "inputs larger than L2 (colour function 1.07 GB per GPU vs 126 MB L2)",
+                   "mixed_cells_last_step_rank0": state.mixed_cells, "time": state.time, "dt": state.dt},
+        "clocks": sampler.report(),
+        "e2e": e2e,
+        "gpu_launches": launches,
+        "kernels": kernels,
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

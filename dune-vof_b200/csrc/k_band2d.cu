@@ -1,0 +1,26 @@
+// vofx: launchers of band kernels (see vofx_launch.h); generated layout, one group of kernels per translation unit.
+#include "vofx_launch.h"
+#include "vofx_kernels.cuh"
+
+namespace vofx
+{
+  namespace launch
+  {
+    void youngs2 ( int blocks, cudaStream_t s, Grid g, const double *u, const int *mixedList, const StepState *state, int capacity, double *hs )
+    { k_youngs< 2 ><<< blocks, 128, 0, s >>>( g, u, mixedList, state, capacity, hs ); }
+    void hf2 ( int blocks, cudaStream_t s, Grid g, const double *u, const int *mixedList, const StepState *state, int capacity, double *hs )
+    { k_hf< 2 ><<< blocks, 128, 0, s >>>( g, u, mixedList, state, capacity, hs ); }
+    void swartz2 ( int blocks, cudaStream_t s, Grid g, const double *u, const unsigned char *flags, const int *mixedList, const StepState *state,
+                   int capacity, double *hs, int maxIterations )
+    { k_swartz< 2 ><<< blocks, 64, 0, s >>>( g, u, flags, mixedList, state, capacity, hs, maxIterations ); }
+    void flux2 ( int blocks, cudaStream_t s, Grid g, const Velocity *velocity, const double *hs, const unsigned char *flags, const int *mixedList,
+                 StepState *state, int capacity, FluxRecord *records, const double *timeOverride, const double *dtOverride )
+    { k_flux< 2 ><<< blocks, 128, 0, s >>>( g, velocity, hs, flags, mixedList, state, capacity, records, timeOverride, dtOverride ); }
+    void test_locate2 ( int blocks, long long count, const double *lo, const double *h, const double *normal, const double *fraction, double *out )
+    { k_test_locate< 2 ><<< blocks, 64 >>>( count, lo, h, normal, fraction, out ); }
+    void test_flux2 ( int blocks, long long count, const double *lo, const double *h, const int *face, const double *v, const double *hs, double *out )
+    { k_test_flux< 2 ><<< blocks, 64 >>>( count, lo, h, face, v, hs, out ); }
+    void test_interface2 ( int blocks, long long count, const double *lo, const double *h, const double *hs, int *nverts, double *centroid, double *measure )
+    { k_test_interface< 2 ><<< blocks, 64 >>>( count, lo, h, hs, nverts, centroid, measure ); }
+  } // namespace launch
+} // namespace vofx

@@ -1,0 +1,71 @@
+// vofx: launchers of the dense / bookkeeping kernels (flags + compaction, gather update, curvature, init).
+#include "vofx_launch.h"
+#include "vofx_kernels.cuh"
+
+namespace vofx
+{
+  namespace launch
+  {
+    void flag_rows ( int dim, int blocks, cudaStream_t s, Grid g, const double *u, double eps, unsigned char *flags, int *mixedList, int *slot,
+                     int capacity, StepState *state, int compact, int rowsPerBlock )
+    {
+      if( dim == 2 )
+        k_flag_rows< 2 ><<< blocks, 128, 0, s >>>( g, u, eps, flags, mixedList, slot, capacity, state, compact, rowsPerBlock );
+      else
+        k_flag_rows< 3 ><<< blocks, 128, 0, s >>>( g, u, eps, flags, mixedList, slot, capacity, state, compact, rowsPerBlock );
+    }
+    void flag_compact ( int dim, int blocks, cudaStream_t s, Grid g, const double *u, double eps, unsigned char *flags, int *mixedList, int *slot,
+                        int capacity, StepState *state, int compact )
+    {
+      if( dim == 2 )
+        k_flag_compact< 2 ><<< blocks, 256, 0, s >>>( g, u, eps, flags, mixedList, slot, capacity, state, compact );
+      else
+        k_flag_compact< 3 ><<< blocks, 256, 0, s >>>( g, u, eps, flags, mixedList, slot, capacity, state, compact );
+    }
+    void compact_flags ( int dim, int blocks, cudaStream_t s, Grid g, const unsigned char *flags, int *mixedList, int *slot, int capacity, StepState *state )
+    {
+      if( dim == 2 )
+        k_compact_flags< 2 ><<< blocks, 256, 0, s >>>( g, flags, mixedList, slot, capacity, state );
+      else
+        k_compact_flags< 3 ><<< blocks, 256, 0, s >>>( g, flags, mixedList, slot, capacity, state );
+    }
+    void update ( int dim, int blocks, cudaStream_t s, Grid g, const unsigned char *flags, const int *mixedList, const int *slot, const StepState *state,
+                  int capacity, const FluxRecord *records, double *target, int accumulate )
+    {
+      if( dim == 2 )
+        k_update< 2 ><<< blocks, 128, 0, s >>>( g, flags, mixedList, slot, state, capacity, records, target, accumulate );
+      else
+        k_update< 3 ><<< blocks, 128, 0, s >>>( g, flags, mixedList, slot, state, capacity, records, target, accumulate );
+    }
+    void curvature_local ( int dim, int blocks, cudaStream_t s, Grid g, const double *u, const double *hs, const int *mixedList, const StepState *state,
+                           int capacity, double *curv1, unsigned char *ok1 )
+    {
+      if( dim == 2 )
+        k_curvature_local< 2 ><<< blocks, 128, 0, s >>>( g, u, hs, mixedList, state, capacity, curv1, ok1 );
+      else
+        k_curvature_local< 3 ><<< blocks, 128, 0, s >>>( g, u, hs, mixedList, state, capacity, curv1, ok1 );
+    }
+    void curvature_average ( int dim, int blocks, cudaStream_t s, Grid g, const unsigned char *flags, const int *mixedList, const int *slot,
+                             const StepState *state, int capacity, const double *curv1, const unsigned char *ok1, double *kappa, unsigned char *valid )
+    {
+      if( dim == 2 )
+        k_curvature_average< 2 ><<< blocks, 128, 0, s >>>( g, flags, mixedList, slot, state, capacity, curv1, ok1, kappa, valid );
+      else
+        k_curvature_average< 3 ><<< blocks, 128, 0, s >>>( g, flags, mixedList, slot, state, capacity, curv1, ok1, kappa, valid );
+    }
+    void finalize ( cudaStream_t s, StepState *state, double cfl ) { k_finalize<<< 1, 1, 0, s >>>( state, cfl ); }
+    void reset_counters ( cudaStream_t s, StepState *state ) { k_reset_counters<<< 1, 1, 0, s >>>( state ); }
+    void axpy ( int blocks, cudaStream_t s, long long n, double *u, double a, const double *x ) { k_axpy<<< blocks, 256, 0, s >>>( n, u, a, x ); }
+    void init ( int dim, int blocks, cudaStream_t s, Grid g, Indicator I, double *u )
+    {
+      if( dim == 2 )
+        k_init< 2 ><<< blocks, 128, 0, s >>>( g, I, u );
+      else
+        k_init< 3 ><<< blocks, 128, 0, s >>>( g, I, u );
+    }
+    void test_face_velocity ( cudaStream_t s, Grid g, const Velocity *velocity, double time, long long cell, int face, double *out )
+    {
+      k_test_face_velocity<<< 1, 1, 0, s >>>( g, velocity, time, cell, face, out );
+    }
+  } // namespace launch
+} // namespace vofx

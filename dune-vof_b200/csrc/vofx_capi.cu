@@ -9,7 +9,7 @@
 #include <string>
 #include <vector>
 
-#include "vofx_kernels.cuh"
+#include "vofx_launch.h"
 
 using namespace vofx;
 
@@ -166,20 +166,26 @@ namespace
   int launchFlag ( vofx_ctx *ctx, const double *u, double eps, unsigned char *flags, bool compact )
   {
     const Grid &g = ctx->grid;
+    profBegin( ctx );
+    if( ( g.ns[ 0 ] & 3 ) == 0 && ( reinterpret_cast< uintptr_t >( u ) & 15 ) == 0 && ( reinterpret_cast< uintptr_t >( flags ) & 3 ) == 0 )
+    {
+      // row kernel: blocks of 128 threads walk 4 rows each (grid >> 148 SMs x resident blocks on every production size)
+      const int nRows = g.ns[ 1 ] * g.ns[ 2 ];
+      const int rowsPerBlock = ( nRows >= 8 * ctx->numSMs * 16 ) ? 4 : 1;
+      const int blocks = ( nRows + rowsPerBlock - 1 ) / rowsPerBlock;
+      launch::flag_rows( g.dim, blocks, ctx->stream, g, u, eps, flags, ctx->mixedList, ctx->slot, ctx->capacity, ctx->state, compact ? 1 : 0, rowsPerBlock );
+      return checkLaunch( ctx, "k_flag_compact" );
+    }
     const long long quads = ( g.cells + 3 ) / 4;
     const int blocks = gridBlocks( ctx, quads, 256, 8 );
-    profBegin( ctx );
-    if( g.dim == 2 )
-      k_flag_compact< 2 ><<< blocks, 256, 0, ctx->stream >>>( g, u, eps, flags, ctx->mixedList, ctx->slot, ctx->capacity, ctx->state, compact ? 1 : 0 );
-    else
-      k_flag_compact< 3 ><<< blocks, 256, 0, ctx->stream >>>( g, u, eps, flags, ctx->mixedList, ctx->slot, ctx->capacity, ctx->state, compact ? 1 : 0 );
+    launch::flag_compact( g.dim, blocks, ctx->stream, g, u, eps, flags, ctx->mixedList, ctx->slot, ctx->capacity, ctx->state, compact ? 1 : 0 );
     return checkLaunch( ctx, "k_flag_compact" );
   }
 
   int launchResetCounters ( vofx_ctx *ctx )
   {
     profBegin( ctx );
-    k_reset_counters<<< 1, 1, 0, ctx->stream >>>( ctx->state );
+    launch::reset_counters( ctx->stream, ctx->state );
     return checkLaunch( ctx, "k_reset_counters" );
   }
 
@@ -188,10 +194,7 @@ namespace
     const Grid &g = ctx->grid;
     const int blocks = gridBlocks( ctx, g.cells, 256, 8 );
     profBegin( ctx );
-    if( g.dim == 2 )
-      k_compact_flags< 2 ><<< blocks, 256, 0, ctx->stream >>>( g, flags, ctx->mixedList, ctx->slot, ctx->capacity, ctx->state );
-    else
-      k_compact_flags< 3 ><<< blocks, 256, 0, ctx->stream >>>( g, flags, ctx->mixedList, ctx->slot, ctx->capacity, ctx->state );
+    launch::compact_flags( g.dim, blocks, ctx->stream, g, flags, ctx->mixedList, ctx->slot, ctx->capacity, ctx->state );
     return checkLaunch( ctx, "k_compact_flags" );
   }
 
@@ -201,9 +204,9 @@ namespace
     const int blocks = ctx->numSMs * 8;
     profBegin( ctx );
     if( g.dim == 2 )
-      k_youngs< 2 ><<< blocks, 128, 0, ctx->stream >>>( g, u, ctx->mixedList, ctx->state, ctx->capacity, hs );
+      launch::youngs2( blocks, ctx->stream, g, u, ctx->mixedList, ctx->state, ctx->capacity, hs );
     else
-      k_youngs< 3 ><<< blocks, 128, 0, ctx->stream >>>( g, u, ctx->mixedList, ctx->state, ctx->capacity, hs );
+      launch::youngs3( blocks, ctx->stream, g, u, ctx->mixedList, ctx->state, ctx->capacity, hs );
     int rc = checkLaunch( ctx, "k_youngs" );
     if( rc )
       return rc;
@@ -211,18 +214,18 @@ namespace
     {
       profBegin( ctx );
       if( g.dim == 2 )
-        k_hf< 2 ><<< blocks, 128, 0, ctx->stream >>>( g, u, ctx->mixedList, ctx->state, ctx->capacity, hs );
+        launch::hf2( blocks, ctx->stream, g, u, ctx->mixedList, ctx->state, ctx->capacity, hs );
       else
-        k_hf< 3 ><<< blocks, 128, 0, ctx->stream >>>( g, u, ctx->mixedList, ctx->state, ctx->capacity, hs );
+        launch::hf3( blocks, ctx->stream, g, u, ctx->mixedList, ctx->state, ctx->capacity, hs );
       rc = checkLaunch( ctx, "k_hf" );
     }
     else if( kind == VOFX_RECON_SWARTZ )
     {
       profBegin( ctx );
       if( g.dim == 2 )
-        k_swartz< 2 ><<< ctx->numSMs * 16, 64, 0, ctx->stream >>>( g, u, flags, ctx->mixedList, ctx->state, ctx->capacity, hs, maxIterations );
+        launch::swartz2( ctx->numSMs * 16, ctx->stream, g, u, flags, ctx->mixedList, ctx->state, ctx->capacity, hs, maxIterations );
       else
-        k_swartz< 3 ><<< ctx->numSMs * 16, 64, 0, ctx->stream >>>( g, u, flags, ctx->mixedList, ctx->state, ctx->capacity, hs, maxIterations );
+        launch::swartz3( ctx->numSMs * 16, ctx->stream, g, u, flags, ctx->mixedList, ctx->state, ctx->capacity, hs, maxIterations );
       rc = checkLaunch( ctx, "k_swartz" );
     }
     else if( kind != VOFX_RECON_YOUNGS )
@@ -236,9 +239,9 @@ namespace
     const int blocks = ctx->numSMs * 8;
     profBegin( ctx );
     if( g.dim == 2 )
-      k_flux< 2 ><<< blocks, 128, 0, ctx->stream >>>( g, ctx->velDev, hs, flags, ctx->mixedList, ctx->state, ctx->capacity, ctx->records, timeOverride, dtOverride );
+      launch::flux2( blocks, ctx->stream, g, ctx->velDev, hs, flags, ctx->mixedList, ctx->state, ctx->capacity, ctx->records, timeOverride, dtOverride );
     else
-      k_flux< 3 ><<< blocks, 128, 0, ctx->stream >>>( g, ctx->velDev, hs, flags, ctx->mixedList, ctx->state, ctx->capacity, ctx->records, timeOverride, dtOverride );
+      launch::flux3( blocks, ctx->stream, g, ctx->velDev, hs, flags, ctx->mixedList, ctx->state, ctx->capacity, ctx->records, timeOverride, dtOverride );
     return checkLaunch( ctx, "k_flux" );
   }
 
@@ -247,10 +250,7 @@ namespace
     const Grid &g = ctx->grid;
     const int blocks = ctx->numSMs * 8;
     profBegin( ctx );
-    if( g.dim == 2 )
-      k_update< 2 ><<< blocks, 128, 0, ctx->stream >>>( g, flags, ctx->mixedList, ctx->slot, ctx->state, ctx->capacity, ctx->records, target, accumulate ? 1 : 0 );
-    else
-      k_update< 3 ><<< blocks, 128, 0, ctx->stream >>>( g, flags, ctx->mixedList, ctx->slot, ctx->state, ctx->capacity, ctx->records, target, accumulate ? 1 : 0 );
+    launch::update( g.dim, blocks, ctx->stream, g, flags, ctx->mixedList, ctx->slot, ctx->state, ctx->capacity, ctx->records, target, accumulate ? 1 : 0 );
     return checkLaunch( ctx, "k_update" );
   }
 
@@ -263,18 +263,12 @@ namespace
     if( valid )
       VOFX_CUDA( cudaMemsetAsync( valid, 0, (size_t) g.cells, ctx->stream ) );
     profBegin( ctx );
-    if( g.dim == 2 )
-      k_curvature_local< 2 ><<< blocks, 128, 0, ctx->stream >>>( g, u, hs, ctx->mixedList, ctx->state, ctx->capacity, ctx->curv1, ctx->ok1 );
-    else
-      k_curvature_local< 3 ><<< blocks, 128, 0, ctx->stream >>>( g, u, hs, ctx->mixedList, ctx->state, ctx->capacity, ctx->curv1, ctx->ok1 );
+    launch::curvature_local( g.dim, blocks, ctx->stream, g, u, hs, ctx->mixedList, ctx->state, ctx->capacity, ctx->curv1, ctx->ok1 );
     int rc = checkLaunch( ctx, "k_curvature_local" );
     if( rc )
       return rc;
     profBegin( ctx );
-    if( g.dim == 2 )
-      k_curvature_average< 2 ><<< blocks, 128, 0, ctx->stream >>>( g, flags, ctx->mixedList, ctx->slot, ctx->state, ctx->capacity, ctx->curv1, ctx->ok1, kappa, valid );
-    else
-      k_curvature_average< 3 ><<< blocks, 128, 0, ctx->stream >>>( g, flags, ctx->mixedList, ctx->slot, ctx->state, ctx->capacity, ctx->curv1, ctx->ok1, kappa, valid );
+    launch::curvature_average( g.dim, blocks, ctx->stream, g, flags, ctx->mixedList, ctx->slot, ctx->state, ctx->capacity, ctx->curv1, ctx->ok1, kappa, valid );
     return checkLaunch( ctx, "k_curvature_average" );
   }
 
@@ -670,7 +664,8 @@ extern "C"
     rc = rc ? rc : requireVelocity( ctx );
     if( rc )
       return rc;
-    k_test_face_velocity<<< 1, 1, 0, ctx->stream >>>( ctx->grid, ctx->velDev, time, cell, face, ctx->scalars );
+    profBegin( ctx );
+    launch::test_face_velocity( ctx->stream, ctx->grid, ctx->velDev, time, cell, face, ctx->scalars );
     rc = checkLaunch( ctx, "k_test_face_velocity" );
     if( rc )
       return rc;
@@ -742,7 +737,7 @@ extern "C"
     if( rc )
       return rc;
     profBegin( ctx );
-    k_axpy<<< gridBlocks( ctx, ctx->grid.cells, 256, 8 ), 256, 0, ctx->stream >>>( ctx->grid.cells, u, a, x );
+    launch::axpy( gridBlocks( ctx, ctx->grid.cells, 256, 8 ), ctx->stream, ctx->grid.cells, u, a, x );
     return checkLaunch( ctx, "k_axpy" );
   }
 
@@ -803,7 +798,7 @@ extern "C"
     if( rc )
       return rc;
     profBegin( ctx );
-    k_finalize<<< 1, 1, 0, ctx->stream >>>( ctx->state, p->cfl );
+    launch::finalize( ctx->stream, ctx->state, p->cfl );
     return checkLaunch( ctx, "k_finalize" );
   }
 
@@ -1010,10 +1005,8 @@ extern "C"
       return fail( VOFX_ERR_ARGUMENT, "unknown built-in problem" );
     }
     const int blocks = gridBlocks( ctx, ctx->grid.cells, 128, 16 );
-    if( dim == 2 )
-      k_init< 2 ><<< blocks, 128, 0, ctx->stream >>>( ctx->grid, I, u );
-    else
-      k_init< 3 ><<< blocks, 128, 0, ctx->stream >>>( ctx->grid, I, u );
+    profBegin( ctx );
+    launch::init( dim, blocks, ctx->stream, ctx->grid, I, u );
     return checkLaunch( ctx, "k_init" );
   }
 
@@ -1067,9 +1060,9 @@ extern "C"
       return rc;
     const int blocks = (int) ( ( n + 63 ) / 64 ) > 0 ? (int) ( ( n + 63 ) / 64 ) : 1;
     if( dim == 2 )
-      k_test_locate< 2 ><<< blocks, 64 >>>( count, (double *) dLo.p, (double *) dH.p, (double *) dN.p, (double *) dF.p, (double *) dOut.p );
+      launch::test_locate2( blocks, count, (double *) dLo.p, (double *) dH.p, (double *) dN.p, (double *) dF.p, (double *) dOut.p );
     else
-      k_test_locate< 3 ><<< blocks, 64 >>>( count, (double *) dLo.p, (double *) dH.p, (double *) dN.p, (double *) dF.p, (double *) dOut.p );
+      launch::test_locate3( blocks, count, (double *) dLo.p, (double *) dH.p, (double *) dN.p, (double *) dF.p, (double *) dOut.p );
     VOFX_CUDA( cudaGetLastError() );
     VOFX_CUDA( cudaMemcpy( halfspaces, dOut.p, n * ( dim + 1 ) * 8, cudaMemcpyDeviceToHost ) );
     return VOFX_OK;
@@ -1094,9 +1087,9 @@ extern "C"
       return rc;
     const int blocks = (int) ( ( n + 63 ) / 64 ) > 0 ? (int) ( ( n + 63 ) / 64 ) : 1;
     if( dim == 2 )
-      k_test_flux< 2 ><<< blocks, 64 >>>( count, (double *) dLo.p, (double *) dH.p, (int *) dFace.p, (double *) dV.p, (double *) dHs.p, (double *) dOut.p );
+      launch::test_flux2( blocks, count, (double *) dLo.p, (double *) dH.p, (int *) dFace.p, (double *) dV.p, (double *) dHs.p, (double *) dOut.p );
     else
-      k_test_flux< 3 ><<< blocks, 64 >>>( count, (double *) dLo.p, (double *) dH.p, (int *) dFace.p, (double *) dV.p, (double *) dHs.p, (double *) dOut.p );
+      launch::test_flux3( blocks, count, (double *) dLo.p, (double *) dH.p, (int *) dFace.p, (double *) dV.p, (double *) dHs.p, (double *) dOut.p );
     VOFX_CUDA( cudaGetLastError() );
     VOFX_CUDA( cudaMemcpy( flux, dOut.p, n * 8, cudaMemcpyDeviceToHost ) );
     return VOFX_OK;
@@ -1121,9 +1114,9 @@ extern "C"
       return rc;
     const int blocks = (int) ( ( n + 63 ) / 64 ) > 0 ? (int) ( ( n + 63 ) / 64 ) : 1;
     if( dim == 2 )
-      k_test_interface< 2 ><<< blocks, 64 >>>( count, (double *) dLo.p, (double *) dH.p, (double *) dHs.p, (int *) dNv.p, (double *) dCen.p, (double *) dMeas.p );
+      launch::test_interface2( blocks, count, (double *) dLo.p, (double *) dH.p, (double *) dHs.p, (int *) dNv.p, (double *) dCen.p, (double *) dMeas.p );
     else
-      k_test_interface< 3 ><<< blocks, 64 >>>( count, (double *) dLo.p, (double *) dH.p, (double *) dHs.p, (int *) dNv.p, (double *) dCen.p, (double *) dMeas.p );
+      launch::test_interface3( blocks, count, (double *) dLo.p, (double *) dH.p, (double *) dHs.p, (int *) dNv.p, (double *) dCen.p, (double *) dMeas.p );
     VOFX_CUDA( cudaGetLastError() );
     VOFX_CUDA( cudaMemcpy( nverts, dNv.p, n * 4, cudaMemcpyDeviceToHost ) );
     VOFX_CUDA( cudaMemcpy( centroid, dCen.p, n * dim * 8, cudaMemcpyDeviceToHost ) );

@@ -16,31 +16,12 @@
 #include "vofx_geom2d.cuh"
 #include "vofx_geom3d.cuh"
 #include "vofx_grid.cuh"
+#include "vofx_types.cuh"
 
 namespace vofx
 {
 
-  // device-resident loop state (Algorithm::operator() locals, algorithm.hh:61)
-  struct StepState
-  {
-    double time;
-    double dt;
-    double dtEst;               // running MIN of the current step (bits compared as unsigned: values are >= 0)
-    double dtEstLast;           // estimate of the last finished step
-    int mixedCount;             // entries in the mixed list
-    int mixedCountLast;
-    int overflow;               // mixed list capacity exceeded
-    int pad;
-  };
 
-  // per mixed cell: what it adds to its own update and to each face neighbour's update (Appendix C of SURVEY.md)
-  struct FluxRecord
-  {
-    double self[ 6 ];
-    double nb[ 6 ];
-    unsigned char selfMask, nbMask;
-    unsigned char pad[ 6 ];
-  };
 
   // ------------------------------------------------------------------------------------------------------------
   // F1: flags + compaction.  Each thread owns 4 consecutive cells (two 16-byte loads, one 4-byte flag store).
@@ -158,6 +139,145 @@ namespace vofx
               {
                 mixedList[ pos ] = int( c0 + k );
                 slot[ c0 + k ] = pos;
+              }
+              else
+                state->overflow = 1;
+              pos++;
+            }
+        }
+      }
+    }
+  }
+
+  // Fast path of F1 for row lengths that are a multiple of 4 (every production grid): one block walks `rowsPerBlock`
+  // consecutive x-rows, a thread owns 4 consecutive cells of a row (two 16-byte loads, one 4-byte flag store), all
+  // index arithmetic is 32-bit and row-uniform, and the warp-aggregated append only runs in warps that hold a mixed
+  // cell (about 1 in 100 on the BASELINE configs).  ~11 instructions per cell: the kernel is HBM-bound, not issue-bound.
+  template< int DIM >
+  __global__ void __launch_bounds__( 128 ) k_flag_rows ( Grid g, const double *__restrict__ u, double eps, unsigned char *__restrict__ flags,
+                                                          int *__restrict__ mixedList, int *__restrict__ slot, int capacity, StepState *state,
+                                                          int compact, int rowsPerBlock )
+  {
+    const int nx = g.ns[ 0 ];
+    const int ny = g.ns[ 1 ];
+    const int nRows = g.ns[ 1 ] * g.ns[ 2 ];
+    const int quadsPerRow = nx >> 2;
+    const int quadsRounded = ( quadsPerRow + 31 ) & ~31;
+    const int lane = threadIdx.x & 31;
+    const double oneMinusEps = 1 - eps;
+    const int planeStride = nx * ny;
+
+    for( int r = 0; r < rowsPerBlock; ++r )
+    {
+      const int row = blockIdx.x * rowsPerBlock + r;
+      if( row >= nRows )
+        break;
+      const int j = ( DIM == 3 ) ? row % ny : row;
+      const int k = ( DIM == 3 ) ? row / ny : 0;
+      const int la = ( DIM == 3 ) ? k : j;                       // index along the decomposed (last) axis
+      const int gla = la + g.g0[ DIM - 1 ];
+      const bool inList = la >= g.list0 && la < g.list1;
+      // neighbour rows that exist (inside the global domain and inside this context's storage)
+      const bool lastLo = la > 0 && gla > 0;
+      const bool lastHi = la + 1 < g.ns[ DIM - 1 ] && gla + 1 < g.ng[ DIM - 1 ];
+      const bool yLo = ( DIM == 3 ) ? ( j > 0 ) : lastLo;
+      const bool yHi = ( DIM == 3 ) ? ( j + 1 < ny ) : lastHi;
+      const bool zLo = ( DIM == 3 ) && lastLo;
+      const bool zHi = ( DIM == 3 ) && lastHi;
+      const int rowBase = row * nx;
+
+      for( int q = threadIdx.x; q < quadsRounded; q += blockDim.x )
+      {
+        int nMixed = 0;
+        unsigned mixedBits = 0;
+        const int i0 = q << 2;
+        const int c0 = rowBase + i0;
+        if( q < quadsPerRow )
+        {
+          const double2 a = __ldg( reinterpret_cast< const double2 * >( u + c0 ) );
+          const double2 b = __ldg( reinterpret_cast< const double2 * >( u + c0 + 2 ) );
+          const double uu[ 4 ] = { a.x, a.y, b.x, b.y };
+          unsigned ff[ 4 ];
+          bool anyFull = false;
+#pragma unroll
+          for( int t = 0; t < 4; ++t )
+          {
+            // flagging.hh:46-55
+            ff[ t ] = ( uu[ t ] < eps ) ? 0u : ( ( uu[ t ] <= oneMinusEps ) ? 1u : ( ( uu[ t ] != uu[ t ] ) ? 99u : 3u ) );
+            anyFull |= ( ff[ t ] == 3u );
+          }
+          if( anyFull )
+          {
+            // full cells with an empty face neighbour become mixedfull, flagging.hh:56-63
+#pragma unroll
+            for( int t = 0; t < 4; ++t )
+              if( ff[ t ] == 3u )
+              {
+                const int i = i0 + t;
+                const int c = c0 + t;
+                bool emptyNb = false;
+                if( t > 0 )
+                  emptyNb = uu[ t > 0 ? t - 1 : 0 ] < eps;
+                else if( i > 0 )
+                  emptyNb = __ldg( u + c - 1 ) < eps;
+                if( !emptyNb )
+                {
+                  if( t < 3 )
+                    emptyNb = uu[ t < 3 ? t + 1 : 3 ] < eps;
+                  else if( i + 1 < nx )
+                    emptyNb = __ldg( u + c + 1 ) < eps;
+                }
+                if( !emptyNb && yLo )
+                  emptyNb = __ldg( u + c - nx ) < eps;
+                if( !emptyNb && yHi )
+                  emptyNb = __ldg( u + c + nx ) < eps;
+                if( DIM == 3 )
+                {
+                  if( !emptyNb && zLo )
+                    emptyNb = __ldg( u + c - planeStride ) < eps;
+                  if( !emptyNb && zHi )
+                    emptyNb = __ldg( u + c + planeStride ) < eps;
+                }
+                if( emptyNb )
+                  ff[ t ] = 2u;
+              }
+          }
+          *reinterpret_cast< unsigned * >( flags + c0 ) = ff[ 0 ] | ( ff[ 1 ] << 8 ) | ( ff[ 2 ] << 16 ) | ( ff[ 3 ] << 24 );
+          if( inList )
+          {
+#pragma unroll
+            for( int t = 0; t < 4; ++t )
+              if( ff[ t ] == 1u || ff[ t ] == 2u )
+              {
+                mixedBits |= 1u << t;
+                nMixed++;
+              }
+          }
+        }
+
+        if( compact && __any_sync( 0xffffffffu, nMixed > 0 ) )
+        {
+          int incl = nMixed;
+#pragma unroll
+          for( int o = 1; o < 32; o <<= 1 )
+          {
+            const int t = __shfl_up_sync( 0xffffffffu, incl, o );
+            if( lane >= o )
+              incl += t;
+          }
+          const int total = __shfl_sync( 0xffffffffu, incl, 31 );
+          int base = 0;
+          if( lane == 31 )
+            base = atomicAdd( &state->mixedCount, total );
+          base = __shfl_sync( 0xffffffffu, base, 31 );
+          int pos = base + incl - nMixed;
+          for( int t = 0; t < 4; ++t )
+            if( mixedBits & ( 1u << t ) )
+            {
+              if( pos < capacity )
+              {
+                mixedList[ pos ] = c0 + t;
+                slot[ c0 + t ] = pos;
               }
               else
                 state->overflow = 1;
@@ -992,7 +1112,7 @@ namespace vofx
   }
 
   // T1: algorithm.hh:85-93
-  __global__ void k_finalize ( StepState *state, double cfl )
+  static __global__ void k_finalize ( StepState *state, double cfl )
   {
     if( state->dt > 0.0 )
       state->time += state->dt;
@@ -1003,14 +1123,14 @@ namespace vofx
     state->mixedCount = 0;
   }
 
-  __global__ void k_reset_counters ( StepState *state )
+  static __global__ void k_reset_counters ( StepState *state )
   {
     state->mixedCount = 0;
     state->dtEst = DBL_MAX;
   }
 
   // U1 (operator-level API): ColorFunction::axpy, colorfunction.hh:31-37
-  __global__ void __launch_bounds__( 256 ) k_axpy ( long long n, double *__restrict__ u, double a, const double *__restrict__ x )
+  static __global__ void __launch_bounds__( 256 ) k_axpy ( long long n, double *__restrict__ u, double a, const double *__restrict__ x )
   {
     for( long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x; i < n; i += (long long) gridDim.x * blockDim.x )
       u[ i ] += a * x[ i ];
@@ -1147,14 +1267,6 @@ namespace vofx
   // evaluated on the host and passed in, so the device only does + - * sqrt and comparisons.
   // ------------------------------------------------------------------------------------------------------------
 
-  struct Indicator
-  {
-    int kind;          // 0 ball |x-c| < r, 1 ball |x-c|^2 <= r^2, 2 slotted cylinder, 3 half space x0 <= pos
-    int dim;
-    double c[ 3 ];     // centre (kinds 0,1) / wall position in c[0] (kind 3)
-    double r;
-    double cs, sn;     // slotted cylinder: cos/sin of the rotation angle
-  };
 
   __device__ __forceinline__ int indicator_eval ( const Indicator &I, const double *x )
   {
@@ -1356,7 +1468,7 @@ namespace vofx
     }
   }
 
-  __global__ void k_test_face_velocity ( Grid g, const Velocity *velocity, double time, long long cell, int face, double *out )
+  static __global__ void k_test_face_velocity ( Grid g, const Velocity *velocity, double time, long long cell, int face, double *out )
   {
     int ijk[ 3 ];
     cell_ijk( g, cell, ijk );

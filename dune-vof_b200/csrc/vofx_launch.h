@@ -1,0 +1,53 @@
+// vofx: host-callable launchers of the kernels, one translation unit per group so that nvcc compiles them in parallel
+// (the geometry code is heavily inlined).  The C-ABI implementation (vofx_capi.cu) only sees these prototypes.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "vofx_types.cuh"
+
+namespace vofx
+{
+  namespace launch
+  {
+    // k_dense.cu
+    void flag_rows ( int dim, int blocks, cudaStream_t s, Grid g, const double *u, double eps, unsigned char *flags, int *mixedList, int *slot,
+                     int capacity, StepState *state, int compact, int rowsPerBlock );
+    void flag_compact ( int dim, int blocks, cudaStream_t s, Grid g, const double *u, double eps, unsigned char *flags, int *mixedList, int *slot,
+                        int capacity, StepState *state, int compact );
+    void compact_flags ( int dim, int blocks, cudaStream_t s, Grid g, const unsigned char *flags, int *mixedList, int *slot, int capacity, StepState *state );
+    void update ( int dim, int blocks, cudaStream_t s, Grid g, const unsigned char *flags, const int *mixedList, const int *slot, const StepState *state,
+                  int capacity, const FluxRecord *records, double *target, int accumulate );
+    void curvature_local ( int dim, int blocks, cudaStream_t s, Grid g, const double *u, const double *hs, const int *mixedList, const StepState *state,
+                           int capacity, double *curv1, unsigned char *ok1 );
+    void curvature_average ( int dim, int blocks, cudaStream_t s, Grid g, const unsigned char *flags, const int *mixedList, const int *slot,
+                             const StepState *state, int capacity, const double *curv1, const unsigned char *ok1, double *kappa, unsigned char *valid );
+    void finalize ( cudaStream_t s, StepState *state, double cfl );
+    void reset_counters ( cudaStream_t s, StepState *state );
+    void axpy ( int blocks, cudaStream_t s, long long n, double *u, double a, const double *x );
+    void init ( int dim, int blocks, cudaStream_t s, Grid g, Indicator I, double *u );
+    void test_face_velocity ( cudaStream_t s, Grid g, const Velocity *velocity, double time, long long cell, int face, double *out );
+
+    // k_band2d.cu
+    void youngs2 ( int blocks, cudaStream_t s, Grid g, const double *u, const int *mixedList, const StepState *state, int capacity, double *hs );
+    void hf2 ( int blocks, cudaStream_t s, Grid g, const double *u, const int *mixedList, const StepState *state, int capacity, double *hs );
+    void swartz2 ( int blocks, cudaStream_t s, Grid g, const double *u, const unsigned char *flags, const int *mixedList, const StepState *state,
+                   int capacity, double *hs, int maxIterations );
+    void flux2 ( int blocks, cudaStream_t s, Grid g, const Velocity *velocity, const double *hs, const unsigned char *flags, const int *mixedList,
+                 StepState *state, int capacity, FluxRecord *records, const double *timeOverride, const double *dtOverride );
+    void test_locate2 ( int blocks, long long count, const double *lo, const double *h, const double *normal, const double *fraction, double *out );
+    void test_flux2 ( int blocks, long long count, const double *lo, const double *h, const int *face, const double *v, const double *hs, double *out );
+    void test_interface2 ( int blocks, long long count, const double *lo, const double *h, const double *hs, int *nverts, double *centroid, double *measure );
+
+    // k_recon3d.cu, k_swartz3d.cu, k_flux3d.cu
+    void youngs3 ( int blocks, cudaStream_t s, Grid g, const double *u, const int *mixedList, const StepState *state, int capacity, double *hs );
+    void hf3 ( int blocks, cudaStream_t s, Grid g, const double *u, const int *mixedList, const StepState *state, int capacity, double *hs );
+    void swartz3 ( int blocks, cudaStream_t s, Grid g, const double *u, const unsigned char *flags, const int *mixedList, const StepState *state,
+                   int capacity, double *hs, int maxIterations );
+    void flux3 ( int blocks, cudaStream_t s, Grid g, const Velocity *velocity, const double *hs, const unsigned char *flags, const int *mixedList,
+                 StepState *state, int capacity, FluxRecord *records, const double *timeOverride, const double *dtOverride );
+    void test_locate3 ( int blocks, long long count, const double *lo, const double *h, const double *normal, const double *fraction, double *out );
+    void test_flux3 ( int blocks, long long count, const double *lo, const double *h, const int *face, const double *v, const double *hs, double *out );
+    void test_interface3 ( int blocks, long long count, const double *lo, const double *h, const double *hs, int *nverts, double *centroid, double *measure );
+  } // namespace launch
+} // namespace vofx

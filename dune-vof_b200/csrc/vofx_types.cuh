@@ -1,0 +1,40 @@
+// vofx: plain-data types shared by the kernels and the host side of the C ABI.
+#pragma once
+
+#include "vofx_grid.cuh"
+
+namespace vofx
+{
+
+  // device-resident loop state (Algorithm::operator() locals, algorithm.hh:61)
+  struct StepState
+  {
+    double time;
+    double dt;
+    double dtEst;               // running MIN of the current step (bits compared as unsigned: values are >= 0)
+    double dtEstLast;           // estimate of the last finished step
+    int mixedCount;             // entries in the mixed list
+    int mixedCountLast;
+    int overflow;               // mixed list capacity exceeded
+    int pad;
+  };
+
+  // per mixed cell: what it adds to its own update and to each face neighbour's update (Appendix C of SURVEY.md)
+  struct FluxRecord
+  {
+    double self[ 6 ];
+    double nb[ 6 ];
+    unsigned char selfMask, nbMask;
+    unsigned char pad[ 6 ];
+  };
+
+  struct Indicator
+  {
+    int kind;          // 0 ball |x-c| < r, 1 ball |x-c|^2 <= r^2, 2 slotted cylinder, 3 half space x0 <= pos
+    int dim;
+    double c[ 3 ];     // centre (kinds 0,1) / wall position in c[0] (kind 3)
+    double r;
+    double cs, sn;     // slotted cylinder: cos/sin of the rotation angle
+  };
+
+} // namespace vofx

@@ -52,7 +52,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     """nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false ... -> dune-vof_b200/libvofx.so (in-tree)."""
     newest = max(os.path.getmtime(s) for s in sources())
     if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < newest:
-        cmd = ["make", "-f", os.path.join(CSRC, "Makefile")]
+        cmd = ["make", "-j8", "-f", os.path.join(CSRC, "Makefile")]
         if force:
             cmd.append("-B")
         subprocess.check_call(cmd, cwd=ROOT, stdout=None if verbose else subprocess.DEVNULL)
