@@ -58,6 +58,7 @@ struct vofx_ctx
   Velocity velHost;                 // device pointers inside
   Velocity *velDev = nullptr;
   std::vector< double * > velTables;
+  double *velFaces = nullptr;
   bool velocitySet = false;
 
   // staging for the host-buffer variants
@@ -457,6 +458,7 @@ extern "C"
     cudaFree( ctx->velDev );
     for( double *t : ctx->velTables )
       cudaFree( t );
+    cudaFree( ctx->velFaces );
     cudaFree( ctx->dU );
     cudaFree( ctx->dHs );
     cudaFree( ctx->dUpd );
@@ -581,6 +583,23 @@ extern "C"
       VOFX_CUDA( cudaMemcpy( dev, src[ k ], n * sizeof( double ), cudaMemcpyHostToDevice ) );
       ctx->velHost.tab[ component ][ term ][ axis ][ k ] = dev;
     }
+    return uploadVelocity( ctx );
+  }
+
+  int vofx_velocity_set_faces ( vofx_ctx *ctx, const double *v_host )
+  {
+    if( !ctx || !v_host )
+      return fail( VOFX_ERR_ARGUMENT, "null argument" );
+    int rc = setDevice( ctx );
+    if( rc )
+      return rc;
+    const size_t count = (size_t) ctx->grid.cells * 2 * ctx->desc.dim * ctx->desc.dim;
+    rc = ensureDevice( ctx->velFaces, count );
+    if( rc )
+      return rc;
+    VOFX_CUDA( cudaMemcpyAsync( ctx->velFaces, v_host, count * sizeof( double ), cudaMemcpyHostToDevice, ctx->stream ) );
+    ctx->velHost.faces = ctx->velFaces;
+    ctx->velocitySet = true;
     return uploadVelocity( ctx );
   }
 
@@ -938,6 +957,43 @@ extern "C"
       VOFX_CUDA( cudaMemcpyAsync( flags, ctx->dFlags, N, cudaMemcpyDeviceToHost, ctx->stream ) );
     VOFX_CUDA( cudaStreamSynchronize( ctx->stream ) );
     return VOFX_OK;
+  }
+
+  // context-resident colour function: upload once, step on the device, download when the host needs it
+  int vofx_color_upload ( vofx_ctx *ctx, const double *u )
+  {
+    if( !ctx || !u )
+      return fail( VOFX_ERR_ARGUMENT, "null argument" );
+    int rc = ensureMirrors( ctx );
+    if( rc )
+      return rc;
+    VOFX_CUDA( cudaMemcpyAsync( ctx->dU, u, (size_t) ctx->grid.cells * sizeof( double ), cudaMemcpyHostToDevice, ctx->stream ) );
+    VOFX_CUDA( cudaStreamSynchronize( ctx->stream ) );
+    return VOFX_OK;
+  }
+
+  int vofx_color_download ( vofx_ctx *ctx, double *u, uint8_t *flags )
+  {
+    if( !ctx || !u )
+      return fail( VOFX_ERR_ARGUMENT, "null argument" );
+    int rc = ensureMirrors( ctx );
+    if( rc )
+      return rc;
+    VOFX_CUDA( cudaMemcpyAsync( u, ctx->dU, (size_t) ctx->grid.cells * sizeof( double ), cudaMemcpyDeviceToHost, ctx->stream ) );
+    if( flags )
+      VOFX_CUDA( cudaMemcpyAsync( flags, ctx->dFlags, (size_t) ctx->grid.cells, cudaMemcpyDeviceToHost, ctx->stream ) );
+    VOFX_CUDA( cudaStreamSynchronize( ctx->stream ) );
+    return VOFX_OK;
+  }
+
+  int vofx_step_resident ( vofx_ctx *ctx, const vofx_step_params *p )
+  {
+    if( !ctx || !p )
+      return fail( VOFX_ERR_ARGUMENT, "null argument" );
+    int rc = ensureMirrors( ctx );
+    if( !rc && p->with_curvature )
+      rc = ensureDevice( ctx->dKappa, (size_t) ctx->grid.cells );
+    return rc ? rc : vofx_step( ctx, p, ctx->dU, ctx->dFlags, ctx->dHs, ctx->dKappa );
   }
 
   // ---- initial data -------------------------------------------------------------------------------------------------------

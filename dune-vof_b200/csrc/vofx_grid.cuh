@@ -93,12 +93,22 @@ namespace vofx
     double period[ 3 ];
     // tab[component][term][axis][0 centre | 1 lower face | 2 upper face] -> table indexed by the GLOBAL cell index
     const double *tab[ 3 ][ 2 ][ 3 ][ 3 ];
+    // general fallback (vofx_velocity_set_faces): velocity sampled by the host functor at every face centre,
+    // faces[ ( cell * 2*dim + face ) * dim + component ], frozen at the start-of-step time by the caller
+    const double *faces;
   };
 
   // velocity at the centre of `face` of the cell with storage multi-index ijk, as that cell's own intersection sees
   // it (Velocity::operator(), velocity.hh:15-20).  v has 3 entries; unused ones are 0.
   VOFX_HD inline void face_velocity ( const Grid &g, const Velocity &vel, const int *ijk, int face, double time, double *v )
   {
+    if( vel.faces )
+    {
+      const long long c = cell_index( g, ijk );
+      for( int a = 0; a < 3; ++a )
+        v[ a ] = ( a < g.dim ) ? vel.faces[ ( c * 2 * g.dim + face ) * g.dim + a ] : 0.0;
+      return;
+    }
     const int fa = face >> 1;
     const int kindOfFaceAxis = ( face & 1 ) ? 2 : 1;
     for( int a = 0; a < 3; ++a )

@@ -20,10 +20,11 @@ TIME_CONST, TIME_COSPI = 0, 1
 # every symbol include/vofx.h declares
 SYMBOLS = [
     "vofx_last_error", "vofx_create", "vofx_destroy", "vofx_set_stream", "vofx_cells", "vofx_velocity_clear",
-    "vofx_velocity_set_component", "vofx_velocity_set_factor", "vofx_velocity_builtin", "vofx_face_velocity",
+    "vofx_velocity_set_component", "vofx_velocity_set_factor", "vofx_velocity_set_faces", "vofx_velocity_builtin", "vofx_face_velocity",
     "vofx_flag", "vofx_reconstruct", "vofx_evolve", "vofx_axpy", "vofx_curvature", "vofx_step_begin", "vofx_step",
     "vofx_step_state", "vofx_step_local", "vofx_step_finish", "vofx_dt_est_device", "vofx_flag_host",
-    "vofx_reconstruct_host", "vofx_evolve_host", "vofx_curvature_host", "vofx_step_host", "vofx_init",
+    "vofx_reconstruct_host", "vofx_evolve_host", "vofx_curvature_host", "vofx_step_host", "vofx_color_upload",
+    "vofx_step_resident", "vofx_color_download", "vofx_init",
     "vofx_test_locate", "vofx_test_flux", "vofx_test_interface", "vofx_launch_count", "vofx_profile_enable",
     "vofx_profile_read",
 ]
@@ -84,6 +85,7 @@ def load():
     L.vofx_velocity_clear.argtypes = [vp]
     L.vofx_velocity_set_component.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_int, C.c_double]
     L.vofx_velocity_set_factor.argtypes = [vp, C.c_int, C.c_int, C.c_int, dp, dp, dp]
+    L.vofx_velocity_set_faces.argtypes = [vp, dp]
     L.vofx_velocity_builtin.argtypes = [vp, C.c_int]
     L.vofx_face_velocity.argtypes = [vp, C.c_double, C.c_int64, C.c_int, dp]
     L.vofx_flag.argtypes = [vp, dp, C.c_double, bp]
@@ -103,6 +105,9 @@ def load():
     L.vofx_evolve_host.argtypes = [vp, dp, bp, C.c_double, C.c_double, dp, C.POINTER(C.c_double)]
     L.vofx_curvature_host.argtypes = [vp, dp, dp, bp, dp, bp]
     L.vofx_step_host.argtypes = [vp, C.POINTER(StepParams), dp, bp]
+    L.vofx_color_upload.argtypes = [vp, dp]
+    L.vofx_step_resident.argtypes = [vp, C.POINTER(StepParams)]
+    L.vofx_color_download.argtypes = [vp, dp, bp]
     L.vofx_init.argtypes = [vp, C.c_int, C.c_double, dp]
     L.vofx_profile_enable.argtypes = [vp, C.c_int]
     L.vofx_profile_read.argtypes = [vp, C.c_int, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int)]

@@ -98,6 +98,12 @@ int vofx_velocity_set_component ( vofx_ctx *ctx, int component, int nterms, doub
 int vofx_velocity_set_factor ( vofx_ctx *ctx, int component, int term, int axis,
                                const double *at_centre, const double *at_lower_face, const double *at_upper_face );
 
+/* general fallback for an arbitrary host velocity functor: the caller samples it at every face centre (as
+ * Velocity::operator() would, velocity.hh:15-20, frozen at the start-of-step time) and passes
+ * v_host[ ( cell * 2*dim + face ) * dim + component ] over all cells of the context (HOST pointer, copied).
+ * While set it overrides the separable description; vofx_velocity_clear() removes it. */
+int vofx_velocity_set_faces ( vofx_ctx *ctx, const double *v_host );
+
 /* built-in problems (tables generated on the host with libm from the coordinates defined above):
  * 0 RotatingCircle (test/problems/rotatingcircle.hh:45-52,92-101), 1 SFlow (sflow.hh:35-42,73-82),
  * 2 SlottedCylinder (slottedcylinder.hh:47-55, 2D), 3 LinearWall (linearwall.hh:27-31), 4 LeVeque deformation field */
@@ -161,6 +167,12 @@ int vofx_evolve_host ( vofx_ctx *ctx, const double *halfspaces, const uint8_t *f
 int vofx_curvature_host ( vofx_ctx *ctx, const double *u, const double *halfspaces, const uint8_t *flags, double *kappa, uint8_t *valid );
 /* one full loop pass on a host colour function: H2D u, step, D2H u (and flags if non-NULL) */
 int vofx_step_host ( vofx_ctx *ctx, const vofx_step_params *params, double *u, uint8_t *flags );
+
+/* context-resident colour function (what a drop-in for Algorithm::operator() uses, algorithm.hh:54-103): upload the
+ * host colour function once, run loop passes on the device mirror, download when the data writer wants it */
+int vofx_color_upload ( vofx_ctx *ctx, const double *u_host );
+int vofx_step_resident ( vofx_ctx *ctx, const vofx_step_params *params );
+int vofx_color_download ( vofx_ctx *ctx, double *u_host, uint8_t *flags_host /* may be NULL */ );
 
 /* ---- initial data on the device (replaces Average< Problem >, test/average.hh:28-54, i.e.
  * RecursiveInterpolationCube depth 3, interpolation/recursiveinterpolationcube.hh:33-82, for the built-in problems) */

@@ -1,0 +1,20 @@
+"""The C++ header adaptor include/dune/vofx/*.hh driven like the reference drives its operators (algorithm.hh:57-93):
+tests/adaptor/test_adaptor is built on the CPU box by __graft_entry__.build() and travels to the GPU box."""
+import os
+import subprocess
+
+import pytest
+
+from util import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def test_adaptor_binary():
+    exe = os.path.join(ROOT, "tests", "adaptor", "test_adaptor")
+    assert os.path.exists(exe), "tests/adaptor/test_adaptor is missing: run __graft_entry__.build()"
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    print(r.stdout)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "ADAPTOR TEST PASSED" in r.stdout
+    assert "FAIL" not in r.stdout
