@@ -49,6 +49,9 @@ struct vofx_ctx
   int *mixedList = nullptr;
   int *slot = nullptr;
   FluxRecord *records = nullptr;
+  int *tasks = nullptr;             // 3D clip tasks ( mixed-list slot * 8 + face ), at most 6 per mixed cell
+  int taskCapacity = 0;
+  void *clipTable = nullptr;        // coop::ClipCase[ 256 ]
   StepState *state = nullptr;
   double *curv1 = nullptr;
   unsigned char *ok1 = nullptr;
@@ -240,10 +243,18 @@ namespace
     const int blocks = ctx->numSMs * 8;
     profBegin( ctx );
     if( g.dim == 2 )
+    {
       launch::flux2( blocks, ctx->stream, g, ctx->velDev, hs, flags, ctx->mixedList, ctx->state, ctx->capacity, ctx->records, timeOverride, dtOverride );
-    else
-      launch::flux3( blocks, ctx->stream, g, ctx->velDev, hs, flags, ctx->mixedList, ctx->state, ctx->capacity, ctx->records, timeOverride, dtOverride );
-    return checkLaunch( ctx, "k_flux" );
+      return checkLaunch( ctx, "k_flux" );
+    }
+    launch::flux_prepare3( blocks, ctx->stream, g, ctx->velDev, flags, ctx->mixedList, ctx->state, ctx->capacity, ctx->records, ctx->tasks, ctx->taskCapacity, timeOverride, dtOverride );
+    int rc = checkLaunch( ctx, "k_flux_prepare" );
+    if( rc )
+      return rc;
+    profBegin( ctx );
+    launch::flux_clip3( ctx->numSMs * 8, ctx->stream, g, ctx->velDev, hs, flags, ctx->mixedList, ctx->state, ctx->records, ctx->tasks, ctx->clipTable, ctx->taskCapacity, timeOverride, dtOverride );
+    ctx->launches++;   // k_flux_clip_serial3 rides along (a handful of tasks per step)
+    return checkLaunch( ctx, "k_flux_clip" );
   }
 
   int launchUpdate ( vofx_ctx *ctx, const unsigned char *flags, double *target, bool accumulate )
@@ -425,6 +436,14 @@ extern "C"
     alloc( (void **) &ctx->slot, sizeof( int ) * (size_t) g.cells );
     alloc( (void **) &ctx->records, sizeof( FluxRecord ) * (size_t) ctx->capacity );
     alloc( (void **) &ctx->state, sizeof( StepState ) );
+    if( desc->dim == 3 )
+    {
+      // worst case 6 clip tasks per mixed cell, plus the serial leftovers stored from the end
+      const long long tc = 7LL * ctx->capacity;
+      ctx->taskCapacity = (int) ( tc < ( 1LL << 30 ) ? tc : ( 1LL << 30 ) );
+      alloc( (void **) &ctx->tasks, sizeof( int ) * (size_t) ctx->taskCapacity );
+      alloc( (void **) &ctx->clipTable, 256 * 64 );
+    }
     alloc( (void **) &ctx->curv1, sizeof( double ) * (size_t) ctx->capacity );
     alloc( (void **) &ctx->ok1, (size_t) ctx->capacity );
     alloc( (void **) &ctx->scalars, sizeof( double ) * 4 );
@@ -438,6 +457,12 @@ extern "C"
     std::memset( &init, 0, sizeof( init ) );
     init.dtEst = DBL_MAX;
     cudaMemcpy( ctx->state, &init, sizeof( init ), cudaMemcpyHostToDevice );
+    if( ctx->clipTable )
+    {
+      std::vector< unsigned char > table( 256 * 64 );
+      launch::make_clip_table( table.data() );
+      cudaMemcpy( ctx->clipTable, table.data(), table.size(), cudaMemcpyHostToDevice );
+    }
     std::memset( &ctx->velHost, 0, sizeof( Velocity ) );
     *out = ctx;
     return VOFX_OK;
@@ -451,6 +476,8 @@ extern "C"
     cudaFree( ctx->mixedList );
     cudaFree( ctx->slot );
     cudaFree( ctx->records );
+    cudaFree( ctx->tasks );
+    cudaFree( ctx->clipTable );
     cudaFree( ctx->state );
     cudaFree( ctx->curv1 );
     cudaFree( ctx->ok1 );

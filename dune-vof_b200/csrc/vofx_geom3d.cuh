@@ -176,7 +176,7 @@ namespace vofx
     cross3( v1, v2, normal );
     const double s = -1.0 * norm3( normal );
     for( int k = 0; k < 3; ++k )
-      normal[ k ] /= s;
+      normal[ k ] = vdiv( normal[ k ], s );
   }
 
   // one edge's term of Face::volume: ( edge.center() . edge.outerNormal( faceNormal ) ) * edge.volume()
@@ -191,7 +191,7 @@ namespace vofx
     cross3( v1, fn, en );
     const double nrm = norm3( en );
     for( int k = 0; k < 3; ++k )
-      en[ k ] /= nrm;
+      en[ k ] = vdiv( en[ k ], nrm );
     return dot3( center, en ) * norm3( v1 );
   }
 
@@ -225,17 +225,13 @@ namespace vofx
 
   // ---- G5: clip against a half-space and take the volume ----------------------------------------------------------
 
-  constexpr int kMaxClipNodes = 16;
-  constexpr int kMaxClipEdges = 64;
-  constexpr int kMaxFaceEdges = 12;
-
   // Edge::intersection( hyperplane ), 3d/polyhedron.hh:93-101
   VOFX_HD inline void edge_plane_point ( const double *x0, const double *x1, const Hs3 &hs, double *out )
   {
     double p[ 3 ];
     for( int k = 0; k < 3; ++k )
       p[ k ] = x0[ k ] - x1[ k ];
-    const double s = ( dot3( hs.n, x0 ) + hs.d ) / ( dot3( hs.n, p ) * -1.0 );
+    const double s = vdiv( dot3( hs.n, x0 ) + hs.d, dot3( hs.n, p ) * -1.0 );
     for( int k = 0; k < 3; ++k )
     {
       p[ k ] *= s;
@@ -244,103 +240,72 @@ namespace vofx
     }
   }
 
-  struct ClipScratch
+  // Topology of the clipped polyhedron (3d/intersect.hh:123-262).  The walk only depends on which nodes are inner /
+  // on the boundary, not on coordinates: the serial path runs it per clip, the cooperative path (vofx_coop3d.cuh)
+  // looks it up in a table indexed by the inner mask that is generated from this very function.
+  struct ClipTopo
   {
-    double x[ kMaxClipNodes ][ 3 ];     // nodes of the clipped polyhedron: inner nodes in order, then the cut nodes
-    signed char e0[ kMaxClipEdges ], e1[ kMaxClipEdges ];
+    int n, nNew;                              // inner nodes (new ids 0..n-1), cut nodes (new ids n..n+nNew-1)
+    signed char innerNode[ 8 ];               // original id of new node k < n (ascending, :252-257)
+    signed char cutA[ 12 ], cutB[ 12 ];       // cut node n+j = Edge( cutA[j], cutB[j] ).intersection( plane ), :171-183
+    int nFaces;                               // faces that enter Polyhedron::volume, in summation order
+    signed char flen[ 7 ];
+    signed char fe0[ 7 ][ 16 ], fe1[ 7 ][ 16 ];   // directed edges (new node ids) of each face
   };
 
-  // contribution ( face.center() . face.outerNormal() ) * face.volume() of one face given as a list of edge ids
-  VOFX_HD inline double clipped_face_term ( const ClipScratch &s, const signed char *edges, int n )
+  // returns false for the trivial cases of :115-120 (empty result)
+  VOFX_HD inline bool clip_walk ( unsigned innerMask, unsigned boundaryMask, ClipTopo &t )
   {
-    double center[ 3 ] = { 0.0, 0.0, 0.0 }, fn[ 3 ];
-    for( int i = 0; i < n; ++i )
-    {
-      const double *x = s.x[ s.e0[ edges[ i ] ] ];
-      for( int d = 0; d < 3; ++d )
-        center[ d ] += x[ d ];
-    }
-    const double inv = 1.0 / n;
-    for( int d = 0; d < 3; ++d )
-      center[ d ] *= inv;
-    outer_normal3( s.x[ s.e0[ edges[ 0 ] ] ], s.x[ s.e0[ edges[ 1 ] ] ], s.x[ s.e0[ edges[ 2 ] ] ], fn );
-    double fv = 0.0;
-    for( int i = 0; i < n; ++i )
-      fv += face_edge_term( s.x[ s.e0[ edges[ i ] ] ], s.x[ s.e1[ edges[ i ] ] ], fn );
-    return dot3( center, fn ) * fabs( fv / 2.0 );
-  }
-
-  // volume of { hex } n { hs > 0 }: 3d/intersect.hh:72-263 + 3d/polyhedron.hh:317-324
-  VOFX_HD inline double clip_volume ( const Hex &poly, const Hs3 &hs )
-  {
-    if( !hs_valid( hs ) )
-      return fabs( 0.0 / 3.0 );
-
-    ClipScratch s;
-    unsigned innerMask = 0, boundaryMask = 0;
     signed char p[ 8 ];
     int n = 0, onBoundary = 0;
     for( int i = 0; i < 8; ++i )
     {
-      const double ls = level_set( hs, poly.x[ i ] );
-      if( ls > -kEps )
+      if( innerMask & ( 1u << i ) )
       {
-        innerMask |= 1u << i;
+        t.innerNode[ n ] = (signed char) i;
         p[ i ] = (signed char) n;
         n++;
-        if( fabs( ls ) < kEps )
-        {
-          boundaryMask |= 1u << i;
+        if( boundaryMask & ( 1u << i ) )
           onBoundary++;
-        }
       }
       else
         p[ i ] = -1;
     }
+    t.n = n;
+    t.nNew = 0;
+    t.nFaces = 0;
     if( n == 0 || ( n == 1 && onBoundary == 1 ) || ( n == 2 && onBoundary == 2 ) )
-      return fabs( 0.0 / 3.0 );
+      return false;
 
-    // inner nodes first, 3d/intersect.hh:252-257
-    for( int i = 0; i < 8; ++i )
-      if( innerMask & ( 1u << i ) )
-        for( int d = 0; d < 3; ++d )
-          s.x[ p[ i ] ][ d ] = poly.x[ i ][ d ];
-
-    int ne = 0, nNew = 0;
+    int nNew = 0;
     signed char cutNode[ 24 ];                 // new node id created on directed edge e, or -1 (std::map of :93-95)
     for( int e = 0; e < 24; ++e )
       cutNode[ e ] = -1;
-    signed char isect[ 16 ];
+    signed char is0[ 16 ], is1[ 16 ];          // edges of the intersection face
     int nIF = 0;
-    double vol = 0.0;
-
-#define VOFX_PUSH_EDGE( a_, b_ ) ( s.e0[ ne ] = (signed char) ( a_ ), s.e1[ ne ] = (signed char) ( b_ ), ne++ )
 
     for( int f = 0; f < 6; ++f )
     {
-      signed char newFace[ kMaxFaceEdges ];
+      signed char *n0 = t.fe0[ t.nFaces ], *n1 = t.fe1[ t.nFaces ];
       int nNF = 0;
       int lastIsId = -1;
+#define VOFX_FACE_EDGE( a_, b_ ) ( n0[ nNF ] = (signed char) ( a_ ), n1[ nNF ] = (signed char) ( b_ ), nNF++ )
+#define VOFX_CAP_EDGE( a_, b_ ) ( is0[ nIF ] = (signed char) ( a_ ), is1[ nIF ] = (signed char) ( b_ ), nIF++ )
       for( int k = 0; k < 4; ++k )
       {
         const int edge = cube::faceEdge( f, k );
         const int a = cube::edgeN0( edge ), b = cube::edgeN1( edge );
         const bool ia = innerMask & ( 1u << a ), ib = innerMask & ( 1u << b );
         if( ia && ib )
-        {
-          VOFX_PUSH_EDGE( p[ a ], p[ b ] );
-          newFace[ nNF++ ] = (signed char) ( ne - 1 );
-        }
+          VOFX_FACE_EDGE( p[ a ], p[ b ] );
         else if( ia != ib )
         {
           if( boundaryMask & ( 1u << a ) )
           {
             if( lastIsId != -1 && lastIsId != p[ a ] )
             {
-              VOFX_PUSH_EDGE( p[ a ], lastIsId );
-              newFace[ nNF++ ] = (signed char) ( ne - 1 );
-              VOFX_PUSH_EDGE( lastIsId, p[ a ] );
-              isect[ nIF++ ] = (signed char) ( ne - 1 );
+              VOFX_FACE_EDGE( p[ a ], lastIsId );
+              VOFX_CAP_EDGE( lastIsId, p[ a ] );
             }
             lastIsId = p[ a ];
           }
@@ -348,10 +313,8 @@ namespace vofx
           {
             if( lastIsId != -1 && lastIsId != p[ b ] )
             {
-              VOFX_PUSH_EDGE( lastIsId, p[ b ] );
-              newFace[ nNF++ ] = (signed char) ( ne - 1 );
-              VOFX_PUSH_EDGE( p[ b ], lastIsId );
-              isect[ nIF++ ] = (signed char) ( ne - 1 );
+              VOFX_FACE_EDGE( lastIsId, p[ b ] );
+              VOFX_CAP_EDGE( p[ b ], lastIsId );
             }
             lastIsId = p[ b ];
           }
@@ -361,76 +324,144 @@ namespace vofx
             if( isNodeId == -1 )
             {
               isNodeId = n + nNew;
-              edge_plane_point( poly.x[ a ], poly.x[ b ], hs, s.x[ isNodeId ] );
+              t.cutA[ nNew ] = (signed char) a;
+              t.cutB[ nNew ] = (signed char) b;
               nNew++;
               cutNode[ edge ] = (signed char) isNodeId;
             }
             if( ia )
             {
-              VOFX_PUSH_EDGE( p[ a ], isNodeId );
-              newFace[ nNF++ ] = (signed char) ( ne - 1 );
+              VOFX_FACE_EDGE( p[ a ], isNodeId );
               if( lastIsId != -1 && lastIsId != isNodeId )
               {
-                VOFX_PUSH_EDGE( isNodeId, lastIsId );
-                newFace[ nNF++ ] = (signed char) ( ne - 1 );
-                VOFX_PUSH_EDGE( lastIsId, isNodeId );
-                isect[ nIF++ ] = (signed char) ( ne - 1 );
+                VOFX_FACE_EDGE( isNodeId, lastIsId );
+                VOFX_CAP_EDGE( lastIsId, isNodeId );
               }
             }
             else
             {
               if( lastIsId != -1 && lastIsId != isNodeId )
               {
-                VOFX_PUSH_EDGE( lastIsId, isNodeId );
-                newFace[ nNF++ ] = (signed char) ( ne - 1 );
-                VOFX_PUSH_EDGE( isNodeId, lastIsId );
-                isect[ nIF++ ] = (signed char) ( ne - 1 );
+                VOFX_FACE_EDGE( lastIsId, isNodeId );
+                VOFX_CAP_EDGE( isNodeId, lastIsId );
               }
-              VOFX_PUSH_EDGE( isNodeId, p[ b ] );
-              newFace[ nNF++ ] = (signed char) ( ne - 1 );
+              VOFX_FACE_EDGE( isNodeId, p[ b ] );
             }
             lastIsId = isNodeId;
           }
         }
       }
-      // all cut nodes of this face exist now, so its term of Polyhedron::volume can be taken immediately
-      // (faces are summed in this order, the intersection face last)
+#undef VOFX_FACE_EDGE
+#undef VOFX_CAP_EDGE
+      // faces are summed in this order, the intersection face last; faces with fewer than 3 edges are dropped, :185-190
       if( nNF > 2 )
-        vol += clipped_face_term( s, newFace, nNF );
+      {
+        t.flen[ t.nFaces ] = (signed char) nNF;
+        t.nFaces++;
+      }
     }
-#undef VOFX_PUSH_EDGE
+    t.nNew = nNew;
 
     // erase null edges (the reference does not re-test position i after an erase), 3d/intersect.hh:217-222
     for( int i = 0; i < nIF; ++i )
-      if( s.e0[ isect[ i ] ] == s.e1[ isect[ i ] ] )
+      if( is0[ i ] == is1[ i ] )
       {
         for( int j = i; j + 1 < nIF; ++j )
-          isect[ j ] = isect[ j + 1 ];
+        {
+          is0[ j ] = is0[ j + 1 ];
+          is1[ j ] = is1[ j + 1 ];
+        }
         nIF--;
       }
     // chain the edges of the intersection face, :224-239
     for( int i = 0; i + 1 < nIF; ++i )
     {
-      if( s.e1[ isect[ i ] ] == s.e0[ isect[ i + 1 ] ] )
+      if( is1[ i ] == is0[ i + 1 ] )
         continue;
-      const int index = s.e1[ isect[ i ] ];
+      const int index = is1[ i ];
       int pos = -1;
       for( int j = i; j < nIF; ++j )
-        if( s.e0[ isect[ j ] ] == index )
+        if( is0[ j ] == index )
         {
           pos = j;
           break;
         }
       if( pos != -1 )
       {
-        const signed char t = isect[ i + 1 ];
-        isect[ i + 1 ] = isect[ pos ];
-        isect[ pos ] = t;
+        signed char s = is0[ i + 1 ];
+        is0[ i + 1 ] = is0[ pos ];
+        is0[ pos ] = s;
+        s = is1[ i + 1 ];
+        is1[ i + 1 ] = is1[ pos ];
+        is1[ pos ] = s;
       }
     }
     if( nIF > 2 )
-      vol += clipped_face_term( s, isect, nIF );
+    {
+      for( int i = 0; i < nIF; ++i )
+      {
+        t.fe0[ t.nFaces ][ i ] = is0[ i ];
+        t.fe1[ t.nFaces ][ i ] = is1[ i ];
+      }
+      t.flen[ t.nFaces ] = (signed char) nIF;
+      t.nFaces++;
+    }
+    return true;
+  }
 
+  // contribution ( face.center() . face.outerNormal() ) * face.volume() of one face given as directed edges between
+  // rows of the node table x, 3d/polyhedron.hh:187-222
+  VOFX_HD inline double clipped_face_term ( const double ( *x )[ 3 ], const signed char *e0, const signed char *e1, int n )
+  {
+    double center[ 3 ] = { 0.0, 0.0, 0.0 }, fn[ 3 ];
+    for( int i = 0; i < n; ++i )
+      for( int d = 0; d < 3; ++d )
+        center[ d ] += x[ e0[ i ] ][ d ];
+    const double inv = 1.0 / n;
+    for( int d = 0; d < 3; ++d )
+      center[ d ] *= inv;
+    outer_normal3( x[ e0[ 0 ] ], x[ e0[ 1 ] ], x[ e0[ 2 ] ], fn );
+    double fv = 0.0;
+    for( int i = 0; i < n; ++i )
+      fv += face_edge_term( x[ e0[ i ] ], x[ e1[ i ] ], fn );
+    return dot3( center, fn ) * fabs( fv / 2.0 );
+  }
+
+  // classification of the nodes, 3d/intersect.hh:99-112
+  VOFX_HD inline void clip_classify ( const Hex &poly, const Hs3 &hs, unsigned &innerMask, unsigned &boundaryMask )
+  {
+    innerMask = boundaryMask = 0;
+    for( int i = 0; i < 8; ++i )
+    {
+      const double ls = level_set( hs, poly.x[ i ] );
+      if( ls > -kEps )
+      {
+        innerMask |= 1u << i;
+        if( fabs( ls ) < kEps )
+          boundaryMask |= 1u << i;
+      }
+    }
+  }
+
+  // volume of { hex } n { hs > 0 }: 3d/intersect.hh:72-263 + 3d/polyhedron.hh:317-324
+  VOFX_HD inline double clip_volume ( const Hex &poly, const Hs3 &hs )
+  {
+    if( !hs_valid( hs ) )
+      return fabs( 0.0 / 3.0 );
+    unsigned innerMask, boundaryMask;
+    clip_classify( poly, hs, innerMask, boundaryMask );
+    ClipTopo t;
+    if( !clip_walk( innerMask, boundaryMask, t ) )
+      return fabs( 0.0 / 3.0 );
+    double x[ 20 ][ 3 ];
+    for( int k = 0; k < t.n; ++k )
+      for( int d = 0; d < 3; ++d )
+        x[ k ][ d ] = poly.x[ t.innerNode[ k ] ][ d ];
+    for( int j = 0; j < t.nNew; ++j )
+      edge_plane_point( poly.x[ t.cutA[ j ] ], poly.x[ t.cutB[ j ] ], hs, x[ t.n + j ] );
+    double vol = 0.0;
+    for( int f = 0; f < t.nFaces; ++f )
+      vol += clipped_face_term( x, t.fe0[ f ], t.fe1[ f ], t.flen[ f ] );
     return fabs( vol / 3.0 );
   }
 
@@ -588,7 +619,7 @@ namespace vofx
     const double norm = norm2( dv[ 0 ], dv[ 1 ] );
     if( norm > 0 )
       for( int c = 0; c < 3; ++c )
-        dv[ c ] /= norm;
+        dv[ c ] = vdiv( dv[ c ], norm );
   }
 
   // PolygonWithDirections::initialize, 3d/polygonwithdirections.hh:76-174.  ids = node ids sorted by height, ds = sorted heights
@@ -758,7 +789,7 @@ namespace vofx
           }
           double dv[ 3 ];
           direction_vector( P, dirEdge, dv );
-          const double f = h / dv[ 2 ];
+          const double f = vdiv( h, dv[ 2 ] );
           const double ax = dv[ 0 ] * f, ay = dv[ 1 ] * f;
           nx[ nNew ] = s.px[ n ] + ax;
           ny[ nNew ] = s.py[ n ] + ay;
@@ -822,7 +853,7 @@ namespace vofx
   {
     double A, B, C, target;
     // V(h) of geometry/algorithm.hh:211 (minus the target of :223)
-    VOFX_HD double operator() ( double h ) const { return ( C * h + B * h * h / 2.0 + A * h * h * h / 6.0 ) - target; }
+    VOFX_HD double operator() ( double h ) const { return ( C * h + B * h * h / 2.0 + vdiv( A * h * h * h, 6.0 ) ) - target; }
   };
 
   // locateHalfSpace( Polyhedron, innerNormal, fraction ), geometry/algorithm.hh:119-236.  Returns the plane constant;
@@ -884,13 +915,13 @@ namespace vofx
         double v1[ 3 ], v2[ 3 ];
         direction_vector( P, s.dirs[ n ].e[ epsn ], v1 );
         direction_vector( P, s.dirs[ nxt ].e[ 0 ], v2 );
-        A -= ( v1[ 0 ] * v2[ 1 ] - v1[ 1 ] * v2[ 0 ] ) / ( v1[ 2 ] * v2[ 2 ] );
+        A -= vdiv( v1[ 0 ] * v2[ 1 ] - v1[ 1 ] * v2[ 0 ], v1[ 2 ] * v2[ 2 ] );
         for( int l = 0; l < epsn; ++l )
         {
           double w1[ 3 ], w2[ 3 ];
           direction_vector( P, s.dirs[ n ].e[ l ], w1 );
           direction_vector( P, s.dirs[ n ].e[ l + 1 ], w2 );
-          A -= ( w1[ 0 ] * w2[ 1 ] - w1[ 1 ] * w2[ 0 ] ) / ( w1[ 2 ] * w2[ 2 ] );
+          A -= vdiv( w1[ 0 ] * w2[ 1 ] - w1[ 1 ] * w2[ 0 ], w1[ 2 ] * w2[ 2 ] );
         }
       }
 
@@ -907,7 +938,7 @@ namespace vofx
         {
           const int j = ( i + 1 == s.nn ) ? 0 : i + 1;
           const double ex = s.px[ j ] - s.px[ i ], ey = s.py[ j ] - s.py[ i ];
-          B -= norm2( ex, ey ) * normal[ 2 ] / norm;
+          B -= vdiv( norm2( ex, ey ) * normal[ 2 ], norm );
         }
       }
 
@@ -919,8 +950,8 @@ namespace vofx
         const double ex = s.px[ j ] - s.px[ i ], ey = s.py[ j ] - s.py[ i ];
         double onx = ey, ony = -ex;
         const double nrm = norm2( onx, ony );
-        onx /= nrm;
-        ony /= nrm;
+        onx = vdiv( onx, nrm );
+        ony = vdiv( ony, nrm );
         const double cx = ( s.px[ i ] + s.px[ j ] ) * 0.5, cy = ( s.py[ i ] + s.py[ j ] ) * 0.5;
         C += dot2( cx, cy, onx, ony ) * norm2( ex, ey );
       }
@@ -972,7 +1003,7 @@ namespace vofx
     cross3( a, b, f.unitNormal );
     const double nrm = norm3( f.unitNormal );
     for( int k = 0; k < 3; ++k )
-      f.unitNormal[ k ] /= nrm;
+      f.unitNormal[ k ] = vdiv( f.unitNormal[ k ], nrm );
   }
 
   // __impl::intersect( Polyhedron, HyperPlane ), 3d/intersect.hh:274-355 (eps = 1e-12)

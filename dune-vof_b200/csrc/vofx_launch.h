@@ -46,6 +46,11 @@ namespace vofx
                    int capacity, double *hs, int maxIterations );
     void flux3 ( int blocks, cudaStream_t s, Grid g, const Velocity *velocity, const double *hs, const unsigned char *flags, const int *mixedList,
                  StepState *state, int capacity, FluxRecord *records, const double *timeOverride, const double *dtOverride );
+    void flux_prepare3 ( int blocks, cudaStream_t s, Grid g, const Velocity *velocity, const unsigned char *flags, const int *mixedList, StepState *state,
+                         int capacity, FluxRecord *records, int *tasks, int taskCapacity, const double *timeOverride, const double *dtOverride );
+    void flux_clip3 ( int blocks, cudaStream_t s, Grid g, const Velocity *velocity, const double *hs, const unsigned char *flags, const int *mixedList,
+                      StepState *state, FluxRecord *records, int *tasks, const void *clipTable, int taskCapacity, const double *timeOverride, const double *dtOverride );
+    void make_clip_table ( void *host256x64 );   // 256 entries of 64 bytes (coop::ClipCase)
     void test_locate3 ( int blocks, long long count, const double *lo, const double *h, const double *normal, const double *fraction, double *out );
     void test_flux3 ( int blocks, long long count, const double *lo, const double *h, const int *face, const double *v, const double *hs, double *out );
     void test_interface3 ( int blocks, long long count, const double *lo, const double *h, const double *hs, int *nverts, double *centroid, double *measure );

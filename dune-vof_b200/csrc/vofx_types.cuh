@@ -16,7 +16,9 @@ namespace vofx
     int mixedCount;             // entries in the mixed list
     int mixedCountLast;
     int overflow;               // mixed list capacity exceeded
-    int pad;
+    int taskCount;              // entries in the clip-task list of the current step (k_flux_prepare -> k_flux_clip)
+    int serialCount;            // clip tasks left to the serial kernel (stored from the end of the task array)
+    int serialLocate;           // mixed cells whose plane-constant solve is left to the serial kernel
   };
 
   // per mixed cell: what it adds to its own update and to each face neighbour's update (Appendix C of SURVEY.md)

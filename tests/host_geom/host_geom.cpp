@@ -5,6 +5,7 @@
 
 #include "vofx_geom2d.cuh"
 #include "vofx_geom3d.cuh"
+#include "vofx_coop3d.cuh"
 
 using namespace vofx;
 
@@ -103,5 +104,57 @@ extern "C"
   }
 
   double hg_det_cospi ( double s ) { return det_cospi( s ); }
+
+  // the 8-lane cooperative flux (vofx_coop3d.cuh), lanes emulated phase by phase.  *path: 0 table, 1 empty, 2 serial
+  int hg_flux_coop ( const double *lo, const double *h, int face, const double *v, const double *hs, double *out, int *path )
+  {
+    static coop::ClipCase table[ 256 ];
+    static bool have = false;
+    if( !have )
+    {
+      coop::make_clip_table( table );
+      have = true;
+    }
+    const Hs3 H = { { hs[ 0 ], hs[ 1 ], hs[ 2 ] }, hs[ 3 ] };
+    if( !hs_valid( H ) )
+    {
+      *out = fabs( 0.0 / 3.0 );
+      *path = 1;
+      return 0;
+    }
+    coop::ClipScratch S;
+    for( int lane = 0; lane < 8; ++lane )
+    {
+      double xn[ 3 ];
+      coop::upwind_node( lane, lo, h, face, v, xn );
+      coop::clip_phase_classify( lane, S, xn, H );
+    }
+    const coop::ClipCase *cs = nullptr;
+    int status = 0;
+    for( int lane = 0; lane < 8; ++lane )
+      status = coop::clip_phase_cut( lane, S, H, table, cs );
+    *path = status;
+    if( status == 1 )
+      *out = fabs( 0.0 / 3.0 );
+    else if( status == 2 )
+      *out = coop::clip_serial_from_scratch( S, H );
+    else
+    {
+      for( int lane = 0; lane < 8; ++lane )
+        coop::clip_phase_faces( lane, S, *cs );
+      *out = coop::clip_phase_sum( S, *cs );
+    }
+    return 0;
+  }
+
+  int hg_clip_table_irregular ( void )
+  {
+    coop::ClipCase table[ 256 ];
+    coop::make_clip_table( table );
+    int n = 0;
+    for( int m = 0; m < 256; ++m )
+      n += table[ m ].nCut == 0xFF;
+    return n;
+  }
 
 } // extern "C"

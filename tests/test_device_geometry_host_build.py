@@ -45,6 +45,15 @@ def hg_flux(L, lo, h, face, vel, hs):
     return out.value
 
 
+def hg_flux_coop(L, lo, h, face, vel, hs):
+    """the 8-lane cooperative clip of vofx_coop3d.cuh, lanes emulated phase by phase; returns (flux, path)"""
+    lo, h, vel, hs = _v(lo), _v(h), _v(vel), _v(hs)
+    out = C.c_double(0)
+    path = C.c_int(-1)
+    L.hg_flux_coop(_d(lo), _d(h), int(face), _d(vel), _d(hs), C.byref(out), C.byref(path))
+    return out.value, path.value
+
+
 def hg_vf(L, lo, h, hs):
     lo, h, hs = _v(lo), _v(h), _v(hs)
     out = C.c_double(0)
@@ -66,6 +75,7 @@ def hg_iface(L, lo, h, hs):
 @pytest.mark.parametrize("dim", [2, 3])
 def test_geometry_bit_exact(hg, dim):
     rng = np.random.default_rng(70 + dim)
+    paths = {}
     for it in range(6000):
         res = int(rng.choice([64, 128, 512, 1024, 4096, 100, 37]))
         h = np.full(dim, 1.0 / res)
@@ -100,11 +110,20 @@ def test_geometry_bit_exact(hg, dim):
         vel = rng.normal(size=dim) * h[0] * 0.5
         if it % 11 == 3:
             vel[rng.integers(0, dim)] = 0
-        assert same_bits(O.flux(lo, h, face, vel, hs), hg_flux(hg, lo, h, face, vel, hs))
+        fo = O.flux(lo, h, face, vel, hs)
+        assert same_bits(fo, hg_flux(hg, lo, h, face, vel, hs))
+        if dim == 3:
+            fc, path = hg_flux_coop(hg, lo, h, face, vel, hs)
+            assert same_bits(fo, fc), (path, lo, h, face, vel, hs)
+            paths[path] = paths.get(path, 0) + 1
         assert same_bits(O.volume_fraction(lo, h, hs), hg_vf(hg, lo, h, hs))
         na, va, ca, ma = O.interface(lo, h, hs)
         nb, vb, cb, mb = hg_iface(hg, lo, h, hs)
         assert na == nb and same_bits(va, vb) and same_bits(ca, cb) and same_bits(ma, mb)
+    if dim == 3:
+        # the table path must carry the bulk of the clips; the serial path is for nodes on the plane
+        assert paths.get(0, 0) > 2000 and paths.get(2, 0) < 0.2 * sum(paths.values()), paths
+        print("cooperative clip paths (0 table, 1 empty, 2 serial):", paths)
 
 
 def test_det_cospi_matches_oracle(hg):
