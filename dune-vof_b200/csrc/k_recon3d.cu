@@ -8,6 +8,23 @@ namespace vofx
   {
     void youngs3 ( int blocks, cudaStream_t s, Grid g, const double *u, const int *mixedList, const StepState *state, int capacity, double *hs )
     { k_youngs< 3 ><<< blocks, 128, 0, s >>>( g, u, mixedList, state, capacity, hs ); }
+    void youngs_coop3 ( int lanes, int blocks, cudaStream_t s, Grid g, const double *u, const int *mixedList, StepState *state, int capacity, double *hs,
+                        const void *sweepTable, int *serialCells )
+    {
+      if( lanes == 4 )
+        k_youngs_coop3< 4 ><<< blocks * 2, 64, 0, s >>>( g, u, mixedList, state, capacity, hs, (const coop::SweepTable *) sweepTable, serialCells );
+      else
+        k_youngs_coop3< 8 ><<< blocks, 128, 0, s >>>( g, u, mixedList, state, capacity, hs, (const coop::SweepTable *) sweepTable, serialCells );
+    }
+    void locate_serial3 ( cudaStream_t s, Grid g, const double *u, const StepState *state, double *hs, const int *serialCells )
+    { k_locate_serial3< 3 ><<< 148, 64, 0, s >>>( g, u, state, hs, serialCells ); }
+    int make_sweep_table ( void *host, size_t bytes )
+    {
+      if( bytes < sizeof( coop::SweepTable ) )
+        return -1;
+      return coop::make_sweep_table( *(coop::SweepTable *) host );
+    }
+    size_t sweep_table_bytes () { return sizeof( coop::SweepTable ); }
     void hf3 ( int blocks, cudaStream_t s, Grid g, const double *u, const int *mixedList, const StepState *state, int capacity, double *hs )
     { k_hf< 3 ><<< blocks, 128, 0, s >>>( g, u, mixedList, state, capacity, hs ); }
   } // namespace launch

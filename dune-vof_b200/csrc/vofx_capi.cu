@@ -5,6 +5,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -51,6 +52,9 @@ struct vofx_ctx
   FluxRecord *records = nullptr;
   int *tasks = nullptr;             // 3D clip tasks ( mixed-list slot * 8 + face ), at most 6 per mixed cell
   int taskCapacity = 0;
+  void *sweepTable = nullptr;       // coop::SweepTable
+  int *serialCells = nullptr;       // mixed cells whose plane constant is left to the serial walk
+  int lanesPerCell = 8;
   void *clipTable = nullptr;        // coop::ClipCase[ 256 ]
   StepState *state = nullptr;
   double *curv1 = nullptr;
@@ -210,8 +214,16 @@ namespace
     if( g.dim == 2 )
       launch::youngs2( blocks, ctx->stream, g, u, ctx->mixedList, ctx->state, ctx->capacity, hs );
     else
-      launch::youngs3( blocks, ctx->stream, g, u, ctx->mixedList, ctx->state, ctx->capacity, hs );
-    int rc = checkLaunch( ctx, "k_youngs" );
+    {
+      launch::youngs_coop3( ctx->lanesPerCell, blocks, ctx->stream, g, u, ctx->mixedList, ctx->state, ctx->capacity, hs, ctx->sweepTable, ctx->serialCells );
+      int rc3 = checkLaunch( ctx, "k_youngs" );
+      if( rc3 )
+        return rc3;
+      // cells whose walk hits a state the reference leaves undefined (never seen on the BASELINE configs): serial kernel
+      profBegin( ctx );
+      launch::locate_serial3( ctx->stream, g, u, ctx->state, hs, ctx->serialCells );
+    }
+    int rc = checkLaunch( ctx, g.dim == 2 ? "k_youngs" : "k_locate_serial" );
     if( rc )
       return rc;
     if( kind == VOFX_RECON_HF )
@@ -443,6 +455,8 @@ extern "C"
       ctx->taskCapacity = (int) ( tc < ( 1LL << 30 ) ? tc : ( 1LL << 30 ) );
       alloc( (void **) &ctx->tasks, sizeof( int ) * (size_t) ctx->taskCapacity );
       alloc( (void **) &ctx->clipTable, 256 * 64 );
+      alloc( (void **) &ctx->sweepTable, launch::sweep_table_bytes() );
+      alloc( (void **) &ctx->serialCells, sizeof( int ) * (size_t) ctx->capacity );
     }
     alloc( (void **) &ctx->curv1, sizeof( double ) * (size_t) ctx->capacity );
     alloc( (void **) &ctx->ok1, (size_t) ctx->capacity );
@@ -457,6 +471,18 @@ extern "C"
     std::memset( &init, 0, sizeof( init ) );
     init.dtEst = DBL_MAX;
     cudaMemcpy( ctx->state, &init, sizeof( init ), cudaMemcpyHostToDevice );
+    if( ctx->sweepTable )
+    {
+      std::vector< unsigned char > table( launch::sweep_table_bytes() );
+      if( launch::make_sweep_table( table.data(), table.size() ) != 96 )
+      {
+        vofx_destroy( ctx );
+        return fail( VOFX_ERR_STATE, "sweep table generation failed" );
+      }
+      cudaMemcpy( ctx->sweepTable, table.data(), table.size(), cudaMemcpyHostToDevice );
+      if( const char *env = std::getenv( "VOFX_LANES_PER_CELL" ) )
+        ctx->lanesPerCell = ( std::atoi( env ) == 4 ) ? 4 : 8;
+    }
     if( ctx->clipTable )
     {
       std::vector< unsigned char > table( 256 * 64 );
@@ -478,6 +504,8 @@ extern "C"
     cudaFree( ctx->records );
     cudaFree( ctx->tasks );
     cudaFree( ctx->clipTable );
+    cudaFree( ctx->sweepTable );
+    cudaFree( ctx->serialCells );
     cudaFree( ctx->state );
     cudaFree( ctx->curv1 );
     cudaFree( ctx->ok1 );

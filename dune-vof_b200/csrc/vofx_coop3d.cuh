@@ -227,3 +227,659 @@ namespace vofx
 
   } // namespace coop
 } // namespace vofx
+
+// ====================================================================================================================
+// G2 for groups of lanes: plane-constant solve of a Cartesian cell with the sweep topology looked up by the order of
+// the node heights.
+//
+// For a hexahedron whose eight rotated node heights are pairwise distinct (by more than the reference's 1e-10 merge
+// tolerance) everything PolygonWithDirections does between the brackets (3d/polygonwithdirections.hh:76-290) depends
+// only on the ORDER of the heights: which polygon nodes exist, which edge each one slides along, the direction lists
+// and the faces the polygon edges lie in.  There are 96 such orders for a box (lowest node x order of the three axis
+// increments x whether the third increment exceeds the sum of the other two); the table is generated by running the
+// reference's walk (sweep_init / sweep_evolve of vofx_geom3d.cuh) on synthetic heights.  Cells with merged or tied
+// heights (axis-aligned normals) are left to the serial walk.
+// ====================================================================================================================
+namespace vofx
+{
+  namespace coop
+  {
+
+    constexpr int kSweepCases = 96;
+    constexpr int kMaxPoly = 8;       // nodes of the cross-section polygon (6 for a generic box; 8 = the walk's own bound)
+    constexpr int kMaxATerms = 12;
+
+    // what the arithmetic of one bracket [ d_k, d_k+1 ] needs to know about the sweep polygon
+    struct SweepBracket
+    {
+      unsigned char nn, nEdges, nA, ok;      // ok = 0: the walk ran into a state the reference does not define
+      unsigned char srcNode[ kMaxPoly ];     // parent node id (srcEdge == 0xFF) or index of the old polygon node it slides from
+      unsigned char srcEdge[ kMaxPoly ];     // directed edge the node slides along, 0xFF: the node IS the parent node
+      unsigned char corrFace[ kMaxPoly ];    // face of the hexahedron that holds polygon edge (i, i+1)
+      unsigned char aE1[ kMaxATerms ], aE2[ kMaxATerms ];   // pairs of directed edges of the A terms, in summation order
+      unsigned char pad[ 4 ];
+    };
+    static_assert( sizeof( SweepBracket ) == 56, "SweepBracket layout" );
+
+    struct SweepCase
+    {
+      unsigned char perm[ 8 ];               // node ids by ascending height
+      SweepBracket bracket[ 7 ];
+    };
+    static_assert( sizeof( SweepCase ) == 400, "SweepCase layout" );
+
+    struct SweepTable
+    {
+      unsigned char caseOf[ 1024 ];          // sweep_key( ids[0..3] ) -> case or 0xFF
+      SweepCase cases[ kSweepCases ];
+    };
+
+    // the three lowest nodes and whether the fourth is their common "diagonal" (else it is the third axis neighbour)
+    VOFX_INLINE int sweep_key ( int i0, int i1, int i2, int i3 ) { return i0 | ( i1 << 3 ) | ( i2 << 6 ) | ( ( i3 == ( i0 ^ i1 ^ i2 ) ) ? 512 : 0 ); }
+
+    // descriptor of the current polygon of the walk: nodes, faces of its edges, and the A terms in the order of
+    // geometry/algorithm.hh:177-194
+    VOFX_HD inline void sweep_describe ( const Sweep &s, SweepBracket &B )
+    {
+      B.ok = 0;
+      B.nn = (unsigned char) s.nn;
+      B.nEdges = (unsigned char) s.nEdges;
+      B.nA = 0;
+      if( s.degenerate || s.nn > kMaxPoly || s.nEdges > kMaxPoly || s.nEdges > s.nCF )
+        return;
+      for( int a = 0; a < s.nn; ++a )
+      {
+        B.srcNode[ a ] = (unsigned char) s.srcNode[ a ];
+        B.srcEdge[ a ] = ( s.srcEdge[ a ] < 0 ) ? (unsigned char) 0xFF : (unsigned char) s.srcEdge[ a ];
+      }
+      for( int i = 0; i < s.nEdges; ++i )
+        B.corrFace[ i ] = (unsigned char) s.corrFace[ i ];
+      int nA = 0;
+      for( int n = 0; n < s.nn; ++n )
+      {
+        const int nxt = ( n + 1 == s.nn ) ? 0 : n + 1;
+        if( s.dirs[ n ].n == 0 || s.dirs[ nxt ].n == 0 )
+          return;                                        // reference: assert( !directions( n ).empty() )
+        const int epsn = s.dirs[ n ].n - 1;
+        if( nA + 1 + epsn > kMaxATerms )
+          return;
+        B.aE1[ nA ] = (unsigned char) s.dirs[ n ].e[ epsn ];
+        B.aE2[ nA ] = (unsigned char) s.dirs[ nxt ].e[ 0 ];
+        nA++;
+        for( int l = 0; l < epsn; ++l )
+        {
+          B.aE1[ nA ] = (unsigned char) s.dirs[ n ].e[ l ];
+          B.aE2[ nA ] = (unsigned char) s.dirs[ n ].e[ l + 1 ];
+          nA++;
+        }
+      }
+      B.nA = (unsigned char) nA;
+      B.ok = 1;
+    }
+
+    // returns the number of cases generated (96) or -1 if a case does not fit
+    inline int make_sweep_table ( SweepTable &T )
+    {
+      for( int i = 0; i < 1024; ++i )
+        T.caseOf[ i ] = 0xFF;
+      int nCases = 0;
+      for( int low = 0; low < 8; ++low )
+        for( int ax1 = 0; ax1 < 3; ++ax1 )
+          for( int ax2 = 0; ax2 < 3; ++ax2 )
+          {
+            if( ax2 == ax1 )
+              continue;
+            const int ax3 = 3 - ax1 - ax2;
+            for( int third = 0; third < 2; ++third )
+            {
+              double inc[ 3 ];
+              inc[ ax1 ] = 1.0;
+              inc[ ax2 ] = 2.0;
+              inc[ ax3 ] = third ? 2.5 : 4.0;          // 2.5 < 1 + 2 < 4
+              double z[ 8 ];
+              for( int i = 0; i < 8; ++i )
+              {
+                z[ i ] = 0.0;
+                for( int d = 0; d < 3; ++d )
+                  if( ( ( i ^ low ) >> d ) & 1 )
+                    z[ i ] += inc[ d ];
+              }
+              int ids[ 8 ];
+              double ds[ 8 ];
+              for( int i = 0; i < 8; ++i )
+              {
+                const double di = z[ i ];
+                int j = i;
+                while( j > 0 && di < ds[ j - 1 ] )
+                {
+                  ds[ j ] = ds[ j - 1 ];
+                  ids[ j ] = ids[ j - 1 ];
+                  --j;
+                }
+                ds[ j ] = di;
+                ids[ j ] = i;
+              }
+              if( nCases >= kSweepCases )
+                return -1;
+              SweepCase &C = T.cases[ nCases ];
+              for( unsigned b = 0; b < sizeof( SweepCase ); ++b )
+                reinterpret_cast< unsigned char * >( &C )[ b ] = 0;
+              for( int i = 0; i < 8; ++i )
+                C.perm[ i ] = (unsigned char) ids[ i ];
+
+              Sweep s;
+              sweep_init< false >( s, nullptr, ids, ds );
+              for( int k = 0; k < 7; ++k )
+              {
+                sweep_describe( s, C.bracket[ k ] );
+                if( !C.bracket[ k ].ok || C.bracket[ k ].nn > 6 )
+                  return -1;
+                if( k < 6 )
+                  sweep_evolve< false >( s, nullptr, z, ds[ k ], ds[ k + 1 ], ds[ k + 1 ] - ds[ k ] );
+              }
+              if( T.caseOf[ sweep_key( ids[ 0 ], ids[ 1 ], ids[ 2 ], ids[ 3 ] ) ] != 0xFF )
+                return -1;
+              T.caseOf[ sweep_key( ids[ 0 ], ids[ 1 ], ids[ 2 ], ids[ 3 ] ) ] = (unsigned char) nCases;
+              nCases++;
+            }
+          }
+      return nCases;
+    }
+
+  } // namespace coop
+} // namespace vofx
+
+namespace vofx
+{
+  namespace coop
+  {
+
+    // A group of L lanes working on one item.  Device: L consecutive lanes of a warp, sync() = __syncwarp on their mask.
+    // Host (tests): the lanes are emulated by a loop, phase by phase.
+    struct Group
+    {
+      int lane;
+      unsigned mask;
+      VOFX_INLINE void sync () const
+      {
+#if defined( __CUDA_ARCH__ )
+        __syncwarp( mask );
+#endif
+      }
+    };
+
+    // VOFX_LANES( G, L, lane ) { phase }: the phase is run by every lane of the group; a group barrier follows.
+    // Code between two phases is "uniform": every lane computes the same values from the scratch.
+#if defined( __CUDA_ARCH__ )
+#define VOFX_LANES( G, L, lane ) for( int lane = ( G ).lane, vofx_once_ = 1; vofx_once_; vofx_once_ = 0, ( G ).sync() )
+#else
+#define VOFX_LANES( G, L, lane ) for( int lane = 0; lane < ( L ); ++lane )
+#endif
+
+    struct LocateScratch
+    {
+      double P[ 3 ][ 8 ];               // rotated nodes
+      union
+      {
+        double dv[ 3 ][ 24 ];           // PolygonWithDirections::directionVector of every directed edge
+        double ls[ 8 ][ 9 ];            // least-squares contributions of one round of stencil slots (before the solve)
+      };
+      double fnz[ 6 ], fnrm[ 6 ];       // outer normal of face f of P: z component, norm of the xy part
+      double px[ 2 ][ 8 ], py[ 2 ][ 8 ];   // polygon nodes of the current / next bracket
+      double aterm[ kMaxATerms ], bterm[ 8 ], cterm[ 8 ];
+      double term[ 8 ];                 // face terms of the cell volume
+      double ds[ 8 ];                   // sorted node heights
+      double sums[ 12 ];                // AtA (6 unique entries) and Atb
+      unsigned char ids[ 8 ];
+      unsigned char lsValid[ 8 ];
+      SweepBracket walked;              // descriptor produced by the walk of lane 0 (cells with tied node heights)
+      Sweep sweep;                      // state of that walk (topology only)
+      double bankPad[ 1 ];              // see the static_assert below
+    };
+    // consecutive groups of a warp address the same members: an odd stride in 8-byte words spreads them over the banks
+    static_assert( sizeof( LocateScratch ) % 8 == 0 && ( sizeof( LocateScratch ) / 8 ) % 2 == 1, "LocateScratch stride must be an odd number of doubles" );
+
+    // the walk of lane 0 for cells with tied node heights: rare, kept out of line so that the hot path stays compact
+    // in the instruction cache (the inlined walk is 11k of the kernel's 20k instructions)
+    VOFX_NOINLINE static void walk_begin ( Sweep &sweep, SweepBracket &walked, const unsigned char *ids8, const double *ds )
+    {
+      int ids[ 8 ];
+      for( int k = 0; k < 8; ++k )
+        ids[ k ] = ids8[ k ];
+      sweep_init< false >( sweep, nullptr, ids, ds );
+      sweep_describe( sweep, walked );
+    }
+
+    VOFX_NOINLINE static void walk_next ( Sweep &sweep, SweepBracket &walked, const double *z, double dk, double dk1 )
+    {
+      sweep_evolve< false >( sweep, nullptr, z, dk, dk1, dk1 - dk );
+      sweep_describe( sweep, walked );
+    }
+
+    VOFX_INLINE void cell_node ( const double *lo, const double *hi, int i, double *x )
+    {
+      x[ 0 ] = ( i & 1 ) ? hi[ 0 ] : lo[ 0 ];
+      x[ 1 ] = ( i & 2 ) ? hi[ 1 ] : lo[ 1 ];
+      x[ 2 ] = ( i & 4 ) ? hi[ 2 ] : lo[ 2 ];
+    }
+
+    // locateHalfSpace( Polyhedron( cube geometry ), innerNormal, fraction ), geometry/algorithm.hh:119-236, for a group of
+    // L lanes.  Returns true and the plane constant, or false if the cell must take the serial walk (tied node heights).
+    template< int L >
+    VOFX_HD inline bool locate_coop ( const Group &G, LocateScratch &S, const SweepTable &T, const double *lo, const double *h,
+                                      const double *innerNormal, double fraction, double &dist )
+    {
+      double hi[ 3 ], outerNormal[ 3 ];
+      for( int k = 0; k < 3; ++k )
+      {
+        hi[ k ] = lo[ k ] + h[ k ];                      // make_cell: lo + h
+        outerNormal[ k ] = innerNormal[ k ] * -1.0;
+      }
+      fraction = ( fraction > 1.0 ) ? 1.0 : fraction;
+      fraction = ( fraction < 0.0 ) ? 0.0 : fraction;
+
+      // rotateToReferenceFrame, 3d/rotation.hh:17-53
+      const double *n = outerNormal;
+      const bool identity = ( n[ 0 ] == 0.0 && n[ 1 ] == 0.0 && n[ 2 ] == 1.0 );
+      double R[ 3 ][ 3 ] = { { 0.0, 0.0, 0.0 }, { 0.0, 0.0, 0.0 }, { 0.0, 0.0, 0.0 } };
+      if( n[ 0 ] == 0.0 && n[ 1 ] == 0.0 && n[ 2 ] == -1.0 )
+      {
+        R[ 0 ][ 0 ] = 1.0;
+        R[ 1 ][ 1 ] = -1.0;
+        R[ 2 ][ 2 ] = -1.0;
+      }
+      else if( !identity )
+      {
+        const double gamma = ( 1 - n[ 2 ] ) / ( n[ 0 ] * n[ 0 ] + n[ 1 ] * n[ 1 ] );
+        R[ 0 ][ 0 ] = n[ 1 ] * n[ 1 ] * gamma + n[ 2 ];
+        R[ 0 ][ 1 ] = -n[ 0 ] * n[ 1 ] * gamma;
+        R[ 1 ][ 0 ] = R[ 0 ][ 1 ];
+        R[ 0 ][ 2 ] = -n[ 0 ];
+        R[ 1 ][ 1 ] = n[ 0 ] * n[ 0 ] * gamma + n[ 2 ];
+        R[ 1 ][ 2 ] = -n[ 1 ];
+        R[ 2 ][ 0 ] = n[ 0 ];
+        R[ 2 ][ 1 ] = n[ 1 ];
+        R[ 2 ][ 2 ] = n[ 2 ];
+      }
+
+      // phase 1: face terms of the cell volume (hex_volume) and the rotated nodes
+      VOFX_LANES( G, L, lane )
+      {
+#pragma unroll 1
+        for( int f = lane; f < 6; f += L )
+        {
+          double x[ 4 ][ 3 ], center[ 3 ] = { 0.0, 0.0, 0.0 }, fn[ 3 ];
+          for( int k = 0; k < 4; ++k )
+          {
+            cell_node( lo, hi, cube::faceNode( f, k ), x[ k ] );
+            for( int d = 0; d < 3; ++d )
+              center[ d ] += x[ k ][ d ];
+          }
+          const double s = 1.0 / 4;
+          for( int d = 0; d < 3; ++d )
+            center[ d ] *= s;
+          outer_normal3( x[ 0 ], x[ 1 ], x[ 2 ], fn );
+          double fv = 0.0;
+          for( int k = 0; k < 4; ++k )
+            fv += face_edge_term( x[ k ], x[ ( k + 1 ) & 3 ], fn );
+          S.term[ f ] = dot3( center, fn ) * fabs( fv / 2.0 );
+        }
+#pragma unroll 1
+        for( int i = lane; i < 8; i += L )
+        {
+          double x[ 3 ];
+          cell_node( lo, hi, i, x );
+          for( int r = 0; r < 3; ++r )
+          {
+            double y = 0.0;
+            for( int c = 0; c < 3; ++c )
+              y += R[ r ][ c ] * x[ c ];
+            S.P[ r ][ i ] = identity ? x[ r ] : y;
+          }
+        }
+      }
+
+      double vol = 0.0;
+      for( int f = 0; f < 6; ++f )
+        vol += S.term[ f ];
+      const double givenVolume = fraction * fabs( vol / 3.0 );
+
+      // phase 2: sort the node heights (std::sort = stable insertion sort on 8 elements: rank by (height, id)),
+      // direction vectors of all directed edges, face normals of the rotated cell
+      VOFX_LANES( G, L, lane )
+      {
+#pragma unroll 1
+        for( int i = lane; i < 8; i += L )
+        {
+          const double zi = S.P[ 2 ][ i ];
+          int rank = 0;
+          for( int j = 0; j < 8; ++j )
+          {
+            const double zj = S.P[ 2 ][ j ];
+            rank += ( zj < zi || ( zj == zi && j < i ) ) ? 1 : 0;
+          }
+          S.ids[ rank ] = (unsigned char) i;
+          S.ds[ rank ] = zi;
+        }
+#pragma unroll 1
+        for( int e = lane; e < 24; e += L )
+        {
+          const int a = cube::edgeN0( e ), b = cube::edgeN1( e );
+          double dv[ 3 ];
+          for( int c = 0; c < 3; ++c )
+            dv[ c ] = S.P[ c ][ b ] - S.P[ c ][ a ];
+          const double norm = norm2( dv[ 0 ], dv[ 1 ] );
+          if( norm > 0 )
+            for( int c = 0; c < 3; ++c )
+              dv[ c ] = vdiv( dv[ c ], norm );
+          for( int c = 0; c < 3; ++c )
+            S.dv[ c ][ e ] = dv[ c ];
+        }
+#pragma unroll 1
+        for( int f = lane; f < 6; f += L )
+        {
+          double x[ 3 ][ 3 ], normal[ 3 ];
+          for( int k = 0; k < 3; ++k )
+          {
+            const int id = cube::faceNode( f, k );
+            for( int c = 0; c < 3; ++c )
+              x[ k ][ c ] = S.P[ c ][ id ];
+          }
+          outer_normal3( x[ 0 ], x[ 1 ], x[ 2 ], normal );
+          S.fnz[ f ] = normal[ 2 ];
+          S.fnrm[ f ] = norm2( normal[ 0 ], normal[ 1 ] );
+        }
+      }
+
+      // uniform: is this one of the tabulated height orders?
+      for( int i = 0; i < 8; ++i )
+        if( !( fabs( S.P[ 2 ][ i ] ) < DBL_MAX ) )
+          return false;                                  // NaN / inf heights: the ranks below are meaningless
+      double ds[ 8 ];
+      for( int k = 0; k < 8; ++k )
+        ds[ k ] = S.ds[ k ];
+      // std::unique with | x - y | < 1e-10 against the last kept element, geometry/algorithm.hh:160-162
+      double dU[ 8 ];
+      int nU = 0;
+      dU[ nU++ ] = ds[ 0 ];
+      for( int i = 1; i < 8; ++i )
+        if( !( fabs( dU[ nU - 1 ] - ds[ i ] ) < 1e-10 ) )
+          dU[ nU++ ] = ds[ i ];
+
+      // tabulated height order?  Otherwise (merged / tied heights) lane 0 runs the reference's walk on the topology
+      // and publishes one descriptor per bracket; the arithmetic below is the same either way.
+      const SweepCase *C = nullptr;
+      if( nU == 8 )
+      {
+        const int ci = T.caseOf[ sweep_key( S.ids[ 0 ], S.ids[ 1 ], S.ids[ 2 ], S.ids[ 3 ] ) ];
+        if( ci != 0xFF )
+        {
+          C = &T.cases[ ci ];
+          for( int k = 0; k < 8; ++k )
+            if( C->perm[ k ] != S.ids[ k ] )
+              C = nullptr;
+        }
+      }
+      const bool walking = ( C == nullptr );
+      if( walking )
+      {
+        VOFX_LANES( G, L, lane )
+        {
+          if( lane == 0 )
+          {
+            double dsCopy[ 8 ];
+            for( int k = 0; k < 8; ++k )
+              dsCopy[ k ] = S.ds[ k ];
+            walk_begin( S.sweep, S.walked, S.ids, dsCopy );
+          }
+        }
+      }
+
+      double Vd_k = 0.0;
+      for( int k = 0; k + 1 < nU; ++k )
+      {
+        if( walking && k > 0 )
+        {
+          VOFX_LANES( G, L, lane )
+          {
+            if( lane == 0 )
+              walk_next( S.sweep, S.walked, S.P[ 2 ], dU[ k - 1 ], dU[ k ] );
+          }
+        }
+        const SweepBracket &B = walking ? S.walked : C->bracket[ k ];
+        if( !B.ok )
+          return false;                                  // undefined in the reference: left to the serial kernel (NaN)
+        const int cur = k & 1;
+        const double hPrev = ( k > 0 ) ? dU[ k ] - dU[ k - 1 ] : 0.0;
+
+        // polygon nodes of this bracket (PolygonWithDirections::evolveToNextPolygon, :177-250)
+        VOFX_LANES( G, L, lane )
+        {
+#pragma unroll 1
+          for( int a = lane; a < B.nn; a += L )
+          {
+            if( B.srcEdge[ a ] == 0xFF )
+            {
+              S.px[ cur ][ a ] = S.P[ 0 ][ B.srcNode[ a ] ];
+              S.py[ cur ][ a ] = S.P[ 1 ][ B.srcNode[ a ] ];
+            }
+            else
+            {
+              const int e = B.srcEdge[ a ], from = B.srcNode[ a ];
+              const double f = vdiv( hPrev, S.dv[ 2 ][ e ] );
+              const double ax = S.dv[ 0 ][ e ] * f, ay = S.dv[ 1 ][ e ] * f;
+              S.px[ cur ][ a ] = S.px[ cur ^ 1 ][ from ] + ax;
+              S.py[ cur ][ a ] = S.py[ cur ^ 1 ][ from ] + ay;
+            }
+          }
+        }
+
+        // the terms of A, B, C (geometry/algorithm.hh:177-208), one per lane
+        VOFX_LANES( G, L, lane )
+        {
+#pragma unroll 1
+          for( int t = lane; t < B.nA; t += L )
+          {
+            const int e1 = B.aE1[ t ], e2 = B.aE2[ t ];
+            const double v1x = S.dv[ 0 ][ e1 ], v1y = S.dv[ 1 ][ e1 ], v1z = S.dv[ 2 ][ e1 ];
+            const double v2x = S.dv[ 0 ][ e2 ], v2y = S.dv[ 1 ][ e2 ], v2z = S.dv[ 2 ][ e2 ];
+            S.aterm[ t ] = vdiv( v1x * v2y - v1y * v2x, v1z * v2z );
+          }
+#pragma unroll 1
+          for( int i = lane; i < B.nEdges; i += L )
+          {
+            const int j = ( i + 1 == B.nn ) ? 0 : i + 1;
+            const double xi = S.px[ cur ][ i ], yi = S.py[ cur ][ i ], xj = S.px[ cur ][ j ], yj = S.py[ cur ][ j ];
+            const double ex = xj - xi, ey = yj - yi;
+            const int f = B.corrFace[ i ];
+            const double norm = S.fnrm[ f ];
+            S.bterm[ i ] = ( norm > 0 ) ? vdiv( norm2( ex, ey ) * S.fnz[ f ], norm ) : 0.0;
+            double onx = ey, ony = -ex;
+            const double nrm = norm2( onx, ony );
+            onx = vdiv( onx, nrm );
+            ony = vdiv( ony, nrm );
+            const double cx = ( xi + xj ) * 0.5, cy = ( yi + yj ) * 0.5;
+            S.cterm[ i ] = dot2( cx, cy, onx, ony ) * norm2( ex, ey );
+          }
+        }
+
+        double A = 0.0, Bc = 0.0, Cc = 0.0;
+#pragma unroll 1
+        for( int t = 0; t < B.nA; ++t )
+          A -= S.aterm[ t ];
+#pragma unroll 1
+        for( int i = 0; i < B.nEdges; ++i )
+        {
+          Bc -= S.bterm[ i ];
+          Cc += S.cterm[ i ];
+        }
+        Cc = fabs( Cc / 2.0 );
+
+        const double hk = dU[ k + 1 ] - dU[ k ];
+        Cubic V = { A, Bc, Cc, 0.0 };
+        const double Vd_k1 = Vd_k + V( hk );
+        if( fabs( Vd_k1 - givenVolume ) < 1e-14 )
+        {
+          dist = dU[ k + 1 ];
+          return true;
+        }
+        else if( Vd_k1 > givenVolume )
+        {
+          V.target = givenVolume - Vd_k;
+          dist = dU[ k ] + brent( V, 0.0, hk, 1e-14 );
+          return true;
+        }
+        Vd_k = Vd_k1;
+      }
+      dist = dU[ nU - 1 ];
+      return true;
+    }
+
+  } // namespace coop
+} // namespace vofx
+
+#include "vofx_grid.cuh"
+
+namespace vofx
+{
+  namespace coop
+  {
+
+    // FieldMatrix< double, 3, 3 >::solve of dune-common 2.6 (closed form, the same expression tree as solve_small< 3 >)
+    VOFX_HD inline void solve3 ( const double M[ 3 ][ 3 ], const double *b, double *x )
+    {
+      const double t4 = M[ 0 ][ 0 ] * M[ 1 ][ 1 ];
+      const double t6 = M[ 0 ][ 0 ] * M[ 1 ][ 2 ];
+      const double t8 = M[ 0 ][ 1 ] * M[ 1 ][ 0 ];
+      const double t10 = M[ 0 ][ 2 ] * M[ 1 ][ 0 ];
+      const double t12 = M[ 0 ][ 1 ] * M[ 2 ][ 0 ];
+      const double t14 = M[ 0 ][ 2 ] * M[ 2 ][ 0 ];
+      const double d = ( t4 * M[ 2 ][ 2 ] - t6 * M[ 2 ][ 1 ] - t8 * M[ 2 ][ 2 ] + t10 * M[ 2 ][ 1 ] + t12 * M[ 1 ][ 2 ] - t14 * M[ 1 ][ 1 ] );
+      x[ 0 ] = vdiv( b[ 0 ] * M[ 1 ][ 1 ] * M[ 2 ][ 2 ] - b[ 0 ] * M[ 2 ][ 1 ] * M[ 1 ][ 2 ]
+                     - b[ 1 ] * M[ 0 ][ 1 ] * M[ 2 ][ 2 ] + b[ 1 ] * M[ 2 ][ 1 ] * M[ 0 ][ 2 ]
+                     + b[ 2 ] * M[ 0 ][ 1 ] * M[ 1 ][ 2 ] - b[ 2 ] * M[ 1 ][ 1 ] * M[ 0 ][ 2 ], d );
+      x[ 1 ] = vdiv( M[ 0 ][ 0 ] * b[ 1 ] * M[ 2 ][ 2 ] - M[ 0 ][ 0 ] * b[ 2 ] * M[ 1 ][ 2 ]
+                     - M[ 1 ][ 0 ] * b[ 0 ] * M[ 2 ][ 2 ] + M[ 1 ][ 0 ] * b[ 2 ] * M[ 0 ][ 2 ]
+                     + M[ 2 ][ 0 ] * b[ 0 ] * M[ 1 ][ 2 ] - M[ 2 ][ 0 ] * b[ 1 ] * M[ 0 ][ 2 ], d );
+      x[ 2 ] = vdiv( M[ 0 ][ 0 ] * M[ 1 ][ 1 ] * b[ 2 ] - M[ 0 ][ 0 ] * M[ 2 ][ 1 ] * b[ 1 ]
+                     - M[ 1 ][ 0 ] * M[ 0 ][ 1 ] * b[ 2 ] + M[ 1 ][ 0 ] * M[ 2 ][ 1 ] * b[ 0 ]
+                     + M[ 2 ][ 0 ] * M[ 0 ][ 1 ] * b[ 1 ] - M[ 2 ][ 0 ] * M[ 1 ][ 1 ] * b[ 0 ], d );
+    }
+
+    // ModifiedYoungsReconstruction::applyLocal up to the normal, reconstruction/modifiedyoungs.hh:90-131, for a group of
+    // L lanes: slot s < 26 is the s-th vertex neighbour in ascending cell index, slot 26 + f the ghost of wall face f
+    // (:112-124); a lane evaluates the contribution of one slot, the sums run over the slots in order.
+    // Returns false if the normal degenerates (:128-129).
+    template< int L >
+    VOFX_HD inline bool youngs_normal_coop ( const Group &G, LocateScratch &S, const Grid &g, const double *u, const int *ijk,
+                                             double colorEn, double *normal )
+    {
+      constexpr int kOwn = ( 9 + L - 1 ) / L;
+      double center[ 3 ], lower[ 3 ];
+      for( int d = 0; d < 3; ++d )
+      {
+        lower[ d ] = cell_lower( g, d, ijk[ d ] );
+        center[ d ] = lower[ d ] + 0.5 * g.h[ d ];
+      }
+#pragma unroll 1
+      for( int round = 0; round * L < 32; ++round )
+      {
+        VOFX_LANES( G, L, lane )
+        {
+          const int s = round * L + lane;
+          bool valid = false;
+          double d[ 3 ] = { 0.0, 0.0, 0.0 }, colorDiff = 0.0;
+          if( s < 26 )
+          {
+            const int m = ( s < 13 ) ? s : s + 1;
+            const int nb[ 3 ] = { ijk[ 0 ] + ( m % 3 ) - 1, ijk[ 1 ] + ( ( m / 3 ) % 3 ) - 1, ijk[ 2 ] + ( m / 9 ) - 1 };
+            if( cell_exists( g, nb ) )
+            {
+              valid = true;
+              const double colorNb = clamp01( u[ cell_index( g, nb ) ] );
+              for( int k = 0; k < 3; ++k )
+                d[ k ] = ( cell_lower( g, k, nb[ k ] ) + 0.5 * g.h[ k ] ) - center[ k ];
+              colorDiff = colorNb - colorEn;
+            }
+          }
+          else if( s < 32 )
+          {
+            const int face = s - 26;
+            int nb[ 3 ] = { ijk[ 0 ], ijk[ 1 ], ijk[ 2 ] };
+            nb[ face >> 1 ] += ( face & 1 ) ? 1 : -1;
+            if( !in_domain( g, nb ) )
+            {
+              valid = true;
+              for( int k = 0; k < 3; ++k )
+              {
+                double fc = lower[ k ];
+                if( k == ( face >> 1 ) )
+                {
+                  if( face & 1 )
+                    fc += g.h[ k ];
+                }
+                else
+                  fc += 0.5 * g.h[ k ];
+                d[ k ] = fc - center[ k ];
+                d[ k ] *= 2.0;
+              }
+              colorDiff = 0.5 - colorEn;
+            }
+          }
+          S.lsValid[ lane ] = valid ? 1 : 0;
+          if( valid )
+          {
+            // ls_accumulate: weight = 1/|d|^2, d *= weight, AtA += d d^T, Atb += weight * colorDiff * d
+            double n2 = 0.0;
+            for( int k = 0; k < 3; ++k )
+              n2 += d[ k ] * d[ k ];
+            const double weight = 1.0 / n2;
+            for( int k = 0; k < 3; ++k )
+              d[ k ] *= weight;
+            int c = 0;
+            for( int i = 0; i < 3; ++i )
+              for( int j = i; j < 3; ++j )
+              {
+                double mm = 0.0;          // outerProduct: axpy onto a zero matrix, geometry/utility.hh:161-169
+                mm += d[ i ] * d[ j ];
+                S.ls[ lane ][ c++ ] = mm;
+              }
+            const double w = weight * colorDiff;
+            for( int k = 0; k < 3; ++k )
+              S.ls[ lane ][ 6 + k ] = w * d[ k ];
+          }
+        }
+        VOFX_LANES( G, L, lane )
+        {
+          for( int q = 0; q < kOwn; ++q )
+          {
+            const int c = lane + q * L;
+            if( c < 9 )
+            {
+              double a = ( round == 0 ) ? 0.0 : S.sums[ c ];
+              for( int j = 0; j < L; ++j )
+                if( S.lsValid[ j ] )
+                  a += S.ls[ j ][ c ];
+              S.sums[ c ] = a;
+            }
+          }
+        }
+      }
+
+      const double AtA[ 3 ][ 3 ] = { { S.sums[ 0 ], S.sums[ 1 ], S.sums[ 2 ] }, { S.sums[ 1 ], S.sums[ 3 ], S.sums[ 4 ] }, { S.sums[ 2 ], S.sums[ 4 ], S.sums[ 5 ] } };
+      const double Atb[ 3 ] = { S.sums[ 6 ], S.sums[ 7 ], S.sums[ 8 ] };
+      normal[ 0 ] = normal[ 1 ] = normal[ 2 ] = 0.0;
+      solve3( AtA, Atb, normal );
+      double n2 = 0.0;
+      for( int k = 0; k < 3; ++k )
+        n2 += normal[ k ] * normal[ k ];
+      if( n2 < kEps )
+        return false;
+      const double nrm = sqrt( n2 );
+      for( int k = 0; k < 3; ++k )
+        normal[ k ] = vdiv( normal[ k ], nrm );
+      return true;
+    }
+
+  } // namespace coop
+} // namespace vofx

@@ -607,6 +607,8 @@ namespace vofx
     double px[ kMaxSweep ], py[ kMaxSweep ];
     signed char nodeId[ kMaxSweep ];   // parent node or -1
     signed char corrFace[ kMaxSweep ];
+    signed char srcNode[ kMaxSweep ];  // where the node came from: the parent node id (srcEdge == -1), or the index of
+    signed char srcEdge[ kMaxSweep ];  // the previous polygon's node that slid here along the directed edge srcEdge
     Dirs dirs[ kMaxSweep ];
   };
 
@@ -623,7 +625,9 @@ namespace vofx
   }
 
   // PolygonWithDirections::initialize, 3d/polygonwithdirections.hh:76-174.  ids = node ids sorted by height, ds = sorted heights
-  VOFX_HD inline void sweep_init ( Sweep &s, const Hex &P, const int *ids, const double *ds )
+  // POS = false: topology only (the cooperative path evaluates the positions itself); P may then be null
+  template< bool POS >
+  VOFX_HD inline void sweep_init ( Sweep &s, const Hex *Pp, const int *ids, const double *ds )
   {
     s.nn = 0;
     s.nEdges = 0;
@@ -636,8 +640,11 @@ namespace vofx
 
     if( N == 1 )
     {
-      s.px[ 0 ] = P.x[ ids[ 0 ] ][ 0 ];
-      s.py[ 0 ] = P.x[ ids[ 0 ] ][ 1 ];
+      if( POS )
+      {
+        s.px[ 0 ] = Pp->x[ ids[ 0 ] ][ 0 ];
+        s.py[ 0 ] = Pp->x[ ids[ 0 ] ][ 1 ];
+      }
       s.nodeId[ 0 ] = (signed char) ids[ 0 ];
       dirs_of_node( ids[ 0 ], s.dirs[ 0 ] );
       dirs_sort( s.dirs[ 0 ] );
@@ -647,8 +654,11 @@ namespace vofx
     {
       for( int k = 0; k < 2; ++k )
       {
-        s.px[ k ] = P.x[ ids[ k ] ][ 0 ];
-        s.py[ k ] = P.x[ ids[ k ] ][ 1 ];
+        if( POS )
+        {
+          s.px[ k ] = Pp->x[ ids[ k ] ][ 0 ];
+          s.py[ k ] = Pp->x[ ids[ k ] ][ 1 ];
+        }
         s.nodeId[ k ] = (signed char) ids[ k ];
       }
       Dirs d1, d2;
@@ -695,8 +705,11 @@ namespace vofx
       {
         const int id = cube::faceNode( found, k );
         s.nodeId[ k ] = (signed char) id;
-        s.px[ k ] = P.x[ id ][ 0 ];
-        s.py[ k ] = P.x[ id ][ 1 ];
+        if( POS )
+        {
+          s.px[ k ] = Pp->x[ id ][ 0 ];
+          s.py[ k ] = Pp->x[ id ][ 1 ];
+        }
       }
       s.nn = 4;
       for( int k = 0; k < N; ++k )
@@ -715,6 +728,11 @@ namespace vofx
       }
     }
 
+    for( int i = 0; i < s.nn; ++i )
+    {
+      s.srcNode[ i ] = s.nodeId[ i ];
+      s.srcEdge[ i ] = -1;
+    }
     if( s.nn != 1 )
     {
       for( int i = 0; i < s.nn; ++i )
@@ -733,10 +751,12 @@ namespace vofx
   }
 
   // PolygonWithDirections::evolveToNextPolygon, 3d/polygonwithdirections.hh:177-290
-  VOFX_HD inline void sweep_evolve ( Sweep &s, const Hex &P, double dk, double dk1, double h )
+  // z: the eight node heights (P.x[ . ][ 2 ]); P only for POS = true
+  template< bool POS >
+  VOFX_HD inline void sweep_evolve ( Sweep &s, const Hex *Pp, const double *z, double dk, double dk1, double h )
   {
     double nx[ kMaxSweep ], ny[ kMaxSweep ];
-    signed char nid[ kMaxSweep ];
+    signed char nid[ kMaxSweep ], nsrcN[ kMaxSweep ], nsrcE[ kMaxSweep ];
     Dirs nd[ kMaxSweep ];
     int nNew = 0;
     const int oldN = s.nn;
@@ -749,7 +769,7 @@ namespace vofx
       {
         const int dirEdge = s.dirs[ n ].e[ i ];
         const int target = cube::edgeN1( dirEdge );
-        const double z1 = P.x[ target ][ 2 ];
+        const double z1 = z[ target ];
 
         if( fabs( z1 - dk1 ) < 1e-10 )
         {
@@ -763,16 +783,21 @@ namespace vofx
             s.degenerate = true;
             return;
           }
-          nx[ nNew ] = P.x[ target ][ 0 ];
-          ny[ nNew ] = P.x[ target ][ 1 ];
+          if( POS )
+          {
+            nx[ nNew ] = Pp->x[ target ][ 0 ];
+            ny[ nNew ] = Pp->x[ target ][ 1 ];
+          }
           nid[ nNew ] = (signed char) target;
+          nsrcN[ nNew ] = (signed char) target;
+          nsrcE[ nNew ] = -1;
           Dirs dd;
           dd.n = 0;
           dd.e[ 3 ] = 0;
           for( int a = 0; a < 3; ++a )
           {
             const int e = cube::outEdge( target, a );
-            if( P.x[ cube::edgeN1( e ) ][ 2 ] > dk )
+            if( z[ cube::edgeN1( e ) ] > dk )
               dd.e[ dd.n++ ] = (signed char) e;
           }
           dirs_sort( dd );
@@ -787,13 +812,18 @@ namespace vofx
             s.degenerate = true;
             return;
           }
-          double dv[ 3 ];
-          direction_vector( P, dirEdge, dv );
-          const double f = vdiv( h, dv[ 2 ] );
-          const double ax = dv[ 0 ] * f, ay = dv[ 1 ] * f;
-          nx[ nNew ] = s.px[ n ] + ax;
-          ny[ nNew ] = s.py[ n ] + ay;
+          if( POS )
+          {
+            double dv[ 3 ];
+            direction_vector( *Pp, dirEdge, dv );
+            const double f = vdiv( h, dv[ 2 ] );
+            const double ax = dv[ 0 ] * f, ay = dv[ 1 ] * f;
+            nx[ nNew ] = s.px[ n ] + ax;
+            ny[ nNew ] = s.py[ n ] + ay;
+          }
           nid[ nNew ] = -1;
+          nsrcN[ nNew ] = (signed char) n;
+          nsrcE[ nNew ] = (signed char) dirEdge;
           nd[ nNew ].n = 1;
           nd[ nNew ].e[ 0 ] = (signed char) dirEdge;
           nNew++;
@@ -842,9 +872,14 @@ namespace vofx
     s.nn = nNew;
     for( int a = 0; a < nNew; ++a )
     {
-      s.px[ a ] = nx[ a ];
-      s.py[ a ] = ny[ a ];
+      if( POS )
+      {
+        s.px[ a ] = nx[ a ];
+        s.py[ a ] = ny[ a ];
+      }
       s.nodeId[ a ] = nid[ a ];
+      s.srcNode[ a ] = nsrcN[ a ];
+      s.srcEdge[ a ] = nsrcE[ a ];
       s.dirs[ a ] = nd[ a ];
     }
   }
@@ -897,7 +932,7 @@ namespace vofx
         dU[ nU++ ] = ds[ i ];
 
     Sweep s;
-    sweep_init( s, P, ids, ds );
+    sweep_init< true >( s, &P, ids, ds );
     if( s.degenerate )
       return NAN;
 
@@ -970,7 +1005,10 @@ namespace vofx
       }
       else
       {
-        sweep_evolve( s, P, dU[ k ], dU[ k + 1 ], h );
+        double zs[ 8 ];
+        for( int i = 0; i < 8; ++i )
+          zs[ i ] = P.x[ i ][ 2 ];
+        sweep_evolve< true >( s, &P, zs, dU[ k ], dU[ k + 1 ], h );
         if( s.degenerate )
           return NAN;
       }

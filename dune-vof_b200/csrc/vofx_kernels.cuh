@@ -514,6 +514,76 @@ namespace vofx
     }
   }
 
+  // R1 in 3D for the B200: L lanes per mixed cell (vofx_coop3d.cuh).  The stencil contributions, the faces of the cell
+  // volume, the direction vectors and the per-bracket terms of the plane-constant solve are spread over the lanes;
+  // the sweep topology comes from a table of the 96 generic height orders.  Cells with tied node heights (axis-aligned
+  // normals) are queued for k_locate_serial3.
+#ifndef VOFX_YOUNGS_THREADS_PER_SM
+#define VOFX_YOUNGS_THREADS_PER_SM 640   // resident threads per SM the register allocation aims for
+#endif
+  template< int L >
+  __global__ void __launch_bounds__( 16 * L, VOFX_YOUNGS_THREADS_PER_SM / ( 16 * L ) ) k_youngs_coop3 ( Grid g, const double *__restrict__ u, const int *__restrict__ mixedList,
+                                                             StepState *state, int capacity, double *__restrict__ hs,
+                                                             const coop::SweepTable *__restrict__ table, int *__restrict__ serialCells )
+  {
+    constexpr int GROUPS = 16;          // 16 groups per block: 128 threads for L = 8, 64 for L = 4
+    __shared__ coop::LocateScratch scratch[ GROUPS ];
+    const int count = mixed_count( state, capacity );
+    const int lane = threadIdx.x % L;
+    const int group = threadIdx.x / L;
+    coop::Group G;
+    G.lane = lane;
+    G.mask = ( ( L == 32 ) ? 0xffffffffu : ( ( 1u << L ) - 1u ) ) << ( ( threadIdx.x & 31 ) - lane );
+    coop::LocateScratch &S = scratch[ group ];
+    for( int idx = blockIdx.x * GROUPS + group; idx < count; idx += gridDim.x * GROUPS )
+    {
+      const int c = mixedList[ idx ];
+      int ijk[ 3 ];
+      cell_ijk( g, c, ijk );
+      const double colorEn = u[ c ];
+      double *out = hs + (long long) c * 4;
+      double normal[ 3 ];
+      if( !coop::youngs_normal_coop< L >( G, S, g, u, ijk, colorEn, normal ) )
+      {
+        if( lane == 0 )
+          out[ 0 ] = out[ 1 ] = out[ 2 ] = out[ 3 ] = 0.0;
+        G.sync();
+        continue;
+      }
+      const double lo[ 3 ] = { cell_lower( g, 0, ijk[ 0 ] ), cell_lower( g, 1, ijk[ 1 ] ), cell_lower( g, 2, ijk[ 2 ] ) };
+      double dist = 0.0;
+      const bool located = coop::locate_coop< L >( G, S, *table, lo, g.h, normal, colorEn, dist );
+      if( lane == 0 )
+      {
+        out[ 0 ] = normal[ 0 ];
+        out[ 1 ] = normal[ 1 ];
+        out[ 2 ] = normal[ 2 ];
+        if( located )
+          out[ 3 ] = dist;
+        else
+          serialCells[ atomicAdd( &state->serialLocate, 1 ) ] = c;
+      }
+      G.sync();
+    }
+  }
+
+  // plane-constant solve by the serial walk for the cells queued by k_youngs_coop3 (normal already in hs)
+  template< int DIM >
+  __global__ void __launch_bounds__( 64 ) k_locate_serial3 ( Grid g, const double *__restrict__ u, const StepState *state, double *__restrict__ hs,
+                                                              const int *__restrict__ serialCells )
+  {
+    const int n = state->serialLocate;
+    for( int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x )
+    {
+      const int c = serialCells[ t ];
+      int ijk[ 3 ];
+      cell_ijk( g, c, ijk );
+      double *rec = hs + (long long) c * 4;
+      const double normal[ 3 ] = { rec[ 0 ], rec[ 1 ], rec[ 2 ] };
+      rec[ 3 ] = locate_cell< 3 >( g, ijk, normal, u[ c ] );
+    }
+  }
+
   // ------------------------------------------------------------------------------------------------------------
   // S2 + R2: Cartesian height functions, stencil/heightfunctionstencil.hh:22-107, reconstruction/heightfunction.hh:101-259
   // ------------------------------------------------------------------------------------------------------------

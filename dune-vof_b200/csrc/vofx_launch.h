@@ -41,6 +41,11 @@ namespace vofx
 
     // k_recon3d.cu, k_swartz3d.cu, k_flux3d.cu
     void youngs3 ( int blocks, cudaStream_t s, Grid g, const double *u, const int *mixedList, const StepState *state, int capacity, double *hs );
+    void youngs_coop3 ( int lanes, int blocks, cudaStream_t s, Grid g, const double *u, const int *mixedList, StepState *state, int capacity, double *hs,
+                        const void *sweepTable, int *serialCells );
+    void locate_serial3 ( cudaStream_t s, Grid g, const double *u, const StepState *state, double *hs, const int *serialCells );
+    int make_sweep_table ( void *host, size_t bytes );   // returns the number of cases (96) or -1
+    size_t sweep_table_bytes ();
     void hf3 ( int blocks, cudaStream_t s, Grid g, const double *u, const int *mixedList, const StepState *state, int capacity, double *hs );
     void swartz3 ( int blocks, cudaStream_t s, Grid g, const double *u, const unsigned char *flags, const int *mixedList, const StepState *state,
                    int capacity, double *hs, int maxIterations );

@@ -158,3 +158,81 @@ extern "C"
   }
 
 } // extern "C"
+
+extern "C" int hg_sweep_table_cases ( void )
+{
+  static coop::SweepTable T;
+  return coop::make_sweep_table( T );
+}
+
+// Young's normal + plane constant of one cell by the cooperative path (lanes emulated).  status: 0 located by the table
+// path, 1 degenerate normal (zero half-space), 2 left to the serial walk (then located serially here)
+template< int L >
+static int youngs_coop_cell ( const int *n, const double *u, const int *ijk, double *out )
+{
+  static coop::SweepTable T;
+  static bool have = false;
+  if( !have )
+  {
+    if( coop::make_sweep_table( T ) != coop::kSweepCases )
+      return -1;
+    have = true;
+  }
+  Grid g;
+  g.dim = 3;
+  g.cells = 1;
+  for( int d = 0; d < 3; ++d )
+  {
+    g.ns[ d ] = g.ng[ d ] = n[ d ];
+    g.g0[ d ] = 0;
+    g.origin[ d ] = 0.0;
+    g.h[ d ] = 1.0 / n[ d ];
+    g.cells *= n[ d ];
+  }
+  g.own0 = g.list0 = 0;
+  g.own1 = g.list1 = n[ 2 ];
+  coop::LocateScratch S;
+  coop::Group G = { 0, 0u };
+  const double colorEn = u[ cell_index( g, ijk ) ];
+  double normal[ 3 ];
+  if( !coop::youngs_normal_coop< L >( G, S, g, u, ijk, colorEn, normal ) )
+  {
+    out[ 0 ] = out[ 1 ] = out[ 2 ] = out[ 3 ] = 0.0;
+    return 1;
+  }
+  const double lo[ 3 ] = { cell_lower( g, 0, ijk[ 0 ] ), cell_lower( g, 1, ijk[ 1 ] ), cell_lower( g, 2, ijk[ 2 ] ) };
+  for( int k = 0; k < 3; ++k )
+    out[ k ] = normal[ k ];
+  double dist;
+  if( coop::locate_coop< L >( G, S, T, lo, g.h, normal, colorEn, dist ) )
+  {
+    out[ 3 ] = dist;
+    return 0;
+  }
+  Hex c;
+  make_cell( lo, g.h, c );
+  out[ 3 ] = locate( c, normal, colorEn );
+  return 2;
+}
+
+extern "C" int hg_youngs_coop ( int lanes, const int *n, const double *u, const int *ijk, double *out )
+{
+  return lanes == 4 ? youngs_coop_cell< 4 >( n, u, ijk, out ) : youngs_coop_cell< 8 >( n, u, ijk, out );
+}
+
+// plane constant only, for fuzzing against the oracle: status 0 table path, 2 serial walk needed
+extern "C" int hg_locate_coop ( int lanes, const double *lo, const double *h, const double *normal, double fraction, double *dist )
+{
+  static coop::SweepTable T;
+  static bool have = false;
+  if( !have )
+  {
+    coop::make_sweep_table( T );
+    have = true;
+  }
+  coop::LocateScratch S;
+  coop::Group G = { 0, 0u };
+  const bool ok = lanes == 4 ? coop::locate_coop< 4 >( G, S, T, lo, h, normal, fraction, *dist )
+                             : coop::locate_coop< 8 >( G, S, T, lo, h, normal, fraction, *dist );
+  return ok ? 0 : 2;
+}

@@ -129,3 +129,72 @@ def test_geometry_bit_exact(hg, dim):
 def test_det_cospi_matches_oracle(hg):
     for s in np.linspace(-2.0, 5.0, 2001):
         assert hg.hg_det_cospi(float(s)) == O.det_cospi(float(s))
+
+
+def hg_locate_coop(L, lanes, lo, h, n, f):
+    lo, h, n = _v(lo), _v(h), _v(n)
+    d = C.c_double(0)
+    st = L.hg_locate_coop(int(lanes), _d(lo), _d(h), _d(n), C.c_double(f), C.byref(d))
+    return st, d.value
+
+
+@pytest.mark.parametrize("lanes", [8, 4])
+def test_cooperative_locate_bit_exact(hg, lanes):
+    """locate_coop (vofx_coop3d.cuh: sweep topology from the table of 96 height orders), lanes emulated, against the
+    oracle's locateHalfSpace on random and near-degenerate normals; the table path must take the generic cases"""
+    assert hg.hg_sweep_table_cases() == 96
+    rng = np.random.default_rng(500 + lanes)
+    paths = {0: 0, 2: 0}
+    for it in range(6000):
+        res = int(rng.choice([64, 128, 512, 1024, 100, 37]))
+        h = np.full(3, 1.0 / res)
+        if it % 7 == 0:
+            h = h * rng.uniform(0.5, 2.0, 3)            # anisotropic cells
+        lo = rng.integers(0, res, 3) * h
+        n = rng.normal(size=3)
+        mode = it % 12
+        if mode == 1:
+            n[rng.integers(0, 3)] = 0
+        if mode == 2:
+            n[rng.integers(0, 3)] *= 1e-9
+        if mode == 3:
+            k = rng.integers(0, 3); n[:] = 0; n[k] = rng.choice([-1.0, 1.0])
+        if mode == 4:
+            n = rng.choice([-1.0, 1.0], size=3)
+        if mode == 6:
+            k = rng.integers(0, 3); n[:] = 0; n[k] = rng.choice([-1, 1])
+            n[(k + 1) % 3] = rng.choice([-1, 1]) * 10.0 ** rng.uniform(-17, -5)
+        n /= np.linalg.norm(n)
+        f = rng.random()
+        if mode == 5:
+            f = float(rng.choice([0.0, 1.0, 1e-7, 1 - 1e-7, 1e-6, 0.5, 1.2, -0.1]))
+        st, d = hg_locate_coop(hg, lanes, lo, h, n, f)
+        paths[st] += 1
+        if st == 0:
+            ref = O.locate(lo, h, n, f)
+            assert same_bits(ref[-1], d), (lanes, mode, lo, h, n, f, ref[-1], d)
+    assert paths[0] > 3500, paths
+    print("cooperative locate paths (0 table, 2 serial):", paths)
+
+
+@pytest.mark.parametrize("lanes", [8, 4])
+def test_cooperative_youngs_bit_exact(hg, lanes):
+    """Young's normal + plane constant of every mixed cell of small 3D problems, cooperative path vs the oracle"""
+    for n, problem in (((16, 16, 16), O.PROB_LEVEQUE), ((20, 12, 16), O.PROB_SFLOW), ((12, 12, 12), O.PROB_LINEAR_WALL)):
+        og = O.OracleGrid(n)
+        u = og.init(problem)
+        u, *_ = og.run(O.RECON_YOUNGS, problem, 1e-6, 0.5, 3, u)          # a few passes: over/undershoots appear
+        flags = og.flag(u, 1e-6)
+        hs = og.reconstruct(O.RECON_YOUNGS, u, flags).reshape(-1, 4)
+        nn = np.asarray(n, dtype=np.int32)
+        uu = _v(u)
+        status = {0: 0, 1: 0, 2: 0}
+        for c in np.flatnonzero((flags == 1) | (flags == 2)):
+            ijk = np.asarray([c % n[0], (c // n[0]) % n[1], c // (n[0] * n[1])], dtype=np.int32)
+            out = np.empty(4)
+            st = hg.hg_youngs_coop(int(lanes), C.c_void_p(nn.ctypes.data), _d(uu), C.c_void_p(ijk.ctypes.data), _d(out))
+            assert st in (0, 1, 2)
+            status[st] += 1
+            assert same_bits(out, hs[c]), (n, problem, c, st, out, hs[c])
+        print(n, problem, "cooperative Young's status counts:", status)
+        og.close()
