@@ -9,13 +9,16 @@ namespace vofx
     void youngs3 ( int blocks, cudaStream_t s, Grid g, const double *u, const int *mixedList, const StepState *state, int capacity, double *hs )
     { k_youngs< 3 ><<< blocks, 128, 0, s >>>( g, u, mixedList, state, capacity, hs ); }
     void youngs_coop3 ( int lanes, int blocks, cudaStream_t s, Grid g, const double *u, const int *mixedList, StepState *state, int capacity, double *hs,
-                        const void *sweepTable, int *serialCells )
+                        const void *sweepTable, int *serialCells, void *rootTasks )
     {
       if( lanes == 4 )
-        k_youngs_coop3< 4 ><<< blocks * 2, 64, 0, s >>>( g, u, mixedList, state, capacity, hs, (const coop::SweepTable *) sweepTable, serialCells );
+        k_youngs_coop3< 4 ><<< blocks * 2, 64, 0, s >>>( g, u, mixedList, state, capacity, hs, (const coop::SweepTable *) sweepTable, serialCells, (coop::RootTask *) rootTasks );
       else
-        k_youngs_coop3< 8 ><<< blocks, 128, 0, s >>>( g, u, mixedList, state, capacity, hs, (const coop::SweepTable *) sweepTable, serialCells );
+        k_youngs_coop3< 8 ><<< blocks, 128, 0, s >>>( g, u, mixedList, state, capacity, hs, (const coop::SweepTable *) sweepTable, serialCells, (coop::RootTask *) rootTasks );
     }
+    void locate_root3 ( int blocks, cudaStream_t s, const StepState *state, const void *rootTasks, double *hs )
+    { k_locate_root3< 3 ><<< blocks, 128, 0, s >>>( state, (const coop::RootTask *) rootTasks, hs ); }
+    size_t root_task_bytes () { return sizeof( coop::RootTask ); }
     void locate_serial3 ( cudaStream_t s, Grid g, const double *u, const StepState *state, double *hs, const int *serialCells )
     { k_locate_serial3< 3 ><<< 148, 64, 0, s >>>( g, u, state, hs, serialCells ); }
     int make_sweep_table ( void *host, size_t bytes )

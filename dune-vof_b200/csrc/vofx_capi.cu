@@ -54,7 +54,8 @@ struct vofx_ctx
   int taskCapacity = 0;
   void *sweepTable = nullptr;       // coop::SweepTable
   int *serialCells = nullptr;       // mixed cells whose plane constant is left to the serial walk
-  int lanesPerCell = 8;
+  void *rootTasks = nullptr;        // coop::RootTask per mixed cell: brackets found by k_youngs_coop3, roots by k_locate_root3
+  int lanesPerCell = 4;            // measured on B200 at 512^3: 0.47 ms (4 lanes per cell) vs 0.64 ms (8)
   void *clipTable = nullptr;        // coop::ClipCase[ 256 ]
   StepState *state = nullptr;
   double *curv1 = nullptr;
@@ -215,8 +216,13 @@ namespace
       launch::youngs2( blocks, ctx->stream, g, u, ctx->mixedList, ctx->state, ctx->capacity, hs );
     else
     {
-      launch::youngs_coop3( ctx->lanesPerCell, blocks, ctx->stream, g, u, ctx->mixedList, ctx->state, ctx->capacity, hs, ctx->sweepTable, ctx->serialCells );
+      launch::youngs_coop3( ctx->lanesPerCell, blocks, ctx->stream, g, u, ctx->mixedList, ctx->state, ctx->capacity, hs, ctx->sweepTable, ctx->serialCells, ctx->rootTasks );
       int rc3 = checkLaunch( ctx, "k_youngs" );
+      if( rc3 )
+        return rc3;
+      profBegin( ctx );
+      launch::locate_root3( ctx->numSMs * 8, ctx->stream, ctx->state, ctx->rootTasks, hs );
+      rc3 = checkLaunch( ctx, "k_locate_root" );
       if( rc3 )
         return rc3;
       // cells whose walk hits a state the reference leaves undefined (never seen on the BASELINE configs): serial kernel
@@ -259,14 +265,21 @@ namespace
       launch::flux2( blocks, ctx->stream, g, ctx->velDev, hs, flags, ctx->mixedList, ctx->state, ctx->capacity, ctx->records, timeOverride, dtOverride );
       return checkLaunch( ctx, "k_flux" );
     }
-    launch::flux_prepare3( blocks, ctx->stream, g, ctx->velDev, flags, ctx->mixedList, ctx->state, ctx->capacity, ctx->records, ctx->tasks, ctx->taskCapacity, timeOverride, dtOverride );
-    int rc = checkLaunch( ctx, "k_flux_prepare" );
-    if( rc )
-      return rc;
-    profBegin( ctx );
-    launch::flux_clip3( ctx->numSMs * 8, ctx->stream, g, ctx->velDev, hs, flags, ctx->mixedList, ctx->state, ctx->records, ctx->tasks, ctx->clipTable, ctx->taskCapacity, timeOverride, dtOverride );
-    ctx->launches++;   // k_flux_clip_serial3 rides along (a handful of tasks per step)
-    return checkLaunch( ctx, "k_flux_clip" );
+    if( std::getenv( "VOFX_FLUX_TASKS" ) )
+    {
+      launch::flux_prepare3( blocks, ctx->stream, g, ctx->velDev, flags, ctx->mixedList, ctx->state, ctx->capacity, ctx->records, ctx->tasks, ctx->taskCapacity, timeOverride, dtOverride );
+      int rc = checkLaunch( ctx, "k_flux_prepare" );
+      if( rc )
+        return rc;
+      profBegin( ctx );
+      launch::flux_clip3( ctx->numSMs * 8, ctx->stream, g, ctx->velDev, hs, flags, ctx->mixedList, ctx->state, ctx->records, ctx->tasks, ctx->clipTable, ctx->taskCapacity, timeOverride, dtOverride );
+      ctx->launches++;   // k_flux_clip_serial3 rides along (a handful of tasks per step)
+      return checkLaunch( ctx, "k_flux_clip" );
+    }
+    launch::flux_cell3( ctx->numSMs * 8, ctx->stream, g, ctx->velDev, hs, flags, ctx->mixedList, ctx->state, ctx->capacity, ctx->records, ctx->tasks, ctx->taskCapacity,
+                        ctx->clipTable, timeOverride, dtOverride );
+    ctx->launches++;     // k_flux_clip_serial3 rides along (a handful of clips per step)
+    return checkLaunch( ctx, "k_flux" );
   }
 
   int launchUpdate ( vofx_ctx *ctx, const unsigned char *flags, double *target, bool accumulate )
@@ -457,6 +470,7 @@ extern "C"
       alloc( (void **) &ctx->clipTable, 256 * 64 );
       alloc( (void **) &ctx->sweepTable, launch::sweep_table_bytes() );
       alloc( (void **) &ctx->serialCells, sizeof( int ) * (size_t) ctx->capacity );
+      alloc( (void **) &ctx->rootTasks, launch::root_task_bytes() * (size_t) ctx->capacity );
     }
     alloc( (void **) &ctx->curv1, sizeof( double ) * (size_t) ctx->capacity );
     alloc( (void **) &ctx->ok1, (size_t) ctx->capacity );
@@ -481,7 +495,7 @@ extern "C"
       }
       cudaMemcpy( ctx->sweepTable, table.data(), table.size(), cudaMemcpyHostToDevice );
       if( const char *env = std::getenv( "VOFX_LANES_PER_CELL" ) )
-        ctx->lanesPerCell = ( std::atoi( env ) == 4 ) ? 4 : 8;
+        ctx->lanesPerCell = ( std::atoi( env ) == 8 ) ? 8 : 4;
     }
     if( ctx->clipTable )
     {
@@ -506,6 +520,7 @@ extern "C"
     cudaFree( ctx->clipTable );
     cudaFree( ctx->sweepTable );
     cudaFree( ctx->serialCells );
+    cudaFree( ctx->rootTasks );
     cudaFree( ctx->state );
     cudaFree( ctx->curv1 );
     cudaFree( ctx->ok1 );

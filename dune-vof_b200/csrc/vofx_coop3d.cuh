@@ -23,16 +23,18 @@ namespace vofx
     // ---- G5: clip of a hexahedron, topology looked up by the inner mask ----------------------------------------------
 
     // One entry per inner mask when no node lies on the plane: which cut nodes exist and, face by face in the
-    // reference's summation order, the cyclic node sequence.  ref < 8: original node; ref >= 8: cut node ref - 8.
+    // reference's summation order, the cyclic node sequences (concatenated).  ref < 8: original node; ref >= 8: cut node.
+    constexpr int kMaxClipEdges = 36;
     struct ClipCase
     {
       unsigned char nCut;            // 0xFF: not representable here (take the serial path)
       unsigned char nFaces;
-      unsigned char cut[ 6 ];        // a | b << 3: Edge( a, b ).intersection( plane ), operand order as in the walk
-      unsigned char faceLen[ 7 ];
+      unsigned char nEdges;
       unsigned char pad0;
-      unsigned char ref[ 7 ][ 6 ];   // first node of the k-th edge of the face; its second node is ref[ (k+1) % len ]
-      unsigned char pad1[ 6 ];
+      unsigned char cut[ 6 ];        // a | b << 3: Edge( a, b ).intersection( plane ), operand order as in the walk
+      unsigned char faceStart[ 8 ];  // face f owns the edges faceStart[f] .. faceStart[f+1]-1
+      unsigned char refs[ kMaxClipEdges ];   // first node of every edge; the second node is the next entry (cyclic in the face)
+      unsigned char pad1[ 10 ];
     };
     static_assert( sizeof( ClipCase ) == 64, "ClipCase must be 64 bytes" );
 
@@ -46,16 +48,14 @@ namespace vofx
           reinterpret_cast< unsigned char * >( &c )[ i ] = 0;
         ClipTopo t;
         if( !clip_walk( mask, 0u, t ) )
-        {
-          c.nCut = 0;
-          c.nFaces = 0;      // empty result (only mask 0)
-          continue;
-        }
+          continue;          // empty result (only mask 0)
         bool regular = t.nNew <= 6 && t.nFaces <= 7;
+        int nEdges = 0;
         for( int f = 0; regular && f < t.nFaces; ++f )
         {
           const int len = t.flen[ f ];
-          regular = len <= 6;
+          nEdges += len;
+          regular = len <= 6 && nEdges <= kMaxClipEdges;
           for( int k = 0; regular && k < len; ++k )
             regular = t.fe1[ f ][ k ] == t.fe0[ f ][ ( k + 1 ) % len ];
         }
@@ -68,24 +68,33 @@ namespace vofx
         c.nFaces = (unsigned char) t.nFaces;
         for( int j = 0; j < t.nNew; ++j )
           c.cut[ j ] = (unsigned char) ( t.cutA[ j ] | ( t.cutB[ j ] << 3 ) );
+        int e = 0;
         for( int f = 0; f < t.nFaces; ++f )
         {
-          c.faceLen[ f ] = (unsigned char) t.flen[ f ];
+          c.faceStart[ f ] = (unsigned char) e;
           for( int k = 0; k < t.flen[ f ]; ++k )
           {
             const int id = t.fe0[ f ][ k ];
-            c.ref[ f ][ k ] = (unsigned char) ( id < t.n ? t.innerNode[ id ] : 8 + ( id - t.n ) );
+            c.refs[ e++ ] = (unsigned char) ( id < t.n ? t.innerNode[ id ] : 8 + ( id - t.n ) );
           }
         }
+        for( int f = t.nFaces; f < 8; ++f )
+          c.faceStart[ f ] = (unsigned char) e;
+        c.nEdges = (unsigned char) e;
       }
     }
 
     struct ClipScratch
     {
       double x[ 3 ][ 16 ];             // coordinate d of ref r: 0..7 nodes of the hexahedron, 8..13 cut nodes
+      double fn[ 3 ][ 8 ];             // outer normals of the faces of the clipped polyhedron
+      double cf[ 8 ];                  // face centre . face normal
+      double eterm[ kMaxClipEdges ];   // edge terms of Face::volume
       double term[ 8 ];                // face terms of Polyhedron::volume
       unsigned char inner[ 8 ], bnd[ 8 ];
+      double bankPad[ 1 ];
     };
+    static_assert( sizeof( ClipScratch ) % 8 == 0 && ( sizeof( ClipScratch ) / 8 ) % 2 == 1, "ClipScratch stride must be an odd number of doubles" );
 
     // phase A: lane i classifies node i (3d/intersect.hh:99-112) and publishes it
     VOFX_HD inline void clip_phase_classify ( int lane, ClipScratch &S, const double *xn, const Hs3 &hs )
@@ -131,45 +140,90 @@ namespace vofx
       return 0;
     }
 
-    // phase C: lane f evaluates face f of the clipped polyhedron (3d/polyhedron.hh:187-222 as in clipped_face_term)
+    // phase C1: lane f sets up face f of the clipped polyhedron: centre (mean of the edges' first nodes) and outer
+    // normal from the first three nodes, 3d/polyhedron.hh:187-214
     VOFX_HD inline void clip_phase_faces ( int lane, ClipScratch &S, const ClipCase &cs )
     {
       if( lane >= cs.nFaces )
         return;
-      const int len = cs.faceLen[ lane ];
-      double x[ 6 ][ 3 ];
-#pragma unroll
-      for( int k = 0; k < 6; ++k )
+      const int e0 = cs.faceStart[ lane ], len = cs.faceStart[ lane + 1 ] - e0;
+      double center[ 3 ] = { 0.0, 0.0, 0.0 }, x3[ 3 ][ 3 ], fn[ 3 ];
+#pragma unroll 1
+      for( int k = 0; k < len; ++k )
       {
-        const int r = cs.ref[ lane ][ k < len ? k : 0 ];
-#pragma unroll
+        const int r = cs.refs[ e0 + k ];
         for( int d = 0; d < 3; ++d )
-          x[ k ][ d ] = S.x[ d ][ r ];
+          center[ d ] += S.x[ d ][ r ];
       }
-      double center[ 3 ] = { 0.0, 0.0, 0.0 }, fn[ 3 ];
-#pragma unroll
-      for( int k = 0; k < 6; ++k )
-        if( k < len )
-#pragma unroll
-          for( int d = 0; d < 3; ++d )
-            center[ d ] += x[ k ][ d ];
+      for( int k = 0; k < 3; ++k )
+      {
+        const int r = cs.refs[ e0 + k ];
+        for( int d = 0; d < 3; ++d )
+          x3[ k ][ d ] = S.x[ d ][ r ];
+      }
       const double inv = 1.0 / len;
-#pragma unroll
       for( int d = 0; d < 3; ++d )
         center[ d ] *= inv;
-      outer_normal3( x[ 0 ], x[ 1 ], x[ 2 ], fn );
+      outer_normal3( x3[ 0 ], x3[ 1 ], x3[ 2 ], fn );
+      for( int d = 0; d < 3; ++d )
+        S.fn[ d ][ lane ] = fn[ d ];
+      S.cf[ lane ] = dot3( center, fn );
+    }
+
+    // phase C2: the edge terms of Face::volume (3d/polyhedron.hh:216-222), spread evenly over the L lanes.  Two edges
+    // per iteration in straight-line code: the two dependent fp64 chains (cross, sqrt, three divisions) interleave.
+    VOFX_INLINE void clip_edge_operands ( const ClipScratch &S, const ClipCase &cs, int e, double *x0, double *x1, double *fn )
+    {
+      int f = 0;
+      while( cs.faceStart[ f + 1 ] <= e )
+        ++f;
+      const int r0 = cs.refs[ e ];
+      const int r1 = cs.refs[ ( e + 1 < cs.faceStart[ f + 1 ] ) ? e + 1 : cs.faceStart[ f ] ];
+      for( int d = 0; d < 3; ++d )
+      {
+        x0[ d ] = S.x[ d ][ r0 ];
+        x1[ d ] = S.x[ d ][ r1 ];
+        fn[ d ] = S.fn[ d ][ f ];
+      }
+    }
+
+    template< int L >
+    VOFX_HD inline void clip_phase_edges ( int lane, ClipScratch &S, const ClipCase &cs )
+    {
+      const int nEdges = cs.nEdges;
+#pragma unroll 1
+      for( int ea = lane; ea < nEdges; ea += 2 * L )
+      {
+        const int eb = ea + L;
+        const bool hasB = eb < nEdges;
+        double xa0[ 3 ], xa1[ 3 ], fna[ 3 ], xb0[ 3 ], xb1[ 3 ], fnb[ 3 ];
+        clip_edge_operands( S, cs, ea, xa0, xa1, fna );
+        clip_edge_operands( S, cs, hasB ? eb : ea, xb0, xb1, fnb );
+        const double ta = face_edge_term( xa0, xa1, fna );
+        const double tb = face_edge_term( xb0, xb1, fnb );
+        S.eterm[ ea ] = ta;
+        if( hasB )
+          S.eterm[ eb ] = tb;
+      }
+    }
+
+    // phase C3: lane f sums the edge terms of face f in order
+    VOFX_HD inline void clip_phase_face_sums ( int lane, ClipScratch &S, const ClipCase &cs )
+    {
+      if( lane >= cs.nFaces )
+        return;
       double fv = 0.0;
-#pragma unroll
-      for( int k = 0; k < 6; ++k )
-        if( k < len )
-          fv += face_edge_term( x[ k ], x[ ( k + 1 < 6 ) ? k + 1 : 0 ], fn );   // x[k+1] holds x[0] where k+1 == len
-      S.term[ lane ] = dot3( center, fn ) * fabs( fv / 2.0 );
+#pragma unroll 1
+      for( int e = cs.faceStart[ lane ]; e < cs.faceStart[ lane + 1 ]; ++e )
+        fv += S.eterm[ e ];
+      S.term[ lane ] = S.cf[ lane ] * fabs( fv / 2.0 );
     }
 
     // phase D (every lane): Polyhedron::volume, 3d/polyhedron.hh:317-324
     VOFX_HD inline double clip_phase_sum ( const ClipScratch &S, const ClipCase &cs )
     {
       double vol = 0.0;
+#pragma unroll 1
       for( int f = 0; f < cs.nFaces; ++f )
         vol += S.term[ f ];
       return fabs( vol / 3.0 );
@@ -465,9 +519,18 @@ namespace vofx
 
     // locateHalfSpace( Polyhedron( cube geometry ), innerNormal, fraction ), geometry/algorithm.hh:119-236, for a group of
     // L lanes.  Returns true and the plane constant, or false if the cell must take the serial walk (tied node heights).
+    // deferred root search of locate_coop: dist = base + brent( V, 0, h, 1e-14 ), geometry/algorithm.hh:221-227
+    struct RootTask
+    {
+      Cubic V;
+      double h, base;
+      int pending;
+      int cell;
+    };
+
     template< int L >
     VOFX_HD inline bool locate_coop ( const Group &G, LocateScratch &S, const SweepTable &T, const double *lo, const double *h,
-                                      const double *innerNormal, double fraction, double &dist )
+                                      const double *innerNormal, double fraction, double &dist, RootTask *root = nullptr )
     {
       double hi[ 3 ], outerNormal[ 3 ];
       for( int k = 0; k < 3; ++k )
@@ -726,6 +789,16 @@ namespace vofx
         else if( Vd_k1 > givenVolume )
         {
           V.target = givenVolume - Vd_k;
+          if( root )
+          {
+            // the root of V on [0, hk] is found by a one-thread-per-cell kernel (Brent is serial: here it would run
+            // redundantly in every lane of the group)
+            root->V = V;
+            root->h = hk;
+            root->base = dU[ k ];
+            root->pending = 1;
+            return true;
+          }
           dist = dU[ k ] + brent( V, 0.0, hk, 1e-14 );
           return true;
         }

@@ -22,12 +22,16 @@ namespace vofx
 
   VOFX_INLINE int last_axis ( const Grid &g ) { return g.dim - 1; }
 
+  // a context holds fewer than 2^31 cells (vofx_create): 32-bit division, not the 64-bit software routine
   VOFX_INLINE void cell_ijk ( const Grid &g, long long c, int *ijk )
   {
-    ijk[ 0 ] = int( c % g.ns[ 0 ] );
-    c /= g.ns[ 0 ];
-    ijk[ 1 ] = int( c % g.ns[ 1 ] );
-    ijk[ 2 ] = int( c / g.ns[ 1 ] );
+    unsigned r = (unsigned) c;
+    const unsigned n0 = (unsigned) g.ns[ 0 ], n1 = (unsigned) g.ns[ 1 ];
+    const unsigned q0 = r / n0;
+    ijk[ 0 ] = int( r - q0 * n0 );
+    const unsigned q1 = q0 / n1;
+    ijk[ 1 ] = int( q0 - q1 * n1 );
+    ijk[ 2 ] = int( q1 );
   }
 
   VOFX_INLINE long long cell_index ( const Grid &g, const int *ijk )

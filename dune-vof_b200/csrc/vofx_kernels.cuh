@@ -524,7 +524,8 @@ namespace vofx
   template< int L >
   __global__ void __launch_bounds__( 16 * L, VOFX_YOUNGS_THREADS_PER_SM / ( 16 * L ) ) k_youngs_coop3 ( Grid g, const double *__restrict__ u, const int *__restrict__ mixedList,
                                                              StepState *state, int capacity, double *__restrict__ hs,
-                                                             const coop::SweepTable *__restrict__ table, int *__restrict__ serialCells )
+                                                             const coop::SweepTable *__restrict__ table, int *__restrict__ serialCells,
+                                                             coop::RootTask *__restrict__ rootTasks )
   {
     constexpr int GROUPS = 16;          // 16 groups per block: 128 threads for L = 8, 64 for L = 4
     __shared__ coop::LocateScratch scratch[ GROUPS ];
@@ -552,18 +553,37 @@ namespace vofx
       }
       const double lo[ 3 ] = { cell_lower( g, 0, ijk[ 0 ] ), cell_lower( g, 1, ijk[ 1 ] ), cell_lower( g, 2, ijk[ 2 ] ) };
       double dist = 0.0;
-      const bool located = coop::locate_coop< L >( G, S, *table, lo, g.h, normal, colorEn, dist );
+      coop::RootTask root;
+      root.pending = 0;
+      const bool located = coop::locate_coop< L >( G, S, *table, lo, g.h, normal, colorEn, dist, &root );
       if( lane == 0 )
       {
         out[ 0 ] = normal[ 0 ];
         out[ 1 ] = normal[ 1 ];
         out[ 2 ] = normal[ 2 ];
-        if( located )
-          out[ 3 ] = dist;
-        else
+        if( !located )
           serialCells[ atomicAdd( &state->serialLocate, 1 ) ] = c;
+        else if( root.pending )
+        {
+          root.cell = c;
+          rootTasks[ atomicAdd( &state->rootCount, 1 ) ] = root;
+        }
+        else
+          out[ 3 ] = dist;
       }
       G.sync();
+    }
+  }
+
+  // Brent's method for the cells whose bracket k_youngs_coop3 has found: one thread per cell
+  template< int DIM >
+  __global__ void __launch_bounds__( 128 ) k_locate_root3 ( const StepState *state, const coop::RootTask *__restrict__ rootTasks, double *__restrict__ hs )
+  {
+    const int n = state->rootCount;
+    for( int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x )
+    {
+      const coop::RootTask r = rootTasks[ t ];
+      hs[ (long long) r.cell * 4 + 3 ] = r.base + brent( r.V, 0.0, r.h, 1e-14 );
     }
   }
 
@@ -1222,7 +1242,7 @@ namespace vofx
   }
 
   template< int DIM_ >
-  __global__ void __launch_bounds__( 128 ) k_flux_clip3 ( Grid g, const Velocity *__restrict__ velocity, const double *__restrict__ hs,
+  __global__ void __launch_bounds__( 128, 5 ) k_flux_clip3 ( Grid g, const Velocity *__restrict__ velocity, const double *__restrict__ hs,
                                                            const unsigned char *__restrict__ flags, const int *__restrict__ mixedList,
                                                            StepState *state, FluxRecord *__restrict__ records, int *__restrict__ tasks,
                                                            const coop::ClipCase *__restrict__ clipTable, int taskCapacity,
@@ -1275,6 +1295,10 @@ namespace vofx
         {
           coop::clip_phase_faces( lane, S, *cs );
           __syncwarp( groupMask );
+          coop::clip_phase_edges< LANES >( lane, S, *cs );
+          __syncwarp( groupMask );
+          coop::clip_phase_face_sums( lane, S, *cs );
+          __syncwarp( groupMask );
           flux = coop::clip_phase_sum( S, *cs );
         }
         __syncwarp( groupMask );     // the scratch is reused by the next task
@@ -1300,6 +1324,203 @@ namespace vofx
           nbc = flux / volume;                                   // update[ neighbor ] += flux / volume
         r->nb[ face ] = nbc;
       }
+    }
+  }
+
+  // E1 in 3D, cell-major: a group of 8 lanes owns one mixed cell.  Lanes 0..5 evaluate the motion of the six faces
+  // (velocity, time-step estimate, flux-free contributions); the outflow faces are then clipped one after the other by
+  // all 8 lanes (vofx_coop3d.cuh).  Nothing is evaluated twice and no task list goes through memory.
+  struct FaceScratch
+  {
+    double v[ 6 ][ 3 ];
+    double vN[ 6 ], sf[ 6 ], selfc[ 6 ];
+    unsigned char flagNb[ 6 ], hasNb[ 6 ], clip[ 6 ], hasSelf[ 6 ], hasNbc[ 6 ];
+    unsigned char pad[ 2 ];
+    double bankPad[ 1 ];
+  };
+  static_assert( sizeof( FaceScratch ) % 8 == 0 && ( sizeof( FaceScratch ) / 8 ) % 2 == 1, "FaceScratch stride must be an odd number of doubles" );
+
+  template< int DIM_ >
+  __global__ void __launch_bounds__( 128, 4 ) k_flux_cell3 ( Grid g, const Velocity *__restrict__ velocity, const double *__restrict__ hs,
+                                                              const unsigned char *__restrict__ flags, const int *__restrict__ mixedList,
+                                                              StepState *state, int capacity, FluxRecord *__restrict__ records,
+                                                              int *__restrict__ tasks, int taskCapacity, const coop::ClipCase *__restrict__ clipTable,
+                                                              const double *timeOverride, const double *dtOverride )
+  {
+    constexpr int DIM = 3, LANES = coop::kLanes, NFACES = 6;
+    constexpr int GROUPS = 128 / LANES;
+    __shared__ coop::ClipCase table[ 256 ];
+    __shared__ coop::ClipScratch scratch[ GROUPS ];
+    __shared__ FaceScratch faceScratch[ GROUPS ];
+    __shared__ double blockMin[ 4 ];
+    {
+      const uint4 *src = reinterpret_cast< const uint4 * >( clipTable );
+      uint4 *dst = reinterpret_cast< uint4 * >( table );
+      for( int i = threadIdx.x; i < int( 256 * sizeof( coop::ClipCase ) / sizeof( uint4 ) ); i += blockDim.x )
+        dst[ i ] = src[ i ];
+    }
+    __syncthreads();
+
+    const int count = mixed_count( state, capacity );
+    const double time = timeOverride ? *timeOverride : state->time;
+    const double dt = dtOverride ? *dtOverride : state->dt;
+    const double volume = cell_volume( g );
+    const int lane = threadIdx.x % LANES;
+    const int group = threadIdx.x / LANES;
+    const unsigned groupMask = 0xffu << ( ( threadIdx.x & 31 ) - lane );
+    coop::ClipScratch &S = scratch[ group ];
+    FaceScratch &F = faceScratch[ group ];
+    double dtMin = DBL_MAX;
+
+    for( int idx = blockIdx.x * GROUPS + group; idx < count; idx += gridDim.x * GROUPS )
+    {
+      const int c = mixedList[ idx ];
+      int ijk[ 3 ];
+      cell_ijk( g, c, ijk );
+      FluxRecord *r = records + idx;
+
+      if( lane < NFACES )
+      {
+        const int face = lane;
+        bool hasNb = false, hasSelf = false, hasNbc = false, needClip = false;
+        double sf = 0.0, selfc = 0.0;
+        unsigned char flagNb = 99;
+        int nb[ 3 ] = { ijk[ 0 ], ijk[ 1 ], ijk[ 2 ] };
+        nb[ face >> 1 ] += ( face & 1 ) ? 1 : -1;
+        // a face has a neighbour iff the neighbour is inside the global domain (intersection.neighbor(), :102-103)
+        if( in_domain( g, nb ) )
+        {
+          hasNb = true;
+          flagNb = cell_exists( g, nb ) ? flags[ cell_index( g, nb ) ] : (unsigned char) 99;
+          FaceMotion m;
+          face_motion< DIM >( g, *velocity, ijk, face, time, dt, m );
+          sf = m.sf;
+          F.v[ face ][ 0 ] = m.v[ 0 ];
+          F.v[ face ][ 1 ] = m.v[ 1 ];
+          F.v[ face ][ 2 ] = m.v[ 2 ];
+          F.vN[ face ] = m.vN;
+          if( m.vn > 0 )
+          {
+            needClip = true;
+            hasSelf = true;
+            hasNbc = ( flagNb == 3 ) || ( flagNb == 0 ) || is_mixed( flagNb );
+          }
+          if( flagNb == 3 && m.vn < 0 )
+          {
+            hasSelf = true;
+            selfc = -( m.vN / volume );                          // inflow from a full neighbour
+          }
+        }
+        F.sf[ face ] = sf;
+        F.selfc[ face ] = selfc;
+        F.flagNb[ face ] = flagNb;
+        F.hasNb[ face ] = hasNb;
+        F.clip[ face ] = needClip;
+        F.hasSelf[ face ] = hasSelf;
+        F.hasNbc[ face ] = hasNbc;
+        if( !needClip )
+        {
+          r->self[ face ] = selfc;
+          r->nb[ face ] = 0.0;
+        }
+      }
+      __syncwarp( groupMask );
+
+      if( lane == 0 )
+      {
+        // time-step estimate: volume / sum of |F| |n.v| over the faces in face order, :113,144
+        double sumFluxes = 0.0;
+        unsigned selfBits = 0, nbBits = 0;
+#pragma unroll
+        for( int f = 0; f < NFACES; ++f )
+        {
+          if( F.hasNb[ f ] )
+            sumFluxes += F.sf[ f ];
+          selfBits |= F.hasSelf[ f ] ? ( 1u << f ) : 0u;
+          nbBits |= F.hasNbc[ f ] ? ( 1u << f ) : 0u;
+        }
+        r->selfMask = (unsigned char) selfBits;
+        r->nbMask = (unsigned char) nbBits;
+        // only cells this rank owns enter the estimate (every cell is owned by exactly one rank)
+        const int la = ijk[ DIM - 1 ];
+        if( la >= g.own0 && la < g.own1 )
+        {
+          const double est = volume / sumFluxes;
+          if( est == est && est < dtMin )                        // std::min( dtEst, est ): NaN never wins
+            dtMin = est;
+        }
+      }
+
+      const double *rec = hs + (long long) c * ( DIM + 1 );
+      const Hs3 H = { { rec[ 0 ], rec[ 1 ], rec[ 2 ] }, rec[ 3 ] };
+      const bool valid = hs_valid( H );
+      const double lo[ 3 ] = { cell_lower( g, 0, ijk[ 0 ] ), cell_lower( g, 1, ijk[ 1 ] ), cell_lower( g, 2, ijk[ 2 ] ) };
+#pragma unroll 1
+      for( int face = 0; face < NFACES; ++face )
+      {
+        if( !F.clip[ face ] )
+          continue;
+        double flux = fabs( 0.0 / 3.0 );
+        if( valid )
+        {
+          const double v[ 3 ] = { F.v[ face ][ 0 ], F.v[ face ][ 1 ], F.v[ face ][ 2 ] };
+          double xn[ 3 ];
+          coop::upwind_node( lane, lo, g.h, face, v, xn );
+          coop::clip_phase_classify( lane, S, xn, H );
+          __syncwarp( groupMask );
+          const coop::ClipCase *cs;
+          const int status = coop::clip_phase_cut( lane, S, H, table, cs );
+          __syncwarp( groupMask );
+          if( status == 0 )
+          {
+            coop::clip_phase_faces( lane, S, *cs );
+            __syncwarp( groupMask );
+            coop::clip_phase_edges< LANES >( lane, S, *cs );
+            __syncwarp( groupMask );
+            coop::clip_phase_face_sums( lane, S, *cs );
+            __syncwarp( groupMask );
+            flux = coop::clip_phase_sum( S, *cs );
+          }
+          __syncwarp( groupMask );     // the scratch is reused by the next clip
+          if( status == 2 )
+          {
+            // a node on the plane / irregular mask: rare; queued for k_flux_clip_serial3
+            if( lane == 0 )
+              tasks[ taskCapacity - 1 - atomicAdd( &state->serialCount, 1 ) ] = idx * 8 + face;
+            continue;
+          }
+        }
+        if( lane == 0 )
+        {
+          const unsigned char flagNb = F.flagNb[ face ];
+          r->self[ face ] = -( flux / volume );                  // update[ entity ] -= flux / volume
+          double nbc = 0.0;
+          if( flagNb == 3 )
+            nbc = -( ( F.vN[ face ] - flux ) / volume );         // update[ neighbor ] -= ( v*N - flux ) / volume
+          else if( flagNb == 0 || is_mixed( flagNb ) )
+            nbc = flux / volume;                                 // update[ neighbor ] += flux / volume
+          r->nb[ face ] = nbc;
+        }
+      }
+      __syncwarp( groupMask );         // F is rewritten by the next cell
+    }
+
+    // one atomic per block
+#pragma unroll
+    for( int o = 16; o > 0; o >>= 1 )
+    {
+      const double other = __shfl_xor_sync( 0xffffffffu, dtMin, o );
+      dtMin = ( other < dtMin ) ? other : dtMin;
+    }
+    if( ( threadIdx.x & 31 ) == 0 )
+      blockMin[ threadIdx.x >> 5 ] = dtMin;
+    __syncthreads();
+    if( threadIdx.x == 0 )
+    {
+      for( int w = 1; w < 4; ++w )
+        dtMin = ( blockMin[ w ] < dtMin ) ? blockMin[ w ] : dtMin;
+      if( dtMin < DBL_MAX )
+        atomic_min_positive( &state->dtEst, dtMin );
     }
   }
 
@@ -1479,6 +1700,7 @@ namespace vofx
     state->taskCount = 0;
     state->serialCount = 0;
     state->serialLocate = 0;
+    state->rootCount = 0;
   }
 
   static __global__ void k_reset_counters ( StepState *state )
@@ -1487,6 +1709,7 @@ namespace vofx
     state->taskCount = 0;
     state->serialCount = 0;
     state->serialLocate = 0;
+    state->rootCount = 0;
     state->dtEst = DBL_MAX;
   }
 

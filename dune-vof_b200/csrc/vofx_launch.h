@@ -42,7 +42,9 @@ namespace vofx
     // k_recon3d.cu, k_swartz3d.cu, k_flux3d.cu
     void youngs3 ( int blocks, cudaStream_t s, Grid g, const double *u, const int *mixedList, const StepState *state, int capacity, double *hs );
     void youngs_coop3 ( int lanes, int blocks, cudaStream_t s, Grid g, const double *u, const int *mixedList, StepState *state, int capacity, double *hs,
-                        const void *sweepTable, int *serialCells );
+                        const void *sweepTable, int *serialCells, void *rootTasks );
+    void locate_root3 ( int blocks, cudaStream_t s, const StepState *state, const void *rootTasks, double *hs );
+    size_t root_task_bytes ();
     void locate_serial3 ( cudaStream_t s, Grid g, const double *u, const StepState *state, double *hs, const int *serialCells );
     int make_sweep_table ( void *host, size_t bytes );   // returns the number of cases (96) or -1
     size_t sweep_table_bytes ();
@@ -55,6 +57,9 @@ namespace vofx
                          int capacity, FluxRecord *records, int *tasks, int taskCapacity, const double *timeOverride, const double *dtOverride );
     void flux_clip3 ( int blocks, cudaStream_t s, Grid g, const Velocity *velocity, const double *hs, const unsigned char *flags, const int *mixedList,
                       StepState *state, FluxRecord *records, int *tasks, const void *clipTable, int taskCapacity, const double *timeOverride, const double *dtOverride );
+    void flux_cell3 ( int blocks, cudaStream_t s, Grid g, const Velocity *velocity, const double *hs, const unsigned char *flags, const int *mixedList,
+                      StepState *state, int capacity, FluxRecord *records, int *tasks, int taskCapacity, const void *clipTable,
+                      const double *timeOverride, const double *dtOverride );
     void make_clip_table ( void *host256x64 );   // 256 entries of 64 bytes (coop::ClipCase)
     void test_locate3 ( int blocks, long long count, const double *lo, const double *h, const double *normal, const double *fraction, double *out );
     void test_flux3 ( int blocks, long long count, const double *lo, const double *h, const int *face, const double *v, const double *hs, double *out );

@@ -19,6 +19,8 @@ namespace vofx
     int taskCount;              // entries in the clip-task list of the current step (k_flux_prepare -> k_flux_clip)
     int serialCount;            // clip tasks left to the serial kernel (stored from the end of the task array)
     int serialLocate;           // mixed cells whose plane-constant solve is left to the serial kernel
+    int rootCount;              // mixed cells whose bracket is found and whose root search is left to k_locate_root3
+    int pad;
   };
 
   // per mixed cell: what it adds to its own update and to each face neighbour's update (Appendix C of SURVEY.md)

@@ -142,6 +142,10 @@ extern "C"
     {
       for( int lane = 0; lane < 8; ++lane )
         coop::clip_phase_faces( lane, S, *cs );
+      for( int lane = 0; lane < 8; ++lane )
+        coop::clip_phase_edges< 8 >( lane, S, *cs );
+      for( int lane = 0; lane < 8; ++lane )
+        coop::clip_phase_face_sums( lane, S, *cs );
       *out = coop::clip_phase_sum( S, *cs );
     }
     return 0;
