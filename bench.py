@@ -291,8 +291,17 @@ def main():
     roofline = None
     if flag:
         achieved = FLAG_KERNEL_BYTES_PER_CELL * cells_per_gpu / (flag["avg_ms"] * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "k_flag_compact", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel at this size
+        traffic = None
+        try:
+            summary = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_summary.json")))
+            if N_SIDE == 512:
+                traffic = summary["k_flag_rows"]["dram_bytes_total"]
+        except Exception:
+            traffic = None
+        roofline = {"bound": "hbm", "kernel": "k_flag_rows (profiled as k_flag_compact)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": traffic, "traffic_source": "profiles/r1_ncu_summary.json (ncu --set full, per launch)",
+                    "algorithmic_bytes_per_launch": FLAG_KERNEL_BYTES_PER_CELL * cells_per_gpu, "peak_source": peak_src,
                     "algorithmic_bytes_per_cell": FLAG_KERNEL_BYTES_PER_CELL,
                     "kernel_avg_ms": flag["avg_ms"], "kernel_share_of_step": flag["share"],
                     "note": "dense pass reads u (8 B) and writes the flag (1 B); the u' write of SURVEY 8(d)'s 17 B/cell-step "
