@@ -1,0 +1,71 @@
+"""Worker of tests/test_gpu_multirank.py, launched by torch.distributed.run with one rank per GPU: the slab-decomposed
+run must reproduce the single-context run BIT FOR BIT (coordinates come from global indices, the update is an
+owner-computes gather and the time step is a MIN all-reduce)."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import dune_vof_b200.operators as ops
+    from dune_vof_b200.decomposition import SlabAlgorithm, split_last_axis
+
+    failures = []
+    cases = [((48, 40, 64), ops.PROB_LEVEQUE, ops.RECON_YOUNGS, 6), ((32, 32, 48), ops.PROB_SFLOW, ops.RECON_HF, 4),
+             ((64, 96), ops.PROB_SLOTTED_CYLINDER, ops.RECON_HF, 5), ((24, 24, 32), ops.PROB_ROTATING_CIRCLE, ops.RECON_SWARTZ, 2)]
+    for n, problem, recon, passes in cases:
+        # serial reference on this rank's GPU
+        g1 = ops.CartesianGrid(n, device=local)
+        g1.set_velocity_builtin(problem)
+        if len(n) == 2 and problem == ops.PROB_SLOTTED_CYLINDER:
+            u1 = g1.init(problem)
+        else:
+            u1 = g1.init(problem)
+        u0 = u1.clone()
+        a1 = ops.Algorithm(g1, cfl=0.5, eps=1e-6, reconstruction_kind=recon)
+        st1 = a1.run_passes(u1, passes)
+
+        slab = SlabAlgorithm(n, rank, world, 0.5, 1e-6, recon, device=local)
+        slab.grid.set_velocity_builtin(problem)
+        uh = slab.grid.empty("color")
+        lo, cnt = split_last_axis(n[-1], world, rank)
+        layer = u0.numel() // n[-1]
+        slab.owned(uh).copy_(u0.view(n[-1], layer)[lo:lo + cnt])
+        slab.begin(0.0, 0.0)
+        for _ in range(passes):
+            slab.step(uh)
+        st = slab.state()
+        torch.cuda.synchronize()
+        mine = slab.owned(uh).contiguous()
+        ref = u1.view(n[-1], layer)[lo:lo + cnt]
+        same = torch.equal(mine.view(torch.int64), ref.contiguous().view(torch.int64))
+        ok = torch.tensor([1 if (same and st.time == st1.time and st.dt == st1.dt) else 0], device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) != 1:
+            failures.append((n, problem, recon))
+        if rank == 0:
+            print(f"case n={n} problem={problem} recon={recon}: {'bit-identical' if int(ok.item()) == 1 else 'MISMATCH'} "
+                  f"(time={st.time!r} dt={st.dt!r})", flush=True)
+        g1.close()
+        slab.grid.close()
+    dist.barrier()
+    dist.destroy_process_group()
+    if failures:
+        print("MULTIRANK FAILED", failures)
+        return 1
+    if rank == 0:
+        print("MULTIRANK PASSED")
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
