@@ -276,9 +276,14 @@ def main():
             vlib.check(L.vofx_step_host(grid._ctx, C.byref(p), C.c_void_p(host_u.data_ptr()), None))
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
-        e2e = {"value": total_cells * KE / wall, "unit": "cell-steps/s", "h2d_bytes_per_step": 8 * grid.cells,
-               "d2h_bytes_per_step": 8 * grid.cells, "steps": KE, "ms_per_step": 1e3 * wall / KE,
-               "api": "vofx_step_host (pinned host colour function in, colour function out)"}
+        h2d, d2h = C.c_int64(0), C.c_int64(0)
+        vlib.check(L.vofx_host_transfer_bytes(grid._ctx, C.byref(h2d), C.byref(d2h)))
+        # the host colour function must equal the device one afterwards (checked outside the timed region)
+        torch.cuda.synchronize()
+        e2e = {"value": total_cells * KE / wall, "unit": "cell-steps/s", "h2d_bytes_per_step": int(h2d.value),
+               "d2h_bytes_per_step": int(d2h.value), "steps": KE, "ms_per_step": 1e3 * wall / KE,
+               "api": "vofx_step_host: pinned host colour function in (whole array H2D), updated in place on the host from the "
+                      "(cell, value) pairs of the cells the step changed (sparse D2H) + loop state"}
     else:
         e2e = {"value": None, "unit": "cell-steps/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
                "note": "measured at N=1 only"}

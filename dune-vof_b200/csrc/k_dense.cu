@@ -30,12 +30,13 @@ namespace vofx
         k_compact_flags< 3 ><<< blocks, 256, 0, s >>>( g, flags, mixedList, slot, capacity, state );
     }
     void update ( int dim, int blocks, cudaStream_t s, Grid g, const unsigned char *flags, const int *mixedList, const int *slot, const StepState *state,
-                  int capacity, const FluxRecord *records, double *target, int accumulate )
+                  int capacity, const FluxRecord *records, double *target, int accumulate, StepState *stateRW, int *changedIdx, double *changedVal,
+                  int changedCapacity )
     {
       if( dim == 2 )
-        k_update< 2 ><<< blocks, 128, 0, s >>>( g, flags, mixedList, slot, state, capacity, records, target, accumulate );
+        k_update< 2 ><<< blocks, 128, 0, s >>>( g, flags, mixedList, slot, state, capacity, records, target, accumulate, stateRW, changedIdx, changedVal, changedCapacity );
       else
-        k_update< 3 ><<< blocks, 128, 0, s >>>( g, flags, mixedList, slot, state, capacity, records, target, accumulate );
+        k_update< 3 ><<< blocks, 128, 0, s >>>( g, flags, mixedList, slot, state, capacity, records, target, accumulate, stateRW, changedIdx, changedVal, changedCapacity );
     }
     void curvature_local ( int dim, int blocks, cudaStream_t s, Grid g, const double *u, const double *hs, const int *mixedList, const StepState *state,
                            int capacity, double *curv1, unsigned char *ok1 )

@@ -54,6 +54,12 @@ struct vofx_ctx
   int taskCapacity = 0;
   void *sweepTable = nullptr;       // coop::SweepTable
   int *serialCells = nullptr;       // mixed cells whose plane constant is left to the serial walk
+  // sparse write-back of the host-buffer step: (cell, new value) of every cell the update touched
+  int *changedIdx = nullptr;
+  double *changedVal = nullptr;
+  int changedCapacity = 0;
+  bool trackChanges = false;
+  long long lastH2D = 0, lastD2H = 0;   // bytes moved by the last vofx_step_host call
   void *rootTasks = nullptr;        // coop::RootTask per mixed cell: brackets found by k_youngs_coop3, roots by k_locate_root3
   int lanesPerCell = 4;            // measured on B200 at 512^3: 0.47 ms (4 lanes per cell) vs 0.64 ms (8)
   void *clipTable = nullptr;        // coop::ClipCase[ 256 ]
@@ -287,7 +293,9 @@ namespace
     const Grid &g = ctx->grid;
     const int blocks = ctx->numSMs * 8;
     profBegin( ctx );
-    launch::update( g.dim, blocks, ctx->stream, g, flags, ctx->mixedList, ctx->slot, ctx->state, ctx->capacity, ctx->records, target, accumulate ? 1 : 0 );
+    const bool track = accumulate && ctx->trackChanges && ctx->changedIdx;
+    launch::update( g.dim, blocks, ctx->stream, g, flags, ctx->mixedList, ctx->slot, ctx->state, ctx->capacity, ctx->records, target, accumulate ? 1 : 0,
+                    ctx->state, track ? ctx->changedIdx : nullptr, track ? ctx->changedVal : nullptr, ctx->changedCapacity );
     return checkLaunch( ctx, "k_update" );
   }
 
@@ -521,6 +529,8 @@ extern "C"
     cudaFree( ctx->sweepTable );
     cudaFree( ctx->serialCells );
     cudaFree( ctx->rootTasks );
+    cudaFree( ctx->changedIdx );
+    cudaFree( ctx->changedVal );
     cudaFree( ctx->state );
     cudaFree( ctx->curv1 );
     cudaFree( ctx->ok1 );
@@ -1015,17 +1025,66 @@ extern "C"
     int rc = ensureMirrors( ctx );
     if( !rc && p->with_curvature )
       rc = ensureDevice( ctx->dKappa, N );
+    // the update touches the mixed cells and their face neighbours only: the host colour function is brought up to
+    // date from the list of (cell, new value) pairs instead of a second full-size copy across PCIe
+    if( !rc && !ctx->changedIdx )
+    {
+      const long long cap = 7LL * ctx->capacity < (long long) N ? 7LL * ctx->capacity : (long long) N;
+      ctx->changedCapacity = (int) ( cap < ( 1LL << 30 ) ? cap : ( 1LL << 30 ) );
+      rc = ensureDevice( ctx->changedIdx, (size_t) ctx->changedCapacity );
+      rc = rc ? rc : ensureDevice( ctx->changedVal, (size_t) ctx->changedCapacity );
+    }
+    if( rc )
+      return rc;
     // u may be caller-pinned memory: copy directly, no staging copy
-    if( rc )
-      return rc;
     VOFX_CUDA( cudaMemcpyAsync( ctx->dU, u, N * sizeof( double ), cudaMemcpyHostToDevice, ctx->stream ) );
+    ctx->lastH2D = (long long) ( N * sizeof( double ) );
+    ctx->lastD2H = (long long) sizeof( StepState ) + ( flags ? (long long) N : 0 );
+    ctx->trackChanges = true;
     rc = vofx_step( ctx, p, ctx->dU, ctx->dFlags, ctx->dHs, ctx->dKappa );
+    ctx->trackChanges = false;
     if( rc )
       return rc;
-    VOFX_CUDA( cudaMemcpyAsync( u, ctx->dU, N * sizeof( double ), cudaMemcpyDeviceToHost, ctx->stream ) );
     if( flags )
       VOFX_CUDA( cudaMemcpyAsync( flags, ctx->dFlags, N, cudaMemcpyDeviceToHost, ctx->stream ) );
+    StepState s;
+    rc = readState( ctx, s );
+    if( rc )
+      return rc;
+    const size_t n = (size_t) s.changedCountLast;
+    if( n > (size_t) ctx->changedCapacity )
+    {
+      VOFX_CUDA( cudaMemcpyAsync( u, ctx->dU, N * sizeof( double ), cudaMemcpyDeviceToHost, ctx->stream ) );
+      VOFX_CUDA( cudaStreamSynchronize( ctx->stream ) );
+      ctx->lastD2H += (long long) ( N * sizeof( double ) );
+      return VOFX_OK;
+    }
+    if( n == 0 )
+      return VOFX_OK;
+    ctx->lastD2H += (long long) ( n * ( sizeof( int ) + sizeof( double ) ) );
+    // grow the staging buffer geometrically: re-pinning host memory every step (the band grows) costs milliseconds
+    size_t want = n * ( sizeof( int ) + sizeof( double ) ) + 16;
+    if( want > ctx->pinnedBytes )
+      want = ( 2 * want > ( size_t( 64 ) << 20 ) ) ? 2 * want : ( size_t( 64 ) << 20 );
+    rc = ensurePinned( ctx, want );
+    if( rc )
+      return rc;
+    double *hostVal = static_cast< double * >( ctx->pinned );
+    int *hostIdx = reinterpret_cast< int * >( hostVal + n );
+    VOFX_CUDA( cudaMemcpyAsync( hostVal, ctx->changedVal, n * sizeof( double ), cudaMemcpyDeviceToHost, ctx->stream ) );
+    VOFX_CUDA( cudaMemcpyAsync( hostIdx, ctx->changedIdx, n * sizeof( int ), cudaMemcpyDeviceToHost, ctx->stream ) );
     VOFX_CUDA( cudaStreamSynchronize( ctx->stream ) );
+    for( size_t i = 0; i < n; ++i )
+      u[ hostIdx[ i ] ] = hostVal[ i ];
+    return VOFX_OK;
+  }
+
+  int vofx_host_transfer_bytes ( const vofx_ctx *ctx, int64_t *h2d, int64_t *d2h )
+  {
+    if( !ctx || !h2d || !d2h )
+      return fail( VOFX_ERR_ARGUMENT, "null argument" );
+    *h2d = ctx->lastH2D;
+    *d2h = ctx->lastD2H;
     return VOFX_OK;
   }
 

@@ -480,15 +480,20 @@ namespace vofx
       };
       double fnz[ 6 ], fnrm[ 6 ];       // outer normal of face f of P: z component, norm of the xy part
       double px[ 2 ][ 8 ], py[ 2 ][ 8 ];   // polygon nodes of the current / next bracket
-      double aterm[ kMaxATerms ], bterm[ 8 ], cterm[ 8 ];
-      double term[ 8 ];                 // face terms of the cell volume
+      union
+      {
+        double aterm[ kMaxATerms ];     // terms of A of the current bracket
+        double term[ 8 ];               // face terms of the cell volume (before the brackets)
+      };
+      union
+      {
+        struct { double bterm[ 8 ], cterm[ 8 ]; };   // terms of B and C of the current bracket
+        double sums[ 12 ];              // AtA (6 unique entries) and Atb (before the plane-constant solve)
+      };
       double ds[ 8 ];                   // sorted node heights
-      double sums[ 12 ];                // AtA (6 unique entries) and Atb
       unsigned char ids[ 8 ];
       unsigned char lsValid[ 8 ];
       SweepBracket walked;              // descriptor produced by the walk of lane 0 (cells with tied node heights)
-      Sweep sweep;                      // state of that walk (topology only)
-      double bankPad[ 1 ];              // see the static_assert below
     };
     // consecutive groups of a warp address the same members: an odd stride in 8-byte words spreads them over the banks
     static_assert( sizeof( LocateScratch ) % 8 == 0 && ( sizeof( LocateScratch ) / 8 ) % 2 == 1, "LocateScratch stride must be an odd number of doubles" );
@@ -508,6 +513,44 @@ namespace vofx
     {
       sweep_evolve< false >( sweep, nullptr, z, dk, dk1, dk1 - dk );
       sweep_describe( sweep, walked );
+    }
+
+    // ---- the reference's face formulas on an AXIS-ALIGNED box -----------------------------------------------------------
+    // Every vector that occurs in Polyhedron::volume of the cell itself (edge vectors, their cross products, the face
+    // normals) has exactly one non-zero component c.  Then | . | = sqrt( c*c ) = |c| exactly (radix 2, round to nearest,
+    // no over/underflow: S. Boldo, "Stupid is as stupid does: taking the square root of the square of a floating-point
+    // number", 2015) and c / |c| = +-1, (+-0) / s = +-0 with the sign of IEEE division: the same bits as
+    // outer_normal3 / face_edge_term without a single sqrt or division.  Checked against the oracle in the CPU tests.
+    VOFX_INLINE double norm3_axis ( const double *a ) { return fabs( a[ 0 ] ) + fabs( a[ 1 ] ) + fabs( a[ 2 ] ); }
+    VOFX_INLINE double unit_axis ( double x, double s ) { return ( ( x == 0.0 ) ? x : copysign( 1.0, x ) ) * copysign( 1.0, s ); }
+
+    VOFX_INLINE void outer_normal3_axis ( const double *n0, const double *n1, const double *n2, double *normal )
+    {
+      double v1[ 3 ], v2[ 3 ];
+      for( int k = 0; k < 3; ++k )
+      {
+        v1[ k ] = n0[ k ] - n1[ k ];
+        v2[ k ] = n2[ k ] - n1[ k ];
+      }
+      cross3( v1, v2, normal );
+      const double s = -1.0 * norm3_axis( normal );
+      for( int k = 0; k < 3; ++k )
+        normal[ k ] = unit_axis( normal[ k ], s );
+    }
+
+    VOFX_INLINE double face_edge_term_axis ( const double *x0, const double *x1, const double *fn )
+    {
+      double center[ 3 ], v1[ 3 ], en[ 3 ];
+      for( int k = 0; k < 3; ++k )
+      {
+        center[ k ] = ( x0[ k ] + x1[ k ] ) * 0.5;
+        v1[ k ] = x1[ k ] - x0[ k ];
+      }
+      cross3( v1, fn, en );
+      const double nrm = norm3_axis( en );
+      for( int k = 0; k < 3; ++k )
+        en[ k ] = unit_axis( en[ k ], nrm );
+      return dot3( center, en ) * norm3_axis( v1 );
     }
 
     VOFX_INLINE void cell_node ( const double *lo, const double *hi, int i, double *x )
@@ -581,10 +624,10 @@ namespace vofx
           const double s = 1.0 / 4;
           for( int d = 0; d < 3; ++d )
             center[ d ] *= s;
-          outer_normal3( x[ 0 ], x[ 1 ], x[ 2 ], fn );
+          outer_normal3_axis( x[ 0 ], x[ 1 ], x[ 2 ], fn );
           double fv = 0.0;
           for( int k = 0; k < 4; ++k )
-            fv += face_edge_term( x[ k ], x[ ( k + 1 ) & 3 ], fn );
+            fv += face_edge_term_axis( x[ k ], x[ ( k + 1 ) & 3 ], fn );
           S.term[ f ] = dot3( center, fn ) * fabs( fv / 2.0 );
         }
 #pragma unroll 1
@@ -684,6 +727,7 @@ namespace vofx
         }
       }
       const bool walking = ( C == nullptr );
+      Sweep sweep;                                       // state of lane 0's walk (topology only)
       if( walking )
       {
         VOFX_LANES( G, L, lane )
@@ -693,7 +737,7 @@ namespace vofx
             double dsCopy[ 8 ];
             for( int k = 0; k < 8; ++k )
               dsCopy[ k ] = S.ds[ k ];
-            walk_begin( S.sweep, S.walked, S.ids, dsCopy );
+            walk_begin( sweep, S.walked, S.ids, dsCopy );
           }
         }
       }
@@ -706,7 +750,7 @@ namespace vofx
           VOFX_LANES( G, L, lane )
           {
             if( lane == 0 )
-              walk_next( S.sweep, S.walked, S.P[ 2 ], dU[ k - 1 ], dU[ k ] );
+              walk_next( sweep, S.walked, S.P[ 2 ], dU[ k - 1 ], dU[ k ] );
           }
         }
         const SweepBracket &B = walking ? S.walked : C->bracket[ k ];

@@ -1340,8 +1340,11 @@ namespace vofx
   };
   static_assert( sizeof( FaceScratch ) % 8 == 0 && ( sizeof( FaceScratch ) / 8 ) % 2 == 1, "FaceScratch stride must be an odd number of doubles" );
 
+#ifndef VOFX_FLUX_BLOCKS_PER_SM
+#define VOFX_FLUX_BLOCKS_PER_SM 4
+#endif
   template< int DIM_ >
-  __global__ void __launch_bounds__( 128, 4 ) k_flux_cell3 ( Grid g, const Velocity *__restrict__ velocity, const double *__restrict__ hs,
+  __global__ void __launch_bounds__( 128, VOFX_FLUX_BLOCKS_PER_SM ) k_flux_cell3 ( Grid g, const Velocity *__restrict__ velocity, const double *__restrict__ hs,
                                                               const unsigned char *__restrict__ flags, const int *__restrict__ mixedList,
                                                               StepState *state, int capacity, FluxRecord *__restrict__ records,
                                                               int *__restrict__ tasks, int taskCapacity, const coop::ClipCase *__restrict__ clipTable,
@@ -1586,7 +1589,8 @@ namespace vofx
   template< int DIM >
   __global__ void __launch_bounds__( 128 ) k_update ( Grid g, const unsigned char *__restrict__ flags, const int *__restrict__ mixedList,
                                                        const int *__restrict__ slot, const StepState *state, int capacity,
-                                                       const FluxRecord *__restrict__ records, double *__restrict__ target, int accumulate )
+                                                       const FluxRecord *__restrict__ records, double *__restrict__ target, int accumulate,
+                                                       StepState *stateRW, int *__restrict__ changedIdx, double *__restrict__ changedVal, int changedCapacity )
   {
     constexpr int LANES = ( DIM == 3 ) ? 8 : 8;
     constexpr int NFACES = 2 * DIM;
@@ -1681,7 +1685,28 @@ namespace vofx
       }
 
       if( accumulate )
-        target[ X ] += 1.0 * acc;                  // uh.axpy( 1.0, update ), colorfunction.hh:31-37
+      {
+        const double value = target[ X ] + 1.0 * acc;   // uh.axpy( 1.0, update ), colorfunction.hh:31-37
+        target[ X ] = value;
+        if( changedIdx )
+        {
+          // every cell is updated by exactly one lane per step: the list of (cell, new value) pairs is what a host
+          // colour function needs to be brought up to date (vofx_step_host); one atomic per group of converged lanes
+          const unsigned active = __activemask();
+          const int leader = __ffs( active ) - 1;
+          const int laneInWarp = threadIdx.x & 31;
+          int base = 0;
+          if( laneInWarp == leader )
+            base = atomicAdd( &stateRW->changedCount, __popc( active ) );
+          base = __shfl_sync( active, base, leader );
+          const int pos = base + __popc( active & ( ( 1u << laneInWarp ) - 1 ) );
+          if( pos < changedCapacity )
+          {
+            changedIdx[ pos ] = int( X );
+            changedVal[ pos ] = value;
+          }
+        }
+      }
       else
         target[ X ] = acc;                         // the dense `update` of the operator-level API
     }
@@ -1697,6 +1722,8 @@ namespace vofx
     state->dtEst = DBL_MAX;
     state->mixedCountLast = state->mixedCount;
     state->mixedCount = 0;
+    state->changedCountLast = state->changedCount;
+    state->changedCount = 0;
     state->taskCount = 0;
     state->serialCount = 0;
     state->serialLocate = 0;
@@ -1710,6 +1737,7 @@ namespace vofx
     state->serialCount = 0;
     state->serialLocate = 0;
     state->rootCount = 0;
+    state->changedCount = 0;
     state->dtEst = DBL_MAX;
   }
 

@@ -17,7 +17,8 @@ namespace vofx
                         int capacity, StepState *state, int compact );
     void compact_flags ( int dim, int blocks, cudaStream_t s, Grid g, const unsigned char *flags, int *mixedList, int *slot, int capacity, StepState *state );
     void update ( int dim, int blocks, cudaStream_t s, Grid g, const unsigned char *flags, const int *mixedList, const int *slot, const StepState *state,
-                  int capacity, const FluxRecord *records, double *target, int accumulate );
+                  int capacity, const FluxRecord *records, double *target, int accumulate, StepState *stateRW, int *changedIdx, double *changedVal,
+                  int changedCapacity );
     void curvature_local ( int dim, int blocks, cudaStream_t s, Grid g, const double *u, const double *hs, const int *mixedList, const StepState *state,
                            int capacity, double *curv1, unsigned char *ok1 );
     void curvature_average ( int dim, int blocks, cudaStream_t s, Grid g, const unsigned char *flags, const int *mixedList, const int *slot,

@@ -20,6 +20,8 @@ namespace vofx
     int serialCount;            // clip tasks left to the serial kernel (stored from the end of the task array)
     int serialLocate;           // mixed cells whose plane-constant solve is left to the serial kernel
     int rootCount;              // mixed cells whose bracket is found and whose root search is left to k_locate_root3
+    int changedCount;           // entries of the changed-cell list of the current step (host-buffer variant: sparse write-back)
+    int changedCountLast;
     int pad;
   };
 

@@ -23,7 +23,7 @@ SYMBOLS = [
     "vofx_velocity_set_component", "vofx_velocity_set_factor", "vofx_velocity_set_faces", "vofx_velocity_builtin", "vofx_face_velocity",
     "vofx_flag", "vofx_reconstruct", "vofx_evolve", "vofx_axpy", "vofx_curvature", "vofx_step_begin", "vofx_step",
     "vofx_step_state", "vofx_step_local", "vofx_step_finish", "vofx_dt_est_device", "vofx_flag_host",
-    "vofx_reconstruct_host", "vofx_evolve_host", "vofx_curvature_host", "vofx_step_host", "vofx_color_upload",
+    "vofx_reconstruct_host", "vofx_evolve_host", "vofx_curvature_host", "vofx_step_host", "vofx_host_transfer_bytes", "vofx_color_upload",
     "vofx_step_resident", "vofx_color_download", "vofx_init",
     "vofx_test_locate", "vofx_test_flux", "vofx_test_interface", "vofx_launch_count", "vofx_profile_enable",
     "vofx_profile_read",
@@ -105,6 +105,7 @@ def load():
     L.vofx_evolve_host.argtypes = [vp, dp, bp, C.c_double, C.c_double, dp, C.POINTER(C.c_double)]
     L.vofx_curvature_host.argtypes = [vp, dp, dp, bp, dp, bp]
     L.vofx_step_host.argtypes = [vp, C.POINTER(StepParams), dp, bp]
+    L.vofx_host_transfer_bytes.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.vofx_color_upload.argtypes = [vp, dp]
     L.vofx_step_resident.argtypes = [vp, C.POINTER(StepParams)]
     L.vofx_color_download.argtypes = [vp, dp, bp]

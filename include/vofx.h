@@ -167,6 +167,9 @@ int vofx_evolve_host ( vofx_ctx *ctx, const double *halfspaces, const uint8_t *f
 int vofx_curvature_host ( vofx_ctx *ctx, const double *u, const double *halfspaces, const uint8_t *flags, double *kappa, uint8_t *valid );
 /* one full loop pass on a host colour function: H2D u, step, D2H u (and flags if non-NULL) */
 int vofx_step_host ( vofx_ctx *ctx, const vofx_step_params *params, double *u, uint8_t *flags );
+/* bytes the last vofx_step_host call moved across PCIe: the whole colour function host->device; device->host only the
+ * (cell, new value) pairs of the cells the update touched (mixed cells and their face neighbours) plus the loop state */
+int vofx_host_transfer_bytes ( const vofx_ctx *ctx, int64_t *h2d_bytes, int64_t *d2h_bytes );
 
 /* context-resident colour function (what a drop-in for Algorithm::operator() uses, algorithm.hh:54-103): upload the
  * host colour function once, run loop passes on the device mirror, download when the data writer wants it */
