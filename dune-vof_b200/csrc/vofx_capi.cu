@@ -253,7 +253,14 @@ namespace
       if( g.dim == 2 )
         launch::swartz2( ctx->numSMs * 16, ctx->stream, g, u, flags, ctx->mixedList, ctx->state, ctx->capacity, hs, maxIterations );
       else
-        launch::swartz3( ctx->numSMs * 16, ctx->stream, g, u, flags, ctx->mixedList, ctx->state, ctx->capacity, hs, maxIterations );
+      {
+        const char *env = std::getenv( "VOFX_SWARTZ_LANES" );
+        const int lanes = ( env && std::atoi( env ) == 8 ) ? 8 : 4;   // measured at 256^3: 38.6 ms (4 lanes) vs 45.4 ms (8), serial kernel 261 ms
+        if( env && std::atoi( env ) == 1 )
+          launch::swartz3( ctx->numSMs * 16, ctx->stream, g, u, flags, ctx->mixedList, ctx->state, ctx->capacity, hs, maxIterations );
+        else
+          launch::swartz_coop3( lanes, ctx->numSMs * 16, ctx->stream, g, u, flags, ctx->mixedList, ctx->state, ctx->capacity, hs, maxIterations, ctx->sweepTable );
+      }
       rc = checkLaunch( ctx, "k_swartz" );
     }
     else if( kind != VOFX_RECON_YOUNGS )

@@ -1000,3 +1000,263 @@ namespace vofx
 
   } // namespace coop
 } // namespace vofx
+
+// ====================================================================================================================
+// R3 in 3D for a group of L lanes: ModifiedSwartzReconstruction::applyLocal, reconstruction/modifiedswartz.hh:167-243.
+// Per iteration the cell and each of its mixed vertex neighbours is located with the cell's OLD normal
+// (locate_coop: brackets by all lanes), then the root searches, the interface polygons and their centroids
+// (3d/intersect.hh:274-355, 3d/face.hh:69-90) are taken by different lanes for different neighbours, and the
+// n(n-1) cross-product terms of the new normal are evaluated row by row and summed in the reference's order.
+// ====================================================================================================================
+namespace vofx
+{
+  namespace coop
+  {
+
+    constexpr int kMaxSwartzNb = 26;
+
+    template< int L >
+    struct SwartzScratch
+    {
+      union
+      {
+        LocateScratch loc;                 // while cells are being located
+        double row[ kMaxSwartzNb ][ 3 ];   // afterwards: normalised cross products of one row a
+      };
+      RootTask root[ L ];                  // one batch of L located cells
+      double dist[ L ];
+      double cen[ kMaxSwartzNb + 1 ][ 3 ]; // interface centroids: entry 0 the cell itself, 1.. its neighbours
+      double nsum[ 3 ];
+      double bcast;
+      unsigned char state[ 8 ];            // per batch entry: 0 plane constant known, 1 root pending, 2 serial walk needed
+      unsigned char nbOff[ kMaxSwartzNb ]; // packed offsets ( dx+1 ) | ( dy+1 ) << 2 | ( dz+1 ) << 4 of the mixed neighbours
+      unsigned char nbSlot[ 32 ];          // per stencil slot: 1 if it is a mixed neighbour
+      unsigned char rowValid[ kMaxSwartzNb ];
+      unsigned char pad[ 4 ];
+    };
+
+    // interface( cell, ( normal, dist ) ).centroid(): serial, one lane per located cell
+    VOFX_NOINLINE static void interface_centroid_serial ( const double *lo, const double *h, const double *normal, double dist, double *centroid )
+    {
+      Hex cell;
+      make_cell( lo, h, cell );
+      const Hs3 H = { { normal[ 0 ], normal[ 1 ], normal[ 2 ] }, dist };
+      Face3 f;
+      plane_cut( cell, H, f );
+      face_centroid( f, centroid );
+    }
+
+    VOFX_NOINLINE static double locate_serial ( const double *lo, const double *h, const double *normal, double fraction )
+    {
+      Hex cell;
+      make_cell( lo, h, cell );
+      return locate( cell, normal, fraction );
+    }
+
+    // out-of-line instances: the Swartz routine calls these from several places, and its instruction-cache footprint
+    // decides its speed (inlined everywhere the kernel was 96 k instructions and stalled 28 of 33 cycles on fetch)
+    template< int L >
+    VOFX_NOINLINE static bool locate_coop_call ( const Group &G, LocateScratch &S, const SweepTable &T, const double *lo, const double *h,
+                                                 const double *innerNormal, double fraction, double *dist, RootTask *root )
+    {
+      return locate_coop< L >( G, S, T, lo, h, innerNormal, fraction, *dist, root );
+    }
+
+    VOFX_NOINLINE static double root_of ( const RootTask &r ) { return r.base + brent( r.V, 0.0, r.h, 1e-14 ); }
+
+    // rec: in = the Young's reconstruction of the cell, out = the Swartz one (4 doubles)
+    template< int L >
+    VOFX_HD inline void swartz_cell_coop ( const Group &G, SwartzScratch< L > &S, const SweepTable &T, const Grid &g, const double *u,
+                                           const unsigned char *flags, const int *ijk, int maxIterations, double *rec )
+    {
+      const double colorEn = u[ cell_index( g, ijk ) ];
+
+      // mixed vertex neighbours in ascending cell index (stencil slot order)
+      VOFX_LANES( G, L, lane )
+      {
+        for( int s = lane; s < 26; s += L )
+        {
+          const int m = ( s < 13 ) ? s : s + 1;
+          const int nb[ 3 ] = { ijk[ 0 ] + ( m % 3 ) - 1, ijk[ 1 ] + ( ( m / 3 ) % 3 ) - 1, ijk[ 2 ] + ( m / 9 ) - 1 };
+          S.nbSlot[ s ] = ( cell_exists( g, nb ) && is_mixed( flags[ cell_index( g, nb ) ] ) ) ? 1 : 0;
+        }
+      }
+      int nNb = 0;
+      VOFX_LANES( G, L, lane )
+      {
+        if( lane == 0 )
+        {
+          int n = 0;
+          for( int s = 0; s < 26; ++s )
+            if( S.nbSlot[ s ] )
+            {
+              const int m = ( s < 13 ) ? s : s + 1;
+              S.nbOff[ n++ ] = (unsigned char) ( ( m % 3 ) | ( ( ( m / 3 ) % 3 ) << 2 ) | ( ( m / 9 ) << 4 ) );
+            }
+          S.bcast = (double) n;
+        }
+      }
+      nNb = (int) S.bcast;
+
+      double normal[ 3 ] = { rec[ 0 ], rec[ 1 ], rec[ 2 ] };
+      int iterations = 0;
+      double residuum = 0.0;
+      do
+      {
+        const double oldNormal[ 3 ] = { normal[ 0 ], normal[ 1 ], normal[ 2 ] };
+
+        // interface centroids of the cell (entry 0) and of its mixed neighbours, all with the old normal, in batches of L
+        for( int first = 0; first < nNb + 1; first += L )
+        {
+          const int batch = ( nNb + 1 - first < L ) ? nNb + 1 - first : L;
+          for( int j = 0; j < batch; ++j )
+          {
+            const int a = first + j;
+            int cell[ 3 ] = { ijk[ 0 ], ijk[ 1 ], ijk[ 2 ] };
+            if( a > 0 )
+            {
+              const int off = S.nbOff[ a - 1 ];
+              cell[ 0 ] += ( off & 3 ) - 1;
+              cell[ 1 ] += ( ( off >> 2 ) & 3 ) - 1;
+              cell[ 2 ] += ( ( off >> 4 ) & 3 ) - 1;
+            }
+            const double lo[ 3 ] = { cell_lower( g, 0, cell[ 0 ] ), cell_lower( g, 1, cell[ 1 ] ), cell_lower( g, 2, cell[ 2 ] ) };
+            const double color = ( a == 0 ) ? colorEn : u[ cell_index( g, cell ) ];
+            RootTask root;
+            root.pending = 0;
+            double dist = 0.0;
+            const bool ok = locate_coop_call< L >( G, S.loc, T, lo, g.h, oldNormal, color, &dist, &root );
+            VOFX_LANES( G, L, lane )
+            {
+              if( lane == 0 )
+              {
+                S.state[ j ] = (unsigned char) ( !ok ? 2 : ( root.pending ? 1 : 0 ) );
+                S.dist[ j ] = dist;
+                S.root[ j ] = root;
+              }
+            }
+          }
+          // lane j finishes located cell j: root search (or serial walk), interface polygon, centroid
+          VOFX_LANES( G, L, lane )
+          {
+            if( lane < batch )
+            {
+              const int a = first + lane;
+              int cell[ 3 ] = { ijk[ 0 ], ijk[ 1 ], ijk[ 2 ] };
+              if( a > 0 )
+              {
+                const int off = S.nbOff[ a - 1 ];
+                cell[ 0 ] += ( off & 3 ) - 1;
+                cell[ 1 ] += ( ( off >> 2 ) & 3 ) - 1;
+                cell[ 2 ] += ( ( off >> 4 ) & 3 ) - 1;
+              }
+              const double lo[ 3 ] = { cell_lower( g, 0, cell[ 0 ] ), cell_lower( g, 1, cell[ 1 ] ), cell_lower( g, 2, cell[ 2 ] ) };
+              double dist = S.dist[ lane ];
+              if( S.state[ lane ] == 1 )
+                dist = root_of( S.root[ lane ] );
+              else if( S.state[ lane ] == 2 )
+                dist = locate_serial( lo, g.h, oldNormal, ( a == 0 ) ? colorEn : u[ cell_index( g, cell ) ] );
+              double c[ 3 ];
+              interface_centroid_serial( lo, g.h, oldNormal, dist, c );
+              for( int k = 0; k < 3; ++k )
+                S.cen[ a ][ k ] = c[ k ];
+            }
+          }
+        }
+
+        // normal = sum over ordered pairs ( a, b ), a != b, of the normalised cross products, modifiedswartz.hh:196-229
+        VOFX_LANES( G, L, lane )
+        {
+          if( lane < 3 )
+            S.nsum[ lane ] = 0.0;
+        }
+        for( int a = 0; a < nNb; ++a )
+        {
+          VOFX_LANES( G, L, lane )
+          {
+            for( int b = lane; b < nNb; b += L )
+            {
+              bool valid = false;
+              double cn[ 3 ] = { 0.0, 0.0, 0.0 };
+              if( b != a )
+              {
+                double d1[ 3 ], d2[ 3 ];
+                for( int k = 0; k < 3; ++k )
+                {
+                  d1[ k ] = S.cen[ a + 1 ][ k ] - S.cen[ 0 ][ k ];
+                  d2[ k ] = S.cen[ b + 1 ][ k ] - S.cen[ 0 ][ k ];
+                }
+                cross3( d1, d2, cn );
+                if( !( norm3( cn ) < 1e-12 ) )
+                {
+                  valid = true;
+                  if( dot3( cn, oldNormal ) < 0 )
+                    for( int k = 0; k < 3; ++k )
+                      cn[ k ] *= -1.0;
+                  const double nrm = norm3( cn );
+                  for( int k = 0; k < 3; ++k )
+                    cn[ k ] = vdiv( cn[ k ], nrm );
+                }
+              }
+              S.rowValid[ b ] = valid ? 1 : 0;
+              for( int k = 0; k < 3; ++k )
+                S.row[ b ][ k ] = cn[ k ];
+            }
+          }
+          VOFX_LANES( G, L, lane )
+          {
+            if( lane < 3 )
+            {
+              double acc = S.nsum[ lane ];
+              for( int b = 0; b < nNb; ++b )
+                if( S.rowValid[ b ] )
+                  acc += 1.0 * S.row[ b ][ lane ];
+              S.nsum[ lane ] = acc;
+            }
+          }
+        }
+        normal[ 0 ] = S.nsum[ 0 ];
+        normal[ 1 ] = S.nsum[ 1 ];
+        normal[ 2 ] = S.nsum[ 2 ];
+
+        double n2 = 0.0;
+        for( int k = 0; k < 3; ++k )
+          n2 += normal[ k ] * normal[ k ];
+        const double nrm = sqrt( n2 );
+        if( nrm < 0.5 )
+          break;   // "return": keep the last reconstruction, modifiedswartz.hh:231-232
+        for( int k = 0; k < 3; ++k )
+          normal[ k ] = vdiv( normal[ k ], nrm );
+
+        const double lo[ 3 ] = { cell_lower( g, 0, ijk[ 0 ] ), cell_lower( g, 1, ijk[ 1 ] ), cell_lower( g, 2, ijk[ 2 ] ) };
+        double dist = 0.0;
+        RootTask finalRoot;
+        finalRoot.pending = 0;
+        const bool ok = locate_coop_call< L >( G, S.loc, T, lo, g.h, normal, colorEn, &dist, &finalRoot );
+        if( ok && finalRoot.pending )
+          dist = root_of( finalRoot );
+        if( !ok )
+        {
+          VOFX_LANES( G, L, lane )
+          {
+            if( lane == 0 )
+              S.bcast = locate_serial( lo, g.h, normal, colorEn );
+          }
+          dist = S.bcast;
+        }
+        G.sync();     // the locate scratch is reused by the next iteration's first locate
+        for( int k = 0; k < 3; ++k )
+          rec[ k ] = normal[ k ];
+        rec[ 3 ] = dist;
+
+        double dotp = 0.0;
+        for( int k = 0; k < 3; ++k )
+          dotp += normal[ k ] * oldNormal[ k ];
+        residuum = 1.0 - dotp;
+        ++iterations;
+      }
+      while( residuum > 1e-12 && iterations < maxIterations );
+    }
+
+  } // namespace coop
+} // namespace vofx

@@ -240,3 +240,36 @@ extern "C" int hg_locate_coop ( int lanes, const double *lo, const double *h, co
                              : coop::locate_coop< 8 >( G, S, T, lo, h, normal, fraction, *dist );
   return ok ? 0 : 2;
 }
+
+// ModifiedSwartz on one cell by the cooperative path (lanes emulated); rec: in Young's, out Swartz
+extern "C" int hg_swartz_coop ( int lanes, const int *n, const double *u, const unsigned char *flags, const int *ijk, int maxIterations, double *rec )
+{
+  static coop::SweepTable T;
+  static bool have = false;
+  if( !have )
+  {
+    coop::make_sweep_table( T );
+    have = true;
+  }
+  Grid g;
+  g.dim = 3;
+  g.cells = 1;
+  for( int d = 0; d < 3; ++d )
+  {
+    g.ns[ d ] = g.ng[ d ] = n[ d ];
+    g.g0[ d ] = 0;
+    g.origin[ d ] = 0.0;
+    g.h[ d ] = 1.0 / n[ d ];
+    g.cells *= n[ d ];
+  }
+  g.own0 = g.list0 = 0;
+  g.own1 = g.list1 = n[ 2 ];
+  static coop::SwartzScratch< 4 > S4;
+  static coop::SwartzScratch< 8 > S8;
+  coop::Group G = { 0, 0u };
+  if( lanes == 4 )
+    coop::swartz_cell_coop< 4 >( G, S4, T, g, u, flags, ijk, maxIterations, rec );
+  else
+    coop::swartz_cell_coop< 8 >( G, S8, T, g, u, flags, ijk, maxIterations, rec );
+  return 0;
+}

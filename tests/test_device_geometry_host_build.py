@@ -198,3 +198,26 @@ def test_cooperative_youngs_bit_exact(hg, lanes):
             assert same_bits(out, hs[c]), (n, problem, c, st, out, hs[c])
         print(n, problem, "cooperative Young's status counts:", status)
         og.close()
+
+
+@pytest.mark.parametrize("lanes", [8, 4])
+def test_cooperative_swartz_bit_exact(hg, lanes):
+    """ModifiedSwartz (3D) of every mixed cell, cooperative path (lanes emulated) vs the oracle"""
+    for n, problem in (((12, 12, 12), O.PROB_LEVEQUE), ((16, 10, 12), O.PROB_SFLOW)):
+        og = O.OracleGrid(n)
+        u = og.init(problem)
+        u, *_ = og.run(O.RECON_YOUNGS, problem, 1e-6, 0.5, 2, u)
+        flags = og.flag(u, 1e-6)
+        hy = og.reconstruct(O.RECON_YOUNGS, u, flags).reshape(-1, 4)
+        hs = og.reconstruct(O.RECON_SWARTZ, u, flags).reshape(-1, 4)
+        nn = np.asarray(n, dtype=np.int32)
+        uu = _v(u)
+        ff = np.ascontiguousarray(flags, dtype=np.uint8)
+        cells = np.flatnonzero((flags == 1) | (flags == 2))
+        for c in cells:
+            ijk = np.asarray([c % n[0], (c // n[0]) % n[1], c // (n[0] * n[1])], dtype=np.int32)
+            rec = hy[c].copy()
+            hg.hg_swartz_coop(int(lanes), C.c_void_p(nn.ctypes.data), _d(uu), C.c_void_p(ff.ctypes.data), C.c_void_p(ijk.ctypes.data), 10, _d(rec))
+            assert same_bits(rec, hs[c]), (n, problem, c, rec, hs[c])
+        print(n, problem, "cooperative Swartz cells checked:", len(cells))
+        og.close()
