@@ -10,6 +10,12 @@ namespace vofx
     { k_youngs< 2 ><<< blocks, 128, 0, s >>>( g, u, mixedList, state, capacity, hs ); }
     void hf2 ( int blocks, cudaStream_t s, Grid g, const double *u, const int *mixedList, const StepState *state, int capacity, double *hs )
     { k_hf< 2 ><<< blocks, 128, 0, s >>>( g, u, mixedList, state, capacity, hs ); }
+    void hf_fused2 ( int blocks, cudaStream_t s, Grid g, const double *u, const int *mixedList, const StepState *state, int capacity, double *hs )
+    { k_hf_fused< 2 ><<< blocks, 128, 0, s >>>( g, u, mixedList, state, capacity, hs ); }
+    void clear_listed ( int blocks, cudaStream_t s, const int *list, const int *count, double *target )
+    { k_clear_listed<<< blocks, 256, 0, s >>>( list, count, target ); }
+    void copy_list ( int blocks, cudaStream_t s, const int *list, const StepState *state, int capacity, int *out, int *outCount )
+    { k_copy_list<<< blocks, 256, 0, s >>>( list, state, capacity, out, outCount ); }
     void swartz2 ( int blocks, cudaStream_t s, Grid g, const double *u, const unsigned char *flags, const int *mixedList, const StepState *state,
                    int capacity, double *hs, int maxIterations )
     { k_swartz< 2 ><<< blocks, 64, 0, s >>>( g, u, flags, mixedList, state, capacity, hs, maxIterations ); }

@@ -54,6 +54,9 @@ struct vofx_ctx
   int taskCapacity = 0;
   void *sweepTable = nullptr;       // coop::SweepTable
   int *serialCells = nullptr;       // mixed cells whose plane constant is left to the serial walk
+  // curvature entries written by the previous step of the time loop (sparse clear instead of a dense memset)
+  int *curvList = nullptr, *curvListCount = nullptr;
+  const double *curvListOwner = nullptr;
   // sparse write-back of the host-buffer step: (cell, new value) of every cell the update touched
   int *changedIdx = nullptr;
   double *changedVal = nullptr;
@@ -217,6 +220,13 @@ namespace
   {
     const Grid &g = ctx->grid;
     const int blocks = ctx->numSMs * 8;
+    if( g.dim == 2 && kind == VOFX_RECON_HF )
+    {
+      // Young's normal + height-function normal + one plane-constant solve per cell, in one pass
+      profBegin( ctx );
+      launch::hf_fused2( blocks, ctx->stream, g, u, ctx->mixedList, ctx->state, ctx->capacity, hs );
+      return checkLaunch( ctx, "k_hf_fused" );
+    }
     profBegin( ctx );
     if( g.dim == 2 )
       launch::youngs2( blocks, ctx->stream, g, u, ctx->mixedList, ctx->state, ctx->capacity, hs );
@@ -306,12 +316,20 @@ namespace
     return checkLaunch( ctx, "k_update" );
   }
 
-  int launchCurvature ( vofx_ctx *ctx, const double *u, const double *hs, const unsigned char *flags, double *kappa, unsigned char *valid )
+  int launchCurvature ( vofx_ctx *ctx, const double *u, const double *hs, const unsigned char *flags, double *kappa, unsigned char *valid,
+                        bool sparseClear = false )
   {
     const Grid &g = ctx->grid;
     const int blocks = ctx->numSMs * 8;
-    // curvature[ entity ] = 0 and satisfiesConstraint_[ entity ] = 0 for all cells, cartesianheightfunctioncurvature.hh:57-60
-    VOFX_CUDA( cudaMemsetAsync( kappa, 0, sizeof( double ) * (size_t) g.cells, ctx->stream ) );
+    // curvature[ entity ] = 0 and satisfiesConstraint_[ entity ] = 0 for all cells, cartesianheightfunctioncurvature.hh:57-60.
+    // Inside the time loop the array is the one written by the previous step: only those entries are non-zero.
+    if( sparseClear && ctx->curvList && ctx->curvListOwner == kappa )
+    {
+      launch::clear_listed( ctx->numSMs * 2, ctx->stream, ctx->curvList, ctx->curvListCount, kappa );
+      ctx->launches++;
+    }
+    else
+      VOFX_CUDA( cudaMemsetAsync( kappa, 0, sizeof( double ) * (size_t) g.cells, ctx->stream ) );
     if( valid )
       VOFX_CUDA( cudaMemsetAsync( valid, 0, (size_t) g.cells, ctx->stream ) );
     profBegin( ctx );
@@ -321,7 +339,24 @@ namespace
       return rc;
     profBegin( ctx );
     launch::curvature_average( g.dim, blocks, ctx->stream, g, flags, ctx->mixedList, ctx->slot, ctx->state, ctx->capacity, ctx->curv1, ctx->ok1, kappa, valid );
-    return checkLaunch( ctx, "k_curvature_average" );
+    rc = checkLaunch( ctx, "k_curvature_average" );
+    if( rc || !sparseClear )
+    {
+      ctx->curvListOwner = nullptr;
+      return rc;
+    }
+    // remember which entries are non-zero now
+    if( !ctx->curvList )
+    {
+      rc = ensureDevice( ctx->curvList, (size_t) ctx->capacity );
+      rc = rc ? rc : ensureDevice( ctx->curvListCount, (size_t) 1 );
+      if( rc )
+        return rc;
+    }
+    launch::copy_list( ctx->numSMs * 2, ctx->stream, ctx->mixedList, ctx->state, ctx->capacity, ctx->curvList, ctx->curvListCount );
+    ctx->launches++;
+    ctx->curvListOwner = kappa;
+    return VOFX_OK;
   }
 
   int checkOverflow ( vofx_ctx *ctx, const StepState &s )
@@ -536,6 +571,8 @@ extern "C"
     cudaFree( ctx->sweepTable );
     cudaFree( ctx->serialCells );
     cudaFree( ctx->rootTasks );
+    cudaFree( ctx->curvList );
+    cudaFree( ctx->curvListCount );
     cudaFree( ctx->changedIdx );
     cudaFree( ctx->changedVal );
     cudaFree( ctx->state );
@@ -890,7 +927,7 @@ extern "C"
     rc = rc ? rc : launchFlag( ctx, u, p->eps, flags, true );
     rc = rc ? rc : launchReconstruct( ctx, p->reconstruction, u, flags, halfspaces, p->max_iterations );
     if( !rc && p->with_curvature )
-      rc = launchCurvature( ctx, u, halfspaces, flags, kappa, nullptr );
+      rc = launchCurvature( ctx, u, halfspaces, flags, kappa, nullptr, true );
     rc = rc ? rc : launchFlux( ctx, halfspaces, flags, nullptr, nullptr );
     rc = rc ? rc : launchUpdate( ctx, flags, u, true );
     return rc;

@@ -778,6 +778,54 @@ namespace vofx
     }
   }
 
+  // HeightFunctionReconstruction in one kernel (2D): the reference first runs ModifiedYoungs on every mixed cell
+  // (heightfunction.hh:73) and then overwrites each reconstruction (:122); of the Young's result only the NORMAL of the
+  // cell itself is read (getOrientation, :104), so its plane-constant solve is dead work and the two band passes fuse.
+  template< int DIM >
+  __global__ void __launch_bounds__( 128 ) k_hf_fused ( Grid g, const double *__restrict__ u, const int *__restrict__ mixedList,
+                                                         const StepState *state, int capacity, double *__restrict__ hs )
+  {
+    const int count = mixed_count( state, capacity );
+    for( int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < count; idx += gridDim.x * blockDim.x )
+    {
+      const long long c = mixedList[ idx ];
+      int ijk[ 3 ];
+      cell_ijk( g, c, ijk );
+      const double colorEn = u[ c ];
+      double youngs[ 3 ];
+      if( !youngs_normal< DIM >( g, u, ijk, colorEn, youngs ) )
+        youngs[ 0 ] = youngs[ 1 ] = youngs[ 2 ] = 0.0;     // the zero half-space, modifiedyoungs.hh:128-129
+      int dir, sign;
+      hf_orientation< DIM >( youngs, dir, sign );
+      double heights[ 9 ], newNormal[ 3 ];
+      hf_heights< DIM >( g, u, ijk, dir, sign, 3, heights );
+      hf_normal< DIM >( heights, dir, sign, newNormal );
+      const double dist = locate_cell< DIM >( g, ijk, newNormal, colorEn );
+      double *rec = hs + c * ( DIM + 1 );
+#pragma unroll
+      for( int k = 0; k < DIM; ++k )
+        rec[ k ] = newNormal[ k ];
+      rec[ DIM ] = dist;
+    }
+  }
+
+  // curvature[ c ] = 0 for the cells that received a value in the previous step (instead of a dense clear)
+  static __global__ void __launch_bounds__( 256 ) k_clear_listed ( const int *__restrict__ list, const int *__restrict__ count, double *__restrict__ target )
+  {
+    const int n = *count;
+    for( int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x )
+      target[ list[ i ] ] = 0.0;
+  }
+
+  static __global__ void __launch_bounds__( 256 ) k_copy_list ( const int *__restrict__ list, const StepState *state, int capacity, int *__restrict__ out, int *__restrict__ outCount )
+  {
+    const int n = mixed_count( state, capacity );
+    for( int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x )
+      out[ i ] = list[ i ];
+    if( blockIdx.x == 0 && threadIdx.x == 0 )
+      *outCount = n;
+  }
+
   // ------------------------------------------------------------------------------------------------------------
   // R3: modified Swartz, reconstruction/modifiedswartz.hh:102-243.  One thread per mixed cell; the neighbours'
   // interface centroids depend only on (neighbour, oldNormal) and are computed once per iteration.

@@ -32,6 +32,9 @@ namespace vofx
     // k_band2d.cu
     void youngs2 ( int blocks, cudaStream_t s, Grid g, const double *u, const int *mixedList, const StepState *state, int capacity, double *hs );
     void hf2 ( int blocks, cudaStream_t s, Grid g, const double *u, const int *mixedList, const StepState *state, int capacity, double *hs );
+    void hf_fused2 ( int blocks, cudaStream_t s, Grid g, const double *u, const int *mixedList, const StepState *state, int capacity, double *hs );
+    void clear_listed ( int blocks, cudaStream_t s, const int *list, const int *count, double *target );
+    void copy_list ( int blocks, cudaStream_t s, const int *list, const StepState *state, int capacity, int *out, int *outCount );
     void swartz2 ( int blocks, cudaStream_t s, Grid g, const double *u, const unsigned char *flags, const int *mixedList, const StepState *state,
                    int capacity, double *hs, int maxIterations );
     void flux2 ( int blocks, cudaStream_t s, Grid g, const Velocity *velocity, const double *hs, const unsigned char *flags, const int *mixedList,

@@ -179,3 +179,33 @@ def test_mass_and_bounds_512_slab(vofx):
     assert int(alg.flags.max()) <= 3
     assert float(uh.min()) > -1e-2 and float(uh.max()) < 1 + 1e-2
     grid.close()
+
+
+@pytest.mark.parametrize("case", ["2d_zalesak_64", "3d_sphere_16"])
+def test_curvature_inside_time_loop(vofx, case):
+    """The time loop with curvature (fused HF kernel in 2D, sparse clear of the previous step's curvature entries)
+    against the operator-level calls on the same state: bit-identical, and zero wherever no mixed cell is."""
+    import torch
+    g = golden(f"operators_{case}.npz")
+    n = tuple(int(x) for x in g["n"])
+    problem, eps, cfl = int(g["problem"]), float(g["eps"]), float(g["cfl"])
+    grid = vofx.CartesianGrid(n)
+    grid.set_velocity_builtin(problem)
+    u0 = torch.tensor(g["u0"], device=grid.device)
+    passes = 5
+    alg = vofx.Algorithm(grid, cfl, eps, reconstruction_kind=vofx.RECON_HF, with_curvature=True)
+    ua = u0.clone()
+    alg.run_passes(ua, passes)
+    # state before the last pass, then the operators one by one
+    ref = vofx.Algorithm(grid, cfl, eps, reconstruction_kind=vofx.RECON_HF)
+    ub = u0.clone()
+    ref.run_passes(ub, passes - 1)
+    flags, recs, kappa = grid.empty("flags"), grid.empty("reconstructions"), grid.empty("curvature")
+    vofx.FlagOperator(grid, eps)(ub, flags)
+    vofx.HeightFunctionReconstruction(grid)(ub, recs, flags)
+    vofx.CartesianHeightFunctionCurvature(grid)(ub, recs, flags, kappa)
+    assert same_bits(alg.curvature.cpu().numpy(), kappa.cpu().numpy())
+    mixed = (flags == 1) | (flags == 2)
+    assert float(alg.curvature[~mixed].abs().max()) == 0.0
+    assert same_bits(alg.reconstructions.cpu().numpy()[mixed.cpu().numpy()], recs.cpu().numpy()[mixed.cpu().numpy()])
+    grid.close()
