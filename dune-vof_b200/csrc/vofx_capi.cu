@@ -54,6 +54,12 @@ struct vofx_ctx
   int taskCapacity = 0;
   void *sweepTable = nullptr;       // coop::SweepTable
   int *serialCells = nullptr;       // mixed cells whose plane constant is left to the serial walk
+  // interface extraction (vofx_interface): grow-only scratch
+  int *ifBlockSums = nullptr, *ifCells = nullptr, *ifNverts = nullptr, *ifOffsets = nullptr;
+  long long *ifTotal = nullptr;
+  double *ifVerts = nullptr, *ifCsr = nullptr;
+  size_t ifBlockCap = 0, ifCellCap = 0, ifNvertsCap = 0, ifOffsetsCap = 0, ifVertsCap = 0, ifCsrCap = 0;
+  long long ifMixed = 0, ifVertices = 0;
   // curvature entries written by the previous step of the time loop (sparse clear instead of a dense memset)
   int *curvList = nullptr, *curvListCount = nullptr;
   const double *curvListOwner = nullptr;
@@ -163,6 +169,20 @@ namespace
     if( p )
       return VOFX_OK;
     VOFX_CUDA( cudaMalloc( (void **) &p, count * sizeof( T ) ) );
+    return VOFX_OK;
+  }
+
+  template< class T >
+  int growDevice ( T *&p, size_t &cap, size_t count )
+  {
+    if( count <= cap )
+      return VOFX_OK;
+    cudaFree( p );
+    p = nullptr;
+    cap = 0;
+    const size_t want = count + count / 4 + 1024;
+    VOFX_CUDA( cudaMalloc( (void **) &p, want * sizeof( T ) ) );
+    cap = want;
     return VOFX_OK;
   }
 
@@ -571,6 +591,13 @@ extern "C"
     cudaFree( ctx->sweepTable );
     cudaFree( ctx->serialCells );
     cudaFree( ctx->rootTasks );
+    cudaFree( ctx->ifBlockSums );
+    cudaFree( ctx->ifCells );
+    cudaFree( ctx->ifNverts );
+    cudaFree( ctx->ifOffsets );
+    cudaFree( ctx->ifTotal );
+    cudaFree( ctx->ifVerts );
+    cudaFree( ctx->ifCsr );
     cudaFree( ctx->curvList );
     cudaFree( ctx->curvListCount );
     cudaFree( ctx->changedIdx );
@@ -1167,6 +1194,95 @@ extern "C"
     if( !rc && p->with_curvature )
       rc = ensureDevice( ctx->dKappa, (size_t) ctx->grid.cells );
     return rc ? rc : vofx_step( ctx, p, ctx->dU, ctx->dFlags, ctx->dHs, ctx->dKappa );
+  }
+
+  // ---- interface extraction ------------------------------------------------------------------------------------------------
+
+  int vofx_interface ( vofx_ctx *ctx, const double *halfspaces, const uint8_t *flags, int64_t *n_mixed, int64_t *n_vertices )
+  {
+    if( !ctx || !halfspaces || !flags || !n_mixed || !n_vertices )
+      return fail( VOFX_ERR_ARGUMENT, "null argument" );
+    int rc = setDevice( ctx );
+    if( rc )
+      return rc;
+    const Grid &g = ctx->grid;
+    const int dim = g.dim;
+    const int stride = ( dim == 2 ) ? 2 : 12;
+    rc = growDevice( ctx->ifBlockSums, ctx->ifBlockCap, (size_t) launch::scan_blocks( g.cells ) );
+    rc = rc ? rc : ensureDevice( ctx->ifTotal, (size_t) 2 );
+    if( rc )
+      return rc;
+    // ordered list of the owned mixed cells (MixedCellMapper numbering)
+    launch::scan( dim, ctx->stream, g, g.cells, flags, nullptr, ctx->ifBlockSums, ctx->ifTotal, nullptr, 0 );
+    long long total = 0;
+    VOFX_CUDA( cudaMemcpyAsync( &total, ctx->ifTotal, sizeof( total ), cudaMemcpyDeviceToHost, ctx->stream ) );
+    VOFX_CUDA( cudaStreamSynchronize( ctx->stream ) );
+    ctx->launches += 2;
+    ctx->ifMixed = total;
+    ctx->ifVertices = 0;
+    *n_mixed = total;
+    *n_vertices = 0;
+    if( total == 0 )
+      return VOFX_OK;
+    if( total > ctx->capacity )
+      return fail( VOFX_ERR_STATE, "more mixed cells than the context's capacity" );
+    rc = growDevice( ctx->ifCells, ctx->ifCellCap, (size_t) total );
+    rc = rc ? rc : growDevice( ctx->ifNverts, ctx->ifNvertsCap, (size_t) total );
+    rc = rc ? rc : growDevice( ctx->ifOffsets, ctx->ifOffsetsCap, (size_t) total );
+    rc = rc ? rc : growDevice( ctx->ifVerts, ctx->ifVertsCap, (size_t) total * stride * dim );
+    if( rc )
+      return rc;
+    launch::scan( dim, ctx->stream, g, g.cells, flags, nullptr, ctx->ifBlockSums, ctx->ifTotal, ctx->ifCells, 1 );
+    const int blocks = gridBlocks( ctx, total, 128, 8 );
+    launch::interface_cut( dim, blocks, ctx->stream, g, halfspaces, ctx->ifCells, total, ctx->ifNverts, ctx->ifVerts );
+    // CSR offsets = exclusive scan of the vertex counts
+    launch::scan( dim, ctx->stream, g, total, nullptr, ctx->ifNverts, ctx->ifBlockSums, ctx->ifTotal + 1, nullptr, 0 );
+    long long nv = 0;
+    VOFX_CUDA( cudaMemcpyAsync( &nv, ctx->ifTotal + 1, sizeof( nv ), cudaMemcpyDeviceToHost, ctx->stream ) );
+    VOFX_CUDA( cudaStreamSynchronize( ctx->stream ) );
+    launch::scan( dim, ctx->stream, g, total, nullptr, ctx->ifNverts, ctx->ifBlockSums, ctx->ifTotal + 1, ctx->ifOffsets, 1 );
+    rc = growDevice( ctx->ifCsr, ctx->ifCsrCap, (size_t) ( nv > 0 ? nv : 1 ) * dim );
+    if( rc )
+      return rc;
+    launch::interface_gather( dim, blocks, ctx->stream, total, ctx->ifNverts, ctx->ifOffsets, ctx->ifVerts, ctx->ifCsr );
+    ctx->launches += 6;
+    VOFX_CUDA( cudaGetLastError() );
+    ctx->ifVertices = nv;
+    *n_vertices = nv;
+    return VOFX_OK;
+  }
+
+  int vofx_interface_host ( vofx_ctx *ctx, const double *halfspaces, const uint8_t *flags, int64_t *n_mixed, int64_t *n_vertices )
+  {
+    if( !ctx || !halfspaces || !flags || !n_mixed || !n_vertices )
+      return fail( VOFX_ERR_ARGUMENT, "null argument" );
+    const size_t N = (size_t) ctx->grid.cells;
+    int rc = ensureMirrors( ctx );
+    rc = rc ? rc : stageIn( ctx, ctx->dHs, halfspaces, N * ( ctx->desc.dim + 1 ) * sizeof( double ) );
+    rc = rc ? rc : stageIn( ctx, ctx->dFlags, flags, N );
+    return rc ? rc : vofx_interface( ctx, ctx->dHs, ctx->dFlags, n_mixed, n_vertices );
+  }
+
+  int vofx_interface_fetch ( vofx_ctx *ctx, int32_t *cells, int64_t *offsets, double *vertices )
+  {
+    if( !ctx || !cells || !offsets || !vertices )
+      return fail( VOFX_ERR_ARGUMENT, "null argument" );
+    int rc = setDevice( ctx );
+    if( rc )
+      return rc;
+    const size_t n = (size_t) ctx->ifMixed;
+    offsets[ 0 ] = 0;
+    if( n == 0 )
+      return VOFX_OK;
+    std::vector< int > off32( n );
+    VOFX_CUDA( cudaMemcpyAsync( cells, ctx->ifCells, n * sizeof( int ), cudaMemcpyDeviceToHost, ctx->stream ) );
+    VOFX_CUDA( cudaMemcpyAsync( off32.data(), ctx->ifOffsets, n * sizeof( int ), cudaMemcpyDeviceToHost, ctx->stream ) );
+    VOFX_CUDA( cudaMemcpyAsync( vertices, ctx->ifCsr, (size_t) ctx->ifVertices * ctx->desc.dim * sizeof( double ), cudaMemcpyDeviceToHost, ctx->stream ) );
+    VOFX_CUDA( cudaStreamSynchronize( ctx->stream ) );
+    for( size_t i = 0; i < n; ++i )
+      offsets[ i ] = off32[ i ];
+    offsets[ n ] = ctx->ifVertices;
+    return VOFX_OK;
   }
 
   // ---- initial data -------------------------------------------------------------------------------------------------------

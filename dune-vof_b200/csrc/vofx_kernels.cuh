@@ -2079,6 +2079,181 @@ namespace vofx
   }
 
   // ------------------------------------------------------------------------------------------------------------
+  // interface extraction.  getInterfaceVertices (utility.hh:19-48) visits the mixed cells in
+  // ASCENDING cell index and appends interface( entity, reconstructions ) of each: a CSR ( offsets, vertices ), with
+  // MixedCellMapper::update's numbering (mixedcellmapper.hh:82-86).  The step's own mixed list is unordered (atomics),
+  // so the order comes from a deterministic exclusive scan of the mixed predicate.
+  // ------------------------------------------------------------------------------------------------------------
+
+  constexpr int kScanBlock = 1024;   // items per block of the scan kernels (256 threads x 4)
+
+  // a mixed cell this context owns (halo layers belong to the neighbouring slab)
+  template< int DIM >
+  __device__ __forceinline__ int owned_mixed ( const Grid &g, const unsigned char *__restrict__ flags, long long i )
+  {
+    if( !is_mixed( flags[ i ] ) )
+      return 0;
+    const long long layer = (long long) g.ns[ 0 ] * ( DIM == 3 ? g.ns[ 1 ] : 1 );
+    const int la = int( i / layer );
+    return ( la >= g.own0 && la < g.own1 ) ? 1 : 0;
+  }
+
+  // pass 1: per block, the number of selected items ( mode 0: is_mixed( flags[i] ) inside the listed layers; mode 1: counts[i] )
+  template< int DIM >
+  __global__ void __launch_bounds__( 256 ) k_scan_block_sums ( Grid g, long long n, const unsigned char *__restrict__ flags, const int *__restrict__ counts,
+                                                                int *__restrict__ blockSums )
+  {
+    __shared__ int warpSums[ 8 ];
+    const long long base = (long long) blockIdx.x * kScanBlock;
+    int mine = 0;
+    for( int k = 0; k < 4; ++k )
+    {
+      const long long i = base + threadIdx.x * 4 + k;
+      if( i < n )
+        mine += counts ? counts[ i ] : owned_mixed< DIM >( g, flags, i );
+    }
+    for( int o = 16; o > 0; o >>= 1 )
+      mine += __shfl_xor_sync( 0xffffffffu, mine, o );
+    if( ( threadIdx.x & 31 ) == 0 )
+      warpSums[ threadIdx.x >> 5 ] = mine;
+    __syncthreads();
+    if( threadIdx.x == 0 )
+    {
+      int s = 0;
+      for( int w = 0; w < 8; ++w )
+        s += warpSums[ w ];
+      blockSums[ blockIdx.x ] = s;
+    }
+  }
+
+  // pass 2: exclusive scan of the block sums by one block; total -> *total
+  static __global__ void __launch_bounds__( 1024 ) k_scan_block_offsets ( int nBlocks, int *__restrict__ blockSums, long long *__restrict__ total )
+  {
+    __shared__ long long partial[ 1024 ];
+    const int per = ( nBlocks + 1023 ) / 1024;
+    const int lo = threadIdx.x * per, hi = ( lo + per < nBlocks ) ? lo + per : nBlocks;
+    long long s = 0;
+    for( int i = lo; i < hi; ++i )
+      s += blockSums[ i ];
+    partial[ threadIdx.x ] = s;
+    __syncthreads();
+    if( threadIdx.x == 0 )
+    {
+      long long run = 0;
+      for( int t = 0; t < 1024; ++t )
+      {
+        const long long v = partial[ t ];
+        partial[ t ] = run;
+        run += v;
+      }
+      *total = run;
+    }
+    __syncthreads();
+    long long run = partial[ threadIdx.x ];
+    for( int i = lo; i < hi; ++i )
+    {
+      const int v = blockSums[ i ];
+      blockSums[ i ] = (int) run;
+      run += v;
+    }
+  }
+
+  // pass 3 (mode 0): ordered list of the mixed cells; (mode 1): exclusive offsets of counts
+  template< int DIM >
+  __global__ void __launch_bounds__( 256 ) k_scan_scatter ( Grid g, long long n, const unsigned char *__restrict__ flags, const int *__restrict__ counts,
+                                                             const int *__restrict__ blockOffsets, int *__restrict__ out )
+  {
+    __shared__ int warpSums[ 8 ];
+    const long long base = (long long) blockIdx.x * kScanBlock;
+    int v[ 4 ], mine = 0;
+    for( int k = 0; k < 4; ++k )
+    {
+      const long long i = base + threadIdx.x * 4 + k;
+      v[ k ] = ( i < n ) ? ( counts ? counts[ i ] : owned_mixed< DIM >( g, flags, i ) ) : 0;
+      mine += v[ k ];
+    }
+    int incl = mine;
+    const int lane = threadIdx.x & 31;
+    for( int o = 1; o < 32; o <<= 1 )
+    {
+      const int t = __shfl_up_sync( 0xffffffffu, incl, o );
+      if( lane >= o )
+        incl += t;
+    }
+    if( lane == 31 )
+      warpSums[ threadIdx.x >> 5 ] = incl;
+    __syncthreads();
+    int before = blockOffsets[ blockIdx.x ];
+    for( int w = 0; w < ( threadIdx.x >> 5 ); ++w )
+      before += warpSums[ w ];
+    int pos = before + incl - mine;
+    for( int k = 0; k < 4; ++k )
+    {
+      const long long i = base + threadIdx.x * 4 + k;
+      if( i >= n )
+        break;
+      if( counts )
+        out[ i ] = pos;                       // exclusive offset of item i
+      else if( v[ k ] )
+        out[ pos ] = (int) i;                 // the pos-th mixed cell
+      pos += v[ k ];
+    }
+  }
+
+  // interface polygon of the p-th mixed cell: vertex count and vertices into a fixed-stride scratch
+  template< int DIM >
+  __global__ void __launch_bounds__( 128 ) k_interface_cut ( Grid g, const double *__restrict__ hs, const int *__restrict__ cells, long long nMixed,
+                                                              int *__restrict__ nverts, double *__restrict__ verts )
+  {
+    constexpr int STRIDE = ( DIM == 2 ) ? 2 : 12;
+    for( long long p = blockIdx.x * (long long) blockDim.x + threadIdx.x; p < nMixed; p += (long long) gridDim.x * blockDim.x )
+    {
+      const long long c = cells[ p ];
+      int ijk[ 3 ];
+      cell_ijk( g, c, ijk );
+      const double *rec = hs + c * ( DIM + 1 );
+      double *out = verts + p * STRIDE * DIM;
+      if( DIM == 2 )
+      {
+        Poly2 poly;
+        make_cell( cell_lower( g, 0, ijk[ 0 ] ), cell_lower( g, 1, ijk[ 1 ] ), g.h[ 0 ], g.h[ 1 ], poly );
+        const Hs2 H = { rec[ 0 ], rec[ 1 ], rec[ 2 ] };
+        double lx[ 2 ], ly[ 2 ];
+        plane_cut( poly, H, lx, ly );
+        nverts[ p ] = 2;
+        out[ 0 ] = lx[ 0 ]; out[ 1 ] = ly[ 0 ]; out[ 2 ] = lx[ 1 ]; out[ 3 ] = ly[ 1 ];
+      }
+      else
+      {
+        const double lo[ 3 ] = { cell_lower( g, 0, ijk[ 0 ] ), cell_lower( g, 1, ijk[ 1 ] ), cell_lower( g, 2, ijk[ 2 ] ) };
+        Hex cell;
+        make_cell( lo, g.h, cell );
+        const Hs3 H = { { rec[ 0 ], rec[ 1 ], rec[ 2 ] }, rec[ 3 ] };
+        Face3 f;
+        plane_cut( cell, H, f );
+        nverts[ p ] = f.n;
+        for( int i = 0; i < f.n; ++i )
+          for( int k = 0; k < 3; ++k )
+            out[ 3 * i + k ] = f.v[ i ][ k ];
+      }
+    }
+  }
+
+  template< int DIM >
+  __global__ void __launch_bounds__( 128 ) k_interface_gather ( long long nMixed, const int *__restrict__ nverts, const int *__restrict__ offsets,
+                                                                 const double *__restrict__ verts, double *__restrict__ csr )
+  {
+    constexpr int STRIDE = ( DIM == 2 ) ? 2 : 12;
+    for( long long p = blockIdx.x * (long long) blockDim.x + threadIdx.x; p < nMixed; p += (long long) gridDim.x * blockDim.x )
+    {
+      const double *in = verts + p * STRIDE * DIM;
+      double *out = csr + (long long) offsets[ p ] * DIM;
+      for( int i = 0; i < nverts[ p ] * DIM; ++i )
+        out[ i ] = in[ i ];
+    }
+  }
+
+  // ------------------------------------------------------------------------------------------------------------
   // single-cell primitives on small batches (parity tests of G1/G2/G5/G6/G7 on the device)
   // ------------------------------------------------------------------------------------------------------------
 

@@ -29,6 +29,12 @@ namespace vofx
     void init ( int dim, int blocks, cudaStream_t s, Grid g, Indicator I, double *u );
     void test_face_velocity ( cudaStream_t s, Grid g, const Velocity *velocity, double time, long long cell, int face, double *out );
 
+    // k_interface.cu
+    int scan_blocks ( long long n );
+    void scan ( int dim, cudaStream_t s, Grid g, long long n, const unsigned char *flags, const int *counts, int *blockSums, long long *total, int *out, int phase );
+    void interface_cut ( int dim, int blocks, cudaStream_t s, Grid g, const double *hs, const int *cells, long long nMixed, int *nverts, double *verts );
+    void interface_gather ( int dim, int blocks, cudaStream_t s, long long nMixed, const int *nverts, const int *offsets, const double *verts, double *csr );
+
     // k_band2d.cu
     void youngs2 ( int blocks, cudaStream_t s, Grid g, const double *u, const int *mixedList, const StepState *state, int capacity, double *hs );
     void hf2 ( int blocks, cudaStream_t s, Grid g, const double *u, const int *mixedList, const StepState *state, int capacity, double *hs );

@@ -250,6 +250,21 @@ class StepResult:
     mixed_cells: int
 
 
+def get_interface_vertices(grid: CartesianGrid, reconstructions, flags):
+    """getInterfaceVertices (utility.hh:19-48) + MixedCellMapper::update (mixedcellmapper.hh:82-86): returns numpy arrays
+    (cells, offsets, vertices): the owned mixed cells in ascending index and the CSR of their interface polygons."""
+    import numpy as np
+    g = grid
+    g.use_current_stream()
+    nm, nv = C.c_int64(0), C.c_int64(0)
+    check(g._L.vofx_interface(g._ctx, g.ph(reconstructions), g.pf(flags), C.byref(nm), C.byref(nv)))
+    cells = np.empty(nm.value, dtype=np.int32)
+    offsets = np.zeros(nm.value + 1, dtype=np.int64)
+    vertices = np.empty((nv.value, g.dim), dtype=np.float64)
+    check(g._L.vofx_interface_fetch(g._ctx, C.c_void_p(cells.ctypes.data), C.c_void_p(offsets.ctypes.data), C.c_void_p(vertices.ctypes.data)))
+    return cells, offsets, vertices
+
+
 class Algorithm:
     """The time loop of algorithm.hh:37-120 on a device-resident colour function (no l1error, no writer).
 

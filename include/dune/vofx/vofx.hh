@@ -410,6 +410,37 @@ namespace Dune
 
 
     // Algorithm, algorithm.hh:37-120 (without l1error): the colour function stays on the device between steps.
+    // getInterfaceVertices
+    // --------------------
+    // utility.hh:19-48: the vertices of interface( entity, reconstructions ) of every mixed cell in the order the grid
+    // view visits them, as a CSR.  (On YaspGrid / SPGrid that order is the x-fastest index order the device uses.)
+    template< class Stencils, class ReconstructionSet, class Flags >
+    void getInterfaceVertices ( const Stencils &stencils, const ReconstructionSet &reconstructions, const Flags &flags,
+                                std::vector< typename ReconstructionSet::DataType::Coordinate > &vertices, std::vector< std::size_t > &offsets )
+    {
+      using Coordinate = typename ReconstructionSet::DataType::Coordinate;
+      auto &c = stencils.context();
+      constexpr int dim = std::decay_t< decltype( c ) >::dim;
+      c.gatherReconstructions( reconstructions );
+      c.gatherFlags( flags );
+      std::int64_t nMixed = 0, nVertices = 0;
+      check( vofx_interface_host( c.ctx(), c.halfspaces.data(), c.flags.data(), &nMixed, &nVertices ) );
+      std::vector< std::int32_t > cells( static_cast< std::size_t >( nMixed ) + 1 );
+      std::vector< std::int64_t > off( static_cast< std::size_t >( nMixed ) + 1 );
+      std::vector< double > flat( static_cast< std::size_t >( nVertices ) * dim + 1 );
+      check( vofx_interface_fetch( c.ctx(), cells.data(), off.data(), flat.data() ) );
+      offsets.assign( off.begin(), off.end() );
+      vertices.resize( static_cast< std::size_t >( nVertices ) );
+      for( std::size_t i = 0; i < vertices.size(); ++i )
+      {
+        Coordinate x;
+        for( int d = 0; d < dim; ++d )
+          x[ d ] = flat[ i * dim + d ];
+        vertices[ i ] = x;
+      }
+    }
+
+
     namespace Impl
     {
       template< class DW, class = void >

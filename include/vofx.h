@@ -177,6 +177,16 @@ int vofx_color_upload ( vofx_ctx *ctx, const double *u_host );
 int vofx_step_resident ( vofx_ctx *ctx, const vofx_step_params *params );
 int vofx_color_download ( vofx_ctx *ctx, double *u_host, uint8_t *flags_host /* may be NULL */ );
 
+/* ---- interface extraction (replaces getInterfaceVertices, utility.hh:19-48, and MixedCellMapper::update,
+ * mixedcellmapper.hh:82-86): the owned mixed cells in ascending cell index, and for the i-th of them the vertices of
+ * interface( entity, reconstructions ) (geometry/polytope.hh:69-75: a segment in 2D, a polygon with 3..6 vertices in
+ * 3D) as a CSR ( offsets[ i ] .. offsets[ i+1 ] ).  vofx_interface works on DEVICE arrays and returns the sizes;
+ * vofx_interface_fetch copies cells[ n_mixed ], offsets[ n_mixed + 1 ] and vertices[ n_vertices * dim ] to the HOST
+ * (the InterfaceGrid / bin2vtk consumers, interfacegrid/dataset.hh:114-120, bin2vtk.cc:264-281, live there). */
+int vofx_interface ( vofx_ctx *ctx, const double *halfspaces, const uint8_t *flags, int64_t *n_mixed, int64_t *n_vertices );
+int vofx_interface_host ( vofx_ctx *ctx, const double *halfspaces_host, const uint8_t *flags_host, int64_t *n_mixed, int64_t *n_vertices );
+int vofx_interface_fetch ( vofx_ctx *ctx, int32_t *cells_host, int64_t *offsets_host, double *vertices_host );
+
 /* ---- initial data on the device (replaces Average< Problem >, test/average.hh:28-54, i.e.
  * RecursiveInterpolationCube depth 3, interpolation/recursiveinterpolationcube.hh:33-82, for the built-in problems) */
 int vofx_init ( vofx_ctx *ctx, int problem, double time, double *u );

@@ -272,7 +272,43 @@ namespace
       (void) refVelocity;
 #endif
     }
+    // getInterfaceVertices (utility.hh:19-48) on the last reconstructions against the oracle's per-cell interface()
+    bool okIface = true;
+    {
+      using Coordinate = Dune::FieldVector< double, dim >;
+      std::vector< Coordinate > vertices;
+      std::vector< std::size_t > offsets;
+      Dune::VoFx::getInterfaceVertices( stencils, reconstructions, flags, vertices, offsets );
+      std::size_t m = 0;
+      for( std::size_t c = 0; c < N; ++c )
+      {
+        if( flo[ c ] != 1 && flo[ c ] != 2 )
+          continue;
+        double lo[ 3 ] = { 0, 0, 0 }, hh[ 3 ] = { 1, 1, 1 };
+        std::size_t r = c;
+        for( int d = 0; d < dim; ++d )
+        {
+          hh[ d ] = 1.0 / n[ d ];
+          lo[ d ] = 0.0 + double( r % n[ d ] ) * hh[ d ];
+          r /= n[ d ];
+        }
+        int nv = 0;
+        double verts[ 16 * 3 ], cen[ 3 ], meas = 0.0;
+        vo_interface( dim, lo, hh, hso.data() + c * ( dim + 1 ), &nv, verts, cen, &meas );
+        okIface = okIface && m + 1 < offsets.size() && offsets[ m + 1 ] - offsets[ m ] == std::size_t( nv );
+        for( int i = 0; okIface && i < nv; ++i )
+        {
+          double x[ 3 ];
+          for( int d = 0; d < dim; ++d )
+            x[ d ] = vertices[ offsets[ m ] + i ][ d ];
+          okIface = okIface && sameBits( x, verts + i * dim, dim );
+        }
+        ++m;
+      }
+      okIface = okIface && offsets.size() == m + 1 && offsets.back() == vertices.size();
+    }
     std::string tag( name );
+    expect( okIface, ( std::string( name ) + ": getInterfaceVertices == oracle (bit-exact)" ).c_str() );
     expect( okFlags, ( tag + ": FlagOperator == oracle (bit-exact)" ).c_str() );
     expect( okRecs, ( tag + ": ModifiedYoungsReconstruction == oracle (bit-exact)" ).c_str() );
     expect( okUpd, ( tag + ": Evolution update == oracle (bit-exact)" ).c_str() );

@@ -209,3 +209,34 @@ def test_curvature_inside_time_loop(vofx, case):
     assert float(alg.curvature[~mixed].abs().max()) == 0.0
     assert same_bits(alg.reconstructions.cpu().numpy()[mixed.cpu().numpy()], recs.cpu().numpy()[mixed.cpu().numpy()])
     grid.close()
+
+
+@pytest.mark.parametrize("case", ["2d_zalesak_64", "2d_sflow_40x24", "3d_leveque_32", "3d_sflow_20x12x16"])
+def test_interface_extraction(vofx, case):
+    """getInterfaceVertices / MixedCellMapper on the device against the oracle's per-cell
+    interface(): ordered mixed cells, CSR offsets and vertices, bit for bit"""
+    import torch
+    from oracle import oraclelib as O
+    g = golden(f"operators_{case}.npz")
+    n = tuple(int(x) for x in g["n"])
+    dim = len(n)
+    grid = vofx.CartesianGrid(n)
+    u = torch.tensor(g["u"], device=grid.device)
+    flags, recs = grid.empty("flags"), grid.empty("reconstructions")
+    vofx.FlagOperator(grid, float(g["eps"]))(u, flags)
+    vofx.ModifiedYoungsReconstruction(grid)(u, recs, flags)
+    cells, offsets, vertices = vofx.get_interface_vertices(grid, recs, flags)
+    f = flags.cpu().numpy()
+    expect = np.flatnonzero((f == 1) | (f == 2))
+    assert np.array_equal(cells, expect)
+    hs = recs.cpu().numpy()
+    h = np.array([1.0 / x for x in n])
+    for i, c in enumerate(cells):
+        ijk = [c % n[0], (c // n[0]) % n[1]] + ([c // (n[0] * n[1])] if dim == 3 else [])
+        lo = np.array(ijk, dtype=np.float64)
+        lo = np.array([0.0 + ijk[d] * h[d] for d in range(dim)])
+        nv, verts, _, _ = O.interface(lo, h, hs[c])
+        assert offsets[i + 1] - offsets[i] == nv, (case, c)
+        assert same_bits(vertices[offsets[i]:offsets[i + 1]], verts[:nv]), (case, c)
+    assert offsets[-1] == len(vertices)
+    grid.close()
