@@ -252,8 +252,10 @@ namespace
       launch::youngs2( blocks, ctx->stream, g, u, ctx->mixedList, ctx->state, ctx->capacity, hs );
     else
     {
-      launch::youngs_coop3( ctx->lanesPerCell, blocks, ctx->stream, g, u, ctx->mixedList, ctx->state, ctx->capacity, hs, ctx->sweepTable, ctx->serialCells, ctx->rootTasks );
-      int rc3 = checkLaunch( ctx, "k_youngs" );
+      // 3D height functions ride in the same kernel (Young's normal -> HF normal -> one plane-constant solve)
+      const bool hf3 = ( kind == VOFX_RECON_HF );
+      launch::youngs_coop3( ctx->lanesPerCell, blocks, ctx->stream, g, u, ctx->mixedList, ctx->state, ctx->capacity, hs, ctx->sweepTable, ctx->serialCells, ctx->rootTasks, hf3 ? 1 : 0 );
+      int rc3 = checkLaunch( ctx, hf3 ? "k_hf_coop" : "k_youngs" );
       if( rc3 )
         return rc3;
       profBegin( ctx );
@@ -270,12 +272,7 @@ namespace
       return rc;
     if( kind == VOFX_RECON_HF )
     {
-      profBegin( ctx );
-      if( g.dim == 2 )
-        launch::hf2( blocks, ctx->stream, g, u, ctx->mixedList, ctx->state, ctx->capacity, hs );
-      else
-        launch::hf3( blocks, ctx->stream, g, u, ctx->mixedList, ctx->state, ctx->capacity, hs );
-      rc = checkLaunch( ctx, "k_hf" );
+      // 2D: k_hf_fused above; 3D: done inside k_youngs_coop3< L, true >
     }
     else if( kind == VOFX_RECON_SWARTZ )
     {

@@ -514,96 +514,6 @@ namespace vofx
     }
   }
 
-  // R1 in 3D for the B200: L lanes per mixed cell (vofx_coop3d.cuh).  The stencil contributions, the faces of the cell
-  // volume, the direction vectors and the per-bracket terms of the plane-constant solve are spread over the lanes;
-  // the sweep topology comes from a table of the 96 generic height orders.  Cells with tied node heights (axis-aligned
-  // normals) are queued for k_locate_serial3.
-#ifndef VOFX_YOUNGS_THREADS_PER_SM
-#define VOFX_YOUNGS_THREADS_PER_SM 640   // resident threads per SM the register allocation aims for
-#endif
-  template< int L >
-  __global__ void __launch_bounds__( 16 * L, VOFX_YOUNGS_THREADS_PER_SM / ( 16 * L ) ) k_youngs_coop3 ( Grid g, const double *__restrict__ u, const int *__restrict__ mixedList,
-                                                             StepState *state, int capacity, double *__restrict__ hs,
-                                                             const coop::SweepTable *__restrict__ table, int *__restrict__ serialCells,
-                                                             coop::RootTask *__restrict__ rootTasks )
-  {
-    constexpr int GROUPS = 16;          // 16 groups per block: 128 threads for L = 8, 64 for L = 4
-    __shared__ coop::LocateScratch scratch[ GROUPS ];
-    const int count = mixed_count( state, capacity );
-    const int lane = threadIdx.x % L;
-    const int group = threadIdx.x / L;
-    coop::Group G;
-    G.lane = lane;
-    G.mask = ( ( L == 32 ) ? 0xffffffffu : ( ( 1u << L ) - 1u ) ) << ( ( threadIdx.x & 31 ) - lane );
-    coop::LocateScratch &S = scratch[ group ];
-    for( int idx = blockIdx.x * GROUPS + group; idx < count; idx += gridDim.x * GROUPS )
-    {
-      const int c = mixedList[ idx ];
-      int ijk[ 3 ];
-      cell_ijk( g, c, ijk );
-      const double colorEn = u[ c ];
-      double *out = hs + (long long) c * 4;
-      double normal[ 3 ];
-      if( !coop::youngs_normal_coop< L >( G, S, g, u, ijk, colorEn, normal ) )
-      {
-        if( lane == 0 )
-          out[ 0 ] = out[ 1 ] = out[ 2 ] = out[ 3 ] = 0.0;
-        G.sync();
-        continue;
-      }
-      const double lo[ 3 ] = { cell_lower( g, 0, ijk[ 0 ] ), cell_lower( g, 1, ijk[ 1 ] ), cell_lower( g, 2, ijk[ 2 ] ) };
-      double dist = 0.0;
-      coop::RootTask root;
-      root.pending = 0;
-      const bool located = coop::locate_coop< L >( G, S, *table, lo, g.h, normal, colorEn, dist, &root );
-      if( lane == 0 )
-      {
-        out[ 0 ] = normal[ 0 ];
-        out[ 1 ] = normal[ 1 ];
-        out[ 2 ] = normal[ 2 ];
-        if( !located )
-          serialCells[ atomicAdd( &state->serialLocate, 1 ) ] = c;
-        else if( root.pending )
-        {
-          root.cell = c;
-          rootTasks[ atomicAdd( &state->rootCount, 1 ) ] = root;
-        }
-        else
-          out[ 3 ] = dist;
-      }
-      G.sync();
-    }
-  }
-
-  // Brent's method for the cells whose bracket k_youngs_coop3 has found: one thread per cell
-  template< int DIM >
-  __global__ void __launch_bounds__( 128 ) k_locate_root3 ( const StepState *state, const coop::RootTask *__restrict__ rootTasks, double *__restrict__ hs )
-  {
-    const int n = state->rootCount;
-    for( int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x )
-    {
-      const coop::RootTask r = rootTasks[ t ];
-      hs[ (long long) r.cell * 4 + 3 ] = r.base + brent( r.V, 0.0, r.h, 1e-14 );
-    }
-  }
-
-  // plane-constant solve by the serial walk for the cells queued by k_youngs_coop3 (normal already in hs)
-  template< int DIM >
-  __global__ void __launch_bounds__( 64 ) k_locate_serial3 ( Grid g, const double *__restrict__ u, const StepState *state, double *__restrict__ hs,
-                                                              const int *__restrict__ serialCells )
-  {
-    const int n = state->serialLocate;
-    for( int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x )
-    {
-      const int c = serialCells[ t ];
-      int ijk[ 3 ];
-      cell_ijk( g, c, ijk );
-      double *rec = hs + (long long) c * 4;
-      const double normal[ 3 ] = { rec[ 0 ], rec[ 1 ], rec[ 2 ] };
-      rec[ 3 ] = locate_cell< 3 >( g, ijk, normal, u[ c ] );
-    }
-  }
-
   // ------------------------------------------------------------------------------------------------------------
   // S2 + R2: Cartesian height functions, stencil/heightfunctionstencil.hh:22-107, reconstruction/heightfunction.hh:101-259
   // ------------------------------------------------------------------------------------------------------------
@@ -656,45 +566,51 @@ namespace vofx
     return cell_exists( g, nb ) ? cell_index( g, nb ) : -1;
   }
 
+  // one column of getHeightValues, heightfunction.hh:147-196
+  template< int DIM >
+  __device__ double hf_column ( const Grid &g, const double *__restrict__ u, const int *ijk, int i, int j, int tup, int c )
+  {
+    const double TOL = 1e-10;
+    double height = 0.0;
+    long long cell = hf_cell< DIM >( g, ijk, i, j, c, 0 );
+    if( cell < 0 )
+      return height;
+    const double u0 = clamp01( __ldg( u + cell ) );
+    height += u0;
+    double lastU = u0;
+    for( int t = 1; t <= tup; ++t )
+    {
+      cell = hf_cell< DIM >( g, ijk, i, j, c, t );
+      if( cell < 0 )
+        break;
+      const double uu = clamp01( __ldg( u + cell ) );
+      if( uu > lastU - TOL && !( uu > 1.0 - TOL ) )
+        break;
+      height += uu;
+      lastU = uu;
+    }
+    lastU = u0;
+    for( int t = -1; t >= -tup; --t )
+    {
+      cell = hf_cell< DIM >( g, ijk, i, j, c, t );
+      if( cell < 0 )
+        break;
+      double uu = clamp01( __ldg( u + cell ) );
+      if( uu < lastU + TOL && !( uu < TOL ) )
+        uu = 1.0;
+      height += uu;
+      lastU = uu;
+    }
+    return height;
+  }
+
   // getHeightValues, heightfunction.hh:147-196
   template< int DIM >
   __device__ void hf_heights ( const Grid &g, const double *__restrict__ u, const int *ijk, int i, int j, int tup, double *heights )
   {
     constexpr int noc = ( DIM == 2 ) ? 3 : 9;
-    const double TOL = 1e-10;
     for( int c = 0; c < noc; ++c )
-    {
-      heights[ c ] = 0.0;
-      long long cell = hf_cell< DIM >( g, ijk, i, j, c, 0 );
-      if( cell < 0 )
-        continue;
-      const double u0 = clamp01( __ldg( u + cell ) );
-      heights[ c ] += u0;
-      double lastU = u0;
-      for( int t = 1; t <= tup; ++t )
-      {
-        cell = hf_cell< DIM >( g, ijk, i, j, c, t );
-        if( cell < 0 )
-          break;
-        const double uu = clamp01( __ldg( u + cell ) );
-        if( uu > lastU - TOL && !( uu > 1.0 - TOL ) )
-          break;
-        heights[ c ] += uu;
-        lastU = uu;
-      }
-      lastU = u0;
-      for( int t = -1; t >= -tup; --t )
-      {
-        cell = hf_cell< DIM >( g, ijk, i, j, c, t );
-        if( cell < 0 )
-          break;
-        double uu = clamp01( __ldg( u + cell ) );
-        if( uu < lastU + TOL && !( uu < TOL ) )
-          uu = 1.0;
-        heights[ c ] += uu;
-        lastU = uu;
-      }
-    }
+      heights[ c ] = hf_column< DIM >( g, u, ijk, i, j, tup, c );
   }
 
   // computeNormal, heightfunction.hh:200-226 (2D) / :229-259 (3D)
@@ -775,6 +691,116 @@ namespace vofx
       for( int k = 0; k < DIM; ++k )
         rec[ k ] = newNormal[ k ];
       rec[ DIM ] = dist;
+    }
+  }
+
+  // R1 in 3D for the B200: L lanes per mixed cell (vofx_coop3d.cuh).  The stencil contributions, the faces of the cell
+  // volume, the direction vectors and the per-bracket terms of the plane-constant solve are spread over the lanes;
+  // the sweep topology comes from a table of the 96 generic height orders.  Cells with tied node heights (axis-aligned
+  // normals) are queued for k_locate_serial3.
+#ifndef VOFX_YOUNGS_THREADS_PER_SM
+#define VOFX_YOUNGS_THREADS_PER_SM 640   // resident threads per SM the register allocation aims for
+#endif
+  template< int L, bool HF >
+  __global__ void __launch_bounds__( 16 * L, VOFX_YOUNGS_THREADS_PER_SM / ( 16 * L ) ) k_youngs_coop3 ( Grid g, const double *__restrict__ u, const int *__restrict__ mixedList,
+                                                             StepState *state, int capacity, double *__restrict__ hs,
+                                                             const coop::SweepTable *__restrict__ table, int *__restrict__ serialCells,
+                                                             coop::RootTask *__restrict__ rootTasks )
+  {
+    constexpr int GROUPS = 16;          // 16 groups per block: 128 threads for L = 8, 64 for L = 4
+    __shared__ coop::LocateScratch scratch[ GROUPS ];
+    const int count = mixed_count( state, capacity );
+    const int lane = threadIdx.x % L;
+    const int group = threadIdx.x / L;
+    coop::Group G;
+    G.lane = lane;
+    G.mask = ( ( L == 32 ) ? 0xffffffffu : ( ( 1u << L ) - 1u ) ) << ( ( threadIdx.x & 31 ) - lane );
+    coop::LocateScratch &S = scratch[ group ];
+    for( int idx = blockIdx.x * GROUPS + group; idx < count; idx += gridDim.x * GROUPS )
+    {
+      const int c = mixedList[ idx ];
+      int ijk[ 3 ];
+      cell_ijk( g, c, ijk );
+      const double colorEn = u[ c ];
+      double *out = hs + (long long) c * 4;
+      double normal[ 3 ];
+      const bool haveYoungs = coop::youngs_normal_coop< L >( G, S, g, u, ijk, colorEn, normal );
+      if( !HF && !haveYoungs )
+      {
+        if( lane == 0 )
+          out[ 0 ] = out[ 1 ] = out[ 2 ] = out[ 3 ] = 0.0;
+        G.sync();
+        continue;
+      }
+      if( HF )
+      {
+        // HeightFunctionReconstruction::applyLocal, heightfunction.hh:101-123: of the Young's reconstruction only the normal
+        // of the cell is read, so its plane-constant solve is skipped; the nine columns are summed by different lanes
+        if( !haveYoungs )
+          normal[ 0 ] = normal[ 1 ] = normal[ 2 ] = 0.0;       // the zero half-space, modifiedyoungs.hh:128-129
+        int dir, sign;
+        hf_orientation< 3 >( normal, dir, sign );
+        G.sync();                                              // S.sums (the least-squares sums) has been read by every lane
+        for( int col = lane; col < 9; col += L )
+          S.sums[ col ] = hf_column< 3 >( g, u, ijk, dir, sign, 3, col );
+        G.sync();
+        double heights[ 9 ];
+#pragma unroll
+        for( int col = 0; col < 9; ++col )
+          heights[ col ] = S.sums[ col ];
+        hf_normal< 3 >( heights, dir, sign, normal );
+        G.sync();                                              // before locate_coop reuses the scratch
+      }
+      const double lo[ 3 ] = { cell_lower( g, 0, ijk[ 0 ] ), cell_lower( g, 1, ijk[ 1 ] ), cell_lower( g, 2, ijk[ 2 ] ) };
+      double dist = 0.0;
+      coop::RootTask root;
+      root.pending = 0;
+      const bool located = coop::locate_coop< L >( G, S, *table, lo, g.h, normal, colorEn, dist, &root );
+      if( lane == 0 )
+      {
+        out[ 0 ] = normal[ 0 ];
+        out[ 1 ] = normal[ 1 ];
+        out[ 2 ] = normal[ 2 ];
+        if( !located )
+          serialCells[ atomicAdd( &state->serialLocate, 1 ) ] = c;
+        else if( root.pending )
+        {
+          root.cell = c;
+          rootTasks[ atomicAdd( &state->rootCount, 1 ) ] = root;
+        }
+        else
+          out[ 3 ] = dist;
+      }
+      G.sync();
+    }
+  }
+
+  // Brent's method for the cells whose bracket k_youngs_coop3 has found: one thread per cell
+  template< int DIM >
+  __global__ void __launch_bounds__( 128 ) k_locate_root3 ( const StepState *state, const coop::RootTask *__restrict__ rootTasks, double *__restrict__ hs )
+  {
+    const int n = state->rootCount;
+    for( int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x )
+    {
+      const coop::RootTask r = rootTasks[ t ];
+      hs[ (long long) r.cell * 4 + 3 ] = r.base + brent( r.V, 0.0, r.h, 1e-14 );
+    }
+  }
+
+  // plane-constant solve by the serial walk for the cells queued by k_youngs_coop3 (normal already in hs)
+  template< int DIM >
+  __global__ void __launch_bounds__( 64 ) k_locate_serial3 ( Grid g, const double *__restrict__ u, const StepState *state, double *__restrict__ hs,
+                                                              const int *__restrict__ serialCells )
+  {
+    const int n = state->serialLocate;
+    for( int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x )
+    {
+      const int c = serialCells[ t ];
+      int ijk[ 3 ];
+      cell_ijk( g, c, ijk );
+      double *rec = hs + (long long) c * 4;
+      const double normal[ 3 ] = { rec[ 0 ], rec[ 1 ], rec[ 2 ] };
+      rec[ 3 ] = locate_cell< 3 >( g, ijk, normal, u[ c ] );
     }
   }
 
