@@ -17,5 +17,29 @@ namespace vofx
       else
         k_swartz_coop3< 8 ><<< blocks, 64, 0, s >>>( g, u, flags, mixedList, state, capacity, hs, maxIterations, (const coop::SweepTable *) sweepTable );
     }
+    size_t swz_cell_bytes () { return sizeof( SwzCell ); }
+    size_t swz_task_bytes () { return sizeof( SwzTask ); }
+    // all iterations of the batched Swartz reconstruction (4 kernels each) after the setup; `counter` is zeroed by the caller
+    void swartz_batched3 ( int lanes, int sms, cudaStream_t s, Grid g, const double *u, const unsigned char *flags, const int *mixedList, StepState *state,
+                           int capacity, double *hs, int maxIterations, const void *sweepTable, void *cells, void *tasks, int *counter )
+    {
+      const coop::SweepTable *T = (const coop::SweepTable *) sweepTable;
+      SwzCell *C = (SwzCell *) cells;
+      SwzTask *K = (SwzTask *) tasks;
+      k_swz_setup< 3 ><<< sms * 8, 128, 0, s >>>( g, flags, mixedList, state, capacity, hs, C, K, counter );
+      for( int it = 0; it < maxIterations; ++it )
+      {
+        if( lanes == 8 )
+          k_swz_locate< 8 ><<< sms * 8, 128, 0, s >>>( g, u, C, K, counter, T );
+        else
+          k_swz_locate< 4 ><<< sms * 16, 64, 0, s >>>( g, u, C, K, counter, T );
+        k_swz_centroid< 3 ><<< sms * 16, 64, 0, s >>>( g, u, C, K, counter );
+        if( lanes == 8 )
+          k_swz_normal< 8 ><<< sms * 8, 64, 0, s >>>( g, u, C, K, state, capacity, T );
+        else
+          k_swz_normal< 4 ><<< sms * 16, 32, 0, s >>>( g, u, C, K, state, capacity, T );
+        k_swz_finish< 3 ><<< sms * 8, 64, 0, s >>>( g, u, C, state, capacity, hs, maxIterations );
+      }
+    }
   } // namespace launch
 } // namespace vofx

@@ -54,6 +54,10 @@ struct vofx_ctx
   int taskCapacity = 0;
   void *sweepTable = nullptr;       // coop::SweepTable
   int *serialCells = nullptr;       // mixed cells whose plane constant is left to the serial walk
+  // batched 3D Swartz: per-cell and per-(cell, neighbour) records, grow-only
+  unsigned char *swzCells = nullptr, *swzTasks = nullptr;
+  size_t swzCellCap = 0, swzTaskCap = 0;
+  int *swzCounter = nullptr;
   // interface extraction (vofx_interface): grow-only scratch
   int *ifBlockSums = nullptr, *ifCells = nullptr, *ifNverts = nullptr, *ifOffsets = nullptr;
   long long *ifTotal = nullptr;
@@ -236,6 +240,8 @@ namespace
     return checkLaunch( ctx, "k_compact_flags" );
   }
 
+  int readState ( vofx_ctx *ctx, StepState &s );
+
   int launchReconstruct ( vofx_ctx *ctx, int kind, const double *u, const unsigned char *flags, double *hs, int maxIterations )
   {
     const Grid &g = ctx->grid;
@@ -282,11 +288,31 @@ namespace
       else
       {
         const char *env = std::getenv( "VOFX_SWARTZ_LANES" );
-        const int lanes = ( env && std::atoi( env ) == 8 ) ? 8 : 4;   // measured at 256^3: 38.6 ms (4 lanes) vs 45.4 ms (8), serial kernel 261 ms
-        if( env && std::atoi( env ) == 1 )
+        const int lanes = ( env && std::atoi( env ) == 8 ) ? 8 : 4;   // measured at 256^3 per step: batched 10.2 ms (4 lanes) / 12.7 ms (8); per-cell kernel 38.6 ms; serial kernel 261 ms
+        const char *mode = std::getenv( "VOFX_SWARTZ_MODE" );
+        if( mode && std::strcmp( mode, "serial" ) == 0 )
           launch::swartz3( ctx->numSMs * 16, ctx->stream, g, u, flags, ctx->mixedList, ctx->state, ctx->capacity, hs, maxIterations );
-        else
+        else if( mode && std::strcmp( mode, "cell" ) == 0 )
           launch::swartz_coop3( lanes, ctx->numSMs * 16, ctx->stream, g, u, flags, ctx->mixedList, ctx->state, ctx->capacity, hs, maxIterations, ctx->sweepTable );
+        else
+        {
+          // batched over the band: the buffers are sized from the mixed-cell count of this step (one small read-back)
+          StepState now;
+          int rcs = readState( ctx, now );
+          if( rcs )
+            return rcs;
+          const size_t nCells = (size_t) ( now.mixedCount < ctx->capacity ? now.mixedCount : ctx->capacity );
+          rcs = growDevice( ctx->swzCells, ctx->swzCellCap, nCells * launch::swz_cell_bytes() + 16 );
+          rcs = rcs ? rcs : growDevice( ctx->swzTasks, ctx->swzTaskCap, nCells * 27 * launch::swz_task_bytes() + 16 );
+          rcs = rcs ? rcs : ensureDevice( ctx->swzCounter, (size_t) 1 );
+          if( rcs )
+            return rcs;
+          VOFX_CUDA( cudaMemsetAsync( ctx->swzCounter, 0, sizeof( int ), ctx->stream ) );
+          profBegin( ctx );
+          launch::swartz_batched3( lanes, ctx->numSMs, ctx->stream, g, u, flags, ctx->mixedList, ctx->state, ctx->capacity, hs, maxIterations, ctx->sweepTable,
+                                   ctx->swzCells, ctx->swzTasks, ctx->swzCounter );
+          ctx->launches += 4 * maxIterations;
+        }
       }
       rc = checkLaunch( ctx, "k_swartz" );
     }
@@ -588,6 +614,9 @@ extern "C"
     cudaFree( ctx->sweepTable );
     cudaFree( ctx->serialCells );
     cudaFree( ctx->rootTasks );
+    cudaFree( ctx->swzCells );
+    cudaFree( ctx->swzTasks );
+    cudaFree( ctx->swzCounter );
     cudaFree( ctx->ifBlockSums );
     cudaFree( ctx->ifCells );
     cudaFree( ctx->ifNverts );

@@ -1047,6 +1047,310 @@ namespace vofx
   }
 
   // ------------------------------------------------------------------------------------------------------------
+  // R3 in 3D, batched over the whole band (modifiedswartz.hh:167-243).  One iteration of every still-active cell is four
+  // small kernels with compact code and full grids instead of one long per-cell program:
+  //   k_swz_locate   group of L lanes per (cell, neighbour) task: bracket of the plane constant with the cell's normal
+  //   k_swz_centroid one thread per task: root search, interface polygon, centroid
+  //   k_swz_normal   group per cell: the n(n-1) cross products row by row, new normal, bracket for the cell itself
+  //   k_swz_finish   one thread per cell: root search, write the reconstruction, convergence test
+  // The iteration count is data dependent (<= maxIterations, default 10): all iterations are enqueued and the cells
+  // that have converged are skipped on the device (no host round trip).
+  // ------------------------------------------------------------------------------------------------------------
+
+  struct SwzCell
+  {
+    double normal[ 3 ], oldNormal[ 3 ];
+    double dist;
+    coop::RootTask root;              // bracket of the cell's own plane constant (k_swz_normal -> k_swz_finish)
+    int taskBase, nNb;
+    int active, iterations, state;    // state of `root`: 0 dist known, 1 root pending, 2 serial walk, 3 keep the last reconstruction
+    int cell;
+    unsigned char nbOff[ 28 ];
+  };
+
+  struct SwzTask
+  {
+    coop::RootTask root;
+    double dist;
+    double cen[ 3 ];
+    int owner;                        // index into the mixed list / SwzCell array
+    int which;                        // 0: the cell itself, a > 0: its (a-1)-th mixed neighbour
+    int state, pad;
+  };
+
+  template< int DIM_ >
+  __global__ void __launch_bounds__( 128 ) k_swz_setup ( Grid g, const unsigned char *__restrict__ flags, const int *__restrict__ mixedList,
+                                                          StepState *state, int capacity, const double *__restrict__ hs,
+                                                          SwzCell *__restrict__ cells, SwzTask *__restrict__ tasks, int *taskCounter )
+  {
+    const int count = mixed_count( state, capacity );
+    for( int p = blockIdx.x * blockDim.x + threadIdx.x; p < count; p += gridDim.x * blockDim.x )
+    {
+      const int c = mixedList[ p ];
+      int ijk[ 3 ];
+      cell_ijk( g, c, ijk );
+      SwzCell &C = cells[ p ];
+      int n = 0;
+      for( int s = 0; s < 26; ++s )
+      {
+        const int m = ( s < 13 ) ? s : s + 1;
+        const int nb[ 3 ] = { ijk[ 0 ] + ( m % 3 ) - 1, ijk[ 1 ] + ( ( m / 3 ) % 3 ) - 1, ijk[ 2 ] + ( m / 9 ) - 1 };
+        if( cell_exists( g, nb ) && is_mixed( flags[ cell_index( g, nb ) ] ) )
+          C.nbOff[ n++ ] = (unsigned char) ( ( m % 3 ) | ( ( ( m / 3 ) % 3 ) << 2 ) | ( ( m / 9 ) << 4 ) );
+      }
+      const double *rec = hs + (long long) c * 4;
+      for( int k = 0; k < 3; ++k )
+        C.normal[ k ] = rec[ k ];
+      C.dist = rec[ 3 ];
+      C.nNb = n;
+      C.cell = c;
+      C.active = 1;
+      C.iterations = 0;
+      C.state = 0;
+      const int base = atomicAdd( taskCounter, n + 1 );
+      C.taskBase = base;
+      for( int a = 0; a <= n; ++a )
+      {
+        tasks[ base + a ].owner = p;
+        tasks[ base + a ].which = a;
+      }
+    }
+  }
+
+  __device__ __forceinline__ void swz_task_cell ( const SwzCell &C, const Grid &g, int which, int *cell )
+  {
+    cell_ijk( g, C.cell, cell );
+    if( which > 0 )
+    {
+      const int off = C.nbOff[ which - 1 ];
+      cell[ 0 ] += ( off & 3 ) - 1;
+      cell[ 1 ] += ( ( off >> 2 ) & 3 ) - 1;
+      cell[ 2 ] += ( ( off >> 4 ) & 3 ) - 1;
+    }
+  }
+
+  template< int L >
+  __global__ void __launch_bounds__( 16 * L, VOFX_YOUNGS_THREADS_PER_SM / ( 16 * L ) ) k_swz_locate ( Grid g, const double *__restrict__ u, const SwzCell *__restrict__ cells,
+                                                                                                        SwzTask *__restrict__ tasks, const int *taskCounter,
+                                                                                                        const coop::SweepTable *__restrict__ table )
+  {
+    constexpr int GROUPS = 16;
+    __shared__ coop::LocateScratch scratch[ GROUPS ];
+    const int nTasks = *taskCounter;
+    const int lane = threadIdx.x % L;
+    const int group = threadIdx.x / L;
+    coop::Group G;
+    G.lane = lane;
+    G.mask = ( ( 1u << L ) - 1u ) << ( ( threadIdx.x & 31 ) - lane );
+    coop::LocateScratch &S = scratch[ group ];
+    for( int t = blockIdx.x * GROUPS + group; t < nTasks; t += gridDim.x * GROUPS )
+    {
+      SwzTask &T = tasks[ t ];
+      const SwzCell &C = cells[ T.owner ];
+      if( !C.active )
+        continue;
+      int cell[ 3 ];
+      swz_task_cell( C, g, T.which, cell );
+      const double lo[ 3 ] = { cell_lower( g, 0, cell[ 0 ] ), cell_lower( g, 1, cell[ 1 ] ), cell_lower( g, 2, cell[ 2 ] ) };
+      const double normal[ 3 ] = { C.normal[ 0 ], C.normal[ 1 ], C.normal[ 2 ] };
+      const double color = u[ cell_index( g, cell ) ];
+      coop::RootTask root;
+      root.pending = 0;
+      double dist = 0.0;
+      const bool ok = coop::locate_coop< L >( G, S, *table, lo, g.h, normal, color, dist, &root );
+      if( lane == 0 )
+      {
+        T.state = !ok ? 2 : ( root.pending ? 1 : 0 );
+        T.dist = dist;
+        T.root = root;
+      }
+      G.sync();
+    }
+  }
+
+  template< int DIM_ >
+  __global__ void __launch_bounds__( 64 ) k_swz_centroid ( Grid g, const double *__restrict__ u, const SwzCell *__restrict__ cells, SwzTask *__restrict__ tasks,
+                                                            const int *taskCounter )
+  {
+    const int nTasks = *taskCounter;
+    for( int t = blockIdx.x * blockDim.x + threadIdx.x; t < nTasks; t += gridDim.x * blockDim.x )
+    {
+      SwzTask &T = tasks[ t ];
+      const SwzCell &C = cells[ T.owner ];
+      if( !C.active )
+        continue;
+      int cell[ 3 ];
+      swz_task_cell( C, g, T.which, cell );
+      const double lo[ 3 ] = { cell_lower( g, 0, cell[ 0 ] ), cell_lower( g, 1, cell[ 1 ] ), cell_lower( g, 2, cell[ 2 ] ) };
+      const double normal[ 3 ] = { C.normal[ 0 ], C.normal[ 1 ], C.normal[ 2 ] };
+      double dist = T.dist;
+      if( T.state == 1 )
+        dist = coop::root_of( T.root );
+      else if( T.state == 2 )
+        dist = coop::locate_serial( lo, g.h, normal, u[ cell_index( g, cell ) ] );
+      double c[ 3 ];
+      coop::interface_centroid_serial( lo, g.h, normal, dist, c );
+      T.cen[ 0 ] = c[ 0 ];
+      T.cen[ 1 ] = c[ 1 ];
+      T.cen[ 2 ] = c[ 2 ];
+    }
+  }
+
+  struct SwzNormalScratch
+  {
+    coop::LocateScratch loc;
+    double row[ coop::kMaxSwartzNb ][ 3 ];
+    double cen[ coop::kMaxSwartzNb + 1 ][ 3 ];
+    double nsum[ 3 ];
+    unsigned char rowValid[ 32 ];
+  };
+
+  template< int L >
+  __global__ void __launch_bounds__( 8 * L ) k_swz_normal ( Grid g, const double *__restrict__ u, SwzCell *__restrict__ cells, const SwzTask *__restrict__ tasks,
+                                                             const StepState *state, int capacity, const coop::SweepTable *__restrict__ table )
+  {
+    constexpr int GROUPS = 8;
+    __shared__ SwzNormalScratch scratch[ GROUPS ];
+    const int count = mixed_count( state, capacity );
+    const int lane = threadIdx.x % L;
+    const int group = threadIdx.x / L;
+    coop::Group G;
+    G.lane = lane;
+    G.mask = ( ( 1u << L ) - 1u ) << ( ( threadIdx.x & 31 ) - lane );
+    SwzNormalScratch &S = scratch[ group ];
+    for( int p = blockIdx.x * GROUPS + group; p < count; p += gridDim.x * GROUPS )
+    {
+      SwzCell &C = cells[ p ];
+      if( !C.active )
+        continue;
+      const int nNb = C.nNb;
+      const double oldNormal[ 3 ] = { C.normal[ 0 ], C.normal[ 1 ], C.normal[ 2 ] };
+      for( int a = lane; a <= nNb; a += L )
+        for( int k = 0; k < 3; ++k )
+          S.cen[ a ][ k ] = tasks[ C.taskBase + a ].cen[ k ];
+      if( lane < 3 )
+        S.nsum[ lane ] = 0.0;
+      G.sync();
+      // normal = sum over ordered pairs ( a, b ), a != b, of the normalised cross products, modifiedswartz.hh:196-229
+      for( int a = 0; a < nNb; ++a )
+      {
+        for( int b = lane; b < nNb; b += L )
+        {
+          bool valid = false;
+          double cn[ 3 ] = { 0.0, 0.0, 0.0 };
+          if( b != a )
+          {
+            double d1[ 3 ], d2[ 3 ];
+            for( int k = 0; k < 3; ++k )
+            {
+              d1[ k ] = S.cen[ a + 1 ][ k ] - S.cen[ 0 ][ k ];
+              d2[ k ] = S.cen[ b + 1 ][ k ] - S.cen[ 0 ][ k ];
+            }
+            cross3( d1, d2, cn );
+            if( !( norm3( cn ) < 1e-12 ) )
+            {
+              valid = true;
+              if( dot3( cn, oldNormal ) < 0 )
+                for( int k = 0; k < 3; ++k )
+                  cn[ k ] *= -1.0;
+              const double nrm = norm3( cn );
+              for( int k = 0; k < 3; ++k )
+                cn[ k ] = vdiv( cn[ k ], nrm );
+            }
+          }
+          S.rowValid[ b ] = valid ? 1 : 0;
+          for( int k = 0; k < 3; ++k )
+            S.row[ b ][ k ] = cn[ k ];
+        }
+        G.sync();
+        if( lane < 3 )
+        {
+          double acc = S.nsum[ lane ];
+          for( int b = 0; b < nNb; ++b )
+            if( S.rowValid[ b ] )
+              acc += 1.0 * S.row[ b ][ lane ];
+          S.nsum[ lane ] = acc;
+        }
+        G.sync();
+      }
+      double normal[ 3 ] = { S.nsum[ 0 ], S.nsum[ 1 ], S.nsum[ 2 ] };
+      double n2 = 0.0;
+      for( int k = 0; k < 3; ++k )
+        n2 += normal[ k ] * normal[ k ];
+      const double nrm = sqrt( n2 );
+      G.sync();
+      if( nrm < 0.5 )
+      {
+        // "return": keep the last reconstruction, modifiedswartz.hh:231-232
+        if( lane == 0 )
+          C.state = 3;
+        continue;
+      }
+      for( int k = 0; k < 3; ++k )
+        normal[ k ] = vdiv( normal[ k ], nrm );
+      int ijk[ 3 ];
+      cell_ijk( g, C.cell, ijk );
+      const double lo[ 3 ] = { cell_lower( g, 0, ijk[ 0 ] ), cell_lower( g, 1, ijk[ 1 ] ), cell_lower( g, 2, ijk[ 2 ] ) };
+      coop::RootTask root;
+      root.pending = 0;
+      double dist = 0.0;
+      const bool ok = coop::locate_coop< L >( G, S.loc, *table, lo, g.h, normal, u[ C.cell ], dist, &root );
+      if( lane == 0 )
+      {
+        for( int k = 0; k < 3; ++k )
+        {
+          C.oldNormal[ k ] = oldNormal[ k ];
+          C.normal[ k ] = normal[ k ];
+        }
+        C.dist = dist;
+        C.root = root;
+        C.state = !ok ? 2 : ( root.pending ? 1 : 0 );
+      }
+      G.sync();
+    }
+  }
+
+  template< int DIM_ >
+  __global__ void __launch_bounds__( 64 ) k_swz_finish ( Grid g, const double *__restrict__ u, SwzCell *__restrict__ cells, const StepState *state, int capacity,
+                                                          double *__restrict__ hs, int maxIterations )
+  {
+    const int count = mixed_count( state, capacity );
+    for( int p = blockIdx.x * blockDim.x + threadIdx.x; p < count; p += gridDim.x * blockDim.x )
+    {
+      SwzCell &C = cells[ p ];
+      if( !C.active )
+        continue;
+      if( C.state == 3 )
+      {
+        C.active = 0;
+        continue;
+      }
+      double dist = C.dist;
+      if( C.state == 1 )
+        dist = coop::root_of( C.root );
+      else if( C.state == 2 )
+      {
+        int ijk[ 3 ];
+        cell_ijk( g, C.cell, ijk );
+        const double lo[ 3 ] = { cell_lower( g, 0, ijk[ 0 ] ), cell_lower( g, 1, ijk[ 1 ] ), cell_lower( g, 2, ijk[ 2 ] ) };
+        dist = coop::locate_serial( lo, g.h, C.normal, u[ C.cell ] );
+      }
+      double *rec = hs + (long long) C.cell * 4;
+      rec[ 0 ] = C.normal[ 0 ];
+      rec[ 1 ] = C.normal[ 1 ];
+      rec[ 2 ] = C.normal[ 2 ];
+      rec[ 3 ] = dist;
+      double dotp = 0.0;
+      for( int k = 0; k < 3; ++k )
+        dotp += C.normal[ k ] * C.oldNormal[ k ];
+      const double residuum = 1.0 - dotp;
+      const int it = C.iterations + 1;
+      C.iterations = it;
+      C.active = ( residuum > 1e-12 && it < maxIterations ) ? 1 : 0;
+    }
+  }
+
+  // ------------------------------------------------------------------------------------------------------------
   // E1: geometric fluxes, evolution/evolution.hh:90-174.  LANES lanes per mixed cell, one per face.
   // ------------------------------------------------------------------------------------------------------------
 

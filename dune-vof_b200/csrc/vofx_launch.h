@@ -63,6 +63,10 @@ namespace vofx
                    int capacity, double *hs, int maxIterations );
     void swartz_coop3 ( int lanes, int blocks, cudaStream_t s, Grid g, const double *u, const unsigned char *flags, const int *mixedList, const StepState *state,
                         int capacity, double *hs, int maxIterations, const void *sweepTable );
+    size_t swz_cell_bytes ();
+    size_t swz_task_bytes ();
+    void swartz_batched3 ( int lanes, int sms, cudaStream_t s, Grid g, const double *u, const unsigned char *flags, const int *mixedList, StepState *state,
+                           int capacity, double *hs, int maxIterations, const void *sweepTable, void *cells, void *tasks, int *counter );
     void flux3 ( int blocks, cudaStream_t s, Grid g, const Velocity *velocity, const double *hs, const unsigned char *flags, const int *mixedList,
                  StepState *state, int capacity, FluxRecord *records, const double *timeOverride, const double *dtOverride );
     void flux_prepare3 ( int blocks, cudaStream_t s, Grid g, const Velocity *velocity, const unsigned char *flags, const int *mixedList, StepState *state,
