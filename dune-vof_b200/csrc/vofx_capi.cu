@@ -342,7 +342,7 @@ namespace
       ctx->launches++;   // k_flux_clip_serial3 rides along (a handful of tasks per step)
       return checkLaunch( ctx, "k_flux_clip" );
     }
-    launch::flux_cell3( ctx->numSMs * 8, ctx->stream, g, ctx->velDev, hs, flags, ctx->mixedList, ctx->state, ctx->capacity, ctx->records, ctx->tasks, ctx->taskCapacity,
+    launch::flux_cell3( ctx->numSMs * 8, ctx->stream, g, ctx->velDev, ctx->velHost, hs, flags, ctx->mixedList, ctx->state, ctx->capacity, ctx->records, ctx->tasks, ctx->taskCapacity,
                         ctx->clipTable, timeOverride, dtOverride );
     ctx->launches++;     // k_flux_clip_serial3 rides along (a handful of clips per step)
     return checkLaunch( ctx, "k_flux" );

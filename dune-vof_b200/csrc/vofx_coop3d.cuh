@@ -33,7 +33,7 @@ namespace vofx
       unsigned char pad0;
       unsigned char cut[ 6 ];        // a | b << 3: Edge( a, b ).intersection( plane ), operand order as in the walk
       unsigned char faceStart[ 8 ];  // face f owns the edges faceStart[f] .. faceStart[f+1]-1
-      unsigned char refs[ kMaxClipEdges ];   // first node of every edge; the second node is the next entry (cyclic in the face)
+      unsigned char refs[ kMaxClipEdges ];   // per edge: first node (low nibble) | face (high nibble); second node = next entry (cyclic in the face)
       unsigned char pad1[ 10 ];
     };
     static_assert( sizeof( ClipCase ) == 64, "ClipCase must be 64 bytes" );
@@ -75,7 +75,7 @@ namespace vofx
           for( int k = 0; k < t.flen[ f ]; ++k )
           {
             const int id = t.fe0[ f ][ k ];
-            c.refs[ e++ ] = (unsigned char) ( id < t.n ? t.innerNode[ id ] : 8 + ( id - t.n ) );
+            c.refs[ e++ ] = (unsigned char) ( ( id < t.n ? t.innerNode[ id ] : 8 + ( id - t.n ) ) | ( f << 4 ) );
           }
         }
         for( int f = t.nFaces; f < 8; ++f )
@@ -151,13 +151,13 @@ namespace vofx
 #pragma unroll 1
       for( int k = 0; k < len; ++k )
       {
-        const int r = cs.refs[ e0 + k ];
+        const int r = cs.refs[ e0 + k ] & 15;
         for( int d = 0; d < 3; ++d )
           center[ d ] += S.x[ d ][ r ];
       }
       for( int k = 0; k < 3; ++k )
       {
-        const int r = cs.refs[ e0 + k ];
+        const int r = cs.refs[ e0 + k ] & 15;
         for( int d = 0; d < 3; ++d )
           x3[ k ][ d ] = S.x[ d ][ r ];
       }
@@ -174,11 +174,9 @@ namespace vofx
     // per iteration in straight-line code: the two dependent fp64 chains (cross, sqrt, three divisions) interleave.
     VOFX_INLINE void clip_edge_operands ( const ClipScratch &S, const ClipCase &cs, int e, double *x0, double *x1, double *fn )
     {
-      int f = 0;
-      while( cs.faceStart[ f + 1 ] <= e )
-        ++f;
-      const int r0 = cs.refs[ e ];
-      const int r1 = cs.refs[ ( e + 1 < cs.faceStart[ f + 1 ] ) ? e + 1 : cs.faceStart[ f ] ];
+      const int f = cs.refs[ e ] >> 4;
+      const int r0 = cs.refs[ e ] & 15;
+      const int r1 = cs.refs[ ( e + 1 < cs.faceStart[ f + 1 ] ) ? e + 1 : cs.faceStart[ f ] ] & 15;
       for( int d = 0; d < 3; ++d )
       {
         x0[ d ] = S.x[ d ][ r0 ];
@@ -237,6 +235,49 @@ namespace vofx
         for( int d = 0; d < 3; ++d )
           poly.x[ i ][ d ] = S.x[ d ][ i ];
       return clip_volume( poly, hs );
+    }
+
+    // upwindPolygon3d( face, v ), 3d/upwindpolygon.hh:24-74: is the shifted copy of the face the first half of the nodes?
+    VOFX_HD inline bool upwind_shifted_first ( const double *lo, const double *h, int face, const double *v )
+    {
+      const int axis = face >> 1;
+      double o[ 3 ] = { lo[ 0 ], lo[ 1 ], lo[ 2 ] };
+      if( face & 1 )
+        o[ axis ] += h[ axis ];
+      const int a0 = ( axis == 0 ) ? 1 : 0;
+      const int a1 = ( axis == 2 ) ? 1 : 2;
+      double c1[ 3 ] = { o[ 0 ], o[ 1 ], o[ 2 ] }, c2[ 3 ] = { o[ 0 ], o[ 1 ], o[ 2 ] };
+      c1[ a0 ] += h[ a0 ];
+      c2[ a1 ] += h[ a1 ];
+      double e1[ 3 ], e2[ 3 ], cr[ 3 ];
+      for( int d = 0; d < 3; ++d )
+      {
+        e1[ d ] = c1[ d ] - o[ d ];
+        e2[ d ] = c2[ d ] - o[ d ];
+      }
+      cross3( e1, e2, cr );
+      return dot3( cr, v ) < 0.0;
+    }
+
+    // node `lane` of that polytope once the orientation is known
+    VOFX_HD inline void upwind_node_oriented ( int lane, const double *lo, const double *h, int face, const double *v, bool shiftedFirst, double *xn )
+    {
+      const int axis = face >> 1;
+      const int a0 = ( axis == 0 ) ? 1 : 0;
+      const int a1 = ( axis == 2 ) ? 1 : 2;
+      const int i = lane & 3;
+      const bool moved = ( lane < 4 ) == shiftedFirst;
+      for( int d = 0; d < 3; ++d )
+      {
+        double cd = lo[ d ];
+        if( d == axis && ( face & 1 ) )
+          cd += h[ d ];
+        if( d == a0 && ( i & 1 ) )
+          cd += h[ d ];
+        if( d == a1 && ( i & 2 ) )
+          cd += h[ d ];
+        xn[ d ] = moved ? cd - v[ d ] : cd;
+      }
     }
 
     // node `lane` of upwindPolygon3d( face, v ) for the cell with lower corner lo (same arithmetic as vofx::flux)

@@ -136,4 +136,44 @@ namespace vofx
     }
   }
 
+  // the time factors of a step are the same for every face: evaluate them once per thread ...
+  VOFX_HD inline void velocity_time_factors ( const Velocity &vel, double time, double *tf )
+  {
+    for( int a = 0; a < 3; ++a )
+      tf[ a ] = ( vel.timeKind[ a ] == 1 ) ? det_cospi( time / vel.period[ a ] ) : 1.0;
+  }
+
+  // ... and use them here: the same operations as face_velocity with det_cospi( time / period ) already evaluated
+  VOFX_HD inline void face_velocity_tf ( const Grid &g, const Velocity &vel, const int *ijk, int face, const double *tf, double *v )
+  {
+    if( vel.faces )
+    {
+      const long long c = cell_index( g, ijk );
+      for( int a = 0; a < 3; ++a )
+        v[ a ] = ( a < g.dim ) ? vel.faces[ ( c * 2 * g.dim + face ) * g.dim + a ] : 0.0;
+      return;
+    }
+    const int fa = face >> 1;
+    const int kindOfFaceAxis = ( face & 1 ) ? 2 : 1;
+    for( int a = 0; a < 3; ++a )
+    {
+      v[ a ] = 0.0;
+      if( a >= g.dim || vel.nterms[ a ] == 0 )
+        continue;
+      double sum = 0.0;
+      for( int r = 0; r < vel.nterms[ a ]; ++r )
+      {
+        double term = vel.tab[ a ][ r ][ 0 ][ fa == 0 ? kindOfFaceAxis : 0 ][ ijk[ 0 ] + g.g0[ 0 ] ];
+        term = term * vel.tab[ a ][ r ][ 1 ][ fa == 1 ? kindOfFaceAxis : 0 ][ ijk[ 1 ] + g.g0[ 1 ] ];
+        if( g.dim == 3 )
+          term = term * vel.tab[ a ][ r ][ 2 ][ fa == 2 ? kindOfFaceAxis : 0 ][ ijk[ 2 ] + g.g0[ 2 ] ];
+        sum = ( r == 0 ) ? term : sum + term;
+      }
+      double va = sum * vel.coef[ a ];
+      if( vel.timeKind[ a ] == 1 )
+        va = va * tf[ a ];
+      v[ a ] = va;
+    }
+  }
+
 } // namespace vofx

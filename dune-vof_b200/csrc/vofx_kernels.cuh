@@ -1506,11 +1506,28 @@ namespace vofx
   };
 
   template< int DIM >
+  __device__ __forceinline__ void face_motion_rest ( const Grid &g, int face, double dt, FaceMotion &m );
+
+  // with the time factors of the step already evaluated (velocity_time_factors)
+  template< int DIM >
+  __device__ __forceinline__ void face_motion_tf ( const Grid &g, const Velocity &velocity, const int *ijk, int face, const double *tf, double dt, FaceMotion &m )
+  {
+    face_velocity_tf( g, velocity, ijk, face, tf, m.v );
+    face_motion_rest< DIM >( g, face, dt, m );
+  }
+
+  template< int DIM >
   __device__ __forceinline__ void face_motion ( const Grid &g, const Velocity &velocity, const int *ijk, int face, double time, double dt, FaceMotion &m )
+  {
+    face_velocity( g, velocity, ijk, face, time, m.v );
+    face_motion_rest< DIM >( g, face, dt, m );
+  }
+
+  template< int DIM >
+  __device__ __forceinline__ void face_motion_rest ( const Grid &g, int face, double dt, FaceMotion &m )
   {
     double outerNormal[ 3 ] = { 0.0, 0.0, 0.0 };
     outerNormal[ face >> 1 ] = ( face & 1 ) ? 1.0 : -1.0;
-    face_velocity( g, velocity, ijk, face, time, m.v );
     const double faceVol = face_measure_of( g, face );
     double nv = 0.0;
 #pragma unroll
@@ -1747,8 +1764,8 @@ namespace vofx
   {
     double v[ 6 ][ 3 ];
     double vN[ 6 ], sf[ 6 ], selfc[ 6 ];
-    unsigned char flagNb[ 6 ], hasNb[ 6 ], clip[ 6 ], hasSelf[ 6 ], hasNbc[ 6 ];
-    unsigned char pad[ 2 ];
+    unsigned char flagNb[ 6 ], hasNb[ 6 ], clip[ 6 ], hasSelf[ 6 ], hasNbc[ 6 ], shiftedFirst[ 6 ];
+    unsigned char pad[ 12 ];
     double bankPad[ 1 ];
   };
   static_assert( sizeof( FaceScratch ) % 8 == 0 && ( sizeof( FaceScratch ) / 8 ) % 2 == 1, "FaceScratch stride must be an odd number of doubles" );
@@ -1757,7 +1774,7 @@ namespace vofx
 #define VOFX_FLUX_BLOCKS_PER_SM 4
 #endif
   template< int DIM_ >
-  __global__ void __launch_bounds__( 128, VOFX_FLUX_BLOCKS_PER_SM ) k_flux_cell3 ( Grid g, const Velocity *__restrict__ velocity, const double *__restrict__ hs,
+  __global__ void __launch_bounds__( 128, VOFX_FLUX_BLOCKS_PER_SM ) k_flux_cell3 ( Grid g, const Velocity velocity, const double *__restrict__ hs,
                                                               const unsigned char *__restrict__ flags, const int *__restrict__ mixedList,
                                                               StepState *state, int capacity, FluxRecord *__restrict__ records,
                                                               int *__restrict__ tasks, int taskCapacity, const coop::ClipCase *__restrict__ clipTable,
@@ -1781,6 +1798,8 @@ namespace vofx
     const double time = timeOverride ? *timeOverride : state->time;
     const double dt = dtOverride ? *dtOverride : state->dt;
     const double volume = cell_volume( g );
+    double tf[ 3 ];
+    velocity_time_factors( velocity, time, tf );
     const int lane = threadIdx.x % LANES;
     const int group = threadIdx.x / LANES;
     const unsigned groupMask = 0xffu << ( ( threadIdx.x & 31 ) - lane );
@@ -1809,7 +1828,7 @@ namespace vofx
           hasNb = true;
           flagNb = cell_exists( g, nb ) ? flags[ cell_index( g, nb ) ] : (unsigned char) 99;
           FaceMotion m;
-          face_motion< DIM >( g, *velocity, ijk, face, time, dt, m );
+          face_motion_tf< DIM >( g, velocity, ijk, face, tf, dt, m );
           sf = m.sf;
           F.v[ face ][ 0 ] = m.v[ 0 ];
           F.v[ face ][ 1 ] = m.v[ 1 ];
@@ -1820,6 +1839,8 @@ namespace vofx
             needClip = true;
             hasSelf = true;
             hasNbc = ( flagNb == 3 ) || ( flagNb == 0 ) || is_mixed( flagNb );
+            const double lo[ 3 ] = { cell_lower( g, 0, ijk[ 0 ] ), cell_lower( g, 1, ijk[ 1 ] ), cell_lower( g, 2, ijk[ 2 ] ) };
+            F.shiftedFirst[ face ] = coop::upwind_shifted_first( lo, g.h, face, m.v ) ? 1 : 0;
           }
           if( flagNb == 3 && m.vn < 0 )
           {
@@ -1881,7 +1902,7 @@ namespace vofx
         {
           const double v[ 3 ] = { F.v[ face ][ 0 ], F.v[ face ][ 1 ], F.v[ face ][ 2 ] };
           double xn[ 3 ];
-          coop::upwind_node( lane, lo, g.h, face, v, xn );
+          coop::upwind_node_oriented( lane, lo, g.h, face, v, F.shiftedFirst[ face ] != 0, xn );
           coop::clip_phase_classify( lane, S, xn, H );
           __syncwarp( groupMask );
           const coop::ClipCase *cs;

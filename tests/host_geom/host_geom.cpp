@@ -2,6 +2,7 @@
 // The same functions run on the GPU in the product; compiling them with g++ lets the CPU test-suite check their
 // logic bit-for-bit against the oracle where no GPU exists.  The product never loads this library.
 #include <cstdint>
+#include <cstring>
 
 #include "vofx_geom2d.cuh"
 #include "vofx_geom3d.cuh"
@@ -125,9 +126,12 @@ extern "C"
     coop::ClipScratch S;
     for( int lane = 0; lane < 8; ++lane )
     {
-      double xn[ 3 ];
+      double xn[ 3 ], xo[ 3 ];
       coop::upwind_node( lane, lo, h, face, v, xn );
-      coop::clip_phase_classify( lane, S, xn, H );
+      coop::upwind_node_oriented( lane, lo, h, face, v, coop::upwind_shifted_first( lo, h, face, v ), xo );
+      if( std::memcmp( xn, xo, sizeof( xn ) ) != 0 )
+        return 3;
+      coop::clip_phase_classify( lane, S, xo, H );
     }
     const coop::ClipCase *cs = nullptr;
     int status = 0;
