@@ -164,10 +164,21 @@ def main():
     if args.impl == "reference":
         return run_reference_arm(args)
 
+    # stdout must carry exactly ONE JSON line: libraries that print there (NCCL's version banner at NCCL_DEBUG >= VERSION)
+    # are sent to stderr for the duration of the run; the saved descriptor is restored for the final print
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(line, flush=True)
+
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
-        print(json.dumps({"error": "no CUDA device: vofx has no CPU fallback"}))
+        emit(json.dumps({"error": "no CUDA device: vofx has no CPU fallback"}))
         return 2
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -191,7 +202,8 @@ def main():
     K = max(1, args.steps)
     n_global = (N_SIDE, N_SIDE, N_SIDE * world)
     h = (1.0 / N_SIDE,) * 3
-    slab = SlabAlgorithm(n_global, rank, world, CFL, EPS, ops.RECON_YOUNGS, h=h, device=local_rank)
+    slab = SlabAlgorithm(n_global, rank, world, CFL, EPS, ops.RECON_YOUNGS, h=h, device=local_rank,
+                         overlap=os.environ.get("VOFX_NO_OVERLAP", "0") != "1")
     grid = slab.grid
     grid.set_velocity_builtin(ops.PROB_LEVEQUE)
     grid.use_current_stream()
@@ -338,7 +350,7 @@ def main():
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
     }
-    print(json.dumps(line))
+    emit(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

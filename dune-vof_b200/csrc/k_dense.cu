@@ -7,12 +7,12 @@ namespace vofx
   namespace launch
   {
     void flag_rows ( int dim, int blocks, cudaStream_t s, Grid g, const double *u, double eps, unsigned char *flags, int *mixedList, int *slot,
-                     int capacity, StepState *state, int compact, int rowsPerBlock )
+                     int capacity, StepState *state, int compact, int rowsPerBlock, int rowBegin, int rowEnd )
     {
       if( dim == 2 )
-        k_flag_rows< 2 ><<< blocks, 128, 0, s >>>( g, u, eps, flags, mixedList, slot, capacity, state, compact, rowsPerBlock );
+        k_flag_rows< 2 ><<< blocks, 128, 0, s >>>( g, u, eps, flags, mixedList, slot, capacity, state, compact, rowsPerBlock, rowBegin, rowEnd );
       else
-        k_flag_rows< 3 ><<< blocks, 128, 0, s >>>( g, u, eps, flags, mixedList, slot, capacity, state, compact, rowsPerBlock );
+        k_flag_rows< 3 ><<< blocks, 128, 0, s >>>( g, u, eps, flags, mixedList, slot, capacity, state, compact, rowsPerBlock, rowBegin, rowEnd );
     }
     void flag_compact ( int dim, int blocks, cudaStream_t s, Grid g, const double *u, double eps, unsigned char *flags, int *mixedList, int *slot,
                         int capacity, StepState *state, int compact )

@@ -205,19 +205,34 @@ namespace
 
   // ---- launches -------------------------------------------------------------------------------------------------
 
-  int launchFlag ( vofx_ctx *ctx, const double *u, double eps, unsigned char *flags, bool compact )
+  bool flagByRows ( const vofx_ctx *ctx, const double *u, const unsigned char *flags )
+  {
+    return ( ctx->grid.ns[ 0 ] & 3 ) == 0 && ( reinterpret_cast< uintptr_t >( u ) & 15 ) == 0 && ( reinterpret_cast< uintptr_t >( flags ) & 3 ) == 0;
+  }
+
+  // flags (+ mixed list) of the storage layers [ layer0, layer1 ) along the last axis; the whole box by default
+  int launchFlag ( vofx_ctx *ctx, const double *u, double eps, unsigned char *flags, bool compact, int layer0 = 0, int layer1 = -1 )
   {
     const Grid &g = ctx->grid;
+    const int nLayers = g.ns[ g.dim - 1 ];
+    if( layer1 < 0 )
+      layer1 = nLayers;
+    if( layer0 >= layer1 )
+      return VOFX_OK;
     profBegin( ctx );
-    if( ( g.ns[ 0 ] & 3 ) == 0 && ( reinterpret_cast< uintptr_t >( u ) & 15 ) == 0 && ( reinterpret_cast< uintptr_t >( flags ) & 3 ) == 0 )
+    if( flagByRows( ctx, u, flags ) )
     {
       // row kernel: blocks of 128 threads walk 4 rows each (grid >> 148 SMs x resident blocks on every production size)
-      const int nRows = g.ns[ 1 ] * g.ns[ 2 ];
+      const int rowsPerLayer = ( g.dim == 3 ) ? g.ns[ 1 ] : 1;
+      const int rowBegin = layer0 * rowsPerLayer, rowEnd = layer1 * rowsPerLayer;
+      const int nRows = rowEnd - rowBegin;
       const int rowsPerBlock = ( nRows >= 8 * ctx->numSMs * 16 ) ? 4 : 1;
       const int blocks = ( nRows + rowsPerBlock - 1 ) / rowsPerBlock;
-      launch::flag_rows( g.dim, blocks, ctx->stream, g, u, eps, flags, ctx->mixedList, ctx->slot, ctx->capacity, ctx->state, compact ? 1 : 0, rowsPerBlock );
+      launch::flag_rows( g.dim, blocks, ctx->stream, g, u, eps, flags, ctx->mixedList, ctx->slot, ctx->capacity, ctx->state, compact ? 1 : 0, rowsPerBlock, rowBegin, rowEnd );
       return checkLaunch( ctx, "k_flag_compact" );
     }
+    if( layer0 != 0 || layer1 != nLayers )
+      return fail( VOFX_ERR_ARGUMENT, "partial flagging needs the row kernel (row length a multiple of 4, aligned arrays)" );
     const long long quads = ( g.cells + 3 ) / 4;
     const int blocks = gridBlocks( ctx, quads, 256, 8 );
     launch::flag_compact( g.dim, blocks, ctx->stream, g, u, eps, flags, ctx->mixedList, ctx->slot, ctx->capacity, ctx->state, compact ? 1 : 0 );
@@ -968,6 +983,43 @@ extern "C"
     VOFX_CUDA( cudaMemcpyAsync( ctx->state, &init, sizeof( init ), cudaMemcpyHostToDevice, ctx->stream ) );
     VOFX_CUDA( cudaStreamSynchronize( ctx->stream ) );
     return VOFX_OK;
+  }
+
+  // one loop pass in three phases so that a multi-GPU driver can overlap its communication (decomposition.py):
+  //   0  flags of the interior layers (no halo value is read)            -- while the colour halos are in flight
+  //   1  flags of the layers next to / inside the halos, reconstruction, [curvature,] fluxes (time-step estimate)
+  //   2  update                                                         -- while the time-step estimate is MIN-reduced
+  int vofx_step_phase ( vofx_ctx *ctx, const vofx_step_params *p, double *u, uint8_t *flags, double *halfspaces, double *kappa, int phase )
+  {
+    if( !ctx || !p || !u || !flags || !halfspaces || ( p->with_curvature && !kappa ) || phase < 0 || phase > 2 )
+      return fail( VOFX_ERR_ARGUMENT, "bad argument" );
+    int rc = setDevice( ctx );
+    rc = rc ? rc : requireVelocity( ctx );
+    if( rc )
+      return rc;
+    const Grid &g = ctx->grid;
+    const int nLayers = g.ns[ g.dim - 1 ];
+    // layers whose flags depend on halo values: the halos themselves and the first / last owned layer
+    const bool split = ctx->desc.halo > 0 && flagByRows( ctx, u, flags ) && g.own1 - g.own0 > 2;
+    const int in0 = split ? g.own0 + 1 : 0, in1 = split ? g.own1 - 1 : 0;
+    if( phase == 0 )
+      return split ? launchFlag( ctx, u, p->eps, flags, true, in0, in1 ) : VOFX_OK;
+    if( phase == 1 )
+    {
+      // algorithm.hh:75-81: flagOperator, reconstructionOperator, evolutionOperator
+      if( split )
+      {
+        rc = launchFlag( ctx, u, p->eps, flags, true, 0, in0 );
+        rc = rc ? rc : launchFlag( ctx, u, p->eps, flags, true, in1, nLayers );
+      }
+      else
+        rc = launchFlag( ctx, u, p->eps, flags, true );
+      rc = rc ? rc : launchReconstruct( ctx, p->reconstruction, u, flags, halfspaces, p->max_iterations );
+      if( !rc && p->with_curvature )
+        rc = launchCurvature( ctx, u, halfspaces, flags, kappa, nullptr, true );
+      return rc ? rc : launchFlux( ctx, halfspaces, flags, nullptr, nullptr );
+    }
+    return launchUpdate( ctx, flags, u, true );   // uh.axpy( 1.0, update ), algorithm.hh:83
   }
 
   int vofx_step_local ( vofx_ctx *ctx, const vofx_step_params *p, double *u, uint8_t *flags, double *halfspaces, double *kappa )

@@ -157,11 +157,11 @@ namespace vofx
   template< int DIM >
   __global__ void __launch_bounds__( 128 ) k_flag_rows ( Grid g, const double *__restrict__ u, double eps, unsigned char *__restrict__ flags,
                                                           int *__restrict__ mixedList, int *__restrict__ slot, int capacity, StepState *state,
-                                                          int compact, int rowsPerBlock )
+                                                          int compact, int rowsPerBlock, int rowBegin, int rowEnd )
   {
     const int nx = g.ns[ 0 ];
     const int ny = g.ns[ 1 ];
-    const int nRows = g.ns[ 1 ] * g.ns[ 2 ];
+    const int nRows = rowEnd;            // rows [ rowBegin, rowEnd ) of the ns[1] * ns[2] rows of the storage box
     const int quadsPerRow = nx >> 2;
     const int quadsRounded = ( quadsPerRow + 31 ) & ~31;
     const int lane = threadIdx.x & 31;
@@ -170,7 +170,7 @@ namespace vofx
 
     for( int r = 0; r < rowsPerBlock; ++r )
     {
-      const int row = blockIdx.x * rowsPerBlock + r;
+      const int row = rowBegin + blockIdx.x * rowsPerBlock + r;
       if( row >= nRows )
         break;
       const int j = ( DIM == 3 ) ? row % ny : row;

@@ -12,7 +12,7 @@ namespace vofx
   {
     // k_dense.cu
     void flag_rows ( int dim, int blocks, cudaStream_t s, Grid g, const double *u, double eps, unsigned char *flags, int *mixedList, int *slot,
-                     int capacity, StepState *state, int compact, int rowsPerBlock );
+                     int capacity, StepState *state, int compact, int rowsPerBlock, int rowBegin, int rowEnd );
     void flag_compact ( int dim, int blocks, cudaStream_t s, Grid g, const double *u, double eps, unsigned char *flags, int *mixedList, int *slot,
                         int capacity, StepState *state, int compact );
     void compact_flags ( int dim, int blocks, cudaStream_t s, Grid g, const unsigned char *flags, int *mixedList, int *slot, int capacity, StepState *state );

@@ -64,7 +64,7 @@ class SlabAlgorithm:
     of the time-step estimate -> finish."""
 
     def __init__(self, n_global, rank, world, cfl, eps, reconstruction_kind=0, max_iterations=10, origin=None, h=None,
-                 device=None, group=None, with_curvature=False):
+                 device=None, group=None, with_curvature=False, overlap=True):
         import torch
         from . import operators as ops
         self.rank, self.world, self.group = rank, world, group
@@ -82,6 +82,8 @@ class SlabAlgorithm:
         self.exchanger = HaloExchanger(n_last, halo, rank, world, group)
         self.layer_cells = self.grid.cells // (n_last + 2 * halo)
         self._dt_est = None
+        self._comm = None
+        self.overlap = overlap
         if world > 1:
             ptr = self.grid._L.vofx_dt_est_device(self.grid._ctx)
             self._dt_est = torch.as_tensor(_DevicePtr(ptr), device=self.grid.device)
@@ -98,16 +100,38 @@ class SlabAlgorithm:
         self.alg.begin(time, dt)
 
     def step(self, uh):
+        """one loop pass: the colour halos travel while the interior layers are flagged, the time-step estimate is
+        MIN-reduced while the update runs (vofx_step_phase, include/vofx.h)"""
+        import torch
         import torch.distributed as dist
         from .lib import check
         g, a = self.grid, self.alg
         if self.world == 1:
             a.step(uh)
             return
-        self.exchanger.exchange(self.layers(uh))
         kap = C.c_void_p(a.curvature.data_ptr()) if a.curvature is not None else C.c_void_p(0)
-        check(g._L.vofx_step_local(g._ctx, C.byref(a.params), g.pc(uh), g.pf(a.flags), g.ph(a.reconstructions), kap))
-        dist.all_reduce(self._dt_est, op=dist.ReduceOp.MIN, group=self.group)
+        args = (g._ctx, C.byref(a.params), g.pc(uh), g.pf(a.flags), g.ph(a.reconstructions), kap)
+        if not self.overlap:
+            self.exchanger.exchange(self.layers(uh))
+            check(g._L.vofx_step_local(*args))
+            dist.all_reduce(self._dt_est, op=dist.ReduceOp.MIN, group=self.group)
+            check(g._L.vofx_step_finish(g._ctx, C.byref(a.params)))
+            return
+        main = torch.cuda.current_stream(g.device)
+        if self._comm is None:
+            self._comm = torch.cuda.Stream(device=g.device)
+        comm = self._comm
+        comm.wait_stream(main)                                   # the previous pass has updated the owned layers
+        with torch.cuda.stream(comm):
+            self.exchanger.exchange(self.layers(uh))
+        check(g._L.vofx_step_phase(*args, 0))                    # interior flags: no halo value is read
+        main.wait_stream(comm)
+        check(g._L.vofx_step_phase(*args, 1))                    # boundary flags, reconstruction, fluxes
+        comm.wait_stream(main)
+        with torch.cuda.stream(comm):
+            dist.all_reduce(self._dt_est, op=dist.ReduceOp.MIN, group=self.group)
+        check(g._L.vofx_step_phase(*args, 2))                    # update
+        main.wait_stream(comm)
         check(g._L.vofx_step_finish(g._ctx, C.byref(a.params)))
 
     def state(self):

@@ -22,7 +22,7 @@ SYMBOLS = [
     "vofx_last_error", "vofx_create", "vofx_destroy", "vofx_set_stream", "vofx_cells", "vofx_velocity_clear",
     "vofx_velocity_set_component", "vofx_velocity_set_factor", "vofx_velocity_set_faces", "vofx_velocity_builtin", "vofx_face_velocity",
     "vofx_flag", "vofx_reconstruct", "vofx_evolve", "vofx_axpy", "vofx_curvature", "vofx_step_begin", "vofx_step",
-    "vofx_step_state", "vofx_step_local", "vofx_step_finish", "vofx_dt_est_device", "vofx_flag_host",
+    "vofx_step_state", "vofx_step_local", "vofx_step_phase", "vofx_step_finish", "vofx_dt_est_device", "vofx_flag_host",
     "vofx_reconstruct_host", "vofx_evolve_host", "vofx_curvature_host", "vofx_step_host", "vofx_host_transfer_bytes", "vofx_color_upload",
     "vofx_step_resident", "vofx_color_download", "vofx_interface", "vofx_interface_host", "vofx_interface_fetch", "vofx_init",
     "vofx_test_locate", "vofx_test_flux", "vofx_test_interface", "vofx_launch_count", "vofx_profile_enable",
@@ -96,6 +96,7 @@ def load():
     L.vofx_step_begin.argtypes = [vp, C.c_double, C.c_double]
     L.vofx_step.argtypes = [vp, C.POINTER(StepParams), dp, bp, dp, dp]
     L.vofx_step_local.argtypes = [vp, C.POINTER(StepParams), dp, bp, dp, dp]
+    L.vofx_step_phase.argtypes = [vp, C.POINTER(StepParams), dp, bp, dp, dp, C.c_int]
     L.vofx_step_finish.argtypes = [vp, C.POINTER(StepParams)]
     L.vofx_dt_est_device.argtypes = [vp]
     L.vofx_dt_est_device.restype = C.c_void_p

@@ -157,6 +157,10 @@ int vofx_step_state ( vofx_ctx *ctx, double *time, double *dt, double *dt_est, i
  * vofx_step_local() and vofx_step_finish() (see dune_vof_b200/host/decomposition.py) */
 int vofx_step_local ( vofx_ctx *ctx, const vofx_step_params *params, double *u, uint8_t *flags, double *halfspaces, double *kappa );
 int vofx_step_finish ( vofx_ctx *ctx, const vofx_step_params *params );
+/* vofx_step_local in three phases, so that the halo exchange (during phase 0) and the MIN-reduction of the time-step
+ * estimate (during phase 2) overlap with the kernels: 0 flags of the interior layers, 1 flags next to the halos +
+ * reconstruction + fluxes, 2 update.  Phases 0,1,2 in this order are equivalent to vofx_step_local. */
+int vofx_step_phase ( vofx_ctx *ctx, const vofx_step_params *params, double *u, uint8_t *flags, double *halfspaces, double *kappa, int phase );
 double *vofx_dt_est_device ( vofx_ctx *ctx );
 
 /* ---- HOST-buffer variants: what the DUNE-side containers (std::vector based DataSet, dataset.hh:26-87) bind to.
