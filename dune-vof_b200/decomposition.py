@@ -134,5 +134,23 @@ class SlabAlgorithm:
         main.wait_stream(comm)
         check(g._L.vofx_step_finish(g._ctx, C.byref(a.params)))
 
+    def capture(self, uh):
+        """capture one loop pass (kernels, halo exchange, MIN reduction, both streams) into a CUDA graph; replay() then
+        costs one launch per pass on the host.  The pass only reads device-resident state (time, dt, counters), so the
+        captured work is the same every step."""
+        import torch
+        g = self.grid
+        self._graph_stream = torch.cuda.Stream(device=g.device)
+        self._graph = torch.cuda.CUDAGraph()
+        torch.cuda.synchronize(g.device)
+        with torch.cuda.graph(self._graph, stream=self._graph_stream):
+            g.use_current_stream()
+            self.step(uh)
+        torch.cuda.synchronize(g.device)
+        return self._graph
+
+    def replay(self):
+        self._graph.replay()
+
     def state(self):
         return self.alg.state()
