@@ -214,9 +214,20 @@ namespace
   int launchFlag ( vofx_ctx *ctx, const double *u, double eps, unsigned char *flags, bool compact, int layer0 = 0, int layer1 = -1 )
   {
     const Grid &g = ctx->grid;
-    const int nLayers = g.ns[ g.dim - 1 ];
+    const int la = g.dim - 1;
+    const int nLayers = g.ns[ la ];
     if( layer1 < 0 )
       layer1 = nLayers;
+    const bool whole = ( layer0 == 0 && layer1 == nLayers );
+    if( flagByRows( ctx, u, flags ) )
+    {
+      // storage layers outside the global domain (halos of the first / last slab) hold no cells: they are never read,
+      // so a slab's arrays may alias a window of one contiguous global array (PipelinedAlgorithm, decomposition.py)
+      const int dom0 = ( -g.g0[ la ] > 0 ) ? -g.g0[ la ] : 0;
+      const int dom1 = ( g.ng[ la ] - g.g0[ la ] < nLayers ) ? g.ng[ la ] - g.g0[ la ] : nLayers;
+      layer0 = layer0 > dom0 ? layer0 : dom0;
+      layer1 = layer1 < dom1 ? layer1 : dom1;
+    }
     if( layer0 >= layer1 )
       return VOFX_OK;
     profBegin( ctx );
@@ -231,7 +242,7 @@ namespace
       launch::flag_rows( g.dim, blocks, ctx->stream, g, u, eps, flags, ctx->mixedList, ctx->slot, ctx->capacity, ctx->state, compact ? 1 : 0, rowsPerBlock, rowBegin, rowEnd );
       return checkLaunch( ctx, "k_flag_compact" );
     }
-    if( layer0 != 0 || layer1 != nLayers )
+    if( !whole )
       return fail( VOFX_ERR_ARGUMENT, "partial flagging needs the row kernel (row length a multiple of 4, aligned arrays)" );
     const long long quads = ( g.cells + 3 ) / 4;
     const int blocks = gridBlocks( ctx, quads, 256, 8 );

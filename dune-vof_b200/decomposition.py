@@ -154,3 +154,128 @@ class SlabAlgorithm:
 
     def state(self):
         return self.alg.state()
+
+
+class PipelinedAlgorithm:
+    """The time loop on ONE GPU with the grid cut into `chunks` z-slabs that share the caller's contiguous arrays.
+
+    Every slab is a context of its own (with halo layers that alias the neighbouring slab's owned layers, so nothing is
+    copied) on a stream of its own: while the band kernels of one slab run (latency-bound, few resident warps), the
+    dense flag pass of the next slab streams through HBM.  Slabs only meet twice per pass: before the in-place update
+    (all reads of the old colour function are done) and for the MIN of the time-step estimates.  The result is the
+    single-context result bit for bit (the slab machinery is the multi-GPU one, tests/test_gpu_multirank.py).
+
+    MEASURED (B200, 512^3 sphere, graph replay, tools/pipeline_probe.py): 1.062 / 1.092 / 1.054 / 1.048 ms per step for
+    1 / 2 / 4 / 8 chunks -- no gain: the band kernels fill the register file and shared memory of every SM (9 blocks x
+    23.7 KB, 55 K registers), so the flag pass of the next slab gets one block per SM and streams at a fraction of the
+    HBM rate.  bench.py therefore runs the plain single-context loop; the class stays as the tested way to run several
+    contexts on windows of one contiguous array."""
+
+    def __init__(self, n, cfl, eps, reconstruction_kind=0, chunks=2, origin=None, h=None, device=None, max_iterations=10):
+        import torch
+        from . import operators as ops
+        self.n = tuple(int(x) for x in n)
+        self.dim = len(self.n)
+        self.chunks = int(chunks)
+        halo = HALO_WIDTH[int(reconstruction_kind)]
+        self.grids, self.params, self.offsets = [], [], []
+        self.layer = 1
+        for x in self.n[:-1]:
+            self.layer *= x
+        for k in range(self.chunks):
+            lo_last, n_last = split_last_axis(self.n[-1], self.chunks, k)
+            if n_last < halo + 2:
+                raise ValueError("chunk thinner than its halo")
+            lo = [0] * self.dim
+            lo[-1] = lo_last
+            n_local = list(self.n)
+            n_local[-1] = n_last
+            g = ops.CartesianGrid(self.n, origin=origin, h=h, lo=lo, n_local=n_local, halo=halo, device=device)
+            self.grids.append(g)
+            self.params.append(ops.StepParams(int(reconstruction_kind), int(max_iterations), float(eps), float(cfl), 0))
+            self.offsets.append((lo_last - halo) * self.layer)         # first storage cell of the slab in the global arrays
+        self.device = self.grids[0].device
+        self.cells = self.layer * self.n[-1]
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in range(self.chunks)]
+        self._dt = [torch.as_tensor(_DevicePtr(g._L.vofx_dt_est_device(g._ctx)), device=self.device) for g in self.grids]
+        for g, st in zip(self.grids, self.streams):
+            with torch.cuda.stream(st):
+                g.use_current_stream()
+        self.flags = torch.zeros(self.cells, dtype=torch.uint8, device=self.device)
+        self.reconstructions = torch.zeros(self.cells, self.dim + 1, dtype=torch.float64, device=self.device)
+        self._graph = None
+
+    def set_velocity_builtin(self, problem):
+        for g in self.grids:
+            g.set_velocity_builtin(problem)
+
+    def begin(self, time=0.0, dt=0.0):
+        from .lib import check
+        for g in self.grids:
+            check(g._L.vofx_step_begin(g._ctx, float(time), float(dt)))
+
+    def _args(self, k, uh):
+        off = self.offsets[k]
+        g = self.grids[k]
+        return (g._ctx, C.byref(self.params[k]), C.c_void_p(uh.data_ptr() + 8 * off), C.c_void_p(self.flags.data_ptr() + off),
+                C.c_void_p(self.reconstructions.data_ptr() + 8 * (self.dim + 1) * off), C.c_void_p(0))
+
+    def step(self, uh):
+        import torch
+        from .lib import check
+        if uh.numel() != self.cells or uh.device != self.device or not uh.is_contiguous():
+            raise ValueError("expected the contiguous colour function of the whole grid on the algorithm's device")
+        main = torch.cuda.current_stream(self.device)
+        L = self.grids[0]._L
+        for k, st in enumerate(self.streams):                    # flags, reconstruction, fluxes of every slab
+            st.wait_stream(main)
+            with torch.cuda.stream(st):
+                args = self._args(k, uh)
+                check(L.vofx_step_phase(*args, 0))
+                check(L.vofx_step_phase(*args, 1))
+        for st in self.streams:                                  # nobody reads the old colour function any more
+            main.wait_stream(st)
+        for k, st in enumerate(self.streams):                    # in-place update of the owned cells
+            st.wait_stream(main)
+            with torch.cuda.stream(st):
+                check(L.vofx_step_phase(*self._args(k, uh), 2))
+        for st in self.streams:
+            main.wait_stream(st)
+        m = self._dt[0]                                          # gridView().comm().min( dtEst ), evolution.hh:75
+        for d in self._dt[1:]:
+            torch.minimum(m, d, out=m)
+        for d in self._dt[1:]:
+            d.copy_(m)
+        for k, g in enumerate(self.grids):
+            check(L.vofx_set_stream(g._ctx, C.c_void_p(main.cuda_stream)))
+            check(L.vofx_step_finish(g._ctx, C.byref(self.params[k])))
+            check(L.vofx_set_stream(g._ctx, C.c_void_p(self.streams[k].cuda_stream)))
+
+    def capture(self, uh):
+        import torch
+        self._graph_stream = torch.cuda.Stream(device=self.device)
+        self._graph = torch.cuda.CUDAGraph()
+        torch.cuda.synchronize(self.device)
+        with torch.cuda.graph(self._graph, stream=self._graph_stream):
+            self.step(uh)
+        torch.cuda.synchronize(self.device)
+        return self._graph
+
+    def replay(self):
+        self._graph.replay()
+
+    def state(self):
+        from .operators import StepResult
+        g = self.grids[0]
+        t, dt, de, m = C.c_double(), C.c_double(), C.c_double(), C.c_int64()
+        from .lib import check
+        check(g._L.vofx_step_state(g._ctx, C.byref(t), C.byref(dt), C.byref(de), C.byref(m)))
+        return StepResult(t.value, dt.value, de.value, m.value)
+
+    @property
+    def launch_count(self):
+        return sum(g.launch_count for g in self.grids)
+
+    def close(self):
+        for g in self.grids:
+            g.close()
