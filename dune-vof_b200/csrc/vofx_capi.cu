@@ -1476,6 +1476,32 @@ extern "C"
     }
   } // namespace
 
+  // measured fp64 rates of this GPU in G operations per second (an FMA counts as ONE operation here):
+  // rates[0] fused multiply-add, rates[1] separate multiply + add (two operations per pair)
+  int vofx_test_fp64_rate ( double *rates )
+  {
+    if( !rates )
+      return fail( VOFX_ERR_ARGUMENT, "null argument" );
+    int rc = requireDevice();
+    if( rc )
+      return rc;
+    cudaDeviceProp prop;
+    VOFX_CUDA( cudaGetDeviceProperties( &prop, 0 ) );
+    DevBuf scratch;
+    rc = scratch.alloc( 64 );
+    if( rc )
+      return rc;
+    const int blocks = prop.multiProcessorCount * 8, iters = 4096, reps = 10;
+    for( int mode = 0; mode < 2; ++mode )
+    {
+      const float ms = launch::fp64_rate( mode, blocks, iters, reps, (double *) scratch.p );
+      const double ops = (double) blocks * 256.0 * iters * 8.0 * reps * ( mode == 0 ? 1.0 : 2.0 );
+      rates[ mode ] = ops / ( ms * 1e-3 ) / 1e9;
+    }
+    VOFX_CUDA( cudaGetLastError() );
+    return VOFX_OK;
+  }
+
   int vofx_test_locate ( int dim, int64_t count, const double *lo, const double *h, const double *normal, const double *fraction, double *halfspaces )
   {
     if( ( dim != 2 && dim != 3 ) || count < 0 || !lo || !h || !normal || !fraction || !halfspaces )

@@ -197,6 +197,10 @@ int vofx_init ( vofx_ctx *ctx, int problem, double time, double *u );
 
 /* ---- geometry primitives on single cells (DEVICE work on small batches; for parity tests) ---------------------
  * arrays are HOST pointers of `count` items: lo[count*dim], h[count*dim], ... */
+/* measured fp64 instruction rates of the current GPU, in 1e9 operations/s: rates[0] fused multiply-add (one operation
+ * each), rates[1] separate multiply and add (the parity contract forbids FMA contraction); the denominators of the
+ * band kernels' fp64 rooflines */
+int vofx_test_fp64_rate ( double *rates );
 int vofx_test_locate ( int dim, int64_t count, const double *lo, const double *h, const double *normal, const double *fraction, double *halfspaces );
 int vofx_test_flux ( int dim, int64_t count, const double *lo, const double *h, const int32_t *face, const double *v, const double *halfspaces, double *flux );
 int vofx_test_interface ( int dim, int64_t count, const double *lo, const double *h, const double *halfspaces, int32_t *nverts, double *centroid, double *measure );
