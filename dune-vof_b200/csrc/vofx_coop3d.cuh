@@ -794,7 +794,18 @@ namespace vofx
               walk_next( sweep, S.walked, S.P[ 2 ], dU[ k - 1 ], dU[ k ] );
           }
         }
-        const SweepBracket &B = walking ? S.walked : C->bracket[ k ];
+        if( !walking )
+        {
+          // stage the tabulated descriptor (56 B in global memory) in the scratch: the phases below read it many times
+          VOFX_LANES( G, L, lane )
+          {
+            const unsigned *src = reinterpret_cast< const unsigned * >( &C->bracket[ k ] );
+            unsigned *dst = reinterpret_cast< unsigned * >( &S.walked );
+            for( int w = lane; w < int( sizeof( SweepBracket ) / sizeof( unsigned ) ); w += L )
+              dst[ w ] = src[ w ];
+          }
+        }
+        const SweepBracket &B = S.walked;
         if( !B.ok )
           return false;                                  // undefined in the reference: left to the serial kernel (NaN)
         const int cur = k & 1;

@@ -2051,24 +2051,40 @@ namespace vofx
         continue;                                  // not owned: another rank updates it
       const long long X = cell_index( g, x );
       const unsigned char flagX = flags[ X ];
+      // The six neighbour records of X are fetched level by level (flags, slots, records: independent loads in flight)
+      // and only then summed in the reference's order; the dependent flag -> slot -> record chains used to run one after
+      // the other (long-scoreboard stalls: 16 of 22 cycles per issue).  k runs over z-,y-,x-,x+,y+,z+.
+      long long Yk[ NFACES ];
+      bool mixedK[ NFACES ];
+      unsigned char flagK[ NFACES ];
+#pragma unroll
+      for( int k = 0; k < NFACES; ++k )
+      {
+        const int f = gather_face< DIM >( k );
+        int y[ 3 ] = { x[ 0 ], x[ 1 ], x[ 2 ] };
+        y[ f >> 1 ] += ( k < DIM ) ? -1 : 1;
+        const bool exists = cell_exists( g, y );
+        Yk[ k ] = exists ? cell_index( g, y ) : -1;
+      }
+#pragma unroll
+      for( int k = 0; k < NFACES; ++k )
+        flagK[ k ] = ( Yk[ k ] >= 0 ) ? flags[ Yk[ k ] ] : (unsigned char) 0;
       if( lane > 0 )
       {
         if( is_mixed( flagX ) )
           continue;                                // a mixed cell gathers for itself (lane 0 of its own group)
         // is m the first mixed neighbour of X in gather order?
         bool first = true;
+#pragma unroll
         for( int k = 0; k < NFACES; ++k )
         {
-          const int f = gather_face< DIM >( k );
-          int y[ 3 ] = { x[ 0 ], x[ 1 ], x[ 2 ] };
-          y[ f >> 1 ] += ( f & 1 ) ? 1 : -1;
-          if( !cell_exists( g, y ) )
+          if( Yk[ k ] < 0 )
             continue;
-          const long long Y = cell_index( g, y );
-          if( Y == m )
+          if( Yk[ k ] == m )
             break;
-          const int ly = y[ DIM - 1 ];
-          if( is_mixed( flags[ Y ] ) && ly >= g.list0 && ly < g.list1 )
+          const int f = gather_face< DIM >( k );
+          const int ly = x[ DIM - 1 ] + ( ( ( f >> 1 ) == DIM - 1 ) ? ( ( k < DIM ) ? -1 : 1 ) : 0 );
+          if( is_mixed( flagK[ k ] ) && ly >= g.list0 && ly < g.list1 )
           {
             first = false;
             break;
@@ -2078,45 +2094,54 @@ namespace vofx
           continue;
       }
 
+      int slotK[ NFACES ];
+#pragma unroll
+      for( int k = 0; k < NFACES; ++k )
+      {
+        mixedK[ k ] = is_mixed( flagK[ k ] );
+        slotK[ k ] = mixedK[ k ] ? slot[ Yk[ k ] ] : 0;
+      }
+      const int slotX = is_mixed( flagX ) ? slot[ X ] : 0;
+      double nbK[ NFACES ];
+      bool hasK[ NFACES ];
+#pragma unroll
+      for( int k = 0; k < NFACES; ++k )
+      {
+        const int f = gather_face< DIM >( k );
+        const int toward = ( k < DIM ) ? f + 1 : f - 1;   // Y's face towards X: the opposite face of the same axis
+        hasK[ k ] = false;
+        nbK[ k ] = 0.0;
+        if( mixedK[ k ] )
+        {
+          const FluxRecord &r = records[ slotK[ k ] ];
+          hasK[ k ] = ( r.nbMask & ( 1u << toward ) ) != 0;
+          nbK[ k ] = r.nb[ toward ];
+        }
+      }
+
       double acc = 0.0;
       // mixed neighbours with smaller index: z-, y-, x-
+#pragma unroll
       for( int k = 0; k < DIM; ++k )
-      {
-        const int f = gather_face< DIM >( k );
-        int y[ 3 ] = { x[ 0 ], x[ 1 ], x[ 2 ] };
-        y[ f >> 1 ] -= 1;
-        if( !cell_exists( g, y ) )
-          continue;
-        const long long Y = cell_index( g, y );
-        if( !is_mixed( flags[ Y ] ) )
-          continue;
-        const FluxRecord &r = records[ slot[ Y ] ];
-        const int toward = f + 1;                  // Y's face towards X is the upper face of the same axis
-        if( r.nbMask & ( 1u << toward ) )
-          acc += r.nb[ toward ];
-      }
+        if( hasK[ k ] )
+          acc += nbK[ k ];
       if( is_mixed( flagX ) )
       {
-        const FluxRecord &r = records[ slot[ X ] ];
+        const FluxRecord &r = records[ slotX ];
+        const unsigned selfMask = r.selfMask;
+        double selfK[ NFACES ];
+#pragma unroll
         for( int f = 0; f < NFACES; ++f )
-          if( r.selfMask & ( 1u << f ) )
-            acc += r.self[ f ];
+          selfK[ f ] = r.self[ f ];
+#pragma unroll
+        for( int f = 0; f < NFACES; ++f )
+          if( selfMask & ( 1u << f ) )
+            acc += selfK[ f ];
       }
+#pragma unroll
       for( int k = DIM; k < NFACES; ++k )
-      {
-        const int f = gather_face< DIM >( k );
-        int y[ 3 ] = { x[ 0 ], x[ 1 ], x[ 2 ] };
-        y[ f >> 1 ] += 1;
-        if( !cell_exists( g, y ) )
-          continue;
-        const long long Y = cell_index( g, y );
-        if( !is_mixed( flags[ Y ] ) )
-          continue;
-        const FluxRecord &r = records[ slot[ Y ] ];
-        const int toward = f - 1;                  // Y's lower face of the same axis
-        if( r.nbMask & ( 1u << toward ) )
-          acc += r.nb[ toward ];
-      }
+        if( hasK[ k ] )
+          acc += nbK[ k ];
 
       if( accumulate )
       {
