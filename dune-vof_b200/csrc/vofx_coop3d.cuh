@@ -709,18 +709,30 @@ namespace vofx
           S.ds[ rank ] = zi;
         }
 #pragma unroll 1
-        for( int e = lane; e < 24; e += L )
+        for( int e = lane; e < 12; e += L )
         {
+          // edge e = ( a, b ) and its reverse e + 12 = ( b, a ): the reverse direction vector is ( P_a - P_b ) / norm with the
+          // same norm ( squares ); for a non-zero difference that is exactly the negated quotient, for a zero difference
+          // the (signed) zero is divided on vdiv's fast path
           const int a = cube::edgeN0( e ), b = cube::edgeN1( e );
-          double dv[ 3 ];
+          double dv[ 3 ], rv[ 3 ];
           for( int c = 0; c < 3; ++c )
+          {
             dv[ c ] = S.P[ c ][ b ] - S.P[ c ][ a ];
+            rv[ c ] = S.P[ c ][ a ] - S.P[ c ][ b ];
+          }
           const double norm = norm2( dv[ 0 ], dv[ 1 ] );
           if( norm > 0 )
             for( int c = 0; c < 3; ++c )
+            {
               dv[ c ] = vdiv( dv[ c ], norm );
+              rv[ c ] = ( rv[ c ] == 0.0 ) ? vdiv( rv[ c ], norm ) : -dv[ c ];
+            }
           for( int c = 0; c < 3; ++c )
+          {
             S.dv[ c ][ e ] = dv[ c ];
+            S.dv[ c ][ e + 12 ] = rv[ c ];
+          }
         }
 #pragma unroll 1
         for( int f = lane; f < 6; f += L )
@@ -783,9 +795,24 @@ namespace vofx
         }
       }
 
+#if defined( __CUDA_ARCH__ )
+      constexpr int kWords = int( sizeof( SweepBracket ) / sizeof( unsigned ) );
+      constexpr int kPre = ( kWords + L - 1 ) / L;
+      unsigned pre[ kPre ];
+      if( !walking )
+      {
+        const unsigned *src = reinterpret_cast< const unsigned * >( &C->bracket[ 0 ] );
+#pragma unroll
+        for( int q = 0; q < kPre; ++q )
+          pre[ q ] = ( G.lane + q * L < kWords ) ? src[ G.lane + q * L ] : 0u;
+      }
+#endif
+
       double Vd_k = 0.0;
       for( int k = 0; k + 1 < nU; ++k )
       {
+        if( k > 0 )
+          G.sync();                                      // every lane has finished reading the previous descriptor
         if( walking && k > 0 )
         {
           VOFX_LANES( G, L, lane )
@@ -796,14 +823,31 @@ namespace vofx
         }
         if( !walking )
         {
-          // stage the tabulated descriptor (56 B in global memory) in the scratch: the phases below read it many times
+          // stage the tabulated descriptor (56 B in global memory) in the scratch: the phases below read it many times.
+          // Its words were fetched one bracket ahead (the load latency hides behind the previous bracket's arithmetic).
           VOFX_LANES( G, L, lane )
           {
-            const unsigned *src = reinterpret_cast< const unsigned * >( &C->bracket[ k ] );
+#if defined( __CUDA_ARCH__ )
             unsigned *dst = reinterpret_cast< unsigned * >( &S.walked );
-            for( int w = lane; w < int( sizeof( SweepBracket ) / sizeof( unsigned ) ); w += L )
-              dst[ w ] = src[ w ];
+#pragma unroll
+            for( int q = 0; q < kPre; ++q )
+              if( lane + q * L < kWords )
+                dst[ lane + q * L ] = pre[ q ];
+#else
+            (void) lane;
+            S.walked = C->bracket[ k ];
+#endif
           }
+#if defined( __CUDA_ARCH__ )
+          if( k + 1 < 7 )
+          {
+            const unsigned *src = reinterpret_cast< const unsigned * >( &C->bracket[ k + 1 ] );
+#pragma unroll
+            for( int q = 0; q < kPre; ++q )
+              if( G.lane + q * L < kWords )
+                pre[ q ] = src[ G.lane + q * L ];
+          }
+#endif
         }
         const SweepBracket &B = S.walked;
         if( !B.ok )
@@ -950,8 +994,16 @@ namespace vofx
         lower[ d ] = cell_lower( g, d, ijk[ d ] );
         center[ d ] = lower[ d ] + 0.5 * g.h[ d ];
       }
+      // slots 26..31 are the ghosts of wall faces: a cell away from the domain boundary has none (:112-124)
+      bool atWall = false;
+      for( int d = 0; d < 3; ++d )
+      {
+        const int gi = ijk[ d ] + g.g0[ d ];
+        atWall = atWall || gi == 0 || gi == g.ng[ d ] - 1;
+      }
+      const int nSlots = atWall ? 32 : 26;
 #pragma unroll 1
-      for( int round = 0; round * L < 32; ++round )
+      for( int round = 0; round * L < nSlots; ++round )
       {
         VOFX_LANES( G, L, lane )
         {
