@@ -305,6 +305,24 @@ class Algorithm:
             if self.state().time >= end:
                 return self.state()
 
+    def capture(self, uh):
+        """capture one loop pass into a CUDA graph (it only reads device-resident state: time, dt, counters); replay()
+        then costs one host launch per pass -- what small grids need, whose passes are launch-bound (C1: 5 kernels
+        of a few microseconds each).  Not for the 3D Swartz reconstruction (it sizes its buffers from a read-back)."""
+        torch = _torch()
+        g = self.grid
+        self._graph_stream = torch.cuda.Stream(device=g.device)
+        self._graph = torch.cuda.CUDAGraph()
+        torch.cuda.synchronize(g.device)
+        with torch.cuda.graph(self._graph, stream=self._graph_stream):
+            g.use_current_stream()
+            self.step(uh)
+        torch.cuda.synchronize(g.device)
+        return self._graph
+
+    def replay(self):
+        self._graph.replay()
+
     def run_passes(self, uh, passes, time=0.0, dt=0.0):
         self.begin(time, dt)
         self.grid.use_current_stream()
