@@ -16,6 +16,12 @@ namespace vofx
     { k_clear_listed<<< blocks, 256, 0, s >>>( list, count, target ); }
     void copy_list ( int blocks, cudaStream_t s, const int *list, const StepState *state, int capacity, int *out, int *outCount )
     { k_copy_list<<< blocks, 256, 0, s >>>( list, state, capacity, out, outCount ); }
+    void swartz_curvature2 ( int blocks, cudaStream_t s, Grid g, const double *hs, const unsigned char *flags, const int *mixedList, const int *slot,
+                             const StepState *state, int capacity, double *curv1, double *kappa )
+    {
+      k_swartz_curv_local<<< blocks, 128, 0, s >>>( g, hs, flags, mixedList, state, capacity, curv1 );
+      k_swartz_curv_average<<< blocks, 128, 0, s >>>( g, flags, mixedList, slot, state, capacity, curv1, kappa );
+    }
     void swartz2 ( int blocks, cudaStream_t s, Grid g, const double *u, const unsigned char *flags, const int *mixedList, const StepState *state,
                    int capacity, double *hs, int maxIterations )
     { k_swartz< 2 ><<< blocks, 64, 0, s >>>( g, u, flags, mixedList, state, capacity, hs, maxIterations ); }

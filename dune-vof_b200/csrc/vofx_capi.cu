@@ -977,6 +977,29 @@ extern "C"
     return readState( ctx, s );
   }
 
+  // SwartzCurvature (2D), curvature/swartzcurvature.hh:41-173
+  int vofx_curvature_swartz ( vofx_ctx *ctx, const double *halfspaces, const uint8_t *flags, double *kappa )
+  {
+    if( !ctx || !halfspaces || !flags || !kappa )
+      return fail( VOFX_ERR_ARGUMENT, "null argument" );
+    if( ctx->desc.dim != 2 )
+      return fail( VOFX_ERR_ARGUMENT, "SwartzCurvature is implemented in 2D only (as in the reference)" );
+    int rc = setDevice( ctx );
+    rc = rc ? rc : launchResetCounters( ctx );
+    rc = rc ? rc : launchCompactFlags( ctx, flags );
+    if( rc )
+      return rc;
+    VOFX_CUDA( cudaMemsetAsync( kappa, 0, sizeof( double ) * (size_t) ctx->grid.cells, ctx->stream ) );
+    profBegin( ctx );
+    launch::swartz_curvature2( ctx->numSMs * 8, ctx->stream, ctx->grid, halfspaces, flags, ctx->mixedList, ctx->slot, ctx->state, ctx->capacity, ctx->curv1, kappa );
+    ctx->launches++;
+    rc = checkLaunch( ctx, "k_swartz_curvature" );
+    if( rc )
+      return rc;
+    StepState s;
+    return readState( ctx, s );
+  }
+
   // ---- fused time loop ---------------------------------------------------------------------------------------------------
 
   int vofx_step_begin ( vofx_ctx *ctx, double time, double dt )
@@ -1175,6 +1198,19 @@ extern "C"
     if( !rc && valid )
       rc = stageOut( ctx, valid, ctx->dValid, N );
     return rc;
+  }
+
+  int vofx_curvature_swartz_host ( vofx_ctx *ctx, const double *halfspaces, const uint8_t *flags, double *kappa )
+  {
+    if( !ctx || !halfspaces || !flags || !kappa )
+      return fail( VOFX_ERR_ARGUMENT, "null argument" );
+    const size_t N = (size_t) ctx->grid.cells;
+    int rc = ensureMirrors( ctx );
+    rc = rc ? rc : ensureDevice( ctx->dKappa, N );
+    rc = rc ? rc : stageIn( ctx, ctx->dHs, halfspaces, N * ( ctx->desc.dim + 1 ) * sizeof( double ) );
+    rc = rc ? rc : stageIn( ctx, ctx->dFlags, flags, N );
+    rc = rc ? rc : vofx_curvature_swartz( ctx, ctx->dHs, ctx->dFlags, ctx->dKappa );
+    return rc ? rc : stageOut( ctx, kappa, ctx->dKappa, N * sizeof( double ) );
   }
 
   int vofx_step_host ( vofx_ctx *ctx, const vofx_step_params *p, double *u, uint8_t *flags )

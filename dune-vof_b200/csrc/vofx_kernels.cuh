@@ -2333,6 +2333,131 @@ namespace vofx
   }
 
   // ------------------------------------------------------------------------------------------------------------
+  // SwartzCurvature (2D), curvature/swartzcurvature.hh:41-173
+  // ------------------------------------------------------------------------------------------------------------
+
+  // interface( entity, reconstructions ) of the cell ijk: centroid and length of the segment, 2d/polygon.hh:183-197
+  __device__ __forceinline__ void swc_interface ( const Grid &g, const double *__restrict__ hs, const int *ijk, double *centroid, double &length )
+  {
+    Poly2 p;
+    make_cell( cell_lower( g, 0, ijk[ 0 ] ), cell_lower( g, 1, ijk[ 1 ] ), g.h[ 0 ], g.h[ 1 ], p );
+    const double *rec = hs + cell_index( g, ijk ) * 3;
+    const Hs2 H = { rec[ 0 ], rec[ 1 ], rec[ 2 ] };
+    double lx[ 2 ], ly[ 2 ];
+    plane_cut( p, H, lx, ly );
+    centroid[ 0 ] = ( lx[ 0 ] + lx[ 1 ] ) * 0.5;
+    centroid[ 1 ] = ( ly[ 0 ] + ly[ 1 ] ) * 0.5;
+    length = norm2( lx[ 0 ] - lx[ 1 ], ly[ 0 ] - ly[ 1 ] );
+  }
+
+  // pass 1 (applyLocal, :75-152): one thread per mixed cell; the interfaces of the <= 8 mixed neighbours are cut once
+  static __global__ void __launch_bounds__( 128 ) k_swartz_curv_local ( Grid g, const double *__restrict__ hs, const unsigned char *__restrict__ flags,
+                                                                         const int *__restrict__ mixedList, const StepState *state, int capacity,
+                                                                         double *__restrict__ curv1 )
+  {
+    const int count = mixed_count( state, capacity );
+    for( int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < count; idx += gridDim.x * blockDim.x )
+    {
+      const long long c = mixedList[ idx ];
+      int ijk[ 3 ];
+      cell_ijk( g, c, ijk );
+      const double nEn[ 2 ] = { hs[ c * 3 ], hs[ c * 3 + 1 ] };
+      double cEn[ 2 ], muEn;
+      swc_interface( g, hs, ijk, cEn, muEn );
+      muEn *= muEn / 12.0;
+
+      double cen[ 8 ][ 2 ], mu[ 8 ];
+      bool mixedNb[ 8 ];
+      for( int s = 0; s < 8; ++s )
+      {
+        const int m = ( s < 4 ) ? s : s + 1;
+        const int nb[ 3 ] = { ijk[ 0 ] + ( m % 3 ) - 1, ijk[ 1 ] + ( m / 3 ) - 1, 0 };
+        mixedNb[ s ] = cell_exists( g, nb ) && is_mixed( flags[ cell_index( g, nb ) ] );
+        cen[ s ][ 0 ] = cen[ s ][ 1 ] = mu[ s ] = 0.0;
+        if( mixedNb[ s ] )
+        {
+          swc_interface( g, hs, nb, cen[ s ], mu[ s ] );
+          mu[ s ] *= mu[ s ] / 12.0;
+        }
+      }
+
+      double curv = 0.0, weights = 0.0;
+      for( int s1 = 0; s1 < 8; ++s1 )
+      {
+        if( !mixedNb[ s1 ] )
+          continue;
+        const double midway1[ 2 ] = { ( cen[ s1 ][ 0 ] + cEn[ 0 ] ) * 0.5, ( cen[ s1 ][ 1 ] + cEn[ 1 ] ) * 0.5 };
+        const double triangle1 = norm2( cen[ s1 ][ 0 ] - cEn[ 0 ], cen[ s1 ][ 1 ] - cEn[ 1 ] );
+        double tan1[ 2 ] = { cEn[ 0 ] - cen[ s1 ][ 0 ], cEn[ 1 ] - cen[ s1 ][ 1 ] };
+        const double t1 = norm2( tan1[ 0 ], tan1[ 1 ] );
+        tan1[ 0 ] /= t1;
+        tan1[ 1 ] /= t1;
+        const double nu12[ 2 ] = { -tan1[ 1 ], tan1[ 0 ] };
+        if( dot2( nu12[ 0 ], nu12[ 1 ], nEn[ 0 ], nEn[ 1 ] ) < 0 )
+          continue;
+        for( int s2 = 0; s2 < 8; ++s2 )
+        {
+          if( !mixedNb[ s2 ] || s2 == s1 )
+            continue;
+          const double midway2[ 2 ] = { ( cen[ s2 ][ 0 ] + cEn[ 0 ] ) * 0.5, ( cen[ s2 ][ 1 ] + cEn[ 1 ] ) * 0.5 };
+          const double triangle2 = norm2( cen[ s2 ][ 0 ] - cEn[ 0 ], cen[ s2 ][ 1 ] - cEn[ 1 ] );
+          const double md[ 2 ] = { midway2[ 0 ] - midway1[ 0 ], midway2[ 1 ] - midway1[ 1 ] };
+          const double deltaS = norm2( md[ 0 ], md[ 1 ] );
+          double tan2[ 2 ] = { cen[ s2 ][ 0 ] - cEn[ 0 ], cen[ s2 ][ 1 ] - cEn[ 1 ] };
+          const double t2 = norm2( tan2[ 0 ], tan2[ 1 ] );
+          tan2[ 0 ] /= t2;
+          tan2[ 1 ] /= t2;
+          const double nu23[ 2 ] = { -tan2[ 1 ], tan2[ 0 ] };
+          if( dot2( nu23[ 0 ], nu23[ 1 ], nEn[ 0 ], nEn[ 1 ] ) < 0 )
+            continue;
+          if( dot2( md[ 0 ], md[ 1 ], tan1[ 0 ] + tan2[ 0 ], tan1[ 1 ] + tan2[ 1 ] ) < 0 )
+            continue;
+          const double M = ( ( mu[ s2 ] - muEn ) / triangle2 - ( muEn - mu[ s1 ] ) / triangle1 ) / ( 2.0 * deltaS );
+          const double weight = 1.0;
+          curv += weight * ( nu12[ 0 ] * nu23[ 1 ] - nu12[ 1 ] * nu23[ 0 ] ) / ( ( 1.0 + M ) * deltaS );
+          weights += weight;
+        }
+      }
+      if( weights > 0 )
+        curv /= weights;
+      curv1[ idx ] = curv;
+    }
+  }
+
+  // pass 2 (:57-66,154-170): cells whose curvature is exactly 0 take the mean over all mixed vertex neighbours
+  static __global__ void __launch_bounds__( 128 ) k_swartz_curv_average ( Grid g, const unsigned char *__restrict__ flags, const int *__restrict__ mixedList,
+                                                                           const int *__restrict__ slot, const StepState *state, int capacity,
+                                                                           const double *__restrict__ curv1, double *__restrict__ kappa )
+  {
+    const int count = mixed_count( state, capacity );
+    for( int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < count; idx += gridDim.x * blockDim.x )
+    {
+      const long long c = mixedList[ idx ];
+      double value = curv1[ idx ];
+      if( value == 0.0 )
+      {
+        int ijk[ 3 ], n = 0;
+        cell_ijk( g, c, ijk );
+        for( int s = 0; s < 8; ++s )
+        {
+          const int m = ( s < 4 ) ? s : s + 1;
+          const int nb[ 3 ] = { ijk[ 0 ] + ( m % 3 ) - 1, ijk[ 1 ] + ( m / 3 ) - 1, 0 };
+          if( !cell_exists( g, nb ) )
+            continue;
+          const long long cn = cell_index( g, nb );
+          if( !is_mixed( flags[ cn ] ) )
+            continue;
+          value += curv1[ slot[ cn ] ];
+          n++;
+        }
+        if( n > 0 )
+          value /= (double) n;
+      }
+      kappa[ c ] = value;
+    }
+  }
+
+  // ------------------------------------------------------------------------------------------------------------
   // initial data: RecursiveInterpolationCube depth 3 (interpolation/recursiveinterpolationcube.hh:33-82) of the
   // built-in problems' indicator functions (test/problems, Problem::evaluate).  Transcendental time factors are
   // evaluated on the host and passed in, so the device only does + - * sqrt and comparisons.

@@ -41,6 +41,8 @@ namespace vofx
     void hf_fused2 ( int blocks, cudaStream_t s, Grid g, const double *u, const int *mixedList, const StepState *state, int capacity, double *hs );
     void clear_listed ( int blocks, cudaStream_t s, const int *list, const int *count, double *target );
     void copy_list ( int blocks, cudaStream_t s, const int *list, const StepState *state, int capacity, int *out, int *outCount );
+    void swartz_curvature2 ( int blocks, cudaStream_t s, Grid g, const double *hs, const unsigned char *flags, const int *mixedList, const int *slot,
+                             const StepState *state, int capacity, double *curv1, double *kappa );
     void swartz2 ( int blocks, cudaStream_t s, Grid g, const double *u, const unsigned char *flags, const int *mixedList, const StepState *state,
                    int capacity, double *hs, int maxIterations );
     void flux2 ( int blocks, cudaStream_t s, Grid g, const Velocity *velocity, const double *hs, const unsigned char *flags, const int *mixedList,

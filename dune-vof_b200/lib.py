@@ -21,7 +21,7 @@ TIME_CONST, TIME_COSPI = 0, 1
 SYMBOLS = [
     "vofx_last_error", "vofx_create", "vofx_destroy", "vofx_set_stream", "vofx_cells", "vofx_velocity_clear",
     "vofx_velocity_set_component", "vofx_velocity_set_factor", "vofx_velocity_set_faces", "vofx_velocity_builtin", "vofx_face_velocity",
-    "vofx_flag", "vofx_reconstruct", "vofx_evolve", "vofx_axpy", "vofx_curvature", "vofx_step_begin", "vofx_step",
+    "vofx_flag", "vofx_reconstruct", "vofx_evolve", "vofx_axpy", "vofx_curvature", "vofx_curvature_swartz", "vofx_curvature_swartz_host", "vofx_step_begin", "vofx_step",
     "vofx_step_state", "vofx_step_local", "vofx_step_phase", "vofx_step_finish", "vofx_dt_est_device", "vofx_flag_host",
     "vofx_reconstruct_host", "vofx_evolve_host", "vofx_curvature_host", "vofx_step_host", "vofx_host_transfer_bytes", "vofx_color_upload",
     "vofx_step_resident", "vofx_color_download", "vofx_interface", "vofx_interface_host", "vofx_interface_fetch", "vofx_init",
@@ -110,6 +110,8 @@ def load():
     L.vofx_color_upload.argtypes = [vp, dp]
     L.vofx_step_resident.argtypes = [vp, C.POINTER(StepParams)]
     L.vofx_color_download.argtypes = [vp, dp, bp]
+    L.vofx_curvature_swartz.argtypes = [vp, dp, bp, dp]
+    L.vofx_curvature_swartz_host.argtypes = [vp, dp, bp, dp]
     L.vofx_interface.argtypes = [vp, dp, bp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.vofx_interface_host.argtypes = [vp, dp, bp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.vofx_interface_fetch.argtypes = [vp, C.c_void_p, C.c_void_p, C.c_void_p]

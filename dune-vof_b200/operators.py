@@ -250,6 +250,18 @@ class StepResult:
     mixed_cells: int
 
 
+class SwartzCurvature:
+    """curvature/swartzcurvature.hh:27-181 (2D)"""
+
+    def __init__(self, grid: CartesianGrid):
+        self.grid = grid
+
+    def __call__(self, color, reconstructions, flags, curvature, communicate=True):
+        g = self.grid
+        g.use_current_stream()
+        check(g._L.vofx_curvature_swartz(g._ctx, g.ph(reconstructions), g.pf(flags), g.pc(curvature)))
+
+
 def get_interface_vertices(grid: CartesianGrid, reconstructions, flags):
     """getInterfaceVertices (utility.hh:19-48) + MixedCellMapper::update (mixedcellmapper.hh:82-86): returns numpy arrays
     (cells, offsets, vertices): the owned mixed cells in ascending index and the CSR of their interface polygons."""

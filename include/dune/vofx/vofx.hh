@@ -410,6 +410,32 @@ namespace Dune
 
 
     // Algorithm, algorithm.hh:37-120 (without l1error): the colour function stays on the device between steps.
+    // SwartzCurvature (2D)
+    // --------------------
+    // curvature/swartzcurvature.hh:27-181
+    template< class GV, class StS = VertexNeighborsStencil< GV > >
+    struct SwartzCurvature
+    {
+      using GridView = GV;
+      explicit SwartzCurvature ( const StS &stencils ) : stencils_( stencils ) {}
+
+      template< class ColorFunction, class ReconstructionSet, class Flags, class CurvatureSet >
+      void operator() ( const ColorFunction &, const ReconstructionSet &reconstructions, const Flags &flags, CurvatureSet &curvatureSet,
+                        bool /*communicate*/ = true ) const
+      {
+        auto &c = stencils_.context();
+        c.gatherReconstructions( reconstructions );
+        c.gatherFlags( flags );
+        c.kappa.resize( c.size() );
+        check( vofx_curvature_swartz_host( c.ctx(), c.halfspaces.data(), c.flags.data(), c.kappa.data() ) );
+        c.scatterScalars( c.kappa, curvatureSet );
+      }
+
+    private:
+      const StS &stencils_;
+    };
+
+
     // getInterfaceVertices
     // --------------------
     // utility.hh:19-48: the vertices of interface( entity, reconstructions ) of every mixed cell in the order the grid

@@ -169,6 +169,10 @@ int vofx_flag_host ( vofx_ctx *ctx, const double *u, double eps, uint8_t *flags 
 int vofx_reconstruct_host ( vofx_ctx *ctx, int kind, const double *u, const uint8_t *flags, double *halfspaces, int max_iterations );
 int vofx_evolve_host ( vofx_ctx *ctx, const double *halfspaces, const uint8_t *flags, double time, double dt, double *update, double *dt_est );
 int vofx_curvature_host ( vofx_ctx *ctx, const double *u, const double *halfspaces, const uint8_t *flags, double *kappa, uint8_t *valid );
+/* replaces: SwartzCurvature< GV, StS >( stencils )( color, reconstructions, flags, curvature ), 2D only like the reference
+ * (curvature/swartzcurvature.hh:41-173); kappa is zero outside the mixed cells */
+int vofx_curvature_swartz ( vofx_ctx *ctx, const double *halfspaces, const uint8_t *flags, double *kappa );
+int vofx_curvature_swartz_host ( vofx_ctx *ctx, const double *halfspaces, const uint8_t *flags, double *kappa );
 /* one full loop pass on a host colour function: H2D u, step, D2H u (and flags if non-NULL) */
 int vofx_step_host ( vofx_ctx *ctx, const vofx_step_params *params, double *u, uint8_t *flags );
 /* bytes the last vofx_step_host call moved across PCIe: the whole colour function host->device; device->host only the

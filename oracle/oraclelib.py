@@ -44,6 +44,7 @@ def lib():
         L.vo_reconstruct.argtypes = [G, C.c_int, _dp, _bp, _dp, C.c_int]
         L.vo_evolve.argtypes = [G, _dp, _bp, C.c_int, C.c_double, C.c_double, _dp, _dp]
         L.vo_curvature.argtypes = [G, _dp, _dp, _bp, _dp, _bp]
+        L.vo_curvature_swartz.argtypes = [G, _dp, _bp, _dp]
         L.vo_init.argtypes = [G, C.c_int, C.c_double, _dp]
         L.vo_face_velocity.argtypes = [G, C.c_int, C.c_double, C.c_int64, C.c_int, _dp]
         L.vo_run.argtypes = [G, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, _dp, _dp, _dp, _dp,
@@ -126,6 +127,14 @@ class OracleGrid:
         valid = np.empty(self.cells, dtype=np.uint8)
         _check(lib().vo_curvature(C.byref(self._g), _d(u), _d(hs), _b(flags), _d(kappa), _b(valid)), "curvature")
         return kappa, valid
+
+    def curvature_swartz(self, hs, flags):
+        """SwartzCurvature (2D), curvature/swartzcurvature.hh:41-173"""
+        hs = _vec(hs)
+        flags = np.ascontiguousarray(flags, dtype=np.uint8)
+        kappa = np.empty(self.cells, dtype=np.float64)
+        _check(lib().vo_curvature_swartz(C.byref(self._g), _d(hs), _b(flags), _d(kappa)), "curvature_swartz")
+        return kappa
 
     def init(self, problem, time=0.0):
         u = np.empty(self.cells, dtype=np.float64)

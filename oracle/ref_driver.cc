@@ -46,6 +46,7 @@
 #include <dune/vof/reconstruction/heightfunction.hh>
 #include <dune/vof/reconstruction/modifiedswartz.hh>
 #include <dune/vof/curvature/cartesianheightfunctioncurvature.hh>
+#include <dune/vof/curvature/swartzcurvature.hh>
 #include <dune/vof/interpolation/circleinterpolation.hh>
 #include <dune/vof/interpolation/recursiveinterpolationcube.hh>
 #include <dune/vof/test/problems/rotatingcircle.hh>
@@ -344,6 +345,32 @@ extern "C"
         *dtEstOut = Dune::VoF::evolution( ctx.gv )( recs, flags, velocity, dt, update );
         std::copy( update.begin(), update.end(), updateOut );
       } );
+    } ); } );
+  }
+
+  // curvature/swartzcurvature.hh:41-173 (2D only: the reference static_asserts dimension == 2)
+  int ref_curvature_swartz ( void *handle, const double *hsIn, const std::uint8_t *flagsIn, double *kappaOut )
+  {
+    return guarded( [ & ] { return withCtx( handle, [ & ] ( auto &ctx ) {
+      using C = std::decay_t< decltype( ctx ) >;
+      if constexpr( C::GridView::dimension == 2 )
+      {
+        typename C::Color uh( ctx.gv );
+        typename C::Flags flags( ctx.gv );
+        typename C::Recs recs( ctx.gv );
+        typename C::Curv curvature( ctx.gv );
+        ctx.loadFlags( flagsIn, flags );
+        ctx.loadRecs( hsIn, recs );
+        Dune::VoF::SwartzCurvature< typename C::GridView, typename C::Stencils > op( ctx.vertexStencils() );
+        op( uh, recs, flags, curvature );
+        std::copy( curvature.begin(), curvature.end(), kappaOut );
+        return 0;
+      }
+      else
+      {
+        lastError = "SwartzCurvature is implemented in 2D only";
+        return 1;
+      }
     } ); } );
   }
 

@@ -41,6 +41,7 @@ def lib():
         L.ref_reconstruct.argtypes = [C.c_void_p, C.c_int, _dp, _bp, _dp, C.c_int]
         L.ref_evolve.argtypes = [C.c_void_p, _dp, _bp, C.c_int, C.c_double, C.c_double, _dp, _dp]
         L.ref_curvature.argtypes = [C.c_void_p, _dp, _dp, _bp, _dp, _bp]
+        L.ref_curvature_swartz.argtypes = [C.c_void_p, _dp, _bp, _dp]
         L.ref_init.argtypes = [C.c_void_p, C.c_int, C.c_double, _dp]
         L.ref_face_velocity.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int64, C.c_int, _dp]
         L.ref_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int,
@@ -126,6 +127,13 @@ class RefGrid:
         valid = np.empty(self.cells, dtype=np.uint8)
         _check(lib().ref_curvature(self._h, _d(u), _d(hs), _b(flags), _d(kappa), _b(valid)))
         return kappa, valid
+
+    def curvature_swartz(self, hs, flags):
+        hs = _vec(hs)
+        flags = np.ascontiguousarray(flags, dtype=np.uint8)
+        kappa = np.empty(self.cells, dtype=np.float64)
+        _check(lib().ref_curvature_swartz(self._h, _d(hs), _b(flags), _d(kappa)))
+        return kappa
 
     def init(self, problem, time=0.0):
         u = np.empty(self.cells, dtype=np.float64)

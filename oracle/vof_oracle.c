@@ -2706,6 +2706,128 @@ static double circle_polygon_volume ( const vo_polygon *polygon, const double *c
   return volume;
 }
 
+/* ---- SwartzCurvature, curvature/swartzcurvature.hh:41-173 (2D only, as in the reference) ------------------------------ */
+
+/* interface( entity, reconstructions ) of one cell: centroid and length of the segment (2d/polygon.hh:183-197) */
+static void swartz_curv_interface ( const vo_grid *g, const double *hs, const int *ijk, double *centroid, double *length )
+{
+  double lo[ 3 ];
+  vo_polygon p;
+  double line[ 2 ][ 2 ];
+  cell_lower( g, ijk, lo );
+  make_polygon_cell( lo, g->h, &p );
+  polygon_plane_cut( &p, hs + cell_index( g, ijk ) * 3, line );
+  centroid[ 0 ] = ( line[ 0 ][ 0 ] + line[ 1 ][ 0 ] ) * 0.5;
+  centroid[ 1 ] = ( line[ 0 ][ 1 ] + line[ 1 ][ 1 ] ) * 0.5;
+  const double d[ 2 ] = { line[ 0 ][ 0 ] - line[ 1 ][ 0 ], line[ 0 ][ 1 ] - line[ 1 ][ 1 ] };
+  *length = normn( d, 2 );
+}
+
+/* applyLocal, :75-152 */
+static double swartz_curv_local ( const vo_grid *g, const double *hs, const uint8_t *flags, int64_t cell )
+{
+  int ijk[ 3 ];
+  cell_ijk( g, cell, ijk );
+  const double *normalEn = hs + cell * 3;
+  double curv = 0.0, weights = 0.0;
+  double centroidEn[ 2 ], muEn;
+  swartz_curv_interface( g, hs, ijk, centroidEn, &muEn );
+  muEn *= muEn / 12.0;
+
+  for( int s1 = 0; s1 < 9; ++s1 )
+  {
+    if( s1 == 4 )
+      continue;
+    const int nb1[ 3 ] = { ijk[ 0 ] + ( s1 % 3 ) - 1, ijk[ 1 ] + ( s1 / 3 ) - 1, 0 };
+    if( !in_domain( g, nb1 ) || !is_mixed( flags[ cell_index( g, nb1 ) ] ) )
+      continue;
+    double centroidNb1[ 2 ], muNb1;
+    swartz_curv_interface( g, hs, nb1, centroidNb1, &muNb1 );
+    double midwayNb1[ 2 ] = { centroidNb1[ 0 ] + centroidEn[ 0 ], centroidNb1[ 1 ] + centroidEn[ 1 ] };
+    midwayNb1[ 0 ] *= 0.5;
+    midwayNb1[ 1 ] *= 0.5;
+    const double diff1[ 2 ] = { centroidNb1[ 0 ] - centroidEn[ 0 ], centroidNb1[ 1 ] - centroidEn[ 1 ] };
+    const double triangleNb1 = normn( diff1, 2 );
+    muNb1 *= muNb1 / 12.0;
+    double tanNb1[ 2 ] = { centroidEn[ 0 ] - centroidNb1[ 0 ], centroidEn[ 1 ] - centroidNb1[ 1 ] };
+    const double t1 = normn( tanNb1, 2 );
+    tanNb1[ 0 ] /= t1;
+    tanNb1[ 1 ] /= t1;
+    const double nu12[ 2 ] = { -tanNb1[ 1 ], tanNb1[ 0 ] };
+    if( dotn( nu12, normalEn, 2 ) < 0 )
+      continue;
+
+    for( int s2 = 0; s2 < 9; ++s2 )
+    {
+      if( s2 == 4 || s2 == s1 )
+        continue;
+      const int nb2[ 3 ] = { ijk[ 0 ] + ( s2 % 3 ) - 1, ijk[ 1 ] + ( s2 / 3 ) - 1, 0 };
+      if( !in_domain( g, nb2 ) || !is_mixed( flags[ cell_index( g, nb2 ) ] ) )
+        continue;
+      double centroidNb2[ 2 ], muNb2;
+      swartz_curv_interface( g, hs, nb2, centroidNb2, &muNb2 );
+      double midwayNb2[ 2 ] = { centroidNb2[ 0 ] + centroidEn[ 0 ], centroidNb2[ 1 ] + centroidEn[ 1 ] };
+      midwayNb2[ 0 ] *= 0.5;
+      midwayNb2[ 1 ] *= 0.5;
+      const double diff2[ 2 ] = { centroidNb2[ 0 ] - centroidEn[ 0 ], centroidNb2[ 1 ] - centroidEn[ 1 ] };
+      const double triangleNb2 = normn( diff2, 2 );
+      muNb2 *= muNb2 / 12.0;
+      const double midwayDiff[ 2 ] = { midwayNb2[ 0 ] - midwayNb1[ 0 ], midwayNb2[ 1 ] - midwayNb1[ 1 ] };
+      const double deltaS = normn( midwayDiff, 2 );
+      double tanNb2[ 2 ] = { centroidNb2[ 0 ] - centroidEn[ 0 ], centroidNb2[ 1 ] - centroidEn[ 1 ] };
+      const double t2 = normn( tanNb2, 2 );
+      tanNb2[ 0 ] /= t2;
+      tanNb2[ 1 ] /= t2;
+      const double nu23[ 2 ] = { -tanNb2[ 1 ], tanNb2[ 0 ] };
+      if( dotn( nu23, normalEn, 2 ) < 0 )
+        continue;
+      const double tanSum[ 2 ] = { tanNb1[ 0 ] + tanNb2[ 0 ], tanNb1[ 1 ] + tanNb2[ 1 ] };
+      if( dotn( midwayDiff, tanSum, 2 ) < 0 )
+        continue;
+      const double M = ( ( muNb2 - muEn ) / triangleNb2 - ( muEn - muNb1 ) / triangleNb1 ) / ( 2.0 * deltaS );
+      const double weight = 1.0;
+      curv += weight * ( nu12[ 0 ] * nu23[ 1 ] - nu12[ 1 ] * nu23[ 0 ] ) / ( ( 1.0 + M ) * deltaS );
+      weights += weight;
+    }
+  }
+  if( weights > 0 )
+    curv /= weights;
+  return curv;
+}
+
+int vo_curvature_swartz ( const vo_grid *g, const double *hs, const uint8_t *flags, double *kappa )
+{
+  if( g->dim != 2 )
+    return 1;
+  const int64_t N = grid_cells( g );
+  double *curv = (double *) malloc( sizeof( double ) * (size_t) N );
+  for( int64_t c = 0; c < N; ++c )
+    curv[ c ] = is_mixed( flags[ c ] ) ? swartz_curv_local( g, hs, flags, c ) : 0.0;
+  /* cells whose curvature is exactly 0 take the mean over ALL mixed vertex neighbours, :57-66,154-170 */
+  for( int64_t c = 0; c < N; ++c )
+  {
+    kappa[ c ] = curv[ c ];
+    if( !is_mixed( flags[ c ] ) || curv[ c ] != 0.0 )
+      continue;
+    int ijk[ 3 ], n = 0;
+    cell_ijk( g, c, ijk );
+    for( int s = 0; s < 9; ++s )
+    {
+      if( s == 4 )
+        continue;
+      const int nb[ 3 ] = { ijk[ 0 ] + ( s % 3 ) - 1, ijk[ 1 ] + ( s / 3 ) - 1, 0 };
+      if( !in_domain( g, nb ) || !is_mixed( flags[ cell_index( g, nb ) ] ) )
+        continue;
+      kappa[ c ] += curv[ cell_index( g, nb ) ];
+      n++;
+    }
+    if( n > 0 )
+      kappa[ c ] /= (double) n;
+  }
+  free( curv );
+  return 0;
+}
+
 int vo_init ( const vo_grid *g, int problem, double time, double *u )
 {
   const int dim = g->dim;

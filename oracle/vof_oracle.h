@@ -37,6 +37,7 @@ int vo_flag ( const vo_grid *g, const double *u, double eps, uint8_t *flags );
 int vo_reconstruct ( const vo_grid *g, int kind, const double *u, const uint8_t *flags, double *hs, int max_iterations );
 int vo_evolve ( const vo_grid *g, const double *hs, const uint8_t *flags, int problem, double time, double dt, double *update, double *dt_est );
 int vo_curvature ( const vo_grid *g, const double *u, const double *hs, const uint8_t *flags, double *kappa, uint8_t *valid );
+int vo_curvature_swartz ( const vo_grid *g, const double *hs, const uint8_t *flags, double *kappa );   /* 2D; curvature/swartzcurvature.hh:41-173 */
 int vo_init ( const vo_grid *g, int problem, double time, double *u );
 int vo_face_velocity ( const vo_grid *g, int problem, double time, int64_t cell, int face, double *v );
 int vo_run ( const vo_grid *g, int kind, int problem, double eps, double cfl, int max_iterations, int passes,

@@ -333,3 +333,25 @@ def test_full_size_512_properties(vofx):
     assert float((nrm[ok] - 1.0).abs().max()) < 1e-14 and int((~ok).sum()) < 10
     assert float(ua.min()) > -1e-2 and float(ua.max()) < 1 + 1e-2
     grid.close()
+
+
+@pytest.mark.parametrize("case", ["2d_zalesak_64", "2d_sflow_40x24", "2d_circle_32"])
+def test_swartz_curvature_2d(vofx, case):
+    """SwartzCurvature (2D) against the oracle (which is pinned to the reference): bit-exact"""
+    import torch
+    from oracle import oraclelib as O
+    g = golden(f"operators_{case}.npz")
+    n = tuple(int(x) for x in g["n"])
+    grid = vofx.CartesianGrid(n)
+    u = torch.tensor(g["u"], device=grid.device)
+    flags, recs, kappa = grid.empty("flags"), grid.empty("reconstructions"), grid.empty("curvature")
+    vofx.FlagOperator(grid, float(g["eps"]))(u, flags)
+    og = O.OracleGrid(n)
+    for cls in (vofx.ModifiedYoungsReconstruction, vofx.HeightFunctionReconstruction):
+        cls(grid)(u, recs, flags)
+        vofx.SwartzCurvature(grid)(u, recs, flags, kappa)
+        ko = og.curvature_swartz(recs.cpu().numpy(), flags.cpu().numpy())
+        assert np.count_nonzero(ko) > 10
+        assert n_mismatch(kappa.cpu().numpy(), ko) == 0
+    og.close()
+    grid.close()

@@ -124,3 +124,18 @@ def test_operators_live(n, problem):
     kr, vr = rg.curvature(u, hs, fl)
     ko, vo = og.curvature(u, hs, fl)
     assert np.array_equal(vr, vo) and same_bits(kr, ko)
+
+
+@pytest.mark.parametrize("n,problem", [((32, 32), R.PROB_ROTATING_CIRCLE), ((40, 24), R.PROB_SFLOW), ((64, 64), R.PROB_SLOTTED_CYLINDER)])
+def test_swartz_curvature_live(n, problem):
+    """SwartzCurvature (2D, curvature/swartzcurvature.hh:41-173): the C restatement against the unmodified reference"""
+    rg, og = R.RefGrid(n), O.OracleGrid(n)
+    u = og.init(problem)
+    u, *_ = og.run(O.RECON_HF, problem, 1e-6, 0.5, 3, u)
+    flags = og.flag(u, 1e-6)
+    for kind in (O.RECON_YOUNGS, O.RECON_HF):
+        hs = og.reconstruct(kind, u, flags)
+        kr = rg.curvature_swartz(hs, flags)
+        ko = og.curvature_swartz(hs, flags)
+        assert np.count_nonzero(kr) > 10
+        assert same_bits(kr, ko), (n, problem, kind, np.flatnonzero(kr != ko)[:5])
