@@ -90,6 +90,18 @@ def operators(name, n, problem, steps_before=4, eps=1e-6, cfl=0.5, swartz=True):
     g.close()
 
 
+def swartz_curvature_2d():
+    """SwartzCurvature (2D, curvature/swartzcurvature.hh:41-173) of the reference on the reconstructions of the 2D operator cases"""
+    out = {}
+    for name in ("2d_circle_32", "2d_sflow_40x24", "2d_zalesak_64"):
+        g0 = np.load(os.path.join(OUT, f"operators_{name}.npz"))
+        grid = R.RefGrid(tuple(int(x) for x in g0["n"]))
+        for kname in ("youngs", "hf"):
+            out[f"{name}_{kname}"] = grid.curvature_swartz(g0[f"hs_{kname}"], g0["flags"])
+        grid.close()
+    np.savez_compressed(os.path.join(OUT, "curvature_swartz_2d.npz"), **out)
+
+
 def c1_run():
     """SURVEY.md section 8(c) known answer: 128^2, Young's, RotatingCircle, eps 1e-6, cfl 0.5, 20 loop passes."""
     g = R.RefGrid((128, 128))
@@ -110,4 +122,5 @@ if __name__ == "__main__":
     operators("3d_leveque_16", (16, 16, 16), R.PROB_LEVEQUE)
     operators("3d_leveque_32", (32, 32, 32), R.PROB_LEVEQUE, swartz=False)
     c1_run()
+    swartz_curvature_2d()
     print("golden vectors written to", OUT)

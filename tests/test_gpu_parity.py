@@ -353,5 +353,8 @@ def test_swartz_curvature_2d(vofx, case):
         ko = og.curvature_swartz(recs.cpu().numpy(), flags.cpu().numpy())
         assert np.count_nonzero(ko) > 10
         assert n_mismatch(kappa.cpu().numpy(), ko) == 0
+        # and against the vector dumped from the unmodified reference (tests/golden/make_golden.py)
+        kname = "youngs" if cls is vofx.ModifiedYoungsReconstruction else "hf"
+        assert n_mismatch(kappa.cpu().numpy(), golden("curvature_swartz_2d.npz")[f"{case}_{kname}"]) == 0
     og.close()
     grid.close()

@@ -133,3 +133,14 @@ def test_flag_edge_cases():
     assert fl[5] == 99 and fl[6] == 2 and fl[1] == 0 and fl[2] == 1
     u[:] = 1.0
     assert (og.flag(u, 1e-6) == 3).all()
+
+
+def test_swartz_curvature_golden():
+    """oracle SwartzCurvature (2D) against the vectors dumped from the unmodified reference"""
+    gk = golden("curvature_swartz_2d.npz")
+    for name in ("2d_circle_32", "2d_sflow_40x24", "2d_zalesak_64"):
+        g = golden(f"operators_{name}.npz")
+        og = O.OracleGrid(tuple(int(x) for x in g["n"]))
+        for kname in ("youngs", "hf"):
+            assert same_bits(og.curvature_swartz(g[f"hs_{kname}"], g["flags"]), gk[f"{name}_{kname}"]), (name, kname)
+        og.close()
