@@ -9,15 +9,6 @@ namespace vofx
     void flux3 ( int blocks, cudaStream_t s, Grid g, const Velocity *velocity, const double *hs, const unsigned char *flags, const int *mixedList,
                  StepState *state, int capacity, FluxRecord *records, const double *timeOverride, const double *dtOverride )
     { k_flux< 3 ><<< blocks, 128, 0, s >>>( g, velocity, hs, flags, mixedList, state, capacity, records, timeOverride, dtOverride ); }
-    void flux_prepare3 ( int blocks, cudaStream_t s, Grid g, const Velocity *velocity, const unsigned char *flags, const int *mixedList, StepState *state,
-                         int capacity, FluxRecord *records, int *tasks, int taskCapacity, const double *timeOverride, const double *dtOverride )
-    { k_flux_prepare3< 3 ><<< blocks, 128, 0, s >>>( g, velocity, flags, mixedList, state, capacity, records, tasks, taskCapacity, timeOverride, dtOverride ); }
-    void flux_clip3 ( int blocks, cudaStream_t s, Grid g, const Velocity *velocity, const double *hs, const unsigned char *flags, const int *mixedList,
-                      StepState *state, FluxRecord *records, int *tasks, const void *clipTable, int taskCapacity, const double *timeOverride, const double *dtOverride )
-    {
-      k_flux_clip3< 3 ><<< blocks, 128, 0, s >>>( g, velocity, hs, flags, mixedList, state, records, tasks, (const coop::ClipCase *) clipTable, taskCapacity, timeOverride, dtOverride );
-      k_flux_clip_serial3< 3 ><<< 148, 64, 0, s >>>( g, velocity, hs, flags, mixedList, state, records, tasks, taskCapacity, timeOverride, dtOverride );
-    }
     void flux_cell3 ( int blocks, cudaStream_t s, Grid g, const Velocity *velocity, const Velocity &velocityByValue, const double *hs, const unsigned char *flags, const int *mixedList,
                       StepState *state, int capacity, FluxRecord *records, int *tasks, int taskCapacity, const void *clipTable,
                       const double *timeOverride, const double *dtOverride )

@@ -360,17 +360,6 @@ namespace
       launch::flux2( blocks, ctx->stream, g, ctx->velDev, hs, flags, ctx->mixedList, ctx->state, ctx->capacity, ctx->records, timeOverride, dtOverride );
       return checkLaunch( ctx, "k_flux" );
     }
-    if( std::getenv( "VOFX_FLUX_TASKS" ) )
-    {
-      launch::flux_prepare3( blocks, ctx->stream, g, ctx->velDev, flags, ctx->mixedList, ctx->state, ctx->capacity, ctx->records, ctx->tasks, ctx->taskCapacity, timeOverride, dtOverride );
-      int rc = checkLaunch( ctx, "k_flux_prepare" );
-      if( rc )
-        return rc;
-      profBegin( ctx );
-      launch::flux_clip3( ctx->numSMs * 8, ctx->stream, g, ctx->velDev, hs, flags, ctx->mixedList, ctx->state, ctx->records, ctx->tasks, ctx->clipTable, ctx->taskCapacity, timeOverride, dtOverride );
-      ctx->launches++;   // k_flux_clip_serial3 rides along (a handful of tasks per step)
-      return checkLaunch( ctx, "k_flux_clip" );
-    }
     launch::flux_cell3( ctx->numSMs * 8, ctx->stream, g, ctx->velDev, ctx->velHost, hs, flags, ctx->mixedList, ctx->state, ctx->capacity, ctx->records, ctx->tasks, ctx->taskCapacity,
                         ctx->clipTable, timeOverride, dtOverride );
     ctx->launches++;     // k_flux_clip_serial3 rides along (a handful of clips per step)
@@ -585,8 +574,8 @@ extern "C"
     alloc( (void **) &ctx->state, sizeof( StepState ) );
     if( desc->dim == 3 )
     {
-      // worst case 6 clip tasks per mixed cell, plus the serial leftovers stored from the end
-      const long long tc = 7LL * ctx->capacity;
+      // clips left to the serial kernel (a node of the swept box exactly on the plane), stored from the end
+      const long long tc = 6LL * ctx->capacity;
       ctx->taskCapacity = (int) ( tc < ( 1LL << 30 ) ? tc : ( 1LL << 30 ) );
       alloc( (void **) &ctx->tasks, sizeof( int ) * (size_t) ctx->taskCapacity );
       alloc( (void **) &ctx->clipTable, 256 * 64 );

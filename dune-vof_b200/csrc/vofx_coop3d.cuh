@@ -896,13 +896,15 @@ namespace vofx
             const double ex = xj - xi, ey = yj - yi;
             const int f = B.corrFace[ i ];
             const double norm = S.fnrm[ f ];
-            S.bterm[ i ] = ( norm > 0 ) ? vdiv( norm2( ex, ey ) * S.fnz[ f ], norm ) : 0.0;
+            // | edge | is needed three times: as norm2( ex, ey ) in B and C and as the norm of the edge normal ( ey, -ex ),
+            // sqrt( ey*ey + ex*ex ): the same bits, because the two squares are added to zero in either order
+            const double len = norm2( ex, ey );
+            S.bterm[ i ] = ( norm > 0 ) ? vdiv( len * S.fnz[ f ], norm ) : 0.0;
             double onx = ey, ony = -ex;
-            const double nrm = norm2( onx, ony );
-            onx = vdiv( onx, nrm );
-            ony = vdiv( ony, nrm );
+            onx = vdiv( onx, len );
+            ony = vdiv( ony, len );
             const double cx = ( xi + xj ) * 0.5, cy = ( yi + yj ) * 0.5;
-            S.cterm[ i ] = dot2( cx, cy, onx, ony ) * norm2( ex, ey );
+            S.cterm[ i ] = dot2( cx, cy, onx, ony ) * len;
           }
         }
 

@@ -1492,10 +1492,9 @@ namespace vofx
   }
 
   // ------------------------------------------------------------------------------------------------------------
-  // E1 in 3D, split for the B200: k_flux_prepare (one lane per (mixed cell, face): velocities, time-step estimate,
-  // the flux-free contributions, and a compacted list of the faces that need a clip) and k_flux_clip (8 lanes per
-  // clip task, vofx_coop3d.cuh).  Only ~half of the faces of a mixed cell are outflow faces, and a serial clip per
-  // lane diverges 4-way inside a warp; the task list keeps every lane of the clip kernel busy.
+  // E1 in 3D for the B200 (k_flux_cell3 below).  A first version compacted the outflow faces into a task list
+  // (k_flux_prepare3 + k_flux_clip3: 0.043 + 0.46 ms at 512^3); the cell-major kernel evaluates nothing twice and
+  // passes no task list through memory (0.36 ms).
   // ------------------------------------------------------------------------------------------------------------
 
   struct FaceMotion
@@ -1544,216 +1543,6 @@ namespace vofx
     {
       m.vn += m.v[ k ] * outerNormal[ k ];
       m.vN += m.v[ k ] * ( outerNormal[ k ] * faceVol );   // v * integrationOuterNormal
-    }
-  }
-
-  template< int DIM_ >
-  __global__ void __launch_bounds__( 128 ) k_flux_prepare3 ( Grid g, const Velocity *__restrict__ velocity, const unsigned char *__restrict__ flags,
-                                                              const int *__restrict__ mixedList, StepState *state, int capacity,
-                                                              FluxRecord *__restrict__ records, int *__restrict__ tasks, int taskCapacity,
-                                                              const double *timeOverride, const double *dtOverride )
-  {
-    constexpr int DIM = 3, LANES = 8, NFACES = 6;
-    const int count = mixed_count( state, capacity );
-    const double time = timeOverride ? *timeOverride : state->time;
-    const double dt = dtOverride ? *dtOverride : state->dt;
-    const double volume = cell_volume( g );
-    const int groupsPerBlock = blockDim.x / LANES;
-    const int lane = threadIdx.x % LANES;
-    const int laneInWarp = threadIdx.x & 31;
-    const int groupBase = laneInWarp - lane;
-    const int nGroupsRounded = ( ( count + 32 / LANES - 1 ) / ( 32 / LANES ) ) * ( 32 / LANES );
-    double dtMin = DBL_MAX;
-    for( int idx = blockIdx.x * groupsPerBlock + threadIdx.x / LANES; idx < nGroupsRounded; idx += gridDim.x * groupsPerBlock )
-    {
-      const bool active = idx < count;
-      double sf = 0.0, selfc = 0.0;
-      bool hasNb = false, hasSelf = false, hasNbc = false, needClip = false;
-      int c = 0;
-      int ijk[ 3 ] = { 0, 0, 0 };
-      if( active && lane < NFACES )
-      {
-        c = mixedList[ idx ];
-        cell_ijk( g, c, ijk );
-        const int face = lane;
-        int nb[ 3 ] = { ijk[ 0 ], ijk[ 1 ], ijk[ 2 ] };
-        nb[ face >> 1 ] += ( face & 1 ) ? 1 : -1;
-        if( in_domain( g, nb ) )
-        {
-          hasNb = true;
-          const unsigned char flagNb = cell_exists( g, nb ) ? flags[ cell_index( g, nb ) ] : (unsigned char) 99;
-          FaceMotion m;
-          face_motion< DIM >( g, *velocity, ijk, face, time, dt, m );
-          sf = m.sf;
-          if( m.vn > 0 )
-          {
-            needClip = true;
-            hasSelf = true;
-            hasNbc = ( flagNb == 3 ) || ( flagNb == 0 ) || is_mixed( flagNb );
-          }
-          if( flagNb == 3 && m.vn < 0 )
-          {
-            hasSelf = true;
-            selfc = -( m.vN / volume );                          // inflow from a full neighbour
-          }
-        }
-      }
-
-      double sumFluxes = 0.0;
-#pragma unroll
-      for( int f = 0; f < NFACES; ++f )
-      {
-        const double sff = __shfl_sync( 0xffffffffu, sf, groupBase + f );
-        const int has = __shfl_sync( 0xffffffffu, (int) hasNb, groupBase + f );
-        if( has )
-          sumFluxes += sff;
-      }
-      const unsigned selfBits = __ballot_sync( 0xffffffffu, hasSelf ) >> groupBase;
-      const unsigned nbBits = __ballot_sync( 0xffffffffu, hasNbc ) >> groupBase;
-
-      // warp-aggregated append of the clip tasks
-      const unsigned clipBits = __ballot_sync( 0xffffffffu, needClip );
-      if( clipBits )
-      {
-        int base = 0;
-        if( laneInWarp == 0 )
-          base = atomicAdd( &state->taskCount, __popc( clipBits ) );
-        base = __shfl_sync( 0xffffffffu, base, 0 );
-        if( needClip )
-        {
-          const int pos = base + __popc( clipBits & ( ( 1u << laneInWarp ) - 1 ) );
-          if( pos < taskCapacity - count )                         // the tail is kept for the serial leftovers
-            tasks[ pos ] = idx * 8 + lane;
-          else
-            state->overflow = 1;
-        }
-      }
-
-      if( active )
-      {
-        FluxRecord *r = records + idx;
-        if( lane < NFACES && !needClip )
-        {
-          r->self[ lane ] = selfc;
-          r->nb[ lane ] = 0.0;
-        }
-        if( lane == 0 )
-        {
-          r->selfMask = (unsigned char) ( selfBits & ( ( 1u << NFACES ) - 1 ) );
-          r->nbMask = (unsigned char) ( nbBits & ( ( 1u << NFACES ) - 1 ) );
-          const int la = ijk[ DIM - 1 ];
-          if( la >= g.own0 && la < g.own1 )
-          {
-            const double est = volume / sumFluxes;
-            if( est == est && est < dtMin )                      // std::min( dtEst, est ): NaN never wins
-              dtMin = est;
-          }
-        }
-      }
-    }
-    // one atomic per block (1e5 atomics on one address serialise in L2)
-    __shared__ double blockMin[ 4 ];
-#pragma unroll
-    for( int o = 16; o > 0; o >>= 1 )
-    {
-      const double other = __shfl_xor_sync( 0xffffffffu, dtMin, o );
-      dtMin = ( other < dtMin ) ? other : dtMin;
-    }
-    if( laneInWarp == 0 )
-      blockMin[ threadIdx.x >> 5 ] = dtMin;
-    __syncthreads();
-    if( threadIdx.x == 0 )
-    {
-      for( int w = 1; w < 4; ++w )
-        dtMin = ( blockMin[ w ] < dtMin ) ? blockMin[ w ] : dtMin;
-      if( dtMin < DBL_MAX )
-        atomic_min_positive( &state->dtEst, dtMin );
-    }
-  }
-
-  template< int DIM_ >
-  __global__ void __launch_bounds__( 128, 5 ) k_flux_clip3 ( Grid g, const Velocity *__restrict__ velocity, const double *__restrict__ hs,
-                                                           const unsigned char *__restrict__ flags, const int *__restrict__ mixedList,
-                                                           StepState *state, FluxRecord *__restrict__ records, int *__restrict__ tasks,
-                                                           const coop::ClipCase *__restrict__ clipTable, int taskCapacity,
-                                                           const double *timeOverride, const double *dtOverride )
-  {
-    constexpr int DIM = 3, LANES = coop::kLanes;
-    constexpr int GROUPS = 128 / LANES;
-    __shared__ coop::ClipCase table[ 256 ];
-    __shared__ coop::ClipScratch scratch[ GROUPS ];
-    {
-      const uint4 *src = reinterpret_cast< const uint4 * >( clipTable );
-      uint4 *dst = reinterpret_cast< uint4 * >( table );
-      for( int i = threadIdx.x; i < int( 256 * sizeof( coop::ClipCase ) / sizeof( uint4 ) ); i += blockDim.x )
-        dst[ i ] = src[ i ];
-    }
-    __syncthreads();
-
-    const int nTasks = state->taskCount;
-    const double time = timeOverride ? *timeOverride : state->time;
-    const double dt = dtOverride ? *dtOverride : state->dt;
-    const double volume = cell_volume( g );
-    const int lane = threadIdx.x % LANES;
-    const int group = threadIdx.x / LANES;
-    const unsigned groupMask = 0xffu << ( ( threadIdx.x & 31 ) - lane );
-    coop::ClipScratch &S = scratch[ group ];
-
-    for( int t = blockIdx.x * GROUPS + group; t < nTasks; t += gridDim.x * GROUPS )
-    {
-      const int task = tasks[ t ];
-      const int idx = task >> 3, face = task & 7;
-      const int c = mixedList[ idx ];
-      int ijk[ 3 ];
-      cell_ijk( g, c, ijk );
-      FaceMotion m;
-      face_motion< DIM >( g, *velocity, ijk, face, time, dt, m );
-      const double *rec = hs + (long long) c * ( DIM + 1 );
-      const Hs3 H = { { rec[ 0 ], rec[ 1 ], rec[ 2 ] }, rec[ 3 ] };
-      double flux = fabs( 0.0 / 3.0 );
-      if( hs_valid( H ) )
-      {
-        const double lo[ 3 ] = { cell_lower( g, 0, ijk[ 0 ] ), cell_lower( g, 1, ijk[ 1 ] ), cell_lower( g, 2, ijk[ 2 ] ) };
-        double xn[ 3 ];
-        coop::upwind_node( lane, lo, g.h, face, m.v, xn );
-        coop::clip_phase_classify( lane, S, xn, H );
-        __syncwarp( groupMask );
-        const coop::ClipCase *cs;
-        const int status = coop::clip_phase_cut( lane, S, H, table, cs );
-        __syncwarp( groupMask );
-        if( status == 0 )
-        {
-          coop::clip_phase_faces( lane, S, *cs );
-          __syncwarp( groupMask );
-          coop::clip_phase_edges< LANES >( lane, S, *cs );
-          __syncwarp( groupMask );
-          coop::clip_phase_face_sums( lane, S, *cs );
-          __syncwarp( groupMask );
-          flux = coop::clip_phase_sum( S, *cs );
-        }
-        __syncwarp( groupMask );     // the scratch is reused by the next task
-        if( status == 2 )
-        {
-          // a node on the plane / irregular mask: rare; queued at the END of the task array for k_flux_clip_serial3
-          if( lane == 0 )
-            tasks[ taskCapacity - 1 - atomicAdd( &state->serialCount, 1 ) ] = task;
-          continue;
-        }
-      }
-      if( lane == 0 )
-      {
-        int nb[ 3 ] = { ijk[ 0 ], ijk[ 1 ], ijk[ 2 ] };
-        nb[ face >> 1 ] += ( face & 1 ) ? 1 : -1;
-        const unsigned char flagNb = cell_exists( g, nb ) ? flags[ cell_index( g, nb ) ] : (unsigned char) 99;
-        FluxRecord *r = records + idx;
-        r->self[ face ] = -( flux / volume );                    // update[ entity ] -= flux / volume
-        double nbc = 0.0;
-        if( flagNb == 3 )
-          nbc = -( ( m.vN - flux ) / volume );                   // update[ neighbor ] -= ( v*N - flux ) / volume
-        else if( flagNb == 0 || is_mixed( flagNb ) )
-          nbc = flux / volume;                                   // update[ neighbor ] += flux / volume
-        r->nb[ face ] = nbc;
-      }
     }
   }
 
