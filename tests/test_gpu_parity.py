@@ -358,3 +358,54 @@ def test_swartz_curvature_2d(vofx, case):
         assert n_mismatch(kappa.cpu().numpy(), golden("curvature_swartz_2d.npz")[f"{case}_{kname}"]) == 0
     og.close()
     grid.close()
+
+
+@pytest.mark.parametrize("n,problem,passes", [((24, 20, 16), 3, 8), ((40, 32), 3, 8), ((20, 20, 20), 0, 6)])
+def test_edge_cases_axis_aligned_and_walls(vofx, n, problem, passes):
+    """SURVEY.md "edge cases": a planar interface aligned with an axis (LinearWall: normals exactly +-e_x -> the tied-height
+    walk of the plane-constant solve, planes exactly on cell faces -> the serial clip for nodes on the plane), cells at
+    the domain wall (ghost terms of Young's, wall faces skipped by the flux), all three reconstructions, against the
+    oracle bit for bit"""
+    import torch
+    from oracle import oraclelib as O
+    og = O.OracleGrid(n)
+    grid = vofx.CartesianGrid(n)
+    grid.set_velocity_builtin(problem)
+    u0 = og.init(problem)
+    kinds = [vofx.RECON_YOUNGS, vofx.RECON_HF] + ([vofx.RECON_SWARTZ] if len(n) == 2 or problem == 3 else [])
+    for kind in kinds:
+        p = passes if kind != vofx.RECON_SWARTZ else 3
+        uo, to, do, _, _ = og.run(kind, problem, 1e-6, 0.5, p, u0)
+        uh = torch.tensor(u0, device=grid.device)
+        st = vofx.Algorithm(grid, 0.5, 1e-6, reconstruction_kind=kind).run_passes(uh, p)
+        assert n_mismatch(uh.cpu().numpy(), uo) == 0, kind
+        assert st.time == to and st.dt == do, kind
+    grid.close()
+    og.close()
+
+
+def test_edge_cases_special_colours(vofx):
+    """NaN colour -> flag 99 (never mixed); colours slightly outside [0,1] (over/undershoots) and just above eps (the
+    corner-plane artefact of the absolute 1e-14 volume tolerance) reconstruct exactly like the oracle"""
+    import torch
+    from oracle import oraclelib as O
+    n = (16, 16, 16)
+    og = O.OracleGrid(n)
+    grid = vofx.CartesianGrid(n, h=(1.0 / 512,) * 3)          # small cells: u * h^3 < 1e-14 for u < 1.3e-6
+    og2 = O.OracleGrid(n, h=(1.0 / 512,) * 3)
+    u = og.init(O.PROB_LEVEQUE)
+    rng = np.random.default_rng(9)
+    mixed = np.flatnonzero((u > 1e-6) & (u < 1 - 1e-6))
+    u[mixed[::7]] = 10.0 ** rng.uniform(-6, -5, size=len(mixed[::7]))     # just above eps
+    u[mixed[1::7]] = 1.0 + 3e-3
+    u[mixed[2::7]] = -2e-3
+    u[5] = np.nan
+    fo = og2.flag(u, 1e-6)
+    ut = torch.tensor(u, device=grid.device)
+    flags, recs = grid.empty("flags"), grid.empty("reconstructions")
+    vofx.FlagOperator(grid, 1e-6)(ut, flags)
+    assert np.array_equal(flags.cpu().numpy(), fo) and fo[5] == 99
+    for cls, kind in ((vofx.ModifiedYoungsReconstruction, O.RECON_YOUNGS), (vofx.HeightFunctionReconstruction, O.RECON_HF)):
+        cls(grid)(ut, recs, flags)
+        assert n_mismatch(recs.cpu().numpy(), og2.reconstruct(kind, u, fo)) == 0
+    grid.close()
