@@ -409,3 +409,22 @@ def test_edge_cases_special_colours(vofx):
         cls(grid)(ut, recs, flags)
         assert n_mismatch(recs.cpu().numpy(), og2.reconstruct(kind, u, fo)) == 0
     grid.close()
+
+
+def test_256_cubed_against_oracle(vofx):
+    """the largest case the oracle finishes in seconds (configs[3]'s grid, 2.8e4 mixed cells): 12 loop passes of the
+    3D Young's step, every colour value, time and dt bit-identical"""
+    import torch
+    from oracle import oraclelib as O
+    n = (256, 256, 256)
+    og = O.OracleGrid(n)
+    grid = vofx.CartesianGrid(n)
+    grid.set_velocity_builtin(vofx.PROB_LEVEQUE)
+    u0 = grid.init(vofx.PROB_LEVEQUE)
+    uo, to, do, _, _ = og.run(O.RECON_YOUNGS, O.PROB_LEVEQUE, 1e-6, 0.5, 12, u0.cpu().numpy())
+    uh = u0.clone()
+    st = vofx.Algorithm(grid, 0.5, 1e-6, reconstruction_kind=vofx.RECON_YOUNGS).run_passes(uh, 12)
+    assert n_mismatch(uh.cpu().numpy(), uo) == 0
+    assert st.time == to and st.dt == do
+    grid.close()
+    og.close()
