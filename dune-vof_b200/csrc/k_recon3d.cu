@@ -1,5 +1,4 @@
 // vofx: launchers of band kernels (see vofx_launch.h); generated layout, one group of kernels per translation unit.
-#include <cstdlib>
 #include "vofx_launch.h"
 #include "vofx_kernels.cuh"
 
@@ -14,9 +13,8 @@ namespace vofx
     {
       const coop::SweepTable *T = (const coop::SweepTable *) sweepTable;
       coop::RootTask *R = (coop::RootTask *) rootTasks;
-      static const int pad = std::getenv( "VOFX_DEBUG_SMEM_PAD" ) ? std::atoi( std::getenv( "VOFX_DEBUG_SMEM_PAD" ) ) : 0;   // occupancy experiments
       if( lanes == 4 && !heightFunction )
-        k_youngs_coop3< 4, false ><<< blocks * 2, 64, pad, s >>>( g, u, mixedList, state, capacity, hs, T, serialCells, R );
+        k_youngs_coop3< 4, false ><<< blocks * 2, 64, 0, s >>>( g, u, mixedList, state, capacity, hs, T, serialCells, R );
       else if( lanes == 4 )
         k_youngs_coop3< 4, true ><<< blocks * 2, 64, 0, s >>>( g, u, mixedList, state, capacity, hs, T, serialCells, R );
       else if( !heightFunction )

@@ -237,10 +237,9 @@ namespace
       const int rowsPerLayer = ( g.dim == 3 ) ? g.ns[ 1 ] : 1;
       const int rowBegin = layer0 * rowsPerLayer, rowEnd = layer1 * rowsPerLayer;
       const int nRows = rowEnd - rowBegin;
-      static const int rowsEnv = std::getenv( "VOFX_DEBUG_FLAG_ROWS" ) ? std::atoi( std::getenv( "VOFX_DEBUG_FLAG_ROWS" ) ) : 0;   // tuning experiments
       // measured at 512^3 (ms): 1 row 0.234, 2 0.230, 4 0.226, 8 0.222, 16 0.229, 32 0.248; a software-pipelined variant
       // (loads of the next row issued before the current one is processed) was slower (0.259)
-      const int rowsPerBlock = rowsEnv > 0 ? rowsEnv : ( ( nRows >= 8 * ctx->numSMs * 16 ) ? 8 : 1 );
+      const int rowsPerBlock = ( nRows >= 8 * ctx->numSMs * 16 ) ? 8 : 1;
       const int blocks = ( nRows + rowsPerBlock - 1 ) / rowsPerBlock;
       launch::flag_rows( g.dim, blocks, ctx->stream, g, u, eps, flags, ctx->mixedList, ctx->slot, ctx->capacity, ctx->state, compact ? 1 : 0, rowsPerBlock, rowBegin, rowEnd );
       return checkLaunch( ctx, "k_flag_compact" );
