@@ -313,8 +313,37 @@ def main():
                "api": "vofx_step_host: pinned host colour function in (whole array H2D), updated in place on the host from the "
                       "(cell, value) pairs of the cells the step changed (sparse D2H) + loop state"}
     else:
-        e2e = {"value": None, "unit": "cell-steps/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
-               "note": "measured at N=1 only"}
+        # every rank: H2D of its owned slab from pinned host memory, one loop pass (halo exchange, MIN reduction), the
+        # changed (cell, value) pairs back into the host slab
+        H = slab.exchanger.halo
+        owned = slab.owned(uh)
+        host_u = torch.empty(owned.numel(), dtype=torch.float64).pin_memory()
+        host_u.copy_(owned.reshape(-1))
+        grid.use_current_stream()
+        vlib.check(L.vofx_track_changes(grid._ctx, 1))
+        KE = max(1, args.e2e_steps)
+        nchg = C.c_int64(0)
+
+        def e2e_step():
+            owned.copy_(host_u.view_as(owned), non_blocking=True)
+            slab.step(uh)
+            vlib.check(L.vofx_changed_fetch(grid._ctx, C.c_void_p(host_u.data_ptr()), C.c_int64(-H * slab.layer_cells), C.byref(nchg)))
+
+        e2e_step()
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(KE):
+            e2e_step()
+        sync_all()
+        wall = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(wall, op=dist.ReduceOp.MAX)
+        wall = float(wall.item())
+        vlib.check(L.vofx_track_changes(grid._ctx, 0))
+        e2e = {"value": total_cells * KE / wall, "unit": "cell-steps/s", "h2d_bytes_per_step": 8 * cells_per_gpu * world,
+               "d2h_bytes_per_step": (12 * int(nchg.value) + 64) * world, "steps": KE, "ms_per_step": 1e3 * wall / KE,
+               "api": "per rank: pinned host slab -> device, SlabAlgorithm.step (halo exchange + MIN reduction over NCCL), "
+                      "vofx_changed_fetch writes the changed (cell, value) pairs back into the host slab; d2h bytes estimated "
+                      "from rank 0's count"}
 
     if rank != 0:
         if world > 1:

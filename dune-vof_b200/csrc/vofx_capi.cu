@@ -1227,9 +1227,10 @@ extern "C"
     VOFX_CUDA( cudaMemcpyAsync( ctx->dU, u, N * sizeof( double ), cudaMemcpyHostToDevice, ctx->stream ) );
     ctx->lastH2D = (long long) ( N * sizeof( double ) );
     ctx->lastD2H = (long long) sizeof( StepState ) + ( flags ? (long long) N : 0 );
+    const bool tracking = ctx->trackChanges;
     ctx->trackChanges = true;
     rc = vofx_step( ctx, p, ctx->dU, ctx->dFlags, ctx->dHs, ctx->dKappa );
-    ctx->trackChanges = false;
+    ctx->trackChanges = tracking;
     if( rc )
       return rc;
     if( flags )
@@ -1263,6 +1264,64 @@ extern "C"
     VOFX_CUDA( cudaStreamSynchronize( ctx->stream ) );
     for( size_t i = 0; i < n; ++i )
       u[ hostIdx[ i ] ] = hostVal[ i ];
+    return VOFX_OK;
+  }
+
+  // Sparse write-back for drivers that run the pass themselves (slab decomposition): vofx_track_changes( 1 ) makes every
+  // following update record the (cell, new value) pairs it writes; vofx_changed_fetch copies the pairs of the LAST
+  // finished pass into the caller's host colour function (indices are storage indices of this context, shifted by
+  // `index_offset` cells) and returns their number.
+  int vofx_track_changes ( vofx_ctx *ctx, int enable )
+  {
+    if( !ctx )
+      return fail( VOFX_ERR_ARGUMENT, "null context" );
+    int rc = setDevice( ctx );
+    if( rc )
+      return rc;
+    if( enable && !ctx->changedIdx )
+    {
+      const size_t N = (size_t) ctx->grid.cells;
+      const long long cap = 7LL * ctx->capacity < (long long) N ? 7LL * ctx->capacity : (long long) N;
+      ctx->changedCapacity = (int) ( cap < ( 1LL << 30 ) ? cap : ( 1LL << 30 ) );
+      rc = ensureDevice( ctx->changedIdx, (size_t) ctx->changedCapacity );
+      rc = rc ? rc : ensureDevice( ctx->changedVal, (size_t) ctx->changedCapacity );
+      if( rc )
+        return rc;
+    }
+    ctx->trackChanges = enable != 0;
+    return VOFX_OK;
+  }
+
+  int vofx_changed_fetch ( vofx_ctx *ctx, double *u_host, int64_t index_offset, int64_t *n_changed )
+  {
+    if( !ctx || !u_host || !n_changed )
+      return fail( VOFX_ERR_ARGUMENT, "null argument" );
+    if( !ctx->changedIdx )
+      return fail( VOFX_ERR_STATE, "vofx_track_changes has not been enabled" );
+    StepState s;
+    int rc = readState( ctx, s );
+    if( rc )
+      return rc;
+    const size_t n = (size_t) s.changedCountLast;
+    *n_changed = (int64_t) n;
+    if( n > (size_t) ctx->changedCapacity )
+      return fail( VOFX_ERR_STATE, "changed-cell list overflow" );
+    ctx->lastD2H = (long long) sizeof( StepState ) + (long long) ( n * ( sizeof( int ) + sizeof( double ) ) );
+    if( n == 0 )
+      return VOFX_OK;
+    size_t want = n * ( sizeof( int ) + sizeof( double ) ) + 16;
+    if( want > ctx->pinnedBytes )
+      want = ( 2 * want > ( size_t( 64 ) << 20 ) ) ? 2 * want : ( size_t( 64 ) << 20 );
+    rc = ensurePinned( ctx, want );
+    if( rc )
+      return rc;
+    double *hostVal = static_cast< double * >( ctx->pinned );
+    int *hostIdx = reinterpret_cast< int * >( hostVal + n );
+    VOFX_CUDA( cudaMemcpyAsync( hostVal, ctx->changedVal, n * sizeof( double ), cudaMemcpyDeviceToHost, ctx->stream ) );
+    VOFX_CUDA( cudaMemcpyAsync( hostIdx, ctx->changedIdx, n * sizeof( int ), cudaMemcpyDeviceToHost, ctx->stream ) );
+    VOFX_CUDA( cudaStreamSynchronize( ctx->stream ) );
+    for( size_t i = 0; i < n; ++i )
+      u_host[ (int64_t) hostIdx[ i ] + index_offset ] = hostVal[ i ];
     return VOFX_OK;
   }
 

@@ -37,6 +37,11 @@ extern "C" {
 
 #define VOFX_VERSION 1
 
+/* Tunables read from the environment at context creation / launch (defaults are the measured optima on B200):
+ *   VOFX_LANES_PER_CELL = 4 | 8   lanes per mixed cell of the 3D Young's / height-function kernel (default 4)
+ *   VOFX_SWARTZ_LANES   = 4 | 8   lanes per task of the 3D Swartz kernels (default 4)
+ *   VOFX_SWARTZ_MODE    = batched (default) | cell | serial   formulation of the 3D Swartz reconstruction */
+
 enum vofx_status
 {
   VOFX_OK = 0,
@@ -178,6 +183,12 @@ int vofx_step_host ( vofx_ctx *ctx, const vofx_step_params *params, double *u, u
 /* bytes the last vofx_step_host call moved across PCIe: the whole colour function host->device; device->host only the
  * (cell, new value) pairs of the cells the update touched (mixed cells and their face neighbours) plus the loop state */
 int vofx_host_transfer_bytes ( const vofx_ctx *ctx, int64_t *h2d_bytes, int64_t *d2h_bytes );
+
+/* sparse write-back for drivers that run the pass themselves on DEVICE arrays (slab decomposition): after
+ * vofx_track_changes( ctx, 1 ) every update records the (cell, new value) pairs it writes; vofx_changed_fetch copies
+ * the pairs of the last finished pass into a HOST colour function: u_host[ storage index + index_offset ] = value. */
+int vofx_track_changes ( vofx_ctx *ctx, int enable );
+int vofx_changed_fetch ( vofx_ctx *ctx, double *u_host, int64_t index_offset, int64_t *n_changed );
 
 /* context-resident colour function (what a drop-in for Algorithm::operator() uses, algorithm.hh:54-103): upload the
  * host colour function once, run loop passes on the device mirror, download when the data writer wants it */

@@ -80,6 +80,30 @@ def main():
                 failures.append((n, problem, recon, "graph"))
             if rank == 0:
                 print(f"   graph replay: {'bit-identical' if int(ok2.item()) == 1 else 'MISMATCH'}", flush=True)
+        # host-resident slab: H2D every pass, changed (cell, value) pairs written back (what bench.py's e2e does for N > 1)
+        if recon == ops.RECON_YOUNGS:
+            import ctypes as C
+            from dune_vof_b200.lib import check
+            slab3 = SlabAlgorithm(n, rank, world, 0.5, 1e-6, recon, device=local)
+            g3 = slab3.grid
+            g3.set_velocity_builtin(problem)
+            u3 = g3.empty("color")
+            own3 = slab3.owned(u3)
+            host = u0.view(n[-1], layer)[lo:lo + cnt].contiguous().cpu().pin_memory()
+            check(g3._L.vofx_track_changes(g3._ctx, 1))
+            slab3.begin(0.0, 0.0)
+            nchg = C.c_int64(0)
+            for _ in range(passes):
+                own3.copy_(host.view_as(own3), non_blocking=True)
+                slab3.step(u3)
+                check(g3._L.vofx_changed_fetch(g3._ctx, C.c_void_p(host.data_ptr()), C.c_int64(-slab3.exchanger.halo * slab3.layer_cells), C.byref(nchg)))
+            same3 = torch.equal(host.view(torch.int64), ref.contiguous().cpu().view(torch.int64))
+            ok3 = torch.tensor([1 if same3 else 0], device="cuda")
+            dist.all_reduce(ok3, op=dist.ReduceOp.MIN)
+            if int(ok3.item()) != 1:
+                failures.append((n, problem, recon, "host slab"))
+            if rank == 0:
+                print(f"   host-resident slab with sparse write-back: {'bit-identical' if int(ok3.item()) == 1 else 'MISMATCH'}", flush=True)
         g1.close()
     dist.barrier()
     torch.cuda.synchronize()
