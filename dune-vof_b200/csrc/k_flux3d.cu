@@ -9,11 +9,14 @@ namespace vofx
     void flux3 ( int blocks, cudaStream_t s, Grid g, const Velocity *velocity, const double *hs, const unsigned char *flags, const int *mixedList,
                  StepState *state, int capacity, FluxRecord *records, const double *timeOverride, const double *dtOverride )
     { k_flux< 3 ><<< blocks, 128, 0, s >>>( g, velocity, hs, flags, mixedList, state, capacity, records, timeOverride, dtOverride ); }
-    void flux_cell3 ( int blocks, cudaStream_t s, Grid g, const Velocity *velocity, const Velocity &velocityByValue, const double *hs, const unsigned char *flags, const int *mixedList,
+    void flux_cell3 ( int lanes, int blocks, cudaStream_t s, Grid g, const Velocity *velocity, const Velocity &velocityByValue, const double *hs, const unsigned char *flags, const int *mixedList,
                       StepState *state, int capacity, FluxRecord *records, int *tasks, int taskCapacity, const void *clipTable,
                       const double *timeOverride, const double *dtOverride )
     {
-      k_flux_cell3< 3 ><<< blocks, 128, 0, s >>>( g, velocityByValue, hs, flags, mixedList, state, capacity, records, tasks, taskCapacity, (const coop::ClipCase *) clipTable, timeOverride, dtOverride );
+      if( lanes == 4 )
+        k_flux_cell3< 3, 4 ><<< blocks * 2, 64, 0, s >>>( g, velocityByValue, hs, flags, mixedList, state, capacity, records, tasks, taskCapacity, (const coop::ClipCase *) clipTable, timeOverride, dtOverride );
+      else
+        k_flux_cell3< 3, 8 ><<< blocks, 128, 0, s >>>( g, velocityByValue, hs, flags, mixedList, state, capacity, records, tasks, taskCapacity, (const coop::ClipCase *) clipTable, timeOverride, dtOverride );
       k_flux_clip_serial3< 3 ><<< 148, 64, 0, s >>>( g, velocity, hs, flags, mixedList, state, records, tasks, taskCapacity, timeOverride, dtOverride );
     }
     void make_clip_table ( void *host256x64 ) { coop::make_clip_table( (coop::ClipCase *) host256x64 ); }

@@ -1562,15 +1562,15 @@ namespace vofx
 #ifndef VOFX_FLUX_BLOCKS_PER_SM
 #define VOFX_FLUX_BLOCKS_PER_SM 4
 #endif
-  template< int DIM_ >
-  __global__ void __launch_bounds__( 128, VOFX_FLUX_BLOCKS_PER_SM ) k_flux_cell3 ( Grid g, const Velocity velocity, const double *__restrict__ hs,
+  template< int DIM_, int L >
+  __global__ void __launch_bounds__( 16 * L, VOFX_FLUX_BLOCKS_PER_SM * 8 / L ) k_flux_cell3 ( Grid g, const Velocity velocity, const double *__restrict__ hs,
                                                               const unsigned char *__restrict__ flags, const int *__restrict__ mixedList,
                                                               StepState *state, int capacity, FluxRecord *__restrict__ records,
                                                               int *__restrict__ tasks, int taskCapacity, const coop::ClipCase *__restrict__ clipTable,
                                                               const double *timeOverride, const double *dtOverride )
   {
-    constexpr int DIM = 3, LANES = coop::kLanes, NFACES = 6;
-    constexpr int GROUPS = 128 / LANES;
+    constexpr int DIM = 3, LANES = L, NFACES = 6;
+    constexpr int GROUPS = 16;          // 128 threads for 8 lanes per cell, 64 for 4
     __shared__ coop::ClipCase table[ 256 ];
     __shared__ coop::ClipScratch scratch[ GROUPS ];
     __shared__ FaceScratch faceScratch[ GROUPS ];
@@ -1591,7 +1591,7 @@ namespace vofx
     velocity_time_factors( velocity, time, tf );
     const int lane = threadIdx.x % LANES;
     const int group = threadIdx.x / LANES;
-    const unsigned groupMask = 0xffu << ( ( threadIdx.x & 31 ) - lane );
+    const unsigned groupMask = ( ( 1u << LANES ) - 1u ) << ( ( threadIdx.x & 31 ) - lane );
     coop::ClipScratch &S = scratch[ group ];
     FaceScratch &F = faceScratch[ group ];
     double dtMin = DBL_MAX;
@@ -1603,9 +1603,9 @@ namespace vofx
       cell_ijk( g, c, ijk );
       FluxRecord *r = records + idx;
 
-      if( lane < NFACES )
+#pragma unroll 1
+      for( int face = lane; face < NFACES; face += LANES )
       {
-        const int face = lane;
         bool hasNb = false, hasSelf = false, hasNbc = false, needClip = false;
         double sf = 0.0, selfc = 0.0;
         unsigned char flagNb = 99;
@@ -1690,20 +1690,31 @@ namespace vofx
         if( valid )
         {
           const double v[ 3 ] = { F.v[ face ][ 0 ], F.v[ face ][ 1 ], F.v[ face ][ 2 ] };
-          double xn[ 3 ];
-          coop::upwind_node_oriented( lane, lo, g.h, face, v, F.shiftedFirst[ face ] != 0, xn );
-          coop::clip_phase_classify( lane, S, xn, H );
+#pragma unroll
+          for( int node = lane; node < 8; node += LANES )
+          {
+            double xn[ 3 ];
+            coop::upwind_node_oriented( node, lo, g.h, face, v, F.shiftedFirst[ face ] != 0, xn );
+            coop::clip_phase_classify( node, S, xn, H );
+          }
           __syncwarp( groupMask );
           const coop::ClipCase *cs;
-          const int status = coop::clip_phase_cut( lane, S, H, table, cs );
+          int status = 0;
+#pragma unroll
+          for( int j = lane; j < 8; j += LANES )
+            status = coop::clip_phase_cut( j, S, H, table, cs );
           __syncwarp( groupMask );
           if( status == 0 )
           {
-            coop::clip_phase_faces( lane, S, *cs );
+#pragma unroll
+            for( int f = lane; f < 8; f += LANES )
+              coop::clip_phase_faces( f, S, *cs );
             __syncwarp( groupMask );
             coop::clip_phase_edges< LANES >( lane, S, *cs );
             __syncwarp( groupMask );
-            coop::clip_phase_face_sums( lane, S, *cs );
+#pragma unroll
+            for( int f = lane; f < 8; f += LANES )
+              coop::clip_phase_face_sums( f, S, *cs );
             __syncwarp( groupMask );
             flux = coop::clip_phase_sum( S, *cs );
           }
@@ -1743,7 +1754,7 @@ namespace vofx
     __syncthreads();
     if( threadIdx.x == 0 )
     {
-      for( int w = 1; w < 4; ++w )
+      for( int w = 1; w < ( 16 * L ) / 32; ++w )
         dtMin = ( blockMin[ w ] < dtMin ) ? blockMin[ w ] : dtMin;
       if( dtMin < DBL_MAX )
         atomic_min_positive( &state->dtEst, dtMin );

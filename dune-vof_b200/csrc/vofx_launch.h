@@ -71,7 +71,7 @@ namespace vofx
                            int capacity, double *hs, int maxIterations, const void *sweepTable, void *cells, void *tasks, int *counter );
     void flux3 ( int blocks, cudaStream_t s, Grid g, const Velocity *velocity, const double *hs, const unsigned char *flags, const int *mixedList,
                  StepState *state, int capacity, FluxRecord *records, const double *timeOverride, const double *dtOverride );
-    void flux_cell3 ( int blocks, cudaStream_t s, Grid g, const Velocity *velocity, const Velocity &velocityByValue, const double *hs, const unsigned char *flags, const int *mixedList,
+    void flux_cell3 ( int lanes, int blocks, cudaStream_t s, Grid g, const Velocity *velocity, const Velocity &velocityByValue, const double *hs, const unsigned char *flags, const int *mixedList,
                       StepState *state, int capacity, FluxRecord *records, int *tasks, int taskCapacity, const void *clipTable,
                       const double *timeOverride, const double *dtOverride );
     void make_clip_table ( void *host256x64 );   // 256 entries of 64 bytes (coop::ClipCase)

@@ -39,6 +39,7 @@ extern "C" {
 
 /* Tunables read from the environment at context creation / launch (defaults are the measured optima on B200):
  *   VOFX_LANES_PER_CELL = 4 | 8   lanes per mixed cell of the 3D Young's / height-function kernel (default 4)
+ *   VOFX_FLUX_LANES     = 8 | 4   lanes per mixed cell of the 3D flux kernel (default 8)
  *   VOFX_SWARTZ_LANES   = 4 | 8   lanes per task of the 3D Swartz kernels (default 4)
  *   VOFX_SWARTZ_MODE    = batched (default) | cell | serial   formulation of the 3D Swartz reconstruction */
 
