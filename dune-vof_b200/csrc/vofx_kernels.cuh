@@ -1574,7 +1574,7 @@ namespace vofx
     __shared__ coop::ClipCase table[ 256 ];
     __shared__ coop::ClipScratch scratch[ GROUPS ];
     __shared__ FaceScratch faceScratch[ GROUPS ];
-    __shared__ double blockMin[ 4 ];
+    __shared__ double blockMin[ ( 16 * L + 31 ) / 32 ];
     {
       const uint4 *src = reinterpret_cast< const uint4 * >( clipTable );
       uint4 *dst = reinterpret_cast< uint4 * >( table );

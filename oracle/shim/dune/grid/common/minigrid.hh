@@ -43,10 +43,11 @@ namespace Dune
   struct GeometryType
   {
     int dim;
-    bool isCube () const { return true; }
-    bool isSimplex () const { return false; }
-    bool isTriangle () const { return false; }
-    bool isQuadrilateral () const { return dim == 2; }
+    bool simplex = false;   // only the unstructured model (meshgrid.hh) has simplices
+    bool isCube () const { return !simplex; }
+    bool isSimplex () const { return simplex; }
+    bool isTriangle () const { return dim == 2 && simplex; }
+    bool isQuadrilateral () const { return dim == 2 && !simplex; }
     bool isLine () const { return dim == 1; }
   };
 

@@ -3008,3 +3008,171 @@ int vo_interface ( int dim, const double *lo, const double *h, const double *hs,
   }
   return 0;
 }
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Unstructured 2D meshes: the same operators on flattened arrays (vo_mesh).  F1 flagging.hh:35-70,
+ * R1 reconstruction/modifiedyoungs.hh:63-134 with the CSR vertex stencil of stencil/vertexneighborsstencil.hh:52-94,
+ * E1 evolution/evolution.hh:58-145, G7 2d/upwindpolygon.hh:24-30.  Pinned against oracle/_ref/libvofrefmesh.so.
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* makePolygon( geometry ), 2d/polygon.hh:230-241: triangle corners 0,1,2; quadrilateral corners 0,1,3,2 */
+static int mesh_cell_polygon ( const vo_mesh *m, int64_t cell, vo_polygon *p )
+{
+  const int b = m->corner_offsets[ cell ], n = m->corner_offsets[ cell + 1 ] - b;
+  static const int tri[ 3 ] = { 0, 1, 2 }, quad[ 4 ] = { 0, 1, 3, 2 };
+  if( n != 3 && n != 4 )
+    return 1;                                 /* DUNE_THROW( InvalidStateException, "Invalid GeometryType." ) */
+  const int *order = ( n == 3 ) ? tri : quad;
+  p->n = n;
+  for( int k = 0; k < n; ++k )
+  {
+    p->v[ k ][ 0 ] = m->corners[ 2 * ( b + order[ k ] ) ];
+    p->v[ k ][ 1 ] = m->corners[ 2 * ( b + order[ k ] ) + 1 ];
+  }
+  return 0;
+}
+
+int vo_mesh_flag ( const vo_mesh *m, const double *u, double eps, uint8_t *flags )
+{
+  for( int64_t c = 0; c < m->n_cells; ++c )
+  {
+    const double colorEn = u[ c ];
+    uint8_t flag;
+    if( colorEn < eps )
+      flag = 0;
+    else if( colorEn <= ( 1 - eps ) )
+      flag = 1;
+    else if( isnan( colorEn ) )
+      flag = 99;
+    else
+    {
+      flag = 3;
+      for( int s = m->face_offsets[ c ]; s < m->face_offsets[ c + 1 ]; ++s )
+        if( m->face_neighbor[ s ] >= 0 && u[ m->face_neighbor[ s ] ] < eps )
+        {
+          flag = 2;
+          break;
+        }
+    }
+    flags[ c ] = flag;
+  }
+  return 0;
+}
+
+int vo_mesh_locate ( const vo_mesh *m, int64_t cell, const double *normal, double fraction, double *out )
+{
+  vo_polygon p;
+  if( mesh_cell_polygon( m, cell, &p ) )
+    return 1;
+  locate_2d( &p, normal, fraction, out );
+  return 0;
+}
+
+/* applyLocal, modifiedyoungs.hh:90-134 */
+static int mesh_youngs_local ( const vo_mesh *m, const double *u, int64_t cell, double *hs )
+{
+  const double *center = m->centers + 2 * cell;
+  const double colorEn = u[ cell ];
+  double AtA[ 3 ][ 3 ] = { { 0, 0, 0 }, { 0, 0, 0 }, { 0, 0, 0 } };
+  double Atb[ 3 ] = { 0, 0, 0 };
+
+  for( int s = m->stencil_offsets[ cell ]; s < m->stencil_offsets[ cell + 1 ]; ++s )
+  {
+    const int64_t nb = m->stencil[ s ];
+    const double colorNb = clampd( u[ nb ], 0.0, 1.0 );
+    double d[ 2 ] = { m->centers[ 2 * nb ] - center[ 0 ], m->centers[ 2 * nb + 1 ] - center[ 1 ] };
+    ls_accumulate( 2, d, colorNb - colorEn, AtA, Atb );
+  }
+  for( int s = m->face_offsets[ cell ]; s < m->face_offsets[ cell + 1 ]; ++s )
+  {
+    if( m->face_neighbor[ s ] >= 0 )
+      continue;
+    double d[ 2 ] = { m->face_centers[ 2 * s ] - center[ 0 ], m->face_centers[ 2 * s + 1 ] - center[ 1 ] };
+    d[ 0 ] *= 2.0;
+    d[ 1 ] *= 2.0;
+    ls_accumulate( 2, d, 0.5 - colorEn, AtA, Atb );
+  }
+
+  double normal[ 3 ] = { 0, 0, 0 };
+  solve_small( 2, AtA, Atb, normal );
+  if( norm2n( normal, 2 ) < VO_EPS )
+    return 0;
+  const double nrm = normn( normal, 2 );
+  normal[ 0 ] /= nrm;
+  normal[ 1 ] /= nrm;
+  return vo_mesh_locate( m, cell, normal, colorEn, hs );
+}
+
+int vo_mesh_youngs ( const vo_mesh *m, const double *u, const uint8_t *flags, double *hs )
+{
+  memset( hs, 0, sizeof( double ) * 3 * (size_t) m->n_cells );   /* reconstructions.clear(), :65 */
+  for( int64_t c = 0; c < m->n_cells; ++c )
+    if( is_mixed( flags[ c ] ) && mesh_youngs_local( m, u, c, hs + 3 * c ) )
+      return 1;
+  return 0;
+}
+
+/* truncVolume( upwindPolygon2d( iGeometry, v ), hs ), 2d/upwindpolygon.hh:24-30 + geometry/upwindpolygon.hh:58-62 */
+static double mesh_flux ( const double *c0, const double *c1, const double *v, const double *hs )
+{
+  const double d[ 2 ] = { c1[ 0 ] - c0[ 0 ], c1[ 1 ] - c0[ 1 ] };
+  const double cr[ 2 ] = { -d[ 1 ], d[ 0 ] };   /* generalizedCrossProduct 2D, geometry/utility.hh:82-85 */
+  vo_polygon up, cl;
+  up.n = 4;
+  const double *a = c0, *b = c1;
+  if( !( dotn( cr, v, 2 ) < 0.0 ) )
+  {
+    a = c1;
+    b = c0;
+  }
+  up.v[ 0 ][ 0 ] = a[ 0 ]; up.v[ 0 ][ 1 ] = a[ 1 ];
+  up.v[ 1 ][ 0 ] = b[ 0 ]; up.v[ 1 ][ 1 ] = b[ 1 ];
+  up.v[ 2 ][ 0 ] = b[ 0 ] - v[ 0 ]; up.v[ 2 ][ 1 ] = b[ 1 ] - v[ 1 ];
+  up.v[ 3 ][ 0 ] = a[ 0 ] - v[ 0 ]; up.v[ 3 ][ 1 ] = a[ 1 ] - v[ 1 ];
+  polygon_clip( &up, hs, &cl );
+  return polygon_volume( &cl );
+}
+
+int vo_mesh_evolve ( const vo_mesh *m, const double *hs, const uint8_t *flags, const double *face_velocity, double dt, double *update, double *dt_est )
+{
+  double dtEst = DBL_MAX;
+  memset( update, 0, sizeof( double ) * (size_t) m->n_cells );   /* update.clear(), :62 */
+  for( int64_t c = 0; c < m->n_cells; ++c )
+  {
+    if( !is_mixed( flags[ c ] ) )
+      continue;
+    double sumFluxes = 0.0;
+    const double volume = m->volumes[ c ];
+    for( int s = m->face_offsets[ c ]; s < m->face_offsets[ c + 1 ]; ++s )
+    {
+      const int64_t nb = m->face_neighbor[ s ];
+      if( nb < 0 )
+        continue;
+      const double *outerNormal = m->face_unit_normals + 2 * s;
+      const double *intNormal = m->face_int_normals + 2 * s;
+      double v[ 2 ] = { face_velocity[ 2 * s ], face_velocity[ 2 * s + 1 ] };
+      sumFluxes += m->face_volumes[ s ] * fabs( dotn( outerNormal, v, 2 ) );
+      v[ 0 ] *= dt;
+      v[ 1 ] *= dt;
+      double flux = 0.0;
+      if( dotn( v, outerNormal, 2 ) > 0 )
+      {
+        flux = mesh_flux( m->face_corners + 4 * s, m->face_corners + 4 * s + 2, v, hs + 3 * c );
+        update[ c ] -= flux / volume;
+        if( flags[ nb ] == 3 )
+          update[ nb ] -= ( ( dotn( v, intNormal, 2 ) ) - flux ) / m->volumes[ nb ];
+        if( flags[ nb ] == 0 )
+          update[ nb ] += flux / m->volumes[ nb ];
+        if( is_mixed( flags[ nb ] ) )
+          update[ nb ] += flux / m->volumes[ nb ];
+      }
+      if( flags[ nb ] == 3 )
+        if( dotn( v, outerNormal, 2 ) < 0 )
+          update[ c ] -= ( dotn( v, intNormal, 2 ) ) / volume;
+    }
+    const double est = volume / sumFluxes;
+    dtEst = ( est < dtEst ) ? est : dtEst;
+  }
+  *dt_est = dtEst;
+  return 0;
+}

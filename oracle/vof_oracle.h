@@ -51,6 +51,31 @@ int vo_interface ( int dim, const double *lo, const double *h, const double *hs,
 double vo_brent_cubic ( double A, double B, double C, double target, double a, double b, double tol );
 double vo_det_cospi ( double s );
 
+/* ---- unstructured 2D meshes (triangles and quadrilaterals) as flattened arrays: the layout of include/vofx.h's
+ *      vofx_mesh_desc.  All geometry of the grid (centres, volumes, normals) is DATA supplied by the grid side. ---- */
+typedef struct
+{
+  int64_t n_cells;
+  const int32_t *corner_offsets;     /* [n_cells+1] */
+  const double *corners;             /* [..][2] cell corners in DUNE corner order */
+  const double *centers;             /* [n_cells][2] */
+  const double *volumes;             /* [n_cells] */
+  const int32_t *face_offsets;       /* [n_cells+1] intersections in iteration order */
+  const int32_t *face_neighbor;      /* outside cell or -1 */
+  const double *face_corners;        /* [..][2][2] */
+  const double *face_centers;        /* [..][2] */
+  const double *face_unit_normals;   /* [..][2] centerUnitOuterNormal */
+  const double *face_int_normals;    /* [..][2] integrationOuterNormal at the centre */
+  const double *face_volumes;        /* [..] */
+  const int32_t *stencil_offsets;    /* [n_cells+1] CSR vertex-neighbour stencil, */
+  const int32_t *stencil;            /*             ascending cell index, self excluded */
+} vo_mesh;
+
+int vo_mesh_flag ( const vo_mesh *m, const double *u, double eps, uint8_t *flags );
+int vo_mesh_youngs ( const vo_mesh *m, const double *u, const uint8_t *flags, double *hs );
+int vo_mesh_evolve ( const vo_mesh *m, const double *hs, const uint8_t *flags, const double *face_velocity, double dt, double *update, double *dt_est );
+int vo_mesh_locate ( const vo_mesh *m, int64_t cell, const double *normal, double fraction, double *out );
+
 #ifdef __cplusplus
 }
 #endif
