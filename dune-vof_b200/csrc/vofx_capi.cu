@@ -37,6 +37,12 @@ namespace
 
 } // namespace
 
+namespace vofx
+{
+  // the error text of this thread, shared with the other translation units of the C ABI (vofx_mesh.cu)
+  int set_error ( int status, const std::string &msg ) { return fail( status, msg ); }
+}
+
 struct vofx_ctx
 {
   vofx_grid_desc desc;

@@ -1,0 +1,751 @@
+// vofx on unstructured 2D grids (triangles and quadrilaterals given as flattened arrays, include/vofx.h: vofx_mesh_desc):
+// kernels and the C ABI.  The arithmetic restates, operation for operation (vofx_math.cuh, -fmad=false),
+//   F1  flagging.hh:35-70
+//   R1  reconstruction/modifiedyoungs.hh:63-134 over the CSR vertex-neighbour stencil (stencil/vertexneighborsstencil.hh:52-94)
+//   G1  locateHalfSpace( Polygon ), geometry/algorithm.hh:68-111        (vofx_geom2d.cuh)
+//   E1  evolution/evolution.hh:58-145, G7 2d/upwindpolygon.hh:24-30
+// Layout: SoA device copies of the descriptor arrays; flags 1 B/cell; half-spaces (n, d) 24 B/cell; per-intersection flux
+// records (flux, v.N, direction) written by the mixed cells and GATHERED by every cell in the reference's accumulation
+// order (ascending index of the contributing mixed cell, its faces in order), so that no atomics touch the update and
+// the sums carry the reference's bits.
+#include "../../include/vofx.h"
+
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "vofx_geom2d.cuh"
+
+namespace vofx
+{
+  int set_error ( int status, const std::string &msg );   // vofx_capi.cu
+}
+
+using namespace vofx;
+
+namespace
+{
+
+#define VOFX_MESH_CUDA( call )                                                                                  \
+  do                                                                                                            \
+  {                                                                                                             \
+    const cudaError_t vofx_err_ = ( call );                                                                     \
+    if( vofx_err_ != cudaSuccess )                                                                              \
+      return set_error( VOFX_ERR_CUDA, std::string( #call ) + ": " + cudaGetErrorString( vofx_err_ ) );         \
+  } while( 0 )
+
+  struct MeshDev
+  {
+    int nCells, nFaces;
+    const int *cornerOffsets;
+    const double *corners, *centers, *volumes;
+    const int *faceOffsets, *faceNeighbor, *backSlot;
+    const double *faceCorners, *faceCenters, *faceUnit, *faceInt, *faceVolumes;
+    const int *stencilOffsets, *stencil;
+  };
+
+  // device-resident loop state
+  struct MeshState
+  {
+    double time, dt;
+    unsigned long long dtEstBits;   // min over the mixed cells of volume / sumFluxes, as the bits of a non-negative double
+    int mixedCount, pad;
+  };
+
+  __device__ __forceinline__ bool is_mixed ( unsigned char f ) { return f == 1 || f == 2; }   // flagset.hh:71-72,78
+
+  // flagging.hh:35-70; mixed cells are appended to the list (its order does not enter any result)
+  __global__ void __launch_bounds__( 256 ) k_mesh_flag ( MeshDev M, const double *__restrict__ u, double eps, unsigned char *__restrict__ flags,
+                                                          int *__restrict__ mixedList, MeshState *state )
+  {
+    for( int c = blockIdx.x * blockDim.x + threadIdx.x; c < M.nCells; c += gridDim.x * blockDim.x )
+    {
+      const double colorEn = u[ c ];
+      unsigned char flag;
+      if( colorEn < eps )
+        flag = 0;
+      else if( colorEn <= ( 1 - eps ) )
+        flag = 1;
+      else if( colorEn != colorEn )
+        flag = 99;
+      else
+      {
+        flag = 3;
+        for( int s = M.faceOffsets[ c ]; s < M.faceOffsets[ c + 1 ]; ++s )
+        {
+          const int nb = M.faceNeighbor[ s ];
+          if( nb >= 0 && u[ nb ] < eps )
+          {
+            flag = 2;
+            break;
+          }
+        }
+      }
+      flags[ c ] = flag;
+      if( mixedList && is_mixed( flag ) )
+        mixedList[ atomicAdd( &state->mixedCount, 1 ) ] = c;
+    }
+  }
+
+  __global__ void __launch_bounds__( 256 ) k_mesh_list_mixed ( MeshDev M, const unsigned char *__restrict__ flags, int *__restrict__ mixedList,
+                                                                MeshState *state )
+  {
+    for( int c = blockIdx.x * blockDim.x + threadIdx.x; c < M.nCells; c += gridDim.x * blockDim.x )
+      if( is_mixed( flags[ c ] ) )
+        mixedList[ atomicAdd( &state->mixedCount, 1 ) ] = c;
+  }
+
+  // one least-squares contribution, modifiedyoungs.hh:104-108 / :117-123
+  __device__ __forceinline__ void ls_accumulate2 ( double dx, double dy, double colorDiff, double AtA[ 2 ][ 2 ], double *Atb )
+  {
+    double n2 = 0.0;
+    n2 += dx * dx;
+    n2 += dy * dy;
+    const double weight = 1.0 / n2;
+    const double d[ 2 ] = { dx * weight, dy * weight };
+#pragma unroll
+    for( int i = 0; i < 2; ++i )
+#pragma unroll
+      for( int j = 0; j < 2; ++j )
+      {
+        double m = 0.0;          // outerProduct: axpy onto a zero matrix, geometry/utility.hh:161-169
+        m += d[ i ] * d[ j ];
+        AtA[ i ][ j ] += m;
+      }
+    const double w = weight * colorDiff;
+    Atb[ 0 ] += w * d[ 0 ];
+    Atb[ 1 ] += w * d[ 1 ];
+  }
+
+  // makePolygon( geometry ), 2d/polygon.hh:230-241
+  __device__ __forceinline__ void cell_polygon ( const MeshDev &M, int c, Poly2 &p )
+  {
+    const int b = M.cornerOffsets[ c ], n = M.cornerOffsets[ c + 1 ] - b;
+    p.n = n;
+    for( int k = 0; k < n; ++k )
+    {
+      const int src = ( n == 4 && k >= 2 ) ? 5 - k : k;   // quadrilateral: corners 0,1,3,2
+      p.x[ k ] = M.corners[ 2 * ( b + src ) ];
+      p.y[ k ] = M.corners[ 2 * ( b + src ) + 1 ];
+    }
+  }
+
+  // applyLocal, modifiedyoungs.hh:90-134: one thread per mixed cell; the half-spaces were cleared before
+  __global__ void __launch_bounds__( 128 ) k_mesh_youngs ( MeshDev M, const double *__restrict__ u, const int *__restrict__ mixedList,
+                                                            const MeshState *state, double *__restrict__ hs )
+  {
+    const int count = state->mixedCount;
+    for( int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < count; idx += gridDim.x * blockDim.x )
+    {
+      const int c = mixedList[ idx ];
+      const double cx = M.centers[ 2 * c ], cy = M.centers[ 2 * c + 1 ];
+      const double colorEn = u[ c ];
+      double AtA[ 2 ][ 2 ] = { { 0.0, 0.0 }, { 0.0, 0.0 } }, Atb[ 2 ] = { 0.0, 0.0 };
+      for( int s = M.stencilOffsets[ c ]; s < M.stencilOffsets[ c + 1 ]; ++s )
+      {
+        const int nb = M.stencil[ s ];
+        const double colorNb = clamp01( u[ nb ] );
+        ls_accumulate2( M.centers[ 2 * nb ] - cx, M.centers[ 2 * nb + 1 ] - cy, colorNb - colorEn, AtA, Atb );
+      }
+      // boundary intersections get a ghost with colour 0.5 at twice the distance of the intersection centre, :112-124
+      for( int s = M.faceOffsets[ c ]; s < M.faceOffsets[ c + 1 ]; ++s )
+      {
+        if( M.faceNeighbor[ s ] >= 0 )
+          continue;
+        double dx = M.faceCenters[ 2 * s ] - cx, dy = M.faceCenters[ 2 * s + 1 ] - cy;
+        dx *= 2.0;
+        dy *= 2.0;
+        ls_accumulate2( dx, dy, 0.5 - colorEn, AtA, Atb );
+      }
+      // FieldMatrix< double, 2, 2 >::solve (dune-common closed form, DESIGN.md "parity unpinned")
+      double detinv = AtA[ 0 ][ 0 ] * AtA[ 1 ][ 1 ] - AtA[ 0 ][ 1 ] * AtA[ 1 ][ 0 ];
+      detinv = 1.0 / detinv;
+      double nx = detinv * ( AtA[ 1 ][ 1 ] * Atb[ 0 ] - AtA[ 0 ][ 1 ] * Atb[ 1 ] );
+      double ny = detinv * ( AtA[ 0 ][ 0 ] * Atb[ 1 ] - AtA[ 1 ][ 0 ] * Atb[ 0 ] );
+      const double n2 = dot2( nx, ny, nx, ny );
+      if( n2 < kEps )
+        continue;                       // the reconstruction stays the zero half-space, :128-129
+      const double nrm = sqrt( n2 );
+      nx = nx / nrm;
+      ny = ny / nrm;
+      Poly2 p;
+      cell_polygon( M, c, p );
+      const double dist = locate( p, nx, ny, colorEn );
+      hs[ 3 * c ] = nx;
+      hs[ 3 * c + 1 ] = ny;
+      hs[ 3 * c + 2 ] = dist;
+    }
+  }
+
+  // truncVolume( upwindPolygon2d( iGeometry, v ), hs ), 2d/upwindpolygon.hh:24-30 + geometry/upwindpolygon.hh:58-62
+  __device__ double mesh_flux ( const double *fc, double vx, double vy, const Hs2 &hs )
+  {
+    double ax = fc[ 0 ], ay = fc[ 1 ], bx = fc[ 2 ], by = fc[ 3 ];
+    const double dx = bx - ax, dy = by - ay;
+    if( !( dot2( -dy, dx, vx, vy ) < 0.0 ) )   // generalizedCrossProduct( c1 - c0 ) * v, geometry/utility.hh:82-85
+    {
+      double t = ax; ax = bx; bx = t;
+      t = ay; ay = by; by = t;
+    }
+    Poly2 up, cl;
+    up.n = 4;
+    up.x[ 0 ] = ax; up.y[ 0 ] = ay;
+    up.x[ 1 ] = bx; up.y[ 1 ] = by;
+    up.x[ 2 ] = bx - vx; up.y[ 2 ] = by - vy;
+    up.x[ 3 ] = ax - vx; up.y[ 3 ] = ay - vy;
+    poly_clip( up, hs, cl );
+    return poly_volume( cl );
+  }
+
+  // the per-intersection part of Evolution::applyLocal (evolution.hh:100-141) for every mixed cell: flux and v.N of each
+  // of its intersections, the direction of v there, and the cell's time-step estimate volume / sumFluxes
+  __global__ void __launch_bounds__( 128 ) k_mesh_flux ( MeshDev M, const double *__restrict__ hs, const double *__restrict__ faceVelocity,
+                                                          const double *dtPtr, const int *__restrict__ mixedList, MeshState *state,
+                                                          double *__restrict__ recFlux, double *__restrict__ recVN, signed char *__restrict__ recDir )
+  {
+    const int count = state->mixedCount;
+    const double dt = *dtPtr;
+    for( int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < count; idx += gridDim.x * blockDim.x )
+    {
+      const int c = mixedList[ idx ];
+      const Hs2 rec = { hs[ 3 * c ], hs[ 3 * c + 1 ], hs[ 3 * c + 2 ] };
+      double sumFluxes = 0.0;
+      for( int s = M.faceOffsets[ c ]; s < M.faceOffsets[ c + 1 ]; ++s )
+      {
+        if( M.faceNeighbor[ s ] < 0 )
+          continue;
+        const double nx = M.faceUnit[ 2 * s ], ny = M.faceUnit[ 2 * s + 1 ];
+        double vx = faceVelocity[ 2 * s ], vy = faceVelocity[ 2 * s + 1 ];
+        sumFluxes += M.faceVolumes[ s ] * fabs( dot2( nx, ny, vx, vy ) );
+        vx *= dt;
+        vy *= dt;
+        const double vn = dot2( vx, vy, nx, ny );
+        double flux = 0.0;
+        if( vn > 0 )
+          flux = mesh_flux( M.faceCorners + 4 * s, vx, vy, rec );
+        recFlux[ s ] = flux;
+        recVN[ s ] = dot2( vx, vy, M.faceInt[ 2 * s ], M.faceInt[ 2 * s + 1 ] );
+        recDir[ s ] = ( vn > 0 ) ? 1 : ( ( vn < 0 ) ? -1 : 0 );
+      }
+      const double est = M.volumes[ c ] / sumFluxes;
+      if( est >= 0.0 )                  // not NaN; +inf never wins against the initial DBL_MAX
+        atomicMin( &state->dtEstBits, (unsigned long long) __double_as_longlong( est ) );
+    }
+  }
+
+  // the accumulation of Evolution::operator() (evolution.hh:64-71, :117-141) as a gather: the entity loop visits the
+  // mixed cells in ascending index and each adds to itself and to the outside cells of its intersections; cell c therefore
+  // receives, in this order, the contributions of its mixed neighbours below c, its own (if mixed), its mixed neighbours above
+  template< bool FUSED >
+  __global__ void __launch_bounds__( 256 ) k_mesh_update ( MeshDev M, const unsigned char *__restrict__ flags, const double *__restrict__ recFlux,
+                                                            const double *__restrict__ recVN, const signed char *__restrict__ recDir,
+                                                            double *__restrict__ target )
+  {
+    for( int c = blockIdx.x * blockDim.x + threadIdx.x; c < M.nCells; c += gridDim.x * blockDim.x )
+    {
+      const unsigned char flag = flags[ c ];
+      const int begin = M.faceOffsets[ c ], end = M.faceOffsets[ c + 1 ];
+      // contributors ( cell, slot in that cell ) sorted lexicographically; own entry ( c, -1 )
+      int key1[ 5 ], key2[ 5 ], n = 0;
+      if( is_mixed( flag ) )
+      {
+        key1[ n ] = c;
+        key2[ n++ ] = -1;
+      }
+      for( int s = begin; s < end && n < 5; ++s )
+      {
+        const int nb = M.faceNeighbor[ s ];
+        if( nb < 0 || !is_mixed( flags[ nb ] ) )
+          continue;
+        const int back = M.backSlot[ s ];
+        int k = n++;
+        while( k > 0 && ( key1[ k - 1 ] > nb || ( key1[ k - 1 ] == nb && key2[ k - 1 ] > back ) ) )
+        {
+          key1[ k ] = key1[ k - 1 ];
+          key2[ k ] = key2[ k - 1 ];
+          --k;
+        }
+        key1[ k ] = nb;
+        key2[ k ] = back;
+      }
+      if( n == 0 )
+      {
+        if( !FUSED )
+          target[ c ] = 0.0;             // update.clear(), :62
+        continue;
+      }
+      const double volume = M.volumes[ c ];
+      double upd = 0.0;
+      for( int k = 0; k < n; ++k )
+      {
+        if( key2[ k ] < 0 )
+        {
+          // own intersections in order, :100-141
+          for( int s = begin; s < end; ++s )
+          {
+            const int nb = M.faceNeighbor[ s ];
+            if( nb < 0 )
+              continue;
+            if( recDir[ s ] > 0 )
+              upd -= recFlux[ s ] / volume;
+            if( flags[ nb ] == 3 && recDir[ s ] < 0 )
+              upd -= recVN[ s ] / volume;
+          }
+        }
+        else
+        {
+          const int b = key2[ k ];
+          if( recDir[ b ] > 0 )
+          {
+            if( flag == 3 )
+              upd -= ( recVN[ b ] - recFlux[ b ] ) / volume;
+            if( flag == 0 )
+              upd += recFlux[ b ] / volume;
+            if( is_mixed( flag ) )
+              upd += recFlux[ b ] / volume;
+          }
+        }
+      }
+      if( FUSED )
+        target[ c ] += upd;              // uh.axpy( 1.0, update ), colorfunction.hh:31-37
+      else
+        target[ c ] = upd;
+    }
+  }
+
+  __global__ void k_mesh_begin ( MeshState *state )
+  {
+    state->mixedCount = 0;
+    state->dtEstBits = (unsigned long long) __double_as_longlong( DBL_MAX );
+  }
+
+  // algorithm.hh:89-91: time += dt (if dt > 0), dt = cfl * dtEst
+  __global__ void k_mesh_finish ( MeshState *state, double cfl )
+  {
+    if( state->dt > 0.0 )
+      state->time += state->dt;
+    state->dt = __longlong_as_double( (long long) state->dtEstBits ) * cfl;
+  }
+
+  __global__ void k_mesh_set_dt ( MeshState *state, double time, double dt )
+  {
+    state->time = time;
+    state->dt = dt;
+  }
+
+  template< class T >
+  cudaError_t upload ( T *&dst, const T *src, size_t count )
+  {
+    cudaError_t e = cudaMalloc( &dst, ( count ? count : 1 ) * sizeof( T ) );
+    if( e != cudaSuccess )
+      return e;
+    return cudaMemcpy( dst, src, count * sizeof( T ), cudaMemcpyHostToDevice );
+  }
+
+} // namespace
+
+struct vofx_mesh
+{
+  int device = 0;
+  cudaStream_t stream = nullptr, ownStream = nullptr;
+  MeshDev dev {};
+  std::vector< void * > owned;       // device allocations behind dev
+  MeshState *state = nullptr;
+  int *mixedList = nullptr;
+  double *recFlux = nullptr, *recVN = nullptr;
+  signed char *recDir = nullptr;
+  // device-resident loop + staging of the host variants
+  double *u = nullptr, *hs = nullptr, *upd = nullptr, *vel = nullptr;
+  unsigned char *flags = nullptr;
+  bool colorSet = false, velocitySet = false;
+  long long launches = 0;
+  int blocksCells = 1;
+};
+
+namespace
+{
+
+  int bandBlocks ( const vofx_mesh *m ) { return 148 * 2; }
+
+  int launchFlag ( vofx_mesh *m, const double *u, double eps, unsigned char *flags, bool list )
+  {
+    k_mesh_begin<<< 1, 1, 0, m->stream >>>( m->state );
+    k_mesh_flag<<< m->blocksCells, 256, 0, m->stream >>>( m->dev, u, eps, flags, list ? m->mixedList : nullptr, m->state );
+    m->launches += 2;
+    VOFX_MESH_CUDA( cudaGetLastError() );
+    return VOFX_OK;
+  }
+
+  int launchYoungs ( vofx_mesh *m, const double *u, double *hs )
+  {
+    VOFX_MESH_CUDA( cudaMemsetAsync( hs, 0, sizeof( double ) * 3 * size_t( m->dev.nCells ), m->stream ) );   // reconstructions.clear(), :65
+    k_mesh_youngs<<< bandBlocks( m ), 128, 0, m->stream >>>( m->dev, u, m->mixedList, m->state, hs );
+    m->launches += 1;
+    VOFX_MESH_CUDA( cudaGetLastError() );
+    return VOFX_OK;
+  }
+
+  template< bool FUSED >
+  int launchEvolve ( vofx_mesh *m, const double *hs, const unsigned char *flags, const double *vel, const double *dtPtr, double *target )
+  {
+    k_mesh_flux<<< bandBlocks( m ), 128, 0, m->stream >>>( m->dev, hs, vel, dtPtr, m->mixedList, m->state, m->recFlux, m->recVN, m->recDir );
+    k_mesh_update< FUSED ><<< m->blocksCells, 256, 0, m->stream >>>( m->dev, flags, m->recFlux, m->recVN, m->recDir, target );
+    m->launches += 2;
+    VOFX_MESH_CUDA( cudaGetLastError() );
+    return VOFX_OK;
+  }
+
+  // the mixed list for operator-level calls that receive the flags from the caller
+  int listMixed ( vofx_mesh *m, const unsigned char *flags )
+  {
+    k_mesh_begin<<< 1, 1, 0, m->stream >>>( m->state );
+    k_mesh_list_mixed<<< m->blocksCells, 256, 0, m->stream >>>( m->dev, flags, m->mixedList, m->state );
+    m->launches += 2;
+    VOFX_MESH_CUDA( cudaGetLastError() );
+    return VOFX_OK;
+  }
+
+  int checkMesh ( const vofx_mesh *m )
+  {
+    if( !m )
+      return set_error( VOFX_ERR_ARGUMENT, "null mesh" );
+    VOFX_MESH_CUDA( cudaSetDevice( m->device ) );
+    return VOFX_OK;
+  }
+
+} // namespace
+
+extern "C"
+{
+
+  int vofx_mesh_create ( const vofx_mesh_desc *d, int device, vofx_mesh **out )
+  {
+    if( !d || !out )
+      return set_error( VOFX_ERR_ARGUMENT, "vofx_mesh_create: null argument" );
+    *out = nullptr;
+    if( d->dim != 2 )
+      return set_error( VOFX_ERR_ARGUMENT, "vofx_mesh_create: only dim == 2 (triangles, quadrilaterals) is built" );
+    if( d->n_cells <= 0 || d->n_cells > 0x7fffffffLL )
+      return set_error( VOFX_ERR_ARGUMENT, "vofx_mesh_create: n_cells out of range" );
+    if( !d->corner_offsets || !d->corners || !d->centers || !d->volumes || !d->face_offsets || !d->face_neighbor || !d->face_corners
+        || !d->face_centers || !d->face_unit_normals || !d->face_int_normals || !d->face_volumes || !d->stencil_offsets || !d->stencil )
+      return set_error( VOFX_ERR_ARGUMENT, "vofx_mesh_create: null array in the descriptor" );
+    const int n = int( d->n_cells );
+    if( d->corner_offsets[ 0 ] != 0 || d->face_offsets[ 0 ] != 0 || d->stencil_offsets[ 0 ] != 0 )
+      return set_error( VOFX_ERR_ARGUMENT, "vofx_mesh_create: CSR offsets must start at 0" );
+    for( int c = 0; c < n; ++c )
+    {
+      const int nc = d->corner_offsets[ c + 1 ] - d->corner_offsets[ c ];
+      if( nc != 3 && nc != 4 )
+        return set_error( VOFX_ERR_ARGUMENT, "vofx_mesh_create: Invalid GeometryType (cells must be triangles or quadrilaterals)" );
+      const int nf = d->face_offsets[ c + 1 ] - d->face_offsets[ c ];
+      if( nf < 0 || nf > 4 )
+        return set_error( VOFX_ERR_ARGUMENT, "vofx_mesh_create: a cell has more than 4 intersections" );
+      for( int s = d->face_offsets[ c ]; s < d->face_offsets[ c + 1 ]; ++s )
+        if( d->face_neighbor[ s ] >= n || d->face_neighbor[ s ] == c )
+          return set_error( VOFX_ERR_ARGUMENT, "vofx_mesh_create: face_neighbor out of range" );
+      if( d->stencil_offsets[ c + 1 ] < d->stencil_offsets[ c ] )
+        return set_error( VOFX_ERR_ARGUMENT, "vofx_mesh_create: stencil_offsets not monotone" );
+      for( int s = d->stencil_offsets[ c ]; s < d->stencil_offsets[ c + 1 ]; ++s )
+      {
+        const int nb = d->stencil[ s ];
+        if( nb < 0 || nb >= n || nb == c || ( s > d->stencil_offsets[ c ] && d->stencil[ s - 1 ] >= nb ) )
+          return set_error( VOFX_ERR_ARGUMENT, "vofx_mesh_create: stencil must be ascending, without the cell itself" );
+      }
+    }
+    const int nFaces = d->face_offsets[ n ], nCorners = d->corner_offsets[ n ], nStencil = d->stencil_offsets[ n ];
+
+    // for every intersection the slot of the same intersection seen from the outside cell
+    std::vector< int > back( size_t( nFaces ), -1 );
+    for( int c = 0; c < n; ++c )
+      for( int s = d->face_offsets[ c ]; s < d->face_offsets[ c + 1 ]; ++s )
+      {
+        const int nb = d->face_neighbor[ s ];
+        if( nb < 0 )
+          continue;
+        int first = -1, match = -1;
+        for( int t = d->face_offsets[ nb ]; t < d->face_offsets[ nb + 1 ]; ++t )
+        {
+          if( d->face_neighbor[ t ] != c )
+            continue;
+          if( first < 0 )
+            first = t;
+          const double *a = d->face_corners + 4 * size_t( s ), *b = d->face_corners + 4 * size_t( t );
+          const bool same = a[ 0 ] == b[ 0 ] && a[ 1 ] == b[ 1 ] && a[ 2 ] == b[ 2 ] && a[ 3 ] == b[ 3 ];
+          const bool swapped = a[ 0 ] == b[ 2 ] && a[ 1 ] == b[ 3 ] && a[ 2 ] == b[ 0 ] && a[ 3 ] == b[ 1 ];
+          if( match < 0 && ( same || swapped ) )
+            match = t;
+        }
+        if( first < 0 )
+          return set_error( VOFX_ERR_ARGUMENT, "vofx_mesh_create: intersections are not symmetric (outside cell does not see the inside cell)" );
+        back[ size_t( s ) ] = ( match >= 0 ) ? match : first;
+      }
+
+    if( device >= 0 )
+      VOFX_MESH_CUDA( cudaSetDevice( device ) );
+    int current = 0;
+    VOFX_MESH_CUDA( cudaGetDevice( &current ) );
+
+    vofx_mesh *m = new vofx_mesh;
+    m->device = current;
+    MeshDev &D = m->dev;
+    D.nCells = n;
+    D.nFaces = nFaces;
+    cudaError_t e = cudaSuccess;
+    auto up = [ & ] ( auto *&dst, const auto *src, size_t count ) {
+      if( e != cudaSuccess )
+        return;
+      std::remove_const_t< std::remove_reference_t< decltype( *src ) > > *p = nullptr;
+      e = upload( p, src, count );
+      if( p )
+        m->owned.push_back( p );
+      dst = p;
+    };
+    up( D.cornerOffsets, d->corner_offsets, size_t( n ) + 1 );
+    up( D.corners, d->corners, 2 * size_t( nCorners ) );
+    up( D.centers, d->centers, 2 * size_t( n ) );
+    up( D.volumes, d->volumes, size_t( n ) );
+    up( D.faceOffsets, d->face_offsets, size_t( n ) + 1 );
+    up( D.faceNeighbor, d->face_neighbor, size_t( nFaces ) );
+    up( D.backSlot, back.data(), size_t( nFaces ) );
+    up( D.faceCorners, d->face_corners, 4 * size_t( nFaces ) );
+    up( D.faceCenters, d->face_centers, 2 * size_t( nFaces ) );
+    up( D.faceUnit, d->face_unit_normals, 2 * size_t( nFaces ) );
+    up( D.faceInt, d->face_int_normals, 2 * size_t( nFaces ) );
+    up( D.faceVolumes, d->face_volumes, size_t( nFaces ) );
+    up( D.stencilOffsets, d->stencil_offsets, size_t( n ) + 1 );
+    up( D.stencil, d->stencil, size_t( nStencil ) );
+    auto alloc = [ & ] ( auto *&p, size_t count ) {
+      if( e == cudaSuccess )
+        e = cudaMalloc( &p, ( count ? count : 1 ) * sizeof( *p ) );
+    };
+    alloc( m->state, 1 );
+    alloc( m->mixedList, size_t( n ) );
+    alloc( m->recFlux, size_t( nFaces ) );
+    alloc( m->recVN, size_t( nFaces ) );
+    alloc( m->recDir, size_t( nFaces ) );
+    alloc( m->u, size_t( n ) );
+    alloc( m->hs, 3 * size_t( n ) );
+    alloc( m->upd, size_t( n ) );
+    alloc( m->vel, 2 * size_t( nFaces ) );
+    alloc( m->flags, size_t( n ) );
+    if( e == cudaSuccess )
+      e = cudaStreamCreateWithFlags( &m->ownStream, cudaStreamNonBlocking );
+    m->stream = m->ownStream;
+    if( e == cudaSuccess )
+      e = cudaMemset( m->state, 0, sizeof( MeshState ) );
+    if( e != cudaSuccess )
+    {
+      const std::string msg = std::string( "vofx_mesh_create: " ) + cudaGetErrorString( e );
+      vofx_mesh_destroy( m );
+      return set_error( VOFX_ERR_CUDA, msg );
+    }
+    // grids in multiples of the SM count (148), grid-stride loops
+    const long long need = ( (long long) n + 255 ) / 256;
+    m->blocksCells = int( need < 148 ? need : ( ( need + 147 ) / 148 < 16 ? ( need + 147 ) / 148 : 16 ) * 148 );
+    if( m->blocksCells < 1 )
+      m->blocksCells = 1;
+    *out = m;
+    return VOFX_OK;
+  }
+
+  void vofx_mesh_destroy ( vofx_mesh *m )
+  {
+    if( !m )
+      return;
+    cudaSetDevice( m->device );
+    if( m->stream )
+      cudaStreamSynchronize( m->stream );
+    if( m->ownStream )
+      cudaStreamDestroy( m->ownStream );
+    for( void *p : m->owned )
+      cudaFree( p );
+    cudaFree( m->state );
+    cudaFree( m->mixedList );
+    cudaFree( m->recFlux );
+    cudaFree( m->recVN );
+    cudaFree( m->recDir );
+    cudaFree( m->u );
+    cudaFree( m->hs );
+    cudaFree( m->upd );
+    cudaFree( m->vel );
+    cudaFree( m->flags );
+    delete m;
+  }
+
+  int vofx_mesh_set_stream ( vofx_mesh *m, void *stream )
+  {
+    if( int rc = checkMesh( m ) )
+      return rc;
+    VOFX_MESH_CUDA( cudaStreamSynchronize( m->stream ) );
+    m->stream = stream ? static_cast< cudaStream_t >( stream ) : m->ownStream;
+    return VOFX_OK;
+  }
+
+  int64_t vofx_mesh_cells ( const vofx_mesh *m ) { return m ? m->dev.nCells : 0; }
+  int64_t vofx_mesh_faces ( const vofx_mesh *m ) { return m ? m->dev.nFaces : 0; }
+  int64_t vofx_mesh_launch_count ( const vofx_mesh *m ) { return m ? m->launches : 0; }
+
+  int vofx_mesh_flag ( vofx_mesh *m, const double *u, double eps, uint8_t *flags )
+  {
+    if( int rc = checkMesh( m ) )
+      return rc;
+    if( !u || !flags )
+      return set_error( VOFX_ERR_ARGUMENT, "vofx_mesh_flag: null argument" );
+    return launchFlag( m, u, eps, flags, false );
+  }
+
+  int vofx_mesh_reconstruct ( vofx_mesh *m, const double *u, const uint8_t *flags, double *hs )
+  {
+    if( int rc = checkMesh( m ) )
+      return rc;
+    if( !u || !flags || !hs )
+      return set_error( VOFX_ERR_ARGUMENT, "vofx_mesh_reconstruct: null argument" );
+    if( int rc = listMixed( m, flags ) )
+      return rc;
+    return launchYoungs( m, u, hs );
+  }
+
+  int vofx_mesh_evolve ( vofx_mesh *m, const double *hs, const uint8_t *flags, const double *vel, double dt, double *update, double *dtEst )
+  {
+    if( int rc = checkMesh( m ) )
+      return rc;
+    if( !hs || !flags || !vel || !update || !dtEst )
+      return set_error( VOFX_ERR_ARGUMENT, "vofx_mesh_evolve: null argument" );
+    if( int rc = listMixed( m, flags ) )
+      return rc;
+    k_mesh_set_dt<<< 1, 1, 0, m->stream >>>( m->state, 0.0, dt );
+    m->launches += 1;
+    if( int rc = launchEvolve< false >( m, hs, flags, vel, &m->state->dt, update ) )
+      return rc;
+    MeshState host;
+    VOFX_MESH_CUDA( cudaMemcpyAsync( &host, m->state, sizeof( MeshState ), cudaMemcpyDeviceToHost, m->stream ) );
+    VOFX_MESH_CUDA( cudaStreamSynchronize( m->stream ) );
+    std::memcpy( dtEst, &host.dtEstBits, sizeof( double ) );
+    return VOFX_OK;
+  }
+
+  int vofx_mesh_flag_host ( vofx_mesh *m, const double *u, double eps, uint8_t *flags )
+  {
+    if( int rc = checkMesh( m ) )
+      return rc;
+    if( !u || !flags )
+      return set_error( VOFX_ERR_ARGUMENT, "vofx_mesh_flag_host: null argument" );
+    const size_t n = size_t( m->dev.nCells );
+    VOFX_MESH_CUDA( cudaMemcpyAsync( m->u, u, n * sizeof( double ), cudaMemcpyHostToDevice, m->stream ) );
+    if( int rc = launchFlag( m, m->u, eps, m->flags, false ) )
+      return rc;
+    VOFX_MESH_CUDA( cudaMemcpyAsync( flags, m->flags, n, cudaMemcpyDeviceToHost, m->stream ) );
+    VOFX_MESH_CUDA( cudaStreamSynchronize( m->stream ) );
+    m->colorSet = false;
+    return VOFX_OK;
+  }
+
+  int vofx_mesh_reconstruct_host ( vofx_mesh *m, const double *u, const uint8_t *flags, double *hs )
+  {
+    if( int rc = checkMesh( m ) )
+      return rc;
+    if( !u || !flags || !hs )
+      return set_error( VOFX_ERR_ARGUMENT, "vofx_mesh_reconstruct_host: null argument" );
+    const size_t n = size_t( m->dev.nCells );
+    VOFX_MESH_CUDA( cudaMemcpyAsync( m->u, u, n * sizeof( double ), cudaMemcpyHostToDevice, m->stream ) );
+    VOFX_MESH_CUDA( cudaMemcpyAsync( m->flags, flags, n, cudaMemcpyHostToDevice, m->stream ) );
+    if( int rc = vofx_mesh_reconstruct( m, m->u, m->flags, m->hs ) )
+      return rc;
+    VOFX_MESH_CUDA( cudaMemcpyAsync( hs, m->hs, 3 * n * sizeof( double ), cudaMemcpyDeviceToHost, m->stream ) );
+    VOFX_MESH_CUDA( cudaStreamSynchronize( m->stream ) );
+    m->colorSet = false;
+    return VOFX_OK;
+  }
+
+  int vofx_mesh_evolve_host ( vofx_mesh *m, const double *hs, const uint8_t *flags, const double *vel, double dt, double *update, double *dtEst )
+  {
+    if( int rc = checkMesh( m ) )
+      return rc;
+    if( !hs || !flags || !vel || !update || !dtEst )
+      return set_error( VOFX_ERR_ARGUMENT, "vofx_mesh_evolve_host: null argument" );
+    const size_t n = size_t( m->dev.nCells ), nf = size_t( m->dev.nFaces );
+    VOFX_MESH_CUDA( cudaMemcpyAsync( m->hs, hs, 3 * n * sizeof( double ), cudaMemcpyHostToDevice, m->stream ) );
+    VOFX_MESH_CUDA( cudaMemcpyAsync( m->flags, flags, n, cudaMemcpyHostToDevice, m->stream ) );
+    VOFX_MESH_CUDA( cudaMemcpyAsync( m->vel, vel, 2 * nf * sizeof( double ), cudaMemcpyHostToDevice, m->stream ) );
+    m->velocitySet = false;
+    if( int rc = vofx_mesh_evolve( m, m->hs, m->flags, m->vel, dt, m->upd, dtEst ) )
+      return rc;
+    VOFX_MESH_CUDA( cudaMemcpyAsync( update, m->upd, n * sizeof( double ), cudaMemcpyDeviceToHost, m->stream ) );
+    VOFX_MESH_CUDA( cudaStreamSynchronize( m->stream ) );
+    return VOFX_OK;
+  }
+
+  int vofx_mesh_color_upload ( vofx_mesh *m, const double *u )
+  {
+    if( int rc = checkMesh( m ) )
+      return rc;
+    if( !u )
+      return set_error( VOFX_ERR_ARGUMENT, "vofx_mesh_color_upload: null argument" );
+    VOFX_MESH_CUDA( cudaMemcpyAsync( m->u, u, size_t( m->dev.nCells ) * sizeof( double ), cudaMemcpyHostToDevice, m->stream ) );
+    VOFX_MESH_CUDA( cudaStreamSynchronize( m->stream ) );
+    m->colorSet = true;
+    return VOFX_OK;
+  }
+
+  int vofx_mesh_velocity_upload ( vofx_mesh *m, const double *vel )
+  {
+    if( int rc = checkMesh( m ) )
+      return rc;
+    if( !vel )
+      return set_error( VOFX_ERR_ARGUMENT, "vofx_mesh_velocity_upload: null argument" );
+    VOFX_MESH_CUDA( cudaMemcpyAsync( m->vel, vel, 2 * size_t( m->dev.nFaces ) * sizeof( double ), cudaMemcpyHostToDevice, m->stream ) );
+    VOFX_MESH_CUDA( cudaStreamSynchronize( m->stream ) );
+    m->velocitySet = true;
+    return VOFX_OK;
+  }
+
+  int vofx_mesh_run ( vofx_mesh *m, double eps, double cfl, int passes, double *timeIO, double *dtIO )
+  {
+    if( int rc = checkMesh( m ) )
+      return rc;
+    if( !timeIO || !dtIO || passes < 0 )
+      return set_error( VOFX_ERR_ARGUMENT, "vofx_mesh_run: bad argument" );
+    if( !m->colorSet || !m->velocitySet )
+      return set_error( VOFX_ERR_STATE, "vofx_mesh_run: call vofx_mesh_color_upload and vofx_mesh_velocity_upload first" );
+    k_mesh_set_dt<<< 1, 1, 0, m->stream >>>( m->state, *timeIO, *dtIO );
+    m->launches += 1;
+    for( int pass = 0; pass < passes; ++pass )
+    {
+      if( int rc = launchFlag( m, m->u, eps, m->flags, true ) )
+        return rc;
+      if( int rc = launchYoungs( m, m->u, m->hs ) )
+        return rc;
+      if( int rc = launchEvolve< true >( m, m->hs, m->flags, m->vel, &m->state->dt, m->u ) )
+        return rc;
+      k_mesh_finish<<< 1, 1, 0, m->stream >>>( m->state, cfl );
+      m->launches += 1;
+    }
+    MeshState host;
+    VOFX_MESH_CUDA( cudaMemcpyAsync( &host, m->state, sizeof( MeshState ), cudaMemcpyDeviceToHost, m->stream ) );
+    VOFX_MESH_CUDA( cudaStreamSynchronize( m->stream ) );
+    *timeIO = host.time;
+    *dtIO = host.dt;
+    return VOFX_OK;
+  }
+
+  int vofx_mesh_color_download ( vofx_mesh *m, double *u, uint8_t *flags )
+  {
+    if( int rc = checkMesh( m ) )
+      return rc;
+    if( !u )
+      return set_error( VOFX_ERR_ARGUMENT, "vofx_mesh_color_download: null argument" );
+    if( !m->colorSet )
+      return set_error( VOFX_ERR_STATE, "vofx_mesh_color_download: no device-resident colour function" );
+    VOFX_MESH_CUDA( cudaMemcpyAsync( u, m->u, size_t( m->dev.nCells ) * sizeof( double ), cudaMemcpyDeviceToHost, m->stream ) );
+    if( flags )
+      VOFX_MESH_CUDA( cudaMemcpyAsync( flags, m->flags, size_t( m->dev.nCells ), cudaMemcpyDeviceToHost, m->stream ) );
+    VOFX_MESH_CUDA( cudaStreamSynchronize( m->stream ) );
+    return VOFX_OK;
+  }
+
+} // extern "C"

@@ -27,12 +27,23 @@ SYMBOLS = [
     "vofx_step_resident", "vofx_color_download", "vofx_interface", "vofx_interface_host", "vofx_interface_fetch", "vofx_init",
     "vofx_test_fp64_rate", "vofx_test_locate", "vofx_test_flux", "vofx_test_interface", "vofx_launch_count", "vofx_profile_enable",
     "vofx_profile_read",
+    "vofx_mesh_create", "vofx_mesh_destroy", "vofx_mesh_set_stream", "vofx_mesh_cells", "vofx_mesh_faces", "vofx_mesh_launch_count",
+    "vofx_mesh_flag", "vofx_mesh_reconstruct", "vofx_mesh_evolve", "vofx_mesh_flag_host", "vofx_mesh_reconstruct_host",
+    "vofx_mesh_evolve_host", "vofx_mesh_color_upload", "vofx_mesh_velocity_upload", "vofx_mesh_run", "vofx_mesh_color_download",
 ]
 
 
 class GridDesc(C.Structure):
     _fields_ = [("dim", C.c_int32), ("n_global", C.c_int32 * 3), ("origin", C.c_double * 3), ("h", C.c_double * 3),
                 ("lo", C.c_int32 * 3), ("n_local", C.c_int32 * 3), ("halo", C.c_int32)]
+
+
+class MeshDesc(C.Structure):
+    _fields_ = [("dim", C.c_int32), ("n_cells", C.c_int64), ("corner_offsets", C.c_void_p), ("corners", C.c_void_p),
+                ("centers", C.c_void_p), ("volumes", C.c_void_p), ("face_offsets", C.c_void_p), ("face_neighbor", C.c_void_p),
+                ("face_corners", C.c_void_p), ("face_centers", C.c_void_p), ("face_unit_normals", C.c_void_p),
+                ("face_int_normals", C.c_void_p), ("face_volumes", C.c_void_p), ("stencil_offsets", C.c_void_p),
+                ("stencil", C.c_void_p)]
 
 
 class StepParams(C.Structure):
@@ -124,6 +135,21 @@ def load():
     L.vofx_test_locate.argtypes = [C.c_int, C.c_int64, dp, dp, dp, dp, dp]
     L.vofx_test_flux.argtypes = [C.c_int, C.c_int64, dp, dp, ip, dp, dp, dp]
     L.vofx_test_interface.argtypes = [C.c_int, C.c_int64, dp, dp, dp, ip, dp, dp]
+    L.vofx_mesh_create.argtypes = [C.POINTER(MeshDesc), C.c_int, C.POINTER(C.c_void_p)]
+    L.vofx_mesh_destroy.argtypes = [vp]
+    L.vofx_mesh_destroy.restype = None
+    L.vofx_mesh_set_stream.argtypes = [vp, vp]
+    for name in ("vofx_mesh_cells", "vofx_mesh_faces", "vofx_mesh_launch_count"):
+        getattr(L, name).argtypes = [vp]
+        getattr(L, name).restype = C.c_int64
+    for suffix in ("", "_host"):
+        getattr(L, "vofx_mesh_flag" + suffix).argtypes = [vp, dp, C.c_double, bp]
+        getattr(L, "vofx_mesh_reconstruct" + suffix).argtypes = [vp, dp, bp, dp]
+        getattr(L, "vofx_mesh_evolve" + suffix).argtypes = [vp, dp, bp, dp, C.c_double, dp, C.POINTER(C.c_double)]
+    L.vofx_mesh_color_upload.argtypes = [vp, dp]
+    L.vofx_mesh_velocity_upload.argtypes = [vp, dp]
+    L.vofx_mesh_run.argtypes = [vp, C.c_double, C.c_double, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.vofx_mesh_color_download.argtypes = [vp, dp, bp]
     _lib = L
     return L
 

@@ -45,6 +45,15 @@ class FlatMesh:
     def n_faces(self) -> int:
         return int(self.face_offsets[-1])
 
+    @classmethod
+    def from_npz(cls, z, prefix: str = "mesh_") -> "FlatMesh":
+        """a flattened mesh stored field by field (tests/golden/mesh2d_*.npz)"""
+        kw = {}
+        for k in cls.__dataclass_fields__:
+            a = z[prefix + k]
+            kw[k] = int(a) if a.ndim == 0 else np.ascontiguousarray(a)
+        return cls(**kw)
+
 
 def flatten(vertices, cells) -> FlatMesh:
     """vertices: (nv, 2) floats; cells: sequence of 3- or 4-tuples of vertex ids in DUNE corner order."""
@@ -138,3 +147,74 @@ def perturbed_square(n: int, kind: str = "tri", seed: int = 0, jitter: float = 0
             else:
                 cells += [(a, b, c), (b, d, c)]
     return v, cells
+
+
+class MeshOperators:
+    """dune-vof's FlagOperator / ModifiedYoungsReconstruction / Evolution on an unstructured 2D grid, computed on the GPU
+    through the C ABI (vofx_mesh_*, include/vofx.h).  Host numpy arrays in and out; `run` keeps the colour function on
+    the device for a whole time loop (algorithm.hh:68-95).  There is no CPU fallback."""
+
+    def __init__(self, m: FlatMesh, device: int = -1):
+        import ctypes as C
+
+        from . import lib as _lib
+        self._C, self._lib, self.L = C, _lib, _lib.load()
+        self.m = m
+        a = lambda x: x.ctypes.data
+        self._desc = _lib.MeshDesc(2, m.n_cells, a(m.corner_offsets), a(m.corners), a(m.centers), a(m.volumes),
+                                   a(m.face_offsets), a(m.face_neighbor), a(m.face_corners), a(m.face_centers),
+                                   a(m.face_unit_normals), a(m.face_int_normals), a(m.face_volumes),
+                                   a(m.stencil_offsets), a(m.stencil))
+        h = C.c_void_p()
+        _lib.check(self.L.vofx_mesh_create(C.byref(self._desc), device, C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.L.vofx_mesh_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launches(self) -> int:
+        return int(self.L.vofx_mesh_launch_count(self._h))
+
+    def flag(self, u, eps):
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        flags = np.empty(self.m.n_cells, dtype=np.uint8)
+        self._lib.check(self.L.vofx_mesh_flag_host(self._h, u.ctypes.data, eps, flags.ctypes.data))
+        return flags
+
+    def youngs(self, u, flags):
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        flags = np.ascontiguousarray(flags, dtype=np.uint8)
+        hs = np.empty((self.m.n_cells, 3))
+        self._lib.check(self.L.vofx_mesh_reconstruct_host(self._h, u.ctypes.data, flags.ctypes.data, hs.ctypes.data))
+        return hs
+
+    def evolve(self, hs, flags, face_velocity, dt):
+        hs = np.ascontiguousarray(hs, dtype=np.float64)
+        flags = np.ascontiguousarray(flags, dtype=np.uint8)
+        vel = np.ascontiguousarray(face_velocity, dtype=np.float64)
+        upd = np.empty(self.m.n_cells)
+        est = self._C.c_double(0.0)
+        self._lib.check(self.L.vofx_mesh_evolve_host(self._h, hs.ctypes.data, flags.ctypes.data, vel.ctypes.data, dt,
+                                                     upd.ctypes.data, self._C.byref(est)))
+        return upd, est.value
+
+    def run(self, u, face_velocity, eps, cfl, passes, time=0.0, dt=0.0):
+        """upload, `passes` device-resident loop passes, download.  Returns (u, time, dt)."""
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        vel = np.ascontiguousarray(face_velocity, dtype=np.float64)
+        self._lib.check(self.L.vofx_mesh_color_upload(self._h, u.ctypes.data))
+        self._lib.check(self.L.vofx_mesh_velocity_upload(self._h, vel.ctypes.data))
+        t, d = self._C.c_double(time), self._C.c_double(dt)
+        self._lib.check(self.L.vofx_mesh_run(self._h, eps, cfl, passes, self._C.byref(t), self._C.byref(d)))
+        out = np.empty(self.m.n_cells)
+        self._lib.check(self.L.vofx_mesh_color_download(self._h, out.ctypes.data, None))
+        return out, t.value, d.value

@@ -230,6 +230,69 @@ int64_t vofx_launch_count ( const vofx_ctx *ctx );
 int vofx_profile_enable ( vofx_ctx *ctx, int enable );
 int vofx_profile_read ( vofx_ctx *ctx, int max_entries, char *names, double *total_ms, int64_t *launches, int *n_entries );
 
+/* ==== unstructured 2D grids (triangles and quadrilaterals): CSR vertex-neighbour stencils ==========================
+ * The grid side (the DUNE adaptor) flattens `elements( gridView )` / `intersections( gridView, entity )` into the
+ * arrays below, in leaf-index order.  All geometry the reference asks the grid for is DATA here and is used verbatim
+ * (never recomputed): geometry().corner/center/volume of cells and intersections, centerUnitOuterNormal,
+ * integrationOuterNormal at the intersection centre.  Arrays are HOST pointers, copied at creation.
+ *   corners        DUNE corner order; the library forms makePolygon( geometry ) (geometry/2d/polygon.hh:230-241:
+ *                  triangle 0,1,2; quadrilateral 0,1,3,2)
+ *   faces          the intersections of a cell in the grid's iteration order; face_neighbor = index of
+ *                  intersection.outside() or -1 without neighbour
+ *   stencil        VertexNeighborsStencil (stencil/vertexneighborsstencil.hh:52-94): all cells sharing a vertex with the
+ *                  cell, ascending index, self excluded
+ * Operators (same semantics and bits as the structured ones): flagging.hh:35-70, reconstruction/modifiedyoungs.hh:63-134
+ * (height functions and HF curvature are Cartesian-only in the reference too), evolution/evolution.hh:58-145 with
+ * 2d/upwindpolygon.hh:24-30.  The velocity is SAMPLED: one vector per intersection = what the reference's Velocity
+ * returns for refElement.position( 0, 0 ) (velocity.hh:15-20, evolution.hh:107-108).  3D simplices are not built. */
+typedef struct vofx_mesh_desc
+{
+  int32_t dim;                       /* 2 */
+  int64_t n_cells;
+  const int32_t *corner_offsets;     /* [n_cells + 1] */
+  const double *corners;             /* [corner_offsets[n_cells]][2] */
+  const double *centers;             /* [n_cells][2] */
+  const double *volumes;             /* [n_cells] */
+  const int32_t *face_offsets;       /* [n_cells + 1] */
+  const int32_t *face_neighbor;      /* [n_faces], n_faces = face_offsets[n_cells] */
+  const double *face_corners;        /* [n_faces][2][2]  intersection.geometry().corner( 0 ), corner( 1 ) */
+  const double *face_centers;        /* [n_faces][2] */
+  const double *face_unit_normals;   /* [n_faces][2] */
+  const double *face_int_normals;    /* [n_faces][2] */
+  const double *face_volumes;        /* [n_faces] */
+  const int32_t *stencil_offsets;    /* [n_cells + 1] */
+  const int32_t *stencil;            /* [stencil_offsets[n_cells]] */
+} vofx_mesh_desc;
+
+typedef struct vofx_mesh vofx_mesh;
+
+int vofx_mesh_create ( const vofx_mesh_desc *desc, int device /* -1: current */, vofx_mesh **out );
+void vofx_mesh_destroy ( vofx_mesh *mesh );
+/* launch on the caller's CUDA stream (cudaStream_t; NULL: the mesh's own non-blocking stream), like vofx_set_stream */
+int vofx_mesh_set_stream ( vofx_mesh *mesh, void *stream );
+int64_t vofx_mesh_cells ( const vofx_mesh *mesh );
+int64_t vofx_mesh_faces ( const vofx_mesh *mesh );
+int64_t vofx_mesh_launch_count ( const vofx_mesh *mesh );
+
+/* operators on DEVICE arrays: u[n_cells], flags[n_cells], halfspaces[n_cells][3] = (n, d), face_velocity[n_faces][2],
+ * update[n_cells]; dt_est is a HOST scalar (the call synchronises the mesh's stream to return it) */
+int vofx_mesh_flag ( vofx_mesh *mesh, const double *u, double eps, uint8_t *flags );
+int vofx_mesh_reconstruct ( vofx_mesh *mesh, const double *u, const uint8_t *flags, double *halfspaces );
+int vofx_mesh_evolve ( vofx_mesh *mesh, const double *halfspaces, const uint8_t *flags, const double *face_velocity, double dt,
+                       double *update, double *dt_est );
+/* the same on HOST arrays (staged through device scratch of the mesh object) */
+int vofx_mesh_flag_host ( vofx_mesh *mesh, const double *u, double eps, uint8_t *flags );
+int vofx_mesh_reconstruct_host ( vofx_mesh *mesh, const double *u, const uint8_t *flags, double *halfspaces );
+int vofx_mesh_evolve_host ( vofx_mesh *mesh, const double *halfspaces, const uint8_t *flags, const double *face_velocity, double dt,
+                            double *update, double *dt_est );
+/* the time loop of algorithm.hh:68-95 on a DEVICE-RESIDENT colour function: upload once, run `passes` loop passes
+ * (flag, Young's, evolve, u += update, time += dt if dt > 0, dt = cfl * dtEst) without any host synchronisation, read
+ * back.  time_io / dt_io are HOST scalars: in = state before the first pass, out = state after the last. */
+int vofx_mesh_color_upload ( vofx_mesh *mesh, const double *u_host );
+int vofx_mesh_velocity_upload ( vofx_mesh *mesh, const double *face_velocity_host );
+int vofx_mesh_run ( vofx_mesh *mesh, double eps, double cfl, int passes, double *time_io, double *dt_io );
+int vofx_mesh_color_download ( vofx_mesh *mesh, double *u_host, uint8_t *flags_host /* may be NULL */ );
+
 #ifdef __cplusplus
 }
 #endif
