@@ -1,0 +1,413 @@
+// Test of include/dune/vofx/unstructured.hh (needs a GPU at run time; built on the CPU box).
+//
+// A conforming mesh of triangles and quadrilaterals (jittered lattice, seeded) is put behind the unstructured grid-view
+// model of oracle/shim (test infrastructure); the adaptor flattens that grid view through the DUNE interface and is driven
+// like the reference drives its operators (algorithm.hh:57-93).  Results are compared bit-for-bit with the oracle
+// (vo_mesh_*, libvoforacle.so) on the arrays the grid view was built from.  With -DVOFX_TEST_WITH_REFERENCE (only where
+// /root/reference is mounted) the containers are the reference's own and the reference's operators run side by side.
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#define GRIDDIM 2
+#include <dune/common/fvector.hh>
+#include <dune/grid/common/meshgrid.hh>
+
+#ifdef VOFX_TEST_WITH_REFERENCE
+#include <dune/vof/colorfunction.hh>
+#include <dune/vof/flagset.hh>
+#include <dune/vof/flagging.hh>
+#include <dune/vof/reconstructionset.hh>
+#include <dune/vof/evolution.hh>
+#include <dune/vof/stencil/vertexneighborsstencil.hh>
+#include <dune/vof/reconstruction/modifiedyoungs.hh>
+#endif
+
+#include <dune/vofx/unstructured.hh>
+
+extern "C"
+{
+#include "vof_oracle.h"
+}
+
+namespace
+{
+
+  using GV = Dune::MeshGridView;
+  using Coord = Dune::FieldVector< double, 2 >;
+
+#ifndef VOFX_TEST_WITH_REFERENCE
+  enum class Flag : std::size_t { empty = 0, mixed = 1, mixedfull = 2, full = 3, nan = 99 };
+
+  template< class T >
+  struct DataSet   // interface of dune/vof/dataset.hh:26-87
+  {
+    using DataType = T;
+    explicit DataSet ( const GV &gv ) : data_( gv.indexSet().size( 0 ) ) {}
+    const T &operator[] ( std::size_t i ) const { return data_[ i ]; }
+    T &operator[] ( std::size_t i ) { return data_[ i ]; }
+    auto begin () { return data_.begin(); }
+    auto end () { return data_.end(); }
+    auto begin () const { return data_.begin(); }
+    auto end () const { return data_.end(); }
+    std::vector< T > data_;
+  };
+  struct HyperPlane { Coord n; double d; double distance () const { return d; } };
+  struct HalfSpace
+  {
+    using Coordinate = Coord;
+    HalfSpace () : n_( 0.0 ), d_( 0.0 ) {}
+    HalfSpace ( const Coord &n, double d ) : n_( n ), d_( d ) {}
+    const Coord &innerNormal () const { return n_; }
+    HyperPlane boundary () const { return { n_, d_ }; }
+    Coord n_;
+    double d_;
+  };
+  using ColorFunction = DataSet< double >;
+  using FlagSet = DataSet< Flag >;
+  using ReconstructionSet = DataSet< HalfSpace >;
+#else
+  using ColorFunction = Dune::VoF::ColorFunction< GV >;
+  using FlagSet = Dune::VoF::FlagSet< GV >;
+  using ReconstructionSet = Dune::VoF::ReconstructionSet< GV >;
+#endif
+
+  // rigid rotation, test/problems/rotatingcircle.hh:45-52, evaluated at the centre of the bound intersection
+  struct RotationVelocity
+  {
+    const Dune::MeshIntersection *is = nullptr;
+    void bind ( const Dune::MeshIntersection &i ) { is = &i; }
+    void unbind () { is = nullptr; }
+    Coord operator() ( const Dune::FieldVector< double, 1 > & ) const
+    {
+      const Coord x = is->geometry().center();
+      Coord r( { x[ 1 ] - 0.5, 0.5 - x[ 0 ] } );
+      r *= 2 * M_PI / 10;
+      return r;
+    }
+  };
+
+  int failures = 0;
+  void expect ( bool ok, const char *what )
+  {
+    std::printf( "%s %s\n", ok ? "ok  " : "FAIL", what );
+    if( !ok )
+      ++failures;
+  }
+  bool sameBits ( const double *a, const double *b, std::size_t n )
+  {
+    for( std::size_t i = 0; i < n; ++i )
+      if( std::memcmp( a + i, b + i, sizeof( double ) ) != 0 && !( a[ i ] == 0.0 && b[ i ] == 0.0 ) && !( std::isnan( a[ i ] ) && std::isnan( b[ i ] ) ) )
+        return false;
+    return true;
+  }
+
+  struct Arrays
+  {
+    std::vector< std::int32_t > cornerOffsets { 0 }, cornerVertex, faceOffsets { 0 }, faceNeighbor, stencilOffsets { 0 }, stencil;
+    std::vector< double > corners, centers, volumes, faceCorners, faceCenters, faceUnit, faceInt, faceVolumes;
+    std::int64_t nVertices = 0;
+  };
+
+  // jittered lattice; every other quadrilateral is split into two triangles
+  Arrays makeMesh ( int n )
+  {
+    Arrays A;
+    std::uint64_t seed = 12345;
+    auto rnd = [ &seed ] { seed = seed * 6364136223846793005ull + 1442695040888963407ull; return double( seed >> 11 ) / 9007199254740992.0; };
+    const double h = 1.0 / n;
+    std::vector< double > vx( ( n + 1 ) * ( n + 1 ) ), vy( vx.size() );
+    for( int j = 0; j <= n; ++j )
+      for( int i = 0; i <= n; ++i )
+      {
+        const bool interior = i > 0 && i < n && j > 0 && j < n;
+        vx[ j * ( n + 1 ) + i ] = i * h + ( interior ? ( rnd() - 0.5 ) * 0.4 * h : 0.0 );
+        vy[ j * ( n + 1 ) + i ] = j * h + ( interior ? ( rnd() - 0.5 ) * 0.4 * h : 0.0 );
+      }
+    A.nVertices = std::int64_t( vx.size() );
+    std::vector< std::vector< int > > cells;
+    for( int j = 0; j < n; ++j )
+      for( int i = 0; i < n; ++i )
+      {
+        const int a = j * ( n + 1 ) + i, b = a + 1, c = a + n + 1, d = c + 1;
+        if( ( i + 2 * j ) % 3 == 0 )
+          cells.push_back( { a, b, c, d } );
+        else if( ( i + j ) % 2 == 0 )
+        {
+          cells.push_back( { a, b, d } );
+          cells.push_back( { a, d, c } );
+        }
+        else
+        {
+          cells.push_back( { a, b, c } );
+          cells.push_back( { b, d, c } );
+        }
+      }
+    static const int triFaces[ 3 ][ 2 ] = { { 0, 1 }, { 0, 2 }, { 1, 2 } }, quadFaces[ 4 ][ 2 ] = { { 0, 2 }, { 1, 3 }, { 0, 1 }, { 2, 3 } };
+    static const int quadPoly[ 4 ] = { 0, 1, 3, 2 };
+    const std::size_t N = cells.size();
+    for( std::size_t c = 0; c < N; ++c )
+    {
+      const auto &vs = cells[ c ];
+      const int nc = int( vs.size() );
+      double cx = 0, cy = 0, area = 0;
+      for( int k = 0; k < nc; ++k )
+      {
+        A.cornerVertex.push_back( vs[ k ] );
+        A.corners.push_back( vx[ vs[ k ] ] );
+        A.corners.push_back( vy[ vs[ k ] ] );
+        cx += vx[ vs[ k ] ];
+        cy += vy[ vs[ k ] ];
+      }
+      for( int k = 0; k < nc; ++k )
+      {
+        const int p = vs[ nc == 3 ? k : quadPoly[ k ] ], q = vs[ nc == 3 ? ( k + 1 ) % 3 : quadPoly[ ( k + 1 ) % 4 ] ];
+        area += vx[ p ] * vy[ q ] - vx[ q ] * vy[ p ];
+      }
+      A.centers.push_back( cx / nc );
+      A.centers.push_back( cy / nc );
+      A.volumes.push_back( std::fabs( 0.5 * area ) );
+      A.cornerOffsets.push_back( std::int32_t( A.cornerVertex.size() ) );
+      for( int f = 0; f < nc; ++f )
+      {
+        const int p = vs[ nc == 3 ? triFaces[ f ][ 0 ] : quadFaces[ f ][ 0 ] ], q = vs[ nc == 3 ? triFaces[ f ][ 1 ] : quadFaces[ f ][ 1 ] ];
+        int neighbor = -1;
+        for( std::size_t o = 0; o < N && neighbor < 0; ++o )
+        {
+          if( o == c )
+            continue;
+          bool hasP = false, hasQ = false;
+          for( int v : cells[ o ] )
+          {
+            hasP |= v == p;
+            hasQ |= v == q;
+          }
+          if( hasP && hasQ )
+            neighbor = int( o );
+        }
+        A.faceNeighbor.push_back( neighbor );
+        const double dx = vx[ q ] - vx[ p ], dy = vy[ q ] - vy[ p ], len = std::sqrt( dx * dx + dy * dy );
+        const double mx = 0.5 * ( vx[ p ] + vx[ q ] ), my = 0.5 * ( vy[ p ] + vy[ q ] );
+        double nx = dy / len, ny = -dx / len;
+        if( nx * ( mx - cx / nc ) + ny * ( my - cy / nc ) < 0 )
+        {
+          nx = -nx;
+          ny = -ny;
+        }
+        A.faceCorners.insert( A.faceCorners.end(), { vx[ p ], vy[ p ], vx[ q ], vy[ q ] } );
+        A.faceCenters.insert( A.faceCenters.end(), { mx, my } );
+        A.faceUnit.insert( A.faceUnit.end(), { nx, ny } );
+        A.faceInt.insert( A.faceInt.end(), { nx * len, ny * len } );
+        A.faceVolumes.push_back( len );
+      }
+      A.faceOffsets.push_back( std::int32_t( A.faceNeighbor.size() ) );
+    }
+    // vertex-neighbour stencil for the oracle (the adaptor builds its own through the grid view)
+    for( std::size_t c = 0; c < N; ++c )
+    {
+      std::vector< std::int32_t > nb;
+      for( std::size_t o = 0; o < N; ++o )
+      {
+        if( o == c )
+          continue;
+        bool shares = false;
+        for( int v : cells[ c ] )
+          for( int w : cells[ o ] )
+            shares |= v == w;
+        if( shares )
+          nb.push_back( std::int32_t( o ) );
+      }
+      A.stencil.insert( A.stencil.end(), nb.begin(), nb.end() );
+      A.stencilOffsets.push_back( std::int32_t( A.stencil.size() ) );
+    }
+    return A;
+  }
+
+} // namespace
+
+int main ()
+{
+  const Arrays A = makeMesh( 20 );
+  const std::size_t N = A.volumes.size(), F = A.faceVolumes.size();
+
+  Dune::MeshGrid2 grid;
+  grid.nCells = std::int64_t( N );
+  grid.nVertices = A.nVertices;
+  grid.cornerOffsets = A.cornerOffsets.data();
+  grid.cornerVertex = A.cornerVertex.data();
+  grid.corners = A.corners.data();
+  grid.centers = A.centers.data();
+  grid.volumes = A.volumes.data();
+  grid.faceOffsets = A.faceOffsets.data();
+  grid.faceNeighbor = A.faceNeighbor.data();
+  grid.faceCorners = A.faceCorners.data();
+  grid.faceCenters = A.faceCenters.data();
+  grid.faceUnitNormals = A.faceUnit.data();
+  grid.faceIntNormals = A.faceInt.data();
+  grid.faceVolumes = A.faceVolumes.data();
+  GV gv( grid );
+
+  vo_mesh om;
+  om.n_cells = std::int64_t( N );
+  om.corner_offsets = A.cornerOffsets.data();
+  om.corners = A.corners.data();
+  om.centers = A.centers.data();
+  om.volumes = A.volumes.data();
+  om.face_offsets = A.faceOffsets.data();
+  om.face_neighbor = A.faceNeighbor.data();
+  om.face_corners = A.faceCorners.data();
+  om.face_centers = A.faceCenters.data();
+  om.face_unit_normals = A.faceUnit.data();
+  om.face_int_normals = A.faceInt.data();
+  om.face_volumes = A.faceVolumes.data();
+  om.stencil_offsets = A.stencilOffsets.data();
+  om.stencil = A.stencil.data();
+
+  // a disc, sub-sampled (only an input)
+  std::vector< double > u0( N );
+  for( std::size_t c = 0; c < N; ++c )
+  {
+    const int b = A.cornerOffsets[ c ], nc = A.cornerOffsets[ c + 1 ] - b;
+    int inside = 0, total = 0;
+    for( int i = 0; i < 16; ++i )
+      for( int j = 0; j < 16; ++j )
+      {
+        const double s = ( i + 0.5 ) / 16, t = ( j + 0.5 ) / 16;
+        double x, y;
+        if( nc == 3 )
+        {
+          if( s + t > 1 )
+            continue;
+          x = A.corners[ 2 * b ] + s * ( A.corners[ 2 * b + 2 ] - A.corners[ 2 * b ] ) + t * ( A.corners[ 2 * b + 4 ] - A.corners[ 2 * b ] );
+          y = A.corners[ 2 * b + 1 ] + s * ( A.corners[ 2 * b + 3 ] - A.corners[ 2 * b + 1 ] ) + t * ( A.corners[ 2 * b + 5 ] - A.corners[ 2 * b + 1 ] );
+        }
+        else
+        {
+          x = ( 1 - s ) * ( 1 - t ) * A.corners[ 2 * b ] + s * ( 1 - t ) * A.corners[ 2 * b + 2 ] + ( 1 - s ) * t * A.corners[ 2 * b + 4 ] + s * t * A.corners[ 2 * b + 6 ];
+          y = ( 1 - s ) * ( 1 - t ) * A.corners[ 2 * b + 1 ] + s * ( 1 - t ) * A.corners[ 2 * b + 3 ] + ( 1 - s ) * t * A.corners[ 2 * b + 5 ] + s * t * A.corners[ 2 * b + 7 ];
+        }
+        ++total;
+        inside += std::hypot( x - 0.5, y - 0.7 ) < 0.2;
+      }
+    u0[ c ] = double( inside ) / total;
+  }
+
+  // the sampled velocity the oracle gets: the same functor evaluated the same way
+  std::vector< double > vel( 2 * F );
+  for( std::size_t s = 0; s < F; ++s )
+  {
+    vel[ 2 * s ] = ( A.faceCenters[ 2 * s + 1 ] - 0.5 ) * ( 2 * M_PI / 10 );
+    vel[ 2 * s + 1 ] = ( 0.5 - A.faceCenters[ 2 * s ] ) * ( 2 * M_PI / 10 );
+  }
+
+  try
+  {
+    Dune::VoFx::Unstructured::VertexNeighborsStencil< GV > stencils( gv );
+    const auto &ctx = stencils.context();
+    expect( ctx.stencilOffsets == A.stencilOffsets && ctx.stencil == A.stencil, "flattened CSR vertex stencil equals the brute-force one" );
+    expect( ctx.faceNeighbor == A.faceNeighbor && ctx.corners == A.corners && ctx.faceIntNormals == A.faceInt, "flattened geometry equals the grid's arrays" );
+
+    Dune::VoFx::Unstructured::FlagOperator< GV > flagOperator( stencils, 1e-6 );
+    Dune::VoFx::Unstructured::ModifiedYoungsReconstruction< GV > reconstruction( stencils );
+    auto evolutionOperator = Dune::VoFx::Unstructured::evolution( stencils );
+
+    ColorFunction uh( gv ), update( gv );
+    FlagSet flags( gv );
+    ReconstructionSet recs( gv );
+    std::copy( u0.begin(), u0.end(), uh.begin() );
+
+#ifdef VOFX_TEST_WITH_REFERENCE
+    Dune::VoF::VertexNeighborsStencil< GV > refStencils( gv );
+    Dune::VoF::FlagOperator< GV > refFlag( 1e-6 );
+    Dune::VoF::ModifiedYoungsReconstruction< GV, Dune::VoF::VertexNeighborsStencil< GV > > refRecon( refStencils );
+    auto refEvolution = Dune::VoF::evolution( gv );
+    ColorFunction ruh( gv ), rupdate( gv );
+    FlagSet rflags( gv );
+    ReconstructionSet rrecs( gv );
+    std::copy( u0.begin(), u0.end(), ruh.begin() );
+#endif
+
+    std::vector< double > uo( u0 ), hso( 3 * N ), updo( N );
+    std::vector< std::uint8_t > flo( N );
+    double dt = 0.0, dto = 0.0, rdt = 0.0;
+    (void) rdt;
+    bool flagsOk = true, recsOk = true, updOk = true, dtOk = true, refOk = true;
+    for( int pass = 0; pass < 12; ++pass )
+    {
+      RotationVelocity velocity;
+      flagOperator( uh, flags );
+      reconstruction( uh, recs, flags );
+      const double dtEst = evolutionOperator( recs, flags, velocity, dt, update );
+      for( std::size_t i = 0; i < N; ++i )
+        uh[ i ] += 1.0 * update[ i ];
+      dt = 0.5 * dtEst;
+
+      double esto = 0.0;
+      vo_mesh_flag( &om, uo.data(), 1e-6, flo.data() );
+      vo_mesh_youngs( &om, uo.data(), flo.data(), hso.data() );
+      vo_mesh_evolve( &om, hso.data(), flo.data(), vel.data(), dto, updo.data(), &esto );
+      for( std::size_t i = 0; i < N; ++i )
+        uo[ i ] += updo[ i ];
+      dto = 0.5 * esto;
+
+      std::size_t i = 0;
+      for( auto it = flags.begin(); it != flags.end(); ++it, ++i )
+        flagsOk &= std::uint8_t( static_cast< std::size_t >( *it ) ) == flo[ i ];
+      i = 0;
+      for( auto it = recs.begin(); it != recs.end(); ++it, ++i )
+      {
+        const double hs[ 3 ] = { it->innerNormal()[ 0 ], it->innerNormal()[ 1 ], it->boundary().distance() };
+        recsOk &= sameBits( hs, hso.data() + 3 * i, 3 );
+      }
+      for( i = 0; i < N; ++i )
+      {
+        const double a = update[ i ];
+        updOk &= sameBits( &a, &updo[ i ], 1 );
+      }
+      dtOk &= dtEst == esto;
+
+#ifdef VOFX_TEST_WITH_REFERENCE
+      RotationVelocity rvelocity;
+      refFlag( ruh, rflags );
+      refRecon( ruh, rrecs, rflags );
+      const double rEst = refEvolution( rrecs, rflags, rvelocity, rdt, rupdate );
+      ruh.axpy( 1.0, rupdate );
+      rdt = 0.5 * rEst;
+      refOk &= rEst == dtEst;
+      {
+        auto a = uh.begin();
+        for( auto b = ruh.begin(); b != ruh.end(); ++a, ++b )
+        {
+          const double x = *a, y = *b;
+          refOk &= sameBits( &x, &y, 1 );
+        }
+      }
+#endif
+    }
+#ifdef VOFX_TEST_WITH_REFERENCE
+    expect( refOk, "colour function and dtEst of every pass equal the REFERENCE's own operators on the same grid view" );
+#else
+    (void) refOk;
+#endif
+    expect( flagsOk, "flags of 12 loop passes equal the oracle's" );
+    expect( recsOk, "half-spaces of 12 loop passes equal the oracle's bit for bit" );
+    expect( updOk, "updates of 12 loop passes equal the oracle's bit for bit" );
+    expect( dtOk, "time-step estimates equal the oracle's" );
+    bool colorOk = true;
+    for( std::size_t i = 0; i < N; ++i )
+    {
+      const double a = uh[ i ];
+      colorOk &= sameBits( &a, &uo[ i ], 1 );
+    }
+    expect( colorOk, "colour function after 12 passes equals the oracle's bit for bit" );
+  }
+  catch( const std::exception &e )
+  {
+    std::printf( "FAIL exception: %s\n", e.what() );
+    ++failures;
+  }
+  std::printf( failures == 0 ? "ADAPTOR MESH TEST PASSED\n" : "ADAPTOR MESH TEST FAILED (%d)\n", failures );
+  return failures == 0 ? 0 : 1;
+}

@@ -18,3 +18,19 @@ def test_adaptor_binary():
     assert r.returncode == 0, r.stdout + r.stderr
     assert "ADAPTOR TEST PASSED" in r.stdout
     assert "FAIL" not in r.stdout
+
+
+def test_unstructured_adaptor_binary():
+    """include/dune/vofx/unstructured.hh on a mixed triangle/quadrilateral grid view"""
+    exe = os.path.join(ROOT, "tests", "adaptor", "test_adaptor_mesh")
+    assert os.path.exists(exe), "tests/adaptor/test_adaptor_mesh is missing: run __graft_entry__.build()"
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    print(r.stdout)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "ADAPTOR MESH TEST PASSED" in r.stdout
+    assert "FAIL" not in r.stdout
+    ref = exe + "_ref"
+    if os.path.exists(ref):   # built only where /root/reference was mounted; travels to the GPU box as a binary
+        r = subprocess.run([ref], capture_output=True, text=True, timeout=600)
+        print(r.stdout)
+        assert r.returncode == 0 and "ADAPTOR MESH TEST PASSED" in r.stdout, r.stdout + r.stderr
