@@ -364,6 +364,11 @@ struct vofx_mesh
   bool colorSet = false, velocitySet = false;
   long long launches = 0;
   int blocksCells = 1;
+  // the captured loop pass (vofx_mesh_run)
+  cudaGraphExec_t passGraph = nullptr;
+  double graphEps = 0.0, graphCfl = 0.0;
+  cudaStream_t graphStream = nullptr;
+  int launchesPerPass = 0;
 };
 
 namespace
@@ -560,6 +565,8 @@ extern "C"
     cudaSetDevice( m->device );
     if( m->stream )
       cudaStreamSynchronize( m->stream );
+    if( m->passGraph )
+      cudaGraphExecDestroy( m->passGraph );
     if( m->ownStream )
       cudaStreamDestroy( m->ownStream );
     for( void *p : m->owned )
@@ -714,8 +721,45 @@ extern "C"
       return set_error( VOFX_ERR_STATE, "vofx_mesh_run: call vofx_mesh_color_upload and vofx_mesh_velocity_upload first" );
     k_mesh_set_dt<<< 1, 1, 0, m->stream >>>( m->state, *timeIO, *dtIO );
     m->launches += 1;
+    // one loop pass reads only device-resident state: it is captured once into a CUDA graph and replayed
+    // (7 small launches per pass are launch-latency bound when issued one by one; VOFX_NO_GRAPH=1 issues them eagerly)
+    static const bool noGraph = std::getenv( "VOFX_NO_GRAPH" ) != nullptr;
+    if( !noGraph && passes > 1 && ( !m->passGraph || m->graphEps != eps || m->graphCfl != cfl || m->graphStream != m->stream ) )
+    {
+      if( m->passGraph )
+      {
+        cudaGraphExecDestroy( m->passGraph );
+        m->passGraph = nullptr;
+      }
+      const long long before = m->launches;
+      cudaGraph_t graph = nullptr;
+      VOFX_MESH_CUDA( cudaStreamBeginCapture( m->stream, cudaStreamCaptureModeThreadLocal ) );
+      int rc = launchFlag( m, m->u, eps, m->flags, true );
+      if( !rc )
+        rc = launchYoungs( m, m->u, m->hs );
+      if( !rc )
+        rc = launchEvolve< true >( m, m->hs, m->flags, m->vel, &m->state->dt, m->u );
+      k_mesh_finish<<< 1, 1, 0, m->stream >>>( m->state, cfl );
+      const cudaError_t endErr = cudaStreamEndCapture( m->stream, &graph );
+      m->launchesPerPass = int( m->launches - before ) + 1;
+      m->launches = before;
+      if( rc )
+        return rc;
+      VOFX_MESH_CUDA( endErr );
+      VOFX_MESH_CUDA( cudaGraphInstantiate( &m->passGraph, graph, 0 ) );
+      cudaGraphDestroy( graph );
+      m->graphEps = eps;
+      m->graphCfl = cfl;
+      m->graphStream = m->stream;
+    }
     for( int pass = 0; pass < passes; ++pass )
     {
+      if( m->passGraph && !noGraph && passes > 1 )
+      {
+        VOFX_MESH_CUDA( cudaGraphLaunch( m->passGraph, m->stream ) );
+        m->launches += m->launchesPerPass;
+        continue;
+      }
       if( int rc = launchFlag( m, m->u, eps, m->flags, true ) )
         return rc;
       if( int rc = launchYoungs( m, m->u, m->hs ) )
