@@ -209,36 +209,44 @@ namespace vofx
           }
           if( anyFull )
           {
-            // full cells with an empty face neighbour become mixedfull, flagging.hh:56-63
+            // full cells with an empty face neighbour become mixedfull, flagging.hh:56-63.  The quads of the neighbour rows
+            // are fetched with the same 16-byte loads as the row itself (inside the fluid every cell of the quad is full:
+            // per-cell 8-byte loads would touch every sector four times), the x neighbours come from the registers
+            bool emptyRow[ 4 ] = { false, false, false, false };
+            auto scanRow = [ & ] ( int offset ) {
+              const double2 p = __ldg( reinterpret_cast< const double2 * >( u + c0 + offset ) );
+              const double2 q2 = __ldg( reinterpret_cast< const double2 * >( u + c0 + offset + 2 ) );
+              emptyRow[ 0 ] |= p.x < eps;
+              emptyRow[ 1 ] |= p.y < eps;
+              emptyRow[ 2 ] |= q2.x < eps;
+              emptyRow[ 3 ] |= q2.y < eps;
+            };
+            if( yLo )
+              scanRow( -nx );
+            if( yHi )
+              scanRow( nx );
+            if( DIM == 3 )
+            {
+              if( zLo )
+                scanRow( -planeStride );
+              if( zHi )
+                scanRow( planeStride );
+            }
 #pragma unroll
             for( int t = 0; t < 4; ++t )
               if( ff[ t ] == 3u )
               {
                 const int i = i0 + t;
                 const int c = c0 + t;
-                bool emptyNb = false;
+                bool emptyNb = emptyRow[ t ];
                 if( t > 0 )
-                  emptyNb = uu[ t > 0 ? t - 1 : 0 ] < eps;
+                  emptyNb |= uu[ t > 0 ? t - 1 : 0 ] < eps;
                 else if( i > 0 )
-                  emptyNb = __ldg( u + c - 1 ) < eps;
-                if( !emptyNb )
-                {
-                  if( t < 3 )
-                    emptyNb = uu[ t < 3 ? t + 1 : 3 ] < eps;
-                  else if( i + 1 < nx )
-                    emptyNb = __ldg( u + c + 1 ) < eps;
-                }
-                if( !emptyNb && yLo )
-                  emptyNb = __ldg( u + c - nx ) < eps;
-                if( !emptyNb && yHi )
-                  emptyNb = __ldg( u + c + nx ) < eps;
-                if( DIM == 3 )
-                {
-                  if( !emptyNb && zLo )
-                    emptyNb = __ldg( u + c - planeStride ) < eps;
-                  if( !emptyNb && zHi )
-                    emptyNb = __ldg( u + c + planeStride ) < eps;
-                }
+                  emptyNb |= __ldg( u + c - 1 ) < eps;
+                if( t < 3 )
+                  emptyNb |= uu[ t < 3 ? t + 1 : 3 ] < eps;
+                else if( i + 1 < nx )
+                  emptyNb |= __ldg( u + c + 1 ) < eps;
                 if( emptyNb )
                   ff[ t ] = 2u;
               }
