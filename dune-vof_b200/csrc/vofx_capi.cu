@@ -79,6 +79,7 @@ struct vofx_ctx
   int changedCapacity = 0;
   bool trackChanges = false;
   long long lastH2D = 0, lastD2H = 0;   // bytes moved by the last vofx_step_host call
+  void *diagScratch = nullptr;     // block partials + results of vofx_diagnostics
   void *rootTasks = nullptr;        // coop::RootTask per mixed cell: brackets found by k_youngs_coop3, roots by k_locate_root3
   int fluxLanes = 8;               // lanes per mixed cell of the 3D flux kernel; measured at 512^3: 0.36 ms (8) vs 0.51 ms (4)
   int lanesPerCell = 4;            // measured on B200 at 512^3: 0.47 ms (4 lanes per cell) vs 0.64 ms (8)
@@ -640,6 +641,7 @@ extern "C"
     cudaFree( ctx->sweepTable );
     cudaFree( ctx->serialCells );
     cudaFree( ctx->rootTasks );
+    cudaFree( ctx->diagScratch );
     cudaFree( ctx->swzCells );
     cudaFree( ctx->swzTasks );
     cudaFree( ctx->swzCounter );
@@ -961,6 +963,32 @@ extern "C"
     profBegin( ctx );
     launch::axpy( gridBlocks( ctx, ctx->grid.cells, 256, 8 ), ctx->stream, ctx->grid.cells, u, a, x );
     return checkLaunch( ctx, "k_axpy" );
+  }
+
+  int vofx_diagnostics ( vofx_ctx *ctx, const double *u, const double *u_exact, double *out_host )
+  {
+    if( !ctx || !u || !out_host )
+      return fail( VOFX_ERR_ARGUMENT, "null argument" );
+    int rc = setDevice( ctx );
+    if( rc )
+      return rc;
+    if( !ctx->diagScratch )
+      VOFX_CUDA( cudaMalloc( &ctx->diagScratch, launch::diag_scratch_bytes() ) );
+    const Grid &g = ctx->grid;
+    const long long layer = g.cells / g.ns[ g.dim - 1 ];
+    const long long first = layer * g.own0, n = layer * ( g.own1 - g.own0 );
+    double volume = 1.0;
+    for( int d = 0; d < g.dim; ++d )
+      volume *= g.h[ d ];
+    profBegin( ctx );
+    const double *out = launch::diagnostics( ctx->stream, n, u + first, u_exact ? u_exact + first : nullptr, volume, ctx->diagScratch );
+    ctx->launches += 1;
+    rc = checkLaunch( ctx, "k_diagnostics" );
+    if( rc )
+      return rc;
+    VOFX_CUDA( cudaMemcpyAsync( out_host, out, 5 * sizeof( double ), cudaMemcpyDeviceToHost, ctx->stream ) );
+    VOFX_CUDA( cudaStreamSynchronize( ctx->stream ) );
+    return VOFX_OK;
   }
 
   int vofx_curvature ( vofx_ctx *ctx, const double *u, const double *halfspaces, const uint8_t *flags, double *kappa, uint8_t *valid )

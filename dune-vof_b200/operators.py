@@ -262,6 +262,14 @@ class SwartzCurvature:
         check(g._L.vofx_curvature_swartz(g._ctx, g.ph(reconstructions), g.pf(flags), g.pc(curvature)))
 
 
+def diagnostics(grid: CartesianGrid, color, exact=None):
+    """sum, min, max, cellwiseL1error (test/errors.hh:138-151) and mass of the owned cells, reduced on the device"""
+    out = (C.c_double * 5)()
+    ex = grid.pc(exact) if exact is not None else C.c_void_p(0)
+    check(grid._L.vofx_diagnostics(grid._ctx, grid.pc(color), ex, out))
+    return {"sum": out[0], "min": out[1], "max": out[2], "l1": out[3], "mass": out[4]}
+
+
 def get_interface_vertices(grid: CartesianGrid, reconstructions, flags):
     """getInterfaceVertices (utility.hh:19-48) + MixedCellMapper::update (mixedcellmapper.hh:82-86): returns numpy arrays
     (cells, offsets, vertices): the owned mixed cells in ascending index and the CSR of their interface polygons."""

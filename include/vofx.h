@@ -207,6 +207,14 @@ int vofx_interface ( vofx_ctx *ctx, const double *halfspaces, const uint8_t *fla
 int vofx_interface_host ( vofx_ctx *ctx, const double *halfspaces_host, const uint8_t *flags_host, int64_t *n_mixed, int64_t *n_vertices );
 int vofx_interface_fetch ( vofx_ctx *ctx, int32_t *cells_host, int64_t *offsets_host, double *vertices_host );
 
+/* ---- diagnostics of the colour function over the OWNED cells, reduced on the device (keeps a driver's conservation /
+ * EOC reporting without a full-field copy per step): out_host[0] = sum of the cell values, [1] = min, [2] = max,
+ * [3] = cellwiseL1error (test/errors.hh:138-151: sum |uh - uhExact| * volume; 0 when u_exact is NULL),
+ * [4] = mass = sum uh * volume.  u, u_exact: DEVICE arrays of the context's storage size; out_host: 5 HOST doubles
+ * (the call synchronises the context's stream).  Fixed summation tree: reproducible, equal to the reference's
+ * sequential sums up to round-off (1e-12 relative in the tests), min / max exact. */
+int vofx_diagnostics ( vofx_ctx *ctx, const double *u, const double *u_exact /* may be NULL */, double *out_host );
+
 /* ---- initial data on the device (replaces Average< Problem >, test/average.hh:28-54, i.e.
  * RecursiveInterpolationCube depth 3, interpolation/recursiveinterpolationcube.hh:33-82, for the built-in problems) */
 int vofx_init ( vofx_ctx *ctx, int problem, double time, double *u );

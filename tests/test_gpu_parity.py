@@ -428,3 +428,32 @@ def test_256_cubed_against_oracle(vofx):
     assert st.time == to and st.dt == do
     grid.close()
     og.close()
+
+
+@pytest.mark.parametrize("n,problem", [((128, 128), 4), ((48, 40, 56), 4), ((37 * 4, 50), 2)])
+def test_device_diagnostics(vofx, n, problem):
+    """vofx_diagnostics against sequential sums over the same arrays (what ColorFunction / cellwiseL1error,
+    test/errors.hh:138-151, accumulate): min and max exact, the sums within 1e-12 relative (different summation tree)."""
+    import math
+
+    import torch
+    grid = vofx.CartesianGrid(n)
+    grid.set_velocity_builtin(problem)
+    u0 = grid.init(problem)
+    alg = vofx.Algorithm(grid, 0.5, 1e-6, vofx.RECON_YOUNGS)
+    uh = u0.clone()
+    alg.run_passes(uh, 6)
+    d = vofx.diagnostics(grid, uh, u0)
+    a, e = uh.cpu().numpy(), u0.cpu().numpy()
+    volume = float(np.prod([1.0 / k for k in n]))
+    ref_sum = math.fsum(a.tolist())
+    ref_l1 = math.fsum(np.abs(a - e).tolist()) * volume
+    assert d["min"] == a.min() and d["max"] == a.max()
+    assert abs(d["sum"] - ref_sum) <= 1e-12 * abs(ref_sum)
+    assert abs(d["mass"] - ref_sum * volume) <= 1e-12 * abs(ref_sum * volume)
+    assert abs(d["l1"] - ref_l1) <= 1e-12 * max(abs(ref_l1), volume)
+    assert d["l1"] > 0.0
+    # without an exact solution the error entry is zero
+    d0 = vofx.diagnostics(grid, u0)
+    assert d0["l1"] == 0.0 and d0["min"] >= 0.0 and d0["max"] <= 1.0
+    torch.cuda.synchronize()
