@@ -516,19 +516,23 @@ namespace vofx
       double P[ 3 ][ 8 ];               // rotated nodes
       union
       {
-        double dv[ 3 ][ 24 ];           // PolygonWithDirections::directionVector of every directed edge
-        double ls[ 8 ][ 9 ];            // least-squares contributions of one round of stencil slots (before the solve)
+        struct
+        {
+          double dv[ 3 ][ 12 ];         // PolygonWithDirections::directionVector of edge e = ( a, b ); the reverse edge e + 12 is
+                                        // derived on read (dv_get): 1192 B per cell let 10 blocks of 16 cells share an SM
+          double px[ 2 ][ 8 ], py[ 2 ][ 8 ];   // polygon nodes of the current / next bracket
+          union
+          {
+            double aterm[ kMaxATerms ]; // terms of A of the current bracket
+            double term[ 8 ];           // face terms of the cell volume (before the brackets)
+          };
+          double bterm[ 8 ], cterm[ 8 ];   // terms of B and C of the current bracket
+        };
+        double ls[ 8 ][ 9 ];            // least-squares contributions of one round of stencil slots (before the plane-constant solve)
       };
-      double fnz[ 6 ], fnrm[ 6 ];       // outer normal of face f of P: z component, norm of the xy part
-      double px[ 2 ][ 8 ], py[ 2 ][ 8 ];   // polygon nodes of the current / next bracket
       union
       {
-        double aterm[ kMaxATerms ];     // terms of A of the current bracket
-        double term[ 8 ];               // face terms of the cell volume (before the brackets)
-      };
-      union
-      {
-        struct { double bterm[ 8 ], cterm[ 8 ]; };   // terms of B and C of the current bracket
+        struct { double fnz[ 6 ], fnrm[ 6 ]; };   // outer normal of face f of P: z component, norm of the xy part
         double sums[ 12 ];              // AtA (6 unique entries) and Atb (before the plane-constant solve)
       };
       double ds[ 8 ];                   // sorted node heights
@@ -536,6 +540,15 @@ namespace vofx
       unsigned char lsValid[ 8 ];
       SweepBracket walked;              // descriptor produced by the walk of lane 0 (cells with tied node heights)
     };
+
+    // direction vector component c of the directed edge e; e >= 12 is the reverse of e - 12: ( P_a - P_b ) / norm with the same
+    // norm, i.e. the negated component - except that a zero difference is +0 in either direction ( x - x = +0, +0 / norm = +0 )
+    VOFX_INLINE double dv_get ( const LocateScratch &S, int c, int e )
+    {
+      const bool reverse = e >= 12;
+      const double x = S.dv[ c ][ reverse ? e - 12 : e ];
+      return ( reverse && x != 0.0 ) ? -x : x;
+    }
     // consecutive groups of a warp address the same members: an odd stride in 8-byte words spreads them over the banks
     static_assert( sizeof( LocateScratch ) % 8 == 0 && ( sizeof( LocateScratch ) / 8 ) % 2 == 1, "LocateScratch stride must be an odd number of doubles" );
 
@@ -711,28 +724,17 @@ namespace vofx
 #pragma unroll 1
         for( int e = lane; e < 12; e += L )
         {
-          // edge e = ( a, b ) and its reverse e + 12 = ( b, a ): the reverse direction vector is ( P_a - P_b ) / norm with the
-          // same norm ( squares ); for a non-zero difference that is exactly the negated quotient, for a zero difference
-          // the (signed) zero is divided on vdiv's fast path
+          // edge e = ( a, b ); its reverse e + 12 = ( b, a ) is not stored (dv_get)
           const int a = cube::edgeN0( e ), b = cube::edgeN1( e );
-          double dv[ 3 ], rv[ 3 ];
+          double dv[ 3 ];
           for( int c = 0; c < 3; ++c )
-          {
             dv[ c ] = S.P[ c ][ b ] - S.P[ c ][ a ];
-            rv[ c ] = S.P[ c ][ a ] - S.P[ c ][ b ];
-          }
           const double norm = norm2( dv[ 0 ], dv[ 1 ] );
           if( norm > 0 )
             for( int c = 0; c < 3; ++c )
-            {
               dv[ c ] = vdiv( dv[ c ], norm );
-              rv[ c ] = ( rv[ c ] == 0.0 ) ? vdiv( rv[ c ], norm ) : -dv[ c ];
-            }
           for( int c = 0; c < 3; ++c )
-          {
             S.dv[ c ][ e ] = dv[ c ];
-            S.dv[ c ][ e + 12 ] = rv[ c ];
-          }
         }
 #pragma unroll 1
         for( int f = lane; f < 6; f += L )
@@ -869,8 +871,8 @@ namespace vofx
             else
             {
               const int e = B.srcEdge[ a ], from = B.srcNode[ a ];
-              const double f = vdiv( hPrev, S.dv[ 2 ][ e ] );
-              const double ax = S.dv[ 0 ][ e ] * f, ay = S.dv[ 1 ][ e ] * f;
+              const double f = vdiv( hPrev, dv_get( S, 2, e ) );
+              const double ax = dv_get( S, 0, e ) * f, ay = dv_get( S, 1, e ) * f;
               S.px[ cur ][ a ] = S.px[ cur ^ 1 ][ from ] + ax;
               S.py[ cur ][ a ] = S.py[ cur ^ 1 ][ from ] + ay;
             }
@@ -884,8 +886,8 @@ namespace vofx
           for( int t = lane; t < B.nA; t += L )
           {
             const int e1 = B.aE1[ t ], e2 = B.aE2[ t ];
-            const double v1x = S.dv[ 0 ][ e1 ], v1y = S.dv[ 1 ][ e1 ], v1z = S.dv[ 2 ][ e1 ];
-            const double v2x = S.dv[ 0 ][ e2 ], v2y = S.dv[ 1 ][ e2 ], v2z = S.dv[ 2 ][ e2 ];
+            const double v1x = dv_get( S, 0, e1 ), v1y = dv_get( S, 1, e1 ), v1z = dv_get( S, 2, e1 );
+            const double v2x = dv_get( S, 0, e2 ), v2y = dv_get( S, 1, e2 ), v2z = dv_get( S, 2, e2 );
             S.aterm[ t ] = vdiv( v1x * v2y - v1y * v2x, v1z * v2z );
           }
 #pragma unroll 1
