@@ -181,6 +181,76 @@ namespace
     }
   }
 
+  // interface( entity, reconstructions ) of a cell located with a given normal: centroid of the cut segment
+  // ( locateHalfSpace + intersect( polygon, boundary ) + Line::centroid, 2d/polygon.hh:183-188 )
+  __device__ void mesh_interface_centroid ( const MeshDev &M, int c, double nx, double ny, double color, double &cx, double &cy )
+  {
+    Poly2 p;
+    cell_polygon( M, c, p );
+    const Hs2 H = { nx, ny, locate( p, nx, ny, color ) };
+    double lx[ 2 ], ly[ 2 ];
+    plane_cut( p, H, lx, ly );
+    cx = ( lx[ 0 ] + lx[ 1 ] ) * 0.5;
+    cy = ( ly[ 0 ] + ly[ 1 ] ) * 0.5;
+  }
+
+  // ModifiedSwartzReconstruction::applyLocal in 2D, reconstruction/modifiedswartz.hh:102-153: one thread per mixed cell,
+  // on top of the Young's half-spaces already in hs (a cell reads and writes only its own entry)
+  __global__ void __launch_bounds__( 64 ) k_mesh_swartz ( MeshDev M, const double *__restrict__ u, const unsigned char *__restrict__ flags,
+                                                           const int *__restrict__ mixedList, const MeshState *state, double *__restrict__ hs,
+                                                           int maxIterations )
+  {
+    const int count = state->mixedCount;
+    for( int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < count; idx += gridDim.x * blockDim.x )
+    {
+      const int c = mixedList[ idx ];
+      const double colorEn = u[ c ];
+      double nx = hs[ 3 * c ], ny = hs[ 3 * c + 1 ];
+      int iterations = 0;
+      double residuum = 0.0;
+      do
+      {
+        const double ox = nx, oy = ny;
+        nx = ny = 0.0;
+        double ex, ey;
+        mesh_interface_centroid( M, c, ox, oy, colorEn, ex, ey );
+        for( int s = M.stencilOffsets[ c ]; s < M.stencilOffsets[ c + 1 ]; ++s )
+        {
+          const int nb = M.stencil[ s ];
+          if( !is_mixed( flags[ nb ] ) )
+            continue;
+          double bx, by;
+          mesh_interface_centroid( M, nb, ox, oy, u[ nb ], bx, by );
+          const double dx = bx - ex, dy = by - ey;
+          double cx = -dy, cy = dx;                     // generalizedCrossProduct, geometry/utility.hh:82-85
+          if( dot2( cx, cy, ox, oy ) < 0 )
+          {
+            cx *= -1.0;
+            cy *= -1.0;
+          }
+          const double nrm = norm2( cx, cy );
+          cx /= nrm;
+          cy /= nrm;
+          nx += 1.0 * cx;
+          ny += 1.0 * cy;
+        }
+        const double nrm = norm2( nx, ny );
+        if( nrm < 0.5 )
+          break;                                        // "return": keep the last reconstruction, :140-141
+        nx /= nrm;
+        ny /= nrm;
+        Poly2 p;
+        cell_polygon( M, c, p );
+        hs[ 3 * c ] = nx;
+        hs[ 3 * c + 1 ] = ny;
+        hs[ 3 * c + 2 ] = locate( p, nx, ny, colorEn );
+        residuum = 1.0 - dot2( nx, ny, ox, oy );
+        ++iterations;
+      }
+      while( residuum > 1e-12 && iterations < maxIterations );
+    }
+  }
+
   // truncVolume( upwindPolygon2d( iGeometry, v ), hs ), 2d/upwindpolygon.hh:24-30 + geometry/upwindpolygon.hh:58-62
   __device__ double mesh_flux ( const double *fc, double vx, double vy, const Hs2 &hs )
   {
@@ -364,6 +434,7 @@ struct vofx_mesh
   bool colorSet = false, velocitySet = false;
   long long launches = 0;
   int blocksCells = 1;
+  int reconstruction = VOFX_RECON_YOUNGS, maxIterations = 10;   // of vofx_mesh_run (vofx_mesh_set_reconstruction)
   // the captured loop pass (vofx_mesh_run)
   cudaGraphExec_t passGraph = nullptr;
   double graphEps = 0.0, graphCfl = 0.0;
@@ -389,6 +460,14 @@ namespace
   {
     VOFX_MESH_CUDA( cudaMemsetAsync( hs, 0, sizeof( double ) * 3 * size_t( m->dev.nCells ), m->stream ) );   // reconstructions.clear(), :65
     k_mesh_youngs<<< bandBlocks( m ), 128, 0, m->stream >>>( m->dev, u, m->mixedList, m->state, hs );
+    m->launches += 1;
+    VOFX_MESH_CUDA( cudaGetLastError() );
+    return VOFX_OK;
+  }
+
+  int launchSwartz ( vofx_mesh *m, const double *u, const unsigned char *flags, double *hs, int maxIterations )
+  {
+    k_mesh_swartz<<< bandBlocks( m ), 64, 0, m->stream >>>( m->dev, u, flags, m->mixedList, m->state, hs, maxIterations );
     m->launches += 1;
     VOFX_MESH_CUDA( cudaGetLastError() );
     return VOFX_OK;
@@ -617,6 +696,31 @@ extern "C"
     return launchYoungs( m, u, hs );
   }
 
+  int vofx_mesh_reconstruct_swartz ( vofx_mesh *m, const double *u, const uint8_t *flags, double *hs, int maxIterations )
+  {
+    if( int rc = vofx_mesh_reconstruct( m, u, flags, hs ) )      // initializer()( color, reconstructions, flags ), modifiedswartz.hh:72
+      return rc;
+    if( maxIterations < 0 )
+      return set_error( VOFX_ERR_ARGUMENT, "vofx_mesh_reconstruct_swartz: max_iterations < 0" );
+    return launchSwartz( m, u, flags, hs, maxIterations );
+  }
+
+  int vofx_mesh_set_reconstruction ( vofx_mesh *m, int kind, int maxIterations )
+  {
+    if( int rc = checkMesh( m ) )
+      return rc;
+    if( ( kind != VOFX_RECON_YOUNGS && kind != VOFX_RECON_SWARTZ ) || maxIterations < 0 )
+      return set_error( VOFX_ERR_ARGUMENT, "vofx_mesh_set_reconstruction: VOFX_RECON_YOUNGS or VOFX_RECON_SWARTZ (height functions are Cartesian-only)" );
+    if( m->passGraph && ( kind != m->reconstruction || maxIterations != m->maxIterations ) )
+    {
+      cudaGraphExecDestroy( m->passGraph );
+      m->passGraph = nullptr;
+    }
+    m->reconstruction = kind;
+    m->maxIterations = maxIterations;
+    return VOFX_OK;
+  }
+
   int vofx_mesh_evolve ( vofx_mesh *m, const double *hs, const uint8_t *flags, const double *vel, double dt, double *update, double *dtEst )
   {
     if( int rc = checkMesh( m ) )
@@ -662,6 +766,23 @@ extern "C"
     VOFX_MESH_CUDA( cudaMemcpyAsync( m->u, u, n * sizeof( double ), cudaMemcpyHostToDevice, m->stream ) );
     VOFX_MESH_CUDA( cudaMemcpyAsync( m->flags, flags, n, cudaMemcpyHostToDevice, m->stream ) );
     if( int rc = vofx_mesh_reconstruct( m, m->u, m->flags, m->hs ) )
+      return rc;
+    VOFX_MESH_CUDA( cudaMemcpyAsync( hs, m->hs, 3 * n * sizeof( double ), cudaMemcpyDeviceToHost, m->stream ) );
+    VOFX_MESH_CUDA( cudaStreamSynchronize( m->stream ) );
+    m->colorSet = false;
+    return VOFX_OK;
+  }
+
+  int vofx_mesh_reconstruct_swartz_host ( vofx_mesh *m, const double *u, const uint8_t *flags, double *hs, int maxIterations )
+  {
+    if( int rc = checkMesh( m ) )
+      return rc;
+    if( !u || !flags || !hs )
+      return set_error( VOFX_ERR_ARGUMENT, "vofx_mesh_reconstruct_swartz_host: null argument" );
+    const size_t n = size_t( m->dev.nCells );
+    VOFX_MESH_CUDA( cudaMemcpyAsync( m->u, u, n * sizeof( double ), cudaMemcpyHostToDevice, m->stream ) );
+    VOFX_MESH_CUDA( cudaMemcpyAsync( m->flags, flags, n, cudaMemcpyHostToDevice, m->stream ) );
+    if( int rc = vofx_mesh_reconstruct_swartz( m, m->u, m->flags, m->hs, maxIterations ) )
       return rc;
     VOFX_MESH_CUDA( cudaMemcpyAsync( hs, m->hs, 3 * n * sizeof( double ), cudaMemcpyDeviceToHost, m->stream ) );
     VOFX_MESH_CUDA( cudaStreamSynchronize( m->stream ) );
@@ -737,6 +858,8 @@ extern "C"
       int rc = launchFlag( m, m->u, eps, m->flags, true );
       if( !rc )
         rc = launchYoungs( m, m->u, m->hs );
+      if( !rc && m->reconstruction == VOFX_RECON_SWARTZ )
+        rc = launchSwartz( m, m->u, m->flags, m->hs, m->maxIterations );
       if( !rc )
         rc = launchEvolve< true >( m, m->hs, m->flags, m->vel, &m->state->dt, m->u );
       k_mesh_finish<<< 1, 1, 0, m->stream >>>( m->state, cfl );
@@ -764,6 +887,9 @@ extern "C"
         return rc;
       if( int rc = launchYoungs( m, m->u, m->hs ) )
         return rc;
+      if( m->reconstruction == VOFX_RECON_SWARTZ )
+        if( int rc = launchSwartz( m, m->u, m->flags, m->hs, m->maxIterations ) )
+          return rc;
       if( int rc = launchEvolve< true >( m, m->hs, m->flags, m->vel, &m->state->dt, m->u ) )
         return rc;
       k_mesh_finish<<< 1, 1, 0, m->stream >>>( m->state, cfl );

@@ -29,7 +29,7 @@ SYMBOLS = [
     "vofx_profile_read",
     "vofx_mesh_create", "vofx_mesh_destroy", "vofx_mesh_set_stream", "vofx_mesh_cells", "vofx_mesh_faces", "vofx_mesh_launch_count",
     "vofx_mesh_flag", "vofx_mesh_reconstruct", "vofx_mesh_evolve", "vofx_mesh_flag_host", "vofx_mesh_reconstruct_host",
-    "vofx_mesh_evolve_host", "vofx_mesh_color_upload", "vofx_mesh_velocity_upload", "vofx_mesh_run", "vofx_mesh_color_download",
+    "vofx_mesh_evolve_host", "vofx_mesh_reconstruct_swartz", "vofx_mesh_reconstruct_swartz_host", "vofx_mesh_set_reconstruction", "vofx_mesh_color_upload", "vofx_mesh_velocity_upload", "vofx_mesh_run", "vofx_mesh_color_download",
 ]
 
 
@@ -147,6 +147,9 @@ def load():
         getattr(L, "vofx_mesh_flag" + suffix).argtypes = [vp, dp, C.c_double, bp]
         getattr(L, "vofx_mesh_reconstruct" + suffix).argtypes = [vp, dp, bp, dp]
         getattr(L, "vofx_mesh_evolve" + suffix).argtypes = [vp, dp, bp, dp, C.c_double, dp, C.POINTER(C.c_double)]
+    L.vofx_mesh_reconstruct_swartz.argtypes = [vp, dp, bp, dp, C.c_int]
+    L.vofx_mesh_reconstruct_swartz_host.argtypes = [vp, dp, bp, dp, C.c_int]
+    L.vofx_mesh_set_reconstruction.argtypes = [vp, C.c_int, C.c_int]
     L.vofx_mesh_color_upload.argtypes = [vp, dp]
     L.vofx_mesh_velocity_upload.argtypes = [vp, dp]
     L.vofx_mesh_run.argtypes = [vp, C.c_double, C.c_double, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]

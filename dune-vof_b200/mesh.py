@@ -197,6 +197,14 @@ class MeshOperators:
         self._lib.check(self.L.vofx_mesh_reconstruct_host(self._h, u.ctypes.data, flags.ctypes.data, hs.ctypes.data))
         return hs
 
+    def swartz(self, u, flags, max_iterations=10):
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        flags = np.ascontiguousarray(flags, dtype=np.uint8)
+        hs = np.empty((self.m.n_cells, 3))
+        self._lib.check(self.L.vofx_mesh_reconstruct_swartz_host(self._h, u.ctypes.data, flags.ctypes.data, hs.ctypes.data,
+                                                                 int(max_iterations)))
+        return hs
+
     def evolve(self, hs, flags, face_velocity, dt):
         hs = np.ascontiguousarray(hs, dtype=np.float64)
         flags = np.ascontiguousarray(flags, dtype=np.uint8)
@@ -207,8 +215,10 @@ class MeshOperators:
                                                      upd.ctypes.data, self._C.byref(est)))
         return upd, est.value
 
-    def run(self, u, face_velocity, eps, cfl, passes, time=0.0, dt=0.0):
+    def run(self, u, face_velocity, eps, cfl, passes, time=0.0, dt=0.0, swartz=False, max_iterations=10):
         """upload, `passes` device-resident loop passes, download.  Returns (u, time, dt)."""
+        self._lib.check(self.L.vofx_mesh_set_reconstruction(self._h, self._lib.RECON_SWARTZ if swartz else self._lib.RECON_YOUNGS,
+                                                            int(max_iterations)))
         u = np.ascontiguousarray(u, dtype=np.float64)
         vel = np.ascontiguousarray(face_velocity, dtype=np.float64)
         self._lib.check(self.L.vofx_mesh_color_upload(self._h, u.ctypes.data))

@@ -11,6 +11,7 @@
 //   VertexNeighborsStencil< GV >( gv )                           Unstructured::VertexNeighborsStencil< GV >( gv )
 //   FlagOperator< GV >( eps )( uh, flags )                       Unstructured::FlagOperator< GV >( stencils, eps )( uh, flags )
 //   ModifiedYoungsReconstruction< GV, StS >( st )( uh, r, f )    Unstructured::ModifiedYoungsReconstruction< GV >( stencils )( uh, r, f )
+//   ModifiedSwartzReconstruction< GV, StS, IR >( st, n )(..)     Unstructured::ModifiedSwartzReconstruction< GV >( stencils, n )( uh, r, f )
 //   evolution( gv )( recs, flags, velocity, dt, update )         Unstructured::evolution( stencils )( recs, flags, velocity, dt, update )
 //
 // Containers: anything with the interface of dune/vof/dataset.hh:26-87 (begin()/end() in leaf-index order, operator[]( index )).
@@ -322,6 +323,40 @@ namespace Dune
 
       private:
         Context< GV > *context_;
+      };
+
+
+      // reconstruction/modifiedswartz.hh:34-153 (2D): Young's initialiser, then the fixed-point iteration on the normal
+      template< class GV, class StS = VertexNeighborsStencil< GV >, class IR = ModifiedYoungsReconstruction< GV, StS > >
+      struct ModifiedSwartzReconstruction
+      {
+        explicit ModifiedSwartzReconstruction ( const StS &stencils, std::size_t maxIterations = 10 )
+        : context_( &stencils.context() ), maxIterations_( maxIterations )
+        {}
+
+        template< class ColorFunction, class ReconstructionSet, class Flags >
+        void operator() ( const ColorFunction &color, ReconstructionSet &reconstructions, const Flags &flags ) const
+        {
+          auto &c = *context_;
+          c.gatherScalars( color, c.color );
+          c.gatherFlags( flags );
+          c.halfspaces.resize( 3 * c.size() );
+          check( vofx_mesh_reconstruct_swartz_host( c.mesh(), c.color.data(), c.flags.data(), c.halfspaces.data(), int( maxIterations_ ) ) );
+          using HalfSpace = typename ReconstructionSet::DataType;
+          using Coordinate = typename HalfSpace::Coordinate;
+          std::size_t i = 0;
+          for( auto it = reconstructions.begin(); it != reconstructions.end(); ++it, ++i )
+          {
+            Coordinate normal;
+            normal[ 0 ] = c.halfspaces[ 3 * i ];
+            normal[ 1 ] = c.halfspaces[ 3 * i + 1 ];
+            *it = HalfSpace( normal, c.halfspaces[ 3 * i + 2 ] );
+          }
+        }
+
+      private:
+        Context< GV > *context_;
+        std::size_t maxIterations_;
       };
 
 

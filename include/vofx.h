@@ -286,16 +286,21 @@ int64_t vofx_mesh_launch_count ( const vofx_mesh *mesh );
  * update[n_cells]; dt_est is a HOST scalar (the call synchronises the mesh's stream to return it) */
 int vofx_mesh_flag ( vofx_mesh *mesh, const double *u, double eps, uint8_t *flags );
 int vofx_mesh_reconstruct ( vofx_mesh *mesh, const double *u, const uint8_t *flags, double *halfspaces );
+/* ModifiedSwartzReconstruction in 2D (reconstruction/modifiedswartz.hh:70-153): Young's first, then the fixed-point iteration */
+int vofx_mesh_reconstruct_swartz ( vofx_mesh *mesh, const double *u, const uint8_t *flags, double *halfspaces, int max_iterations );
 int vofx_mesh_evolve ( vofx_mesh *mesh, const double *halfspaces, const uint8_t *flags, const double *face_velocity, double dt,
                        double *update, double *dt_est );
 /* the same on HOST arrays (staged through device scratch of the mesh object) */
 int vofx_mesh_flag_host ( vofx_mesh *mesh, const double *u, double eps, uint8_t *flags );
 int vofx_mesh_reconstruct_host ( vofx_mesh *mesh, const double *u, const uint8_t *flags, double *halfspaces );
+int vofx_mesh_reconstruct_swartz_host ( vofx_mesh *mesh, const double *u, const uint8_t *flags, double *halfspaces, int max_iterations );
 int vofx_mesh_evolve_host ( vofx_mesh *mesh, const double *halfspaces, const uint8_t *flags, const double *face_velocity, double dt,
                             double *update, double *dt_est );
 /* the time loop of algorithm.hh:68-95 on a DEVICE-RESIDENT colour function: upload once, run `passes` loop passes
  * (flag, Young's, evolve, u += update, time += dt if dt > 0, dt = cfl * dtEst) without any host synchronisation, read
  * back.  time_io / dt_io are HOST scalars: in = state before the first pass, out = state after the last. */
+/* reconstruction used by vofx_mesh_run: VOFX_RECON_YOUNGS (default) or VOFX_RECON_SWARTZ with max_iterations (reference default 10) */
+int vofx_mesh_set_reconstruction ( vofx_mesh *mesh, int kind, int max_iterations );
 int vofx_mesh_color_upload ( vofx_mesh *mesh, const double *u_host );
 int vofx_mesh_velocity_upload ( vofx_mesh *mesh, const double *face_velocity_host );
 int vofx_mesh_run ( vofx_mesh *mesh, double eps, double cfl, int passes, double *time_io, double *dt_io );

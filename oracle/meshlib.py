@@ -60,6 +60,7 @@ def _reflib():
         L.refmesh_flag.argtypes = [C.c_void_p, _dp, C.c_double, _bp]
         L.refmesh_youngs.argtypes = [C.c_void_p, _dp, _bp, _dp]
         L.refmesh_evolve.argtypes = [C.c_void_p, _dp, _bp, _dp, C.c_double, _dp, _dp]
+        L.refmesh_swartz.argtypes = [C.c_void_p, _dp, _bp, _dp, C.c_int]
         L.refmesh_locate.argtypes = [C.c_void_p, C.c_int64, _dp, C.c_double, _dp]
         _ref = L
     return _ref
@@ -110,6 +111,12 @@ class RefMesh:
         self._check(_reflib().refmesh_youngs(self._h, _d(u), _b(flags), _d(hs)))
         return hs
 
+    def swartz(self, u, flags, max_iterations=10):
+        u, flags = _f64(u), _u8(flags)
+        hs = np.empty((self.m.n_cells, 3))
+        self._check(_reflib().refmesh_swartz(self._h, _d(u), _b(flags), _d(hs), max_iterations))
+        return hs
+
     def evolve(self, hs, flags, face_velocity, dt):
         hs, flags, face_velocity = _f64(hs), _u8(flags), _f64(face_velocity)
         upd = np.empty(self.m.n_cells)
@@ -140,6 +147,7 @@ class OracleMesh:
         L.vo_mesh_flag.argtypes = [M, _dp, C.c_double, _bp]
         L.vo_mesh_youngs.argtypes = [M, _dp, _bp, _dp]
         L.vo_mesh_evolve.argtypes = [M, _dp, _bp, _dp, C.c_double, _dp, _dp]
+        L.vo_mesh_swartz.argtypes = [M, _dp, _bp, _dp, C.c_int]
         L.vo_mesh_locate.argtypes = [M, C.c_int64, _dp, C.c_double, _dp]
         self.L = L
         self.desc = VoMesh(m.n_cells, _i(m.corner_offsets), _d(m.corners), _d(m.centers), _d(m.volumes),
@@ -161,6 +169,12 @@ class OracleMesh:
         u, flags = _f64(u), _u8(flags)
         hs = np.empty((self.m.n_cells, 3))
         self._check(self.L.vo_mesh_youngs(C.byref(self.desc), _d(u), _b(flags), _d(hs)), "vo_mesh_youngs")
+        return hs
+
+    def swartz(self, u, flags, max_iterations=10):
+        u, flags = _f64(u), _u8(flags)
+        hs = np.empty((self.m.n_cells, 3))
+        self._check(self.L.vo_mesh_swartz(C.byref(self.desc), _d(u), _b(flags), _d(hs), max_iterations), "vo_mesh_swartz")
         return hs
 
     def evolve(self, hs, flags, face_velocity, dt):
@@ -210,13 +224,13 @@ def rotation_velocity(m):
     return np.ascontiguousarray(np.stack([fc[:, 1] - 0.5, 0.5 - fc[:, 0]], axis=1) * (2.0 * np.pi / 10.0))
 
 
-def run(ops, m, u, face_velocity, eps, cfl, passes, dt=0.0):
+def run(ops, m, u, face_velocity, eps, cfl, passes, dt=0.0, swartz=False):
     """algorithm.hh:68-95 on a mesh with any of RefMesh / OracleMesh / the device operators"""
     u = _f64(u).copy()
     time = 0.0
     for _ in range(passes):
         flags = ops.flag(u, eps)
-        hs = ops.youngs(u, flags)
+        hs = ops.swartz(u, flags) if swartz else ops.youngs(u, flags)
         upd, est = ops.evolve(hs, flags, face_velocity, dt)
         u = u + upd
         if dt > 0.0:

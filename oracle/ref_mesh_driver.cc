@@ -33,6 +33,7 @@
 #include <dune/vof/geometry/upwindpolygon.hh>
 #include <dune/vof/stencil/vertexneighborsstencil.hh>
 #include <dune/vof/reconstruction/modifiedyoungs.hh>
+#include <dune/vof/reconstruction/modifiedswartz.hh>
 
 namespace
 {
@@ -62,6 +63,7 @@ namespace
     using Flags = Dune::VoF::FlagSet< GridView >;
     using Recs = Dune::VoF::ReconstructionSet< GridView >;
     using Youngs = Dune::VoF::ModifiedYoungsReconstruction< GridView, Stencils >;
+    using Swartz = Dune::VoF::ModifiedSwartzReconstruction< GridView, Stencils, Youngs >;
 
     // owned copies of the caller's arrays
     std::vector< std::int32_t > cornerOffsets, cornerVertex, faceOffsets, faceNeighbor;
@@ -202,6 +204,29 @@ extern "C"
       ctx.loadFlags( flagsIn, flags );
       Ctx::Youngs youngs( *ctx.stencils );
       youngs( uh, recs, flags );
+      auto it = recs.begin();
+      for( std::size_t i = 0; i < ctx.cells(); ++i, ++it )
+      {
+        hs[ 3 * i ] = it->innerNormal()[ 0 ];
+        hs[ 3 * i + 1 ] = it->innerNormal()[ 1 ];
+        hs[ 3 * i + 2 ] = it->boundary().distance();
+      }
+      return 0;
+    } );
+  }
+
+  // reconstruction/modifiedswartz.hh:70-153 (2D), initialised by ModifiedYoungsReconstruction
+  int refmesh_swartz ( void *handle, const double *u, const std::uint8_t *flagsIn, double *hs, int maxIterations )
+  {
+    return guarded( [ & ] {
+      Ctx &ctx = *static_cast< Ctx * >( handle );
+      Ctx::Color uh( *ctx.gv );
+      Ctx::Flags flags( *ctx.gv );
+      Ctx::Recs recs( *ctx.gv );
+      std::copy( u, u + ctx.cells(), uh.begin() );
+      ctx.loadFlags( flagsIn, flags );
+      Ctx::Swartz swartz( *ctx.stencils, std::size_t( maxIterations ) );
+      swartz( uh, recs, flags );
       auto it = recs.begin();
       for( std::size_t i = 0; i < ctx.cells(); ++i, ++it )
       {

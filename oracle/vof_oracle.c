@@ -3176,3 +3176,77 @@ int vo_mesh_evolve ( const vo_mesh *m, const double *hs, const uint8_t *flags, c
   *dt_est = dtEst;
   return 0;
 }
+
+/* R3 on a mesh: ModifiedSwartzReconstruction::applyLocal for 2D, reconstruction/modifiedswartz.hh:102-153 */
+static int mesh_interface_centroid ( const vo_mesh *m, int64_t cell, const double *normal, double color, double *centroid )
+{
+  vo_polygon p;
+  double hs[ 3 ], line[ 2 ][ 2 ];
+  if( mesh_cell_polygon( m, cell, &p ) )
+    return 1;
+  locate_2d( &p, normal, color, hs );
+  polygon_plane_cut( &p, hs, line );
+  centroid[ 0 ] = ( line[ 0 ][ 0 ] + line[ 1 ][ 0 ] ) * 0.5;   /* Line::centroid, 2d/polygon.hh:183-188 */
+  centroid[ 1 ] = ( line[ 0 ][ 1 ] + line[ 1 ][ 1 ] ) * 0.5;
+  return 0;
+}
+
+static int mesh_swartz_local ( const vo_mesh *m, const double *u, const uint8_t *flags, int64_t cell, double *hsAll, int maxIterations )
+{
+  double *reconstruction = hsAll + 3 * cell;
+  double normal[ 2 ] = { reconstruction[ 0 ], reconstruction[ 1 ] };
+  int iterations = 0;
+  double residuum = 0.0;
+  do
+  {
+    const double oldNormal[ 2 ] = { normal[ 0 ], normal[ 1 ] };
+    normal[ 0 ] = normal[ 1 ] = 0.0;
+    double cEn[ 2 ];
+    if( mesh_interface_centroid( m, cell, oldNormal, u[ cell ], cEn ) )
+      return 1;
+    for( int s = m->stencil_offsets[ cell ]; s < m->stencil_offsets[ cell + 1 ]; ++s )
+    {
+      const int64_t nb = m->stencil[ s ];
+      if( !is_mixed( flags[ nb ] ) )
+        continue;
+      double cNb[ 2 ];
+      if( mesh_interface_centroid( m, nb, oldNormal, u[ nb ], cNb ) )
+        return 1;
+      const double dd[ 2 ] = { cNb[ 0 ] - cEn[ 0 ], cNb[ 1 ] - cEn[ 1 ] };
+      double centerNormal[ 2 ] = { -dd[ 1 ], dd[ 0 ] };
+      if( dotn( centerNormal, oldNormal, 2 ) < 0 )
+      {
+        centerNormal[ 0 ] *= -1.0;
+        centerNormal[ 1 ] *= -1.0;
+      }
+      const double nrm = normn( centerNormal, 2 );
+      centerNormal[ 0 ] /= nrm;
+      centerNormal[ 1 ] /= nrm;
+      const double weight = 1.0;
+      normal[ 0 ] += weight * centerNormal[ 0 ];
+      normal[ 1 ] += weight * centerNormal[ 1 ];
+    }
+    if( normn( normal, 2 ) < 0.5 )
+      return 0;
+    const double nrm = normn( normal, 2 );
+    normal[ 0 ] /= nrm;
+    normal[ 1 ] /= nrm;
+    if( vo_mesh_locate( m, cell, normal, u[ cell ], reconstruction ) )
+      return 1;
+    residuum = 1.0 - dotn( normal, oldNormal, 2 );
+    ++iterations;
+  }
+  while( residuum > 1e-12 && iterations < maxIterations );
+  return 0;
+}
+
+int vo_mesh_swartz ( const vo_mesh *m, const double *u, const uint8_t *flags, double *hs, int max_iterations )
+{
+  if( vo_mesh_youngs( m, u, flags, hs ) )      /* initializer()(..), modifiedswartz.hh:72 */
+    return 1;
+  for( int64_t c = 0; c < m->n_cells; ++c )
+    if( is_mixed( flags[ c ] ) && mesh_swartz_local( m, u, flags, c, hs, max_iterations ) )
+      return 1;
+  return 0;
+}
+

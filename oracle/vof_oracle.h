@@ -73,6 +73,7 @@ typedef struct
 
 int vo_mesh_flag ( const vo_mesh *m, const double *u, double eps, uint8_t *flags );
 int vo_mesh_youngs ( const vo_mesh *m, const double *u, const uint8_t *flags, double *hs );
+int vo_mesh_swartz ( const vo_mesh *m, const double *u, const uint8_t *flags, double *hs, int max_iterations );   /* 2D, modifiedswartz.hh:70-153 */
 int vo_mesh_evolve ( const vo_mesh *m, const double *hs, const uint8_t *flags, const double *face_velocity, double dt, double *update, double *dt_est );
 int vo_mesh_locate ( const vo_mesh *m, int64_t cell, const double *normal, double fraction, double *out );
 

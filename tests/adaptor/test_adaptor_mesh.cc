@@ -391,6 +391,22 @@ int main ()
 #else
     (void) refOk;
 #endif
+    {
+      // ModifiedSwartzReconstruction on the final state
+      Dune::VoFx::Unstructured::ModifiedSwartzReconstruction< GV > swartz( stencils, 10 );
+      flagOperator( uh, flags );
+      swartz( uh, recs, flags );
+      vo_mesh_flag( &om, uo.data(), 1e-6, flo.data() );
+      vo_mesh_swartz( &om, uo.data(), flo.data(), hso.data(), 10 );
+      bool swartzOk = true;
+      std::size_t i = 0;
+      for( auto it = recs.begin(); it != recs.end(); ++it, ++i )
+      {
+        const double hs[ 3 ] = { it->innerNormal()[ 0 ], it->innerNormal()[ 1 ], it->boundary().distance() };
+        swartzOk &= sameBits( hs, hso.data() + 3 * i, 3 );
+      }
+      expect( swartzOk, "modified Swartz half-spaces equal the oracle's bit for bit" );
+    }
     expect( flagsOk, "flags of 12 loop passes equal the oracle's" );
     expect( recsOk, "half-spaces of 12 loop passes equal the oracle's bit for bit" );
     expect( updOk, "updates of 12 loop passes equal the oracle's bit for bit" );

@@ -1,6 +1,6 @@
 """Generates tests/golden/mesh2d_{tri,quad,mixed}.npz from the UNMODIFIED reference on the unstructured 2D grid model
-(oracle/_ref/libvofrefmesh.so: /root/reference's FlagOperator, ModifiedYoungsReconstruction, VertexNeighborsStencil and
-Evolution on oracle/shim/dune/grid/common/meshgrid.hh).  Run where /root/reference is mounted:
+(oracle/_ref/libvofrefmesh.so: /root/reference's FlagOperator, ModifiedYoungsReconstruction, ModifiedSwartzReconstruction,
+VertexNeighborsStencil and Evolution on oracle/shim/dune/grid/common/meshgrid.hh).  Run where /root/reference is mounted:
 
     python tests/golden/make_golden_mesh.py
 
@@ -33,15 +33,18 @@ def main():
         flags = ref.flag(u, EPS)
         hs = ref.youngs(u, flags)
         upd, est = ref.evolve(hs, flags, vel, DT)
+        hs_swartz = ref.swartz(u, flags, 10)
         u_run = meshlib.circle_fractions(m)
         u_end, t_end, dt_end = meshlib.run(ref, m, u_run, vel, EPS, CFL, PASSES)
+        u_end_sw, t_end_sw, dt_end_sw = meshlib.run(ref, m, u_run, vel, EPS, CFL, PASSES, swartz=True)
         assert np.array_equal(s_off, m.stencil_offsets) and np.array_equal(s_ent, m.stencil)
         # the flattened mesh is stored field by field (mesh_*): the fixtures do not depend on numpy's rounding elsewhere
         fields = {"mesh_" + k: getattr(m, k) for k in m.__dataclass_fields__}
         np.savez_compressed(os.path.join(OUT, f"mesh2d_{kind}.npz"), **fields, ref_stencil_offsets=s_off,
                             ref_stencil=s_ent, u=u, velocity=vel,
                             eps=EPS, dt=DT, cfl=CFL, passes=PASSES, flags=flags, halfspaces=hs, update=upd, dt_est=est,
-                            u_run=u_run, u_end=u_end, time_end=t_end, dt_end=dt_end)
+                            u_run=u_run, u_end=u_end, time_end=t_end, dt_end=dt_end,
+                            halfspaces_swartz=hs_swartz, u_end_swartz=u_end_sw, time_end_swartz=t_end_sw, dt_end_swartz=dt_end_sw)
         print(kind, m.n_cells, "cells", int(np.count_nonzero((flags == 1) | (flags == 2))), "mixed")
 
 

@@ -40,6 +40,33 @@ def test_resident_loop_matches_golden(kind):
     assert n_mismatch(u, v) == 0 and (t, dt) == (t2, dt2)
 
 
+@pytest.mark.parametrize("kind", KINDS)
+def test_swartz_matches_golden(kind):
+    """ModifiedSwartzReconstruction in 2D on the mesh: operator and device-resident loop"""
+    z = golden(f"mesh2d_{kind}.npz")
+    m = mesh.FlatMesh.from_npz(z)
+    D = mesh.MeshOperators(m)
+    hs = D.swartz(z["u"], z["flags"], 10)
+    assert n_mismatch(hs, z["halfspaces_swartz"]) == 0
+    u, t, dt = D.run(z["u_run"], z["velocity"], float(z["eps"]), float(z["cfl"]), int(z["passes"]), swartz=True)
+    assert n_mismatch(u, z["u_end_swartz"]) == 0
+    assert t == float(z["time_end_swartz"]) and dt == float(z["dt_end_swartz"])
+    # switching back to Young's on the same object rebuilds the captured pass
+    u, t, dt = D.run(z["u_run"], z["velocity"], float(z["eps"]), float(z["cfl"]), int(z["passes"]))
+    assert n_mismatch(u, z["u_end"]) == 0
+
+
+def test_swartz_larger_mesh_matches_oracle():
+    v, cells = mesh.perturbed_square(96, "mixed", 31)
+    m = mesh.flatten(v, cells)
+    O, D = meshlib.OracleMesh(m), mesh.MeshOperators(m)
+    u = meshlib.circle_fractions(m, center=(0.5, 0.7), radius=0.2, samples=8)
+    vel = meshlib.rotation_velocity(m)
+    a = meshlib.run(O, m, u, vel, 1e-6, 0.5, 15, swartz=True)
+    b = D.run(u, vel, 1e-6, 0.5, 15, swartz=True)
+    assert n_mismatch(a[0], b[0]) == 0 and a[1:] == b[1:]
+
+
 @pytest.mark.parametrize("kind,n,seed", [("tri", 160, 21), ("mixed", 192, 22), ("quad", 256, 23)])
 def test_larger_meshes_match_oracle(kind, n, seed):
     v, cells = mesh.perturbed_square(n, kind, seed)

@@ -57,6 +57,20 @@ def test_oracle_matches_golden_time_loop(kind):
     assert abs(((u - z["u_run"]) * m.volumes).sum()) < 1e-15
 
 
+@pytest.mark.parametrize("kind", KINDS)
+def test_oracle_matches_golden_swartz(kind):
+    """ModifiedSwartzReconstruction in 2D (reconstruction/modifiedswartz.hh:70-153) on the mesh"""
+    z = golden(f"mesh2d_{kind}.npz")
+    m = mesh.FlatMesh.from_npz(z)
+    O = meshlib.OracleMesh(m)
+    hs = O.swartz(z["u"], z["flags"], 10)
+    assert n_mismatch(hs, z["halfspaces_swartz"]) == 0
+    assert n_mismatch(hs, z["halfspaces"]) > 0          # the iteration does change the Young's normals
+    u, t, dt = meshlib.run(O, m, z["u_run"], z["velocity"], float(z["eps"]), float(z["cfl"]), int(z["passes"]), swartz=True)
+    assert n_mismatch(u, z["u_end_swartz"]) == 0
+    assert t == float(z["time_end_swartz"]) and dt == float(z["dt_end_swartz"])
+
+
 @pytest.mark.skipif(not meshlib.ref_available(), reason="reference harness not built (needs /root/reference)")
 @pytest.mark.parametrize("kind,n,seed", [("tri", 40, 1), ("quad", 48, 2), ("mixed", 36, 3), ("tri", 17, 4)])
 def test_oracle_matches_live_reference(kind, n, seed):
@@ -69,6 +83,9 @@ def test_oracle_matches_live_reference(kind, n, seed):
     vel = meshlib.rotation_velocity(m)
     a = meshlib.run(R, m, u, vel, 1e-6, 0.5, 20)
     b = meshlib.run(O, m, u, vel, 1e-6, 0.5, 20)
+    assert n_mismatch(a[0], b[0]) == 0 and a[1:] == b[1:]
+    a = meshlib.run(R, m, u, vel, 1e-6, 0.5, 10, swartz=True)
+    b = meshlib.run(O, m, u, vel, 1e-6, 0.5, 10, swartz=True)
     assert n_mismatch(a[0], b[0]) == 0 and a[1:] == b[1:]
     # the plane-constant solve on single cells, random normals and fractions (geometry/algorithm.hh:68-111)
     rng = np.random.default_rng(seed)
