@@ -19,6 +19,11 @@ namespace vofx
         k_flux_cell3< 3, 8 ><<< blocks, 128, 0, s >>>( g, velocityByValue, hs, flags, mixedList, state, capacity, records, tasks, taskCapacity, (const coop::ClipCase *) clipTable, timeOverride, dtOverride );
       k_flux_clip_serial3< 3 ><<< 148, 64, 0, s >>>( g, velocity, hs, flags, mixedList, state, records, tasks, taskCapacity, timeOverride, dtOverride );
     }
-    void make_clip_table ( void *host256x64 ) { coop::make_clip_table( (coop::ClipCase *) host256x64 ); }
+    size_t clip_table_bytes () { return sizeof( coop::ClipCase ) * ( 256 + coop::kClipBoundaryCases ); }
+    void make_clip_table ( void *host )
+    {
+      coop::make_clip_table( (coop::ClipCase *) host );
+      coop::make_clip_boundary_table( (coop::ClipCase *) host + 256 );
+    }
   } // namespace launch
 } // namespace vofx

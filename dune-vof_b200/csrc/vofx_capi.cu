@@ -83,7 +83,7 @@ struct vofx_ctx
   void *rootTasks = nullptr;        // coop::RootTask per mixed cell: brackets found by k_youngs_coop3, roots by k_locate_root3
   int fluxLanes = 8;               // lanes per mixed cell of the 3D flux kernel; measured at 512^3: 0.36 ms (8) vs 0.51 ms (4)
   int lanesPerCell = 4;            // measured on B200 at 512^3: 0.47 ms (4 lanes per cell) vs 0.64 ms (8)
-  void *clipTable = nullptr;        // coop::ClipCase[ 256 ]
+  void *clipTable = nullptr;        // coop::ClipCase[ 256 ] by inner mask, then [ 6561 ] by ( outer / inner / on the plane ) pattern
   StepState *state = nullptr;
   double *curv1 = nullptr;
   unsigned char *ok1 = nullptr;
@@ -585,7 +585,7 @@ extern "C"
       const long long tc = 6LL * ctx->capacity;
       ctx->taskCapacity = (int) ( tc < ( 1LL << 30 ) ? tc : ( 1LL << 30 ) );
       alloc( (void **) &ctx->tasks, sizeof( int ) * (size_t) ctx->taskCapacity );
-      alloc( (void **) &ctx->clipTable, 256 * 64 );
+      alloc( (void **) &ctx->clipTable, launch::clip_table_bytes() );
       alloc( (void **) &ctx->sweepTable, launch::sweep_table_bytes() );
       alloc( (void **) &ctx->serialCells, sizeof( int ) * (size_t) ctx->capacity );
       alloc( (void **) &ctx->rootTasks, launch::root_task_bytes() * (size_t) ctx->capacity );
@@ -619,7 +619,7 @@ extern "C"
     }
     if( ctx->clipTable )
     {
-      std::vector< unsigned char > table( 256 * 64 );
+      std::vector< unsigned char > table( launch::clip_table_bytes() );
       launch::make_clip_table( table.data() );
       cudaMemcpy( ctx->clipTable, table.data(), table.size(), cudaMemcpyHostToDevice );
     }
@@ -1137,6 +1137,22 @@ extern "C"
       *dt_est = s.dtEstLast;
     if( mixed_cells )
       *mixed_cells = s.mixedCountLast;
+    return rc;
+  }
+
+  int vofx_step_counters ( vofx_ctx *ctx, int64_t *out )
+  {
+    if( !ctx || !out )
+      return fail( VOFX_ERR_ARGUMENT, "null argument" );
+    int rc = setDevice( ctx );
+    if( rc )
+      return rc;
+    StepState s;
+    rc = readState( ctx, s );
+    out[ 0 ] = s.mixedCount;
+    out[ 1 ] = s.serialCount;
+    out[ 2 ] = s.serialLocate;
+    out[ 3 ] = s.rootCount;
     return rc;
   }
 

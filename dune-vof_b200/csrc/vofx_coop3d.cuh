@@ -38,49 +38,91 @@ namespace vofx
     };
     static_assert( sizeof( ClipCase ) == 64, "ClipCase must be 64 bytes" );
 
-    // table generator: runs the reference's walk (clip_walk) for every inner mask
+    // Nodes ON the plane (|levelSet| < eps, 3d/intersect.hh:104-108) change the walk (no cut node on their edges, the cap
+    // passes through them).  They are not rare: a cell whose fraction reached 0 or 1 is located with the plane through one of
+    // its nodes, and the swept boxes of its faces share that node - 10 % of the clips of the 512^3 LeVeque run after 60 steps.
+    // A second table, indexed by the ternary code of ( outer / inner / on the plane ) per node, covers them.
+    constexpr int kClipBoundaryCases = 6561;   // 3^8
+
+    VOFX_HD inline unsigned clip_ternary ( unsigned innerMask, unsigned boundaryMask )
+    {
+      unsigned code = 0, power = 1;
+      for( int i = 0; i < 8; ++i )
+      {
+        code += ( ( ( innerMask >> i ) & 1u ) + ( ( boundaryMask >> i ) & 1u ) ) * power;
+        power *= 3;
+      }
+      return code;
+    }
+
+    // one table entry from the reference's walk (clip_walk); nCut = 0xFE: empty result, 0xFF: not representable (serial path)
+    inline void fill_clip_case ( ClipCase &c, unsigned innerMask, unsigned boundaryMask )
+    {
+      for( unsigned i = 0; i < sizeof( ClipCase ); ++i )
+        reinterpret_cast< unsigned char * >( &c )[ i ] = 0;
+      ClipTopo t;
+      if( !clip_walk( innerMask, boundaryMask, t ) )
+      {
+        c.nCut = 0xFE;       // empty result, 3d/intersect.hh:115-120
+        return;
+      }
+      bool regular = t.nNew <= 6 && t.nFaces <= 7;
+      int nEdges = 0;
+      for( int f = 0; regular && f < t.nFaces; ++f )
+      {
+        const int len = t.flen[ f ];
+        nEdges += len;
+        regular = len <= 6 && nEdges <= kMaxClipEdges;
+        for( int k = 0; regular && k < len; ++k )
+          regular = t.fe1[ f ][ k ] == t.fe0[ f ][ ( k + 1 ) % len ];
+      }
+      if( !regular )
+      {
+        c.nCut = 0xFF;
+        return;
+      }
+      c.nCut = (unsigned char) t.nNew;
+      c.nFaces = (unsigned char) t.nFaces;
+      for( int j = 0; j < t.nNew; ++j )
+        c.cut[ j ] = (unsigned char) ( t.cutA[ j ] | ( t.cutB[ j ] << 3 ) );
+      int e = 0;
+      for( int f = 0; f < t.nFaces; ++f )
+      {
+        c.faceStart[ f ] = (unsigned char) e;
+        for( int k = 0; k < t.flen[ f ]; ++k )
+        {
+          const int id = t.fe0[ f ][ k ];
+          c.refs[ e++ ] = (unsigned char) ( ( id < t.n ? t.innerNode[ id ] : 8 + ( id - t.n ) ) | ( f << 4 ) );
+        }
+      }
+      for( int f = t.nFaces; f < 8; ++f )
+        c.faceStart[ f ] = (unsigned char) e;
+      c.nEdges = (unsigned char) e;
+    }
+
+    // table generators: the reference's walk for every inner mask (no node on the plane) ...
     inline void make_clip_table ( ClipCase *table )
     {
       for( unsigned mask = 0; mask < 256; ++mask )
+        fill_clip_case( table[ mask ], mask, 0u );
+    }
+
+    // ... and for every ( outer / inner / on the plane ) pattern, indexed by clip_ternary
+    inline void make_clip_boundary_table ( ClipCase *table )
+    {
+      for( unsigned code = 0; code < (unsigned) kClipBoundaryCases; ++code )
       {
-        ClipCase &c = table[ mask ];
-        for( unsigned i = 0; i < sizeof( ClipCase ); ++i )
-          reinterpret_cast< unsigned char * >( &c )[ i ] = 0;
-        ClipTopo t;
-        if( !clip_walk( mask, 0u, t ) )
-          continue;          // empty result (only mask 0)
-        bool regular = t.nNew <= 6 && t.nFaces <= 7;
-        int nEdges = 0;
-        for( int f = 0; regular && f < t.nFaces; ++f )
+        unsigned inner = 0, bnd = 0, rest = code;
+        for( int i = 0; i < 8; ++i )
         {
-          const int len = t.flen[ f ];
-          nEdges += len;
-          regular = len <= 6 && nEdges <= kMaxClipEdges;
-          for( int k = 0; regular && k < len; ++k )
-            regular = t.fe1[ f ][ k ] == t.fe0[ f ][ ( k + 1 ) % len ];
+          const unsigned digit = rest % 3;
+          rest /= 3;
+          if( digit >= 1 )
+            inner |= 1u << i;
+          if( digit == 2 )
+            bnd |= 1u << i;
         }
-        if( !regular )
-        {
-          c.nCut = 0xFF;
-          continue;
-        }
-        c.nCut = (unsigned char) t.nNew;
-        c.nFaces = (unsigned char) t.nFaces;
-        for( int j = 0; j < t.nNew; ++j )
-          c.cut[ j ] = (unsigned char) ( t.cutA[ j ] | ( t.cutB[ j ] << 3 ) );
-        int e = 0;
-        for( int f = 0; f < t.nFaces; ++f )
-        {
-          c.faceStart[ f ] = (unsigned char) e;
-          for( int k = 0; k < t.flen[ f ]; ++k )
-          {
-            const int id = t.fe0[ f ][ k ];
-            c.refs[ e++ ] = (unsigned char) ( ( id < t.n ? t.innerNode[ id ] : 8 + ( id - t.n ) ) | ( f << 4 ) );
-          }
-        }
-        for( int f = t.nFaces; f < 8; ++f )
-          c.faceStart[ f ] = (unsigned char) e;
-        c.nEdges = (unsigned char) e;
+        fill_clip_case( table[ code ], inner, bnd );
       }
     }
 
@@ -118,14 +160,23 @@ namespace vofx
     }
 
     // phase B: lane j creates cut node j.  Returns 0 table path, 1 empty result, 2 serial path (the same for all lanes)
-    VOFX_HD inline int clip_phase_cut ( int lane, ClipScratch &S, const Hs3 &hs, const ClipCase *table, const ClipCase *&cs )
+    VOFX_HD inline int clip_phase_cut ( int lane, ClipScratch &S, const Hs3 &hs, const ClipCase *table, const ClipCase *&cs,
+                                        const ClipCase *boundaryTable = nullptr )
     {
       unsigned innerMask, boundaryMask;
       clip_masks( S, innerMask, boundaryMask );
       cs = table + innerMask;
       if( innerMask == 0 )
         return 1;
-      if( boundaryMask != 0 || cs->nCut == 0xFF )
+      if( boundaryMask != 0 )
+      {
+        if( !boundaryTable )
+          return 2;
+        cs = boundaryTable + clip_ternary( innerMask, boundaryMask );
+        if( cs->nCut == 0xFE )
+          return 1;
+      }
+      if( cs->nCut == 0xFF )
         return 2;
       if( lane < cs->nCut )
       {

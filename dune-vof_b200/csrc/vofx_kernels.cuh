@@ -1710,7 +1710,7 @@ namespace vofx
           int status = 0;
 #pragma unroll
           for( int j = lane; j < 8; j += LANES )
-            status = coop::clip_phase_cut( j, S, H, table, cs );
+            status = coop::clip_phase_cut( j, S, H, table, cs, clipTable + 256 );   // patterns with nodes on the plane: global table
           __syncwarp( groupMask );
           if( status == 0 )
           {

@@ -77,7 +77,8 @@ namespace vofx
     void flux_cell3 ( int lanes, int blocks, cudaStream_t s, Grid g, const Velocity *velocity, const Velocity &velocityByValue, const double *hs, const unsigned char *flags, const int *mixedList,
                       StepState *state, int capacity, FluxRecord *records, int *tasks, int taskCapacity, const void *clipTable,
                       const double *timeOverride, const double *dtOverride );
-    void make_clip_table ( void *host256x64 );   // 256 entries of 64 bytes (coop::ClipCase)
+    size_t clip_table_bytes ();
+    void make_clip_table ( void *host );   // clip_table_bytes(): 256 + 6561 entries of 64 bytes (coop::ClipCase)
     void test_locate3 ( int blocks, long long count, const double *lo, const double *h, const double *normal, const double *fraction, double *out );
     void test_flux3 ( int blocks, long long count, const double *lo, const double *h, const int *face, const double *v, const double *hs, double *out );
     float fp64_rate ( int mode, int blocks, int iters, int reps, double *scratch );

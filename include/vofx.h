@@ -229,6 +229,11 @@ int vofx_test_locate ( int dim, int64_t count, const double *lo, const double *h
 int vofx_test_flux ( int dim, int64_t count, const double *lo, const double *h, const int32_t *face, const double *v, const double *halfspaces, double *flux );
 int vofx_test_interface ( int dim, int64_t count, const double *lo, const double *h, const double *halfspaces, int32_t *nverts, double *centroid, double *measure );
 
+/* work counters of the step in flight (between vofx_step_phase( 1 ) and vofx_step_finish; synchronises): out[0] cells in the
+ * band list, out[1] face clips left to the serial kernel (a node of the swept box on the plane), out[2] cells whose
+ * plane-constant solve is left to the serial kernel (tied node heights outside the table), out[3] cells with a root search */
+int vofx_step_counters ( vofx_ctx *ctx, int64_t *out );
+
 /* counters of kernel launches issued by this context since creation (bench.py reports them as gpu_launches) */
 int64_t vofx_launch_count ( const vofx_ctx *ctx );
 

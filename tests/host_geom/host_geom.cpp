@@ -109,11 +109,12 @@ extern "C"
   // the 8-lane cooperative flux (vofx_coop3d.cuh), lanes emulated phase by phase.  *path: 0 table, 1 empty, 2 serial
   int hg_flux_coop ( const double *lo, const double *h, int face, const double *v, const double *hs, double *out, int *path )
   {
-    static coop::ClipCase table[ 256 ];
+    static coop::ClipCase table[ 256 + coop::kClipBoundaryCases ];
     static bool have = false;
     if( !have )
     {
       coop::make_clip_table( table );
+      coop::make_clip_boundary_table( table + 256 );
       have = true;
     }
     const Hs3 H = { { hs[ 0 ], hs[ 1 ], hs[ 2 ] }, hs[ 3 ] };
@@ -136,7 +137,7 @@ extern "C"
     const coop::ClipCase *cs = nullptr;
     int status = 0;
     for( int lane = 0; lane < 8; ++lane )
-      status = coop::clip_phase_cut( lane, S, H, table, cs );
+      status = coop::clip_phase_cut( lane, S, H, table, cs, table + 256 );
     *path = status;
     if( status == 1 )
       *out = fabs( 0.0 / 3.0 );
@@ -153,6 +154,20 @@ extern "C"
       *out = coop::clip_phase_sum( S, *cs );
     }
     return 0;
+  }
+
+  // entries of the boundary-pattern table: *irregular left to the serial path, *empty empty results
+  int hg_clip_boundary_table ( int *irregular, int *empty )
+  {
+    static coop::ClipCase table[ coop::kClipBoundaryCases ];
+    coop::make_clip_boundary_table( table );
+    *irregular = *empty = 0;
+    for( int m = 0; m < coop::kClipBoundaryCases; ++m )
+    {
+      *irregular += table[ m ].nCut == 0xFF;
+      *empty += table[ m ].nCut == 0xFE;
+    }
+    return coop::kClipBoundaryCases;
   }
 
   int hg_clip_table_irregular ( void )

@@ -121,9 +121,56 @@ def test_geometry_bit_exact(hg, dim):
         nb, vb, cb, mb = hg_iface(hg, lo, h, hs)
         assert na == nb and same_bits(va, vb) and same_bits(ca, cb) and same_bits(ma, mb)
     if dim == 3:
-        # the table path must carry the bulk of the clips; the serial path is for nodes on the plane
-        assert paths.get(0, 0) > 2000 and paths.get(2, 0) < 0.2 * sum(paths.values()), paths
+        # the tables carry the clips, including the patterns with nodes ON the plane (cells located at fraction 0 or 1);
+        # the serial path is only for the few patterns the table cannot represent
+        assert paths.get(0, 0) > 2000 and paths.get(2, 0) < 0.01 * sum(paths.values()), paths
         print("cooperative clip paths (0 table, 1 empty, 2 serial):", paths)
+
+
+def test_clip_on_plane_patterns(hg):
+    """nodes of the swept box exactly on the plane (3d/intersect.hh:104-108): planes through cell nodes, edges and faces"""
+    irregular, empty = C.c_int(0), C.c_int(0)
+    total = hg.hg_clip_boundary_table(C.byref(irregular), C.byref(empty))
+    assert total == 6561 and irregular.value < 0.5 * total, (irregular.value, empty.value)
+    rng = np.random.default_rng(5)
+    paths = {}
+    for it in range(3000):
+        res = int(rng.choice([64, 128, 512]))
+        h = np.full(3, 1.0 / res)
+        lo = rng.integers(0, res, 3) * h
+        face = int(rng.integers(0, 6))
+        vel = rng.normal(size=3) * h[0] * 0.5
+        mode = it % 4
+        if mode == 0:      # a cell filled to fraction 0 or 1: the plane passes through one of its nodes
+            n = rng.normal(size=3)
+            n /= np.linalg.norm(n)
+            hs = O.locate(lo, h, n, float(rng.choice([0.0, 1.0, 1.3, -0.2])))
+        elif mode == 1:    # axis-aligned plane through a cell face
+            k = int(rng.integers(0, 3))
+            n = np.zeros(3)
+            n[k] = rng.choice([-1.0, 1.0])
+            hs = np.append(n, -n[k] * (lo[k] + rng.integers(0, 2) * h[k]))
+            vel[int(rng.integers(0, 3))] = 0.0
+        elif mode == 2:    # diagonal plane through an edge of the cell (exactly representable)
+            k = int(rng.integers(0, 3))
+            n = np.ones(3) * rng.choice([-1.0, 1.0], size=3)
+            n[k] = 0.0
+            corner = lo + rng.integers(0, 2, 3) * h
+            hs = np.append(n, -np.dot(n, corner))
+        else:              # plane through three nodes of the swept box
+            n = np.array([1.0, 1.0, 1.0]) * rng.choice([-1.0, 1.0], size=3)
+            corner = lo + rng.integers(0, 2, 3) * h
+            hs = np.append(n, -np.dot(n, corner))
+            vel = np.zeros(3)
+            vel[face // 2] = (1 if face % 2 else -1) * h[0] * 0.25
+        if np.isnan(hs[-1]):
+            continue
+        fo = O.flux(lo, h, face, vel, hs)
+        fc, path = hg_flux_coop(hg, lo, h, face, vel, hs)
+        assert same_bits(fo, fc), (mode, path, lo, h, face, vel, hs)
+        paths[(mode, path)] = paths.get((mode, path), 0) + 1
+    print("on-plane clips by (mode, path):", dict(sorted(paths.items())))
+    assert sum(v for (m, p), v in paths.items() if p == 0) > 1000
 
 
 def test_det_cospi_matches_oracle(hg):
