@@ -38,3 +38,17 @@ namespace vofx
     { k_hf< 3 ><<< blocks, 128, 0, s >>>( g, u, mixedList, state, capacity, hs ); }
   } // namespace launch
 } // namespace vofx
+
+#if defined( VOFX_COUNT_WALKS )
+extern "C" int vofx_debug_counters ( unsigned long long *out, int reset )
+{
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol( out, vofx::coop::g_dbg, 8 * sizeof( unsigned long long ) );
+  if( reset )
+  {
+    unsigned long long zero[ 8 ] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+    cudaMemcpyToSymbol( vofx::coop::g_dbg, zero, sizeof( zero ) );
+  }
+  return 0;
+}
+#endif

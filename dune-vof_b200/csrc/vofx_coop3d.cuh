@@ -676,6 +676,9 @@ namespace vofx
       int cell;
     };
 
+#if defined( __CUDACC__ ) && defined( VOFX_COUNT_WALKS )
+    static __device__ unsigned long long g_dbg[ 8 ];
+#endif
     template< int L >
     VOFX_HD inline bool locate_coop ( const Group &G, LocateScratch &S, const SweepTable &T, const double *lo, const double *h,
                                       const double *innerNormal, double fraction, double &dist, RootTask *root = nullptr )
@@ -833,6 +836,16 @@ namespace vofx
         }
       }
       const bool walking = ( C == nullptr );
+#if defined( __CUDA_ARCH__ ) && defined( VOFX_COUNT_WALKS )
+      if( G.lane == 0 )
+      {
+        atomicAdd( &g_dbg[ 0 ], 1ull );
+        atomicAdd( &g_dbg[ 1 ], walking ? 1ull : 0ull );
+        atomicAdd( &g_dbg[ 2 ], (unsigned long long) nU );
+        atomicAdd( &g_dbg[ 3 ], ( fraction >= 1.0 ) ? 1ull : 0ull );
+        atomicAdd( &g_dbg[ 4 ], ( fraction <= 0.0 ) ? 1ull : 0ull );
+      }
+#endif
       Sweep sweep;                                       // state of lane 0's walk (topology only)
       if( walking )
       {
@@ -978,6 +991,16 @@ namespace vofx
         const double Vd_k1 = Vd_k + V( hk );
         if( fabs( Vd_k1 - givenVolume ) < 1e-14 )
         {
+#if defined( __CUDA_ARCH__ ) && defined( VOFX_COUNT_WALKS )
+          if( G.lane == 0 )
+          {
+            atomicAdd( &g_dbg[ 5 ], 1ull );
+            if( k + 1 == nU - 1 )
+              atomicAdd( &g_dbg[ 6 ], 1ull );
+            if( k == 0 )
+              atomicAdd( &g_dbg[ 7 ], 1ull );
+          }
+#endif
           dist = dU[ k + 1 ];
           return true;
         }
