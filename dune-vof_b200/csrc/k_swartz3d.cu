@@ -1,4 +1,6 @@
 // vofx: launchers of band kernels (see vofx_launch.h); generated layout, one group of kernels per translation unit.
+#include <cstdlib>
+
 #include "vofx_launch.h"
 #include "vofx_kernels.cuh"
 
@@ -27,17 +29,21 @@ namespace vofx
       SwzCell *C = (SwzCell *) cells;
       SwzTask *K = (SwzTask *) tasks;
       k_swz_setup< 3 ><<< sms * 8, 128, 0, s >>>( g, flags, mixedList, state, capacity, hs, C, K, counter );
+      // grid-stride kernels over the (cell, neighbour) tasks: grids well beyond the resident blocks balance the waves
+      // (256^3, ms per step: 16 blocks/SM 9.75, 40 8.99, 80 8.72)
+      static const int locateBlocks = std::getenv( "VOFX_SWZ_BLOCKS_PER_SM" ) ? std::atoi( std::getenv( "VOFX_SWZ_BLOCKS_PER_SM" ) ) : 80;
+      static const int otherBlocks = std::getenv( "VOFX_SWZ_OTHER_BLOCKS_PER_SM" ) ? std::atoi( std::getenv( "VOFX_SWZ_OTHER_BLOCKS_PER_SM" ) ) : 48;
       for( int it = 0; it < maxIterations; ++it )
       {
         if( lanes == 8 )
           k_swz_locate< 8 ><<< sms * 8, 128, 0, s >>>( g, u, C, K, counter, T );
         else
-          k_swz_locate< 4 ><<< sms * 16, 64, 0, s >>>( g, u, C, K, counter, T );
-        k_swz_centroid< 3 ><<< sms * 16, 64, 0, s >>>( g, u, C, K, counter );
+          k_swz_locate< 4 ><<< sms * locateBlocks, 64, 0, s >>>( g, u, C, K, counter, T );
+        k_swz_centroid< 3 ><<< sms * otherBlocks, 64, 0, s >>>( g, u, C, K, counter );
         if( lanes == 8 )
           k_swz_normal< 8 ><<< sms * 8, 64, 0, s >>>( g, u, C, K, state, capacity, T );
         else
-          k_swz_normal< 4 ><<< sms * 16, 32, 0, s >>>( g, u, C, K, state, capacity, T );
+          k_swz_normal< 4 ><<< sms * otherBlocks, 32, 0, s >>>( g, u, C, K, state, capacity, T );
         k_swz_finish< 3 ><<< sms * 8, 64, 0, s >>>( g, u, C, state, capacity, hs, maxIterations );
       }
     }

@@ -82,6 +82,10 @@ struct vofx_ctx
   void *diagScratch = nullptr;     // block partials + results of vofx_diagnostics
   void *rootTasks = nullptr;        // coop::RootTask per mixed cell: brackets found by k_youngs_coop3, roots by k_locate_root3
   int fluxLanes = 8;               // lanes per mixed cell of the 3D flux kernel; measured at 512^3: 0.36 ms (8) vs 0.51 ms (4)
+  int fluxBlocksPerSM = 8, updateBlocksPerSM = 8;
+  int youngsBlocksPerSM = 40;      // 64-thread blocks of the plane-constant kernel per SM (grid-stride over the band); measured at
+                                   // 512^3 (ms): 10 0.322, 16 0.312, 20 0.300, 30 0.271, 40 0.266, 60 0.266, 120 0.268 - 10 blocks are
+                                   // resident, a grid of 16 left the second wave 40 % empty
   int lanesPerCell = 4;            // measured on B200 at 512^3: 0.47 ms (4 lanes per cell) vs 0.64 ms (8)
   void *clipTable = nullptr;        // coop::ClipCase[ 256 ] by inner mask, then [ 6561 ] by ( outer / inner / on the plane ) pattern
   StepState *state = nullptr;
@@ -296,7 +300,7 @@ namespace
     {
       // 3D height functions ride in the same kernel (Young's normal -> HF normal -> one plane-constant solve)
       const bool hf3 = ( kind == VOFX_RECON_HF );
-      launch::youngs_coop3( ctx->lanesPerCell, blocks, ctx->stream, g, u, ctx->mixedList, ctx->state, ctx->capacity, hs, ctx->sweepTable, ctx->serialCells, ctx->rootTasks, hf3 ? 1 : 0 );
+      launch::youngs_coop3( ctx->lanesPerCell, ctx->numSMs * ctx->youngsBlocksPerSM / 2, ctx->stream, g, u, ctx->mixedList, ctx->state, ctx->capacity, hs, ctx->sweepTable, ctx->serialCells, ctx->rootTasks, hf3 ? 1 : 0 );
       int rc3 = checkLaunch( ctx, hf3 ? "k_hf_coop" : "k_youngs" );
       if( rc3 )
         return rc3;
@@ -367,7 +371,7 @@ namespace
       launch::flux2( blocks, ctx->stream, g, ctx->velDev, hs, flags, ctx->mixedList, ctx->state, ctx->capacity, ctx->records, timeOverride, dtOverride );
       return checkLaunch( ctx, "k_flux" );
     }
-    launch::flux_cell3( ctx->fluxLanes, ctx->numSMs * 8, ctx->stream, g, ctx->velDev, ctx->velHost, hs, flags, ctx->mixedList, ctx->state, ctx->capacity, ctx->records, ctx->tasks, ctx->taskCapacity,
+    launch::flux_cell3( ctx->fluxLanes, ctx->numSMs * ctx->fluxBlocksPerSM, ctx->stream, g, ctx->velDev, ctx->velHost, hs, flags, ctx->mixedList, ctx->state, ctx->capacity, ctx->records, ctx->tasks, ctx->taskCapacity,
                         ctx->clipTable, timeOverride, dtOverride );
     ctx->launches++;     // k_flux_clip_serial3 rides along (a handful of clips per step)
     return checkLaunch( ctx, "k_flux" );
@@ -376,7 +380,7 @@ namespace
   int launchUpdate ( vofx_ctx *ctx, const unsigned char *flags, double *target, bool accumulate )
   {
     const Grid &g = ctx->grid;
-    const int blocks = ctx->numSMs * 8;
+    const int blocks = ctx->numSMs * ctx->updateBlocksPerSM;
     profBegin( ctx );
     const bool track = accumulate && ctx->trackChanges && ctx->changedIdx;
     launch::update( g.dim, blocks, ctx->stream, g, flags, ctx->mixedList, ctx->slot, ctx->state, ctx->capacity, ctx->records, target, accumulate ? 1 : 0,
@@ -614,6 +618,12 @@ extern "C"
       cudaMemcpy( ctx->sweepTable, table.data(), table.size(), cudaMemcpyHostToDevice );
       if( const char *env = std::getenv( "VOFX_FLUX_LANES" ) )
         ctx->fluxLanes = ( std::atoi( env ) == 4 ) ? 4 : 8;
+      if( const char *env = std::getenv( "VOFX_FLUX_BLOCKS_PER_SM" ) )
+        ctx->fluxBlocksPerSM = ( std::atoi( env ) >= 1 ) ? std::atoi( env ) : 8;
+      if( const char *env = std::getenv( "VOFX_UPDATE_BLOCKS_PER_SM" ) )
+        ctx->updateBlocksPerSM = ( std::atoi( env ) >= 1 ) ? std::atoi( env ) : 8;
+      if( const char *env = std::getenv( "VOFX_YOUNGS_BLOCKS_PER_SM" ) )
+        ctx->youngsBlocksPerSM = ( std::atoi( env ) >= 2 ) ? std::atoi( env ) : 40;
       if( const char *env = std::getenv( "VOFX_LANES_PER_CELL" ) )
         ctx->lanesPerCell = ( std::atoi( env ) == 8 ) ? 8 : 4;
     }
