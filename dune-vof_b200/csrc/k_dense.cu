@@ -54,6 +54,8 @@ namespace vofx
       else
         k_curvature_average< 3 ><<< blocks, 128, 0, s >>>( g, flags, mixedList, slot, state, capacity, curv1, ok1, kappa, valid );
     }
+    void cost_order ( int blocks, cudaStream_t s, const int *mixedList, StepState *state, int capacity, const unsigned char *costClass, int *order )
+    { k_cost_order<<< blocks, 256, 0, s >>>( mixedList, state, capacity, costClass, order ); }
     void finalize ( cudaStream_t s, StepState *state, double cfl ) { k_finalize<<< 1, 1, 0, s >>>( state, cfl ); }
     void reset_counters ( cudaStream_t s, StepState *state ) { k_reset_counters<<< 1, 1, 0, s >>>( state ); }
     void axpy ( int blocks, cudaStream_t s, long long n, double *u, double a, const double *x ) { k_axpy<<< blocks, 256, 0, s >>>( n, u, a, x ); }

@@ -9,18 +9,18 @@ namespace vofx
     void youngs3 ( int blocks, cudaStream_t s, Grid g, const double *u, const int *mixedList, const StepState *state, int capacity, double *hs )
     { k_youngs< 3 ><<< blocks, 128, 0, s >>>( g, u, mixedList, state, capacity, hs ); }
     void youngs_coop3 ( int lanes, int blocks, cudaStream_t s, Grid g, const double *u, const int *mixedList, StepState *state, int capacity, double *hs,
-                        const void *sweepTable, int *serialCells, void *rootTasks, int heightFunction )
+                        const void *sweepTable, int *serialCells, void *rootTasks, int heightFunction, const int *order, unsigned char *costClass )
     {
       const coop::SweepTable *T = (const coop::SweepTable *) sweepTable;
       coop::RootTask *R = (coop::RootTask *) rootTasks;
       if( lanes == 4 && !heightFunction )
-        k_youngs_coop3< 4, false ><<< blocks * 2, 64, 0, s >>>( g, u, mixedList, state, capacity, hs, T, serialCells, R );
+        k_youngs_coop3< 4, false ><<< blocks * 2, 64, 0, s >>>( g, u, mixedList, state, capacity, hs, T, serialCells, R, order, costClass );
       else if( lanes == 4 )
-        k_youngs_coop3< 4, true ><<< blocks * 2, 64, 0, s >>>( g, u, mixedList, state, capacity, hs, T, serialCells, R );
+        k_youngs_coop3< 4, true ><<< blocks * 2, 64, 0, s >>>( g, u, mixedList, state, capacity, hs, T, serialCells, R, order, costClass );
       else if( !heightFunction )
-        k_youngs_coop3< 8, false ><<< blocks, 128, 0, s >>>( g, u, mixedList, state, capacity, hs, T, serialCells, R );
+        k_youngs_coop3< 8, false ><<< blocks, 128, 0, s >>>( g, u, mixedList, state, capacity, hs, T, serialCells, R, order, costClass );
       else
-        k_youngs_coop3< 8, true ><<< blocks, 128, 0, s >>>( g, u, mixedList, state, capacity, hs, T, serialCells, R );
+        k_youngs_coop3< 8, true ><<< blocks, 128, 0, s >>>( g, u, mixedList, state, capacity, hs, T, serialCells, R, order, costClass );
     }
     void locate_root3 ( int blocks, cudaStream_t s, const StepState *state, const void *rootTasks, double *hs )
     { k_locate_root3< 3 ><<< blocks, 128, 0, s >>>( state, (const coop::RootTask *) rootTasks, hs ); }

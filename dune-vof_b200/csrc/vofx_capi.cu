@@ -79,6 +79,9 @@ struct vofx_ctx
   int changedCapacity = 0;
   bool trackChanges = false;
   long long lastH2D = 0, lastD2H = 0;   // bytes moved by the last vofx_step_host call
+  unsigned char *costClass = nullptr;   // per cell: how expensive its plane-constant solve was in the previous step (k_cost_order)
+  int *order = nullptr;                 // processing order of the band list for k_youngs_coop3
+  bool costOrder = true;
   void *diagScratch = nullptr;     // block partials + results of vofx_diagnostics
   void *rootTasks = nullptr;        // coop::RootTask per mixed cell: brackets found by k_youngs_coop3, roots by k_locate_root3
   int fluxLanes = 8;               // lanes per mixed cell of the 3D flux kernel; measured at 512^3: 0.36 ms (8) vs 0.51 ms (4)
@@ -300,7 +303,17 @@ namespace
     {
       // 3D height functions ride in the same kernel (Young's normal -> HF normal -> one plane-constant solve)
       const bool hf3 = ( kind == VOFX_RECON_HF );
-      launch::youngs_coop3( ctx->lanesPerCell, ctx->numSMs * ctx->youngsBlocksPerSM / 2, ctx->stream, g, u, ctx->mixedList, ctx->state, ctx->capacity, hs, ctx->sweepTable, ctx->serialCells, ctx->rootTasks, hf3 ? 1 : 0 );
+      const bool ordered = ctx->costOrder && ctx->order && ctx->costClass;
+      if( ordered )
+      {
+        launch::cost_order( ctx->numSMs * 2, ctx->stream, ctx->mixedList, ctx->state, ctx->capacity, ctx->costClass, ctx->order );
+        int rco = checkLaunch( ctx, "k_cost_order" );
+        if( rco )
+          return rco;
+        profBegin( ctx );
+      }
+      launch::youngs_coop3( ctx->lanesPerCell, ctx->numSMs * ctx->youngsBlocksPerSM / 2, ctx->stream, g, u, ctx->mixedList, ctx->state, ctx->capacity, hs, ctx->sweepTable, ctx->serialCells, ctx->rootTasks, hf3 ? 1 : 0,
+                            ordered ? ctx->order : nullptr, ctx->costClass );
       int rc3 = checkLaunch( ctx, hf3 ? "k_hf_coop" : "k_youngs" );
       if( rc3 )
         return rc3;
@@ -593,6 +606,10 @@ extern "C"
       alloc( (void **) &ctx->sweepTable, launch::sweep_table_bytes() );
       alloc( (void **) &ctx->serialCells, sizeof( int ) * (size_t) ctx->capacity );
       alloc( (void **) &ctx->rootTasks, launch::root_task_bytes() * (size_t) ctx->capacity );
+      alloc( (void **) &ctx->costClass, (size_t) g.cells );
+      alloc( (void **) &ctx->order, sizeof( int ) * (size_t) ctx->capacity );
+      if( rc == VOFX_OK && cudaMemset( ctx->costClass, 0, (size_t) g.cells ) != cudaSuccess )
+        rc = fail( VOFX_ERR_CUDA, "cudaMemset of context scratch failed" );
     }
     alloc( (void **) &ctx->curv1, sizeof( double ) * (size_t) ctx->capacity );
     alloc( (void **) &ctx->ok1, (size_t) ctx->capacity );
@@ -618,6 +635,8 @@ extern "C"
       cudaMemcpy( ctx->sweepTable, table.data(), table.size(), cudaMemcpyHostToDevice );
       if( const char *env = std::getenv( "VOFX_FLUX_LANES" ) )
         ctx->fluxLanes = ( std::atoi( env ) == 4 ) ? 4 : 8;
+      if( std::getenv( "VOFX_NO_COST_ORDER" ) )
+        ctx->costOrder = false;
       if( const char *env = std::getenv( "VOFX_FLUX_BLOCKS_PER_SM" ) )
         ctx->fluxBlocksPerSM = ( std::atoi( env ) >= 1 ) ? std::atoi( env ) : 8;
       if( const char *env = std::getenv( "VOFX_UPDATE_BLOCKS_PER_SM" ) )
@@ -652,6 +671,8 @@ extern "C"
     cudaFree( ctx->serialCells );
     cudaFree( ctx->rootTasks );
     cudaFree( ctx->diagScratch );
+    cudaFree( ctx->costClass );
+    cudaFree( ctx->order );
     cudaFree( ctx->swzCells );
     cudaFree( ctx->swzTasks );
     cudaFree( ctx->swzCounter );

@@ -681,7 +681,8 @@ namespace vofx
 #endif
     template< int L >
     VOFX_HD inline bool locate_coop ( const Group &G, LocateScratch &S, const SweepTable &T, const double *lo, const double *h,
-                                      const double *innerNormal, double fraction, double &dist, RootTask *root = nullptr )
+                                      const double *innerNormal, double fraction, double &dist, RootTask *root = nullptr,
+                                      int *cost = nullptr )
     {
       double hi[ 3 ], outerNormal[ 3 ];
       for( int k = 0; k < 3; ++k )
@@ -836,6 +837,9 @@ namespace vofx
         }
       }
       const bool walking = ( C == nullptr );
+      // cost class for the scheduling of the next step: 2 the topology is walked on lane 0, 1 six or seven brackets, 0 otherwise
+      if( cost )
+        *cost = walking ? 2 : ( nU >= 7 ? 1 : 0 );
 #if defined( __CUDA_ARCH__ ) && defined( VOFX_COUNT_WALKS )
       if( G.lane == 0 )
       {
@@ -989,6 +993,8 @@ namespace vofx
         const double hk = dU[ k + 1 ] - dU[ k ];
         Cubic V = { A, Bc, Cc, 0.0 };
         const double Vd_k1 = Vd_k + V( hk );
+        if( cost && !walking && ( fabs( Vd_k1 - givenVolume ) < 1e-14 || Vd_k1 > givenVolume ) && k < 5 )
+          *cost = 0;
         if( fabs( Vd_k1 - givenVolume ) < 1e-14 )
         {
 #if defined( __CUDA_ARCH__ ) && defined( VOFX_COUNT_WALKS )

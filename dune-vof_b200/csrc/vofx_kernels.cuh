@@ -713,7 +713,8 @@ namespace vofx
   __global__ void __launch_bounds__( 16 * L, VOFX_YOUNGS_THREADS_PER_SM / ( 16 * L ) ) k_youngs_coop3 ( Grid g, const double *__restrict__ u, const int *__restrict__ mixedList,
                                                              StepState *state, int capacity, double *__restrict__ hs,
                                                              const coop::SweepTable *__restrict__ table, int *__restrict__ serialCells,
-                                                             coop::RootTask *__restrict__ rootTasks )
+                                                             coop::RootTask *__restrict__ rootTasks, const int *__restrict__ order,
+                                                             unsigned char *__restrict__ costClass )
   {
     constexpr int GROUPS = 16;          // 16 groups per block: 128 threads for L = 8, 64 for L = 4
     __shared__ coop::LocateScratch scratch[ GROUPS ];
@@ -726,7 +727,7 @@ namespace vofx
     coop::LocateScratch &S = scratch[ group ];
     for( int idx = blockIdx.x * GROUPS + group; idx < count; idx += gridDim.x * GROUPS )
     {
-      const int c = mixedList[ idx ];
+      const int c = mixedList[ order ? order[ idx ] : idx ];     // expensive cells first and together (k_cost_order)
       int ijk[ 3 ];
       cell_ijk( g, c, ijk );
       const double colorEn = u[ c ];
@@ -763,9 +764,12 @@ namespace vofx
       double dist = 0.0;
       coop::RootTask root;
       root.pending = 0;
-      const bool located = coop::locate_coop< L >( G, S, *table, lo, g.h, normal, colorEn, dist, &root );
+      int cost = 0;
+      const bool located = coop::locate_coop< L >( G, S, *table, lo, g.h, normal, colorEn, dist, &root, &cost );
       if( lane == 0 )
       {
+        if( costClass )
+          costClass[ c ] = (unsigned char) cost;
         out[ 0 ] = normal[ 0 ];
         out[ 1 ] = normal[ 1 ];
         out[ 2 ] = normal[ 2 ];
@@ -1995,6 +1999,8 @@ namespace vofx
     state->serialCount = 0;
     state->serialLocate = 0;
     state->rootCount = 0;
+    state->slowFront = 0;
+    state->normalBack = 0;
   }
 
   static __global__ void k_reset_counters ( StepState *state )
@@ -2005,7 +2011,58 @@ namespace vofx
     state->serialLocate = 0;
     state->rootCount = 0;
     state->changedCount = 0;
+    state->slowFront = 0;
+    state->normalBack = 0;
     state->dtEst = DBL_MAX;
+  }
+
+  // Processing order of the band for the plane-constant kernel: the cells that were expensive in the previous step (walk on
+  // lane 0 for tied node heights, or all brackets of a nearly full cell; costClass written by k_youngs_coop3) first and
+  // together - eight cells share a warp, and one straggler sets the pace of its warp.  A pure permutation of the band list:
+  // no result depends on it.
+  static __global__ void __launch_bounds__( 256 ) k_cost_order ( const int *__restrict__ mixedList, StepState *state, int capacity,
+                                                                  const unsigned char *__restrict__ costClass, int *__restrict__ order )
+  {
+    __shared__ int warpSlow[ 8 ], warpNormal[ 8 ], baseSlow, baseNormal;
+    const int count = ( state->mixedCount < capacity ) ? state->mixedCount : capacity;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rounded = ( count + 255 ) & ~255;
+    for( int first = blockIdx.x * 256; first < rounded; first += gridDim.x * 256 )
+    {
+      const int idx = first + threadIdx.x;
+      const bool valid = idx < count;
+      const bool slow = valid && costClass[ mixedList[ idx ] ] != 0;
+      const unsigned slowBallot = __ballot_sync( 0xffffffffu, slow );
+      const unsigned normalBallot = __ballot_sync( 0xffffffffu, valid && !slow );
+      if( lane == 0 )
+      {
+        warpSlow[ warp ] = __popc( slowBallot );
+        warpNormal[ warp ] = __popc( normalBallot );
+      }
+      __syncthreads();
+      if( threadIdx.x == 0 )
+      {
+        // one pair of atomics per 256 entries; the warps' shares become exclusive prefixes
+        int nSlow = 0, nNormal = 0;
+        for( int w = 0; w < 8; ++w )
+        {
+          const int a = warpSlow[ w ], b = warpNormal[ w ];
+          warpSlow[ w ] = nSlow;
+          warpNormal[ w ] = nNormal;
+          nSlow += a;
+          nNormal += b;
+        }
+        baseSlow = nSlow ? atomicAdd( &state->slowFront, nSlow ) : 0;
+        baseNormal = nNormal ? atomicAdd( &state->normalBack, nNormal ) : 0;
+      }
+      __syncthreads();
+      const unsigned below = ( 1u << lane ) - 1u;
+      if( slow )
+        order[ baseSlow + warpSlow[ warp ] + __popc( slowBallot & below ) ] = idx;
+      else if( valid )
+        order[ count - 1 - ( baseNormal + warpNormal[ warp ] + __popc( normalBallot & below ) ) ] = idx;
+      __syncthreads();
+    }
   }
 
   // U1 (operator-level API): ColorFunction::axpy, colorfunction.hh:31-37

@@ -56,8 +56,9 @@ namespace vofx
 
     // k_recon3d.cu, k_swartz3d.cu, k_flux3d.cu
     void youngs3 ( int blocks, cudaStream_t s, Grid g, const double *u, const int *mixedList, const StepState *state, int capacity, double *hs );
+    void cost_order ( int blocks, cudaStream_t s, const int *mixedList, StepState *state, int capacity, const unsigned char *costClass, int *order );
     void youngs_coop3 ( int lanes, int blocks, cudaStream_t s, Grid g, const double *u, const int *mixedList, StepState *state, int capacity, double *hs,
-                        const void *sweepTable, int *serialCells, void *rootTasks, int heightFunction );
+                        const void *sweepTable, int *serialCells, void *rootTasks, int heightFunction , const int *order, unsigned char *costClass);
     void locate_root3 ( int blocks, cudaStream_t s, const StepState *state, const void *rootTasks, double *hs );
     size_t root_task_bytes ();
     void locate_serial3 ( cudaStream_t s, Grid g, const double *u, const StepState *state, double *hs, const int *serialCells );

@@ -22,6 +22,8 @@ namespace vofx
     int rootCount;              // mixed cells whose bracket is found and whose root search is left to k_locate_root3
     int changedCount;           // entries of the changed-cell list of the current step (host-buffer variant: sparse write-back)
     int changedCountLast;
+    int slowFront;              // k_cost_order: expensive cells placed from the front of the processing order ...
+    int normalBack;             // ... the others from the back
     int pad;
   };
 
