@@ -23,7 +23,8 @@ def raw(rep):
 
 
 UNITS = {}
-SCALE = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6, "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+SCALE = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6, "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9,
+         "byte/block": 1.0, "Kbyte/block": 1e3}
 
 
 def num(d, k):
@@ -47,7 +48,7 @@ def main():
         top = dict(sorted(stalls.items(), key=lambda kv: -kv[1])[:6])
         rd, wr = num(d, "dram__bytes_read.sum"), num(d, "dram__bytes_write.sum")
         inst = num(d, "smsp__inst_executed.sum")
-        thr = num(d, "smsp__thread_inst_executed.sum")
+        thr_per_inst = num(d, "smsp__thread_inst_executed_per_inst_executed.ratio")
         summary[kernel] = {
             "duration_us": num(d, "gpu__time_duration.sum"),
             "dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes_total": (rd or 0.0) + (wr or 0.0),
@@ -56,7 +57,7 @@ def main():
             "warps_active_pct": num(d, "sm__warps_active.avg.pct_of_peak_sustained_active"),
             "warp_instructions": inst,
             "ipc_active": num(d, "sm__inst_executed.avg.per_cycle_active"),
-            "threads_per_warp_instruction": round(thr / inst, 2) if inst and thr else None,
+            "threads_per_warp_instruction": round(thr_per_inst, 2) if thr_per_inst else None,
             "fp64_pipe_active_pct": num(d, "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
             "stall_cycles_per_issue": top,
         }
