@@ -41,7 +41,13 @@ extern "C" {
  *   VOFX_LANES_PER_CELL = 4 | 8   lanes per mixed cell of the 3D Young's / height-function kernel (default 4)
  *   VOFX_FLUX_LANES     = 8 | 4   lanes per mixed cell of the 3D flux kernel (default 8)
  *   VOFX_SWARTZ_LANES   = 4 | 8   lanes per task of the 3D Swartz kernels (default 4)
- *   VOFX_SWARTZ_MODE    = batched (default) | cell | serial   formulation of the 3D Swartz reconstruction */
+ *   VOFX_SWARTZ_MODE    = batched (default) | cell | serial   formulation of the 3D Swartz reconstruction
+ *   VOFX_YOUNGS_BLOCKS_PER_SM = n   grid of the 3D plane-constant kernel in 64-thread blocks per SM (default 40)
+ *   VOFX_FLUX_BLOCKS_PER_SM, VOFX_UPDATE_BLOCKS_PER_SM = n   grids of the 3D flux / update kernels (default 8)
+ *   VOFX_SWZ_BLOCKS_PER_SM, VOFX_SWZ_OTHER_BLOCKS_PER_SM = n   grids of the batched Swartz kernels (default 80 / 48)
+ *   VOFX_NO_COST_ORDER  = 1   process the band in list order instead of last step's expensive cells first
+ *   VOFX_NO_GRAPH       = 1   vofx_mesh_run issues its kernels one by one instead of replaying a CUDA graph
+ * None of them changes a result. */
 
 enum vofx_status
 {
