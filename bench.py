@@ -35,6 +35,7 @@ CPU_SAMPLE_N = int(os.environ.get("VOFX_BENCH_CPU_N", "128"))  # the reference n
 EPS, CFL = 1e-6, 0.5
 SURVEY_BYTES_PER_CELL_STEP = 17      # read u (8) + write u' (8) + write flag (1)
 FLAG_KERNEL_BYTES_PER_CELL = 9       # what the dense kernel itself must move: read u (8) + write flag (1)
+WORKLOAD_NAME = "3D sphere (R=0.15) in LeVeque deformation field, Young's reconstruction, eps 1e-6, cfl 0.5 (configs[2])"
 
 
 def measured_peaks():
@@ -101,30 +102,73 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def cpu_reference_run(passes, warm, n_side=CPU_SAMPLE_N):
-    """the reference's own CPU implementation (oracle/_ref = /root/reference's templates, 1 thread: the reference has no
-    threading and MPI is absent), or the plain-C port when the prebuilt harness is absent.  Returns (value, info)."""
+def _mem_available_gb():
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable:"):
+                return int(line.split()[1]) / 1e6
+    except Exception:
+        pass
+    return 0.0
+
+
+def cpu_reference_run(passes, warm, sizes=(96, CPU_SAMPLE_N)):
+    """The reference's own CPU implementation (oracle/_ref = /root/reference's templates, 1 thread: the reference has no
+    threading and MPI is absent), or the plain-C port when the prebuilt harness is absent, on the bench problem.
+
+    The reference stores >= 624 B/cell of stencil entities (24.7 GB at 256^3), so 512^3 does not fit a host.  It is
+    therefore timed at TWO sample sizes of the same problem and every phase (flag / reconstruct / evolve / axpy) is
+    fitted as  seconds = a * cells + b * mixed cells;  `value` is the fit evaluated on the bench grid (N_SIDE^3 cells and
+    the mixed-cell count of that grid, scaled from the larger sample by the surface law (N_SIDE / n)^2), i.e. the
+    reference on the bench's own config.  The raw samples are reported next to it.  Returns (value, info)."""
     from oracle import oraclelib as O
     from oracle import reflib as R
-    n = (n_side,) * 3
+    import numpy as np
     if R.available():
-        kind, grid, mod = "reference", R.RefGrid(n), R
+        kind, Grid, mod = "reference", R.RefGrid, R
     else:
-        kind, grid, mod = "port", O.OracleGrid(n), O
-    u = grid.init(mod.PROB_LEVEQUE)
-    t = dt = 0.0
-    if warm > 0:
-        u, t, dt, _, _ = grid.run(mod.RECON_YOUNGS, mod.PROB_LEVEQUE, EPS, CFL, warm, u, t, dt)
-    t0 = time.perf_counter()
-    u, t, dt, phases, mixed = grid.run(mod.RECON_YOUNGS, mod.PROB_LEVEQUE, EPS, CFL, passes, u, t, dt)
-    wall = time.perf_counter() - t0
-    cells = n_side ** 3
-    value = cells * passes / wall
+        kind, Grid, mod = "port", O.OracleGrid, O
+    samples = []
+    t_begin = time.perf_counter()
+    for n_side in sizes:
+        grid = Grid((n_side,) * 3)
+        u = grid.init(mod.PROB_LEVEQUE)
+        t = dt = 0.0
+        if warm > 0:
+            u, t, dt, _, _ = grid.run(mod.RECON_YOUNGS, mod.PROB_LEVEQUE, EPS, CFL, warm, u, t, dt)
+        t0 = time.perf_counter()
+        u, t, dt, phases, mixed = grid.run(mod.RECON_YOUNGS, mod.PROB_LEVEQUE, EPS, CFL, passes, u, t, dt)
+        wall = time.perf_counter() - t0
+        samples.append({"n": n_side, "cells": n_side ** 3, "passes": passes, "seconds": wall,
+                        "cell_steps_per_s": n_side ** 3 * passes / wall, "mixed_cells_per_step": mixed / max(passes, 1),
+                        "phase_seconds": {"flag": phases[0], "reconstruct": phases[1], "evolve": phases[2], "axpy": phases[3]}})
+        grid.close()
+        del grid, u
+    lo, hi = samples[0], samples[-1]
+    target_cells = N_SIDE ** 3
+    target_mixed = hi["mixed_cells_per_step"] * (N_SIDE / hi["n"]) ** 2
+    fit = {}
+    step_seconds = 0.0
+    if len(samples) >= 2 and lo["n"] != hi["n"]:
+        A = np.array([[lo["cells"], lo["mixed_cells_per_step"]], [hi["cells"], hi["mixed_cells_per_step"]]], dtype=float)
+        for name in ("flag", "reconstruct", "evolve", "axpy"):
+            b = np.array([lo["phase_seconds"][name] / lo["passes"], hi["phase_seconds"][name] / hi["passes"]])
+            per_cell, per_mixed = np.linalg.solve(A, b)
+            per_cell, per_mixed = max(per_cell, 0.0), max(per_mixed, 0.0)
+            fit[name] = {"ns_per_cell": per_cell * 1e9, "us_per_mixed_cell": per_mixed * 1e6}
+            step_seconds += per_cell * target_cells + per_mixed * target_mixed
+        other = [(smp["seconds"] - sum(smp["phase_seconds"].values())) / smp["passes"] / smp["cells"] for smp in samples]
+        step_seconds += max(other[-1], 0.0) * target_cells
+    else:
+        step_seconds = hi["seconds"] / hi["passes"] * target_cells / hi["cells"]
+    value = target_cells / step_seconds
     info = {"value": value, "unit": "cell-steps/s", "cores": 1, "kind": kind,
-            "sample": f"{n_side}^3 grid of the same problem (sphere in LeVeque field, Young's), {passes} loop passes after "
-                      f"{warm} warm-up passes; the reference stores >= 624 B/cell of stencil entities, so 512^3 does not fit a host",
-            "host_cores_available": os.cpu_count(), "seconds": wall, "mixed_cells_per_step": mixed / max(passes, 1),
-            "phase_seconds": {"flag": phases[0], "reconstruct": phases[1], "evolve": phases[2], "axpy": phases[3]}}
+            "sample": f"{kind} timed at " + " and ".join(f"{smp['n']}^3" for smp in samples) + f" ({passes} loop passes after {warm} warm-up "
+                      f"passes each, sphere in LeVeque field, Young's); per-phase fit seconds = a*cells + b*mixed evaluated at "
+                      f"{N_SIDE}^3 cells / {target_mixed:.0f} mixed cells (the reference needs >= 624 B/cell: {N_SIDE}^3 does not fit a host)",
+            "host_cores_available": os.cpu_count(), "seconds": time.perf_counter() - t_begin,
+            "equivalent_seconds_per_step_on_bench_grid": step_seconds, "bench_grid_mixed_cells_assumed": target_mixed,
+            "fit": fit, "samples": samples}
     return value, info
 
 
@@ -132,17 +176,33 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    steps = min(args.steps, 40)
-    warm = max(1, min(args.warmup, 5))
-    value, info = cpu_reference_run(steps, warm)
+    steps = min(args.steps, 6)
+    warm = 1
+    sizes = (128, 256) if _mem_available_gb() > 48 else (96, CPU_SAMPLE_N)
+    value, info = cpu_reference_run(steps, warm, sizes)
+    # cross-check on the exact bench grid with the plain-C port (it needs 50 B/cell): measured, not fitted
+    port = None
+    if N_SIDE <= 512 and _mem_available_gb() > 24 and not args.no_port_check:
+        try:
+            from oracle import oraclelib as O
+            og = O.OracleGrid((N_SIDE,) * 3)
+            u = og.init(O.PROB_LEVEQUE)
+            u, t, dt, _, _ = og.run(O.RECON_YOUNGS, O.PROB_LEVEQUE, EPS, CFL, 1, u)
+            t0 = time.perf_counter()
+            u, t, dt, ph, mixed = og.run(O.RECON_YOUNGS, O.PROB_LEVEQUE, EPS, CFL, 2, u, t, dt)
+            wall = time.perf_counter() - t0
+            port = {"kind": "port", "grid": [N_SIDE] * 3, "passes": 2, "seconds": wall, "cell_steps_per_s": N_SIDE ** 3 * 2 / wall,
+                    "mixed_cells_per_step": mixed / 2, "cores": 1}
+        except Exception as exc:
+            port = {"error": repr(exc)}
+    info["port_on_bench_grid"] = port
     line = {
         "impl": "reference",
         "metric": "VoF cell-steps/sec (reconstruct+advect)", "value": value, "unit": "cell-steps/s",
-        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": 1e3 * info["seconds"] / steps,
+        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": 1e3 * info["equivalent_seconds_per_step_on_bench_grid"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "3D sphere in LeVeque deformation field, Young's reconstruction, eps 1e-6, cfl 0.5 "
-                               f"(configs[2]); CPU sample on {CPU_SAMPLE_N}^3 per step",
-                   "grid": [CPU_SAMPLE_N] * 3},
+        "config": {"workload": WORKLOAD_NAME, "grid": [N_SIDE] * 3,
+                   "cpu_sample": info["sample"]},
         "cpu_baseline": info,
         "e2e": {"value": value, "unit": "cell-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -159,6 +219,8 @@ def main():
     ap.add_argument("--impl", default="vofx", choices=["vofx", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-port-check", action="store_true", help="reference arm: skip the plain-C port on the exact bench grid")
+    ap.add_argument("--dense-flags", action="store_true", help="flag every cell every step instead of incremental flagging")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -202,8 +264,9 @@ def main():
     K = max(1, args.steps)
     n_global = (N_SIDE, N_SIDE, N_SIDE * world)
     h = (1.0 / N_SIDE,) * 3
+    incremental = not args.dense_flags
     slab = SlabAlgorithm(n_global, rank, world, CFL, EPS, ops.RECON_YOUNGS, h=h, device=local_rank,
-                         overlap=os.environ.get("VOFX_NO_OVERLAP", "0") != "1")
+                         overlap=os.environ.get("VOFX_NO_OVERLAP", "0") != "1", incremental=incremental)
     grid = slab.grid
     grid.set_velocity_builtin(ops.PROB_LEVEQUE)
     grid.use_current_stream()
@@ -321,6 +384,7 @@ def main():
         host_u.copy_(owned.reshape(-1))
         grid.use_current_stream()
         vlib.check(L.vofx_track_changes(grid._ctx, 1))
+        vlib.check(L.vofx_set_incremental_flagging(grid._ctx, 0))   # the host owns the colour function here: dense flags every pass
         KE = max(1, args.e2e_steps)
         nchg = C.c_int64(0)
 
@@ -345,39 +409,63 @@ def main():
                       "vofx_changed_fetch writes the changed (cell, value) pairs back into the host slab; d2h bytes estimated "
                       "from rank 0's count"}
 
-    if rank != 0:
+    def teardown():
+        # regular interpreter exit (no os._exit): the driver's exit hook records the libraries this process mapped
+        nonlocal slab
+        torch.cuda.synchronize()
+        for obj in (slab, slab.alg):
+            if hasattr(obj, "_graph"):
+                del obj._graph
+        torch.cuda.synchronize()
+        slab.grid.close()
         if world > 1:
             dist.barrier()
-        sys.stdout.flush()
-        sys.stderr.flush()
-        os._exit(0)      # no teardown of captured graphs / NCCL communicators: nothing left to do
+            dist.destroy_process_group()
+
+    if rank != 0:
+        teardown()
+        return 0
 
     peak, peak_src = measured_peaks()
-    flag = kernels.get("k_flag_compact")
-    roofline = None
-    if flag:
-        achieved = FLAG_KERNEL_BYTES_PER_CELL * cells_per_gpu / (flag["avg_ms"] * 1e-3) / 1e9
-        # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel at this size
-        traffic = None
-        try:
-            summary = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_summary.json")))
-            if N_SIDE == 512:
-                traffic = summary["k_flag_rows"]["dram_bytes_total"]
-        except Exception:
-            traffic = None
-        roofline = {"bound": "hbm", "kernel": "k_flag_rows (profiled as k_flag_compact)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": traffic, "traffic_source": "profiles/r1_ncu_summary.json (ncu --set full, per launch)",
-                    "algorithmic_bytes_per_launch": FLAG_KERNEL_BYTES_PER_CELL * cells_per_gpu, "peak_source": peak_src,
-                    "algorithmic_bytes_per_cell": FLAG_KERNEL_BYTES_PER_CELL,
-                    "kernel_avg_ms": flag["avg_ms"], "kernel_share_of_step": flag["share"],
-                    "note": "dense pass reads u (8 B) and writes the flag (1 B); the u' write of SURVEY 8(d)'s 17 B/cell-step "
-                            "is elided by the in-place band update (k_update)",
-                    "whole_step_equivalent_frac_at_17B": (value / world) * SURVEY_BYTES_PER_CELL_STEP / 1e9 / peak}
+    cs_per_gpu = value / world
+    achieved = cs_per_gpu * SURVEY_BYTES_PER_CELL_STEP / 1e9
+    step_ms = ms / K
+    sub = {}
+    for nm, k in kernels.items():
+        sub[nm] = {"ms_per_step": k["avg_ms"] * k["launches_per_step"], "launches_per_step": k["launches_per_step"], "share_of_profiled_step": k["share"]}
+    dense = kernels.get("k_flag_compact")
+    if dense:
+        dense_ms = dense["avg_ms"] * dense["launches_per_step"]
+        sub["k_flag_compact"].update({"bound": "hbm", "algorithmic_bytes_per_cell": FLAG_KERNEL_BYTES_PER_CELL,
+                                      "note": "dense flag kernel (k_flag_rows); with incremental flagging it only runs on the halo layers"})
+        if not incremental and world == 1:
+            sub["k_flag_compact"]["achieved_gbs"] = FLAG_KERNEL_BYTES_PER_CELL * cells_per_gpu / (dense_ms * 1e-3) / 1e9
+            sub["k_flag_compact"]["frac_of_peak"] = sub["k_flag_compact"]["achieved_gbs"] / peak
+    # fp64-pipe utilisation of the band kernels: from the committed ncu captures of this workload (not measured in this run)
+    try:
+        summary = json.load(open(os.path.join(ROOT, "profiles", "r2_ncu_summary.json")))
+        for nm, key in (("k_youngs", "k_youngs_coop3"), ("k_flux", "k_flux_cell3")):
+            if nm in sub and key in summary and "fp64_pipe_pct" in summary[key]:
+                sub[nm]["bound"] = "fp64 latency"
+                sub[nm]["fp64_pipe_frac"] = summary[key]["fp64_pipe_pct"] / 100.0
+                sub[nm]["fp64_pipe_source"] = "profiles/r2_ncu_summary.json (static: ncu --set full capture of this workload)"
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "whole step (SURVEY.md 8(d): cell-steps/s x 17 B against the measured HBM peak)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "traffic_note": "not captured in this run; per-kernel dram bytes of the ncu captures are under profiles/",
+                "algorithmic_bytes_per_cell_step": SURVEY_BYTES_PER_CELL_STEP,
+                "algorithmic_bytes_per_step_per_gpu": SURVEY_BYTES_PER_CELL_STEP * cells_per_gpu,
+                "peak_source": peak_src, "ms_per_step": step_ms,
+                "note": "the step moves far fewer bytes than 17 B/cell: the u' write is an in-place band update and, with incremental "
+                        "flagging, the dense u read / flag write shrinks to the band's neighbourhood; what bounds the step is the fp64 "
+                        "latency of the band kernels (sub-entries)",
+                "kernels": sub}
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         try:
-            _, cpu_baseline = cpu_reference_run(passes=12, warm=2)
+            _, cpu_baseline = cpu_reference_run(passes=4, warm=1)
         except Exception as exc:   # the checker must never take the bench down
             cpu_baseline = {"value": None, "error": repr(exc)}
 
@@ -385,8 +473,9 @@ def main():
         "metric": "VoF cell-steps/sec (reconstruct+advect)", "value": value, "unit": "cell-steps/s",
         "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "3D sphere (R=0.15) in LeVeque deformation field, Young's reconstruction, eps 1e-6, cfl 0.5 (configs[2])",
+        "config": {"workload": WORKLOAD_NAME,
                    "grid": list(n_global), "cells_per_gpu": cells_per_gpu, "decomposition": f"z-slabs x{world}",
+                   "flagging": "incremental (dense first pass, then re-flag of the band's two-step neighbourhood)" if incremental else "dense every step",
                    "l2": "inputs larger than L2 (colour function 1.07 GB per GPU vs 126 MB L2)",
                    "mixed_cells_last_step_rank0": state.mixed_cells, "time": state.time, "dt": state.dt},
         "clocks": sampler.report(),
@@ -397,11 +486,8 @@ def main():
         "cpu_baseline": cpu_baseline,
     }
     emit(json.dumps(line))
-    if world > 1:
-        dist.barrier()
-    sys.stdout.flush()
-    sys.stderr.flush()
-    os._exit(0)
+    teardown()
+    return 0
 
 
 if __name__ == "__main__":

@@ -31,12 +31,20 @@ namespace vofx
     }
     void update ( int dim, int blocks, cudaStream_t s, Grid g, const unsigned char *flags, const int *mixedList, const int *slot, const StepState *state,
                   int capacity, const FluxRecord *records, double *target, int accumulate, StepState *stateRW, int *changedIdx, double *changedVal,
-                  int changedCapacity )
+                  int changedCapacity, int *prevList )
     {
       if( dim == 2 )
-        k_update< 2 ><<< blocks, 128, 0, s >>>( g, flags, mixedList, slot, state, capacity, records, target, accumulate, stateRW, changedIdx, changedVal, changedCapacity );
+        k_update< 2 ><<< blocks, 128, 0, s >>>( g, flags, mixedList, slot, state, capacity, records, target, accumulate, stateRW, changedIdx, changedVal, changedCapacity, prevList );
       else
-        k_update< 3 ><<< blocks, 128, 0, s >>>( g, flags, mixedList, slot, state, capacity, records, target, accumulate, stateRW, changedIdx, changedVal, changedCapacity );
+        k_update< 3 ><<< blocks, 128, 0, s >>>( g, flags, mixedList, slot, state, capacity, records, target, accumulate, stateRW, changedIdx, changedVal, changedCapacity, prevList );
+    }
+    void reflag ( int dim, int blocks, cudaStream_t s, Grid g, const double *u, double eps, unsigned char *flags, const int *prevList, int *mixedList,
+                  int *slot, int *stamp, int capacity, StepState *state, int layer0, int layer1 )
+    {
+      if( dim == 2 )
+        k_reflag< 2 ><<< blocks, 256, 0, s >>>( g, u, eps, flags, prevList, mixedList, slot, stamp, capacity, state, layer0, layer1 );
+      else
+        k_reflag< 3 ><<< blocks, 256, 0, s >>>( g, u, eps, flags, prevList, mixedList, slot, stamp, capacity, state, layer0, layer1 );
     }
     void curvature_local ( int dim, int blocks, cudaStream_t s, Grid g, const double *u, const double *hs, const int *mixedList, const StepState *state,
                            int capacity, double *curv1, unsigned char *ok1 )

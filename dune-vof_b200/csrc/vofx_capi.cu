@@ -79,6 +79,12 @@ struct vofx_ctx
   int changedCapacity = 0;
   bool trackChanges = false;
   long long lastH2D = 0, lastD2H = 0;   // bytes moved by the last vofx_step_host call
+  // incremental flagging (vofx_set_incremental_flagging): band list of the previous pass, per-cell pass stamps, and the
+  // arrays the last finished pass ran on (the flags / list are only reusable for exactly those)
+  int *prevList = nullptr, *stamp = nullptr;
+  bool incremental = false;
+  const double *primedU = nullptr;
+  const unsigned char *primedFlags = nullptr;
   unsigned char *costClass = nullptr;   // per cell: how expensive its plane-constant solve was in the previous step (k_cost_order)
   int *order = nullptr;                 // processing order of the band list for k_youngs_coop3
   bool costOrder = true;
@@ -89,6 +95,7 @@ struct vofx_ctx
   int youngsBlocksPerSM = 40;      // 64-thread blocks of the plane-constant kernel per SM (grid-stride over the band); measured at
                                    // 512^3 (ms): 10 0.322, 16 0.312, 20 0.300, 30 0.271, 40 0.266, 60 0.266, 120 0.268 - 10 blocks are
                                    // resident, a grid of 16 left the second wave 40 % empty
+  int swartzLanes = 4, swartzMode = 0;   // VOFX_SWARTZ_LANES / VOFX_SWARTZ_MODE (0 batched, 1 cell, 2 serial), read at creation
   int lanesPerCell = 4;            // measured on B200 at 512^3: 0.47 ms (4 lanes per cell) vs 0.64 ms (8)
   void *clipTable = nullptr;        // coop::ClipCase[ 256 ] by inner mask, then [ 6561 ] by ( outer / inner / on the plane ) pattern
   StepState *state = nullptr;
@@ -267,8 +274,60 @@ namespace
     return checkLaunch( ctx, "k_flag_compact" );
   }
 
+  bool capturing ( const vofx_ctx *ctx )
+  {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if( cudaStreamIsCapturing( ctx->stream, &st ) != cudaSuccess )
+    {
+      cudaGetLastError();
+      return false;
+    }
+    return st != cudaStreamCaptureStatusNone;
+  }
+
+  // F1 inside the time loop.  part 0: the layers whose flags depend on owned colour values only (all layers without
+  // halos); part 1: the halo layers and the first / last owned layer (always the dense kernel: their colour values arrive
+  // from another rank).  With incremental flagging part 0 is k_reflag once the previous pass ran on the same arrays.
+  int launchStepFlags ( vofx_ctx *ctx, const vofx_step_params *p, const double *u, unsigned char *flags, int part )
+  {
+    const Grid &g = ctx->grid;
+    const int nLayers = g.ns[ g.dim - 1 ];
+    const bool split = ctx->desc.halo > 0 && flagByRows( ctx, u, flags ) && g.own1 - g.own0 > 2;
+    const int in0 = split ? g.own0 + 1 : 0, in1 = split ? g.own1 - 1 : nLayers;
+    if( ctx->desc.halo > 0 && !split )
+      return part == 1 ? launchFlag( ctx, u, p->eps, flags, true ) : VOFX_OK;     // thin slab: one dense pass after the halos arrived
+    if( part == 1 )
+    {
+      if( !split )
+        return VOFX_OK;
+      int rc = launchFlag( ctx, u, p->eps, flags, true, 0, in0 );
+      return rc ? rc : launchFlag( ctx, u, p->eps, flags, true, in1, nLayers );
+    }
+    const bool inc = ctx->incremental && ctx->prevList && ctx->stamp && ctx->primedU == u && ctx->primedFlags == flags;
+    if( !inc )
+      return launchFlag( ctx, u, p->eps, flags, true, in0, in1 );
+    profBegin( ctx );
+    // 25 (3D) / 13 (2D) candidates per cell of the previous band; the grid is sized for the band of a 512^3 sphere and the
+    // kernel strides over larger ones
+    launch::reflag( g.dim, ctx->numSMs * 8, ctx->stream, g, u, p->eps, flags, ctx->prevList, ctx->mixedList, ctx->slot, ctx->stamp, ctx->capacity,
+                    ctx->state, in0, in1 );
+    return checkLaunch( ctx, "k_reflag" );
+  }
+
+  // the pass that was just issued leaves flags / band list / previous-band list valid for ( u, flags )
+  void notePassIssued ( vofx_ctx *ctx, const double *u, const unsigned char *flags )
+  {
+    if( !ctx->incremental || capturing( ctx ) )
+      return;
+    ctx->primedU = u;
+    ctx->primedFlags = flags;
+  }
+
   int launchResetCounters ( vofx_ctx *ctx )
   {
+    // operator-level calls rebuild the band list of the context: the next loop pass must not reuse it
+    ctx->primedU = nullptr;
+    ctx->primedFlags = nullptr;
     profBegin( ctx );
     launch::reset_counters( ctx->stream, ctx->state );
     return checkLaunch( ctx, "k_reset_counters" );
@@ -340,12 +399,10 @@ namespace
         launch::swartz2( ctx->numSMs * 16, ctx->stream, g, u, flags, ctx->mixedList, ctx->state, ctx->capacity, hs, maxIterations );
       else
       {
-        const char *env = std::getenv( "VOFX_SWARTZ_LANES" );
-        const int lanes = ( env && std::atoi( env ) == 8 ) ? 8 : 4;   // measured at 256^3 per step: batched 10.2 ms (4 lanes) / 12.7 ms (8); per-cell kernel 38.6 ms; serial kernel 261 ms
-        const char *mode = std::getenv( "VOFX_SWARTZ_MODE" );
-        if( mode && std::strcmp( mode, "serial" ) == 0 )
+        const int lanes = ctx->swartzLanes;   // measured at 256^3 per step: batched 10.2 ms (4 lanes) / 12.7 ms (8); per-cell kernel 38.6 ms; serial kernel 261 ms
+        if( ctx->swartzMode == 2 )
           launch::swartz3( ctx->numSMs * 16, ctx->stream, g, u, flags, ctx->mixedList, ctx->state, ctx->capacity, hs, maxIterations );
-        else if( mode && std::strcmp( mode, "cell" ) == 0 )
+        else if( ctx->swartzMode == 1 )
           launch::swartz_coop3( lanes, ctx->numSMs * 16, ctx->stream, g, u, flags, ctx->mixedList, ctx->state, ctx->capacity, hs, maxIterations, ctx->sweepTable );
         else
         {
@@ -397,7 +454,8 @@ namespace
     profBegin( ctx );
     const bool track = accumulate && ctx->trackChanges && ctx->changedIdx;
     launch::update( g.dim, blocks, ctx->stream, g, flags, ctx->mixedList, ctx->slot, ctx->state, ctx->capacity, ctx->records, target, accumulate ? 1 : 0,
-                    ctx->state, track ? ctx->changedIdx : nullptr, track ? ctx->changedVal : nullptr, ctx->changedCapacity );
+                    ctx->state, track ? ctx->changedIdx : nullptr, track ? ctx->changedVal : nullptr, ctx->changedCapacity,
+                    ( accumulate && ctx->incremental ) ? ctx->prevList : nullptr );
     return checkLaunch( ctx, "k_update" );
   }
 
@@ -623,7 +681,10 @@ extern "C"
     StepState init;
     std::memset( &init, 0, sizeof( init ) );
     init.dtEst = DBL_MAX;
+    init.epoch = 1;               // stamps start at 0 (vofx_set_incremental_flagging)
     cudaMemcpy( ctx->state, &init, sizeof( init ), cudaMemcpyHostToDevice );
+    // consumers index records[] / curv1[] with slot[ cell ]: never with uninitialised bits
+    cudaMemset( ctx->slot, 0, sizeof( int ) * (size_t) g.cells );
     if( ctx->sweepTable )
     {
       std::vector< unsigned char > table( launch::sweep_table_bytes() );
@@ -645,6 +706,10 @@ extern "C"
         ctx->youngsBlocksPerSM = ( std::atoi( env ) >= 2 ) ? std::atoi( env ) : 40;
       if( const char *env = std::getenv( "VOFX_LANES_PER_CELL" ) )
         ctx->lanesPerCell = ( std::atoi( env ) == 8 ) ? 8 : 4;
+      if( const char *env = std::getenv( "VOFX_SWARTZ_LANES" ) )
+        ctx->swartzLanes = ( std::atoi( env ) == 8 ) ? 8 : 4;
+      if( const char *env = std::getenv( "VOFX_SWARTZ_MODE" ) )
+        ctx->swartzMode = std::strcmp( env, "serial" ) == 0 ? 2 : ( std::strcmp( env, "cell" ) == 0 ? 1 : 0 );
     }
     if( ctx->clipTable )
     {
@@ -673,6 +738,8 @@ extern "C"
     cudaFree( ctx->diagScratch );
     cudaFree( ctx->costClass );
     cudaFree( ctx->order );
+    cudaFree( ctx->prevList );
+    cudaFree( ctx->stamp );
     cudaFree( ctx->swzCells );
     cudaFree( ctx->swzTasks );
     cudaFree( ctx->swzCounter );
@@ -939,6 +1006,8 @@ extern "C"
     if( !ctx || !u || !flags )
       return fail( VOFX_ERR_ARGUMENT, "null argument" );
     int rc = setDevice( ctx );
+    if( flags == ctx->primedFlags || u == ctx->primedU )
+      ctx->primedU = nullptr, ctx->primedFlags = nullptr;
     return rc ? rc : launchFlag( ctx, u, eps, flags, false );
   }
 
@@ -1068,13 +1137,40 @@ extern "C"
     int rc = setDevice( ctx );
     if( rc )
       return rc;
-    StepState init;
+    StepState init, old;
+    // the pass counter stamps cells in k_reflag: it must never repeat, so it survives a restart of the loop
+    VOFX_CUDA( cudaMemcpyAsync( &old, ctx->state, sizeof( old ), cudaMemcpyDeviceToHost, ctx->stream ) );
+    VOFX_CUDA( cudaStreamSynchronize( ctx->stream ) );
     std::memset( &init, 0, sizeof( init ) );
     init.time = time;
     init.dt = dt;
     init.dtEst = DBL_MAX;
+    init.epoch = old.epoch + 1;
     VOFX_CUDA( cudaMemcpyAsync( ctx->state, &init, sizeof( init ), cudaMemcpyHostToDevice, ctx->stream ) );
     VOFX_CUDA( cudaStreamSynchronize( ctx->stream ) );
+    ctx->primedU = nullptr;       // the first pass of a loop flags densely
+    ctx->primedFlags = nullptr;
+    return VOFX_OK;
+  }
+
+  int vofx_set_incremental_flagging ( vofx_ctx *ctx, int enable )
+  {
+    if( !ctx )
+      return fail( VOFX_ERR_ARGUMENT, "null context" );
+    int rc = setDevice( ctx );
+    if( rc )
+      return rc;
+    ctx->primedU = nullptr;
+    ctx->primedFlags = nullptr;
+    if( enable && !ctx->stamp )
+    {
+      rc = ensureDevice( ctx->prevList, (size_t) ctx->capacity );
+      rc = rc ? rc : ensureDevice( ctx->stamp, (size_t) ctx->grid.cells );
+      if( rc )
+        return rc;
+      VOFX_CUDA( cudaMemsetAsync( ctx->stamp, 0, sizeof( int ) * (size_t) ctx->grid.cells, ctx->stream ) );
+    }
+    ctx->incremental = enable != 0;
     return VOFX_OK;
   }
 
@@ -1090,29 +1186,23 @@ extern "C"
     rc = rc ? rc : requireVelocity( ctx );
     if( rc )
       return rc;
-    const Grid &g = ctx->grid;
-    const int nLayers = g.ns[ g.dim - 1 ];
-    // layers whose flags depend on halo values: the halos themselves and the first / last owned layer
-    const bool split = ctx->desc.halo > 0 && flagByRows( ctx, u, flags ) && g.own1 - g.own0 > 2;
-    const int in0 = split ? g.own0 + 1 : 0, in1 = split ? g.own1 - 1 : 0;
     if( phase == 0 )
-      return split ? launchFlag( ctx, u, p->eps, flags, true, in0, in1 ) : VOFX_OK;
+      return ctx->desc.halo > 0 ? launchStepFlags( ctx, p, u, flags, 0 ) : VOFX_OK;
     if( phase == 1 )
     {
       // algorithm.hh:75-81: flagOperator, reconstructionOperator, evolutionOperator
-      if( split )
-      {
-        rc = launchFlag( ctx, u, p->eps, flags, true, 0, in0 );
-        rc = rc ? rc : launchFlag( ctx, u, p->eps, flags, true, in1, nLayers );
-      }
-      else
-        rc = launchFlag( ctx, u, p->eps, flags, true );
+      if( ctx->desc.halo == 0 )
+        rc = launchStepFlags( ctx, p, u, flags, 0 );
+      rc = rc ? rc : launchStepFlags( ctx, p, u, flags, 1 );
       rc = rc ? rc : launchReconstruct( ctx, p->reconstruction, u, flags, halfspaces, p->max_iterations );
       if( !rc && p->with_curvature )
         rc = launchCurvature( ctx, u, halfspaces, flags, kappa, nullptr, true );
       return rc ? rc : launchFlux( ctx, halfspaces, flags, nullptr, nullptr );
     }
-    return launchUpdate( ctx, flags, u, true );   // uh.axpy( 1.0, update ), algorithm.hh:83
+    rc = launchUpdate( ctx, flags, u, true );   // uh.axpy( 1.0, update ), algorithm.hh:83
+    if( !rc )
+      notePassIssued( ctx, u, flags );
+    return rc;
   }
 
   int vofx_step_local ( vofx_ctx *ctx, const vofx_step_params *p, double *u, uint8_t *flags, double *halfspaces, double *kappa )
@@ -1122,12 +1212,15 @@ extern "C"
     int rc = setDevice( ctx );
     rc = rc ? rc : requireVelocity( ctx );
     // algorithm.hh:75-83: flagOperator, reconstructionOperator, evolutionOperator, uh.axpy( 1.0, update )
-    rc = rc ? rc : launchFlag( ctx, u, p->eps, flags, true );
+    rc = rc ? rc : launchStepFlags( ctx, p, u, flags, 0 );
+    rc = rc ? rc : launchStepFlags( ctx, p, u, flags, 1 );
     rc = rc ? rc : launchReconstruct( ctx, p->reconstruction, u, flags, halfspaces, p->max_iterations );
     if( !rc && p->with_curvature )
       rc = launchCurvature( ctx, u, halfspaces, flags, kappa, nullptr, true );
     rc = rc ? rc : launchFlux( ctx, halfspaces, flags, nullptr, nullptr );
     rc = rc ? rc : launchUpdate( ctx, flags, u, true );
+    if( !rc )
+      notePassIssued( ctx, u, flags );
     return rc;
   }
 
@@ -1169,6 +1262,27 @@ extern "C"
     if( mixed_cells )
       *mixed_cells = s.mixedCountLast;
     return rc;
+  }
+
+  int vofx_band_list_fetch ( vofx_ctx *ctx, int32_t *cells_host, int64_t capacity, int64_t *n_cells )
+  {
+    if( !ctx || !n_cells || ( capacity > 0 && !cells_host ) )
+      return fail( VOFX_ERR_ARGUMENT, "bad argument" );
+    int rc = setDevice( ctx );
+    if( rc )
+      return rc;
+    StepState s;
+    rc = readState( ctx, s );
+    if( rc )
+      return rc;
+    *n_cells = s.mixedCountLast;
+    const size_t n = (size_t) ( s.mixedCountLast < capacity ? s.mixedCountLast : capacity );
+    if( n > 0 )
+    {
+      VOFX_CUDA( cudaMemcpyAsync( cells_host, ctx->mixedList, n * sizeof( int ), cudaMemcpyDeviceToHost, ctx->stream ) );
+      VOFX_CUDA( cudaStreamSynchronize( ctx->stream ) );
+    }
+    return VOFX_OK;
   }
 
   int vofx_step_counters ( vofx_ctx *ctx, int64_t *out )
@@ -1313,6 +1427,8 @@ extern "C"
     ctx->lastD2H = (long long) sizeof( StepState ) + ( flags ? (long long) N : 0 );
     const bool tracking = ctx->trackChanges;
     ctx->trackChanges = true;
+    ctx->primedU = nullptr;       // the caller's colour function was copied in again: dense flags
+    ctx->primedFlags = nullptr;
     rc = vofx_step( ctx, p, ctx->dU, ctx->dFlags, ctx->dHs, ctx->dKappa );
     ctx->trackChanges = tracking;
     if( rc )
@@ -1428,6 +1544,8 @@ extern "C"
       return rc;
     VOFX_CUDA( cudaMemcpyAsync( ctx->dU, u, (size_t) ctx->grid.cells * sizeof( double ), cudaMemcpyHostToDevice, ctx->stream ) );
     VOFX_CUDA( cudaStreamSynchronize( ctx->stream ) );
+    ctx->primedU = nullptr;
+    ctx->primedFlags = nullptr;
     return VOFX_OK;
   }
 
@@ -1452,6 +1570,9 @@ extern "C"
     int rc = ensureMirrors( ctx );
     if( !rc && p->with_curvature )
       rc = ensureDevice( ctx->dKappa, (size_t) ctx->grid.cells );
+    // the mirror is only written by the loop passes and by vofx_color_upload: flags are maintained incrementally
+    if( !rc && !ctx->incremental )
+      rc = vofx_set_incremental_flagging( ctx, 1 );
     return rc ? rc : vofx_step( ctx, p, ctx->dU, ctx->dFlags, ctx->dHs, ctx->dKappa );
   }
 
@@ -1609,6 +1730,8 @@ extern "C"
       return fail( VOFX_ERR_ARGUMENT, "unknown built-in problem" );
     }
     const int blocks = gridBlocks( ctx, ctx->grid.cells, 128, 16 );
+    if( u == ctx->primedU )
+      ctx->primedU = nullptr, ctx->primedFlags = nullptr;
     profBegin( ctx );
     launch::init( dim, blocks, ctx->stream, ctx->grid, I, u );
     return checkLaunch( ctx, "k_init" );

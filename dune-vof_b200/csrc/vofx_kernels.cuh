@@ -336,10 +336,97 @@ namespace vofx
     }
   }
 
+  // number of entries of the band list; 0 once the list has overflowed: the band kernels, the update and the time
+  // advance of that pass become no-ops and the host sees VOFX_ERR_STATE at its next read of the loop state
   __device__ __forceinline__ int mixed_count ( const StepState *state, int capacity )
   {
     const int n = state->mixedCount;
+    if( state->overflow )
+      return 0;
     return n < capacity ? n : capacity;
+  }
+
+  // ------------------------------------------------------------------------------------------------------------
+  // F1, incremental form for a colour function that only the loop itself changes (resident loop, graph replay).
+  // The update of the previous pass wrote u only at the band cells and their face neighbours; a flag depends on u
+  // of the cell and of its face neighbours (flagging.hh:46-63).  So only cells within two face steps of a cell of
+  // the previous band list can change their flag, and only they can be mixed now: they are re-flagged (each once: the
+  // first lane to stamp a cell with the pass number owns it) and the band list is rebuilt from them.  All other flags
+  // stay what the last dense pass / last re-flag wrote.  Layers outside [ layer0, layer1 ) are left to the dense
+  // kernel (halo layers, whose colour values arrive from another rank).
+  // ------------------------------------------------------------------------------------------------------------
+  template< int DIM >
+  __global__ void __launch_bounds__( 256 ) k_reflag ( Grid g, const double *__restrict__ u, double eps, unsigned char *__restrict__ flags,
+                                                       const int *__restrict__ prevList, int *__restrict__ mixedList, int *__restrict__ slot,
+                                                       int *__restrict__ stamp, int capacity, StepState *state, int layer0, int layer1 )
+  {
+    constexpr int NOFF = ( DIM == 3 ) ? 25 : 13;
+    const int prevCount = ( state->overflowLast || state->overflow ) ? 0 : ( state->mixedCountLast < capacity ? state->mixedCountLast : capacity );
+    const int epoch = state->epoch;
+    const int lane = threadIdx.x & 31;
+    const long long total = (long long) prevCount * NOFF;
+    const long long rounded = ( total + 31 ) & ~31LL;
+    for( long long t = blockIdx.x * (long long) blockDim.x + threadIdx.x; t < rounded; t += (long long) gridDim.x * blockDim.x )
+    {
+      bool mixedHere = false;
+      long long X = 0;
+      if( t < total )
+      {
+        const int idx = int( t / NOFF );
+        const int k = int( t - (long long) idx * NOFF );
+        // k-th offset of the two-step face neighbourhood: 0 the cell, 1..2*DIM one step, then two steps along one axis,
+        // then one step along each of two axes
+        int off[ 3 ] = { 0, 0, 0 };
+        if( k >= 1 && k <= 2 * DIM )
+          off[ ( k - 1 ) >> 1 ] = ( ( k - 1 ) & 1 ) ? 1 : -1;
+        else if( k > 2 * DIM && k <= 4 * DIM )
+          off[ ( k - 2 * DIM - 1 ) >> 1 ] = ( ( k - 2 * DIM - 1 ) & 1 ) ? 2 : -2;
+        else if( k > 4 * DIM )
+        {
+          const int r = k - 4 * DIM - 1;          // 0 .. 4*C(DIM,2)-1
+          const int pair = r >> 2;               // 3D: (0,1), (0,2), (1,2); 2D: (0,1)
+          const int a = ( DIM == 3 && pair == 2 ) ? 1 : 0;
+          const int b = ( DIM == 3 ) ? ( pair == 0 ? 1 : 2 ) : 1;
+          off[ a ] = ( r & 1 ) ? 1 : -1;
+          off[ b ] = ( r & 2 ) ? 1 : -1;
+        }
+        int ijk[ 3 ];
+        cell_ijk( g, prevList[ idx ], ijk );
+        ijk[ 0 ] += off[ 0 ];
+        ijk[ 1 ] += off[ 1 ];
+        ijk[ 2 ] += off[ 2 ];
+        const int la = ijk[ DIM - 1 ];
+        if( la >= layer0 && la < layer1 && cell_exists( g, ijk ) )
+        {
+          X = cell_index( g, ijk );
+          if( atomicExch( stamp + X, epoch ) != epoch )
+          {
+            const unsigned char f = flag_of< DIM >( g, u, eps, u[ X ], ijk );
+            flags[ X ] = f;
+            mixedHere = is_mixed( f ) && la >= g.list0 && la < g.list1;
+          }
+        }
+      }
+      const unsigned ballot = __ballot_sync( 0xffffffffu, mixedHere );
+      if( ballot )
+      {
+        int base = 0;
+        if( lane == 0 )
+          base = atomicAdd( &state->mixedCount, __popc( ballot ) );
+        base = __shfl_sync( 0xffffffffu, base, 0 );
+        if( mixedHere )
+        {
+          const int pos = base + __popc( ballot & ( ( 1u << lane ) - 1 ) );
+          if( pos < capacity )
+          {
+            mixedList[ pos ] = int( X );
+            slot[ X ] = pos;
+          }
+          else
+            state->overflow = 1;
+        }
+      }
+    }
   }
 
   // ------------------------------------------------------------------------------------------------------------
@@ -1836,7 +1923,8 @@ namespace vofx
   __global__ void __launch_bounds__( 128 ) k_update ( Grid g, const unsigned char *__restrict__ flags, const int *__restrict__ mixedList,
                                                        const int *__restrict__ slot, const StepState *state, int capacity,
                                                        const FluxRecord *__restrict__ records, double *__restrict__ target, int accumulate,
-                                                       StepState *stateRW, int *__restrict__ changedIdx, double *__restrict__ changedVal, int changedCapacity )
+                                                       StepState *stateRW, int *__restrict__ changedIdx, double *__restrict__ changedVal, int changedCapacity,
+                                                       int *__restrict__ prevList )
   {
     constexpr int LANES = ( DIM == 3 ) ? 8 : 8;
     constexpr int NFACES = 2 * DIM;
@@ -1848,6 +1936,8 @@ namespace vofx
       if( lane > NFACES )
         continue;
       const long long m = mixedList[ idx ];
+      if( prevList && lane == 0 )
+        prevList[ idx ] = int( m );                // the band of this pass seeds the next pass's incremental flagging (k_reflag)
       int mijk[ 3 ];
       cell_ijk( g, m, mijk );
       int x[ 3 ] = { mijk[ 0 ], mijk[ 1 ], mijk[ 2 ] };
@@ -1986,10 +2076,15 @@ namespace vofx
   // T1: algorithm.hh:85-93
   static __global__ void k_finalize ( StepState *state, double cfl )
   {
-    if( state->dt > 0.0 )
-      state->time += state->dt;
-    state->dt = state->dtEst * cfl;
-    state->dtEstLast = state->dtEst;
+    state->epoch += 1;
+    state->overflowLast = state->overflow;       // sticky (vofx_step_begin clears it): the pass was a no-op, see mixed_count()
+    if( !state->overflow )
+    {
+      if( state->dt > 0.0 )
+        state->time += state->dt;
+      state->dt = state->dtEst * cfl;
+      state->dtEstLast = state->dtEst;
+    }
     state->dtEst = DBL_MAX;
     state->mixedCountLast = state->mixedCount;
     state->mixedCount = 0;
@@ -2005,6 +2100,7 @@ namespace vofx
 
   static __global__ void k_reset_counters ( StepState *state )
   {
+    state->overflow = 0;          // operator-level calls are self-contained: each reports its own overflow
     state->mixedCount = 0;
     state->taskCount = 0;
     state->serialCount = 0;
@@ -2024,7 +2120,7 @@ namespace vofx
                                                                   const unsigned char *__restrict__ costClass, int *__restrict__ order )
   {
     __shared__ int warpSlow[ 8 ], warpNormal[ 8 ], baseSlow, baseNormal;
-    const int count = ( state->mixedCount < capacity ) ? state->mixedCount : capacity;
+    const int count = mixed_count( state, capacity );
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int rounded = ( count + 255 ) & ~255;
     for( int first = blockIdx.x * 256; first < rounded; first += gridDim.x * 256 )

@@ -64,7 +64,7 @@ class SlabAlgorithm:
     of the time-step estimate -> finish."""
 
     def __init__(self, n_global, rank, world, cfl, eps, reconstruction_kind=0, max_iterations=10, origin=None, h=None,
-                 device=None, group=None, with_curvature=False, overlap=True):
+                 device=None, group=None, with_curvature=False, overlap=True, incremental=False):
         import torch
         from . import operators as ops
         self.rank, self.world, self.group = rank, world, group
@@ -78,7 +78,7 @@ class SlabAlgorithm:
         n_local = list(n_global)
         n_local[-1] = n_last
         self.grid = ops.CartesianGrid(n_global, origin=origin, h=h, lo=lo, n_local=n_local, halo=halo, device=device)
-        self.alg = ops.Algorithm(self.grid, cfl, eps, reconstruction_kind, max_iterations, with_curvature)
+        self.alg = ops.Algorithm(self.grid, cfl, eps, reconstruction_kind, max_iterations, with_curvature, incremental)
         self.exchanger = HaloExchanger(n_last, halo, rank, world, group)
         self.layer_cells = self.grid.cells // (n_last + 2 * halo)
         self._dt_est = None

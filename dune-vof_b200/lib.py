@@ -21,8 +21,8 @@ TIME_CONST, TIME_COSPI = 0, 1
 SYMBOLS = [
     "vofx_last_error", "vofx_create", "vofx_destroy", "vofx_set_stream", "vofx_cells", "vofx_velocity_clear",
     "vofx_velocity_set_component", "vofx_velocity_set_factor", "vofx_velocity_set_faces", "vofx_velocity_builtin", "vofx_face_velocity",
-    "vofx_flag", "vofx_reconstruct", "vofx_evolve", "vofx_axpy", "vofx_curvature", "vofx_curvature_swartz", "vofx_curvature_swartz_host", "vofx_step_begin", "vofx_step",
-    "vofx_step_state", "vofx_step_counters", "vofx_step_local", "vofx_step_phase", "vofx_step_finish", "vofx_dt_est_device", "vofx_flag_host",
+    "vofx_flag", "vofx_reconstruct", "vofx_evolve", "vofx_axpy", "vofx_curvature", "vofx_curvature_swartz", "vofx_curvature_swartz_host", "vofx_step_begin", "vofx_set_incremental_flagging", "vofx_step",
+    "vofx_step_state", "vofx_band_list_fetch", "vofx_step_counters", "vofx_step_local", "vofx_step_phase", "vofx_step_finish", "vofx_dt_est_device", "vofx_flag_host",
     "vofx_reconstruct_host", "vofx_evolve_host", "vofx_curvature_host", "vofx_step_host", "vofx_host_transfer_bytes", "vofx_track_changes", "vofx_changed_fetch", "vofx_color_upload",
     "vofx_step_resident", "vofx_color_download", "vofx_diagnostics", "vofx_interface", "vofx_interface_host", "vofx_interface_fetch", "vofx_init",
     "vofx_test_fp64_rate", "vofx_test_locate", "vofx_test_flux", "vofx_test_interface", "vofx_launch_count", "vofx_profile_enable",
@@ -56,7 +56,7 @@ class VofxError(RuntimeError):
 
 
 def sources():
-    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))] + \
+    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".h"))] + \
            [os.path.join(ROOT, "include", "vofx.h")]
 
 
@@ -105,6 +105,7 @@ def load():
     L.vofx_axpy.argtypes = [vp, dp, C.c_double, dp]
     L.vofx_curvature.argtypes = [vp, dp, dp, bp, dp, bp]
     L.vofx_step_begin.argtypes = [vp, C.c_double, C.c_double]
+    L.vofx_set_incremental_flagging.argtypes = [vp, C.c_int]
     L.vofx_step.argtypes = [vp, C.POINTER(StepParams), dp, bp, dp, dp]
     L.vofx_step_local.argtypes = [vp, C.POINTER(StepParams), dp, bp, dp, dp]
     L.vofx_step_phase.argtypes = [vp, C.POINTER(StepParams), dp, bp, dp, dp, C.c_int]
@@ -113,6 +114,7 @@ def load():
     L.vofx_dt_est_device.restype = C.c_void_p
     L.vofx_step_state.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     L.vofx_step_counters.argtypes = [vp, C.POINTER(C.c_int64)]
+    L.vofx_band_list_fetch.argtypes = [vp, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
     L.vofx_flag_host.argtypes = [vp, dp, C.c_double, bp]
     L.vofx_reconstruct_host.argtypes = [vp, C.c_int, dp, bp, dp, C.c_int]
     L.vofx_evolve_host.argtypes = [vp, dp, bp, C.c_double, C.c_double, dp, C.POINTER(C.c_double)]

@@ -292,8 +292,13 @@ class Algorithm:
     loop pass, fully on the device (time and dt live there); `__call__(uh, start, end)` replays Algorithm::operator()."""
 
     def __init__(self, grid: CartesianGrid, cfl: float, eps: float, reconstruction_kind=RECON_HF, max_iterations=10,
-                 with_curvature=False):
+                 with_curvature=False, incremental=False):
+        """incremental: the caller promises that between two passes only the passes themselves (and a halo exchange)
+        change the colour function, so flags are maintained from the previous band instead of a dense pass per step
+        (vofx_set_incremental_flagging, include/vofx.h)"""
         self.grid = grid
+        if incremental:
+            check(grid._L.vofx_set_incremental_flagging(grid._ctx, 1))
         self.params = StepParams(int(reconstruction_kind), int(max_iterations), float(eps), float(cfl), 1 if with_curvature else 0)
         self.flags = grid.empty("flags")
         self.reconstructions = grid.empty("reconstructions")
@@ -308,6 +313,17 @@ class Algorithm:
         g = self.grid
         kap = C.c_void_p(self.curvature.data_ptr()) if self.curvature is not None else C.c_void_p(0)
         check(g._L.vofx_step(g._ctx, C.byref(self.params), g.pc(uh), g.pf(self.flags), g.ph(self.reconstructions), kap))
+
+    def band_list(self):
+        """storage indices of the mixed cells of the last finished pass (numpy int32, no defined order)"""
+        import numpy as np
+        g = self.grid
+        n = C.c_int64(0)
+        check(g._L.vofx_band_list_fetch(g._ctx, None, 0, C.byref(n)))
+        out = np.empty(n.value, dtype=np.int32)
+        if n.value:
+            check(g._L.vofx_band_list_fetch(g._ctx, C.c_void_p(out.ctypes.data), n.value, C.byref(n)))
+        return out
 
     def state(self) -> StepResult:
         g = self.grid

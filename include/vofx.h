@@ -160,6 +160,15 @@ typedef struct
 } vofx_step_params;
 
 int vofx_step_begin ( vofx_ctx *ctx, double time, double dt );
+/* Incremental flagging for loops on a colour function that ONLY the loop passes of this context change between two
+ * passes (plus the halo layers, refilled by the caller's exchange): flags can then only change within two face steps
+ * of the previous pass's mixed cells (flagging.hh:46-63 reads a cell and its face neighbours; the update writes the
+ * mixed cells and their face neighbours), so the dense pass over all cells is replaced by a re-flag of that
+ * neighbourhood.  The first pass after vofx_step_begin / vofx_color_upload / an operator-level call, or on other
+ * arrays than the previous pass, is dense.  Flags and band list are identical to the dense pass's (as sets; the band
+ * list has no defined order in either).  vofx_step_resident enables it by itself; vofx_step_host never uses it.
+ * Costs one int per cell of device memory. */
+int vofx_set_incremental_flagging ( vofx_ctx *ctx, int enable );
 /* one loop pass: flag -> reconstruct -> evolve -> u += update -> time += dt -> dt = cfl*dtEst.
  * flags / halfspaces / kappa are outputs (kappa may be NULL unless with_curvature). */
 int vofx_step ( vofx_ctx *ctx, const vofx_step_params *params, double *u, uint8_t *flags, double *halfspaces, double *kappa );
@@ -234,6 +243,10 @@ int vofx_test_fp64_rate ( double *rates );
 int vofx_test_locate ( int dim, int64_t count, const double *lo, const double *h, const double *normal, const double *fraction, double *halfspaces );
 int vofx_test_flux ( int dim, int64_t count, const double *lo, const double *h, const int32_t *face, const double *v, const double *halfspaces, double *flux );
 int vofx_test_interface ( int dim, int64_t count, const double *lo, const double *h, const double *halfspaces, int32_t *nverts, double *centroid, double *measure );
+
+/* the band list of the last finished loop pass (storage indices of the mixed cells the pass reconstructed, in no defined
+ * order): at most `capacity` entries are copied to cells_host, *n_cells receives the length of the list; synchronises */
+int vofx_band_list_fetch ( vofx_ctx *ctx, int32_t *cells_host, int64_t capacity, int64_t *n_cells );
 
 /* work counters of the step in flight (between vofx_step_phase( 1 ) and vofx_step_finish; synchronises): out[0] cells in the
  * band list, out[1] face clips left to the serial kernel (a node of the swept box on the plane), out[2] cells whose
