@@ -31,20 +31,30 @@ namespace vofx
     }
     void update ( int dim, int blocks, cudaStream_t s, Grid g, const unsigned char *flags, const int *mixedList, const int *slot, const StepState *state,
                   int capacity, const FluxRecord *records, double *target, int accumulate, StepState *stateRW, int *changedIdx, double *changedVal,
-                  int changedCapacity, int *prevList )
+                  int changedCapacity, unsigned char *marks, int segsPerRow )
     {
       if( dim == 2 )
-        k_update< 2 ><<< blocks, 128, 0, s >>>( g, flags, mixedList, slot, state, capacity, records, target, accumulate, stateRW, changedIdx, changedVal, changedCapacity, prevList );
+        k_update< 2 ><<< blocks, 128, 0, s >>>( g, flags, mixedList, slot, state, capacity, records, target, accumulate, stateRW, changedIdx, changedVal, changedCapacity, marks, segsPerRow );
       else
-        k_update< 3 ><<< blocks, 128, 0, s >>>( g, flags, mixedList, slot, state, capacity, records, target, accumulate, stateRW, changedIdx, changedVal, changedCapacity, prevList );
+        k_update< 3 ><<< blocks, 128, 0, s >>>( g, flags, mixedList, slot, state, capacity, records, target, accumulate, stateRW, changedIdx, changedVal, changedCapacity, marks, segsPerRow );
     }
-    void reflag ( int dim, int blocks, cudaStream_t s, Grid g, const double *u, double eps, unsigned char *flags, const int *prevList, int *mixedList,
-                  int *slot, int *stamp, int capacity, StepState *state, int layer0, int layer1 )
+    void reflag ( int dim, int blocks, cudaStream_t s, Grid g, const double *u, double eps, unsigned char *flags, int *mixedList, int *slot, int capacity,
+                  StepState *state, unsigned char *marks, int *segList, int segsPerRow, long long nSegments, int layer0, int layer1 )
     {
+      const long long chunks = ( nSegments + 15 ) / 16;
+      long long scanBlocks = ( chunks + 255 ) / 256;
+      if( scanBlocks > blocks )
+        scanBlocks = blocks;
       if( dim == 2 )
-        k_reflag< 2 ><<< blocks, 256, 0, s >>>( g, u, eps, flags, prevList, mixedList, slot, stamp, capacity, state, layer0, layer1 );
+      {
+        k_scan_marks< 2 ><<< (int) scanBlocks, 256, 0, s >>>( g, marks, segsPerRow, nSegments, layer0, layer1, segList, state );
+        k_flag_segments< 2 ><<< blocks, 256, 0, s >>>( g, u, eps, flags, mixedList, slot, capacity, state, segList, segsPerRow );
+      }
       else
-        k_reflag< 3 ><<< blocks, 256, 0, s >>>( g, u, eps, flags, prevList, mixedList, slot, stamp, capacity, state, layer0, layer1 );
+      {
+        k_scan_marks< 3 ><<< (int) scanBlocks, 256, 0, s >>>( g, marks, segsPerRow, nSegments, layer0, layer1, segList, state );
+        k_flag_segments< 3 ><<< blocks, 256, 0, s >>>( g, u, eps, flags, mixedList, slot, capacity, state, segList, segsPerRow );
+      }
     }
     void curvature_local ( int dim, int blocks, cudaStream_t s, Grid g, const double *u, const double *hs, const int *mixedList, const StepState *state,
                            int capacity, double *curv1, unsigned char *ok1 )

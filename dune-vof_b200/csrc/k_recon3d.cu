@@ -22,8 +22,8 @@ namespace vofx
       else
         k_youngs_coop3< 8, true ><<< blocks, 128, 0, s >>>( g, u, mixedList, state, capacity, hs, T, serialCells, R, order, costClass );
     }
-    void locate_root3 ( int blocks, cudaStream_t s, const StepState *state, const void *rootTasks, double *hs )
-    { k_locate_root3< 3 ><<< blocks, 128, 0, s >>>( state, (const coop::RootTask *) rootTasks, hs ); }
+    void locate_root3 ( int blocks, cudaStream_t s, StepState *state, int capacity, const void *rootTasks, double *hs )
+    { k_locate_root3< 3 ><<< blocks, 128, 0, s >>>( state, capacity, (const coop::RootTask *) rootTasks, hs ); }
     size_t root_task_bytes () { return sizeof( coop::RootTask ); }
     void locate_serial3 ( cudaStream_t s, Grid g, const double *u, const StepState *state, double *hs, const int *serialCells )
     { k_locate_serial3< 3 ><<< 148, 64, 0, s >>>( g, u, state, hs, serialCells ); }

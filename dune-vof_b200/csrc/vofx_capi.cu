@@ -79,9 +79,12 @@ struct vofx_ctx
   int changedCapacity = 0;
   bool trackChanges = false;
   long long lastH2D = 0, lastD2H = 0;   // bytes moved by the last vofx_step_host call
-  // incremental flagging (vofx_set_incremental_flagging): band list of the previous pass, per-cell pass stamps, and the
-  // arrays the last finished pass ran on (the flags / list are only reusable for exactly those)
-  int *prevList = nullptr, *stamp = nullptr;
+  // incremental flagging (vofx_set_incremental_flagging): one mark per aligned 32-cell row segment, and the arrays the
+  // last finished pass ran on (the flags / band list are only reusable for exactly those)
+  unsigned char *marks = nullptr;
+  int *segList = nullptr;
+  int segsPerRow = 0;
+  long long nSegments = 0;
   bool incremental = false;
   const double *primedU = nullptr;
   const unsigned char *primedFlags = nullptr;
@@ -303,14 +306,14 @@ namespace
       int rc = launchFlag( ctx, u, p->eps, flags, true, 0, in0 );
       return rc ? rc : launchFlag( ctx, u, p->eps, flags, true, in1, nLayers );
     }
-    const bool inc = ctx->incremental && ctx->prevList && ctx->stamp && ctx->primedU == u && ctx->primedFlags == flags;
+    const bool inc = ctx->incremental && ctx->marks && ctx->primedU == u && ctx->primedFlags == flags;
     if( !inc )
       return launchFlag( ctx, u, p->eps, flags, true, in0, in1 );
     profBegin( ctx );
-    // 25 (3D) / 13 (2D) candidates per cell of the previous band; the grid is sized for the band of a 512^3 sphere and the
-    // kernel strides over larger ones
-    launch::reflag( g.dim, ctx->numSMs * 8, ctx->stream, g, u, p->eps, flags, ctx->prevList, ctx->mixedList, ctx->slot, ctx->stamp, ctx->capacity,
-                    ctx->state, in0, in1 );
+    // the previous pass's update marked the row segments within two face steps of its band
+    launch::reflag( g.dim, ctx->numSMs * 8, ctx->stream, g, u, p->eps, flags, ctx->mixedList, ctx->slot, ctx->capacity, ctx->state, ctx->marks,
+                    ctx->segList, ctx->segsPerRow, ctx->nSegments, in0, in1 );
+    ctx->launches += 1;
     return checkLaunch( ctx, "k_reflag" );
   }
 
@@ -377,7 +380,7 @@ namespace
       if( rc3 )
         return rc3;
       profBegin( ctx );
-      launch::locate_root3( ctx->numSMs * 8, ctx->stream, ctx->state, ctx->rootTasks, hs );
+      launch::locate_root3( ctx->numSMs * 8, ctx->stream, ctx->state, ctx->capacity, ctx->rootTasks, hs );
       rc3 = checkLaunch( ctx, "k_locate_root" );
       if( rc3 )
         return rc3;
@@ -455,7 +458,7 @@ namespace
     const bool track = accumulate && ctx->trackChanges && ctx->changedIdx;
     launch::update( g.dim, blocks, ctx->stream, g, flags, ctx->mixedList, ctx->slot, ctx->state, ctx->capacity, ctx->records, target, accumulate ? 1 : 0,
                     ctx->state, track ? ctx->changedIdx : nullptr, track ? ctx->changedVal : nullptr, ctx->changedCapacity,
-                    ( accumulate && ctx->incremental ) ? ctx->prevList : nullptr );
+                    ( accumulate && ctx->incremental ) ? ctx->marks : nullptr, ctx->segsPerRow );
     return checkLaunch( ctx, "k_update" );
   }
 
@@ -681,7 +684,6 @@ extern "C"
     StepState init;
     std::memset( &init, 0, sizeof( init ) );
     init.dtEst = DBL_MAX;
-    init.epoch = 1;               // stamps start at 0 (vofx_set_incremental_flagging)
     cudaMemcpy( ctx->state, &init, sizeof( init ), cudaMemcpyHostToDevice );
     // consumers index records[] / curv1[] with slot[ cell ]: never with uninitialised bits
     cudaMemset( ctx->slot, 0, sizeof( int ) * (size_t) g.cells );
@@ -738,8 +740,8 @@ extern "C"
     cudaFree( ctx->diagScratch );
     cudaFree( ctx->costClass );
     cudaFree( ctx->order );
-    cudaFree( ctx->prevList );
-    cudaFree( ctx->stamp );
+    cudaFree( ctx->marks );
+    cudaFree( ctx->segList );
     cudaFree( ctx->swzCells );
     cudaFree( ctx->swzTasks );
     cudaFree( ctx->swzCounter );
@@ -1137,15 +1139,11 @@ extern "C"
     int rc = setDevice( ctx );
     if( rc )
       return rc;
-    StepState init, old;
-    // the pass counter stamps cells in k_reflag: it must never repeat, so it survives a restart of the loop
-    VOFX_CUDA( cudaMemcpyAsync( &old, ctx->state, sizeof( old ), cudaMemcpyDeviceToHost, ctx->stream ) );
-    VOFX_CUDA( cudaStreamSynchronize( ctx->stream ) );
+    StepState init;
     std::memset( &init, 0, sizeof( init ) );
     init.time = time;
     init.dt = dt;
     init.dtEst = DBL_MAX;
-    init.epoch = old.epoch + 1;
     VOFX_CUDA( cudaMemcpyAsync( ctx->state, &init, sizeof( init ), cudaMemcpyHostToDevice, ctx->stream ) );
     VOFX_CUDA( cudaStreamSynchronize( ctx->stream ) );
     ctx->primedU = nullptr;       // the first pass of a loop flags densely
@@ -1162,13 +1160,18 @@ extern "C"
       return rc;
     ctx->primedU = nullptr;
     ctx->primedFlags = nullptr;
-    if( enable && !ctx->stamp )
+    if( enable && !ctx->marks )
     {
-      rc = ensureDevice( ctx->prevList, (size_t) ctx->capacity );
-      rc = rc ? rc : ensureDevice( ctx->stamp, (size_t) ctx->grid.cells );
+      const Grid &g = ctx->grid;
+      ctx->segsPerRow = ( g.ns[ 0 ] + 31 ) / 32;
+      ctx->nSegments = (long long) ctx->segsPerRow * g.ns[ 1 ] * g.ns[ 2 ];
+      if( ctx->nSegments >= ( 1LL << 31 ) )
+        return fail( VOFX_ERR_ARGUMENT, "too many row segments" );
+      rc = ensureDevice( ctx->marks, (size_t) ctx->nSegments + 16 );     // k_scan_marks reads 16 marks per thread
+      rc = rc ? rc : ensureDevice( ctx->segList, (size_t) ctx->nSegments );
       if( rc )
         return rc;
-      VOFX_CUDA( cudaMemsetAsync( ctx->stamp, 0, sizeof( int ) * (size_t) ctx->grid.cells, ctx->stream ) );
+      VOFX_CUDA( cudaMemsetAsync( ctx->marks, 0, (size_t) ctx->nSegments + 16, ctx->stream ) );
     }
     ctx->incremental = enable != 0;
     return VOFX_OK;

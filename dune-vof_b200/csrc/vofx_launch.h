@@ -21,9 +21,10 @@ namespace vofx
     void compact_flags ( int dim, int blocks, cudaStream_t s, Grid g, const unsigned char *flags, int *mixedList, int *slot, int capacity, StepState *state );
     void update ( int dim, int blocks, cudaStream_t s, Grid g, const unsigned char *flags, const int *mixedList, const int *slot, const StepState *state,
                   int capacity, const FluxRecord *records, double *target, int accumulate, StepState *stateRW, int *changedIdx, double *changedVal,
-                  int changedCapacity, int *prevList );
-    void reflag ( int dim, int blocks, cudaStream_t s, Grid g, const double *u, double eps, unsigned char *flags, const int *prevList, int *mixedList,
-                  int *slot, int *stamp, int capacity, StepState *state, int layer0, int layer1 );
+                  int changedCapacity, unsigned char *marks, int segsPerRow );
+    // incremental flagging: k_scan_marks + k_flag_segments (the marks are set by the previous pass's k_update)
+    void reflag ( int dim, int blocks, cudaStream_t s, Grid g, const double *u, double eps, unsigned char *flags, int *mixedList, int *slot, int capacity,
+                  StepState *state, unsigned char *marks, int *segList, int segsPerRow, long long nSegments, int layer0, int layer1 );
     void curvature_local ( int dim, int blocks, cudaStream_t s, Grid g, const double *u, const double *hs, const int *mixedList, const StepState *state,
                            int capacity, double *curv1, unsigned char *ok1 );
     void curvature_average ( int dim, int blocks, cudaStream_t s, Grid g, const unsigned char *flags, const int *mixedList, const int *slot,
@@ -61,7 +62,7 @@ namespace vofx
     void cost_order ( int blocks, cudaStream_t s, const int *mixedList, StepState *state, int capacity, const unsigned char *costClass, int *order );
     void youngs_coop3 ( int lanes, int blocks, cudaStream_t s, Grid g, const double *u, const int *mixedList, StepState *state, int capacity, double *hs,
                         const void *sweepTable, int *serialCells, void *rootTasks, int heightFunction , const int *order, unsigned char *costClass);
-    void locate_root3 ( int blocks, cudaStream_t s, const StepState *state, const void *rootTasks, double *hs );
+    void locate_root3 ( int blocks, cudaStream_t s, StepState *state, int capacity, const void *rootTasks, double *hs );
     size_t root_task_bytes ();
     void locate_serial3 ( cudaStream_t s, Grid g, const double *u, const StepState *state, double *hs, const int *serialCells );
     int make_sweep_table ( void *host, size_t bytes );   // returns the number of cases (96) or -1

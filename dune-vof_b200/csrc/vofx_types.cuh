@@ -24,8 +24,8 @@ namespace vofx
     int changedCountLast;
     int slowFront;              // k_cost_order: expensive cells placed from the front of the processing order ...
     int normalBack;             // ... the others from the back
-    int epoch;                  // loop-pass counter (k_finalize), the stamp value of the incremental flag pass (k_reflag)
     int overflowLast;           // the last finished pass overflowed the mixed list: it was a no-op (time and u unchanged)
+    int segCount;               // incremental flagging: marked row segments of this pass (k_scan_marks -> k_flag_segments)
     int pad;
   };
 

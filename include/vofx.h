@@ -167,7 +167,7 @@ int vofx_step_begin ( vofx_ctx *ctx, double time, double dt );
  * neighbourhood.  The first pass after vofx_step_begin / vofx_color_upload / an operator-level call, or on other
  * arrays than the previous pass, is dense.  Flags and band list are identical to the dense pass's (as sets; the band
  * list has no defined order in either).  vofx_step_resident enables it by itself; vofx_step_host never uses it.
- * Costs one int per cell of device memory. */
+ * Costs five bytes per 32 cells of device memory. */
 int vofx_set_incremental_flagging ( vofx_ctx *ctx, int enable );
 /* one loop pass: flag -> reconstruct -> evolve -> u += update -> time += dt -> dt = cfl*dtEst.
  * flags / halfspaces / kappa are outputs (kappa may be NULL unless with_curvature). */

@@ -70,7 +70,7 @@ def test_c2_hf_curvature_against_oracle(vofx, n):
         assert np.array_equal(alg.flags.cpu().numpy(), fo)
         ho = og.reconstruct(O.RECON_HF, u2, fo)
         mixed = (fo == 1) | (fo == 2)
-        assert mixed.sum() > 4 * n
+        assert mixed.sum() > 3 * n
         assert n_mismatch(alg.reconstructions.cpu().numpy()[mixed], ho[mixed]) == 0
         ko, vo = og.curvature(u2, ho, fo)
         kd = alg.curvature.cpu().numpy()
