@@ -1798,6 +1798,27 @@ extern "C"
     return VOFX_OK;
   }
 
+  int vofx_test_arith ( int64_t count, uint64_t seed, int64_t *mismatches )
+  {
+    if( count < 0 || !mismatches )
+      return fail( VOFX_ERR_ARGUMENT, "bad argument" );
+    int rc = requireDevice();
+    if( rc )
+      return rc;
+    DevBuf d;
+    rc = d.alloc( 3 * sizeof( unsigned long long ) );
+    if( rc )
+      return rc;
+    VOFX_CUDA( cudaMemset( d.p, 0, 3 * sizeof( unsigned long long ) ) );
+    launch::test_arith( count, seed, (unsigned long long *) d.p );
+    VOFX_CUDA( cudaGetLastError() );
+    unsigned long long out[ 3 ];
+    VOFX_CUDA( cudaMemcpy( out, d.p, sizeof( out ), cudaMemcpyDeviceToHost ) );
+    for( int k = 0; k < 3; ++k )
+      mismatches[ k ] = (int64_t) out[ k ];
+    return VOFX_OK;
+  }
+
   int vofx_test_locate ( int dim, int64_t count, const double *lo, const double *h, const double *normal, const double *fraction, double *halfspaces )
   {
     if( ( dim != 2 && dim != 3 ) || count < 0 || !lo || !h || !normal || !fraction || !halfspaces )

@@ -786,8 +786,7 @@ namespace vofx
             dv[ c ] = S.P[ c ][ b ] - S.P[ c ][ a ];
           const double norm = norm2( dv[ 0 ], dv[ 1 ] );
           if( norm > 0 )
-            for( int c = 0; c < 3; ++c )
-              dv[ c ] = vdiv( dv[ c ], norm );
+            vdiv3( dv[ 0 ], dv[ 1 ], dv[ 2 ], norm );
           for( int c = 0; c < 3; ++c )
             S.dv[ c ][ e ] = dv[ c ];
         }
@@ -971,8 +970,7 @@ namespace vofx
             const double len = norm2( ex, ey );
             S.bterm[ i ] = ( norm > 0 ) ? vdiv( len * S.fnz[ f ], norm ) : 0.0;
             double onx = ey, ony = -ex;
-            onx = vdiv( onx, len );
-            ony = vdiv( ony, len );
+            vdiv2( onx, ony, len );
             const double cx = ( xi + xj ) * 0.5, cy = ( yi + yj ) * 0.5;
             S.cterm[ i ] = dot2( cx, cy, onx, ony ) * len;
           }
@@ -1052,15 +1050,16 @@ namespace vofx
       const double t12 = M[ 0 ][ 1 ] * M[ 2 ][ 0 ];
       const double t14 = M[ 0 ][ 2 ] * M[ 2 ][ 0 ];
       const double d = ( t4 * M[ 2 ][ 2 ] - t6 * M[ 2 ][ 1 ] - t8 * M[ 2 ][ 2 ] + t10 * M[ 2 ][ 1 ] + t12 * M[ 1 ][ 2 ] - t14 * M[ 1 ][ 1 ] );
-      x[ 0 ] = vdiv( b[ 0 ] * M[ 1 ][ 1 ] * M[ 2 ][ 2 ] - b[ 0 ] * M[ 2 ][ 1 ] * M[ 1 ][ 2 ]
-                     - b[ 1 ] * M[ 0 ][ 1 ] * M[ 2 ][ 2 ] + b[ 1 ] * M[ 2 ][ 1 ] * M[ 0 ][ 2 ]
-                     + b[ 2 ] * M[ 0 ][ 1 ] * M[ 1 ][ 2 ] - b[ 2 ] * M[ 1 ][ 1 ] * M[ 0 ][ 2 ], d );
-      x[ 1 ] = vdiv( M[ 0 ][ 0 ] * b[ 1 ] * M[ 2 ][ 2 ] - M[ 0 ][ 0 ] * b[ 2 ] * M[ 1 ][ 2 ]
-                     - M[ 1 ][ 0 ] * b[ 0 ] * M[ 2 ][ 2 ] + M[ 1 ][ 0 ] * b[ 2 ] * M[ 0 ][ 2 ]
-                     + M[ 2 ][ 0 ] * b[ 0 ] * M[ 1 ][ 2 ] - M[ 2 ][ 0 ] * b[ 1 ] * M[ 0 ][ 2 ], d );
-      x[ 2 ] = vdiv( M[ 0 ][ 0 ] * M[ 1 ][ 1 ] * b[ 2 ] - M[ 0 ][ 0 ] * M[ 2 ][ 1 ] * b[ 1 ]
-                     - M[ 1 ][ 0 ] * M[ 0 ][ 1 ] * b[ 2 ] + M[ 1 ][ 0 ] * M[ 2 ][ 1 ] * b[ 0 ]
-                     + M[ 2 ][ 0 ] * M[ 0 ][ 1 ] * b[ 1 ] - M[ 2 ][ 0 ] * M[ 1 ][ 1 ] * b[ 0 ], d );
+      x[ 0 ] = b[ 0 ] * M[ 1 ][ 1 ] * M[ 2 ][ 2 ] - b[ 0 ] * M[ 2 ][ 1 ] * M[ 1 ][ 2 ]
+               - b[ 1 ] * M[ 0 ][ 1 ] * M[ 2 ][ 2 ] + b[ 1 ] * M[ 2 ][ 1 ] * M[ 0 ][ 2 ]
+               + b[ 2 ] * M[ 0 ][ 1 ] * M[ 1 ][ 2 ] - b[ 2 ] * M[ 1 ][ 1 ] * M[ 0 ][ 2 ];
+      x[ 1 ] = M[ 0 ][ 0 ] * b[ 1 ] * M[ 2 ][ 2 ] - M[ 0 ][ 0 ] * b[ 2 ] * M[ 1 ][ 2 ]
+               - M[ 1 ][ 0 ] * b[ 0 ] * M[ 2 ][ 2 ] + M[ 1 ][ 0 ] * b[ 2 ] * M[ 0 ][ 2 ]
+               + M[ 2 ][ 0 ] * b[ 0 ] * M[ 1 ][ 2 ] - M[ 2 ][ 0 ] * b[ 1 ] * M[ 0 ][ 2 ];
+      x[ 2 ] = M[ 0 ][ 0 ] * M[ 1 ][ 1 ] * b[ 2 ] - M[ 0 ][ 0 ] * M[ 2 ][ 1 ] * b[ 1 ]
+               - M[ 1 ][ 0 ] * M[ 0 ][ 1 ] * b[ 2 ] + M[ 1 ][ 0 ] * M[ 2 ][ 1 ] * b[ 0 ]
+               + M[ 2 ][ 0 ] * M[ 0 ][ 1 ] * b[ 1 ] - M[ 2 ][ 0 ] * M[ 1 ][ 1 ] * b[ 0 ];
+      vdiv3( x[ 0 ], x[ 1 ], x[ 2 ], d );
     }
 
     // ModifiedYoungsReconstruction::applyLocal up to the normal, reconstruction/modifiedyoungs.hh:90-131, for a group of
@@ -1180,9 +1179,8 @@ namespace vofx
         n2 += normal[ k ] * normal[ k ];
       if( n2 < kEps )
         return false;
-      const double nrm = sqrt( n2 );
-      for( int k = 0; k < 3; ++k )
-        normal[ k ] = vdiv( normal[ k ], nrm );
+      const double nrm = vsqrt( n2 );
+      vdiv3( normal[ 0 ], normal[ 1 ], normal[ 2 ], nrm );
       return true;
     }
 

@@ -175,8 +175,7 @@ namespace vofx
     }
     cross3( v1, v2, normal );
     const double s = -1.0 * norm3( normal );
-    for( int k = 0; k < 3; ++k )
-      normal[ k ] = vdiv( normal[ k ], s );
+    vdiv3( normal[ 0 ], normal[ 1 ], normal[ 2 ], s );
   }
 
   // one edge's term of Face::volume: ( edge.center() . edge.outerNormal( faceNormal ) ) * edge.volume()
@@ -190,8 +189,7 @@ namespace vofx
     }
     cross3( v1, fn, en );
     const double nrm = norm3( en );
-    for( int k = 0; k < 3; ++k )
-      en[ k ] = vdiv( en[ k ], nrm );
+    vdiv3( en[ 0 ], en[ 1 ], en[ 2 ], nrm );
     return dot3( center, en ) * norm3( v1 );
   }
 
@@ -620,8 +618,7 @@ namespace vofx
       dv[ c ] = P.x[ b ][ c ] - P.x[ a ][ c ];
     const double norm = norm2( dv[ 0 ], dv[ 1 ] );
     if( norm > 0 )
-      for( int c = 0; c < 3; ++c )
-        dv[ c ] = vdiv( dv[ c ], norm );
+      vdiv3( dv[ 0 ], dv[ 1 ], dv[ 2 ], norm );
   }
 
   // PolygonWithDirections::initialize, 3d/polygonwithdirections.hh:76-174.  ids = node ids sorted by height, ds = sorted heights
@@ -985,8 +982,7 @@ namespace vofx
         const double ex = s.px[ j ] - s.px[ i ], ey = s.py[ j ] - s.py[ i ];
         double onx = ey, ony = -ex;
         const double nrm = norm2( onx, ony );
-        onx = vdiv( onx, nrm );
-        ony = vdiv( ony, nrm );
+        vdiv2( onx, ony, nrm );
         const double cx = ( s.px[ i ] + s.px[ j ] ) * 0.5, cy = ( s.py[ i ] + s.py[ j ] ) * 0.5;
         C += dot2( cx, cy, onx, ony ) * norm2( ex, ey );
       }
@@ -1040,8 +1036,7 @@ namespace vofx
     }
     cross3( a, b, f.unitNormal );
     const double nrm = norm3( f.unitNormal );
-    for( int k = 0; k < 3; ++k )
-      f.unitNormal[ k ] = vdiv( f.unitNormal[ k ], nrm );
+    vdiv3( f.unitNormal[ 0 ], f.unitNormal[ 1 ], f.unitNormal[ 2 ], nrm );
   }
 
   // __impl::intersect( Polyhedron, HyperPlane ), 3d/intersect.hh:274-355 (eps = 1e-12)

@@ -86,6 +86,7 @@ namespace vofx
     void test_locate3 ( int blocks, long long count, const double *lo, const double *h, const double *normal, const double *fraction, double *out );
     void test_flux3 ( int blocks, long long count, const double *lo, const double *h, const int *face, const double *v, const double *hs, double *out );
     float fp64_rate ( int mode, int blocks, int iters, int reps, double *scratch );
+    void test_arith ( long long n, unsigned long long seed, unsigned long long *mismatch );
     void test_interface3 ( int blocks, long long count, const double *lo, const double *h, const double *hs, int *nverts, double *centroid, double *measure );
   } // namespace launch
 } // namespace vofx

@@ -25,7 +25,7 @@ SYMBOLS = [
     "vofx_step_state", "vofx_band_list_fetch", "vofx_step_counters", "vofx_step_local", "vofx_step_phase", "vofx_step_finish", "vofx_dt_est_device", "vofx_flag_host",
     "vofx_reconstruct_host", "vofx_evolve_host", "vofx_curvature_host", "vofx_step_host", "vofx_host_transfer_bytes", "vofx_track_changes", "vofx_changed_fetch", "vofx_color_upload",
     "vofx_step_resident", "vofx_color_download", "vofx_diagnostics", "vofx_interface", "vofx_interface_host", "vofx_interface_fetch", "vofx_init",
-    "vofx_test_fp64_rate", "vofx_test_locate", "vofx_test_flux", "vofx_test_interface", "vofx_launch_count", "vofx_profile_enable",
+    "vofx_test_fp64_rate", "vofx_test_arith", "vofx_test_locate", "vofx_test_flux", "vofx_test_interface", "vofx_launch_count", "vofx_profile_enable",
     "vofx_profile_read",
     "vofx_mesh_create", "vofx_mesh_destroy", "vofx_mesh_set_stream", "vofx_mesh_cells", "vofx_mesh_faces", "vofx_mesh_launch_count",
     "vofx_mesh_flag", "vofx_mesh_reconstruct", "vofx_mesh_evolve", "vofx_mesh_flag_host", "vofx_mesh_reconstruct_host",
@@ -134,6 +134,7 @@ def load():
     L.vofx_init.argtypes = [vp, C.c_int, C.c_double, dp]
     L.vofx_diagnostics.argtypes = [vp, dp, dp, C.POINTER(C.c_double)]
     L.vofx_test_fp64_rate.argtypes = [C.POINTER(C.c_double)]
+    L.vofx_test_arith.argtypes = [C.c_int64, C.c_uint64, C.POINTER(C.c_int64)]
     L.vofx_profile_enable.argtypes = [vp, C.c_int]
     L.vofx_profile_read.argtypes = [vp, C.c_int, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int)]
     L.vofx_test_locate.argtypes = [C.c_int, C.c_int64, dp, dp, dp, dp, dp]

@@ -240,6 +240,9 @@ int vofx_init ( vofx_ctx *ctx, int problem, double time, double *u );
  * each), rates[1] separate multiply and add (the parity contract forbids FMA contraction); the denominators of the
  * band kernels' fp64 rooflines */
 int vofx_test_fp64_rate ( double *rates );
+/* the device's straight-line IEEE division / square root (vofx_math.cuh: vdiv, vdiv3 / vdiv2, vsqrt) against the native
+ * operators on `count` pseudo-random operand sets: mismatches[0] vdiv, [1] vdiv3 / vdiv2, [2] vsqrt -- all must be 0 */
+int vofx_test_arith ( int64_t count, uint64_t seed, int64_t *mismatches );
 int vofx_test_locate ( int dim, int64_t count, const double *lo, const double *h, const double *normal, const double *fraction, double *halfspaces );
 int vofx_test_flux ( int dim, int64_t count, const double *lo, const double *h, const int32_t *face, const double *v, const double *halfspaces, double *flux );
 int vofx_test_interface ( int dim, int64_t count, const double *lo, const double *h, const double *halfspaces, int32_t *nverts, double *centroid, double *measure );

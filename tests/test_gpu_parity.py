@@ -28,6 +28,17 @@ def _p(a):
     return C.c_void_p(a.ctypes.data)
 
 
+def test_division_and_sqrt_fast_paths():
+    """vdiv / vdiv3 / vdiv2 / vsqrt (vofx_math.cuh) are the compiler's own division and square-root fast paths written as
+    straight-line code: they must return the native operators' bits for every operand (2^27 operand sets per seed:
+    random mantissas, exponents up to +-1020, signed zeros, powers of two, exact squares)"""
+    L, vlib = _lib()
+    for seed in (1, 0xDEADBEEF, 2 ** 63 + 12345):
+        bad = (C.c_int64 * 3)()
+        vlib.check(L.vofx_test_arith(1 << 27, seed, bad))
+        assert list(bad) == [0, 0, 0], (seed, list(bad))
+
+
 @pytest.mark.parametrize("dim", [2, 3])
 def test_primitives_against_golden(dim):
     L, vlib = _lib()
