@@ -34,5 +34,25 @@ namespace vofx
     { k_test_flux< 2 ><<< blocks, 64 >>>( count, lo, h, face, v, hs, out ); }
     void test_interface2 ( int blocks, long long count, const double *lo, const double *h, const double *hs, int *nverts, double *centroid, double *measure )
     { k_test_interface< 2 ><<< blocks, 64 >>>( count, lo, h, hs, nverts, centroid, measure ); }
+    // forces the (lazily loaded) kernels of this translation unit into the context: a first launch loads its kernel, which
+    // may wait for the device -- fatal while a kernel of another context spins on a signal (vofx_comm_connect*)
+    template< class K >
+    static void preload_one ( K kernel )
+    {
+      cudaFuncAttributes a;
+      cudaFuncGetAttributes( &a, kernel );
+    }
+    void preload_band2d ()
+    {
+      preload_one( k_youngs< 2 > );
+      preload_one( k_hf< 2 > );
+      preload_one( k_hf_fused< 2 > );
+      preload_one( k_clear_listed );
+      preload_one( k_copy_list );
+      preload_one( k_swartz_curv_local );
+      preload_one( k_swartz_curv_average );
+      preload_one( k_swartz< 2 > );
+      preload_one( k_flux< 2 > );
+    }
   } // namespace launch
 } // namespace vofx

@@ -31,13 +31,29 @@ namespace vofx
     }
     void update ( int dim, int blocks, cudaStream_t s, Grid g, const unsigned char *flags, const int *mixedList, const int *slot, const StepState *state,
                   int capacity, const FluxRecord *records, double *target, int accumulate, StepState *stateRW, int *changedIdx, double *changedVal,
-                  int changedCapacity, unsigned char *marks, int segsPerRow )
+                  int changedCapacity, unsigned char *marks, int segsPerRow, const CommPeers *peers )
     {
-      if( dim == 2 )
-        k_update< 2 ><<< blocks, 128, 0, s >>>( g, flags, mixedList, slot, state, capacity, records, target, accumulate, stateRW, changedIdx, changedVal, changedCapacity, marks, segsPerRow );
+      CommPeers P;
+      if( peers )
+        P = *peers;
       else
-        k_update< 3 ><<< blocks, 128, 0, s >>>( g, flags, mixedList, slot, state, capacity, records, target, accumulate, stateRW, changedIdx, changedVal, changedCapacity, marks, segsPerRow );
+      {
+        P.rank = 0;
+        P.world = 1;
+        P.uLo = P.uHi = nullptr;
+        P.offLo = P.offHi = 0;
+        P.pushLo1 = P.pushHi0 = 0;
+      }
+      if( dim == 2 )
+        k_update< 2 ><<< blocks, 128, 0, s >>>( g, flags, mixedList, slot, state, capacity, records, target, accumulate, stateRW, changedIdx, changedVal, changedCapacity, marks, segsPerRow, P );
+      else
+        k_update< 3 ><<< blocks, 128, 0, s >>>( g, flags, mixedList, slot, state, capacity, records, target, accumulate, stateRW, changedIdx, changedVal, changedCapacity, marks, segsPerRow, P );
     }
+    void comm_wait_halo ( cudaStream_t s, const CommPeers &P, StepState *state ) { k_comm_wait_halo<<< 1, 32, 0, s >>>( P, state ); }
+    void comm_flux_done ( cudaStream_t s, const CommPeers &P, StepState *state ) { k_comm_flux_done<<< 1, 32, 0, s >>>( P, state ); }
+    void finalize_dist ( cudaStream_t s, const CommPeers &P, StepState *state, double cfl ) { k_finalize_dist<<< 1, 32, 0, s >>>( P, state, cfl ); }
+    void halo_push ( int blocks, cudaStream_t s, const CommPeers &P, const double *u, long long layerCells, int own0, int own1 )
+    { k_halo_push<<< blocks, 256, 0, s >>>( P, u, layerCells, own0, own1 ); }
     void reflag ( int dim, int blocks, cudaStream_t s, Grid g, const double *u, double eps, unsigned char *flags, int *mixedList, int *slot, int capacity,
                   StepState *state, unsigned char *marks, int *segList, int segsPerRow, long long nSegments, int layer0, int layer1 )
     {
@@ -87,6 +103,43 @@ namespace vofx
     void test_face_velocity ( cudaStream_t s, Grid g, const Velocity *velocity, double time, long long cell, int face, double *out )
     {
       k_test_face_velocity<<< 1, 1, 0, s >>>( g, velocity, time, cell, face, out );
+    }
+    // forces the (lazily loaded) kernels of this translation unit into the context: a first launch loads its kernel, which
+    // may wait for the device -- fatal while a kernel of another context spins on a signal (vofx_comm_connect*)
+    template< class K >
+    static void preload_one ( K kernel )
+    {
+      cudaFuncAttributes a;
+      cudaFuncGetAttributes( &a, kernel );
+    }
+    void preload_dense ()
+    {
+      preload_one( k_flag_rows< 2 > );
+      preload_one( k_flag_rows< 3 > );
+      preload_one( k_flag_compact< 2 > );
+      preload_one( k_flag_compact< 3 > );
+      preload_one( k_compact_flags< 2 > );
+      preload_one( k_compact_flags< 3 > );
+      preload_one( k_update< 2 > );
+      preload_one( k_update< 3 > );
+      preload_one( k_scan_marks< 2 > );
+      preload_one( k_scan_marks< 3 > );
+      preload_one( k_flag_segments< 2 > );
+      preload_one( k_flag_segments< 3 > );
+      preload_one( k_curvature_local< 2 > );
+      preload_one( k_curvature_local< 3 > );
+      preload_one( k_curvature_average< 2 > );
+      preload_one( k_curvature_average< 3 > );
+      preload_one( k_cost_order );
+      preload_one( k_finalize );
+      preload_one( k_reset_counters );
+      preload_one( k_finalize_dist );
+      preload_one( k_comm_wait_halo );
+      preload_one( k_comm_flux_done );
+      preload_one( k_halo_push );
+      preload_one( k_axpy );
+      preload_one( k_init< 2 > );
+      preload_one( k_init< 3 > );
     }
   } // namespace launch
 } // namespace vofx

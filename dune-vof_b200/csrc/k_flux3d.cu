@@ -25,5 +25,19 @@ namespace vofx
       coop::make_clip_table( (coop::ClipCase *) host );
       coop::make_clip_boundary_table( (coop::ClipCase *) host + 256 );
     }
+    // forces the (lazily loaded) kernels of this translation unit into the context: a first launch loads its kernel, which
+    // may wait for the device -- fatal while a kernel of another context spins on a signal (vofx_comm_connect*)
+    template< class K >
+    static void preload_one ( K kernel )
+    {
+      cudaFuncAttributes a;
+      cudaFuncGetAttributes( &a, kernel );
+    }
+    void preload_flux3d ()
+    {
+      preload_one( k_flux_cell3< 3, 4 > );
+      preload_one( k_flux_cell3< 3, 8 > );
+      preload_one( k_flux_clip_serial3< 3 > );
+    }
   } // namespace launch
 } // namespace vofx

@@ -36,6 +36,23 @@ namespace vofx
     size_t sweep_table_bytes () { return sizeof( coop::SweepTable ); }
     void hf3 ( int blocks, cudaStream_t s, Grid g, const double *u, const int *mixedList, const StepState *state, int capacity, double *hs )
     { k_hf< 3 ><<< blocks, 128, 0, s >>>( g, u, mixedList, state, capacity, hs ); }
+    // forces the (lazily loaded) kernels of this translation unit into the context: a first launch loads its kernel, which
+    // may wait for the device -- fatal while a kernel of another context spins on a signal (vofx_comm_connect*)
+    template< class K >
+    static void preload_one ( K kernel )
+    {
+      cudaFuncAttributes a;
+      cudaFuncGetAttributes( &a, kernel );
+    }
+    void preload_recon3d ()
+    {
+      preload_one( k_youngs_coop3< 4, false > );
+      preload_one( k_youngs_coop3< 4, true > );
+      preload_one( k_youngs_coop3< 8, false > );
+      preload_one( k_youngs_coop3< 8, true > );
+      preload_one( k_locate_root3< 3 > );
+      preload_one( k_locate_serial3< 3 > );
+    }
   } // namespace launch
 } // namespace vofx
 

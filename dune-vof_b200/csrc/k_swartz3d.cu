@@ -47,5 +47,26 @@ namespace vofx
         k_swz_finish< 3 ><<< sms * 8, 64, 0, s >>>( g, u, C, state, capacity, hs, maxIterations );
       }
     }
+    // forces the (lazily loaded) kernels of this translation unit into the context: a first launch loads its kernel, which
+    // may wait for the device -- fatal while a kernel of another context spins on a signal (vofx_comm_connect*)
+    template< class K >
+    static void preload_one ( K kernel )
+    {
+      cudaFuncAttributes a;
+      cudaFuncGetAttributes( &a, kernel );
+    }
+    void preload_swartz3d ()
+    {
+      preload_one( k_swartz< 3 > );
+      preload_one( k_swartz_coop3< 4 > );
+      preload_one( k_swartz_coop3< 8 > );
+      preload_one( k_swz_setup< 3 > );
+      preload_one( k_swz_locate< 4 > );
+      preload_one( k_swz_locate< 8 > );
+      preload_one( k_swz_centroid< 3 > );
+      preload_one( k_swz_normal< 4 > );
+      preload_one( k_swz_normal< 8 > );
+      preload_one( k_swz_finish< 3 > );
+    }
   } // namespace launch
 } // namespace vofx

@@ -88,6 +88,13 @@ struct vofx_ctx
   bool incremental = false;
   const double *primedU = nullptr;
   const unsigned char *primedFlags = nullptr;
+  // distributed step (vofx_comm_*): one cudaMalloc block = resident colour function (incl. halos) + CommSlots, exported
+  // to the other ranks; their blocks mapped here
+  void *window = nullptr;
+  size_t windowBytes = 0, slotsOffset = 0;
+  CommPeers peers;
+  bool commConnected = false;
+  std::vector< void * > ipcMapped;
   unsigned char *costClass = nullptr;   // per cell: how expensive its plane-constant solve was in the previous step (k_cost_order)
   int *order = nullptr;                 // processing order of the band list for k_youngs_coop3
   bool costOrder = true;
@@ -95,7 +102,7 @@ struct vofx_ctx
   void *rootTasks = nullptr;        // coop::RootTask per mixed cell: brackets found by k_youngs_coop3, roots by k_locate_root3
   int fluxLanes = 8;               // lanes per mixed cell of the 3D flux kernel; measured at 512^3: 0.36 ms (8) vs 0.51 ms (4)
   int fluxBlocksPerSM = 8, updateBlocksPerSM = 8;
-  int youngsBlocksPerSM = 40;      // 64-thread blocks of the plane-constant kernel per SM (grid-stride over the band); measured at
+  int youngsBlocksPerSM = 60;      // 64-thread blocks of the plane-constant kernel per SM (grid-stride over the band); measured at
                                    // 512^3 (ms): 10 0.322, 16 0.312, 20 0.300, 30 0.271, 40 0.266, 60 0.266, 120 0.268 - 10 blocks are
                                    // resident, a grid of 16 left the second wave 40 % empty
   int swartzLanes = 4, swartzMode = 0;   // VOFX_SWARTZ_LANES / VOFX_SWARTZ_MODE (0 batched, 1 cell, 2 serial), read at creation
@@ -458,7 +465,8 @@ namespace
     const bool track = accumulate && ctx->trackChanges && ctx->changedIdx;
     launch::update( g.dim, blocks, ctx->stream, g, flags, ctx->mixedList, ctx->slot, ctx->state, ctx->capacity, ctx->records, target, accumulate ? 1 : 0,
                     ctx->state, track ? ctx->changedIdx : nullptr, track ? ctx->changedVal : nullptr, ctx->changedCapacity,
-                    ( accumulate && ctx->incremental ) ? ctx->marks : nullptr, ctx->segsPerRow );
+                    ( accumulate && ctx->incremental ) ? ctx->marks : nullptr, ctx->segsPerRow,
+                    ( accumulate && ctx->commConnected && target == ctx->dU ) ? &ctx->peers : nullptr );
     return checkLaunch( ctx, "k_update" );
   }
 
@@ -507,6 +515,10 @@ namespace
 
   int checkOverflow ( vofx_ctx *ctx, const StepState &s )
   {
+    if( s.commError )
+      return fail( VOFX_ERR_STATE, "distributed step: the wait for " + std::string( ( s.commError & 15 ) == 1 ? "the halo pushes" : ( ( s.commError & 15 ) == 2 ? "the fluxes" : "the time-step estimate" ) )
+                   + " of rank " + std::to_string( ( s.commError >> 4 ) & 15 ) + " in pass " + std::to_string( s.commError >> 8 )
+                   + " timed out (a rank died, or the ranks' call sequences differ)" );
     if( s.overflow )
       return fail( VOFX_ERR_STATE, "mixed-cell list overflow: more than " + std::to_string( ctx->capacity ) + " mixed cells" );
     return VOFX_OK;
@@ -684,6 +696,7 @@ extern "C"
     StepState init;
     std::memset( &init, 0, sizeof( init ) );
     init.dtEst = DBL_MAX;
+    init.epoch = 1;
     cudaMemcpy( ctx->state, &init, sizeof( init ), cudaMemcpyHostToDevice );
     // consumers index records[] / curv1[] with slot[ cell ]: never with uninitialised bits
     cudaMemset( ctx->slot, 0, sizeof( int ) * (size_t) g.cells );
@@ -705,7 +718,7 @@ extern "C"
       if( const char *env = std::getenv( "VOFX_UPDATE_BLOCKS_PER_SM" ) )
         ctx->updateBlocksPerSM = ( std::atoi( env ) >= 1 ) ? std::atoi( env ) : 8;
       if( const char *env = std::getenv( "VOFX_YOUNGS_BLOCKS_PER_SM" ) )
-        ctx->youngsBlocksPerSM = ( std::atoi( env ) >= 2 ) ? std::atoi( env ) : 40;
+        ctx->youngsBlocksPerSM = ( std::atoi( env ) >= 2 ) ? std::atoi( env ) : 60;
       if( const char *env = std::getenv( "VOFX_LANES_PER_CELL" ) )
         ctx->lanesPerCell = ( std::atoi( env ) == 8 ) ? 8 : 4;
       if( const char *env = std::getenv( "VOFX_SWARTZ_LANES" ) )
@@ -764,7 +777,12 @@ extern "C"
     for( double *t : ctx->velTables )
       cudaFree( t );
     cudaFree( ctx->velFaces );
-    cudaFree( ctx->dU );
+    for( void *m : ctx->ipcMapped )
+      cudaIpcCloseMemHandle( m );
+    if( ctx->window )
+      cudaFree( ctx->window );        // the resident colour function lives inside the window
+    else
+      cudaFree( ctx->dU );
     cudaFree( ctx->dHs );
     cudaFree( ctx->dUpd );
     cudaFree( ctx->dKappa );
@@ -1144,7 +1162,10 @@ extern "C"
     init.time = time;
     init.dt = dt;
     init.dtEst = DBL_MAX;
+    init.epoch = 1;
     VOFX_CUDA( cudaMemcpyAsync( ctx->state, &init, sizeof( init ), cudaMemcpyHostToDevice, ctx->stream ) );
+    if( ctx->window )
+      VOFX_CUDA( cudaMemsetAsync( static_cast< char * >( ctx->window ) + ctx->slotsOffset, 0, sizeof( CommSlots ), ctx->stream ) );
     VOFX_CUDA( cudaStreamSynchronize( ctx->stream ) );
     ctx->primedU = nullptr;       // the first pass of a loop flags densely
     ctx->primedFlags = nullptr;
@@ -1577,6 +1598,243 @@ extern "C"
     if( !rc && !ctx->incremental )
       rc = vofx_set_incremental_flagging( ctx, 1 );
     return rc ? rc : vofx_step( ctx, p, ctx->dU, ctx->dFlags, ctx->dHs, ctx->dKappa );
+  }
+
+  // ---- distributed step over peer-mapped memory ------------------------------------------------------------------------------
+
+  static int ensureWindow ( vofx_ctx *ctx )
+  {
+    if( ctx->window )
+      return VOFX_OK;
+    if( ctx->dU )
+      return fail( VOFX_ERR_STATE, "vofx_comm_export must come before the first use of the context-resident colour function" );
+    int rc = setDevice( ctx );
+    if( rc )
+      return rc;
+    const size_t uBytes = (size_t) ctx->grid.cells * sizeof( double );
+    ctx->slotsOffset = ( uBytes + 255 ) & ~size_t( 255 );
+    ctx->windowBytes = ctx->slotsOffset + ( ( sizeof( CommSlots ) + 255 ) & ~size_t( 255 ) );
+    VOFX_CUDA( cudaMalloc( &ctx->window, ctx->windowBytes ) );
+    VOFX_CUDA( cudaMemset( ctx->window, 0, ctx->windowBytes ) );
+    ctx->dU = static_cast< double * >( ctx->window );
+    return VOFX_OK;
+  }
+
+  static int fillPeers ( vofx_ctx *ctx, int rank, int world, const int32_t *layers, void *const *windows )
+  {
+    if( world < 1 || world > kMaxRanks || rank < 0 || rank >= world )
+      return fail( VOFX_ERR_ARGUMENT, "bad rank / world (at most 16 ranks)" );
+    const Grid &g = ctx->grid;
+    const int H = ctx->desc.halo;
+    const int nMine = g.own1 - g.own0;
+    if( layers[ rank ] != nMine )
+      return fail( VOFX_ERR_ARGUMENT, "layers[ rank ] differs from the context's owned layers" );
+    if( world > 1 && H < 1 )
+      return fail( VOFX_ERR_ARGUMENT, "a distributed context needs halo layers" );
+    for( int r = 0; r < world; ++r )
+      if( world > 1 && layers[ r ] < H )
+        return fail( VOFX_ERR_ARGUMENT, "a slab is thinner than the halo" );
+    CommPeers &P = ctx->peers;
+    std::memset( &P, 0, sizeof( P ) );
+    P.rank = rank;
+    P.world = world;
+    const long long layerCells = g.cells / g.ns[ g.dim - 1 ];
+    for( int r = 0; r < world; ++r )
+    {
+      // every context's window has the same layout only up to the colour function's size: the slots sit at its own offset
+      const size_t uBytes = (size_t) layerCells * ( layers[ r ] + 2 * H ) * sizeof( double );
+      const size_t off = ( uBytes + 255 ) & ~size_t( 255 );
+      P.slots[ r ] = reinterpret_cast< CommSlots * >( static_cast< char * >( windows[ r ] ) + off );
+    }
+    if( rank > 0 )
+    {
+      P.uLo = static_cast< double * >( windows[ rank - 1 ] );
+      P.offLo = (long long) layers[ rank - 1 ] * layerCells;
+    }
+    if( rank + 1 < world )
+    {
+      P.uHi = static_cast< double * >( windows[ rank + 1 ] );
+      P.offHi = -(long long) nMine * layerCells;
+    }
+    P.pushLo1 = g.own0 + H;
+    P.pushHi0 = g.own1 - H;
+    ctx->commConnected = world > 1;
+    // everything a pass needs is allocated now: a pass of the distributed run must never block the host (cudaMalloc /
+    // cudaFree may wait for the device, and a kernel of ANOTHER context of this process may be spinning on a signal that
+    // only this context's next launches can send)
+    int rc = ensureMirrors( ctx );
+    rc = rc ? rc : ensureDevice( ctx->dKappa, (size_t) g.cells );
+    rc = rc ? rc : vofx_set_incremental_flagging( ctx, 1 );
+    if( rc )
+      return rc;
+    // ... and every kernel is loaded now (CUDA loads kernels lazily at their first launch, which may wait for the device)
+    launch::preload_dense();
+    launch::preload_band2d();
+    launch::preload_recon3d();
+    launch::preload_flux3d();
+    launch::preload_swartz3d();
+    VOFX_CUDA( cudaGetLastError() );
+    VOFX_CUDA( cudaStreamSynchronize( ctx->stream ) );
+    return VOFX_OK;
+  }
+
+  int vofx_comm_export ( vofx_ctx *ctx, void *handle )
+  {
+    if( !ctx || !handle )
+      return fail( VOFX_ERR_ARGUMENT, "null argument" );
+    int rc = ensureWindow( ctx );
+    if( rc )
+      return rc;
+    static_assert( sizeof( cudaIpcMemHandle_t ) == VOFX_COMM_HANDLE_BYTES, "handle size" );
+    cudaIpcMemHandle_t h;
+    VOFX_CUDA( cudaIpcGetMemHandle( &h, ctx->window ) );
+    std::memcpy( handle, &h, sizeof( h ) );
+    return VOFX_OK;
+  }
+
+  int vofx_comm_connect ( vofx_ctx *ctx, int rank, int world, const int32_t *layers, const void *handles )
+  {
+    if( !ctx || !layers || !handles )
+      return fail( VOFX_ERR_ARGUMENT, "null argument" );
+    int rc = ensureWindow( ctx );
+    if( rc )
+      return rc;
+    if( world < 1 || world > kMaxRanks || rank < 0 || rank >= world )
+      return fail( VOFX_ERR_ARGUMENT, "bad rank / world (at most 16 ranks)" );
+    std::vector< void * > windows( world, nullptr );
+    for( int r = 0; r < world; ++r )
+    {
+      if( r == rank )
+      {
+        windows[ r ] = ctx->window;
+        continue;
+      }
+      cudaIpcMemHandle_t h;
+      std::memcpy( &h, static_cast< const char * >( handles ) + (size_t) r * VOFX_COMM_HANDLE_BYTES, sizeof( h ) );
+      void *p = nullptr;
+      VOFX_CUDA( cudaIpcOpenMemHandle( &p, h, cudaIpcMemLazyEnablePeerAccess ) );
+      ctx->ipcMapped.push_back( p );
+      windows[ r ] = p;
+    }
+    return fillPeers( ctx, rank, world, layers, windows.data() );
+  }
+
+  int vofx_comm_connect_local ( vofx_ctx **contexts, int world )
+  {
+    if( !contexts || world < 1 || world > kMaxRanks )
+      return fail( VOFX_ERR_ARGUMENT, "bad argument (at most 16 contexts)" );
+    std::vector< void * > windows( world, nullptr );
+    std::vector< int32_t > layers( world, 0 );
+    for( int r = 0; r < world; ++r )
+    {
+      if( !contexts[ r ] )
+        return fail( VOFX_ERR_ARGUMENT, "null context" );
+      int rc = ensureWindow( contexts[ r ] );
+      if( rc )
+        return rc;
+      windows[ r ] = contexts[ r ]->window;
+      layers[ r ] = contexts[ r ]->grid.own1 - contexts[ r ]->grid.own0;
+    }
+    for( int r = 0; r < world; ++r )
+    {
+      // contexts on different devices of one process: plain peer access
+      for( int q = 0; q < world; ++q )
+        if( contexts[ q ]->device != contexts[ r ]->device )
+        {
+          cudaSetDevice( contexts[ r ]->device );
+          const cudaError_t e = cudaDeviceEnablePeerAccess( contexts[ q ]->device, 0 );
+          if( e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled )
+            return fail( VOFX_ERR_CUDA, std::string( "cudaDeviceEnablePeerAccess: " ) + cudaGetErrorString( e ) );
+          cudaGetLastError();
+        }
+      int rc = fillPeers( contexts[ r ], r, world, layers.data(), windows.data() );
+      if( rc )
+        return rc;
+    }
+    return VOFX_OK;
+  }
+
+  double *vofx_color_device ( vofx_ctx *ctx )
+  {
+    if( !ctx || ensureMirrors( ctx ) )
+      return nullptr;
+    return ctx->dU;
+  }
+
+  uint8_t *vofx_flags_device ( vofx_ctx *ctx )
+  {
+    if( !ctx || ensureMirrors( ctx ) )
+      return nullptr;
+    return ctx->dFlags;
+  }
+
+  double *vofx_halfspaces_device ( vofx_ctx *ctx )
+  {
+    if( !ctx || ensureMirrors( ctx ) )
+      return nullptr;
+    return ctx->dHs;
+  }
+
+  int vofx_halo_push ( vofx_ctx *ctx )
+  {
+    if( !ctx )
+      return fail( VOFX_ERR_ARGUMENT, "null context" );
+    if( !ctx->commConnected )
+      return VOFX_OK;
+    int rc = setDevice( ctx );
+    if( rc )
+      return rc;
+    const Grid &g = ctx->grid;
+    const long long layerCells = g.cells / g.ns[ g.dim - 1 ];
+    profBegin( ctx );
+    launch::halo_push( ctx->numSMs * 4, ctx->stream, ctx->peers, ctx->dU, layerCells, g.own0, g.own1 );
+    rc = checkLaunch( ctx, "k_halo_push" );
+    if( rc )
+      return rc;
+    VOFX_CUDA( cudaStreamSynchronize( ctx->stream ) );
+    return VOFX_OK;
+  }
+
+  int vofx_step_distributed ( vofx_ctx *ctx, const vofx_step_params *p )
+  {
+    if( !ctx || !p )
+      return fail( VOFX_ERR_ARGUMENT, "null argument" );
+    int rc = ensureMirrors( ctx );
+    if( !rc && p->with_curvature )
+      rc = ensureDevice( ctx->dKappa, (size_t) ctx->grid.cells );
+    if( !rc && !ctx->incremental )
+      rc = vofx_set_incremental_flagging( ctx, 1 );
+    rc = rc ? rc : requireVelocity( ctx );
+    if( rc )
+      return rc;
+    if( !ctx->commConnected )
+      return vofx_step( ctx, p, ctx->dU, ctx->dFlags, ctx->dHs, ctx->dKappa );
+    double *u = ctx->dU;
+    unsigned char *flags = ctx->dFlags;
+    // flags of the layers that depend on owned colour values only, while the neighbours' last pushes are still in flight
+    rc = launchStepFlags( ctx, p, u, flags, 0 );
+    if( rc )
+      return rc;
+    profBegin( ctx );
+    launch::comm_wait_halo( ctx->stream, ctx->peers, ctx->state );
+    rc = checkLaunch( ctx, "k_comm_wait_halo" );
+    rc = rc ? rc : launchStepFlags( ctx, p, u, flags, 1 );
+    rc = rc ? rc : launchReconstruct( ctx, p->reconstruction, u, flags, ctx->dHs, p->max_iterations );
+    if( !rc && p->with_curvature )
+      rc = launchCurvature( ctx, u, ctx->dHs, flags, ctx->dKappa, nullptr, true );
+    rc = rc ? rc : launchFlux( ctx, ctx->dHs, flags, nullptr, nullptr );
+    if( rc )
+      return rc;
+    profBegin( ctx );
+    launch::comm_flux_done( ctx->stream, ctx->peers, ctx->state );
+    rc = checkLaunch( ctx, "k_comm_flux_done" );
+    rc = rc ? rc : launchUpdate( ctx, flags, u, true );
+    if( rc )
+      return rc;
+    notePassIssued( ctx, u, flags );
+    profBegin( ctx );
+    launch::finalize_dist( ctx->stream, ctx->peers, ctx->state, p->cfl );
+    return checkLaunch( ctx, "k_finalize_dist" );
   }
 
   // ---- interface extraction ------------------------------------------------------------------------------------------------

@@ -212,7 +212,7 @@ namespace vofx
         for( int d = 0; d < 3; ++d )
           x3[ k ][ d ] = S.x[ d ][ r ];
       }
-      const double inv = 1.0 / len;
+      const double inv = vdiv( 1.0, (double) len );
       for( int d = 0; d < 3; ++d )
         center[ d ] *= inv;
       outer_normal3( x3[ 0 ], x3[ 1 ], x3[ 2 ], fn );
@@ -275,7 +275,7 @@ namespace vofx
 #pragma unroll 1
       for( int f = 0; f < cs.nFaces; ++f )
         vol += S.term[ f ];
-      return fabs( vol / 3.0 );
+      return fabs( vdiv( vol, 3.0 ) );
     }
 
     // serial path for the rare cases (a node on the plane, irregular mask): rebuild the hexahedron from the scratch
@@ -705,7 +705,7 @@ namespace vofx
       }
       else if( !identity )
       {
-        const double gamma = ( 1 - n[ 2 ] ) / ( n[ 0 ] * n[ 0 ] + n[ 1 ] * n[ 1 ] );
+        const double gamma = vdiv( 1 - n[ 2 ], n[ 0 ] * n[ 0 ] + n[ 1 ] * n[ 1 ] );
         R[ 0 ][ 0 ] = n[ 1 ] * n[ 1 ] * gamma + n[ 2 ];
         R[ 0 ][ 1 ] = -n[ 0 ] * n[ 1 ] * gamma;
         R[ 1 ][ 0 ] = R[ 0 ][ 1 ];
@@ -757,7 +757,7 @@ namespace vofx
       double vol = 0.0;
       for( int f = 0; f < 6; ++f )
         vol += S.term[ f ];
-      const double givenVolume = fraction * fabs( vol / 3.0 );
+      const double givenVolume = fraction * fabs( vdiv( vol, 3.0 ) );
 
       // phase 2: sort the node heights (std::sort = stable insertion sort on 8 elements: rank by (height, id)),
       // direction vectors of all directed edges, face normals of the rotated cell
@@ -1137,7 +1137,7 @@ namespace vofx
             double n2 = 0.0;
             for( int k = 0; k < 3; ++k )
               n2 += d[ k ] * d[ k ];
-            const double weight = 1.0 / n2;
+            const double weight = vdiv( 1.0, n2 );
             for( int k = 0; k < 3; ++k )
               d[ k ] *= weight;
             int c = 0;

@@ -2107,7 +2107,7 @@ namespace vofx
                                                        const int *__restrict__ slot, const StepState *state, int capacity,
                                                        const FluxRecord *__restrict__ records, double *__restrict__ target, int accumulate,
                                                        StepState *stateRW, int *__restrict__ changedIdx, double *__restrict__ changedVal, int changedCapacity,
-                                                       unsigned char *__restrict__ marks, int segsPerRow )
+                                                       unsigned char *__restrict__ marks, int segsPerRow, CommPeers peers )
   {
     constexpr int LANES = ( DIM == 3 ) ? 8 : 8;
     constexpr int NFACES = 2 * DIM;
@@ -2232,6 +2232,12 @@ namespace vofx
       {
         const double value = target[ X ] + 1.0 * acc;   // uh.axpy( 1.0, update ), colorfunction.hh:31-37
         target[ X ] = value;
+        // distributed step: the neighbour ranks' halo copies of this cell are kept up to date by direct stores into their
+        // memory (NVLink peer mapping) -- the colour function only ever changes here, so no halo exchange is needed
+        if( peers.uLo && la < peers.pushLo1 )
+          peers.uLo[ X + peers.offLo ] = value;
+        if( peers.uHi && la >= peers.pushHi0 )
+          peers.uHi[ X + peers.offHi ] = value;
         if( changedIdx )
         {
           // every cell is updated by exactly one lane per step: the list of (cell, new value) pairs is what a host
@@ -2257,8 +2263,106 @@ namespace vofx
   }
 
   // T1: algorithm.hh:85-93
+  __device__ __forceinline__ void finalize_state ( StepState *state, double cfl );
+
+  // ---- signals of the distributed step (one block of 32 threads; thread r talks to rank r) -------------------------------
+  // `what`: 1 halo wait, 2 flux wait, 3 finalize wait (reported with the peer rank and the pass number on a time-out)
+  __device__ __forceinline__ void comm_wait ( StepState *state, volatile int *flag, int atLeast, int what, int peer )
+  {
+    const long long t0 = clock64();
+    while( *flag < atLeast )
+    {
+      if( clock64() - t0 > 20000000000LL )       // ~10 s: a peer died or the call sequences of the ranks differ
+      {
+        state->commError = what | ( peer << 4 ) | ( atLeast << 8 );
+        break;
+      }
+      __nanosleep( 64 );
+    }
+  }
+
+  // before the first read of the colour halos in a pass: the neighbours' updates of the previous pass have landed
+  static __global__ void k_comm_wait_halo ( CommPeers P, StepState *state )
+  {
+    const int r = threadIdx.x;
+    if( r < P.world && ( r == P.rank - 1 || r == P.rank + 1 ) )
+      comm_wait( state, P.slots[ P.rank ]->updateDone + r, state->epoch - 1, 1, r );
+  }
+
+  // after the fluxes: publish my time-step estimate and "fluxes done" to every rank, then wait until the neighbours have
+  // finished theirs (they no longer read the halo copies my update is about to overwrite)
+  static __global__ void k_comm_flux_done ( CommPeers P, StepState *state )
+  {
+    const int r = threadIdx.x;
+    const int e = state->epoch;
+    if( r < P.world )
+    {
+      P.slots[ r ]->dtEst[ e & 1 ][ P.rank ] = state->dtEst;
+      __threadfence_system();
+      *( (volatile int *) ( P.slots[ r ]->fluxDone + P.rank ) ) = e;
+    }
+    if( r < P.world && ( r == P.rank - 1 || r == P.rank + 1 ) )
+      comm_wait( state, P.slots[ P.rank ]->fluxDone + r, e, 2, r );
+  }
+
+  // T1 of the distributed step: tell the neighbours that my update (and its pushes into their halos) is done, take the
+  // MIN of all ranks' time-step estimates (gridView().comm().min, evolution/evolution.hh:75), then k_finalize's work
+  static __global__ void k_finalize_dist ( CommPeers P, StepState *state, double cfl )
+  {
+    const int r = threadIdx.x;
+    const int e = state->epoch;
+    if( r < P.world && ( r == P.rank - 1 || r == P.rank + 1 ) )
+    {
+      __threadfence_system();
+      *( (volatile int *) ( P.slots[ r ]->updateDone + P.rank ) ) = e;
+    }
+    double mine = DBL_MAX;
+    if( r < P.world )
+    {
+      comm_wait( state, P.slots[ P.rank ]->fluxDone + r, e, 3, r );
+      mine = *( (volatile double *) &P.slots[ P.rank ]->dtEst[ e & 1 ][ r ] );
+    }
+#pragma unroll
+    for( int o = 16; o > 0; o >>= 1 )
+    {
+      const double other = __shfl_xor_sync( 0xffffffffu, mine, o );
+      mine = ( other < mine ) ? other : mine;
+    }
+    if( r == 0 )
+    {
+      state->dtEst = mine;
+      finalize_state( state, cfl );
+    }
+  }
+
+  // bulk copy of my boundary layers into the neighbours' halos (start of a loop, after an upload): layers are contiguous
+  static __global__ void __launch_bounds__( 256 ) k_halo_push ( CommPeers P, const double *__restrict__ u, long long layerCells, int own0, int own1 )
+  {
+    const long long nLo = P.uLo ? (long long) ( P.pushLo1 - own0 ) * layerCells : 0;
+    const long long nHi = P.uHi ? (long long) ( own1 - P.pushHi0 ) * layerCells : 0;
+    for( long long t = blockIdx.x * (long long) blockDim.x + threadIdx.x; t < nLo + nHi; t += (long long) gridDim.x * blockDim.x )
+    {
+      if( t < nLo )
+      {
+        const long long X = own0 * layerCells + t;
+        P.uLo[ X + P.offLo ] = u[ X ];
+      }
+      else
+      {
+        const long long X = P.pushHi0 * layerCells + ( t - nLo );
+        P.uHi[ X + P.offHi ] = u[ X ];
+      }
+    }
+  }
+
   static __global__ void k_finalize ( StepState *state, double cfl )
   {
+    finalize_state( state, cfl );
+  }
+
+  __device__ __forceinline__ void finalize_state ( StepState *state, double cfl )
+  {
+    state->epoch += 1;
     state->overflowLast = state->overflow;       // sticky (vofx_step_begin clears it): the pass was a no-op, see mixed_count()
     if( !state->overflow )
     {

@@ -10,6 +10,12 @@ namespace vofx
 {
   namespace launch
   {
+    // every translation unit: load its kernels now (see preload_one in k_dense.cu)
+    void preload_dense ();
+    void preload_band2d ();
+    void preload_recon3d ();
+    void preload_flux3d ();
+    void preload_swartz3d ();
     // k_diag.cu
     size_t diag_scratch_bytes ();
     double *diagnostics ( cudaStream_t s, long long n, const double *u, const double *exact, double volume, void *scratch );
@@ -21,7 +27,12 @@ namespace vofx
     void compact_flags ( int dim, int blocks, cudaStream_t s, Grid g, const unsigned char *flags, int *mixedList, int *slot, int capacity, StepState *state );
     void update ( int dim, int blocks, cudaStream_t s, Grid g, const unsigned char *flags, const int *mixedList, const int *slot, const StepState *state,
                   int capacity, const FluxRecord *records, double *target, int accumulate, StepState *stateRW, int *changedIdx, double *changedVal,
-                  int changedCapacity, unsigned char *marks, int segsPerRow );
+                  int changedCapacity, unsigned char *marks, int segsPerRow, const CommPeers *peers );
+    // distributed step over peer-mapped memory
+    void comm_wait_halo ( cudaStream_t s, const CommPeers &P, StepState *state );
+    void comm_flux_done ( cudaStream_t s, const CommPeers &P, StepState *state );
+    void finalize_dist ( cudaStream_t s, const CommPeers &P, StepState *state, double cfl );
+    void halo_push ( int blocks, cudaStream_t s, const CommPeers &P, const double *u, long long layerCells, int own0, int own1 );
     // incremental flagging: k_scan_marks + k_flag_segments (the marks are set by the previous pass's k_update)
     void reflag ( int dim, int blocks, cudaStream_t s, Grid g, const double *u, double eps, unsigned char *flags, int *mixedList, int *slot, int capacity,
                   StepState *state, unsigned char *marks, int *segList, int segsPerRow, long long nSegments, int layer0, int layer1 );

@@ -26,7 +26,31 @@ namespace vofx
     int normalBack;             // ... the others from the back
     int overflowLast;           // the last finished pass overflowed the mixed list: it was a no-op (time and u unchanged)
     int segCount;               // incremental flagging: marked row segments of this pass (k_scan_marks -> k_flag_segments)
+    int epoch;                  // number of the pass in flight (1, 2, ...): the stamp of the peer-memory signals of the distributed step
+    int commError;              // a wait on a peer's signal timed out
     int pad;
+  };
+
+  // ---- distributed step over peer-mapped memory (vofx_comm_*, include/vofx.h) ----------------------------------------
+  constexpr int kMaxRanks = 16;
+
+  // written by the OTHER ranks (and by the rank itself for its own entry) with plain stores over NVLink
+  struct CommSlots
+  {
+    int fluxDone[ kMaxRanks ];          // [ r ]: last pass whose fluxes rank r has finished (it no longer reads its colour halos)
+    int updateDone[ kMaxRanks ];        // [ r ]: last pass whose update rank r has finished (its pushes into my halos have landed)
+    double dtEst[ 2 ][ kMaxRanks ];     // [ pass & 1 ][ r ]: rank r's local time-step estimate of that pass
+  };
+
+  struct CommPeers
+  {
+    int rank, world;
+    CommSlots *slots[ kMaxRanks ];      // every rank's slots as mapped into this process
+    // my owned layers [ own0, pushLo1 ) are the upper halo of the lower neighbour: its cell = my storage index + offLo;
+    // my owned layers [ pushHi0, own1 ) are the lower halo of the upper neighbour
+    double *uLo, *uHi;
+    long long offLo, offHi;
+    int pushLo1, pushHi0;
   };
 
   // per mixed cell: what it adds to its own update and to each face neighbour's update (Appendix C of SURVEY.md)

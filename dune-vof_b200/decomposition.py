@@ -53,40 +53,106 @@ class HaloExchanger:
 
 
 class _DevicePtr:
-    """exposes a raw device address as a 1-element float64 CUDA array (for torch.as_tensor)"""
+    """exposes a raw device address as a CUDA array of `count` float64 / uint8 entries (for torch.as_tensor)"""
 
-    def __init__(self, ptr: int):
-        self.__cuda_array_interface__ = {"shape": (1,), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+    def __init__(self, ptr: int, count: int = 1, typestr: str = "<f8"):
+        self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def split_by_cost(costs, world: int, min_layers: int = 1):
+    """contiguous split of len(costs) layers into `world` slabs with (nearly) equal summed cost: returns the list of layer
+    counts.  costs[k] = estimated work of layer k (e.g. ns_per_cell * cells + us_per_mixed_cell * mixed cells of the layer);
+    every slab gets at least `min_layers` layers (the halo width).  Replaces gridPtr->loadBalance() (example/vof.cc:63)."""
+    n = len(costs)
+    if world * min_layers > n:
+        raise ValueError("more slabs x minimal thickness than layers")
+    total = float(sum(costs))
+    counts, start, acc = [], 0, 0.0
+    for r in range(world):
+        remaining_slabs = world - r - 1
+        if remaining_slabs == 0:
+            counts.append(n - start)
+            break
+        target = total * (r + 1) / world
+        end = start + min_layers
+        acc_end = acc + float(sum(costs[start:end]))
+        # extend while the next layer brings the running sum closer to the target, leaving room for the other slabs
+        while end < n - remaining_slabs * min_layers and abs(acc_end + costs[end] - target) <= abs(acc_end - target):
+            acc_end += costs[end]
+            end += 1
+        counts.append(end - start)
+        start, acc = end, acc_end
+    return counts
 
 
 class SlabAlgorithm:
-    """Algorithm (operators.Algorithm) on the slab of this rank: exchange colour halo -> local step -> MIN all-reduce
-    of the time-step estimate -> finish."""
+    """Algorithm (operators.Algorithm) on the slab of this rank.
+
+    transport "peer" (default for world > 1): the colour function lives in the context's window, the update kernel stores
+    every new boundary value straight into the neighbours' halos over NVLink and the time-step MIN travels through the same
+    peer-mapped windows (vofx_comm_*, include/vofx.h) -- torch.distributed only carries the 64-byte IPC handles at start-up
+    and the two barriers of begin().  transport "nccl": colour halo exchange (grouped send/recv) and MIN all-reduce per
+    pass over torch.distributed on a caller-owned colour tensor (the round-1 path; kept for host-resident colour functions
+    and as the fallback where peer mapping is unavailable)."""
 
     def __init__(self, n_global, rank, world, cfl, eps, reconstruction_kind=0, max_iterations=10, origin=None, h=None,
-                 device=None, group=None, with_curvature=False, overlap=True, incremental=False):
+                 device=None, group=None, with_curvature=False, overlap=True, incremental=False, transport=None, layers=None):
         import torch
         from . import operators as ops
+        from .lib import check
         self.rank, self.world, self.group = rank, world, group
+        self.transport = transport if transport is not None else ("peer" if world > 1 else "local")
         dim = len(n_global)
         halo = HALO_WIDTH[int(reconstruction_kind)] if world > 1 else 0
         if with_curvature:
             halo = max(halo, 4) if world > 1 else 0
-        lo_last, n_last = split_last_axis(n_global[-1], world, rank)
+        if layers is None:
+            layers = [split_last_axis(n_global[-1], world, r)[1] for r in range(world)]
+        if len(layers) != world or sum(layers) != n_global[-1]:
+            raise ValueError("layers must hold one count per rank and sum to the grid's last extent")
+        self.layer_counts = [int(x) for x in layers]
+        lo_last, n_last = sum(self.layer_counts[:rank]), self.layer_counts[rank]
         lo = [0] * dim
         lo[-1] = lo_last
         n_local = list(n_global)
         n_local[-1] = n_last
         self.grid = ops.CartesianGrid(n_global, origin=origin, h=h, lo=lo, n_local=n_local, halo=halo, device=device)
-        self.alg = ops.Algorithm(self.grid, cfl, eps, reconstruction_kind, max_iterations, with_curvature, incremental)
+        self.alg = ops.Algorithm(self.grid, cfl, eps, reconstruction_kind, max_iterations, with_curvature,
+                                 incremental or self.transport == "peer")
         self.exchanger = HaloExchanger(n_last, halo, rank, world, group)
         self.layer_cells = self.grid.cells // (n_last + 2 * halo)
         self._dt_est = None
         self._comm = None
         self.overlap = overlap
-        if world > 1:
-            ptr = self.grid._L.vofx_dt_est_device(self.grid._ctx)
-            self._dt_est = torch.as_tensor(_DevicePtr(ptr), device=self.grid.device)
+        self._color = None
+        g = self.grid
+        if self.transport == "peer" and world > 1:
+            import torch.distributed as dist
+            handle = (C.c_ubyte * 64)()
+            check(g._L.vofx_comm_export(g._ctx, handle))
+            gathered = [None] * world
+            dist.all_gather_object(gathered, bytes(handle), group=group)
+            blob = b"".join(gathered)
+            counts = (C.c_int32 * world)(*self.layer_counts)
+            check(g._L.vofx_comm_connect(g._ctx, rank, world, counts, C.c_char_p(blob)))
+            # the algorithm's containers are the context-resident ones
+            self.alg.flags = torch.as_tensor(_DevicePtr(g._L.vofx_flags_device(g._ctx), g.cells, "|u1"), device=g.device)
+            self.alg.reconstructions = torch.as_tensor(_DevicePtr(g._L.vofx_halfspaces_device(g._ctx), g.cells * (dim + 1)),
+                                                       device=g.device).view(g.cells, dim + 1)
+        elif world > 1:
+            ptr = g._L.vofx_dt_est_device(g._ctx)
+            self._dt_est = torch.as_tensor(_DevicePtr(ptr), device=g.device)
+
+    def color(self):
+        """the colour tensor of this rank (storage size incl. halos): the context-resident one for the peer transport"""
+        import torch
+        g = self.grid
+        if self._color is None:
+            if self.transport == "peer" and self.world > 1:
+                self._color = torch.as_tensor(_DevicePtr(g._L.vofx_color_device(g._ctx), g.cells), device=g.device)
+            else:
+                self._color = g.empty("color")
+        return self._color
 
     def layers(self, t):
         return t.view(self.exchanger.owned + 2 * self.exchanger.halo, -1)
@@ -97,18 +163,36 @@ class SlabAlgorithm:
         return v[H:H + self.exchanger.owned] if H else v
 
     def begin(self, time=0.0, dt=0.0):
+        """start of a loop; for the peer transport the owned layers of color() must hold the initial data: the halos are
+        filled here (two host barriers, the only ones of the run)"""
+        import torch
+        from .lib import check
         self.alg.begin(time, dt)
+        if self.transport == "peer" and self.world > 1:
+            import torch.distributed as dist
+            g = self.grid
+            torch.cuda.synchronize(g.device)
+            dist.barrier(group=self.group)
+            g.use_current_stream()
+            check(g._L.vofx_halo_push(g._ctx))
+            torch.cuda.synchronize(g.device)
+            dist.barrier(group=self.group)
 
     def step(self, uh):
-        """one loop pass: the colour halos travel while the interior layers are flagged, the time-step estimate is
-        MIN-reduced while the update runs (vofx_step_phase, include/vofx.h)"""
+        """one loop pass.  peer: one C call, no host communication.  nccl: the colour halos travel while the interior layers
+        are flagged, the time-step estimate is MIN-reduced while the update runs (vofx_step_phase, include/vofx.h)"""
         import torch
-        import torch.distributed as dist
         from .lib import check
         g, a = self.grid, self.alg
         if self.world == 1:
             a.step(uh)
             return
+        if self.transport == "peer":
+            if uh.data_ptr() != self.color().data_ptr():
+                raise ValueError("the peer transport steps the context-resident colour function: pass SlabAlgorithm.color()")
+            check(g._L.vofx_step_distributed(g._ctx, C.byref(a.params)))
+            return
+        import torch.distributed as dist
         kap = C.c_void_p(a.curvature.data_ptr()) if a.curvature is not None else C.c_void_p(0)
         args = (g._ctx, C.byref(a.params), g.pc(uh), g.pf(a.flags), g.ph(a.reconstructions), kap)
         if not self.overlap:
@@ -135,9 +219,9 @@ class SlabAlgorithm:
         check(g._L.vofx_step_finish(g._ctx, C.byref(a.params)))
 
     def capture(self, uh):
-        """capture one loop pass (kernels, halo exchange, MIN reduction, both streams) into a CUDA graph; replay() then
-        costs one launch per pass on the host.  The pass only reads device-resident state (time, dt, counters), so the
-        captured work is the same every step."""
+        """capture one loop pass (every kernel incl. the peer signals, or the NCCL operations on both streams) into a CUDA
+        graph; replay() then costs one launch per pass on the host.  The pass only reads device-resident state (time, dt,
+        counters, epoch), so the captured work is the same every step."""
         import torch
         g = self.grid
         self._graph_stream = torch.cuda.Stream(device=g.device)
@@ -155,127 +239,76 @@ class SlabAlgorithm:
     def state(self):
         return self.alg.state()
 
-
-class PipelinedAlgorithm:
-    """The time loop on ONE GPU with the grid cut into `chunks` z-slabs that share the caller's contiguous arrays.
-
-    Every slab is a context of its own (with halo layers that alias the neighbouring slab's owned layers, so nothing is
-    copied) on a stream of its own: while the band kernels of one slab run (latency-bound, few resident warps), the
-    dense flag pass of the next slab streams through HBM.  Slabs only meet twice per pass: before the in-place update
-    (all reads of the old colour function are done) and for the MIN of the time-step estimates.  The result is the
-    single-context result bit for bit (the slab machinery is the multi-GPU one, tests/test_gpu_multirank.py).
-
-    MEASURED (B200, 512^3 sphere, graph replay, tools/pipeline_probe.py): 1.062 / 1.092 / 1.054 / 1.048 ms per step for
-    1 / 2 / 4 / 8 chunks -- no gain: the band kernels fill the register file and shared memory of every SM (9 blocks x
-    23.7 KB, 55 K registers), so the flag pass of the next slab gets one block per SM and streams at a fraction of the
-    HBM rate.  bench.py therefore runs the plain single-context loop; the class stays as the tested way to run several
-    contexts on windows of one contiguous array."""
-
-    def __init__(self, n, cfl, eps, reconstruction_kind=0, chunks=2, origin=None, h=None, device=None, max_iterations=10):
-        import torch
-        from . import operators as ops
-        self.n = tuple(int(x) for x in n)
-        self.dim = len(self.n)
-        self.chunks = int(chunks)
-        halo = HALO_WIDTH[int(reconstruction_kind)]
-        self.grids, self.params, self.offsets = [], [], []
-        self.layer = 1
-        for x in self.n[:-1]:
-            self.layer *= x
-        for k in range(self.chunks):
-            lo_last, n_last = split_last_axis(self.n[-1], self.chunks, k)
-            if n_last < halo + 2:
-                raise ValueError("chunk thinner than its halo")
-            lo = [0] * self.dim
-            lo[-1] = lo_last
-            n_local = list(self.n)
-            n_local[-1] = n_last
-            g = ops.CartesianGrid(self.n, origin=origin, h=h, lo=lo, n_local=n_local, halo=halo, device=device)
-            self.grids.append(g)
-            self.params.append(ops.StepParams(int(reconstruction_kind), int(max_iterations), float(eps), float(cfl), 0))
-            self.offsets.append((lo_last - halo) * self.layer)         # first storage cell of the slab in the global arrays
-        self.device = self.grids[0].device
-        self.cells = self.layer * self.n[-1]
-        self.streams = [torch.cuda.Stream(device=self.device) for _ in range(self.chunks)]
-        self._dt = [torch.as_tensor(_DevicePtr(g._L.vofx_dt_est_device(g._ctx)), device=self.device) for g in self.grids]
-        for g, st in zip(self.grids, self.streams):
-            with torch.cuda.stream(st):
-                g.use_current_stream()
-        self.flags = torch.zeros(self.cells, dtype=torch.uint8, device=self.device)
-        self.reconstructions = torch.zeros(self.cells, self.dim + 1, dtype=torch.float64, device=self.device)
-        self._graph = None
-
     def set_velocity_builtin(self, problem):
-        for g in self.grids:
-            g.set_velocity_builtin(problem)
+        self.grid.set_velocity_builtin(problem)
+        self._velocity_problem = int(problem)
 
-    def begin(self, time=0.0, dt=0.0):
-        from .lib import check
-        for g in self.grids:
-            check(g._L.vofx_step_begin(g._ctx, float(time), float(dt)))
-
-    def _args(self, k, uh):
-        off = self.offsets[k]
-        g = self.grids[k]
-        return (g._ctx, C.byref(self.params[k]), C.c_void_p(uh.data_ptr() + 8 * off), C.c_void_p(self.flags.data_ptr() + off),
-                C.c_void_p(self.reconstructions.data_ptr() + 8 * (self.dim + 1) * off), C.c_void_p(0))
-
-    def step(self, uh):
+    def layer_histogram(self):
+        """mixed cells per OWNED layer from the flags of the last pass (numpy int64): the input of split_by_cost"""
         import torch
-        from .lib import check
-        if uh.numel() != self.cells or uh.device != self.device or not uh.is_contiguous():
-            raise ValueError("expected the contiguous colour function of the whole grid on the algorithm's device")
-        main = torch.cuda.current_stream(self.device)
-        L = self.grids[0]._L
-        for k, st in enumerate(self.streams):                    # flags, reconstruction, fluxes of every slab
-            st.wait_stream(main)
-            with torch.cuda.stream(st):
-                args = self._args(k, uh)
-                check(L.vofx_step_phase(*args, 0))
-                check(L.vofx_step_phase(*args, 1))
-        for st in self.streams:                                  # nobody reads the old colour function any more
-            main.wait_stream(st)
-        for k, st in enumerate(self.streams):                    # in-place update of the owned cells
-            st.wait_stream(main)
-            with torch.cuda.stream(st):
-                check(L.vofx_step_phase(*self._args(k, uh), 2))
-        for st in self.streams:
-            main.wait_stream(st)
-        m = self._dt[0]                                          # gridView().comm().min( dtEst ), evolution.hh:75
-        for d in self._dt[1:]:
-            torch.minimum(m, d, out=m)
-        for d in self._dt[1:]:
-            d.copy_(m)
-        for k, g in enumerate(self.grids):
-            check(L.vofx_set_stream(g._ctx, C.c_void_p(main.cuda_stream)))
-            check(L.vofx_step_finish(g._ctx, C.byref(self.params[k])))
-            check(L.vofx_set_stream(g._ctx, C.c_void_p(self.streams[k].cuda_stream)))
+        f = self.owned(self.alg.flags)
+        return ((f == 1) | (f == 2)).sum(dim=1).cpu().numpy().astype("int64")
 
-    def capture(self, uh):
+    def global_layer_costs(self, ns_per_cell=0.02, ns_per_mixed_cell=5.0):
+        """estimated cost of every layer of the whole grid (all ranks): ns_per_cell * cells + ns_per_mixed_cell * mixed cells,
+        from the flags of the last pass; the defaults are the measured costs of the resident loop on B200 (the dense
+        part of a pass is the mark scan only, a mixed cell costs about 5 ns)"""
+        import numpy as np
+        hist = self.layer_histogram()
+        if self.world > 1:
+            import torch.distributed as dist
+            parts = [None] * self.world
+            dist.all_gather_object(parts, hist, group=self.group)
+            hist = np.concatenate(parts)
+        return ns_per_cell * self.layer_cells + ns_per_mixed_cell * hist
+
+    def rebalanced(self, uh, ns_per_cell=0.02, ns_per_mixed_cell=5.0, min_gain=0.05):
+        """Load balancing of the band (the reference calls gridPtr->loadBalance() once, example/vof.cc:63): a new slab
+        decomposition with equal estimated cost per rank, the colour function migrated over torch.distributed (contiguous
+        layer ranges, rank to rank) and the loop state (time, dt) carried over.  Returns (algorithm, colour tensor): the
+        same objects if the estimated gain of the slowest rank is below `min_gain`.  Collective: every rank must call it
+        between two passes.  The results do not depend on the decomposition (bit-identical to the serial run)."""
+        import numpy as np
         import torch
-        self._graph_stream = torch.cuda.Stream(device=self.device)
-        self._graph = torch.cuda.CUDAGraph()
-        torch.cuda.synchronize(self.device)
-        with torch.cuda.graph(self._graph, stream=self._graph_stream):
-            self.step(uh)
-        torch.cuda.synchronize(self.device)
-        return self._graph
+        costs = self.global_layer_costs(ns_per_cell, ns_per_mixed_cell)
+        counts = split_by_cost(costs, self.world, min_layers=max(self.exchanger.halo, 1))
+        edges_old = np.concatenate([[0], np.cumsum(self.layer_counts)])
+        edges_new = np.concatenate([[0], np.cumsum(counts)])
+        worst_old = max(costs[edges_old[r]:edges_old[r + 1]].sum() for r in range(self.world))
+        worst_new = max(costs[edges_new[r]:edges_new[r + 1]].sum() for r in range(self.world))
+        if list(counts) == list(self.layer_counts) or worst_new > (1.0 - min_gain) * worst_old:
+            return self, uh
+        st = self.state()
+        g = self.grid
+        p = self.alg.params
+        new = SlabAlgorithm(g.n, self.rank, self.world, p.cfl, p.eps, p.reconstruction, p.max_iterations, origin=g.origin, h=g.h,
+                            device=g.device.index, group=self.group, with_curvature=bool(p.with_curvature), overlap=self.overlap,
+                            incremental=True, transport=self.transport, layers=counts)
+        if getattr(self, "_velocity_problem", None) is not None:
+            new.set_velocity_builtin(self._velocity_problem)
+        u_new = new.color()
+        # layer ranges that move from rank s (old owner) to rank d (new owner)
+        import torch.distributed as dist
+        src, dst = self.owned(uh), new.owned(u_new)
+        ops_list = []
+        for other in range(self.world):
+            lo = max(edges_old[self.rank], edges_new[other])          # I send [lo, hi) to `other`
+            hi = min(edges_old[self.rank + 1], edges_new[other + 1])
+            if hi > lo:
+                a = src[lo - edges_old[self.rank]:hi - edges_old[self.rank]]
+                if other == self.rank:
+                    dst[lo - edges_new[self.rank]:hi - edges_new[self.rank]].copy_(a)
+                else:
+                    ops_list.append(dist.P2POp(dist.isend, a, other, self.group))
+            lo = max(edges_new[self.rank], edges_old[other])          # I receive [lo, hi) from `other`
+            hi = min(edges_new[self.rank + 1], edges_old[other + 1])
+            if hi > lo and other != self.rank:
+                ops_list.append(dist.P2POp(dist.irecv, dst[lo - edges_new[self.rank]:hi - edges_new[self.rank]], other, self.group))
+        if ops_list:
+            for req in dist.batch_isend_irecv(ops_list):
+                req.wait()
+        torch.cuda.synchronize(g.device)
+        new.begin(st.time, st.dt)
+        return new, u_new
 
-    def replay(self):
-        self._graph.replay()
 
-    def state(self):
-        from .operators import StepResult
-        g = self.grids[0]
-        t, dt, de, m = C.c_double(), C.c_double(), C.c_double(), C.c_int64()
-        from .lib import check
-        check(g._L.vofx_step_state(g._ctx, C.byref(t), C.byref(dt), C.byref(de), C.byref(m)))
-        return StepResult(t.value, dt.value, de.value, m.value)
-
-    @property
-    def launch_count(self):
-        return sum(g.launch_count for g in self.grids)
-
-    def close(self):
-        for g in self.grids:
-            g.close()

@@ -42,7 +42,7 @@ extern "C" {
  *   VOFX_FLUX_LANES     = 8 | 4   lanes per mixed cell of the 3D flux kernel (default 8)
  *   VOFX_SWARTZ_LANES   = 4 | 8   lanes per task of the 3D Swartz kernels (default 4)
  *   VOFX_SWARTZ_MODE    = batched (default) | cell | serial   formulation of the 3D Swartz reconstruction
- *   VOFX_YOUNGS_BLOCKS_PER_SM = n   grid of the 3D plane-constant kernel in 64-thread blocks per SM (default 40)
+ *   VOFX_YOUNGS_BLOCKS_PER_SM = n   grid of the 3D plane-constant kernel in 64-thread blocks per SM (default 60)
  *   VOFX_FLUX_BLOCKS_PER_SM, VOFX_UPDATE_BLOCKS_PER_SM = n   grids of the 3D flux / update kernels (default 8)
  *   VOFX_SWZ_BLOCKS_PER_SM, VOFX_SWZ_OTHER_BLOCKS_PER_SM = n   grids of the batched Swartz kernels (default 80 / 48)
  *   VOFX_NO_COST_ORDER  = 1   process the band in list order instead of last step's expensive cells first
@@ -175,7 +175,7 @@ int vofx_step ( vofx_ctx *ctx, const vofx_step_params *params, double *u, uint8_
 /* copy the device-resident (time, dt, last dtEst, number of mixed cells of the last step) to the host; synchronises */
 int vofx_step_state ( vofx_ctx *ctx, double *time, double *dt, double *dt_est, int64_t *mixed_cells );
 /* multi-GPU: address of the device scalar holding the last local dtEst, for a MIN all-reduce between
- * vofx_step_local() and vofx_step_finish() (see dune_vof_b200/host/decomposition.py) */
+ * vofx_step_local() and vofx_step_finish() (the "nccl" transport of dune-vof_b200/decomposition.py) */
 int vofx_step_local ( vofx_ctx *ctx, const vofx_step_params *params, double *u, uint8_t *flags, double *halfspaces, double *kappa );
 int vofx_step_finish ( vofx_ctx *ctx, const vofx_step_params *params );
 /* vofx_step_local in three phases, so that the halo exchange (during phase 0) and the MIN-reduction of the time-step
@@ -211,6 +211,39 @@ int vofx_changed_fetch ( vofx_ctx *ctx, double *u_host, int64_t index_offset, in
 int vofx_color_upload ( vofx_ctx *ctx, const double *u_host );
 int vofx_step_resident ( vofx_ctx *ctx, const vofx_step_params *params );
 int vofx_color_download ( vofx_ctx *ctx, double *u_host, uint8_t *flags_host /* may be NULL */ );
+
+/* ---- multi-GPU: the grid is cut into slabs along the last axis, one context per GPU (one per process -- one per MPI
+ * rank of a DUNE host -- or several in one process).  Replaces the reference's exchanges over GridView::communicate
+ * (dataset.hh:69-81; call sites flagging.hh:69, modifiedyoungs.hh:75, evolution/evolution.hh:73) and gridView().comm().min
+ * (evolution.hh:75) by stores into the neighbours' memory over NVLink, issued by the kernels themselves:
+ *   - the colour function is context-resident (vofx_color_device / vofx_color_upload) inside a "window" whose CUDA IPC
+ *     handle is handed to the other ranks; it only ever changes in the update kernel, which also writes every new value
+ *     of a boundary layer into the neighbour's halo copy -- there is no halo exchange after the start of a loop;
+ *   - flags and reconstructions of the first halo layer are recomputed locally (owner-computes);
+ *   - the time-step estimates travel as one double per rank into every rank's window; passes are ordered by epoch
+ *     counters in the same windows (a wait that times out after ~10 s makes the next vofx_step_state fail).
+ * Call sequence on every rank: vofx_create (lo / n_local / halo of the slab; halo = 2 Young's, 4 height functions or
+ * curvature, 3 Swartz) -> vofx_comm_export -> [the host all-gathers the handles: MPI_Allgather, torch.distributed, a
+ * pipe] -> vofx_comm_connect -> velocity, initial data (vofx_color_upload or vofx_init on vofx_color_device) ->
+ * vofx_step_begin -> [host barrier] -> vofx_halo_push -> [host barrier] -> vofx_step_distributed ... (no host
+ * communication per pass; the pass is graph-capturable) -> vofx_color_download.
+ * Results are bit-identical to the single-context run: coordinates come from global indices, MIN is exact. */
+#define VOFX_COMM_HANDLE_BYTES 64
+/* allocates the window (must precede any use of the context-resident colour function) and returns its cudaIpcMemHandle_t */
+int vofx_comm_export ( vofx_ctx *ctx, void *handle /* VOFX_COMM_HANDLE_BYTES */ );
+/* layers[ r ] = owned layers of rank r along the last axis; handles = world * VOFX_COMM_HANDLE_BYTES bytes in rank order
+ * (the entry of `rank` itself is ignored) */
+int vofx_comm_connect ( vofx_ctx *ctx, int rank, int world, const int32_t *layers, const void *handles );
+/* the same for `world` contexts of ONE process in slab order (same or different devices; peer access is enabled) */
+int vofx_comm_connect_local ( vofx_ctx **contexts, int world );
+/* device addresses of the context-resident colour function / flags / half-spaces (storage size incl. halos) */
+double *vofx_color_device ( vofx_ctx *ctx );
+uint8_t *vofx_flags_device ( vofx_ctx *ctx );
+double *vofx_halfspaces_device ( vofx_ctx *ctx );
+/* copies the owned boundary layers into the neighbours' halos (after the initial data is in place); synchronises */
+int vofx_halo_push ( vofx_ctx *ctx );
+/* one loop pass of the distributed run on the context-resident colour function (vofx_step_resident when not connected) */
+int vofx_step_distributed ( vofx_ctx *ctx, const vofx_step_params *params );
 
 /* ---- interface extraction (replaces getInterfaceVertices, utility.hh:19-48, and MixedCellMapper::update,
  * mixedcellmapper.hh:82-86): the owned mixed cells in ascending cell index, and for the i-th of them the vertices of

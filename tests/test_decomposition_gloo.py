@@ -81,3 +81,25 @@ def test_halo_exchange_world2(halo):
 def test_exchanger_rejects_thin_slab():
     with pytest.raises(ValueError):
         D.HaloExchanger(owned_layers=1, halo=2, rank=0, world=2)
+
+
+def test_split_by_cost_balances_a_band():
+    """a band of work in the middle third of the layers: the cost-weighted split gives every slab about the same cost,
+    covers every layer once and respects the minimal thickness (the halo width)"""
+    n, world = 1024, 8
+    costs = np.full(n, 1.0)
+    costs[200:520] += 400.0                      # the sphere's band: z in [0.2, 0.5] of a 1024^3 grid
+    counts = D.split_by_cost(costs, world, min_layers=2)
+    assert len(counts) == world and sum(counts) == n and min(counts) >= 2
+    edges = np.concatenate([[0], np.cumsum(counts)])
+    per_slab = [costs[edges[r]:edges[r + 1]].sum() for r in range(world)]
+    assert max(per_slab) <= 1.15 * costs.sum() / world
+    # uniform cost -> the even split
+    assert D.split_by_cost(np.ones(64), 8, 2) == [8] * 8
+    # all work in one layer: nothing better than isolating it, but every slab keeps its minimal thickness
+    spike = np.zeros(40)
+    spike[17] = 5.0
+    c = D.split_by_cost(spike, 4, 3)
+    assert sum(c) == 40 and min(c) >= 3
+    with pytest.raises(ValueError):
+        D.split_by_cost(np.ones(5), 4, 2)

@@ -253,45 +253,6 @@ def test_interface_extraction(vofx, case):
     grid.close()
 
 
-@pytest.mark.parametrize("n,problem,recon,chunks", [((32, 32, 48), 4, 0, 2), ((32, 32, 48), 4, 0, 3), ((24, 24, 40), 1, 1, 2), ((64, 96), 2, 1, 2)])
-def test_pipelined_single_gpu(vofx, n, problem, recon, chunks):
-    """PipelinedAlgorithm (z-slabs of ONE GPU on separate streams, aliasing the caller's contiguous arrays) reproduces the
-    single-context loop bit for bit, eagerly and replayed from a CUDA graph"""
-    import torch
-    from dune_vof_b200.decomposition import PipelinedAlgorithm
-    grid = vofx.CartesianGrid(n)
-    grid.set_velocity_builtin(problem)
-    u0 = grid.init(problem)
-    passes = 6
-    ref = vofx.Algorithm(grid, 0.5, 1e-6, reconstruction_kind=recon)
-    ua = u0.clone()
-    st = ref.run_passes(ua, passes)
-    pipe = PipelinedAlgorithm(n, 0.5, 1e-6, recon, chunks=chunks)
-    pipe.set_velocity_builtin(problem)
-    ub = u0.clone()
-    pipe.begin(0.0, 0.0)
-    for _ in range(passes):
-        pipe.step(ub)
-    torch.cuda.synchronize()
-    sp = pipe.state()
-    assert torch.equal(ua.view(torch.int64), ub.view(torch.int64))
-    assert sp.time == st.time and sp.dt == st.dt
-    # graph replay
-    uc = u0.clone()
-    pipe.begin(0.0, 0.0)
-    side = torch.cuda.Stream()
-    with torch.cuda.stream(side):
-        pipe.step(uc)
-    torch.cuda.synchronize()
-    pipe.capture(uc)
-    for _ in range(passes - 1):
-        pipe.replay()
-    torch.cuda.synchronize()
-    assert torch.equal(ua.view(torch.int64), uc.view(torch.int64))
-    pipe.close()
-    grid.close()
-
-
 def _torch_flags(u, n, eps):
     """flagging.hh:35-70 restated with torch element-wise ops (independent of the kernels): dense check at full size"""
     import torch
