@@ -221,6 +221,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-port-check", action="store_true", help="reference arm: skip the plain-C port on the exact bench grid")
     ap.add_argument("--dense-flags", action="store_true", help="flag every cell every step instead of incremental flagging")
+    ap.add_argument("--transport", default=None, choices=["peer", "nccl"], help="N > 1: peer-mapped windows (default) or NCCL halo exchange")
+    ap.add_argument("--no-extra-workloads", action="store_true", help="N > 1: skip the c3-strong / c5 runs next to the weak-scaling line")
+    ap.add_argument("--extra-steps", type=int, default=60, help="timed steps of the c3-strong / c5 runs")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -257,29 +260,15 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     import dune_vof_b200.operators as ops
-    from dune_vof_b200.decomposition import SlabAlgorithm
+    from dune_vof_b200.decomposition import SlabAlgorithm, split_by_cost
     from dune_vof_b200 import lib as vlib
+    L = vlib.load()
 
     W = max(3, args.warmup)
     K = max(1, args.steps)
-    n_global = (N_SIDE, N_SIDE, N_SIDE * world)
-    h = (1.0 / N_SIDE,) * 3
     incremental = not args.dense_flags
-    slab = SlabAlgorithm(n_global, rank, world, CFL, EPS, ops.RECON_YOUNGS, h=h, device=local_rank,
-                         overlap=os.environ.get("VOFX_NO_OVERLAP", "0") != "1", incremental=incremental)
-    grid = slab.grid
-    grid.set_velocity_builtin(ops.PROB_LEVEQUE)
-    grid.use_current_stream()
-
-    # initial data: every slab is a copy of the unit-cube problem (sphere at (0.35,0.35,0.35) + k e_z)
-    unit = ops.CartesianGrid((N_SIDE,) * 3, h=h, device=local_rank)
-    u_unit = unit.init(ops.PROB_LEVEQUE)
-    uh = grid.empty("color")
-    slab.owned(uh).copy_(u_unit.view(N_SIDE, -1))
-    del u_unit
-    unit.close()
-    cells_per_gpu = N_SIDE ** 3
-    total_cells = cells_per_gpu * world
+    transport = args.transport if world > 1 else None
+    use_graph = os.environ.get("VOFX_NO_GRAPH", "0") != "1"
 
     def sync_all():
         torch.cuda.synchronize()
@@ -287,42 +276,92 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    # the loop pass is captured into a CUDA graph (all state it reads lives on the device): one host launch per step
-    use_graph = os.environ.get("VOFX_NO_GRAPH", "0") != "1"
-    slab.begin(0.0, 0.0)
-    side = torch.cuda.Stream()
-    with torch.cuda.stream(side):
-        grid.use_current_stream()
-        for _ in range(W):
-            slab.step(uh)
-    sync_all()
-    launches_per_graph = 0
-    if use_graph:
+    def max_over_ranks(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def gather_ints(x):
+        if world == 1:
+            return [int(x)]
+        out = [None] * world
+        dist.all_gather_object(out, int(x))
+        return out
+
+    def make_slab(n_global, h, layers=None, tr=transport):
+        slab = SlabAlgorithm(n_global, rank, world, CFL, EPS, ops.RECON_YOUNGS, h=h, device=local_rank,
+                             overlap=os.environ.get("VOFX_NO_OVERLAP", "0") != "1", incremental=incremental, transport=tr, layers=layers)
+        slab.set_velocity_builtin(ops.PROB_LEVEQUE)
+        slab.grid.use_current_stream()
+        return slab
+
+    def timed_run(slab, uh, warm, steps):
+        """W eager warm-up passes, capture, `steps` replays between device events; returns (ms, launches, state)"""
+        grid = slab.grid
+        slab.begin(0.0, 0.0)
+        side = torch.cuda.Stream()
+        with torch.cuda.stream(side):
+            grid.use_current_stream()
+            for _ in range(warm):
+                slab.step(uh)
+        sync_all()
+        per_graph = 0
+        if use_graph:
+            before = grid.launch_count
+            slab.capture(uh)
+            per_graph = grid.launch_count - before            # kernels in one captured pass
+            one_step = slab.replay
+        else:
+            grid.use_current_stream()
+            one_step = lambda: slab.step(uh)
+        sync_all()
         before = grid.launch_count
-        slab.capture(uh)
-        launches_per_graph = grid.launch_count - before        # kernels in one captured pass
-        one_step = slab.replay
-    else:
-        grid.use_current_stream()
-        one_step = lambda: slab.step(uh)
-    sync_all()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync_all()
+        ev0.record()
+        for _ in range(steps):
+            one_step()
+        ev1.record()
+        sync_all()
+        ms = max_over_ranks(ev0.elapsed_time(ev1))
+        launches = per_graph * steps if use_graph else grid.launch_count - before
+        return ms, launches, slab.state()
+
+    def drop(slab):
+        torch.cuda.synchronize()
+        for obj in (slab, slab.alg):
+            if hasattr(obj, "_graph"):
+                del obj._graph
+        torch.cuda.synchronize()
+        slab.close()
+
+    # ---- the headline: weak scaling, every GPU owns a 512^3 copy of the unit-cube problem -----------------------------
+    n_global = (N_SIDE, N_SIDE, N_SIDE * world)
+    h = (1.0 / N_SIDE,) * 3
+    slab = make_slab(n_global, h)
+    grid = slab.grid
+    uh = slab.color()
+    unit = ops.CartesianGrid((N_SIDE,) * 3, h=h, device=local_rank)
+    u_unit = unit.init(ops.PROB_LEVEQUE)
+    uh.zero_()
+    slab.owned(uh).copy_(u_unit.view(N_SIDE, -1))              # sphere at (0.35, 0.35, 0.35) + k e_z in every slab
+    del u_unit
+    unit.close()
+    cells_per_gpu = N_SIDE ** 3
+    total_cells = cells_per_gpu * world
 
     sampler = ClockSampler(local_rank)
     sampler.start()
-    launches0 = grid.launch_count
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sync_all()
-    ev0.record()
-    for _ in range(K):
-        one_step()
-    ev1.record()
-    sync_all()
-    ms = ev0.elapsed_time(ev1)
-    launches = launches_per_graph * K if use_graph else grid.launch_count - launches0
-    state = slab.state()
+    ms, launches, state = timed_run(slab, uh, W, K)
+    if world > 1:
+        ln = torch.tensor([launches], dtype=torch.float64, device="cuda")
+        dist.all_reduce(ln, op=dist.ReduceOp.SUM)
+        launches = int(ln.item())
+    value = total_cells * K / (ms * 1e-3)
 
-    # per-kernel device times of the same workload (separate pass: the event pairs perturb the headline slightly)
-    L = grid._L
+    # per-kernel device times of the same workload (separate eager passes: the event pairs perturb the headline slightly)
     grid.use_current_stream()
     vlib.check(L.vofx_profile_enable(grid._ctx, 1))
     KP = min(K, 50)
@@ -335,6 +374,7 @@ def main():
     vlib.check(L.vofx_profile_read(grid._ctx, 32, names, tot, cnt, C.byref(nent)))
     vlib.check(L.vofx_profile_enable(grid._ctx, 0))
     sampler.stop()
+    sync_all()
     kernels = {}
     for i in range(nent.value):
         nm = names.raw[48 * i:48 * (i + 1)].split(b"\0", 1)[0].decode()
@@ -342,18 +382,9 @@ def main():
     step_ms_profiled = sum(k["avg_ms"] * k["launches_per_step"] for k in kernels.values())
     for k in kernels.values():
         k["share"] = (k["avg_ms"] * k["launches_per_step"]) / step_ms_profiled if step_ms_profiled > 0 else None
+    mixed_per_rank = gather_ints(state.mixed_cells)
 
-    if world > 1:
-        tms = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        ms = float(tms.item())
-        ln = torch.tensor([launches], dtype=torch.float64, device="cuda")
-        dist.all_reduce(ln, op=dist.ReduceOp.SUM)
-        launches = int(ln.item())
-    value = total_cells * K / (ms * 1e-3)
-
-    # end to end through the host-buffer C ABI: H2D colour, one loop pass, D2H colour, every step
-    e2e = None
+    # ---- end to end through the host-buffer entry points: H2D colour, one loop pass, D2H, every step ------------------
     if world == 1:
         host_u = torch.empty(grid.cells, dtype=torch.float64).pin_memory()
         host_u.copy_(uh)
@@ -369,29 +400,36 @@ def main():
         wall = time.perf_counter() - t0
         h2d, d2h = C.c_int64(0), C.c_int64(0)
         vlib.check(L.vofx_host_transfer_bytes(grid._ctx, C.byref(h2d), C.byref(d2h)))
-        # the host colour function must equal the device one afterwards (checked outside the timed region)
-        torch.cuda.synchronize()
         e2e = {"value": total_cells * KE / wall, "unit": "cell-steps/s", "h2d_bytes_per_step": int(h2d.value),
                "d2h_bytes_per_step": int(d2h.value), "steps": KE, "ms_per_step": 1e3 * wall / KE,
-               "api": "vofx_step_host: pinned host colour function in (whole array H2D), updated in place on the host from the "
-                      "(cell, value) pairs of the cells the step changed (sparse D2H) + loop state"}
+               "api": "vofx_step_host: pinned host colour function in (whole array H2D, dense flags), updated in place on the host from "
+                      "the (cell, value) pairs of the cells the step changed (sparse D2H) + loop state"}
+        drop(slab)
     else:
-        # every rank: H2D of its owned slab from pinned host memory, one loop pass (halo exchange, MIN reduction), the
-        # changed (cell, value) pairs back into the host slab
-        H = slab.exchanger.halo
-        owned = slab.owned(uh)
+        # every rank: H2D of its owned slab from pinned host memory, one loop pass on a caller-owned device tensor (NCCL halo
+        # exchange + MIN all-reduce: the host owns the colour function, so nothing may be kept in peer windows), the changed
+        # (cell, value) pairs back into the host slab
+        owned_now = slab.owned(uh).clone()                      # the window is freed with the context
+        drop(slab)
+        slab_e = make_slab(n_global, h, tr="nccl")
+        ge = slab_e.grid
+        ue = ge.empty("color")
+        H = slab_e.exchanger.halo
+        owned = slab_e.owned(ue)
         host_u = torch.empty(owned.numel(), dtype=torch.float64).pin_memory()
-        host_u.copy_(owned.reshape(-1))
-        grid.use_current_stream()
-        vlib.check(L.vofx_track_changes(grid._ctx, 1))
-        vlib.check(L.vofx_set_incremental_flagging(grid._ctx, 0))   # the host owns the colour function here: dense flags every pass
+        host_u.copy_(owned_now.reshape(-1))
+        del owned_now
+        ge.use_current_stream()
+        vlib.check(L.vofx_track_changes(ge._ctx, 1))
+        vlib.check(L.vofx_set_incremental_flagging(ge._ctx, 0))   # the host owns the colour function here: dense flags every pass
+        slab_e.begin(state.time, state.dt)
         KE = max(1, args.e2e_steps)
         nchg = C.c_int64(0)
 
         def e2e_step():
             owned.copy_(host_u.view_as(owned), non_blocking=True)
-            slab.step(uh)
-            vlib.check(L.vofx_changed_fetch(grid._ctx, C.c_void_p(host_u.data_ptr()), C.c_int64(-H * slab.layer_cells), C.byref(nchg)))
+            slab_e.step(ue)
+            vlib.check(L.vofx_changed_fetch(ge._ctx, C.c_void_p(host_u.data_ptr()), C.c_int64(-H * slab_e.layer_cells), C.byref(nchg)))
 
         e2e_step()
         sync_all()
@@ -399,25 +437,88 @@ def main():
         for _ in range(KE):
             e2e_step()
         sync_all()
-        wall = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
-        dist.all_reduce(wall, op=dist.ReduceOp.MAX)
-        wall = float(wall.item())
-        vlib.check(L.vofx_track_changes(grid._ctx, 0))
+        wall = max_over_ranks(time.perf_counter() - t0)
         e2e = {"value": total_cells * KE / wall, "unit": "cell-steps/s", "h2d_bytes_per_step": 8 * cells_per_gpu * world,
                "d2h_bytes_per_step": (12 * int(nchg.value) + 64) * world, "steps": KE, "ms_per_step": 1e3 * wall / KE,
-               "api": "per rank: pinned host slab -> device, SlabAlgorithm.step (halo exchange + MIN reduction over NCCL), "
-                      "vofx_changed_fetch writes the changed (cell, value) pairs back into the host slab; d2h bytes estimated "
+               "api": "per rank: pinned host slab -> device, SlabAlgorithm(transport='nccl').step (halo exchange + MIN reduction over NCCL, dense "
+                      "flags), vofx_changed_fetch writes the changed (cell, value) pairs back into the host slab; d2h bytes estimated "
                       "from rank 0's count"}
+        drop(slab_e)
+
+    # ---- N > 1: the configs that are ONE problem cut into slabs, with the band balanced over the ranks ---------------------
+    workloads = {}
+    multirank_parity = None
+    if world > 1 and not args.no_extra_workloads:
+        def one_problem(tag, n_glob, hh):
+            """one sphere in n_glob: even split -> per-layer cost from the initial flags -> cost-weighted split -> timed run"""
+            res = {"grid": list(n_glob)}
+            out = {}
+            for mode in ("even", "balanced"):
+                layers = None
+                if mode == "balanced":
+                    layers = out["_counts"]
+                    if layers == out["even"]["layers"]:
+                        res["balanced"] = dict(res["even"], note="the cost-weighted split equals the even one")
+                        break
+                s2 = make_slab(n_glob, hh, layers=layers)
+                u2 = s2.color()
+                s2.grid.init(ops.PROB_LEVEQUE, out=u2)          # analytic initial data in global coordinates, halos included
+                torch.cuda.synchronize()
+                if mode == "even":
+                    ops.FlagOperator(s2.grid, EPS)(u2, s2.alg.flags)
+                    costs = s2.global_layer_costs()
+                    out["_counts"] = split_by_cost(costs, world, min_layers=max(s2.exchanger.halo, 1))
+                ms2, _, st2 = timed_run(s2, u2, W, args.extra_steps)
+                cells = 1
+                for x in n_glob:
+                    cells *= x
+                entry = {"layers": list(s2.layer_counts), "ms_per_step": ms2 / args.extra_steps, "steps": args.extra_steps,
+                         "value": cells * args.extra_steps / (ms2 * 1e-3), "unit": "cell-steps/s",
+                         "value_per_gpu": cells * args.extra_steps / (ms2 * 1e-3) / world,
+                         "mixed_cells_per_rank": gather_ints(st2.mixed_cells), "time": st2.time}
+                out[mode] = entry
+                res[mode] = entry
+                drop(s2)
+            return res
+
+        if N_SIDE % world == 0 and N_SIDE // world >= 4:
+            workloads["c3_strong"] = dict(one_problem("c3_strong", (N_SIDE,) * 3, (1.0 / N_SIDE,) * 3),
+                                          workload="configs[2] strong scaling: ONE 512^3 LeVeque sphere cut into z-slabs", scaling="strong")
+        if world == 8:
+            n5 = 2 * N_SIDE
+            workloads["c5"] = dict(one_problem("c5", (n5, n5, n5), (1.0 / n5,) * 3),
+                                   workload="configs[4]: ONE LeVeque sphere on 1024^3 (1024 x 1024 x 128 per GPU on the even split)", scaling="weak vs 1 GPU x 512^3")
+
+        # bit parity of the slab run with the serial run on a case whose sphere crosses the slab boundaries (outside any timed region)
+        n_small = (48, 40, 64)
+        g1 = ops.CartesianGrid(n_small, device=local_rank)
+        g1.set_velocity_builtin(ops.PROB_LEVEQUE)
+        u1 = g1.init(ops.PROB_LEVEQUE)
+        u0 = u1.clone()
+        st1 = ops.Algorithm(g1, CFL, EPS, reconstruction_kind=ops.RECON_YOUNGS).run_passes(u1, 10)
+        sp = SlabAlgorithm(n_small, rank, world, CFL, EPS, ops.RECON_YOUNGS, device=local_rank, transport=transport)
+        sp.set_velocity_builtin(ops.PROB_LEVEQUE)
+        up = sp.color()
+        up.zero_()
+        lo = sum(sp.layer_counts[:rank])
+        layer = u0.numel() // n_small[-1]
+        sp.owned(up).copy_(u0.view(n_small[-1], layer)[lo:lo + sp.layer_counts[rank]])
+        sp.begin(0.0, 0.0)
+        for _ in range(10):
+            sp.step(up)
+        stp = sp.state()
+        torch.cuda.synchronize()
+        same = torch.equal(sp.owned(up).contiguous().view(torch.int64), u1.view(n_small[-1], layer)[lo:lo + sp.layer_counts[rank]].contiguous().view(torch.int64))
+        ok = torch.tensor([1 if (same and stp.time == st1.time and stp.dt == st1.dt) else 0], device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        multirank_parity = {"case": "48 x 40 x 64 LeVeque sphere, Young's, 10 passes, z-slabs vs one context", "transport": sp.transport,
+                            "layers": list(sp.layer_counts), "bit_identical": bool(int(ok.item()) == 1)}
+        sp.close()
+        g1.close()
 
     def teardown():
         # regular interpreter exit (no os._exit): the driver's exit hook records the libraries this process mapped
-        nonlocal slab
         torch.cuda.synchronize()
-        for obj in (slab, slab.alg):
-            if hasattr(obj, "_graph"):
-                del obj._graph
-        torch.cuda.synchronize()
-        slab.grid.close()
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
@@ -451,7 +552,7 @@ def main():
                 sub[nm]["fp64_pipe_source"] = "profiles/r2_ncu_summary.json (static: ncu --set full capture of this workload)"
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "whole step (SURVEY.md 8(d): cell-steps/s x 17 B against the measured HBM peak)",
+    roofline = {"bound": "hbm", "kernel": "whole step (SURVEY.md 8(d): cell-steps/s per GPU x 17 B against the measured HBM peak)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "traffic_note": "not captured in this run; per-kernel dram bytes of the ncu captures are under profiles/",
                 "algorithmic_bytes_per_cell_step": SURVEY_BYTES_PER_CELL_STEP,
@@ -475,9 +576,10 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD_NAME,
                    "grid": list(n_global), "cells_per_gpu": cells_per_gpu, "decomposition": f"z-slabs x{world}",
+                   "transport": (slab.transport if world > 1 else None),
                    "flagging": "incremental (dense first pass, then re-flag of the band's two-step neighbourhood)" if incremental else "dense every step",
                    "l2": "inputs larger than L2 (colour function 1.07 GB per GPU vs 126 MB L2)",
-                   "mixed_cells_last_step_rank0": state.mixed_cells, "time": state.time, "dt": state.dt},
+                   "mixed_cells_last_step_per_rank": mixed_per_rank, "time": state.time, "dt": state.dt},
         "clocks": sampler.report(),
         "e2e": e2e,
         "gpu_launches": launches,
@@ -485,6 +587,9 @@ def main():
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
     }
+    if world > 1:
+        line["workloads"] = workloads
+        line["multirank_parity"] = multirank_parity
     emit(json.dumps(line))
     teardown()
     return 0

@@ -1754,6 +1754,23 @@ extern "C"
     return VOFX_OK;
   }
 
+  int vofx_comm_disconnect ( vofx_ctx *ctx )
+  {
+    if( !ctx )
+      return fail( VOFX_ERR_ARGUMENT, "null context" );
+    int rc = setDevice( ctx );
+    if( rc )
+      return rc;
+    VOFX_CUDA( cudaStreamSynchronize( ctx->stream ) );
+    for( void *m : ctx->ipcMapped )
+      cudaIpcCloseMemHandle( m );
+    ctx->ipcMapped.clear();
+    ctx->commConnected = false;
+    std::memset( &ctx->peers, 0, sizeof( ctx->peers ) );
+    ctx->peers.world = 1;
+    return VOFX_OK;
+  }
+
   double *vofx_color_device ( vofx_ctx *ctx )
   {
     if( !ctx || ensureMirrors( ctx ) )

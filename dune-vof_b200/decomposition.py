@@ -239,6 +239,25 @@ class SlabAlgorithm:
     def state(self):
         return self.alg.state()
 
+    def close(self):
+        """collective: unmap the peers' windows on every rank, barrier, then free (an exported window must outlive its
+        mappings in the other processes)"""
+        import torch
+        from .lib import check
+        g = self.grid
+        if getattr(g, "_ctx", None) is None:
+            return
+        torch.cuda.synchronize(g.device)
+        if hasattr(self, "_graph"):
+            del self._graph
+        if self.transport == "peer" and self.world > 1:
+            import torch.distributed as dist
+            dist.barrier(group=self.group)
+            check(g._L.vofx_comm_disconnect(g._ctx))
+            dist.barrier(group=self.group)
+        self._color = None
+        g.close()
+
     def set_velocity_builtin(self, problem):
         self.grid.set_velocity_builtin(problem)
         self._velocity_problem = int(problem)
@@ -249,9 +268,9 @@ class SlabAlgorithm:
         f = self.owned(self.alg.flags)
         return ((f == 1) | (f == 2)).sum(dim=1).cpu().numpy().astype("int64")
 
-    def global_layer_costs(self, ns_per_cell=0.02, ns_per_mixed_cell=5.0):
+    def global_layer_costs(self, ns_per_cell=1e-4, ns_per_mixed_cell=5.0):
         """estimated cost of every layer of the whole grid (all ranks): ns_per_cell * cells + ns_per_mixed_cell * mixed cells,
-        from the flags of the last pass; the defaults are the measured costs of the resident loop on B200 (the dense
+        from the flags of the last pass; the defaults are the measured costs of the resident loop on B200 (1e-4 ns per cell: the dense
         part of a pass is the mark scan only, a mixed cell costs about 5 ns)"""
         import numpy as np
         hist = self.layer_histogram()
@@ -262,7 +281,7 @@ class SlabAlgorithm:
             hist = np.concatenate(parts)
         return ns_per_cell * self.layer_cells + ns_per_mixed_cell * hist
 
-    def rebalanced(self, uh, ns_per_cell=0.02, ns_per_mixed_cell=5.0, min_gain=0.05):
+    def rebalanced(self, uh, ns_per_cell=1e-4, ns_per_mixed_cell=5.0, min_gain=0.05):
         """Load balancing of the band (the reference calls gridPtr->loadBalance() once, example/vof.cc:63): a new slab
         decomposition with equal estimated cost per rank, the colour function migrated over torch.distributed (contiguous
         layer ranges, rank to rank) and the loop state (time, dt) carried over.  Returns (algorithm, colour tensor): the

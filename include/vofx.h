@@ -236,6 +236,9 @@ int vofx_comm_export ( vofx_ctx *ctx, void *handle /* VOFX_COMM_HANDLE_BYTES */ 
 int vofx_comm_connect ( vofx_ctx *ctx, int rank, int world, const int32_t *layers, const void *handles );
 /* the same for `world` contexts of ONE process in slab order (same or different devices; peer access is enabled) */
 int vofx_comm_connect_local ( vofx_ctx **contexts, int world );
+/* unmaps the other ranks' windows.  Every rank calls it, then the host synchronises the ranks (barrier), THEN the contexts
+ * are destroyed: an exported window must not be freed while another process still maps it */
+int vofx_comm_disconnect ( vofx_ctx *ctx );
 /* device addresses of the context-resident colour function / flags / half-spaces (storage size incl. halos) */
 double *vofx_color_device ( vofx_ctx *ctx );
 uint8_t *vofx_flags_device ( vofx_ctx *ctx );

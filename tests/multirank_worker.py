@@ -1,6 +1,9 @@
 """Worker of tests/test_gpu_multirank.py, launched by torch.distributed.run with one rank per GPU: the slab-decomposed
 run must reproduce the single-context run BIT FOR BIT (coordinates come from global indices, the update is an
-owner-computes gather and the time step is a MIN all-reduce)."""
+owner-computes gather and the time step is an exact MIN), for both transports of SlabAlgorithm:
+  peer  the distributed step of the C ABI (vofx_comm_*): CUDA IPC windows, halo pushes from the update kernel
+  nccl  colour halo exchange + MIN all-reduce over torch.distributed
+eagerly, replayed from a CUDA graph, after a rebalancing of the slabs, and with a host-resident slab."""
 import os
 import sys
 
@@ -17,102 +20,137 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import dune_vof_b200.operators as ops
-    from dune_vof_b200.decomposition import SlabAlgorithm, split_last_axis
+    from dune_vof_b200.decomposition import SlabAlgorithm
 
     failures = []
-    cases = [((48, 40, 64), ops.PROB_LEVEQUE, ops.RECON_YOUNGS, 6), ((32, 32, 48), ops.PROB_SFLOW, ops.RECON_HF, 4),
+
+    def agree(flag):
+        ok = torch.tensor([1 if flag else 0], device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        return int(ok.item()) == 1
+
+    def say(msg):
+        if rank == 0:
+            print(msg, flush=True)
+
+    cases = [((48, 40, 64), ops.PROB_LEVEQUE, ops.RECON_YOUNGS, 8), ((32, 32, 48), ops.PROB_SFLOW, ops.RECON_HF, 4),
              ((64, 96), ops.PROB_SLOTTED_CYLINDER, ops.RECON_HF, 5), ((24, 24, 32), ops.PROB_ROTATING_CIRCLE, ops.RECON_SWARTZ, 2)]
     for n, problem, recon, passes in cases:
         # serial reference on this rank's GPU
         g1 = ops.CartesianGrid(n, device=local)
         g1.set_velocity_builtin(problem)
-        if len(n) == 2 and problem == ops.PROB_SLOTTED_CYLINDER:
-            u1 = g1.init(problem)
-        else:
-            u1 = g1.init(problem)
+        u1 = g1.init(problem)
         u0 = u1.clone()
-        a1 = ops.Algorithm(g1, cfl=0.5, eps=1e-6, reconstruction_kind=recon)
-        st1 = a1.run_passes(u1, passes)
-
-        slab = SlabAlgorithm(n, rank, world, 0.5, 1e-6, recon, device=local)
-        slab.grid.set_velocity_builtin(problem)
-        uh = slab.grid.empty("color")
-        lo, cnt = split_last_axis(n[-1], world, rank)
+        st1 = ops.Algorithm(g1, cfl=0.5, eps=1e-6, reconstruction_kind=recon).run_passes(u1, passes)
         layer = u0.numel() // n[-1]
-        slab.owned(uh).copy_(u0.view(n[-1], layer)[lo:lo + cnt])
-        slab.begin(0.0, 0.0)
-        for _ in range(passes):
-            slab.step(uh)
-        st = slab.state()
-        torch.cuda.synchronize()
-        mine = slab.owned(uh).contiguous()
-        ref = u1.view(n[-1], layer)[lo:lo + cnt]
-        same = torch.equal(mine.view(torch.int64), ref.contiguous().view(torch.int64))
-        ok = torch.tensor([1 if (same and st.time == st1.time and st.dt == st1.dt) else 0], device="cuda")
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        if int(ok.item()) != 1:
-            failures.append((n, problem, recon))
-        if rank == 0:
-            print(f"case n={n} problem={problem} recon={recon}: {'bit-identical' if int(ok.item()) == 1 else 'MISMATCH'} "
-                  f"(time={st.time!r} dt={st.dt!r})", flush=True)
-        # the same passes replayed from a CUDA graph of one captured pass (what bench.py times); Swartz sizes its buffers
-        # from a host read-back and is not capturable
-        if recon != ops.RECON_SWARTZ:
-            slab2 = SlabAlgorithm(n, rank, world, 0.5, 1e-6, recon, device=local)
-            slab2.grid.set_velocity_builtin(problem)
-            u2 = slab2.grid.empty("color")
-            slab2.owned(u2).copy_(u0.view(n[-1], layer)[lo:lo + cnt])
-            side = torch.cuda.Stream()
-            with torch.cuda.stream(side):
-                slab2.grid.use_current_stream()
-                slab2.begin(0.0, 0.0)
-                slab2.step(u2)                                   # first pass eagerly (allocations, NCCL warm-up)
+
+        def reference_slab(slab):
+            lo = sum(slab.layer_counts[:rank])
+            return u1.view(n[-1], layer)[lo:lo + slab.layer_counts[rank]].contiguous()
+
+        def fresh(transport, layers=None):
+            slab = SlabAlgorithm(n, rank, world, 0.5, 1e-6, recon, device=local, transport=transport, layers=layers)
+            slab.set_velocity_builtin(problem)
+            uh = slab.color()
+            uh.zero_()
+            lo = sum(slab.layer_counts[:rank])
+            slab.owned(uh).copy_(u0.view(n[-1], layer)[lo:lo + slab.layer_counts[rank]])
             torch.cuda.synchronize()
-            slab2.capture(u2)
-            for _ in range(passes - 1):
-                slab2.replay()
+            return slab, uh
+
+        for transport in ("peer", "nccl"):
+            slab, uh = fresh(transport)
+            slab.begin(0.0, 0.0)
+            for _ in range(passes):
+                slab.step(uh)
+            st = slab.state()
             torch.cuda.synchronize()
-            st2 = slab2.state()
-            same2 = torch.equal(slab2.owned(u2).contiguous().view(torch.int64), ref.contiguous().view(torch.int64))
-            ok2 = torch.tensor([1 if (same2 and st2.time == st1.time and st2.dt == st1.dt) else 0], device="cuda")
-            dist.all_reduce(ok2, op=dist.ReduceOp.MIN)
-            if int(ok2.item()) != 1:
-                failures.append((n, problem, recon, "graph"))
-            if rank == 0:
-                print(f"   graph replay: {'bit-identical' if int(ok2.item()) == 1 else 'MISMATCH'}", flush=True)
+            same = torch.equal(slab.owned(uh).contiguous().view(torch.int64), reference_slab(slab).view(torch.int64))
+            ok = agree(same and st.time == st1.time and st.dt == st1.dt)
+            if not ok:
+                failures.append((n, problem, recon, transport))
+            say(f"case n={n} problem={problem} recon={recon} [{transport}]: {'bit-identical' if ok else 'MISMATCH'} (time={st.time!r} dt={st.dt!r})")
+            # the same passes replayed from a CUDA graph of one captured pass (what bench.py times); the batched 3D Swartz
+            # pass sizes its buffers from a host read-back and is not capturable
+            if recon != ops.RECON_SWARTZ:
+                slab2, u2 = fresh(transport)
+                side = torch.cuda.Stream()
+                with torch.cuda.stream(side):
+                    slab2.grid.use_current_stream()
+                    slab2.begin(0.0, 0.0)
+                    slab2.step(u2)                                   # first passes eagerly (dense flags, NCCL warm-up)
+                    slab2.step(u2)
+                torch.cuda.synchronize()
+                slab2.capture(u2)
+                for _ in range(passes - 2):
+                    slab2.replay()
+                torch.cuda.synchronize()
+                st2 = slab2.state()
+                same2 = torch.equal(slab2.owned(u2).contiguous().view(torch.int64), reference_slab(slab2).view(torch.int64))
+                ok2 = agree(same2 and st2.time == st1.time and st2.dt == st1.dt)
+                if not ok2:
+                    failures.append((n, problem, recon, transport, "graph"))
+                say(f"   graph replay [{transport}]: {'bit-identical' if ok2 else 'MISMATCH'}")
+                slab2.close()
+            slab.close()
+
+        # rebalancing between two passes: uneven start, cost-weighted split from the flags, migration, continue
+        if recon == ops.RECON_YOUNGS and world == 2:
+            first = max(4, n[-1] // 8)
+            slab3, u3 = fresh("peer", layers=[first, n[-1] - first])
+            slab3.begin(0.0, 0.0)
+            half = passes // 2
+            for _ in range(half):
+                slab3.step(u3)
+            slab4, u4 = slab3.rebalanced(u3, min_gain=0.0)
+            moved = list(slab4.layer_counts) != list(slab3.layer_counts)
+            for _ in range(passes - half):
+                slab4.step(u4)
+            st4 = slab4.state()
+            torch.cuda.synchronize()
+            same4 = torch.equal(slab4.owned(u4).contiguous().view(torch.int64), reference_slab(slab4).view(torch.int64))
+            ok4 = agree(same4 and st4.time == st1.time and st4.dt == st1.dt and moved)
+            if not ok4:
+                failures.append((n, problem, recon, "rebalanced"))
+            say(f"   rebalanced {slab3.layer_counts} -> {slab4.layer_counts}: {'bit-identical' if ok4 else 'MISMATCH'}")
+            if slab4 is not slab3:
+                slab4.close()
+            slab3.close()
+
         # host-resident slab: H2D every pass, changed (cell, value) pairs written back (what bench.py's e2e does for N > 1)
         if recon == ops.RECON_YOUNGS:
             import ctypes as C
             from dune_vof_b200.lib import check
-            slab3 = SlabAlgorithm(n, rank, world, 0.5, 1e-6, recon, device=local)
-            g3 = slab3.grid
-            g3.set_velocity_builtin(problem)
-            u3 = g3.empty("color")
-            own3 = slab3.owned(u3)
-            host = u0.view(n[-1], layer)[lo:lo + cnt].contiguous().cpu().pin_memory()
-            check(g3._L.vofx_track_changes(g3._ctx, 1))
-            slab3.begin(0.0, 0.0)
+            slab5 = SlabAlgorithm(n, rank, world, 0.5, 1e-6, recon, device=local, transport="nccl")
+            g5 = slab5.grid
+            g5.set_velocity_builtin(problem)
+            u5 = g5.empty("color")
+            own5 = slab5.owned(u5)
+            lo = sum(slab5.layer_counts[:rank])
+            host = u0.view(n[-1], layer)[lo:lo + slab5.layer_counts[rank]].contiguous().cpu().pin_memory()
+            check(g5._L.vofx_track_changes(g5._ctx, 1))
+            slab5.begin(0.0, 0.0)
             nchg = C.c_int64(0)
             for _ in range(passes):
-                own3.copy_(host.view_as(own3), non_blocking=True)
-                slab3.step(u3)
-                check(g3._L.vofx_changed_fetch(g3._ctx, C.c_void_p(host.data_ptr()), C.c_int64(-slab3.exchanger.halo * slab3.layer_cells), C.byref(nchg)))
-            same3 = torch.equal(host.view(torch.int64), ref.contiguous().cpu().view(torch.int64))
-            ok3 = torch.tensor([1 if same3 else 0], device="cuda")
-            dist.all_reduce(ok3, op=dist.ReduceOp.MIN)
-            if int(ok3.item()) != 1:
+                own5.copy_(host.view_as(own5), non_blocking=True)
+                slab5.step(u5)
+                check(g5._L.vofx_changed_fetch(g5._ctx, C.c_void_p(host.data_ptr()), C.c_int64(-slab5.exchanger.halo * slab5.layer_cells), C.byref(nchg)))
+            same5 = torch.equal(host.view(torch.int64), reference_slab(slab5).cpu().view(torch.int64))
+            ok5 = agree(same5)
+            if not ok5:
                 failures.append((n, problem, recon, "host slab"))
-            if rank == 0:
-                print(f"   host-resident slab with sparse write-back: {'bit-identical' if int(ok3.item()) == 1 else 'MISMATCH'}", flush=True)
+            say(f"   host-resident slab with sparse write-back: {'bit-identical' if ok5 else 'MISMATCH'}")
+            slab5.close()
         g1.close()
     dist.barrier()
     torch.cuda.synchronize()
     if failures:
         print("MULTIRANK FAILED", failures, flush=True)
-    elif rank == 0:
-        print("MULTIRANK PASSED", flush=True)
+    else:
+        say("MULTIRANK PASSED")
     sys.stdout.flush()
-    os._exit(1 if failures else 0)     # no teardown of captured graphs / communicators
+    dist.destroy_process_group()
+    return 1 if failures else 0
 
 
 if __name__ == "__main__":
