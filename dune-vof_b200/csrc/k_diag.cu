@@ -5,6 +5,7 @@
 // threads, warp shuffles in a fixed pattern, one final block): results are reproducible run to run and independent of
 // the SM schedule; they differ from the reference's sequential sum by round-off only (tests: 1e-12 relative).
 #include "vofx_launch.h"
+#include "vofx_geom2d.cuh"
 
 namespace vofx
 {
@@ -96,10 +97,74 @@ namespace vofx
         out[ 4 ] = v.sum * volume;
       }
     }
+    // circleInterpolation( center, radius, uh ), interpolation/circleinterpolation.hh:140-153: exact area fraction of the disc per cell
+    __global__ void __launch_bounds__( 128 ) k_circle_init ( Grid g, double cx, double cy, double radius, double *__restrict__ u )
+    {
+      for( long long c = blockIdx.x * (long long) blockDim.x + threadIdx.x; c < g.cells; c += (long long) gridDim.x * blockDim.x )
+      {
+        int ijk[ 3 ];
+        cell_ijk( g, c, ijk );
+        if( !in_domain( g, ijk ) )
+        {
+          u[ c ] = 0.0;
+          continue;
+        }
+        Poly2 cell;
+        make_cell( cell_lower( g, 0, ijk[ 0 ] ), cell_lower( g, 1, ijk[ 1 ] ), g.h[ 0 ], g.h[ 1 ], cell );
+        u[ c ] = circle_polygon_volume( cell, cx, cy, radius ) / ( g.h[ 0 ] * g.h[ 1 ] );
+      }
+    }
+
+    // l1error against the exact circle over the OWNED cells: per-cell terms (l1error_circle_cell), fixed summation tree
+    __global__ void __launch_bounds__( kDiagThreads ) k_l1error_circle_partial ( Grid g, const unsigned char *__restrict__ flags, const double *__restrict__ hs,
+                                                                                  double cx, double cy, double radius, Diag *__restrict__ partial )
+    {
+      Diag v = { 0.0, DBL_MAX, -DBL_MAX, 0.0 };
+      const long long layer = g.cells / g.ns[ 1 ];
+      const long long first = layer * g.own0, n = layer * ( g.own1 - g.own0 );
+      for( long long t = blockIdx.x * (long long) blockDim.x + threadIdx.x; t < n; t += (long long) gridDim.x * blockDim.x )
+      {
+        const long long c = first + t;
+        int ijk[ 3 ];
+        cell_ijk( g, c, ijk );
+        const double lox = cell_lower( g, 0, ijk[ 0 ] ), loy = cell_lower( g, 1, ijk[ 1 ] );
+        // the reference clears the reconstructions every pass (modifiedyoungs.hh:65): only mixed cells carry one.  The resident
+        // loop never clears its array, so a stale entry of a cell that is no longer mixed must not be read.
+        const unsigned char f = flags[ c ];
+        const bool mixed = ( f == 1 || f == 2 );
+        const Hs2 h = { mixed ? hs[ 3 * c ] : 0.0, mixed ? hs[ 3 * c + 1 ] : 0.0, mixed ? hs[ 3 * c + 2 ] : 0.0 };
+        v.l1 += l1error_circle_cell( lox, loy, g.h[ 0 ], g.h[ 1 ], h, f == 3, cx, cy, radius );
+      }
+      v = block_reduce( v );
+      if( threadIdx.x == 0 )
+        partial[ blockIdx.x ] = v;
+    }
+
+    __global__ void __launch_bounds__( kDiagThreads ) k_l1error_final ( const Diag *__restrict__ partial, double *__restrict__ out )
+    {
+      Diag v = { 0.0, DBL_MAX, -DBL_MAX, 0.0 };
+      for( int b = threadIdx.x; b < kDiagBlocks; b += kDiagThreads )
+        v = combine( v, partial[ b ] );
+      v = block_reduce( v );
+      if( threadIdx.x == 0 )
+        out[ 0 ] = v.l1;
+    }
   } // namespace
 
   namespace launch
   {
+    void circle_init ( int blocks, cudaStream_t s, Grid g, double cx, double cy, double radius, double *u )
+    { k_circle_init<<< blocks, 128, 0, s >>>( g, cx, cy, radius, u ); }
+
+    double *l1error_circle ( cudaStream_t s, Grid g, const unsigned char *flags, const double *hs, double cx, double cy, double radius, void *scratch )
+    {
+      Diag *partial = static_cast< Diag * >( scratch );
+      double *out = reinterpret_cast< double * >( partial + kDiagBlocks );
+      k_l1error_circle_partial<<< kDiagBlocks, kDiagThreads, 0, s >>>( g, flags, hs, cx, cy, radius, partial );
+      k_l1error_final<<< 1, kDiagThreads, 0, s >>>( partial, out );
+      return out;
+    }
+
     size_t diag_scratch_bytes () { return sizeof( Diag ) * kDiagBlocks + 8 * sizeof( double ); }
 
     // scratch: diag_scratch_bytes() of device memory; the five results are written behind the block partials

@@ -3,6 +3,8 @@
 //   -fmad=false: the parity contract of vofx_math.cuh (no FMA contraction in the device arithmetic).
 #include "../../include/vofx.h"
 
+#include <unistd.h>
+
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -94,6 +96,7 @@ struct vofx_ctx
   size_t windowBytes = 0, slotsOffset = 0;
   CommPeers peers;
   bool commConnected = false;
+  cudaStream_t ownStream = nullptr;   // a distributed context never runs on the legacy default stream (see ensureWindow)
   std::vector< void * > ipcMapped;
   unsigned char *costClass = nullptr;   // per cell: how expensive its plane-constant solve was in the previous step (k_cost_order)
   int *order = nullptr;                 // processing order of the band list for k_youngs_coop3
@@ -118,6 +121,8 @@ struct vofx_ctx
   Velocity *velDev = nullptr;
   std::vector< double * > velTables;
   double *velFaces = nullptr;
+  double *velBandFaces = nullptr;   // vofx_velocity_set_band_faces: grow-only
+  size_t velBandCap = 0;
   bool velocitySet = false;
 
   // staging for the host-buffer variants
@@ -777,8 +782,11 @@ extern "C"
     for( double *t : ctx->velTables )
       cudaFree( t );
     cudaFree( ctx->velFaces );
+    cudaFree( ctx->velBandFaces );
     for( void *m : ctx->ipcMapped )
       cudaIpcCloseMemHandle( m );
+    if( ctx->ownStream )
+      cudaStreamDestroy( ctx->ownStream );
     if( ctx->window )
       cudaFree( ctx->window );        // the resident colour function lives inside the window
     else
@@ -800,6 +808,8 @@ extern "C"
     if( !ctx )
       return fail( VOFX_ERR_ARGUMENT, "null context" );
     ctx->stream = (cudaStream_t) cuda_stream;
+    if( !ctx->stream && ctx->ownStream )
+      ctx->stream = ctx->ownStream;      // distributed contexts keep off the legacy default stream
     return VOFX_OK;
   }
 
@@ -922,6 +932,8 @@ extern "C"
       return rc;
     VOFX_CUDA( cudaMemcpyAsync( ctx->velFaces, v_host, count * sizeof( double ), cudaMemcpyHostToDevice, ctx->stream ) );
     ctx->velHost.faces = ctx->velFaces;
+    ctx->velHost.bandFaces = nullptr;
+    ctx->velHost.bandSlot = nullptr;
     ctx->velocitySet = true;
     return uploadVelocity( ctx );
   }
@@ -1109,6 +1121,53 @@ extern "C"
     VOFX_CUDA( cudaMemcpyAsync( out_host, out, 5 * sizeof( double ), cudaMemcpyDeviceToHost, ctx->stream ) );
     VOFX_CUDA( cudaStreamSynchronize( ctx->stream ) );
     return VOFX_OK;
+  }
+
+  // circleInterpolation on the device (2D), interpolation/circleinterpolation.hh:140-153
+  int vofx_init_circle ( vofx_ctx *ctx, const double *center, double radius, double *u )
+  {
+    if( !ctx || !center || !u )
+      return fail( VOFX_ERR_ARGUMENT, "null argument" );
+    if( ctx->desc.dim != 2 )
+      return fail( VOFX_ERR_ARGUMENT, "circleInterpolation is a 2D initialiser (as in the reference)" );
+    int rc = setDevice( ctx );
+    if( rc )
+      return rc;
+    if( u == ctx->primedU )
+      ctx->primedU = nullptr, ctx->primedFlags = nullptr;
+    profBegin( ctx );
+    launch::circle_init( gridBlocks( ctx, ctx->grid.cells, 128, 16 ), ctx->stream, ctx->grid, center[ 0 ], center[ 1 ], radius, u );
+    return checkLaunch( ctx, "k_circle_init" );
+  }
+
+  // l1error( gridView, reconstructions, flags, RotatingCircle< double, 2 >, time ), test/errors.hh:62-95, over the owned cells
+  int vofx_l1error_circle_device ( vofx_ctx *ctx, const double *halfspaces, const uint8_t *flags, const double *center, double radius, double *error_host )
+  {
+    if( !ctx || !halfspaces || !flags || !center || !error_host )
+      return fail( VOFX_ERR_ARGUMENT, "null argument" );
+    if( ctx->desc.dim != 2 )
+      return fail( VOFX_ERR_ARGUMENT, "the circle error is defined in 2D (as in the reference)" );
+    int rc = setDevice( ctx );
+    if( rc )
+      return rc;
+    if( !ctx->diagScratch )
+      VOFX_CUDA( cudaMalloc( &ctx->diagScratch, launch::diag_scratch_bytes() ) );
+    profBegin( ctx );
+    const double *out = launch::l1error_circle( ctx->stream, ctx->grid, flags, halfspaces, center[ 0 ], center[ 1 ], radius, ctx->diagScratch );
+    ctx->launches += 1;
+    rc = checkLaunch( ctx, "k_l1error_circle" );
+    if( rc )
+      return rc;
+    VOFX_CUDA( cudaMemcpyAsync( error_host, out, sizeof( double ), cudaMemcpyDeviceToHost, ctx->stream ) );
+    VOFX_CUDA( cudaStreamSynchronize( ctx->stream ) );
+    return VOFX_OK;
+  }
+
+  int vofx_l1error_circle ( vofx_ctx *ctx, const double *center, double radius, double *error_host )
+  {
+    if( !ctx || !ctx->dHs || !ctx->dFlags )
+      return fail( VOFX_ERR_STATE, "vofx_l1error_circle reads the flags and reconstructions of the last pass of the context-resident loop" );
+    return vofx_l1error_circle_device( ctx, ctx->dHs, ctx->dFlags, center, radius, error_host );
   }
 
   int vofx_curvature ( vofx_ctx *ctx, const double *u, const double *halfspaces, const uint8_t *flags, double *kappa, uint8_t *valid )
@@ -1307,6 +1366,46 @@ extern "C"
       VOFX_CUDA( cudaStreamSynchronize( ctx->stream ) );
     }
     return VOFX_OK;
+  }
+
+  int vofx_band_list_fetch_in_flight ( vofx_ctx *ctx, int32_t *cells_host, int64_t capacity, int64_t *n_cells )
+  {
+    if( !ctx || !n_cells || ( capacity > 0 && !cells_host ) )
+      return fail( VOFX_ERR_ARGUMENT, "bad argument" );
+    int rc = setDevice( ctx );
+    if( rc )
+      return rc;
+    StepState s;
+    rc = readState( ctx, s );
+    if( rc )
+      return rc;
+    *n_cells = s.mixedCount;
+    const size_t n = (size_t) ( s.mixedCount < capacity ? s.mixedCount : capacity );
+    if( n > 0 )
+    {
+      VOFX_CUDA( cudaMemcpyAsync( cells_host, ctx->mixedList, n * sizeof( int ), cudaMemcpyDeviceToHost, ctx->stream ) );
+      VOFX_CUDA( cudaStreamSynchronize( ctx->stream ) );
+    }
+    return VOFX_OK;
+  }
+
+  int vofx_velocity_set_band_faces ( vofx_ctx *ctx, int64_t n_cells, const double *v_host )
+  {
+    if( !ctx || n_cells < 0 || ( n_cells > 0 && !v_host ) )
+      return fail( VOFX_ERR_ARGUMENT, "bad argument" );
+    int rc = setDevice( ctx );
+    if( rc )
+      return rc;
+    const size_t count = (size_t) n_cells * 2 * ctx->desc.dim * ctx->desc.dim;
+    rc = growDevice( ctx->velBandFaces, ctx->velBandCap, count + 1 );
+    if( rc )
+      return rc;
+    if( count )
+      VOFX_CUDA( cudaMemcpyAsync( ctx->velBandFaces, v_host, count * sizeof( double ), cudaMemcpyHostToDevice, ctx->stream ) );
+    ctx->velHost.bandFaces = ctx->velBandFaces;
+    ctx->velHost.bandSlot = ctx->slot;
+    ctx->velocitySet = true;
+    return uploadVelocity( ctx );
   }
 
   int vofx_step_counters ( vofx_ctx *ctx, int64_t *out )
@@ -1617,6 +1716,13 @@ extern "C"
     VOFX_CUDA( cudaMalloc( &ctx->window, ctx->windowBytes ) );
     VOFX_CUDA( cudaMemset( ctx->window, 0, ctx->windowBytes ) );
     ctx->dU = static_cast< double * >( ctx->window );
+    // the kernels of a distributed pass WAIT for kernels of other contexts: on the legacy default stream, which every
+    // context of a process shares (and which synchronises with all blocking streams), they would wait for ever
+    if( !ctx->stream )
+    {
+      VOFX_CUDA( cudaStreamCreateWithFlags( &ctx->ownStream, cudaStreamNonBlocking ) );
+      ctx->stream = ctx->ownStream;
+    }
     return VOFX_OK;
   }
 
@@ -1685,10 +1791,18 @@ extern "C"
     int rc = ensureWindow( ctx );
     if( rc )
       return rc;
-    static_assert( sizeof( cudaIpcMemHandle_t ) == VOFX_COMM_HANDLE_BYTES, "handle size" );
+    // the handle: cudaIpcMemHandle_t (64 bytes) + process id + the window's address in that process; a rank of the SAME
+    // process (several contexts driven by threads of one process) is connected through the plain pointer -- CUDA IPC
+    // handles cannot be opened by the process that exported them
+    static_assert( sizeof( cudaIpcMemHandle_t ) + 16 == VOFX_COMM_HANDLE_BYTES, "handle size" );
     cudaIpcMemHandle_t h;
     VOFX_CUDA( cudaIpcGetMemHandle( &h, ctx->window ) );
-    std::memcpy( handle, &h, sizeof( h ) );
+    char *out = static_cast< char * >( handle );
+    std::memcpy( out, &h, sizeof( h ) );
+    const long long pid = (long long) getpid();
+    const unsigned long long address = (unsigned long long) reinterpret_cast< uintptr_t >( ctx->window );
+    std::memcpy( out + sizeof( h ), &pid, 8 );
+    std::memcpy( out + sizeof( h ) + 8, &address, 8 );
     return VOFX_OK;
   }
 
@@ -1709,8 +1823,26 @@ extern "C"
         windows[ r ] = ctx->window;
         continue;
       }
+      const char *entry = static_cast< const char * >( handles ) + (size_t) r * VOFX_COMM_HANDLE_BYTES;
       cudaIpcMemHandle_t h;
-      std::memcpy( &h, static_cast< const char * >( handles ) + (size_t) r * VOFX_COMM_HANDLE_BYTES, sizeof( h ) );
+      long long pid = 0;
+      unsigned long long address = 0;
+      std::memcpy( &h, entry, sizeof( h ) );
+      std::memcpy( &pid, entry + sizeof( h ), 8 );
+      std::memcpy( &address, entry + sizeof( h ) + 8, 8 );
+      if( pid == (long long) getpid() )
+      {
+        windows[ r ] = reinterpret_cast< void * >( (uintptr_t) address );     // a context of this process
+        cudaPointerAttributes attr;
+        if( cudaPointerGetAttributes( &attr, windows[ r ] ) == cudaSuccess && attr.device != ctx->device )
+        {
+          const cudaError_t e = cudaDeviceEnablePeerAccess( attr.device, 0 );
+          if( e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled )
+            return fail( VOFX_ERR_CUDA, std::string( "cudaDeviceEnablePeerAccess: " ) + cudaGetErrorString( e ) );
+        }
+        cudaGetLastError();
+        continue;
+      }
       void *p = nullptr;
       VOFX_CUDA( cudaIpcOpenMemHandle( &p, h, cudaIpcMemLazyEnablePeerAccess ) );
       ctx->ipcMapped.push_back( p );
@@ -1812,46 +1944,64 @@ extern "C"
     return VOFX_OK;
   }
 
-  int vofx_step_distributed ( vofx_ctx *ctx, const vofx_step_params *p )
+  int vofx_step_distributed_phase ( vofx_ctx *ctx, const vofx_step_params *p, int phase )
   {
-    if( !ctx || !p )
-      return fail( VOFX_ERR_ARGUMENT, "null argument" );
+    if( !ctx || !p || phase < 0 || phase > 1 )
+      return fail( VOFX_ERR_ARGUMENT, "bad argument" );
     int rc = ensureMirrors( ctx );
     if( !rc && p->with_curvature )
       rc = ensureDevice( ctx->dKappa, (size_t) ctx->grid.cells );
     if( !rc && !ctx->incremental )
       rc = vofx_set_incremental_flagging( ctx, 1 );
-    rc = rc ? rc : requireVelocity( ctx );
     if( rc )
       return rc;
-    if( !ctx->commConnected )
-      return vofx_step( ctx, p, ctx->dU, ctx->dFlags, ctx->dHs, ctx->dKappa );
     double *u = ctx->dU;
     unsigned char *flags = ctx->dFlags;
-    // flags of the layers that depend on owned colour values only, while the neighbours' last pushes are still in flight
-    rc = launchStepFlags( ctx, p, u, flags, 0 );
-    if( rc )
-      return rc;
-    profBegin( ctx );
-    launch::comm_wait_halo( ctx->stream, ctx->peers, ctx->state );
-    rc = checkLaunch( ctx, "k_comm_wait_halo" );
-    rc = rc ? rc : launchStepFlags( ctx, p, u, flags, 1 );
+    if( phase == 0 )
+    {
+      // flags of the layers that depend on owned colour values only, while the neighbours' last pushes are still in flight
+      rc = launchStepFlags( ctx, p, u, flags, 0 );
+      if( rc )
+        return rc;
+      if( ctx->commConnected )
+      {
+        profBegin( ctx );
+        launch::comm_wait_halo( ctx->stream, ctx->peers, ctx->state );
+        rc = checkLaunch( ctx, "k_comm_wait_halo" );
+      }
+      return rc ? rc : launchStepFlags( ctx, p, u, flags, 1 );
+    }
+    rc = requireVelocity( ctx );
     rc = rc ? rc : launchReconstruct( ctx, p->reconstruction, u, flags, ctx->dHs, p->max_iterations );
     if( !rc && p->with_curvature )
       rc = launchCurvature( ctx, u, ctx->dHs, flags, ctx->dKappa, nullptr, true );
     rc = rc ? rc : launchFlux( ctx, ctx->dHs, flags, nullptr, nullptr );
     if( rc )
       return rc;
-    profBegin( ctx );
-    launch::comm_flux_done( ctx->stream, ctx->peers, ctx->state );
-    rc = checkLaunch( ctx, "k_comm_flux_done" );
+    if( ctx->commConnected )
+    {
+      profBegin( ctx );
+      launch::comm_flux_done( ctx->stream, ctx->peers, ctx->state );
+      rc = checkLaunch( ctx, "k_comm_flux_done" );
+    }
     rc = rc ? rc : launchUpdate( ctx, flags, u, true );
     if( rc )
       return rc;
     notePassIssued( ctx, u, flags );
     profBegin( ctx );
-    launch::finalize_dist( ctx->stream, ctx->peers, ctx->state, p->cfl );
-    return checkLaunch( ctx, "k_finalize_dist" );
+    if( ctx->commConnected )
+    {
+      launch::finalize_dist( ctx->stream, ctx->peers, ctx->state, p->cfl );
+      return checkLaunch( ctx, "k_finalize_dist" );
+    }
+    launch::finalize( ctx->stream, ctx->state, p->cfl );
+    return checkLaunch( ctx, "k_finalize" );
+  }
+
+  int vofx_step_distributed ( vofx_ctx *ctx, const vofx_step_params *p )
+  {
+    int rc = vofx_step_distributed_phase( ctx, p, 0 );
+    return rc ? rc : vofx_step_distributed_phase( ctx, p, 1 );
   }
 
   // ---- interface extraction ------------------------------------------------------------------------------------------------

@@ -208,4 +208,140 @@ namespace vofx
     return true;
   }
 
+  // ---- exact circle / polygon overlap (initial data and error of the rotating-circle problem) --------------------------
+  // circleIntersection, interpolation/circleinterpolation.hh:23-72: the points where the segment l0-l1 meets the circle,
+  // ordered along the segment
+  VOFX_HD inline int circle_intersection ( double l0x, double l0y, double l1x, double l1y, double cx, double cy, double r, double *px, double *py )
+  {
+    int np = 0;
+    const double ddx = l1x - l0x, ddy = l1y - l0y;
+    const double nx = -ddy, ny = ddx;                       // generalizedCrossProduct, geometry/utility.hh:82-85
+    const double p = dot2( nx, ny, l0x, l0y );
+    const double d = p - nx * cx - ny * cy;
+    const double nn = dot2( nx, ny, nx, ny );
+    const double diskr = r * r * nn - d * d;
+    if( diskr < 0 )
+      return 0;
+    else if( fabs( diskr ) == 0.0 )
+    {
+      double vx = nx * d, vy = ny * d;
+      vx /= nn; vy /= nn;
+      vx += cx; vy += cy;
+      if( dot2( l0x - vx, l0y - vy, l1x - vx, l1y - vy ) <= 0.0 )
+      {
+        px[ 0 ] = vx; py[ 0 ] = vy;
+        return 1;
+      }
+      return 0;
+    }
+    const double sq = sqrt( diskr );
+    double v1x = nx * d + ny * sq, v1y = ny * d - nx * sq;
+    v1x /= nn; v1y /= nn;
+    v1x += cx; v1y += cy;
+    if( dot2( l0x - v1x, l0y - v1y, l1x - v1x, l1y - v1y ) <= 0.0 )
+    {
+      px[ np ] = v1x; py[ np ] = v1y;
+      np++;
+    }
+    double v2x = nx * d - ny * sq, v2y = ny * d + nx * sq;
+    v2x /= nn; v2y /= nn;
+    v2x += cx; v2y += cy;
+    if( dot2( l0x - v2x, l0y - v2y, l1x - v2x, l1y - v2y ) <= 0.0 )
+    {
+      px[ np ] = v2x; py[ np ] = v2y;
+      np++;
+    }
+    if( np == 2 )
+    {
+      const double ex = px[ 1 ] - px[ 0 ], ey = py[ 1 ] - py[ 0 ];
+      if( dot2( -ey, ex, nx, ny ) < 0 )
+      {
+        const double tx = px[ 0 ], ty = py[ 0 ];
+        px[ 0 ] = px[ 1 ]; py[ 0 ] = py[ 1 ];
+        px[ 1 ] = tx; py[ 1 ] = ty;
+      }
+    }
+    return np;
+  }
+
+  // intersectionVolume( polygon, center, radius ), circleinterpolation.hh:75-138: area of polygon /\ disc (inscribed polygon
+  // + circular segments).  asin / sin are the platform's (CUDA's on the device): within 2 ulp of glibc's, so cut cells
+  // agree with the reference to ~1e-16 absolute, uncut cells exactly.
+  VOFX_HD inline double circle_polygon_volume ( const Poly2 &polygon, double cx, double cy, double radius )
+  {
+    double sx[ 16 ], sy[ 16 ];
+    Poly2 poly;
+    double qx[ 24 ], qy[ 24 ];          // up to 2 intersections + 1 vertex per edge of a polygon with <= 8 vertices
+    int nSec = 0, nPoly = 0;
+    int i = 0, i0 = 0;
+    for( ; i < polygon.n; ++i )
+      if( norm2( polygon.x[ i ] - cx, polygon.y[ i ] - cy ) > radius )
+      {
+        i0 = i;
+        break;
+      }
+    if( i == polygon.n )
+      return poly_volume( polygon );
+    for( int k = 0; k < polygon.n; ++k )
+    {
+      const int e = ( k + i0 ) % polygon.n, e1 = ( e + 1 ) % polygon.n;
+      double px[ 2 ], py[ 2 ];
+      const int np = circle_intersection( polygon.x[ e ], polygon.y[ e ], polygon.x[ e1 ], polygon.y[ e1 ], cx, cy, radius, px, py );
+      for( int q = 0; q < np; ++q )
+      {
+        sx[ nSec ] = px[ q ]; sy[ nSec ] = py[ q ]; nSec++;
+        qx[ nPoly ] = px[ q ]; qy[ nPoly ] = py[ q ]; nPoly++;
+      }
+      if( norm2( polygon.x[ e1 ] - cx, polygon.y[ e1 ] - cy ) < radius )
+      {
+        qx[ nPoly ] = polygon.x[ e1 ]; qy[ nPoly ] = polygon.y[ e1 ]; nPoly++;
+      }
+    }
+    double volume = 0.0;
+    if( nSec > 1 )
+    {
+      if( nPoly > 2 )
+      {
+        // Polygon::volume of the collected points, 2d/polygon.hh:99-106
+        double sum = 0.0;
+        for( int a = 0; a < nPoly; ++a )
+        {
+          const int b = ( a + 1 == nPoly ) ? 0 : a + 1;
+          sum += ( qy[ a ] + qy[ b ] ) * ( qx[ a ] - qx[ b ] );
+        }
+        volume += sum / 2.0;
+      }
+      for( int q = 1; q < nSec; q = q + 2 )
+      {
+        const int q1 = ( q + 1 ) % nSec;
+        const double len = norm2( sx[ q ] - sx[ q1 ], sy[ q ] - sy[ q1 ] );
+        const double alpha = 2.0 * asin( len / ( 2.0 * radius ) );
+        volume += radius * radius / 2.0 * ( alpha - sin( alpha ) );
+      }
+    }
+    (void) poly;
+    return volume;
+  }
+
+  // one cell's term of l1error( gridView, reconstructions, flags, RotatingCircle< double, 2 > ), test/errors.hh:62-95;
+  // exactFraction = the cell's value of circleInterpolation
+  VOFX_HD inline double l1error_circle_cell ( double lox, double loy, double hx, double hy, const Hs2 &hs, bool full, double cx, double cy, double radius )
+  {
+    Poly2 cell;
+    make_cell( lox, loy, hx, hy, cell );
+    const double volume = hx * hy;                                          // geometry().volume() of the grid (include/vofx.h)
+    const double exactFraction = circle_polygon_volume( cell, cx, cy, radius ) / volume;
+    const double T1 = exactFraction * volume;
+    const double T0 = volume - T1;
+    if( !hs_valid( hs ) )
+    {
+      const double c = full ? 1.0 : 0.0;
+      return T0 * fabs( c ) + T1 * fabs( 1.0 - c );
+    }
+    Poly2 one;
+    poly_clip( cell, hs, one );
+    const double shared = circle_polygon_volume( one, cx, cy, radius );
+    return ( T1 - shared ) + ( poly_volume( one ) - shared );
+  }
+
 } // namespace vofx

@@ -100,12 +100,23 @@ namespace vofx
     // general fallback (vofx_velocity_set_faces): velocity sampled by the host functor at every face centre,
     // faces[ ( cell * 2*dim + face ) * dim + component ], frozen at the start-of-step time by the caller
     const double *faces;
+    // the same for the band only (vofx_velocity_set_band_faces): bandFaces[ ( bandSlot[ cell ] * 2*dim + face ) * dim + component ],
+    // bandSlot = position of the cell in the band list of the pass in flight
+    const double *bandFaces;
+    const int *bandSlot;
   };
 
   // velocity at the centre of `face` of the cell with storage multi-index ijk, as that cell's own intersection sees
   // it (Velocity::operator(), velocity.hh:15-20).  v has 3 entries; unused ones are 0.
   VOFX_HD inline void face_velocity ( const Grid &g, const Velocity &vel, const int *ijk, int face, double time, double *v )
   {
+    if( vel.bandFaces )
+    {
+      const long long c = vel.bandSlot[ cell_index( g, ijk ) ];
+      for( int a = 0; a < 3; ++a )
+        v[ a ] = ( a < g.dim ) ? vel.bandFaces[ ( c * 2 * g.dim + face ) * g.dim + a ] : 0.0;
+      return;
+    }
     if( vel.faces )
     {
       const long long c = cell_index( g, ijk );
@@ -146,6 +157,13 @@ namespace vofx
   // ... and use them here: the same operations as face_velocity with det_cospi( time / period ) already evaluated
   VOFX_HD inline void face_velocity_tf ( const Grid &g, const Velocity &vel, const int *ijk, int face, const double *tf, double *v )
   {
+    if( vel.bandFaces )
+    {
+      const long long c = vel.bandSlot[ cell_index( g, ijk ) ];
+      for( int a = 0; a < 3; ++a )
+        v[ a ] = ( a < g.dim ) ? vel.bandFaces[ ( c * 2 * g.dim + face ) * g.dim + a ] : 0.0;
+      return;
+    }
     if( vel.faces )
     {
       const long long c = cell_index( g, ijk );

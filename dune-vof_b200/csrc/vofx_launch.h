@@ -19,6 +19,8 @@ namespace vofx
     // k_diag.cu
     size_t diag_scratch_bytes ();
     double *diagnostics ( cudaStream_t s, long long n, const double *u, const double *exact, double volume, void *scratch );
+    void circle_init ( int blocks, cudaStream_t s, Grid g, double cx, double cy, double radius, double *u );
+    double *l1error_circle ( cudaStream_t s, Grid g, const unsigned char *flags, const double *hs, double cx, double cy, double radius, void *scratch );
     // k_dense.cu
     void flag_rows ( int dim, int blocks, cudaStream_t s, Grid g, const double *u, double eps, unsigned char *flags, int *mixedList, int *slot,
                      int capacity, StepState *state, int compact, int rowsPerBlock, int rowBegin, int rowEnd );

@@ -90,7 +90,7 @@ class SlabAlgorithm:
 
     transport "peer" (default for world > 1): the colour function lives in the context's window, the update kernel stores
     every new boundary value straight into the neighbours' halos over NVLink and the time-step MIN travels through the same
-    peer-mapped windows (vofx_comm_*, include/vofx.h) -- torch.distributed only carries the 64-byte IPC handles at start-up
+    peer-mapped windows (vofx_comm_*, include/vofx.h) -- torch.distributed only carries the 80-byte window handles at start-up
     and the two barriers of begin().  transport "nccl": colour halo exchange (grouped send/recv) and MIN all-reduce per
     pass over torch.distributed on a caller-owned colour tensor (the round-1 path; kept for host-resident colour functions
     and as the fallback where peer mapping is unavailable)."""
@@ -128,7 +128,7 @@ class SlabAlgorithm:
         g = self.grid
         if self.transport == "peer" and world > 1:
             import torch.distributed as dist
-            handle = (C.c_ubyte * 64)()
+            handle = (C.c_ubyte * 80)()
             check(g._L.vofx_comm_export(g._ctx, handle))
             gathered = [None] * world
             dist.all_gather_object(gathered, bytes(handle), group=group)

@@ -25,7 +25,8 @@ SYMBOLS = [
     "vofx_step_state", "vofx_band_list_fetch", "vofx_step_counters", "vofx_step_local", "vofx_step_phase", "vofx_step_finish", "vofx_dt_est_device", "vofx_flag_host",
     "vofx_reconstruct_host", "vofx_evolve_host", "vofx_curvature_host", "vofx_step_host", "vofx_host_transfer_bytes", "vofx_track_changes", "vofx_changed_fetch", "vofx_color_upload",
     "vofx_step_resident", "vofx_color_download", "vofx_comm_export", "vofx_comm_connect", "vofx_comm_connect_local", "vofx_comm_disconnect",
-    "vofx_color_device", "vofx_flags_device", "vofx_halfspaces_device", "vofx_halo_push", "vofx_step_distributed", "vofx_diagnostics", "vofx_interface", "vofx_interface_host", "vofx_interface_fetch", "vofx_init",
+    "vofx_color_device", "vofx_flags_device", "vofx_halfspaces_device", "vofx_halo_push", "vofx_step_distributed", "vofx_step_distributed_phase", "vofx_band_list_fetch_in_flight",
+    "vofx_velocity_set_band_faces", "vofx_diagnostics", "vofx_interface", "vofx_interface_host", "vofx_interface_fetch", "vofx_init", "vofx_init_circle", "vofx_l1error_circle", "vofx_l1error_circle_device",
     "vofx_test_fp64_rate", "vofx_test_arith", "vofx_test_locate", "vofx_test_flux", "vofx_test_interface", "vofx_launch_count", "vofx_profile_enable",
     "vofx_profile_read",
     "vofx_mesh_create", "vofx_mesh_destroy", "vofx_mesh_set_stream", "vofx_mesh_cells", "vofx_mesh_faces", "vofx_mesh_launch_count",
@@ -136,12 +137,18 @@ def load():
         getattr(L, name).restype = C.c_void_p
     L.vofx_halo_push.argtypes = [vp]
     L.vofx_step_distributed.argtypes = [vp, C.POINTER(StepParams)]
+    L.vofx_step_distributed_phase.argtypes = [vp, C.POINTER(StepParams), C.c_int]
+    L.vofx_band_list_fetch_in_flight.argtypes = [vp, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
+    L.vofx_velocity_set_band_faces.argtypes = [vp, C.c_int64, dp]
     L.vofx_curvature_swartz.argtypes = [vp, dp, bp, dp]
     L.vofx_curvature_swartz_host.argtypes = [vp, dp, bp, dp]
     L.vofx_interface.argtypes = [vp, dp, bp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.vofx_interface_host.argtypes = [vp, dp, bp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.vofx_interface_fetch.argtypes = [vp, C.c_void_p, C.c_void_p, C.c_void_p]
     L.vofx_init.argtypes = [vp, C.c_int, C.c_double, dp]
+    L.vofx_init_circle.argtypes = [vp, C.POINTER(C.c_double), C.c_double, dp]
+    L.vofx_l1error_circle.argtypes = [vp, C.POINTER(C.c_double), C.c_double, C.POINTER(C.c_double)]
+    L.vofx_l1error_circle_device.argtypes = [vp, dp, bp, C.POINTER(C.c_double), C.c_double, C.POINTER(C.c_double)]
     L.vofx_diagnostics.argtypes = [vp, dp, dp, C.POINTER(C.c_double)]
     L.vofx_test_fp64_rate.argtypes = [C.POINTER(C.c_double)]
     L.vofx_test_arith.argtypes = [C.c_int64, C.c_uint64, C.POINTER(C.c_int64)]

@@ -289,7 +289,8 @@ class Algorithm:
     """The time loop of algorithm.hh:37-120 on a device-resident colour function (no l1error, no writer).
 
     `reconstruction_kind` selects the operator (the reference hard-wires it in reconstruction.hh); `step()` is one
-    loop pass, fully on the device (time and dt live there); `__call__(uh, start, end)` replays Algorithm::operator()."""
+    loop pass, fully on the device (time and dt live there); `__call__(uh, start, end)` replays Algorithm::operator()
+    and stops at the reference's pass."""
 
     def __init__(self, grid: CartesianGrid, cfl: float, eps: float, reconstruction_kind=RECON_HF, max_iterations=10,
                  with_curvature=False, incremental=False):
@@ -331,15 +332,17 @@ class Algorithm:
         check(g._L.vofx_step_state(g._ctx, C.byref(t), C.byref(dt), C.byref(de), C.byref(m)))
         return StepResult(t.value, dt.value, de.value, m.value)
 
-    def __call__(self, uh, start, end, check_every=16):
-        """do { step } while( time < end ), algorithm.hh:68-95; the loop condition is polled every `check_every` passes
-        (time lives on the device), so up to check_every-1 extra passes may run: use run_passes() for exact replays."""
+    def __call__(self, uh, start, end):
+        """do { pass } while( time < end ), algorithm.hh:68-95: the loop condition is read back after EVERY pass (8 bytes),
+        so the loop stops at exactly the pass the reference stops at and (uh, time, dt) carry its bits; use step() /
+        capture() + replay() for loops whose length is known in advance."""
         self.begin(start, 0.0)
+        self.grid.use_current_stream()
         while True:
-            for _ in range(check_every):
-                self.step(uh)
-            if self.state().time >= end:
-                return self.state()
+            self.step(uh)
+            st = self.state()
+            if st.time >= end:
+                return st
 
     def capture(self, uh):
         """capture one loop pass into a CUDA graph (it only reads device-resident state: time, dt, counters); replay()

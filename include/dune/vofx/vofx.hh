@@ -27,7 +27,9 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <map>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <type_traits>
@@ -52,25 +54,57 @@ namespace Dune
         throw Exception( std::string( "vofx: " ) + vofx_last_error() );
     }
 
+    namespace Impl
+    {
+      // the reference's containers communicate their overlap (dataset.hh:69-81); plain host containers do not
+      template< class DataSet, class = void >
+      struct Communicate
+      {
+        static void apply ( DataSet & ) {}
+      };
+      template< class DataSet >
+      struct Communicate< DataSet, std::void_t< decltype( std::declval< DataSet & >().communicate() ) > >
+      {
+        static void apply ( DataSet &data ) { data.communicate(); }
+      };
+
+      template< class Comm, class = void >
+      struct HasAllgather : std::false_type {};
+      template< class Comm >
+      struct HasAllgather< Comm, std::void_t< decltype( std::declval< const Comm & >().allgather( (char *) nullptr, 1, (char *) nullptr ) ) > > : std::true_type {};
+    } // namespace Impl
+
     // Context
     // -------
-    // The device context of one grid view: the flattened structured grid (include/vofx.h, "Grid convention") and the
-    // permutation between the grid view's index set and the x-fastest lexicographic cell index.
+    // The device context of one grid view: the flattened structured grid (include/vofx.h, "Grid convention") and the map
+    // from the grid view's index set to the storage index of the context (x-fastest lexicographic).
+    //
+    // Parallel grid views (gridView.comm().size() > 1, one GPU per rank): the rank's INTERIOR cells must form a slab of the
+    // global box along the last axis.  The context then owns that slab plus `halo` layers on either side (include/vofx.h,
+    // "multi-GPU"), the ranks' windows are connected through gridView.comm().allgather, and Algorithm steps with
+    // vofx_step_distributed: the kernels exchange halos and the time-step MIN among themselves.  Cells of the grid view's
+    // overlap that lie inside the halo layers are staged like interior cells; results are scattered to interior cells and
+    // the container's own communicate() (dataset.hh:69-81) fills its overlap, as after the reference's operators.
     template< class GV >
     class Context
     {
     public:
       using GridView = GV;
       static constexpr int dim = GridView::dimension;
+      static constexpr std::size_t npos = ~std::size_t( 0 );
 
-      explicit Context ( const GridView &gridView, int device = -1 )
+      explicit Context ( const GridView &gridView, int device = -1, int halo = 4 )
       : gridView_( gridView )
       {
-        // bounding box and mesh width from the cell geometries (the grid must be axis-aligned and uniform)
+        const auto &comm = gridView_.comm();
+        world_ = comm.size();
+        rank_ = comm.rank();
+
+        // bounding box of the interior cells and mesh width from the cell geometries (axis-aligned, uniform)
         double lo[ 3 ] = { 0, 0, 0 }, hi[ 3 ] = { 0, 0, 0 }, h[ 3 ] = { 1, 1, 1 };
         bool first = true;
-        std::size_t count = 0;
-        for( const auto &entity : elements( gridView_ ) )
+        std::size_t interior = 0, all = 0;
+        for( const auto &entity : elements( gridView_, Partitions::interior ) )
         {
           const auto geo = entity.geometry();
           const auto a = geo.corner( 0 );
@@ -87,7 +121,13 @@ namespace Dune
             hi[ d ] = std::max( hi[ d ], double( b[ d ] ) );
           }
           first = false;
-          ++count;
+          ++interior;
+        }
+        double glo[ 3 ], ghi[ 3 ];
+        for( int d = 0; d < 3; ++d )
+        {
+          glo[ d ] = ( world_ > 1 && d < dim ) ? comm.min( lo[ d ] ) : lo[ d ];
+          ghi[ d ] = ( world_ > 1 && d < dim ) ? comm.max( hi[ d ] ) : hi[ d ];
         }
         vofx_grid_desc desc{};
         desc.dim = dim;
@@ -95,89 +135,140 @@ namespace Dune
         for( int d = 0; d < 3; ++d )
         {
           const bool used = d < dim;
-          const int n = used ? int( std::lround( ( hi[ d ] - lo[ d ] ) / h[ d ] ) ) : 1;
-          desc.n_global[ d ] = desc.n_local[ d ] = n;
-          desc.origin[ d ] = used ? lo[ d ] : 0.0;
+          desc.n_global[ d ] = used ? int( std::lround( ( ghi[ d ] - glo[ d ] ) / h[ d ] ) ) : 1;
+          desc.n_local[ d ] = used ? int( std::lround( ( hi[ d ] - lo[ d ] ) / h[ d ] ) ) : 1;
+          desc.lo[ d ] = used ? int( std::lround( ( lo[ d ] - glo[ d ] ) / h[ d ] ) ) : 0;
+          desc.origin[ d ] = used ? glo[ d ] : 0.0;
           desc.h[ d ] = used ? h[ d ] : 1.0;
-          desc.lo[ d ] = 0;
-          cells *= std::size_t( n );
+          cells *= std::size_t( desc.n_local[ d ] );
+          if( used && d != dim - 1 && desc.n_local[ d ] != desc.n_global[ d ] )
+            throw Exception( "vofx: a parallel grid view must be decomposed along the last axis only (slabs)" );
         }
-        desc.halo = 0;
-        if( cells != count )
-          throw Exception( "vofx: the grid view is not a full structured box (only axis-aligned structured grids are supported)" );
+        desc.halo = ( world_ > 1 ) ? halo : 0;
+        if( cells != interior )
+          throw Exception( "vofx: the interior cells of the grid view are not a full structured box (only axis-aligned structured grids are supported)" );
+        if( world_ > 1 && desc.n_local[ dim - 1 ] < desc.halo )
+          throw Exception( "vofx: the slab of this rank is thinner than the halo" );
         desc_ = desc;
+        check( vofx_create( &desc_, device, &ctx_ ) );
+        cells_ = std::size_t( vofx_cells( ctx_ ) );
 
-        // permutation: DUNE index -> lexicographic index (x fastest)
-        toLex_.resize( cells );
-        for( const auto &entity : elements( gridView_ ) )
-        {
+        // map: DUNE index (all partitions) -> storage index; npos for cells outside the context's halo
+        const std::size_t duneCells = std::size_t( gridView_.indexSet().size( 0 ) );
+        toLex_.assign( duneCells, npos );
+        interior_.assign( duneCells, 0 );
+        const int la = dim - 1;
+        auto storageIndex = [ & ] ( const auto &entity ) {
           const auto c = entity.geometry().center();
           std::size_t lex = 0;
           for( int d = dim - 1; d >= 0; --d )
           {
-            const int i = int( std::floor( ( c[ d ] - desc.origin[ d ] ) / desc.h[ d ] ) );
-            lex = lex * std::size_t( desc.n_global[ d ] ) + std::size_t( std::min( std::max( i, 0 ), desc.n_global[ d ] - 1 ) );
+            int i = int( std::floor( ( c[ d ] - desc_.origin[ d ] ) / desc_.h[ d ] ) );
+            i = std::min( std::max( i, 0 ), desc_.n_global[ d ] - 1 );
+            int extent = desc_.n_local[ d ];
+            if( d == la )
+            {
+              i += desc_.halo - desc_.lo[ d ];
+              extent += 2 * desc_.halo;
+              if( i < 0 || i >= extent )
+                return npos;
+            }
+            lex = lex * std::size_t( extent ) + std::size_t( i );
           }
-          toLex_[ gridView_.indexSet().index( entity ) ] = lex;
+          return lex;
+        };
+        for( const auto &entity : elements( gridView_ ) )
+        {
+          toLex_[ gridView_.indexSet().index( entity ) ] = storageIndex( entity );
+          ++all;
         }
-        check( vofx_create( &desc_, device, &ctx_ ) );
+        for( const auto &entity : elements( gridView_, Partitions::interior ) )
+          interior_[ gridView_.indexSet().index( entity ) ] = 1;
+        (void) all;
+
+        if( world_ > 1 )
+          connect();
       }
 
       Context ( const Context & ) = delete;
       Context &operator= ( const Context & ) = delete;
-      ~Context () { vofx_destroy( ctx_ ); }
+      ~Context ()
+      {
+        if( world_ > 1 )
+        {
+          // an exported window must not be freed while another rank still maps it
+          vofx_comm_disconnect( ctx_ );
+          gridView_.comm().barrier();
+        }
+        vofx_destroy( ctx_ );
+      }
 
       vofx_ctx *ctx () const { return ctx_; }
       const GridView &gridView () const { return gridView_; }
       const vofx_grid_desc &desc () const { return desc_; }
-      std::size_t size () const { return toLex_.size(); }
+      std::size_t size () const { return toLex_.size(); }       // cells of the grid view (what the DataSets index)
+      std::size_t cells () const { return cells_; }             // cells of the context's storage (incl. halo layers)
       std::size_t lex ( std::size_t duneIndex ) const { return toLex_[ duneIndex ]; }
+      bool parallel () const { return world_ > 1; }
+      int rank () const { return rank_; }
 
-      // staging buffers in lexicographic order
+      // staging buffers in storage order
       std::vector< double > color, update, kappa, halfspaces, faceVelocity;
       std::vector< std::uint8_t > flags, valid;
+      std::vector< std::int32_t > bandCells;
 
       template< class DataSet >
       void gatherScalars ( const DataSet &data, std::vector< double > &out ) const
       {
-        out.resize( size() );
+        out.assign( cells_, 0.0 );
         for( std::size_t i = 0; i < size(); ++i )
-          out[ toLex_[ i ] ] = data[ i ];
+          if( toLex_[ i ] != npos )
+            out[ toLex_[ i ] ] = data[ i ];
       }
 
+      // results go to the interior cells; the container's communicate() fills its overlap (as after the reference's operators)
       template< class DataSet >
-      void scatterScalars ( const std::vector< double > &in, DataSet &data ) const
+      void scatterScalars ( const std::vector< double > &in, DataSet &data, bool communicate = true ) const
       {
         for( std::size_t i = 0; i < size(); ++i )
-          data[ i ] = in[ toLex_[ i ] ];
+          if( interior_[ i ] )
+            data[ i ] = in[ toLex_[ i ] ];
+        if( communicate && world_ > 1 )
+          Impl::Communicate< DataSet >::apply( data );
       }
 
       // FlagSet::operator[]( Index ) const returns the flag as double (flagset.hh:66): read through begin()
       template< class FlagSet >
       void gatherFlags ( const FlagSet &flagSet )
       {
-        flags.resize( size() );
+        flags.assign( cells_, 0 );
         std::size_t i = 0;
         for( auto it = flagSet.begin(); it != flagSet.end(); ++it, ++i )
-          flags[ toLex_[ i ] ] = std::uint8_t( static_cast< std::size_t >( *it ) );
+          if( toLex_[ i ] != npos )
+            flags[ toLex_[ i ] ] = std::uint8_t( static_cast< std::size_t >( *it ) );
       }
 
       template< class FlagSet >
-      void scatterFlags ( FlagSet &flagSet ) const
+      void scatterFlags ( FlagSet &flagSet, bool communicate = true ) const
       {
         using Flag = typename FlagSet::DataType;
         std::size_t i = 0;
         for( auto it = flagSet.begin(); it != flagSet.end(); ++it, ++i )
-          *it = static_cast< Flag >( static_cast< std::size_t >( flags[ toLex_[ i ] ] ) );
+          if( interior_[ i ] )
+            *it = static_cast< Flag >( static_cast< std::size_t >( flags[ toLex_[ i ] ] ) );
+        if( communicate && world_ > 1 )
+          Impl::Communicate< FlagSet >::apply( flagSet );
       }
 
       template< class ReconstructionSet >
       void gatherReconstructions ( const ReconstructionSet &recs )
       {
-        halfspaces.resize( size() * ( dim + 1 ) );
+        halfspaces.assign( cells_ * ( dim + 1 ), 0.0 );
         std::size_t i = 0;
         for( auto it = recs.begin(); it != recs.end(); ++it, ++i )
         {
+          if( toLex_[ i ] == npos )
+            continue;
           double *hs = halfspaces.data() + toLex_[ i ] * ( dim + 1 );
           for( int d = 0; d < dim; ++d )
             hs[ d ] = it->innerNormal()[ d ];
@@ -186,30 +277,55 @@ namespace Dune
       }
 
       template< class ReconstructionSet >
-      void scatterReconstructions ( ReconstructionSet &recs ) const
+      void scatterReconstructions ( ReconstructionSet &recs, bool communicate = true ) const
       {
         using HalfSpace = typename ReconstructionSet::DataType;
         using Coordinate = typename HalfSpace::Coordinate;
         std::size_t i = 0;
         for( auto it = recs.begin(); it != recs.end(); ++it, ++i )
         {
+          if( !interior_[ i ] )
+            continue;
           const double *hs = halfspaces.data() + toLex_[ i ] * ( dim + 1 );
           Coordinate normal;
           for( int d = 0; d < dim; ++d )
             normal[ d ] = hs[ d ];
           *it = HalfSpace( normal, hs[ dim ] );
         }
+        if( communicate && world_ > 1 )
+          Impl::Communicate< ReconstructionSet >::apply( recs );
+      }
+
+      // centre of `face` (x-,x+,y-,y+,z-,z+) of the storage cell `cell`, by the coordinate formulas of include/vofx.h
+      template< class Coordinate >
+      Coordinate faceCenter ( std::size_t cell, int face ) const
+      {
+        Coordinate x;
+        std::size_t r = cell;
+        for( int d = 0; d < dim; ++d )
+        {
+          const int extent = desc_.n_local[ d ] + ( d == dim - 1 ? 2 * desc_.halo : 0 );
+          const int i = int( r % std::size_t( extent ) ) + desc_.lo[ d ] - ( d == dim - 1 ? desc_.halo : 0 );
+          r /= std::size_t( extent );
+          const double lower = desc_.origin[ d ] + i * desc_.h[ d ];
+          x[ d ] = ( d == ( face >> 1 ) ) ? ( ( face & 1 ) ? lower + desc_.h[ d ] : lower ) : lower + 0.5 * desc_.h[ d ];
+        }
+        return x;
       }
 
       // sample a velocity functor with the reference's concept (bind( intersection ), operator()( local ), unbind();
-      // velocity.hh:15-24) at every face centre and hand it to the device (general fallback of the C ABI)
+      // velocity.hh:15-24) at every face centre of every cell of the grid view and hand it to the device: what the
+      // operator-level Evolution needs, whose caller supplies flags it computed itself.  (Algorithm samples the faces of
+      // the band only, see there.)
       template< class Velocity >
       void setVelocity ( Velocity &velocity )
       {
-        faceVelocity.assign( size() * 2 * dim * dim, 0.0 );
+        faceVelocity.assign( cells_ * 2 * dim * dim, 0.0 );
         for( const auto &entity : elements( gridView_ ) )
         {
           const std::size_t cell = toLex_[ gridView_.indexSet().index( entity ) ];
+          if( cell == npos )
+            continue;
           int face = 0;
           for( const auto &intersection : intersections( gridView_, entity ) )
           {
@@ -230,25 +346,71 @@ namespace Dune
       }
 
     private:
+      void connect ()
+      {
+        const auto &comm = gridView_.comm();
+        using Comm = std::decay_t< decltype( comm ) >;
+        if constexpr ( Impl::HasAllgather< Comm >::value )
+        {
+          std::vector< char > mine( VOFX_COMM_HANDLE_BYTES ), all( std::size_t( VOFX_COMM_HANDLE_BYTES ) * world_ );
+          check( vofx_comm_export( ctx_, mine.data() ) );
+          comm.allgather( mine.data(), VOFX_COMM_HANDLE_BYTES, all.data() );
+          std::vector< std::int32_t > layers( world_ );
+          std::int32_t myLayers = desc_.n_local[ dim - 1 ];
+          comm.allgather( &myLayers, 1, layers.data() );
+          check( vofx_comm_connect( ctx_, rank_, world_, layers.data(), all.data() ) );
+          comm.barrier();
+        }
+        else
+          throw Exception( "vofx: the grid view's communication object has no allgather: cannot connect the ranks' device windows" );
+      }
+
       GridView gridView_;
       vofx_grid_desc desc_;
       vofx_ctx *ctx_ = nullptr;
+      std::size_t cells_ = 0;
+      int world_ = 1, rank_ = 0;
       std::vector< std::size_t > toLex_;
+      std::vector< std::uint8_t > interior_;
+    };
+
+
+    // one context per grid view (keyed by its index set), shared by every operator constructed on it: the reference's
+    // operators are constructed from an eps, a grid view or a stencil set (flagging.hh:30, evolution.hh:26,
+    // modifiedyoungs.hh:48) -- none of which can carry a device context, so it is looked up
+    template< class GV >
+    struct ContextRegistry
+    {
+      static std::shared_ptr< Context< GV > > get ( const GV &gridView, int device = -1 )
+      {
+        static std::mutex mutex;
+        static std::map< const void *, std::weak_ptr< Context< GV > > > contexts;
+        std::unique_lock< std::mutex > lock( mutex );
+        const void *key = static_cast< const void * >( &gridView.indexSet() );
+        auto sp = contexts[ key ].lock();
+        if( sp )
+          return sp;
+        lock.unlock();        // the constructor of a parallel context communicates: never under the lock
+        sp = std::make_shared< Context< GV > >( gridView, device );
+        lock.lock();
+        contexts[ key ] = sp;
+        return sp;
+      }
     };
 
 
     // VertexNeighborsStencil
     // ----------------------
     // In the reference this stores >= 26 entities per cell (stencil/vertexneighborsstencil.hh:29,94-97); on a
-    // structured grid the device derives the neighbours from the index, so the object only owns the device context
-    // that the operators constructed from it share (they take `const StencilSet &`, exactly as in the reference).
+    // structured grid the device derives the neighbours from the index, so the object only holds the device context of
+    // its grid view.
     template< class GV >
     struct VertexNeighborsStencil
     {
       using GridView = GV;
 
       explicit VertexNeighborsStencil ( const GridView &gridView, int device = -1 )
-      : context_( std::make_shared< Context< GridView > >( gridView, device ) )
+      : context_( ContextRegistry< GridView >::get( gridView, device ) )
       {}
 
       const GridView &gridView () const { return context_->gridView(); }
@@ -259,27 +421,30 @@ namespace Dune
     };
 
 
-    // FlagOperator, flagging.hh:24-74
+    // FlagOperator, flagging.hh:24-74.  Constructed from eps alone, as in the reference (flagging.hh:30): the context is
+    // the one of the colour function's grid view.
     template< class GV >
     struct FlagOperator
     {
       using GridView = GV;
 
-      FlagOperator ( const VertexNeighborsStencil< GV > &stencils, double eps ) : context_( &stencils.context() ), eps_( eps ) {}
-      FlagOperator ( Context< GV > &context, double eps ) : context_( &context ), eps_( eps ) {}
+      explicit FlagOperator ( double eps ) : eps_( eps ) {}
+      FlagOperator ( const VertexNeighborsStencil< GV > &stencils, double eps ) : context_( ContextRegistry< GV >::get( stencils.gridView() ) ), eps_( eps ) {}
 
       template< class ColorFunction, class FlagSet >
-      void operator() ( const ColorFunction &color, FlagSet &flags, bool /*communicate*/ = true ) const
+      void operator() ( const ColorFunction &color, FlagSet &flags, bool communicate = true ) const
       {
+        if( !context_ )
+          context_ = ContextRegistry< GV >::get( color.gridView() );
         auto &c = *context_;
         c.gatherScalars( color, c.color );
-        c.flags.resize( c.size() );
+        c.flags.assign( c.cells(), 0 );
         check( vofx_flag_host( c.ctx(), c.color.data(), eps_, c.flags.data() ) );
-        c.scatterFlags( flags );
+        c.scatterFlags( flags, communicate );
       }
 
     private:
-      Context< GV > *context_;
+      mutable std::shared_ptr< Context< GV > > context_;
       const double eps_;
     };
 
@@ -290,25 +455,34 @@ namespace Dune
       struct Reconstruction
       {
         using GridView = GV;
-        using StencilSet = VertexNeighborsStencil< GV >;
 
+        // any stencil set with gridView(): this header's VertexNeighborsStencil or the reference's own
+        // (stencil/vertexneighborsstencil.hh:25-98), whose entity lists are simply not read
+        template< class StencilSet >
         explicit Reconstruction ( const StencilSet &stencils, std::size_t maxIterations = 10 )
-        : context_( &stencils.context() ), maxIterations_( int( maxIterations ) )
+        : context_( ContextRegistry< GV >::get( stencils.gridView() ) ), maxIterations_( int( maxIterations ) )
+        {}
+
+        // ( stencils, initializer[, maxIterations] ) of heightfunction.hh:57-60 / modifiedswartz.hh:54-56: the initial
+        // reconstruction is always modified Young's here (as in the factory, reconstruction.hh:29-37)
+        template< class StencilSet, class Initializer, class = std::enable_if_t< !std::is_integral< Initializer >::value > >
+        Reconstruction ( const StencilSet &stencils, const Initializer &, std::size_t maxIterations = 10 )
+        : context_( ContextRegistry< GV >::get( stencils.gridView() ) ), maxIterations_( int( maxIterations ) )
         {}
 
         template< class ColorFunction, class ReconstructionSet, class Flags >
-        void operator() ( const ColorFunction &color, ReconstructionSet &reconstructions, const Flags &flags, bool /*communicate*/ = true ) const
+        void operator() ( const ColorFunction &color, ReconstructionSet &reconstructions, const Flags &flags, bool communicate = true ) const
         {
           auto &c = *context_;
           c.gatherScalars( color, c.color );
           c.gatherFlags( flags );
-          c.halfspaces.resize( c.size() * ( GV::dimension + 1 ) );
+          c.halfspaces.assign( c.cells() * ( GV::dimension + 1 ), 0.0 );
           check( vofx_reconstruct_host( c.ctx(), kind, c.color.data(), c.flags.data(), c.halfspaces.data(), maxIterations_ ) );
-          c.scatterReconstructions( reconstructions );
+          c.scatterReconstructions( reconstructions, communicate );
         }
 
       protected:
-        Context< GV > *context_;
+        std::shared_ptr< Context< GV > > context_;
         int maxIterations_;
       };
     } // namespace Impl
@@ -343,14 +517,14 @@ namespace Dune
     }
 
 
-    // Evolution, evolution/evolution.hh:37-181
+    // Evolution, evolution/evolution.hh:37-181.  Constructed from the grid view, as in the reference (evolution.hh:48).
     template< class GV >
     struct Evolution
     {
       using GridView = GV;
 
-      explicit Evolution ( const VertexNeighborsStencil< GV > &stencils ) : context_( &stencils.context() ) {}
-      explicit Evolution ( Context< GV > &context ) : context_( &context ) {}
+      explicit Evolution ( const GridView &gridView ) : context_( ContextRegistry< GV >::get( gridView ) ) {}
+      explicit Evolution ( const VertexNeighborsStencil< GV > &stencils ) : context_( ContextRegistry< GV >::get( stencils.gridView() ) ) {}
 
       // velocity: the reference's concept (velocity.hh:5-33), frozen at the start-of-step time by its constructor
       template< class ReconstructionSet, class Flags, class Velocity, class DiscreteFunction >
@@ -360,18 +534,25 @@ namespace Dune
         c.setVelocity( velocity );
         c.gatherReconstructions( reconstructions );
         c.gatherFlags( flags );
-        c.update.resize( c.size() );
+        c.update.assign( c.cells(), 0.0 );
         double dtEst = 0.0;
         check( vofx_evolve_host( c.ctx(), c.halfspaces.data(), c.flags.data(), 0.0, deltaT, c.update.data(), &dtEst ) );
+        // update.communicate( All_All_Interface, Add ) of evolution.hh:73 is not needed: every rank gathers the complete update of
+        // its interior cells (owner-computes); the overlap copies are refreshed instead
         c.scatterScalars( c.update, update );
-        return dtEst;
+        return c.parallel() ? c.gridView().comm().min( dtEst ) : dtEst;     // evolution.hh:75
       }
 
     private:
-      Context< GV > *context_;
+      std::shared_ptr< Context< GV > > context_;
     };
 
-    // evolution.hh:25-30 (takes the stencil set instead of the grid view: it carries the device context)
+    // evolution.hh:25-30
+    template< class GV >
+    static inline Evolution< GV > evolution ( const GV &gridView )
+    {
+      return Evolution< GV >( gridView );
+    }
     template< class GV >
     static inline Evolution< GV > evolution ( const VertexNeighborsStencil< GV > &stencils )
     {
@@ -385,27 +566,27 @@ namespace Dune
     {
       using GridView = GV;
 
-      explicit CartesianHeightFunctionCurvature ( const VNST &stencils ) : context_( &stencils.context() ) {}
+      explicit CartesianHeightFunctionCurvature ( const VNST &stencils ) : context_( ContextRegistry< GV >::get( stencils.gridView() ) ) {}
 
       template< class ColorFunction, class ReconstructionSet, class Flags, class CurvatureSet >
       void operator() ( const ColorFunction &color, const ReconstructionSet &reconstructions, const Flags &flags, CurvatureSet &curvature,
-                        bool /*communicate*/ = true ) const
+                        bool communicate = true ) const
       {
         auto &c = *context_;
         c.gatherScalars( color, c.color );
         c.gatherReconstructions( reconstructions );
         c.gatherFlags( flags );
-        c.kappa.resize( c.size() );
-        c.valid.resize( c.size() );
+        c.kappa.assign( c.cells(), 0.0 );
+        c.valid.assign( c.cells(), 0 );
         check( vofx_curvature_host( c.ctx(), c.color.data(), c.halfspaces.data(), c.flags.data(), c.kappa.data(), c.valid.data() ) );
-        c.scatterScalars( c.kappa, curvature );
+        c.scatterScalars( c.kappa, curvature, communicate );
       }
 
-      // satisfiesConstraint_ of the last call (heightfunction.hh:286), lexicographic order
+      // satisfiesConstraint_ of the last call (heightfunction.hh:286), storage order
       const std::vector< std::uint8_t > &satisfiesConstraint () const { return context_->valid; }
 
     private:
-      Context< GV > *context_;
+      std::shared_ptr< Context< GV > > context_;
     };
 
 
@@ -426,7 +607,7 @@ namespace Dune
         auto &c = stencils_.context();
         c.gatherReconstructions( reconstructions );
         c.gatherFlags( flags );
-        c.kappa.resize( c.size() );
+        c.kappa.assign( c.cells(), 0.0 );
         check( vofx_curvature_swartz_host( c.ctx(), c.halfspaces.data(), c.flags.data(), c.kappa.data() ) );
         c.scatterScalars( c.kappa, curvatureSet );
       }
@@ -479,6 +660,30 @@ namespace Dune
       {
         static bool apply ( DW &writer, double time ) { return writer.willWrite( time ); }
       };
+
+      // l1error( gridView, reconstructions, flags, problem, time ) of test/errors.hh: evaluated on the device for problems
+      // whose exact interface is a circle ( center( t ), radius( t ): RotatingCircle< double, 2 >, errors.hh:62-95 ) from the
+      // flags and reconstructions of the pass that just ran; 0 for every other problem (the quadrature variant,
+      // errors.hh:27-58, needs dune-geometry's rules and stays on the host)
+      template< class Problem, int dim, class = void >
+      struct L1Error
+      {
+        template< class Ctx >
+        static double apply ( Ctx &, const Problem &, double ) { return 0.0; }
+      };
+      template< class Problem >
+      struct L1Error< Problem, 2, std::void_t< decltype( std::declval< const Problem & >().center( 0.0 ) ), decltype( std::declval< const Problem & >().radius( 0.0 ) ) > >
+      {
+        template< class Ctx >
+        static double apply ( Ctx &c, const Problem &problem, double time )
+        {
+          const auto center = problem.center( time );
+          const double xy[ 2 ] = { double( center[ 0 ] ), double( center[ 1 ] ) };
+          double error = 0.0;
+          check( vofx_l1error_circle( c.ctx(), xy, double( problem.radius( time ) ), &error ) );
+          return error;
+        }
+      };
     } // namespace Impl
 
     template< class GV, class PR, class DW >
@@ -488,20 +693,26 @@ namespace Dune
       using Problem = PR;
       using DataWriter = DW;
       using Stencils = VertexNeighborsStencil< GridView >;
+      static constexpr int dim = GridView::dimension;
 
+      // the reference's signature (algorithm.hh:46) plus two optional arguments: the reconstruction (the reference
+      // hard-wires the factory's height functions, reconstruction.hh:29-37) and a built-in velocity (enum vofx_problem)
       Algorithm ( const GridView &gridView, const Problem &problem, DataWriter &dataWriter, double cfl, double eps, const bool verbose = false,
                   int reconstruction = VOFX_RECON_HF, int builtinVelocity = -1 )
       : gridView_( gridView ), problem_( problem ), dataWriter_( dataWriter ), cfl_( cfl ), eps_( eps ), verbose_( verbose ),
         stencils_( gridView ), reconstruction_( reconstruction ), builtinVelocity_( builtinVelocity )
       {}
 
-      // builtinVelocity >= 0 (enum vofx_problem): the separable device tables are used and time lives on the device;
-      // otherwise problem.velocityField is sampled on the host at every face each step (general, slower).
+      // builtinVelocity >= 0: the separable device tables are used.  Otherwise problem.velocityField (what the reference's
+      // Velocity< Problem, GridView > evaluates, velocity.hh:15-20) is sampled on the host at the face centres of the
+      // MIXED cells of each pass only: the pass is issued in two halves (flags | everything else) and the band list is
+      // read back in between -- 2*dim*dim doubles per mixed cell travel to the device instead of per cell of the grid.
+      // Returns the accumulated dt * l1error of the reference (algorithm.hh:85-98) for problems with an exact interface
+      // the device knows (RotatingCircle< double, 2 >: circle.center( t ), circle.radius( t )), else 0.
       template< class ColorFunction >
       double operator() ( ColorFunction &uh, double start, double end, int /*level*/ = 0 )
       {
         auto &c = stencils_.context();
-        const std::size_t N = c.size();
         vofx_step_params params{};
         params.reconstruction = reconstruction_;
         params.max_iterations = 10;
@@ -512,20 +723,26 @@ namespace Dune
           check( vofx_velocity_builtin( c.ctx(), builtinVelocity_ ) );
 
         c.gatherScalars( uh, c.color );
-        c.flags.resize( N );
         check( vofx_color_upload( c.ctx(), c.color.data() ) );
-        double time = start, dt = 0.0, dtEst = 0.0;
+        double time = start, dt = 0.0, dtEst = 0.0, error = 0.0;
         check( vofx_step_begin( c.ctx(), time, dt ) );
+        if( c.parallel() )
+        {
+          // the halo layers of the device copies are filled from the neighbours' interior values: two barriers per run
+          gridView_.comm().barrier();
+          check( vofx_halo_push( c.ctx() ) );
+          gridView_.comm().barrier();
+        }
         do
         {
+          check( vofx_step_distributed_phase( c.ctx(), &params, 0 ) );          // flagOperator( uh, flags_ ), algorithm.hh:75
           if( builtinVelocity_ < 0 )
-          {
-            HostVelocity velocity( problem_, time );
-            c.setVelocity( velocity );
-          }
-          // one loop pass, algorithm.hh:75-93, entirely on the device-resident colour function
-          check( vofx_step_resident( c.ctx(), &params ) );
+            sampleBandVelocity( c, time );                                       // VelocityField velocity( problem_, time ), :73
+          check( vofx_step_distributed_phase( c.ctx(), &params, 1 ) );          // reconstruction, evolution, axpy, :78-83
+          const double passTime = time, passDt = dt;
           check( vofx_step_state( c.ctx(), &time, &dt, &dtEst, nullptr ) );
+          if( passDt > 0.0 )
+            error += passDt * Impl::L1Error< Problem, dim >::apply( c, problem_, passTime );      // :85-89
           if( Impl::WillWrite< DataWriter >::apply( dataWriter_, time ) )
           {
             check( vofx_color_download( c.ctx(), c.color.data(), nullptr ) );
@@ -534,30 +751,35 @@ namespace Dune
           }
         }
         while( time < end );
+        if( time == start )
+          error += Impl::L1Error< Problem, dim >::apply( c, problem_, time );                     // :97-98
+        c.flags.assign( c.cells(), 0 );
         check( vofx_color_download( c.ctx(), c.color.data(), c.flags.data() ) );
         c.scatterScalars( c.color, uh );
-        return 0.0;   // the reference returns the accumulated l1 error (diagnostic, test/errors.hh); not part of the hot path
+        return c.parallel() ? gridView_.comm().sum( error ) : error;
       }
 
     private:
-      // Velocity< Problem, GridView > of velocity.hh:5-33
-      struct HostVelocity
+      void sampleBandVelocity ( Context< GridView > &c, double time )
       {
-        using Intersection = typename GridView::Intersection;
-        HostVelocity ( const Problem &problem, double time ) : problem_( &problem ), time_( time ) {}
-        template< class Local >
-        auto operator() ( const Local &local ) const
-        {
-          typename Problem::DomainType v( 0.0 );
-          problem_->velocityField( intersection_->geometry().global( local ), time_, v );
-          return v;
-        }
-        void bind ( const Intersection &intersection ) { intersection_ = &intersection; }
-        void unbind () { intersection_ = nullptr; }
-        const Intersection *intersection_ = nullptr;
-        const Problem *problem_;
-        double time_;
-      };
+        using Domain = typename Problem::DomainType;
+        std::int64_t n = 0;
+        check( vofx_band_list_fetch_in_flight( c.ctx(), nullptr, 0, &n ) );
+        c.bandCells.resize( std::size_t( n ) + 1 );
+        if( n > 0 )
+          check( vofx_band_list_fetch_in_flight( c.ctx(), c.bandCells.data(), n, &n ) );
+        c.faceVelocity.assign( std::size_t( n ) * 2 * dim * dim + 1, 0.0 );
+        for( std::int64_t i = 0; i < n; ++i )
+          for( int face = 0; face < 2 * dim; ++face )
+          {
+            const Domain x = c.template faceCenter< Domain >( std::size_t( c.bandCells[ std::size_t( i ) ] ), face );
+            Domain v( 0.0 );
+            problem_.velocityField( x, time, v );
+            for( int d = 0; d < dim; ++d )
+              c.faceVelocity[ ( std::size_t( i ) * 2 * dim + face ) * dim + d ] = v[ d ];
+          }
+        check( vofx_velocity_set_band_faces( c.ctx(), n, c.faceVelocity.data() ) );
+      }
 
       const GridView &gridView_;
       const Problem &problem_;

@@ -228,8 +228,10 @@ int vofx_color_download ( vofx_ctx *ctx, double *u_host, uint8_t *flags_host /* 
  * vofx_step_begin -> [host barrier] -> vofx_halo_push -> [host barrier] -> vofx_step_distributed ... (no host
  * communication per pass; the pass is graph-capturable) -> vofx_color_download.
  * Results are bit-identical to the single-context run: coordinates come from global indices, MIN is exact. */
-#define VOFX_COMM_HANDLE_BYTES 64
-/* allocates the window (must precede any use of the context-resident colour function) and returns its cudaIpcMemHandle_t */
+#define VOFX_COMM_HANDLE_BYTES 80
+/* allocates the window (must precede any use of the context-resident colour function) and returns its handle: the
+ * cudaIpcMemHandle_t, the exporting process's id and the window's address there (ranks that are threads of one process
+ * are connected through the address; peer access between their devices must be possible) */
 int vofx_comm_export ( vofx_ctx *ctx, void *handle /* VOFX_COMM_HANDLE_BYTES */ );
 /* layers[ r ] = owned layers of rank r along the last axis; handles = world * VOFX_COMM_HANDLE_BYTES bytes in rank order
  * (the entry of `rank` itself is ignored) */
@@ -247,6 +249,14 @@ double *vofx_halfspaces_device ( vofx_ctx *ctx );
 int vofx_halo_push ( vofx_ctx *ctx );
 /* one loop pass of the distributed run on the context-resident colour function (vofx_step_resident when not connected) */
 int vofx_step_distributed ( vofx_ctx *ctx, const vofx_step_params *params );
+/* the same pass in two calls: phase 0 = flags and band list, phase 1 = everything else.  In between a driver whose
+ * velocity is an arbitrary HOST functor (Velocity< Problem, GridView >, velocity.hh:5-33) samples it on the faces of the
+ * band only: vofx_band_list_fetch_in_flight returns the storage indices of the pass's mixed cells, and
+ * vofx_velocity_set_band_faces takes v_host[ ( i * 2*dim + face ) * dim + component ] for the i-th of them (HOST
+ * pointer, copied) -- 6 x 3 doubles per mixed cell instead of per cell of the grid (vofx_velocity_set_faces). */
+int vofx_step_distributed_phase ( vofx_ctx *ctx, const vofx_step_params *params, int phase );
+int vofx_band_list_fetch_in_flight ( vofx_ctx *ctx, int32_t *cells_host, int64_t capacity, int64_t *n_cells );
+int vofx_velocity_set_band_faces ( vofx_ctx *ctx, int64_t n_cells, const double *v_host );
 
 /* ---- interface extraction (replaces getInterfaceVertices, utility.hh:19-48, and MixedCellMapper::update,
  * mixedcellmapper.hh:82-86): the owned mixed cells in ascending cell index, and for the i-th of them the vertices of
@@ -269,6 +279,16 @@ int vofx_diagnostics ( vofx_ctx *ctx, const double *u, const double *u_exact /* 
 /* ---- initial data on the device (replaces Average< Problem >, test/average.hh:28-54, i.e.
  * RecursiveInterpolationCube depth 3, interpolation/recursiveinterpolationcube.hh:33-82, for the built-in problems) */
 int vofx_init ( vofx_ctx *ctx, int problem, double time, double *u );
+/* circleInterpolation( center, radius, uh ), interpolation/circleinterpolation.hh:75-153 (2D): the exact area fraction of the
+ * disc in every cell -- the initialiser of RotatingCircle< double, 2 > (test/average.hh:82-101, configs[0]).  asin / sin are
+ * CUDA's: cells cut by the circle agree with the host's glibc to ~1e-16, all others exactly. */
+int vofx_init_circle ( vofx_ctx *ctx, const double *center /* [2], host */, double radius, double *u );
+/* l1error( gridView, reconstructions, flags, RotatingCircle< double, 2 >, time ), test/errors.hh:62-95, summed over the owned
+ * cells on the device (fixed summation tree): |exact disc /\ cell  symmetric-difference  reconstructed fluid part|.
+ * vofx_l1error_circle reads the flags / reconstructions the last pass of the context-resident loop left behind (what
+ * Algorithm::operator() accumulates as dt * l1error, algorithm.hh:85-89); the _device variant takes DEVICE arrays. */
+int vofx_l1error_circle ( vofx_ctx *ctx, const double *center, double radius, double *error_host );
+int vofx_l1error_circle_device ( vofx_ctx *ctx, const double *halfspaces, const uint8_t *flags, const double *center, double radius, double *error_host );
 
 /* ---- geometry primitives on single cells (DEVICE work on small batches; for parity tests) ---------------------
  * arrays are HOST pointers of `count` items: lo[count*dim], h[count*dim], ... */

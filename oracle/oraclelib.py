@@ -46,6 +46,8 @@ def lib():
         L.vo_curvature.argtypes = [G, _dp, _dp, _bp, _dp, _bp]
         L.vo_curvature_swartz.argtypes = [G, _dp, _bp, _dp]
         L.vo_init.argtypes = [G, C.c_int, C.c_double, _dp]
+        L.vo_circle_interpolation.argtypes = [G, _dp, C.c_double, _dp]
+        L.vo_l1error_circle.argtypes = [G, _dp, _bp, _dp, C.c_double, _dp]
         L.vo_face_velocity.argtypes = [G, C.c_int, C.c_double, C.c_int64, C.c_int, _dp]
         L.vo_run.argtypes = [G, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, _dp, _dp, _dp, _dp,
                              C.POINTER(C.c_int64)]
@@ -135,6 +137,22 @@ class OracleGrid:
         kappa = np.empty(self.cells, dtype=np.float64)
         _check(lib().vo_curvature_swartz(C.byref(self._g), _d(hs), _b(flags), _d(kappa)), "curvature_swartz")
         return kappa
+
+    def circle_interpolation(self, center, radius):
+        """circleInterpolation (2D), interpolation/circleinterpolation.hh:140-153"""
+        u = np.empty(self.cells, dtype=np.float64)
+        c = _vec(center)
+        _check(lib().vo_circle_interpolation(C.byref(self._g), _d(c), float(radius), _d(u)), "circle_interpolation")
+        return u
+
+    def l1error_circle(self, hs, flags, center, radius):
+        """l1error against the exact circle (2D), test/errors.hh:62-95"""
+        hs = _vec(hs)
+        flags = np.ascontiguousarray(flags, dtype=np.uint8)
+        c = _vec(center)
+        out = C.c_double(0.0)
+        _check(lib().vo_l1error_circle(C.byref(self._g), _d(hs), _b(flags), _d(c), float(radius), C.byref(out)), "l1error_circle")
+        return out.value
 
     def init(self, problem, time=0.0):
         u = np.empty(self.cells, dtype=np.float64)

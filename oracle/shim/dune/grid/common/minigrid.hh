@@ -170,6 +170,8 @@ namespace Dune
     template< class T > T sum ( T x ) const { return x; }
     int rank () const { return 0; }
     int size () const { return 1; }
+    void barrier () const {}
+    template< class T > void allgather ( const T *in, int count, T *out ) const { std::copy( in, in + count, out ); }
   };
 
   // --- the SPGrid internals that stencil/heightfunctionstencil.hh:28-30,55-66 reaches into ------------------

@@ -2828,6 +2828,67 @@ int vo_curvature_swartz ( const vo_grid *g, const double *hs, const uint8_t *fla
   return 0;
 }
 
+/* circleInterpolation( center, radius, uh ), interpolation/circleinterpolation.hh:140-153 (2D) */
+int vo_circle_interpolation ( const vo_grid *g, const double *center, double radius, double *u )
+{
+  if( g->dim != 2 )
+    return 1;
+  const int64_t N = grid_cells( g );
+  for( int64_t c = 0; c < N; ++c )
+  {
+    int ijk[ 3 ];
+    double lo[ 3 ];
+    vo_polygon p;
+    cell_ijk( g, c, ijk );
+    cell_lower( g, ijk, lo );
+    make_polygon_cell( lo, g->h, &p );
+    u[ c ] = circle_polygon_volume( &p, center, radius ) / cell_volume( g );
+  }
+  return 0;
+}
+
+/* l1error( gridView, reconstructionSet, flags, RotatingCircle< double, 2 > circle, time ), test/errors.hh:62-95, with
+ * center = circle.center( time ), radius = circle.radius( time ).  hs: zero half-space = no reconstruction (the reference's
+ * reconstruction set is cleared every pass, so only mixed cells carry one: entries of other cells are ignored here).
+ * errors.hh itself cannot be compiled here (it includes dune-geometry's quadrature rules): the loop is restated, the
+ * primitives it calls (intersect, intersectionVolume, Polygon::volume) are the pinned ones above. */
+int vo_l1error_circle ( const vo_grid *g, const double *hs, const uint8_t *flags, const double *center, double radius, double *error )
+{
+  if( g->dim != 2 )
+    return 1;
+  const int64_t N = grid_cells( g );
+  double l1 = 0.0;
+  for( int64_t c = 0; c < N; ++c )
+  {
+    int ijk[ 3 ];
+    double lo[ 3 ];
+    vo_polygon p;
+    cell_ijk( g, c, ijk );
+    cell_lower( g, ijk, lo );
+    make_polygon_cell( lo, g->h, &p );
+    const double volume = cell_volume( g );
+    const double exact = circle_polygon_volume( &p, center, radius ) / cell_volume( g );
+    const double T1 = exact * volume;
+    const double T0 = volume - T1;
+    const int mixed = ( flags[ c ] == 1 || flags[ c ] == 2 );
+    const double *h = hs + 3 * c;
+    if( !mixed || !( h[ 0 ] * h[ 0 ] + h[ 1 ] * h[ 1 ] > 0.5 ) )
+    {
+      const double cc = ( flags[ c ] == 3 ) ? 1.0 : 0.0;
+      l1 += T0 * fabs( cc ) + T1 * fabs( 1.0 - cc );
+    }
+    else
+    {
+      vo_polygon one;
+      polygon_clip( &p, h, &one );
+      const double shared = circle_polygon_volume( &one, center, radius );
+      l1 += ( T1 - shared ) + ( polygon_volume( &one ) - shared );
+    }
+  }
+  *error = l1;
+  return 0;
+}
+
 int vo_init ( const vo_grid *g, int problem, double time, double *u )
 {
   const int dim = g->dim;

@@ -39,6 +39,8 @@ int vo_evolve ( const vo_grid *g, const double *hs, const uint8_t *flags, int pr
 int vo_curvature ( const vo_grid *g, const double *u, const double *hs, const uint8_t *flags, double *kappa, uint8_t *valid );
 int vo_curvature_swartz ( const vo_grid *g, const double *hs, const uint8_t *flags, double *kappa );   /* 2D; curvature/swartzcurvature.hh:41-173 */
 int vo_init ( const vo_grid *g, int problem, double time, double *u );
+int vo_circle_interpolation ( const vo_grid *g, const double *center, double radius, double *u );   /* interpolation/circleinterpolation.hh:140-153 */
+int vo_l1error_circle ( const vo_grid *g, const double *hs, const uint8_t *flags, const double *center, double radius, double *error );   /* test/errors.hh:62-95 */
 int vo_face_velocity ( const vo_grid *g, int problem, double time, int64_t cell, int face, double *v );
 int vo_run ( const vo_grid *g, int kind, int problem, double eps, double cfl, int max_iterations, int passes,
              double *u, double *time_io, double *dt_io, double *phase_seconds, int64_t *mixed_cell_steps );

@@ -123,6 +123,27 @@ namespace
     }
   };
 
+  // RotatingCircle< double, 2 > of test/problems/rotatingcircle.hh:22-57: velocity field, centre and radius of the exact solution
+  struct RotatingCircle2
+  {
+    using DomainType = Dune::FieldVector< double, 2 >;
+    void velocityField ( const DomainType &x, const double, DomainType &r ) const
+    {
+      r[ 0 ] = x[ 1 ] - 0.5;
+      r[ 1 ] = 0.5 - x[ 0 ];
+      r *= 2 * M_PI / 10;
+    }
+    DomainType center ( double t ) const
+    {
+      DomainType c{ 0.5, 0.5 };
+      const DomainType offset{ 0.0, 0.25 }, normal{ 0.25, 0.0 };
+      c.axpy( std::cos( ( 2 * M_PI / 10 ) * t ), offset );
+      c.axpy( std::sin( ( 2 * M_PI / 10 ) * t ), normal );
+      return c;
+    }
+    double radius ( double ) const { return 0.15; }
+  };
+
   struct NullWriter
   {
     int writes = 0;
@@ -199,10 +220,12 @@ namespace
     vo_init( &og, oracleProblem, 0.0, u0.data() );
 
     // --- operator by operator, as algorithm.hh:57-83 does ---
+    // the reference's own construction lines (algorithm.hh:57-59, test-vof-consistence.cc:155-158) with the namespace changed:
+    //   auto flagOperator = FlagOperator< GridView >( eps_ );   auto evolutionOperator = evolution( gridView_ );
     Dune::VoFx::VertexNeighborsStencil< GV > stencils( gv );
-    Dune::VoFx::FlagOperator< GV > flagOperator( stencils, eps );
-    Dune::VoFx::ModifiedYoungsReconstruction< GV > reconstructionOperator( stencils );
-    auto evolutionOperator = Dune::VoFx::evolution( stencils );
+    auto flagOperator = Dune::VoFx::FlagOperator< GV >( eps );
+    Dune::VoFx::ModifiedYoungsReconstruction< GV, Dune::VoFx::VertexNeighborsStencil< GV > > reconstructionOperator( stencils );
+    auto evolutionOperator = Dune::VoFx::evolution( gv );
 
     ColorFunction< GV > uh( gv ), update( gv );
     FlagSet< GV > flags( gv );
@@ -351,10 +374,76 @@ namespace
 
 } // namespace
 
+  // Algorithm::operator() returns the accumulated dt * l1error( ..., problem, time ) (algorithm.hh:85-98) for the rotating circle
+  void runCircleError ()
+  {
+    using GV = Dune::MiniGridView< 2 >;
+    Dune::MiniGrid< 2 > grid;
+    const int n = 64;
+    vo_grid og;
+    std::memset( &og, 0, sizeof( og ) );
+    og.dim = 2;
+    og.n[ 0 ] = og.n[ 1 ] = n;
+    og.n[ 2 ] = 1;
+    og.h[ 0 ] = og.h[ 1 ] = 1.0 / n;
+    og.h[ 2 ] = 1.0;
+    for( int d = 0; d < 2; ++d )
+    {
+      grid.n[ d ] = n;
+      grid.lo[ d ] = 0.0;
+      grid.h[ d ] = 1.0 / n;
+    }
+    GV gv( grid );
+    const std::size_t N = grid.cells();
+    RotatingCircle2 problem;
+    std::vector< double > uo( N ), hso( N * 3 ), updo( N );
+    std::vector< std::uint8_t > flo( N );
+    const double c0[ 2 ] = { 0.5, 0.75 };
+    vo_circle_interpolation( &og, c0, 0.15, uo.data() );
+    ColorFunction< GV > uh( gv );
+    for( std::size_t i = 0; i < N; ++i )
+      uh[ i ] = uo[ i ];
+    // the reference's loop with its error accumulation, on the oracle (HF reconstruction: the factory's default)
+    double time = 0.0, dt = 0.0, dtEst = 0.0, error = 0.0;
+    const double end = 0.2;
+    do
+    {
+      vo_flag( &og, uo.data(), 1e-6, flo.data() );
+      vo_reconstruct( &og, VO_RECON_HF, uo.data(), flo.data(), hso.data(), 10 );
+      vo_evolve( &og, hso.data(), flo.data(), VO_PROB_ROTATING_CIRCLE, time, dt, updo.data(), &dtEst );
+      for( std::size_t i = 0; i < N; ++i )
+        uo[ i ] += 1.0 * updo[ i ];
+      if( dt > 0.0 )
+      {
+        const auto c = problem.center( time );
+        const double cc[ 2 ] = { c[ 0 ], c[ 1 ] };
+        double e = 0.0;
+        vo_l1error_circle( &og, hso.data(), flo.data(), cc, 0.15, &e );
+        error += dt * e;
+        time += dt;
+      }
+      dt = dtEst * 0.5;
+    }
+    while( time < end );
+    NullWriter writer;
+    Dune::VoFx::Algorithm< GV, RotatingCircle2, NullWriter > algorithm( gv, problem, writer, 0.5, 1e-6 );
+    const double errorX = algorithm( uh, 0.0, end, 0 );
+    bool ok = true;
+    for( std::size_t i = 0; i < N; ++i )
+    {
+      const double a = uh[ i ];
+      ok = ok && sameBits( &a, &uo[ i ], 1 );
+    }
+    expect( ok, "2D 64^2 rotating circle: Algorithm (factory reconstruction, host velocity functor on the band) == oracle loop (bit-exact)" );
+    std::printf( "     accumulated l1 error: adaptor %.17g, oracle loop %.17g\n", errorX, error );
+    expect( error > 0.0 && std::abs( errorX - error ) <= 1e-11 * error, "2D 64^2 rotating circle: returned error == sum dt * l1error of the oracle loop (1e-11 relative)" );
+  }
+
 int main ()
 {
   try
   {
+    runCircleError();
     const int n2[ 2 ] = { 32, 24 };
     run< 2 >( "2D 32x24 SFlow", n2, VO_PROB_SFLOW, SFlowField< 2 >(), 6 );
     const int n3[ 3 ] = { 16, 16, 16 };

@@ -34,3 +34,25 @@ def test_unstructured_adaptor_binary():
         r = subprocess.run([ref], capture_output=True, text=True, timeout=600)
         print(r.stdout)
         assert r.returncode == 0 and "ADAPTOR MESH TEST PASSED" in r.stdout, r.stdout + r.stderr
+
+
+def test_adaptor_reference_containers_binary():
+    """the same driver with the reference's own ColorFunction / FlagSet / ReconstructionSet (built where /root/reference is mounted)"""
+    ref = os.path.join(ROOT, "tests", "adaptor", "test_adaptor_ref")
+    if not os.path.exists(ref):
+        pytest.skip("test_adaptor_ref is only built where the reference sources are mounted")
+    r = subprocess.run([ref], capture_output=True, text=True, timeout=600)
+    print(r.stdout)
+    assert r.returncode == 0 and "ADAPTOR TEST PASSED" in r.stdout, r.stdout + r.stderr
+
+
+def test_adaptor_parallel_binary():
+    """Dune::VoFx::Algorithm on a parallel grid view: the ranks are threads with a slab grid view each, the device contexts connect
+    through vofx_comm_export / vofx_comm_connect; interior values == the oracle on the whole grid, bit for bit"""
+    exe = os.path.join(ROOT, "tests", "adaptor", "test_adaptor_parallel")
+    assert os.path.exists(exe), "tests/adaptor/test_adaptor_parallel is missing: run __graft_entry__.build()"
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    print(r.stdout)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "ADAPTOR PARALLEL TEST PASSED" in r.stdout
+    assert "FAIL" not in r.stdout

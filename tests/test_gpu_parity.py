@@ -118,6 +118,12 @@ def test_c1_run(vofx):
     st = alg.run_passes(uh, 20)
     assert n_mismatch(uh.cpu().numpy(), g["u"]) == 0
     assert st.time == 0.12448621033571523 and st.dt == 0.0064175380278990047
+    # Algorithm::operator()( uh, start, end ): do { pass } while( time < end ) stops at the reference's pass (the 20th: the time
+    # after 19 passes is 0.1181 < 0.12)
+    uh2 = torch.tensor(g["u0"], device=grid.device)
+    st2 = alg(uh2, 0.0, 0.12)
+    assert n_mismatch(uh2.cpu().numpy(), g["u"]) == 0
+    assert st2.time == 0.12448621033571523 and st2.dt == 0.0064175380278990047
     grid.close()
 
 
@@ -429,3 +435,46 @@ def test_device_diagnostics(vofx, n, problem):
     d0 = vofx.diagnostics(grid, u0)
     assert d0["l1"] == 0.0 and d0["min"] >= 0.0 and d0["max"] <= 1.0
     torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("n", [(128, 128), (1024, 768)])
+def test_circle_interpolation_and_l1error(vofx, n):
+    """circleInterpolation (interpolation/circleinterpolation.hh:75-153: the initialiser of RotatingCircle< double, 2 >, configs[0])
+    and l1error against the exact circle (test/errors.hh:62-95) on the device, against the oracle.  Cells the circle does not cut
+    are exact; cut cells go through asin / sin (CUDA's vs glibc's): <= 4e-16 absolute on a fraction, 1e-12 relative on the error."""
+    import torch
+    from oracle import oraclelib as O
+    L, vlib = _lib()
+    grid = vofx.CartesianGrid(n)
+    og = O.OracleGrid(n)
+    center = np.array([0.5, 0.75])
+    uo = og.circle_interpolation(center, 0.15)
+    ud = grid.empty("color")
+    cc = (C.c_double * 2)(*center)
+    vlib.check(L.vofx_init_circle(grid._ctx, cc, 0.15, grid.pc(ud)))
+    u = ud.cpu().numpy()
+    uncut = (uo == 0.0) | (uo == 1.0)
+    assert np.array_equal(u[uncut], uo[uncut])
+    assert np.abs(u - uo).max() <= 4e-16
+    assert np.count_nonzero(~uncut) > 2 * min(n) * 0.15
+    # the known answer of the reference's own initialiser: the cell values sum to the disc's area
+    h2 = 1.0 / (n[0] * n[1])
+    assert abs(u.sum() * h2 - np.pi * 0.15 ** 2) < 1e-13 * np.pi * 0.15 ** 2
+    # error of a reconstruction against the exact circle
+    grid.set_velocity_builtin(vofx.PROB_ROTATING_CIRCLE)
+    uh = torch.tensor(uo, device=grid.device)
+    alg = vofx.Algorithm(grid, 0.5, 1e-6, reconstruction_kind=vofx.RECON_HF)
+    st = alg.run_passes(uh, 12)
+    # flags / reconstructions of the last pass belong to the state before its update
+    u11, t11, d11, _, _ = og.run(O.RECON_HF, O.PROB_ROTATING_CIRCLE, 1e-6, 0.5, 11, uo)
+    fo = og.flag(u11, 1e-6)
+    ho = og.reconstruct(O.RECON_HF, u11, fo)
+    omega = 2 * np.pi / 10
+    c_t = np.array([0.5, 0.5]) + np.cos(omega * t11) * np.array([0.0, 0.25]) + np.sin(omega * t11) * np.array([0.25, 0.0])
+    eo = og.l1error_circle(ho, fo, c_t, 0.15)
+    ed = C.c_double(0.0)
+    cc = (C.c_double * 2)(*c_t)
+    vlib.check(L.vofx_l1error_circle_device(grid._ctx, grid.ph(alg.reconstructions), grid.pf(alg.flags), cc, 0.15, C.byref(ed)))
+    assert eo > 0.0 and abs(ed.value - eo) <= 1e-12 * eo
+    grid.close()
+    og.close()
