@@ -23,12 +23,13 @@ namespace vofx
     size_t swz_task_bytes () { return sizeof( SwzTask ); }
     // all iterations of the batched Swartz reconstruction (4 kernels each) after the setup; `counter` is zeroed by the caller
     void swartz_batched3 ( int lanes, int sms, cudaStream_t s, Grid g, const double *u, const unsigned char *flags, const int *mixedList, StepState *state,
-                           int capacity, double *hs, int maxIterations, const void *sweepTable, void *cells, void *tasks, int *counter )
+                           int capacity, double *hs, int maxIterations, const void *sweepTable, void *cells, void *tasks, int *counter,
+                           int cellCapacity, int taskCapacity )
     {
       const coop::SweepTable *T = (const coop::SweepTable *) sweepTable;
       SwzCell *C = (SwzCell *) cells;
       SwzTask *K = (SwzTask *) tasks;
-      k_swz_setup< 3 ><<< sms * 8, 128, 0, s >>>( g, flags, mixedList, state, capacity, hs, C, K, counter );
+      k_swz_setup< 3 ><<< sms * 8, 128, 0, s >>>( g, flags, mixedList, state, capacity, hs, C, K, counter, cellCapacity, taskCapacity );
       // grid-stride kernels over the (cell, neighbour) tasks: grids well beyond the resident blocks balance the waves
       // (256^3, ms per step: 16 blocks/SM 9.75, 40 8.99, 80 8.72)
       static const int locateBlocks = std::getenv( "VOFX_SWZ_BLOCKS_PER_SM" ) ? std::atoi( std::getenv( "VOFX_SWZ_BLOCKS_PER_SM" ) ) : 80;

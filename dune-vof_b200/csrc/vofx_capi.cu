@@ -65,6 +65,8 @@ struct vofx_ctx
   // batched 3D Swartz: per-cell and per-(cell, neighbour) records, grow-only
   unsigned char *swzCells = nullptr, *swzTasks = nullptr;
   size_t swzCellCap = 0, swzTaskCap = 0;
+  size_t swzCellCount = 0;          // cells the buffers hold
+  size_t swzHint = 0;               // band length of the last pass the host has seen (readState)
   int *swzCounter = nullptr;
   // interface extraction (vofx_interface): grow-only scratch
   int *ifBlockSums = nullptr, *ifCells = nullptr, *ifNverts = nullptr, *ifOffsets = nullptr;
@@ -421,21 +423,37 @@ namespace
           launch::swartz_coop3( lanes, ctx->numSMs * 16, ctx->stream, g, u, flags, ctx->mixedList, ctx->state, ctx->capacity, hs, maxIterations, ctx->sweepTable );
         else
         {
-          // batched over the band: the buffers are sized from the mixed-cell count of this step (one small read-back)
-          StepState now;
-          int rcs = readState( ctx, now );
-          if( rcs )
-            return rcs;
-          const size_t nCells = (size_t) ( now.mixedCount < ctx->capacity ? now.mixedCount : ctx->capacity );
-          rcs = growDevice( ctx->swzCells, ctx->swzCellCap, nCells * launch::swz_cell_bytes() + 16 );
-          rcs = rcs ? rcs : growDevice( ctx->swzTasks, ctx->swzTaskCap, nCells * 27 * launch::swz_task_bytes() + 16 );
-          rcs = rcs ? rcs : ensureDevice( ctx->swzCounter, (size_t) 1 );
-          if( rcs )
-            return rcs;
+          // batched over the band.  The buffers are sized on the host from the band of an EARLIER pass (the first pass reads
+          // its own count back once; afterwards every read of the loop state refreshes the hint), so a pass neither blocks
+          // the stream nor allocates, and it can be captured into a CUDA graph; k_swz_setup guards the capacities on the device
+          if( !capturing( ctx ) )
+          {
+            size_t want = ctx->swzHint;
+            if( !ctx->swzCells || want == 0 )
+            {
+              StepState now;
+              int rcs = readState( ctx, now );
+              if( rcs )
+                return rcs;
+              want = (size_t) ( now.mixedCount < ctx->capacity ? now.mixedCount : ctx->capacity );
+            }
+            const size_t cellsWanted = want + want / 2 + 4096;        // 50 % headroom: the band grows slowly
+            if( cellsWanted > ctx->swzCellCount )
+            {
+              int rcs = growDevice( ctx->swzCells, ctx->swzCellCap, cellsWanted * launch::swz_cell_bytes() + 16 );
+              rcs = rcs ? rcs : growDevice( ctx->swzTasks, ctx->swzTaskCap, cellsWanted * 27 * launch::swz_task_bytes() + 16 );
+              rcs = rcs ? rcs : ensureDevice( ctx->swzCounter, (size_t) 1 );
+              if( rcs )
+                return rcs;
+              ctx->swzCellCount = cellsWanted;
+            }
+          }
+          if( !ctx->swzCells )
+            return fail( VOFX_ERR_STATE, "the batched 3D Swartz pass must run once eagerly before it is captured (it sizes its buffers)" );
           VOFX_CUDA( cudaMemsetAsync( ctx->swzCounter, 0, sizeof( int ), ctx->stream ) );
           profBegin( ctx );
           launch::swartz_batched3( lanes, ctx->numSMs, ctx->stream, g, u, flags, ctx->mixedList, ctx->state, ctx->capacity, hs, maxIterations, ctx->sweepTable,
-                                   ctx->swzCells, ctx->swzTasks, ctx->swzCounter );
+                                   ctx->swzCells, ctx->swzTasks, ctx->swzCounter, (int) ctx->swzCellCount, (int) ( ctx->swzCellCount * 27 ) );
           ctx->launches += 4 * maxIterations;
         }
       }
@@ -524,7 +542,12 @@ namespace
       return fail( VOFX_ERR_STATE, "distributed step: the wait for " + std::string( ( s.commError & 15 ) == 1 ? "the halo pushes" : ( ( s.commError & 15 ) == 2 ? "the fluxes" : "the time-step estimate" ) )
                    + " of rank " + std::to_string( ( s.commError >> 4 ) & 15 ) + " in pass " + std::to_string( s.commError >> 8 )
                    + " timed out (a rank died, or the ranks' call sequences differ)" );
-    if( s.overflow )
+    if( s.overflow == 2 || s.overflowLast == 2 )
+    {
+      ctx->swzHint = ctx->swzHint * 2 + 4096;      // the next eager pass enlarges the buffers
+      return fail( VOFX_ERR_STATE, "the band outgrew the buffers of the batched Swartz reconstruction (restart the loop from the last state: vofx_step_begin)" );
+    }
+    if( s.overflow || s.overflowLast )
       return fail( VOFX_ERR_STATE, "mixed-cell list overflow: more than " + std::to_string( ctx->capacity ) + " mixed cells" );
     return VOFX_OK;
   }
@@ -533,6 +556,9 @@ namespace
   {
     VOFX_CUDA( cudaMemcpyAsync( &s, ctx->state, sizeof( StepState ), cudaMemcpyDeviceToHost, ctx->stream ) );
     VOFX_CUDA( cudaStreamSynchronize( ctx->stream ) );
+    const int band = s.mixedCount > s.mixedCountLast ? s.mixedCount : s.mixedCountLast;
+    if( band > 0 )
+      ctx->swzHint = (size_t) band;
     return checkOverflow( ctx, s );
   }
 
@@ -1683,6 +1709,78 @@ extern "C"
     if( flags )
       VOFX_CUDA( cudaMemcpyAsync( flags, ctx->dFlags, (size_t) ctx->grid.cells, cudaMemcpyDeviceToHost, ctx->stream ) );
     VOFX_CUDA( cudaStreamSynchronize( ctx->stream ) );
+    return VOFX_OK;
+  }
+
+  // ---- checkpoint / restart in the byte format of the reference's BinaryWriter (example/binarywriter.hh:36-60) ------------------
+  // binaryStream << time; uh.write( binaryStream ) (colorfunction.hh:40-44): the time and then one double per cell in the grid
+  // view's iteration order, raw little-endian IEEE doubles (Dune::Fem::BinaryFileOutStream writes primitives verbatim; dune-fem
+  // is a third-party dependency that is not vendored: that layout is restated from its public documentation).  A rank writes
+  // its OWNED cells (x fastest), as a DUNE rank writes the cells of its grid view.
+  static void checkpoint_name ( char *out, size_t bytes, const char *prefix, int level, int step, int rank, int world )
+  {
+    // "s" setw(4) size "-p" setw(4) rank "-" prefix "-" level "-" setw(5) step ".bin", fill '0' (binarywriter.hh:46-51)
+    std::snprintf( out, bytes, "s%04d-p%04d-%s-%d-%05d.bin", world, rank, prefix, level, step );
+  }
+
+  int vofx_checkpoint_name ( char *out, int64_t bytes, const char *prefix, int level, int step, int rank, int world )
+  {
+    if( !out || bytes < 32 || !prefix )
+      return fail( VOFX_ERR_ARGUMENT, "bad argument" );
+    checkpoint_name( out, (size_t) bytes, prefix, level, step, rank, world );
+    return VOFX_OK;
+  }
+
+  int vofx_checkpoint_write ( vofx_ctx *ctx, const char *path, double time )
+  {
+    if( !ctx || !path )
+      return fail( VOFX_ERR_ARGUMENT, "null argument" );
+    int rc = ensureMirrors( ctx );
+    if( rc )
+      return rc;
+    const Grid &g = ctx->grid;
+    const long long layer = g.cells / g.ns[ g.dim - 1 ];
+    const size_t first = (size_t) ( layer * g.own0 ), n = (size_t) ( layer * ( g.own1 - g.own0 ) );
+    rc = ensurePinned( ctx, n * sizeof( double ) );
+    if( rc )
+      return rc;
+    VOFX_CUDA( cudaMemcpyAsync( ctx->pinned, ctx->dU + first, n * sizeof( double ), cudaMemcpyDeviceToHost, ctx->stream ) );
+    VOFX_CUDA( cudaStreamSynchronize( ctx->stream ) );
+    FILE *f = std::fopen( path, "wb" );
+    if( !f )
+      return fail( VOFX_ERR_ARGUMENT, std::string( "cannot open " ) + path + " for writing" );
+    const bool ok = std::fwrite( &time, sizeof( double ), 1, f ) == 1 && std::fwrite( ctx->pinned, sizeof( double ), n, f ) == n;
+    if( std::fclose( f ) != 0 || !ok )
+      return fail( VOFX_ERR_ARGUMENT, std::string( "short write to " ) + path );
+    return VOFX_OK;
+  }
+
+  int vofx_checkpoint_read ( vofx_ctx *ctx, const char *path, double *time )
+  {
+    if( !ctx || !path || !time )
+      return fail( VOFX_ERR_ARGUMENT, "null argument" );
+    int rc = ensureMirrors( ctx );
+    if( rc )
+      return rc;
+    const Grid &g = ctx->grid;
+    const long long layer = g.cells / g.ns[ g.dim - 1 ];
+    const size_t first = (size_t) ( layer * g.own0 ), n = (size_t) ( layer * ( g.own1 - g.own0 ) );
+    rc = ensurePinned( ctx, n * sizeof( double ) );
+    if( rc )
+      return rc;
+    FILE *f = std::fopen( path, "rb" );
+    if( !f )
+      return fail( VOFX_ERR_ARGUMENT, std::string( "cannot open " ) + path );
+    const bool ok = std::fread( time, sizeof( double ), 1, f ) == 1 && std::fread( ctx->pinned, sizeof( double ), n, f ) == n;
+    char extra;
+    const bool tooLong = ok && std::fread( &extra, 1, 1, f ) == 1;
+    std::fclose( f );
+    if( !ok || tooLong )
+      return fail( VOFX_ERR_ARGUMENT, std::string( path ) + " does not hold a time and one double per owned cell of this context" );
+    VOFX_CUDA( cudaMemcpyAsync( ctx->dU + first, ctx->pinned, n * sizeof( double ), cudaMemcpyHostToDevice, ctx->stream ) );
+    VOFX_CUDA( cudaStreamSynchronize( ctx->stream ) );
+    ctx->primedU = nullptr;       // new colour values: the next pass flags densely
+    ctx->primedFlags = nullptr;
     return VOFX_OK;
   }
 

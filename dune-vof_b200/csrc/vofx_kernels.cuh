@@ -1363,9 +1363,19 @@ namespace vofx
   template< int DIM_ >
   __global__ void __launch_bounds__( 128 ) k_swz_setup ( Grid g, const unsigned char *__restrict__ flags, const int *__restrict__ mixedList,
                                                           StepState *state, int capacity, const double *__restrict__ hs,
-                                                          SwzCell *__restrict__ cells, SwzTask *__restrict__ tasks, int *taskCounter )
+                                                          SwzCell *__restrict__ cells, SwzTask *__restrict__ tasks, int *taskCounter,
+                                                          int cellCapacity, int taskCapacity )
   {
     const int count = mixed_count( state, capacity );
+    // the buffers are sized by the host from the band of an earlier pass (no read-back per pass, the pass stays
+    // graph-capturable): a band that outgrew them turns the pass into a no-op and the host sees the overflow at its next
+    // read of the loop state (and enlarges the buffers)
+    if( count > cellCapacity )
+    {
+      if( blockIdx.x == 0 && threadIdx.x == 0 )
+        state->overflow = 2;
+      return;
+    }
     for( int p = blockIdx.x * blockDim.x + threadIdx.x; p < count; p += gridDim.x * blockDim.x )
     {
       const int c = mixedList[ p ];
@@ -1391,6 +1401,13 @@ namespace vofx
       C.state = 0;
       const int base = atomicAdd( taskCounter, n + 1 );
       C.taskBase = base;
+      if( base + n + 1 > taskCapacity )
+      {
+        state->overflow = 2;
+        C.nNb = 0;
+        C.active = 0;
+        continue;
+      }
       for( int a = 0; a <= n; ++a )
       {
         tasks[ base + a ].owner = p;

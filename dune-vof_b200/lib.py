@@ -24,7 +24,7 @@ SYMBOLS = [
     "vofx_flag", "vofx_reconstruct", "vofx_evolve", "vofx_axpy", "vofx_curvature", "vofx_curvature_swartz", "vofx_curvature_swartz_host", "vofx_step_begin", "vofx_set_incremental_flagging", "vofx_step",
     "vofx_step_state", "vofx_band_list_fetch", "vofx_step_counters", "vofx_step_local", "vofx_step_phase", "vofx_step_finish", "vofx_dt_est_device", "vofx_flag_host",
     "vofx_reconstruct_host", "vofx_evolve_host", "vofx_curvature_host", "vofx_step_host", "vofx_host_transfer_bytes", "vofx_track_changes", "vofx_changed_fetch", "vofx_color_upload",
-    "vofx_step_resident", "vofx_color_download", "vofx_comm_export", "vofx_comm_connect", "vofx_comm_connect_local", "vofx_comm_disconnect",
+    "vofx_step_resident", "vofx_color_download", "vofx_checkpoint_name", "vofx_checkpoint_write", "vofx_checkpoint_read", "vofx_comm_export", "vofx_comm_connect", "vofx_comm_connect_local", "vofx_comm_disconnect",
     "vofx_color_device", "vofx_flags_device", "vofx_halfspaces_device", "vofx_halo_push", "vofx_step_distributed", "vofx_step_distributed_phase", "vofx_band_list_fetch_in_flight",
     "vofx_velocity_set_band_faces", "vofx_diagnostics", "vofx_interface", "vofx_interface_host", "vofx_interface_fetch", "vofx_init", "vofx_init_circle", "vofx_l1error_circle", "vofx_l1error_circle_device",
     "vofx_test_fp64_rate", "vofx_test_arith", "vofx_test_locate", "vofx_test_flux", "vofx_test_interface", "vofx_launch_count", "vofx_profile_enable",
@@ -128,6 +128,9 @@ def load():
     L.vofx_color_upload.argtypes = [vp, dp]
     L.vofx_step_resident.argtypes = [vp, C.POINTER(StepParams)]
     L.vofx_color_download.argtypes = [vp, dp, bp]
+    L.vofx_checkpoint_name.argtypes = [C.c_char_p, C.c_int64, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.vofx_checkpoint_write.argtypes = [vp, C.c_char_p, C.c_double]
+    L.vofx_checkpoint_read.argtypes = [vp, C.c_char_p, C.POINTER(C.c_double)]
     L.vofx_comm_export.argtypes = [vp, C.c_void_p]
     L.vofx_comm_connect.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_int32), C.c_void_p]
     L.vofx_comm_connect_local.argtypes = [C.POINTER(C.c_void_p), C.c_int]

@@ -347,7 +347,7 @@ class Algorithm:
     def capture(self, uh):
         """capture one loop pass into a CUDA graph (it only reads device-resident state: time, dt, counters); replay()
         then costs one host launch per pass -- what small grids need, whose passes are launch-bound (C1: 5 kernels
-        of a few microseconds each).  Not for the 3D Swartz reconstruction (it sizes its buffers from a read-back)."""
+        of a few microseconds each).  Run at least one pass eagerly first (dense flags; the batched 3D Swartz pass sizes its buffers there)."""
         torch = _torch()
         g = self.grid
         self._graph_stream = torch.cuda.Stream(device=g.device)

@@ -212,6 +212,16 @@ int vofx_color_upload ( vofx_ctx *ctx, const double *u_host );
 int vofx_step_resident ( vofx_ctx *ctx, const vofx_step_params *params );
 int vofx_color_download ( vofx_ctx *ctx, double *u_host, uint8_t *flags_host /* may be NULL */ );
 
+/* ---- checkpoint / restart of the context-resident colour function in the byte format of the reference's BinaryWriter
+ * (example/binarywriter.hh:36-60: `binaryStream << time; uh.write( binaryStream )`, colorfunction.hh:40-51): the time, then
+ * one double per OWNED cell in x-fastest order (the iteration order of a structured grid view), raw little-endian doubles.
+ * bin2vtk / a restarted example/vof.cc read these files.  vofx_checkpoint_name builds the writer's file name
+ * "s<size:04>-p<rank:04>-<prefix>-<level>-<step:05>.bin" (binarywriter.hh:46-51).  After a read the halos of a distributed
+ * run must be refilled (vofx_halo_push) and the loop restarted with vofx_step_begin( time, dt ). */
+int vofx_checkpoint_name ( char *out, int64_t bytes, const char *prefix, int level, int step, int rank, int world );
+int vofx_checkpoint_write ( vofx_ctx *ctx, const char *path, double time );
+int vofx_checkpoint_read ( vofx_ctx *ctx, const char *path, double *time );
+
 /* ---- multi-GPU: the grid is cut into slabs along the last axis, one context per GPU (one per process -- one per MPI
  * rank of a DUNE host -- or several in one process).  Replaces the reference's exchanges over GridView::communicate
  * (dataset.hh:69-81; call sites flagging.hh:69, modifiedyoungs.hh:75, evolution/evolution.hh:73) and gridView().comm().min

@@ -34,7 +34,7 @@ def main():
             print(msg, flush=True)
 
     cases = [((48, 40, 64), ops.PROB_LEVEQUE, ops.RECON_YOUNGS, 8), ((32, 32, 48), ops.PROB_SFLOW, ops.RECON_HF, 4),
-             ((64, 96), ops.PROB_SLOTTED_CYLINDER, ops.RECON_HF, 5), ((24, 24, 32), ops.PROB_ROTATING_CIRCLE, ops.RECON_SWARTZ, 2)]
+             ((64, 96), ops.PROB_SLOTTED_CYLINDER, ops.RECON_HF, 5), ((24, 24, 32), ops.PROB_ROTATING_CIRCLE, ops.RECON_SWARTZ, 4)]
     for n, problem, recon, passes in cases:
         # serial reference on this rank's GPU
         g1 = ops.CartesianGrid(n, device=local)
@@ -70,9 +70,8 @@ def main():
             if not ok:
                 failures.append((n, problem, recon, transport))
             say(f"case n={n} problem={problem} recon={recon} [{transport}]: {'bit-identical' if ok else 'MISMATCH'} (time={st.time!r} dt={st.dt!r})")
-            # the same passes replayed from a CUDA graph of one captured pass (what bench.py times); the batched 3D Swartz
-            # pass sizes its buffers from a host read-back and is not capturable
-            if recon != ops.RECON_SWARTZ:
+            # the same passes replayed from a CUDA graph of one captured pass (what bench.py times)
+            if passes > 2:
                 slab2, u2 = fresh(transport)
                 side = torch.cuda.Stream()
                 with torch.cuda.stream(side):

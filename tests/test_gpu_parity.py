@@ -478,3 +478,55 @@ def test_circle_interpolation_and_l1error(vofx, n):
     assert eo > 0.0 and abs(ed.value - eo) <= 1e-12 * eo
     grid.close()
     og.close()
+
+
+def test_checkpoint_binarywriter_format(vofx, tmp_path):
+    """vofx_checkpoint_write / _read: the bytes of the reference's BinaryWriter (example/binarywriter.hh:36-60,
+    colorfunction.hh:40-51: the time, then one raw double per cell in iteration order), the writer's file name, and a restart
+    that continues the loop bit for bit"""
+    import torch
+    L, vlib = _lib()
+    name = C.create_string_buffer(64)
+    vlib.check(L.vofx_checkpoint_name(name, 64, b"vof", 1, 7, 3, 8))
+    assert name.value == b"s0008-p0003-vof-1-00007.bin"
+    n = (48, 40, 32)
+    ga, gb = vofx.CartesianGrid(n), vofx.CartesianGrid(n)
+    for g in (ga, gb):
+        g.set_velocity_builtin(vofx.PROB_LEVEQUE)
+    u0 = ga.init(vofx.PROB_LEVEQUE)
+    p = vlib.StepParams(0, 10, 1e-6, 0.5, 0)
+    host = u0.cpu().numpy().copy()
+    vlib.check(L.vofx_step_begin(ga._ctx, 0.0, 0.0))
+    vlib.check(L.vofx_color_upload(ga._ctx, C.c_void_p(host.ctypes.data)))
+    for _ in range(6):
+        vlib.check(L.vofx_step_resident(ga._ctx, C.byref(p)))
+    t, dt = C.c_double(), C.c_double()
+    vlib.check(L.vofx_step_state(ga._ctx, C.byref(t), C.byref(dt), None, None))
+    path = str(tmp_path / name.value.decode())
+    vlib.check(L.vofx_checkpoint_write(ga._ctx, path.encode(), t.value))
+    raw = np.fromfile(path, dtype="<f8")
+    mid = np.empty_like(host)
+    vlib.check(L.vofx_color_download(ga._ctx, C.c_void_p(mid.ctypes.data), None))
+    assert raw.size == 1 + host.size and raw[0] == t.value and np.array_equal(raw[1:].view(np.uint64), mid.view(np.uint64))
+    # continue on the first context, restart on the second from the file: identical afterwards
+    for _ in range(5):
+        vlib.check(L.vofx_step_resident(ga._ctx, C.byref(p)))
+    t2 = C.c_double()
+    vlib.check(L.vofx_checkpoint_read(gb._ctx, path.encode(), C.byref(t2)))
+    assert t2.value == t.value
+    vlib.check(L.vofx_step_begin(gb._ctx, t2.value, dt.value))
+    for _ in range(5):
+        vlib.check(L.vofx_step_resident(gb._ctx, C.byref(p)))
+    a, b = np.empty_like(host), np.empty_like(host)
+    vlib.check(L.vofx_color_download(ga._ctx, C.c_void_p(a.ctypes.data), None))
+    vlib.check(L.vofx_color_download(gb._ctx, C.c_void_p(b.ctypes.data), None))
+    assert np.array_equal(a.view(np.uint64), b.view(np.uint64))
+    ta, tb = C.c_double(), C.c_double()
+    vlib.check(L.vofx_step_state(ga._ctx, C.byref(ta), None, None, None))
+    vlib.check(L.vofx_step_state(gb._ctx, C.byref(tb), None, None, None))
+    assert ta.value == tb.value
+    # a file of the wrong size is refused
+    np.zeros(10).tofile(str(tmp_path / "short.bin"))
+    assert L.vofx_checkpoint_read(gb._ctx, str(tmp_path / "short.bin").encode(), C.byref(t2)) != 0
+    ga.close()
+    gb.close()

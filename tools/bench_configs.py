@@ -40,14 +40,16 @@ def run(name, n, problem, recon, curvature, steps, warmup, cpu):
     grid.set_velocity_builtin(problem)
     grid.use_current_stream()
     if len(n) == 2 and problem == ops.PROB_ROTATING_CIRCLE:
-        from oracle import oraclelib as O                       # exact circle average on the host (test/average.hh:82-101)
-        og = O.OracleGrid(n)
-        uh = torch.from_numpy(og.init(O.PROB_ROTATING_CIRCLE)).to(grid.device)
+        uh = grid.empty("color")                                # exact circle average (test/average.hh:82-101) on the device
+        vlib.check(grid._L.vofx_init_circle(grid._ctx, (C.c_double * 2)(0.5, 0.75), 0.15, grid.pc(uh)))
     else:
         uh = grid.init(problem)
-    alg = ops.Algorithm(grid, 0.5, 1e-6, recon, with_curvature=curvature)
+    alg = ops.Algorithm(grid, 0.5, 1e-6, recon, with_curvature=curvature, incremental=True)
     alg.begin(0.0, 0.0)
-    graph = not (len(n) == 3 and recon == ops.RECON_SWARTZ)      # the 3D Swartz pass reads a count back: not capturable
+    graph = True
+    from bench import ClockSampler, measured_peaks
+    sampler = ClockSampler(torch.cuda.current_device())
+    sampler.start()
     side = torch.cuda.Stream()
     with torch.cuda.stream(side):
         grid.use_current_stream()
@@ -81,16 +83,41 @@ def run(name, n, problem, recon, curvature, steps, warmup, cpu):
     vlib.check(L.vofx_profile_read(grid._ctx, 32, names, tot, cnt, C.byref(nent)))
     vlib.check(L.vofx_profile_enable(grid._ctx, 0))
     kernels = {names.raw[48 * i:48 * (i + 1)].split(b"\0", 1)[0].decode(): round(tot[i] / max(cnt[i], 1), 5) for i in range(nent.value)}
+    sampler.stop()
     st = alg.state()
     cells = 1
     for x in n:
         cells *= x
     bytes_per_cell = 25 if curvature else 17
+    peak, peak_src = measured_peaks()
+    value = cells * steps / (ms * 1e-3)
+    if len(n) == 3 and recon == ops.RECON_SWARTZ:
+        # fp64-bound: executed fp64 thread instructions per pass (static: the ncu counters of one pass of this
+        # workload, profiles/r2_c4_fp64_ops.json) over the measured pass time, against the measured fp64 issue rate of this GPU
+        rates = (C.c_double * 2)()
+        vlib.check(grid._L.vofx_test_fp64_rate(rates))
+        roofline = {"bound": "fp64", "peak": rates[1] / 1e3, "unit": "T fp64 instructions/s (separate multiply / add, as the parity contract compiles)",
+                    "peak_fma": rates[0] / 1e3, "peak_source": "vofx_test_fp64_rate, measured in this run", "achieved": None, "frac": None, "traffic": None}
+        try:
+            prof = json.load(open(os.path.join(ROOT, "profiles", "r2_c4_fp64_ops.json")))
+            per_mixed = prof["fp64_thread_instructions_per_pass"] / prof["mixed_cells"]
+            achieved = per_mixed * st.mixed_cells / (ms / steps * 1e-3) / 1e12
+            roofline.update({"achieved": achieved, "frac": achieved / (rates[1] / 1e3),
+                             "fp64_thread_instructions_per_mixed_cell": per_mixed,
+                             "ops_source": "profiles/r2_c4_fp64_ops.json (ncu smsp__sass_thread_inst_executed_op_{dfma,dmul,dadd}_pred_on of one pass)"})
+        except Exception as exc:
+            roofline["note"] = "no op counts: " + repr(exc)
+    else:
+        roofline = {"bound": "hbm", "achieved": value * bytes_per_cell / 1e9, "peak": peak, "unit": "GB/s", "frac": value * bytes_per_cell / 1e9 / peak,
+                    "algorithmic_bytes_per_cell_step": bytes_per_cell, "peak_source": peak_src, "traffic": None}
     line = {"config": name, "grid": list(n), "reconstruction": int(recon), "curvature": bool(curvature), "steps": steps, "warmup": warmup,
-            "ms_per_step": ms / steps, "launch": "CUDA graph replay" if graph else "eager", "value": cells * steps / (ms * 1e-3), "unit": "cell-steps/s",
-            "frac_of_hbm_peak_at_%dB" % bytes_per_cell: cells * steps / (ms * 1e-3) * bytes_per_cell / 1e9 / 6544.3,
+            "ms_per_step": ms / steps, "launch": "CUDA graph replay" if graph else "eager", "value": value, "unit": "cell-steps/s",
+            "flagging": "incremental", "clocks": sampler.report(), "roofline": roofline,
             "mixed_cells": st.mixed_cells, "kernel_avg_ms": kernels, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
+    if hasattr(alg, "_graph"):
+        del alg._graph
+    torch.cuda.synchronize()
     grid.close()
     sys.stdout.flush()
 
@@ -119,4 +146,3 @@ def main():
 if __name__ == "__main__":
     main()
     sys.stdout.flush()
-    os._exit(0)     # no teardown of captured graphs
