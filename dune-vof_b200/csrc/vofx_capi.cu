@@ -114,6 +114,7 @@ struct vofx_ctx
   int lanesPerCell = 4;            // measured on B200 at 512^3: 0.47 ms (4 lanes per cell) vs 0.64 ms (8)
   void *clipTable = nullptr;        // coop::ClipCase[ 256 ] by inner mask, then [ 6561 ] by ( outer / inner / on the plane ) pattern
   StepState *state = nullptr;
+  StepState *stateHost = nullptr;   // pinned mirror for read-backs
   double *curv1 = nullptr;
   unsigned char *ok1 = nullptr;
   double *scalars = nullptr;        // [0] time override, [1] dt override (operator-level evolve)
@@ -554,8 +555,14 @@ namespace
 
   int readState ( vofx_ctx *ctx, StepState &s )
   {
-    VOFX_CUDA( cudaMemcpyAsync( &s, ctx->state, sizeof( StepState ), cudaMemcpyDeviceToHost, ctx->stream ) );
+    // through PINNED memory: an asynchronous copy into pageable memory is staged by the runtime, which waits for the stream
+    // inside the call -- with several contexts driven by threads of one process that wait can block the other threads' launches
+    // (the stream may hold a kernel that waits for exactly those launches)
+    if( !ctx->stateHost )
+      VOFX_CUDA( cudaMallocHost( (void **) &ctx->stateHost, sizeof( StepState ) ) );
+    VOFX_CUDA( cudaMemcpyAsync( ctx->stateHost, ctx->state, sizeof( StepState ), cudaMemcpyDeviceToHost, ctx->stream ) );
     VOFX_CUDA( cudaStreamSynchronize( ctx->stream ) );
+    s = *ctx->stateHost;
     const int band = s.mixedCount > s.mixedCountLast ? s.mixedCount : s.mixedCountLast;
     if( band > 0 )
       ctx->swzHint = (size_t) band;
@@ -824,6 +831,8 @@ extern "C"
     cudaFree( ctx->dValid );
     if( ctx->pinned )
       cudaFreeHost( ctx->pinned );
+    if( ctx->stateHost )
+      cudaFreeHost( ctx->stateHost );
     for( cudaEvent_t e : ctx->eventPool )
       cudaEventDestroy( e );
     delete ctx;

@@ -391,6 +391,12 @@ namespace vofx
   namespace coop
   {
 
+    // unroll factor of the lane-strided loops of the plane-constant solve whose iterations are independent fp64 chains
+    // (a lane owns up to 3 edges / 2 faces / 3 terms); 1 keeps the code compact (instruction cache), more overlaps the chains
+#ifndef VOFX_PHASE_UNROLL
+#define VOFX_PHASE_UNROLL 1
+#endif
+    constexpr int kPhaseUnroll = VOFX_PHASE_UNROLL;
     constexpr int kSweepCases = 96;
     constexpr int kMaxPoly = 8;       // nodes of the cross-section polygon (6 for a generic box; 8 = the walk's own bound)
     constexpr int kMaxATerms = 12;
@@ -776,7 +782,7 @@ namespace vofx
           S.ids[ rank ] = (unsigned char) i;
           S.ds[ rank ] = zi;
         }
-#pragma unroll 1
+#pragma unroll kPhaseUnroll
         for( int e = lane; e < 12; e += L )
         {
           // edge e = ( a, b ); its reverse e + 12 = ( b, a ) is not stored (dv_get)
@@ -790,7 +796,7 @@ namespace vofx
           for( int c = 0; c < 3; ++c )
             S.dv[ c ][ e ] = dv[ c ];
         }
-#pragma unroll 1
+#pragma unroll kPhaseUnroll
         for( int f = lane; f < 6; f += L )
         {
           double x[ 3 ][ 3 ], normal[ 3 ];
@@ -949,7 +955,7 @@ namespace vofx
         // the terms of A, B, C (geometry/algorithm.hh:177-208), one per lane
         VOFX_LANES( G, L, lane )
         {
-#pragma unroll 1
+#pragma unroll kPhaseUnroll
           for( int t = lane; t < B.nA; t += L )
           {
             const int e1 = B.aE1[ t ], e2 = B.aE2[ t ];
@@ -957,7 +963,7 @@ namespace vofx
             const double v2x = dv_get( S, 0, e2 ), v2y = dv_get( S, 1, e2 ), v2z = dv_get( S, 2, e2 );
             S.aterm[ t ] = vdiv( v1x * v2y - v1y * v2x, v1z * v2z );
           }
-#pragma unroll 1
+#pragma unroll kPhaseUnroll
           for( int i = lane; i < B.nEdges; i += L )
           {
             const int j = ( i + 1 == B.nn ) ? 0 : i + 1;

@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -318,6 +319,13 @@ namespace
 
 int main ()
 {
+  // ranks as THREADS of one process share one CUDA context: a kernel that is loaded lazily at its first launch can make that
+  // launch wait for the device while another thread's kernel spins on a signal only this thread can send.  MPI ranks are
+  // processes and never meet this; here every kernel is loaded up front.
+  setenv( "CUDA_MODULE_LOADING", "EAGER", 1 );
+  // ... and every rank's stream needs a hardware queue of its own (streams that share one are served in order: a waiting
+  // kernel of one rank would block the kernels of another that it waits for)
+  setenv( "CUDA_DEVICE_MAX_CONNECTIONS", "32", 1 );
   runCase< 2 >( "2D 48x64 SFlow", { 48, 64 }, { 30, 34 }, 2, VO_PROB_SFLOW, 8, false );
   runCase< 2 >( "2D 48x64 SFlow", { 48, 64 }, { 30, 34 }, 2, VO_PROB_SFLOW, 8, true );
   runCase< 3 >( "3D 20x12x32 SFlow", { 20, 12, 32 }, { 10, 12, 10 }, 1, VO_PROB_SFLOW, 5, false );
