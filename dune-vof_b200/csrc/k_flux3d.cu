@@ -14,10 +14,10 @@ namespace vofx
                       const double *timeOverride, const double *dtOverride )
     {
       if( lanes == 4 )
-        k_flux_cell3< 3, 4 ><<< blocks * 2, 64, 0, s >>>( g, velocityByValue, hs, flags, mixedList, state, capacity, records, tasks, taskCapacity, (const coop::ClipCase *) clipTable, timeOverride, dtOverride );
+        pdl( k_flux_cell3< 3, 4 >, blocks * 2, 64, s, g, velocityByValue, hs, flags, mixedList, state, capacity, records, tasks, taskCapacity, (const coop::ClipCase *) clipTable, timeOverride, dtOverride );
       else
-        k_flux_cell3< 3, 8 ><<< blocks, 128, 0, s >>>( g, velocityByValue, hs, flags, mixedList, state, capacity, records, tasks, taskCapacity, (const coop::ClipCase *) clipTable, timeOverride, dtOverride );
-      k_flux_clip_serial3< 3 ><<< 148, 64, 0, s >>>( g, velocity, hs, flags, mixedList, state, records, tasks, taskCapacity, timeOverride, dtOverride );
+        pdl( k_flux_cell3< 3, 8 >, blocks, 128, s, g, velocityByValue, hs, flags, mixedList, state, capacity, records, tasks, taskCapacity, (const coop::ClipCase *) clipTable, timeOverride, dtOverride );
+      pdl( k_flux_clip_serial3< 3 >, 148, 64, s, g, velocity, hs, flags, mixedList, state, records, tasks, taskCapacity, timeOverride, dtOverride );
     }
     size_t clip_table_bytes () { return sizeof( coop::ClipCase ) * ( 256 + coop::kClipBoundaryCases ); }
     void make_clip_table ( void *host )

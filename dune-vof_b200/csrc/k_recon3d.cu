@@ -14,19 +14,19 @@ namespace vofx
       const coop::SweepTable *T = (const coop::SweepTable *) sweepTable;
       coop::RootTask *R = (coop::RootTask *) rootTasks;
       if( lanes == 4 && !heightFunction )
-        k_youngs_coop3< 4, false ><<< blocks * 2, 64, 0, s >>>( g, u, mixedList, state, capacity, hs, T, serialCells, R, order, costClass );
+        pdl( k_youngs_coop3< 4, false >, blocks * 2, 64, s, g, u, mixedList, state, capacity, hs, T, serialCells, R, order, costClass );
       else if( lanes == 4 )
-        k_youngs_coop3< 4, true ><<< blocks * 2, 64, 0, s >>>( g, u, mixedList, state, capacity, hs, T, serialCells, R, order, costClass );
+        pdl( k_youngs_coop3< 4, true >, blocks * 2, 64, s, g, u, mixedList, state, capacity, hs, T, serialCells, R, order, costClass );
       else if( !heightFunction )
-        k_youngs_coop3< 8, false ><<< blocks, 128, 0, s >>>( g, u, mixedList, state, capacity, hs, T, serialCells, R, order, costClass );
+        pdl( k_youngs_coop3< 8, false >, blocks, 128, s, g, u, mixedList, state, capacity, hs, T, serialCells, R, order, costClass );
       else
-        k_youngs_coop3< 8, true ><<< blocks, 128, 0, s >>>( g, u, mixedList, state, capacity, hs, T, serialCells, R, order, costClass );
+        pdl( k_youngs_coop3< 8, true >, blocks, 128, s, g, u, mixedList, state, capacity, hs, T, serialCells, R, order, costClass );
     }
     void locate_root3 ( int blocks, cudaStream_t s, StepState *state, int capacity, const void *rootTasks, double *hs )
-    { k_locate_root3< 3 ><<< blocks, 128, 0, s >>>( state, capacity, (const coop::RootTask *) rootTasks, hs ); }
+    { pdl( k_locate_root3< 3 >, blocks, 128, s, state, capacity, (const coop::RootTask *) rootTasks, hs ); }
     size_t root_task_bytes () { return sizeof( coop::RootTask ); }
     void locate_serial3 ( cudaStream_t s, Grid g, const double *u, const StepState *state, double *hs, const int *serialCells )
-    { k_locate_serial3< 3 ><<< 148, 64, 0, s >>>( g, u, state, hs, serialCells ); }
+    { pdl( k_locate_serial3< 3 >, 148, 64, s, g, u, state, hs, serialCells ); }
     int make_sweep_table ( void *host, size_t bytes )
     {
       if( bytes < sizeof( coop::SweepTable ) )

@@ -159,6 +159,7 @@ namespace vofx
                                                           int *__restrict__ mixedList, int *__restrict__ slot, int capacity, StepState *state,
                                                           int compact, int rowsPerBlock, int rowBegin, int rowEnd )
   {
+    pdl_prologue();
     const int nx = g.ns[ 0 ];
     const int ny = g.ns[ 1 ];
     const int nRows = rowEnd;            // rows [ rowBegin, rowEnd ) of the ns[1] * ns[2] rows of the storage box
@@ -403,6 +404,7 @@ namespace vofx
   __global__ void __launch_bounds__( 256 ) k_scan_marks ( Grid g, unsigned char *__restrict__ marks, int segsPerRow, long long nSegments,
                                                            int layer0, int layer1, int *__restrict__ segList, StepState *state )
   {
+    pdl_prologue();
     __shared__ int warpCount[ 8 ], blockBase;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long nChunks = ( nSegments + 15 ) >> 4;
@@ -473,6 +475,7 @@ namespace vofx
                                                               int *__restrict__ mixedList, int *__restrict__ slot, int capacity, StepState *state,
                                                               const int *__restrict__ segList, int segsPerRow )
   {
+    pdl_prologue();
     constexpr int kBlockList = 2048;
     constexpr int U = 4;               // segments in flight per warp: the kernel is bound by the latency of one round trip per segment
     __shared__ int sList[ kBlockList ];
@@ -970,6 +973,7 @@ namespace vofx
                                                              coop::RootTask *__restrict__ rootTasks, const int *__restrict__ order,
                                                              unsigned char *__restrict__ costClass )
   {
+    pdl_prologue();
     constexpr int GROUPS = 16;          // 16 groups per block: 128 threads for L = 8, 64 for L = 4
     __shared__ coop::LocateScratch scratch[ GROUPS ];
     const int count = mixed_count( state, capacity );
@@ -1051,6 +1055,7 @@ namespace vofx
   template< int DIM >
   __global__ void __launch_bounds__( 128 ) k_locate_root3 ( StepState *state, int capacity, const coop::RootTask *__restrict__ rootTasks, double *__restrict__ hs )
   {
+    pdl_prologue();
     const int n = mixed_count( state, capacity );
     int mine = 0;
     for( int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x )
@@ -1074,6 +1079,7 @@ namespace vofx
   __global__ void __launch_bounds__( 64 ) k_locate_serial3 ( Grid g, const double *__restrict__ u, const StepState *state, double *__restrict__ hs,
                                                               const int *__restrict__ serialCells )
   {
+    pdl_prologue();
     const int n = state->serialLocate;
     for( int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x )
     {
@@ -1868,6 +1874,7 @@ namespace vofx
                                                               int *__restrict__ tasks, int taskCapacity, const coop::ClipCase *__restrict__ clipTable,
                                                               const double *timeOverride, const double *dtOverride )
   {
+    pdl_prologue();
     constexpr int DIM = 3, LANES = L, NFACES = 6;
     constexpr int GROUPS = 16;          // 128 threads for 8 lanes per cell, 64 for 4
     __shared__ coop::ClipCase table[ 256 ];
@@ -2067,6 +2074,7 @@ namespace vofx
                                                                         const StepState *state, FluxRecord *__restrict__ records, const int *__restrict__ tasks,
                                                                         int taskCapacity, const double *timeOverride, const double *dtOverride )
   {
+    pdl_prologue();
     constexpr int DIM = 3;
     const int n = state->serialCount;
     const double time = timeOverride ? *timeOverride : state->time;
@@ -2126,6 +2134,7 @@ namespace vofx
                                                        StepState *stateRW, int *__restrict__ changedIdx, double *__restrict__ changedVal, int changedCapacity,
                                                        unsigned char *__restrict__ marks, int segsPerRow, CommPeers peers )
   {
+    pdl_prologue();
     constexpr int LANES = ( DIM == 3 ) ? 8 : 8;
     constexpr int NFACES = 2 * DIM;
     const int count = mixed_count( state, capacity );
@@ -2374,6 +2383,7 @@ namespace vofx
 
   static __global__ void k_finalize ( StepState *state, double cfl )
   {
+    pdl_prologue();
     finalize_state( state, cfl );
   }
 
@@ -2423,6 +2433,7 @@ namespace vofx
   static __global__ void __launch_bounds__( 256 ) k_cost_order ( const int *__restrict__ mixedList, StepState *state, int capacity,
                                                                   const unsigned char *__restrict__ costClass, int *__restrict__ order )
   {
+    pdl_prologue();
     __shared__ int warpSlow[ 8 ], warpNormal[ 8 ], baseSlow, baseNormal;
     const int count = mixed_count( state, capacity );
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

@@ -10,6 +10,27 @@ namespace vofx
 {
   namespace launch
   {
+#if defined( __CUDACC__ )
+    // kernel<<< grid, block, 0, s >>>( args... ) with the programmatic-serialisation attribute (see pdl_prologue, vofx_math.cuh):
+    // for the kernels of the loop pass, every one of which starts with pdl_prologue().  Only with VOFX_PDL=1 (measured slower).
+    bool pdl_enabled ();
+    template< class... P, class... A >
+    inline void pdl ( void ( *kernel )( P... ), dim3 grid, dim3 block, cudaStream_t s, A &&... args )
+    {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = grid;
+      cfg.blockDim = block;
+      cfg.dynamicSmemBytes = 0;
+      cfg.stream = s;
+      cudaLaunchAttribute attr[ 1 ];
+      attr[ 0 ].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[ 0 ].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = pdl_enabled() ? 1 : 0;
+      cudaLaunchKernelEx( &cfg, kernel, static_cast< P >( args )... );
+    }
+#endif
+
     // every translation unit: load its kernels now (see preload_one in k_dense.cu)
     void preload_dense ();
     void preload_band2d ();
