@@ -64,8 +64,18 @@ namespace vofx
     void finalize_dist ( cudaStream_t s, const CommPeers &P, StepState *state, double cfl ) { k_finalize_dist<<< 1, 32, 0, s >>>( P, state, cfl ); }
     void halo_push ( int blocks, cudaStream_t s, const CommPeers &P, const double *u, long long layerCells, int own0, int own1 )
     { k_halo_push<<< blocks, 256, 0, s >>>( P, u, layerCells, own0, own1 ); }
+    // incremental flagging: the marked segments were compacted by the previous pass's side branch (mark_scan)
     void reflag ( int dim, int blocks, cudaStream_t s, Grid g, const double *u, double eps, unsigned char *flags, int *mixedList, int *slot, int capacity,
-                  StepState *state, unsigned char *marks, int *segList, int segsPerRow, long long nSegments, int layer0, int layer1 )
+                  StepState *state, const int *segList, int segsPerRow )
+    {
+      if( dim == 2 )
+        pdl( k_flag_segments< 2 >, blocks, 256, s, g, u, eps, flags, mixedList, slot, capacity, state, segList, segsPerRow );
+      else
+        pdl( k_flag_segments< 3 >, blocks, 256, s, g, u, eps, flags, mixedList, slot, capacity, state, segList, segsPerRow );
+    }
+    // side branch of a pass: marks from the band in flight, then their compaction into the segment list of the next pass
+    void mark_scan ( int dim, int blocks, cudaStream_t s, Grid g, const int *mixedList, int capacity, StepState *state, unsigned char *marks, int *segList,
+                     int segsPerRow, long long nSegments, int layer0, int layer1 )
     {
       const long long chunks = ( nSegments + 15 ) / 16;
       long long scanBlocks = ( chunks + 255 ) / 256;
@@ -73,13 +83,13 @@ namespace vofx
         scanBlocks = blocks;
       if( dim == 2 )
       {
-        pdl( k_scan_marks< 2 >, (int) scanBlocks, 256, s, g, marks, segsPerRow, nSegments, layer0, layer1, segList, state );
-        pdl( k_flag_segments< 2 >, blocks, 256, s, g, u, eps, flags, mixedList, slot, capacity, state, segList, segsPerRow );
+        k_mark_band< 2 ><<< blocks, 256, 0, s >>>( g, mixedList, state, capacity, marks, segsPerRow );
+        k_scan_marks< 2 ><<< (int) scanBlocks, 256, 0, s >>>( g, marks, segsPerRow, nSegments, layer0, layer1, segList, state );
       }
       else
       {
-        pdl( k_scan_marks< 3 >, (int) scanBlocks, 256, s, g, marks, segsPerRow, nSegments, layer0, layer1, segList, state );
-        pdl( k_flag_segments< 3 >, blocks, 256, s, g, u, eps, flags, mixedList, slot, capacity, state, segList, segsPerRow );
+        k_mark_band< 3 ><<< blocks, 256, 0, s >>>( g, mixedList, state, capacity, marks, segsPerRow );
+        k_scan_marks< 3 ><<< (int) scanBlocks, 256, 0, s >>>( g, marks, segsPerRow, nSegments, layer0, layer1, segList, state );
       }
     }
     void curvature_local ( int dim, int blocks, cudaStream_t s, Grid g, const double *u, const double *hs, const int *mixedList, const StepState *state,
@@ -132,6 +142,8 @@ namespace vofx
       preload_one( k_compact_flags< 3 > );
       preload_one( k_update< 2 > );
       preload_one( k_update< 3 > );
+      preload_one( k_mark_band< 2 > );
+      preload_one( k_mark_band< 3 > );
       preload_one( k_scan_marks< 2 > );
       preload_one( k_scan_marks< 3 > );
       preload_one( k_flag_segments< 2 > );

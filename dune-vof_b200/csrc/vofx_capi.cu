@@ -87,6 +87,9 @@ struct vofx_ctx
   // last finished pass ran on (the flags / band list are only reusable for exactly those)
   unsigned char *marks = nullptr;
   int *segList = nullptr;
+  cudaStream_t sideStream = nullptr;      // side branch of a pass: k_mark_band + k_scan_marks next to the band kernels
+  cudaEvent_t evFork = nullptr, evJoin = nullptr;
+  bool sidePending = false;               // the side branch of the pass in flight has not been joined yet
   int segsPerRow = 0;
   long long nSegments = 0;
   bool incremental = false;
@@ -325,11 +328,47 @@ namespace
     if( !inc )
       return launchFlag( ctx, u, p->eps, flags, true, in0, in1 );
     profBegin( ctx );
-    // the previous pass's update marked the row segments within two face steps of its band
-    launch::reflag( g.dim, ctx->numSMs * 8, ctx->stream, g, u, p->eps, flags, ctx->mixedList, ctx->slot, ctx->capacity, ctx->state, ctx->marks,
-                    ctx->segList, ctx->segsPerRow, ctx->nSegments, in0, in1 );
-    ctx->launches += 1;
+    // the previous pass's side branch marked the row segments within two face steps of its band and listed them
+    launch::reflag( g.dim, ctx->numSMs * 8, ctx->stream, g, u, p->eps, flags, ctx->mixedList, ctx->slot, ctx->capacity, ctx->state, ctx->segList, ctx->segsPerRow );
     return checkLaunch( ctx, "k_reflag" );
+  }
+
+  // Side branch of a pass (incremental flagging): once the band list of the pass is complete, k_mark_band and k_scan_marks
+  // prepare the NEXT pass's segment list on a second stream, next to reconstruction, fluxes and update; joinSide() brings
+  // the branch back before the pass ends (inside a stream capture this is a fork / join of the graph).
+  int forkSide ( vofx_ctx *ctx, const double *u, const unsigned char *flags )
+  {
+    if( !ctx->incremental || !ctx->marks )
+      return VOFX_OK;
+    const Grid &g = ctx->grid;
+    if( ctx->desc.halo > 0 && !( flagByRows( ctx, u, flags ) && g.own1 - g.own0 > 2 ) )
+      return VOFX_OK;                        // thin slab: always flagged densely
+    if( !ctx->sideStream )
+    {
+      VOFX_CUDA( cudaStreamCreateWithFlags( &ctx->sideStream, cudaStreamNonBlocking ) );
+      VOFX_CUDA( cudaEventCreateWithFlags( &ctx->evFork, cudaEventDisableTiming ) );
+      VOFX_CUDA( cudaEventCreateWithFlags( &ctx->evJoin, cudaEventDisableTiming ) );
+    }
+    const bool split = ctx->desc.halo > 0;
+    const int in0 = split ? g.own0 + 1 : 0, in1 = split ? g.own1 - 1 : g.ns[ g.dim - 1 ];
+    VOFX_CUDA( cudaEventRecord( ctx->evFork, ctx->stream ) );
+    VOFX_CUDA( cudaStreamWaitEvent( ctx->sideStream, ctx->evFork, 0 ) );
+    launch::mark_scan( g.dim, ctx->numSMs * 4, ctx->sideStream, g, ctx->mixedList, ctx->capacity, ctx->state, ctx->marks, ctx->segList, ctx->segsPerRow,
+                       ctx->nSegments, in0, in1 );
+    ctx->launches += 2;
+    VOFX_CUDA( cudaGetLastError() );
+    VOFX_CUDA( cudaEventRecord( ctx->evJoin, ctx->sideStream ) );
+    ctx->sidePending = true;
+    return VOFX_OK;
+  }
+
+  int joinSide ( vofx_ctx *ctx )
+  {
+    if( !ctx->sidePending )
+      return VOFX_OK;
+    VOFX_CUDA( cudaStreamWaitEvent( ctx->stream, ctx->evJoin, 0 ) );
+    ctx->sidePending = false;
+    return VOFX_OK;
   }
 
   // the pass that was just issued leaves flags / band list / previous-band list valid for ( u, flags )
@@ -489,7 +528,7 @@ namespace
     const bool track = accumulate && ctx->trackChanges && ctx->changedIdx;
     launch::update( g.dim, blocks, ctx->stream, g, flags, ctx->mixedList, ctx->slot, ctx->state, ctx->capacity, ctx->records, target, accumulate ? 1 : 0,
                     ctx->state, track ? ctx->changedIdx : nullptr, track ? ctx->changedVal : nullptr, ctx->changedCapacity,
-                    ( accumulate && ctx->incremental ) ? ctx->marks : nullptr, ctx->segsPerRow,
+                    nullptr, ctx->segsPerRow,
                     ( accumulate && ctx->commConnected && target == ctx->dU ) ? &ctx->peers : nullptr );
     return checkLaunch( ctx, "k_update" );
   }
@@ -793,6 +832,12 @@ extern "C"
     cudaFree( ctx->order );
     cudaFree( ctx->marks );
     cudaFree( ctx->segList );
+    if( ctx->sideStream )
+      cudaStreamDestroy( ctx->sideStream );
+    if( ctx->evFork )
+      cudaEventDestroy( ctx->evFork );
+    if( ctx->evJoin )
+      cudaEventDestroy( ctx->evJoin );
     cudaFree( ctx->swzCells );
     cudaFree( ctx->swzTasks );
     cudaFree( ctx->swzCounter );
@@ -1312,6 +1357,7 @@ extern "C"
       if( ctx->desc.halo == 0 )
         rc = launchStepFlags( ctx, p, u, flags, 0 );
       rc = rc ? rc : launchStepFlags( ctx, p, u, flags, 1 );
+      rc = rc ? rc : forkSide( ctx, u, flags );
       rc = rc ? rc : launchReconstruct( ctx, p->reconstruction, u, flags, halfspaces, p->max_iterations );
       if( !rc && p->with_curvature )
         rc = launchCurvature( ctx, u, halfspaces, flags, kappa, nullptr, true );
@@ -1332,6 +1378,7 @@ extern "C"
     // algorithm.hh:75-83: flagOperator, reconstructionOperator, evolutionOperator, uh.axpy( 1.0, update )
     rc = rc ? rc : launchStepFlags( ctx, p, u, flags, 0 );
     rc = rc ? rc : launchStepFlags( ctx, p, u, flags, 1 );
+    rc = rc ? rc : forkSide( ctx, u, flags );
     rc = rc ? rc : launchReconstruct( ctx, p->reconstruction, u, flags, halfspaces, p->max_iterations );
     if( !rc && p->with_curvature )
       rc = launchCurvature( ctx, u, halfspaces, flags, kappa, nullptr, true );
@@ -1347,6 +1394,7 @@ extern "C"
     if( !ctx || !p )
       return fail( VOFX_ERR_ARGUMENT, "null argument" );
     int rc = setDevice( ctx );
+    rc = rc ? rc : joinSide( ctx );
     if( rc )
       return rc;
     profBegin( ctx );
@@ -2076,7 +2124,8 @@ extern "C"
         launch::comm_wait_halo( ctx->stream, ctx->peers, ctx->state );
         rc = checkLaunch( ctx, "k_comm_wait_halo" );
       }
-      return rc ? rc : launchStepFlags( ctx, p, u, flags, 1 );
+      rc = rc ? rc : launchStepFlags( ctx, p, u, flags, 1 );
+      return rc ? rc : forkSide( ctx, u, flags );
     }
     rc = requireVelocity( ctx );
     rc = rc ? rc : launchReconstruct( ctx, p->reconstruction, u, flags, ctx->dHs, p->max_iterations );
@@ -2095,6 +2144,9 @@ extern "C"
     if( rc )
       return rc;
     notePassIssued( ctx, u, flags );
+    rc = joinSide( ctx );
+    if( rc )
+      return rc;
     profBegin( ctx );
     if( ctx->commConnected )
     {

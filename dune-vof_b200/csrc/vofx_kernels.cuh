@@ -397,6 +397,26 @@ namespace vofx
     }
   }
 
+  // the band of the pass in flight marks the segments the NEXT pass has to re-flag.  Runs on a side branch of the pass (it only
+  // reads the band list), next to the reconstruction and the fluxes, and is followed there by k_scan_marks.
+  template< int DIM >
+  __global__ void __launch_bounds__( 256 ) k_mark_band ( Grid g, const int *__restrict__ mixedList, StepState *state, int capacity,
+                                                          unsigned char *__restrict__ marks, int segsPerRow )
+  {
+    constexpr int LANES = 8;
+    if( blockIdx.x == 0 && threadIdx.x == 0 )
+      state->segCount = 0;                      // k_scan_marks (next on this branch) counts from zero
+    const int count = mixed_count( state, capacity );
+    const int lane = threadIdx.x % LANES;
+    const int groupsPerBlock = blockDim.x / LANES;
+    for( int idx = blockIdx.x * groupsPerBlock + threadIdx.x / LANES; idx < count; idx += gridDim.x * groupsPerBlock )
+    {
+      int ijk[ 3 ];
+      cell_ijk( g, mixedList[ idx ], ijk );
+      mark_band_cell< DIM >( g, ijk, lane, LANES, marks, segsPerRow );
+    }
+  }
+
   // compaction of the marks into a list of segment ids (and reset of the marks): a warp that worked through its own marked
   // segments one after the other was bound by a handful of warps whose 32 marks all lay on the sphere.  A thread owns 16
   // marks (one 16-byte load; the array is padded to a multiple of 16 zero bytes).
@@ -470,8 +490,11 @@ namespace vofx
     }
   }
 
+#ifndef VOFX_FLAGSEG_BLOCKS
+#define VOFX_FLAGSEG_BLOCKS 4     // resident blocks per SM the register allocation aims for (92 registers allowed only 2)
+#endif
   template< int DIM >
-  __global__ void __launch_bounds__( 256 ) k_flag_segments ( Grid g, const double *__restrict__ u, double eps, unsigned char *__restrict__ flags,
+  __global__ void __launch_bounds__( 256, VOFX_FLAGSEG_BLOCKS ) k_flag_segments ( Grid g, const double *__restrict__ u, double eps, unsigned char *__restrict__ flags,
                                                               int *__restrict__ mixedList, int *__restrict__ slot, int capacity, StepState *state,
                                                               const int *__restrict__ segList, int segsPerRow )
   {
@@ -2145,8 +2168,6 @@ namespace vofx
       const long long m = mixedList[ idx ];
       int mijk[ 3 ];
       cell_ijk( g, m, mijk );
-      if( marks )
-        mark_band_cell< DIM >( g, mijk, lane, LANES, marks, segsPerRow );   // seeds the next pass's incremental flagging
       if( lane > NFACES )
         continue;
       int x[ 3 ] = { mijk[ 0 ], mijk[ 1 ], mijk[ 2 ] };
@@ -2403,7 +2424,6 @@ namespace vofx
     state->mixedCount = 0;
     state->changedCountLast = state->changedCount;
     state->changedCount = 0;
-    state->segCount = 0;
     state->taskCount = 0;
     state->serialCount = 0;
     state->serialLocate = 0;

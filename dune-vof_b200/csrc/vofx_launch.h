@@ -56,9 +56,11 @@ namespace vofx
     void comm_flux_done ( cudaStream_t s, const CommPeers &P, StepState *state );
     void finalize_dist ( cudaStream_t s, const CommPeers &P, StepState *state, double cfl );
     void halo_push ( int blocks, cudaStream_t s, const CommPeers &P, const double *u, long long layerCells, int own0, int own1 );
-    // incremental flagging: k_scan_marks + k_flag_segments (the marks are set by the previous pass's k_update)
+    // incremental flagging: k_flag_segments on the segment list the previous pass's side branch (k_mark_band + k_scan_marks) left
     void reflag ( int dim, int blocks, cudaStream_t s, Grid g, const double *u, double eps, unsigned char *flags, int *mixedList, int *slot, int capacity,
-                  StepState *state, unsigned char *marks, int *segList, int segsPerRow, long long nSegments, int layer0, int layer1 );
+                  StepState *state, const int *segList, int segsPerRow );
+    void mark_scan ( int dim, int blocks, cudaStream_t s, Grid g, const int *mixedList, int capacity, StepState *state, unsigned char *marks, int *segList,
+                     int segsPerRow, long long nSegments, int layer0, int layer1 );
     void curvature_local ( int dim, int blocks, cudaStream_t s, Grid g, const double *u, const double *hs, const int *mixedList, const StepState *state,
                            int capacity, double *curv1, unsigned char *ok1 );
     void curvature_average ( int dim, int blocks, cudaStream_t s, Grid g, const unsigned char *flags, const int *mixedList, const int *slot,
