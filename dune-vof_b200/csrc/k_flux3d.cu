@@ -11,14 +11,18 @@ namespace vofx
     { k_flux< 3 ><<< blocks, 128, 0, s >>>( g, velocity, hs, flags, mixedList, state, capacity, records, timeOverride, dtOverride ); }
     void flux_cell3 ( int lanes, int blocks, cudaStream_t s, Grid g, const Velocity *velocity, const Velocity &velocityByValue, const double *hs, const unsigned char *flags, const int *mixedList,
                       StepState *state, int capacity, FluxRecord *records, int *tasks, int taskCapacity, const void *clipTable,
-                      const double *timeOverride, const double *dtOverride )
+                      const double *timeOverride, const double *dtOverride, const int *order, BandPart bp, int withSerialClips )
     {
       if( lanes == 4 )
-        pdl( k_flux_cell3< 3, 4 >, blocks * 2, 64, s, g, velocityByValue, hs, flags, mixedList, state, capacity, records, tasks, taskCapacity, (const coop::ClipCase *) clipTable, timeOverride, dtOverride );
+        pdl( k_flux_cell3< 3, 4 >, blocks * 2, 64, s, g, velocityByValue, hs, flags, mixedList, state, capacity, records, tasks, taskCapacity, (const coop::ClipCase *) clipTable, timeOverride, dtOverride, order, bp );
       else
-        pdl( k_flux_cell3< 3, 8 >, blocks, 128, s, g, velocityByValue, hs, flags, mixedList, state, capacity, records, tasks, taskCapacity, (const coop::ClipCase *) clipTable, timeOverride, dtOverride );
-      pdl( k_flux_clip_serial3< 3 >, 148, 64, s, g, velocity, hs, flags, mixedList, state, records, tasks, taskCapacity, timeOverride, dtOverride );
+        pdl( k_flux_cell3< 3, 8 >, blocks, 128, s, g, velocityByValue, hs, flags, mixedList, state, capacity, records, tasks, taskCapacity, (const coop::ClipCase *) clipTable, timeOverride, dtOverride, order, bp );
+      if( withSerialClips )
+        flux_clip_serial3( s, g, velocity, hs, flags, mixedList, state, records, tasks, taskCapacity, timeOverride, dtOverride );
     }
+    void flux_clip_serial3 ( cudaStream_t s, Grid g, const Velocity *velocity, const double *hs, const unsigned char *flags, const int *mixedList,
+                             StepState *state, FluxRecord *records, int *tasks, int taskCapacity, const double *timeOverride, const double *dtOverride )
+    { pdl( k_flux_clip_serial3< 3 >, 148, 64, s, g, velocity, hs, flags, mixedList, state, records, tasks, taskCapacity, timeOverride, dtOverride ); }
     size_t clip_table_bytes () { return sizeof( coop::ClipCase ) * ( 256 + coop::kClipBoundaryCases ); }
     void make_clip_table ( void *host )
     {

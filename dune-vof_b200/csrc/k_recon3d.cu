@@ -9,24 +9,24 @@ namespace vofx
     void youngs3 ( int blocks, cudaStream_t s, Grid g, const double *u, const int *mixedList, const StepState *state, int capacity, double *hs )
     { k_youngs< 3 ><<< blocks, 128, 0, s >>>( g, u, mixedList, state, capacity, hs ); }
     void youngs_coop3 ( int lanes, int blocks, cudaStream_t s, Grid g, const double *u, const int *mixedList, StepState *state, int capacity, double *hs,
-                        const void *sweepTable, int *serialCells, void *rootTasks, int heightFunction, const int *order, unsigned char *costClass )
+                        const void *sweepTable, int *serialCells, void *rootTasks, int heightFunction, const int *order, unsigned char *costClass, BandPart bp )
     {
       const coop::SweepTable *T = (const coop::SweepTable *) sweepTable;
       coop::RootTask *R = (coop::RootTask *) rootTasks;
       if( lanes == 4 && !heightFunction )
-        pdl( k_youngs_coop3< 4, false >, blocks * 2, 64, s, g, u, mixedList, state, capacity, hs, T, serialCells, R, order, costClass );
+        pdl( k_youngs_coop3< 4, false >, blocks * 2, 64, s, g, u, mixedList, state, capacity, hs, T, serialCells, R, order, costClass, bp );
       else if( lanes == 4 )
-        pdl( k_youngs_coop3< 4, true >, blocks * 2, 64, s, g, u, mixedList, state, capacity, hs, T, serialCells, R, order, costClass );
+        pdl( k_youngs_coop3< 4, true >, blocks * 2, 64, s, g, u, mixedList, state, capacity, hs, T, serialCells, R, order, costClass, bp );
       else if( !heightFunction )
-        pdl( k_youngs_coop3< 8, false >, blocks, 128, s, g, u, mixedList, state, capacity, hs, T, serialCells, R, order, costClass );
+        pdl( k_youngs_coop3< 8, false >, blocks, 128, s, g, u, mixedList, state, capacity, hs, T, serialCells, R, order, costClass, bp );
       else
-        pdl( k_youngs_coop3< 8, true >, blocks, 128, s, g, u, mixedList, state, capacity, hs, T, serialCells, R, order, costClass );
+        pdl( k_youngs_coop3< 8, true >, blocks, 128, s, g, u, mixedList, state, capacity, hs, T, serialCells, R, order, costClass, bp );
     }
-    void locate_root3 ( int blocks, cudaStream_t s, StepState *state, int capacity, const void *rootTasks, double *hs )
-    { pdl( k_locate_root3< 3 >, blocks, 128, s, state, capacity, (const coop::RootTask *) rootTasks, hs ); }
+    void locate_root3 ( int blocks, cudaStream_t s, StepState *state, int capacity, const void *rootTasks, double *hs, BandPart bp )
+    { pdl( k_locate_root3< 3 >, blocks, 128, s, state, capacity, (const coop::RootTask *) rootTasks, hs, bp ); }
     size_t root_task_bytes () { return sizeof( coop::RootTask ); }
-    void locate_serial3 ( cudaStream_t s, Grid g, const double *u, const StepState *state, double *hs, const int *serialCells )
-    { pdl( k_locate_serial3< 3 >, 148, 64, s, g, u, state, hs, serialCells ); }
+    void locate_serial3 ( cudaStream_t s, Grid g, const double *u, const StepState *state, double *hs, const int *serialCells, int capacity, BandPart bp )
+    { pdl( k_locate_serial3< 3 >, 148, 64, s, g, u, state, hs, serialCells, capacity, bp ); }
     int make_sweep_table ( void *host, size_t bytes )
     {
       if( bytes < sizeof( coop::SweepTable ) )

@@ -90,6 +90,10 @@ struct vofx_ctx
   cudaStream_t sideStream = nullptr;      // side branch of a pass: k_mark_band + k_scan_marks next to the band kernels
   cudaEvent_t evFork = nullptr, evJoin = nullptr;
   bool sidePending = false;               // the side branch of the pass in flight has not been joined yet
+  // band parts (BandPart, vofx_types.cuh): the chains plane-constant solve -> root search -> fluxes of a pass on own streams
+  int bandParts = 2;                      // VOFX_BAND_PARTS, read at creation; measured at 512^3 (ms per step, 20 / 200 steps): 1 chain 0.536 / 0.606, 2 chains 0.531 / 0.599, 3 and 4 chains slower (0.585 / 0.672 before the kernels shrank)
+  cudaStream_t partStream[ kMaxBandParts ] = { nullptr, nullptr, nullptr, nullptr };
+  cudaEvent_t evBandFork = nullptr, evBandJoin[ kMaxBandParts ] = { nullptr, nullptr, nullptr, nullptr };
   int segsPerRow = 0;
   long long nSegments = 0;
   bool incremental = false;
@@ -440,7 +444,7 @@ namespace
         return rc3;
       // cells whose walk hits a state the reference leaves undefined (never seen on the BASELINE configs): serial kernel
       profBegin( ctx );
-      launch::locate_serial3( ctx->stream, g, u, ctx->state, hs, ctx->serialCells );
+      launch::locate_serial3( ctx->stream, g, u, ctx->state, hs, ctx->serialCells, ctx->capacity );
     }
     int rc = checkLaunch( ctx, g.dim == 2 ? "k_youngs" : "k_locate_serial" );
     if( rc )
@@ -520,6 +524,74 @@ namespace
     return checkLaunch( ctx, "k_flux" );
   }
 
+  int launchCurvature ( vofx_ctx *ctx, const double *u, const double *hs, const unsigned char *flags, double *kappa, unsigned char *valid, bool sparseClear );
+
+  // Reconstruction and fluxes of a loop pass.  3D Young's / height functions without curvature: `bandParts` chains
+  // ( plane-constant solve -> root search -> serial leftovers -> fluxes ) on as many streams, joined before the update
+  // (BandPart, vofx_types.cuh); everything else: one kernel after the other on the context's stream.
+  int launchBand ( vofx_ctx *ctx, const vofx_step_params *p, const double *u, const unsigned char *flags, double *hs, double *kappa )
+  {
+    const Grid &g = ctx->grid;
+    const int kind = p->reconstruction;
+    const int parts = ctx->bandParts;
+    const bool chains = parts > 1 && g.dim == 3 && ( kind == VOFX_RECON_YOUNGS || kind == VOFX_RECON_HF ) && !p->with_curvature
+                        && !ctx->profiling;      // the per-kernel event pairs of vofx_profile_* time one kernel after the other
+    if( !chains )
+    {
+      int rc = launchReconstruct( ctx, kind, u, flags, hs, p->max_iterations );
+      if( !rc && p->with_curvature )
+        rc = launchCurvature( ctx, u, hs, flags, kappa, nullptr, true );
+      return rc ? rc : launchFlux( ctx, hs, flags, nullptr, nullptr );
+    }
+    if( !ctx->evBandFork )
+    {
+      int least = 0, greatest = 0;
+      VOFX_CUDA( cudaDeviceGetStreamPriorityRange( &least, &greatest ) );
+      for( int q = 0; q < parts; ++q )
+      {
+        // the chain that started first runs at the highest priority: its successors fill what it leaves free
+        const int prio = ( greatest + q < least ) ? greatest + q : least;
+        VOFX_CUDA( cudaStreamCreateWithPriority( &ctx->partStream[ q ], cudaStreamNonBlocking, prio ) );
+        VOFX_CUDA( cudaEventCreateWithFlags( &ctx->evBandJoin[ q ], cudaEventDisableTiming ) );
+      }
+      VOFX_CUDA( cudaEventCreateWithFlags( &ctx->evBandFork, cudaEventDisableTiming ) );
+    }
+    const bool hf3 = ( kind == VOFX_RECON_HF );
+    const bool ordered = ctx->costOrder && ctx->order && ctx->costClass;
+    if( ordered )
+    {
+      launch::cost_order( ctx->numSMs * 2, ctx->stream, ctx->mixedList, ctx->state, ctx->capacity, ctx->costClass, ctx->order );
+      int rc = checkLaunch( ctx, "k_cost_order" );
+      if( rc )
+        return rc;
+    }
+    const int *order = ordered ? ctx->order : nullptr;
+    VOFX_CUDA( cudaEventRecord( ctx->evBandFork, ctx->stream ) );
+    for( int q = 0; q < parts; ++q )
+    {
+      cudaStream_t s = ctx->partStream[ q ];
+      BandPart bp;
+      bp.part = q;
+      bp.parts = parts;
+      VOFX_CUDA( cudaStreamWaitEvent( s, ctx->evBandFork, 0 ) );
+      const int yBlocks = ( ctx->numSMs * ctx->youngsBlocksPerSM / 2 + parts - 1 ) / parts;
+      launch::youngs_coop3( ctx->lanesPerCell, yBlocks, s, g, u, ctx->mixedList, ctx->state, ctx->capacity, hs, ctx->sweepTable, ctx->serialCells, ctx->rootTasks,
+                            hf3 ? 1 : 0, order, ctx->costClass, bp );
+      launch::locate_root3( ( ctx->numSMs * 8 + parts - 1 ) / parts, s, ctx->state, ctx->capacity, ctx->rootTasks, hs, bp );
+      launch::locate_serial3( s, g, u, ctx->state, hs, ctx->serialCells, ctx->capacity, bp );
+      launch::flux_cell3( ctx->fluxLanes, ( ctx->numSMs * ctx->fluxBlocksPerSM + parts - 1 ) / parts, s, g, ctx->velDev, ctx->velHost, hs, flags, ctx->mixedList, ctx->state,
+                          ctx->capacity, ctx->records, ctx->tasks, ctx->taskCapacity, ctx->clipTable, nullptr, nullptr, order, bp, 0 );
+      ctx->launches += 4;
+      VOFX_CUDA( cudaGetLastError() );
+      VOFX_CUDA( cudaEventRecord( ctx->evBandJoin[ q ], s ) );
+    }
+    for( int q = 0; q < parts; ++q )
+      VOFX_CUDA( cudaStreamWaitEvent( ctx->stream, ctx->evBandJoin[ q ], 0 ) );
+    // the clips no chain could take from its table (a handful per step)
+    launch::flux_clip_serial3( ctx->stream, g, ctx->velDev, hs, flags, ctx->mixedList, ctx->state, ctx->records, ctx->tasks, ctx->taskCapacity, nullptr, nullptr );
+    return checkLaunch( ctx, "k_flux_clip_serial" );
+  }
+
   int launchUpdate ( vofx_ctx *ctx, const unsigned char *flags, double *target, bool accumulate )
   {
     const Grid &g = ctx->grid;
@@ -534,7 +606,7 @@ namespace
   }
 
   int launchCurvature ( vofx_ctx *ctx, const double *u, const double *hs, const unsigned char *flags, double *kappa, unsigned char *valid,
-                        bool sparseClear = false )
+                        bool sparseClear )
   {
     const Grid &g = ctx->grid;
     const int blocks = ctx->numSMs * 8;
@@ -754,7 +826,7 @@ extern "C"
       alloc( (void **) &ctx->tasks, sizeof( int ) * (size_t) ctx->taskCapacity );
       alloc( (void **) &ctx->clipTable, launch::clip_table_bytes() );
       alloc( (void **) &ctx->sweepTable, launch::sweep_table_bytes() );
-      alloc( (void **) &ctx->serialCells, sizeof( int ) * (size_t) ctx->capacity );
+      alloc( (void **) &ctx->serialCells, sizeof( int ) * ( (size_t) ctx->capacity + 2 * kMaxBandParts ) );   // one region per band part
       alloc( (void **) &ctx->rootTasks, launch::root_task_bytes() * (size_t) ctx->capacity );
       alloc( (void **) &ctx->costClass, (size_t) g.cells );
       alloc( (void **) &ctx->order, sizeof( int ) * (size_t) ctx->capacity );
@@ -788,6 +860,8 @@ extern "C"
       cudaMemcpy( ctx->sweepTable, table.data(), table.size(), cudaMemcpyHostToDevice );
       if( const char *env = std::getenv( "VOFX_FLUX_LANES" ) )
         ctx->fluxLanes = ( std::atoi( env ) == 4 ) ? 4 : 8;
+      if( const char *env = std::getenv( "VOFX_BAND_PARTS" ) )
+        ctx->bandParts = std::atoi( env ) < 1 ? 1 : ( std::atoi( env ) > kMaxBandParts ? kMaxBandParts : std::atoi( env ) );
       if( std::getenv( "VOFX_NO_COST_ORDER" ) )
         ctx->costOrder = false;
       if( const char *env = std::getenv( "VOFX_FLUX_BLOCKS_PER_SM" ) )
@@ -838,6 +912,15 @@ extern "C"
       cudaEventDestroy( ctx->evFork );
     if( ctx->evJoin )
       cudaEventDestroy( ctx->evJoin );
+    for( int q = 0; q < kMaxBandParts; ++q )
+    {
+      if( ctx->partStream[ q ] )
+        cudaStreamDestroy( ctx->partStream[ q ] );
+      if( ctx->evBandJoin[ q ] )
+        cudaEventDestroy( ctx->evBandJoin[ q ] );
+    }
+    if( ctx->evBandFork )
+      cudaEventDestroy( ctx->evBandFork );
     cudaFree( ctx->swzCells );
     cudaFree( ctx->swzTasks );
     cudaFree( ctx->swzCounter );
@@ -1257,7 +1340,7 @@ extern "C"
     int rc = setDevice( ctx );
     rc = rc ? rc : launchResetCounters( ctx );
     rc = rc ? rc : launchCompactFlags( ctx, flags );
-    rc = rc ? rc : launchCurvature( ctx, u, halfspaces, flags, kappa, valid );
+    rc = rc ? rc : launchCurvature( ctx, u, halfspaces, flags, kappa, valid, false );
     if( rc )
       return rc;
     StepState s;
@@ -1358,10 +1441,7 @@ extern "C"
         rc = launchStepFlags( ctx, p, u, flags, 0 );
       rc = rc ? rc : launchStepFlags( ctx, p, u, flags, 1 );
       rc = rc ? rc : forkSide( ctx, u, flags );
-      rc = rc ? rc : launchReconstruct( ctx, p->reconstruction, u, flags, halfspaces, p->max_iterations );
-      if( !rc && p->with_curvature )
-        rc = launchCurvature( ctx, u, halfspaces, flags, kappa, nullptr, true );
-      return rc ? rc : launchFlux( ctx, halfspaces, flags, nullptr, nullptr );
+      return rc ? rc : launchBand( ctx, p, u, flags, halfspaces, kappa );
     }
     rc = launchUpdate( ctx, flags, u, true );   // uh.axpy( 1.0, update ), algorithm.hh:83
     if( !rc )
@@ -1379,10 +1459,7 @@ extern "C"
     rc = rc ? rc : launchStepFlags( ctx, p, u, flags, 0 );
     rc = rc ? rc : launchStepFlags( ctx, p, u, flags, 1 );
     rc = rc ? rc : forkSide( ctx, u, flags );
-    rc = rc ? rc : launchReconstruct( ctx, p->reconstruction, u, flags, halfspaces, p->max_iterations );
-    if( !rc && p->with_curvature )
-      rc = launchCurvature( ctx, u, halfspaces, flags, kappa, nullptr, true );
-    rc = rc ? rc : launchFlux( ctx, halfspaces, flags, nullptr, nullptr );
+    rc = rc ? rc : launchBand( ctx, p, u, flags, halfspaces, kappa );
     rc = rc ? rc : launchUpdate( ctx, flags, u, true );
     if( !rc )
       notePassIssued( ctx, u, flags );
@@ -1502,7 +1579,7 @@ extern "C"
     rc = readState( ctx, s );
     out[ 0 ] = s.mixedCount;
     out[ 1 ] = s.serialCount;
-    out[ 2 ] = s.serialLocate;
+    out[ 2 ] = s.serialLocate + s.serialLocateMore[ 0 ] + s.serialLocateMore[ 1 ] + s.serialLocateMore[ 2 ];
     out[ 3 ] = s.rootCount;
     return rc;
   }
@@ -2128,10 +2205,7 @@ extern "C"
       return rc ? rc : forkSide( ctx, u, flags );
     }
     rc = requireVelocity( ctx );
-    rc = rc ? rc : launchReconstruct( ctx, p->reconstruction, u, flags, ctx->dHs, p->max_iterations );
-    if( !rc && p->with_curvature )
-      rc = launchCurvature( ctx, u, ctx->dHs, flags, ctx->dKappa, nullptr, true );
-    rc = rc ? rc : launchFlux( ctx, ctx->dHs, flags, nullptr, nullptr );
+    rc = rc ? rc : launchBand( ctx, p, u, flags, ctx->dHs, ctx->dKappa );
     if( rc )
       return rc;
     if( ctx->commConnected )

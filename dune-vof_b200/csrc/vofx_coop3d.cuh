@@ -570,22 +570,20 @@ namespace vofx
 
     struct LocateScratch
     {
-      double P[ 3 ][ 8 ];               // rotated nodes
       union
       {
         struct
         {
+          double P[ 3 ][ 8 ];           // rotated nodes
           double dv[ 3 ][ 12 ];         // PolygonWithDirections::directionVector of edge e = ( a, b ); the reverse edge e + 12 is
                                         // derived on read (dv_get): 1192 B per cell let 10 blocks of 16 cells share an SM
           double px[ 2 ][ 8 ], py[ 2 ][ 8 ];   // polygon nodes of the current / next bracket
-          union
-          {
-            double aterm[ kMaxATerms ]; // terms of A of the current bracket
-            double term[ 8 ];           // face terms of the cell volume (before the brackets)
-          };
+          double aterm[ kMaxATerms ];   // terms of A of the current bracket
           double bterm[ 8 ], cterm[ 8 ];   // terms of B and C of the current bracket
         };
-        double ls[ 8 ][ 9 ];            // least-squares contributions of one round of stencil slots (before the plane-constant solve)
+        // before the plane-constant solve: per stencil slot the weighted difference vector d / |d|^2 and
+        // ( colour difference ) / |d|^2 of the least-squares fit (youngs_normal_coop); zeros for a slot without a cell
+        double lsq[ 26 ][ 4 ];
       };
       union
       {
@@ -594,7 +592,7 @@ namespace vofx
       };
       double ds[ 8 ];                   // sorted node heights
       unsigned char ids[ 8 ];
-      unsigned char lsValid[ 8 ];
+      unsigned char pad8[ 8 ];
       SweepBracket walked;              // descriptor produced by the walk of lane 0 (cells with tied node heights)
     };
 
@@ -632,36 +630,60 @@ namespace vofx
     // no over/underflow: S. Boldo, "Stupid is as stupid does: taking the square root of the square of a floating-point
     // number", 2015) and c / |c| = +-1, (+-0) / s = +-0 with the sign of IEEE division: the same bits as
     // outer_normal3 / face_edge_term without a single sqrt or division.  Checked against the oracle in the CPU tests.
-    VOFX_INLINE double norm3_axis ( const double *a ) { return fabs( a[ 0 ] ) + fabs( a[ 1 ] ) + fabs( a[ 2 ] ); }
-    VOFX_INLINE double unit_axis ( double x, double s ) { return ( ( x == 0.0 ) ? x : copysign( 1.0, x ) ) * copysign( 1.0, s ); }
-
-    VOFX_INLINE void outer_normal3_axis ( const double *n0, const double *n1, const double *n2, double *normal )
+    // Carried through Polyhedron::volume (3d/polyhedron.hh:187-222,317-324) this leaves, for the face f normal to axis k with
+    // the other two axes a, b (tables below, derived from the node order of makePolyhedron's cube faces):
+    //   outerNormal          = fn e_k, fn = -1 for the lower face and +1 for the upper one
+    //   center . outerNormal = fn * ( ( ( ( 0 + c ) + c ) + c ) + c ) * 0.25 ), c = lo_k or hi_k (3 c need not be exact)
+    //   edge term q          = sign_q * ( c_q * len ), c_q = the coordinate along a or b that the edge's two nodes share
+    //                          ( ( c_q + c_q ) * 0.5 = c_q exactly ), len = | hi - lo | along the edge's own axis
+    //   Face::volume         = | ( ( ( ( 0 + t_0 ) + t_1 ) + t_2 ) + t_3 ) / 2 |
+    // i.e. 4 products and 8 additions per face instead of 5 cross products, 5 norms and 15 divisions; zero terms can only
+    // differ in the sign of a zero, which no partial sum keeps (it starts at +0) and the final | . | removes.
+    struct BoxFace
     {
-      double v1[ 3 ], v2[ 3 ];
-      for( int k = 0; k < 3; ++k )
+      signed char k, upper, a, b;       // axis of the normal, lower / upper face, axes of the even / odd edge terms' coordinates
+      signed char sign[ 4 ], hiBit[ 4 ];
+    };
+    constexpr BoxFace kBoxFace[ 6 ] = {
+      { 0, 0, 1, 2, { -1,  1, 1, -1 }, { 0, 1, 1, 0 } },
+      { 0, 1, 2, 1, { -1,  1, 1, -1 }, { 0, 1, 1, 0 } },
+      { 1, 0, 2, 0, { -1,  1, 1, -1 }, { 0, 1, 1, 0 } },
+      { 1, 1, 2, 0, { -1, -1, 1,  1 }, { 0, 0, 1, 1 } },
+      { 2, 0, 0, 1, { -1,  1, 1, -1 }, { 0, 1, 1, 0 } },
+      { 2, 1, 1, 0, { -1,  1, 1, -1 }, { 0, 1, 1, 0 } } };
+
+    // center . outerNormal * Face::volume of face F of the box [ lo, hi ]; len = hi - lo
+    template< int F >
+    VOFX_INLINE double box_face_term ( const double *lo, const double *hi, const double *len )
+    {
+      constexpr BoxFace T = kBoxFace[ F ];
+      const double ck = T.upper ? hi[ T.k ] : lo[ T.k ];
+      double center = 0.0;
+#pragma unroll
+      for( int q = 0; q < 4; ++q )
+        center += ck;
+      center *= 1.0 / 4;
+      double fv = 0.0;
+#pragma unroll
+      for( int q = 0; q < 4; ++q )
       {
-        v1[ k ] = n0[ k ] - n1[ k ];
-        v2[ k ] = n2[ k ] - n1[ k ];
+        const int m = ( q & 1 ) ? T.b : T.a, j = ( q & 1 ) ? T.a : T.b;
+        const double t = ( T.hiBit[ q ] ? hi[ m ] : lo[ m ] ) * len[ j ];
+        fv += ( T.sign[ q ] > 0 ) ? t : -t;
       }
-      cross3( v1, v2, normal );
-      const double s = -1.0 * norm3_axis( normal );
-      for( int k = 0; k < 3; ++k )
-        normal[ k ] = unit_axis( normal[ k ], s );
+      return ( T.upper ? center : -center ) * fabs( fv / 2.0 );
     }
 
-    VOFX_INLINE double face_edge_term_axis ( const double *x0, const double *x1, const double *fn )
+    // the six terms of Polyhedron::volume of the box [ lo, hi ], in face order
+    VOFX_INLINE void box_face_terms ( const double *lo, const double *hi, double *term )
     {
-      double center[ 3 ], v1[ 3 ], en[ 3 ];
-      for( int k = 0; k < 3; ++k )
-      {
-        center[ k ] = ( x0[ k ] + x1[ k ] ) * 0.5;
-        v1[ k ] = x1[ k ] - x0[ k ];
-      }
-      cross3( v1, fn, en );
-      const double nrm = norm3_axis( en );
-      for( int k = 0; k < 3; ++k )
-        en[ k ] = unit_axis( en[ k ], nrm );
-      return dot3( center, en ) * norm3_axis( v1 );
+      const double len[ 3 ] = { hi[ 0 ] - lo[ 0 ], hi[ 1 ] - lo[ 1 ], hi[ 2 ] - lo[ 2 ] };
+      term[ 0 ] = box_face_term< 0 >( lo, hi, len );
+      term[ 1 ] = box_face_term< 1 >( lo, hi, len );
+      term[ 2 ] = box_face_term< 2 >( lo, hi, len );
+      term[ 3 ] = box_face_term< 3 >( lo, hi, len );
+      term[ 4 ] = box_face_term< 4 >( lo, hi, len );
+      term[ 5 ] = box_face_term< 5 >( lo, hi, len );
     }
 
     VOFX_INLINE void cell_node ( const double *lo, const double *hi, int i, double *x )
@@ -723,28 +745,9 @@ namespace vofx
         R[ 2 ][ 2 ] = n[ 2 ];
       }
 
-      // phase 1: face terms of the cell volume (hex_volume) and the rotated nodes
+      // phase 1: the rotated nodes
       VOFX_LANES( G, L, lane )
       {
-#pragma unroll 1
-        for( int f = lane; f < 6; f += L )
-        {
-          double x[ 4 ][ 3 ], center[ 3 ] = { 0.0, 0.0, 0.0 }, fn[ 3 ];
-          for( int k = 0; k < 4; ++k )
-          {
-            cell_node( lo, hi, cube::faceNode( f, k ), x[ k ] );
-            for( int d = 0; d < 3; ++d )
-              center[ d ] += x[ k ][ d ];
-          }
-          const double s = 1.0 / 4;
-          for( int d = 0; d < 3; ++d )
-            center[ d ] *= s;
-          outer_normal3_axis( x[ 0 ], x[ 1 ], x[ 2 ], fn );
-          double fv = 0.0;
-          for( int k = 0; k < 4; ++k )
-            fv += face_edge_term_axis( x[ k ], x[ ( k + 1 ) & 3 ], fn );
-          S.term[ f ] = dot3( center, fn ) * fabs( fv / 2.0 );
-        }
 #pragma unroll 1
         for( int i = lane; i < 8; i += L )
         {
@@ -760,9 +763,13 @@ namespace vofx
         }
       }
 
+      // the cell volume (hex_volume) in closed form, by every lane: 24 products and 48 additions
+      double faceTerm[ 6 ];
+      box_face_terms( lo, hi, faceTerm );
       double vol = 0.0;
+#pragma unroll
       for( int f = 0; f < 6; ++f )
-        vol += S.term[ f ];
+        vol += faceTerm[ f ];
       const double givenVolume = fraction * fabs( vdiv( vol, 3.0 ) );
 
       // phase 2: sort the node heights (std::sort = stable insertion sort on 8 elements: rank by (height, id)),
@@ -1090,36 +1097,82 @@ namespace vofx
         const int gi = ijk[ d ] + g.g0[ d ];
         atWall = atWall || gi == 0 || gi == g.ng[ d ] - 1;
       }
-      const int nSlots = atWall ? 32 : 26;
-#pragma unroll 1
-      for( int round = 0; round * L < nSlots; ++round )
+
+      // phase A: a lane evaluates the slots lane, lane + L, ...: ls_accumulate up to the scaled vector, i.e.
+      // weight = 1 / |d|^2, e = d * weight, wc = weight * colorDiff.  A slot without a cell contributes zeros: every sum below
+      // starts at +0 and therefore never holds -0, so adding a zero of either sign leaves it unchanged.
+      VOFX_LANES( G, L, lane )
       {
+#pragma unroll 1
+        for( int s = lane; s < 26; s += L )
+        {
+          const int m = ( s < 13 ) ? s : s + 1;
+          const int nb[ 3 ] = { ijk[ 0 ] + ( m % 3 ) - 1, ijk[ 1 ] + ( ( m / 3 ) % 3 ) - 1, ijk[ 2 ] + ( m / 9 ) - 1 };
+          double e[ 3 ] = { 0.0, 0.0, 0.0 }, wc = 0.0;
+          if( cell_exists( g, nb ) )
+          {
+            const double colorNb = clamp01( u[ cell_index( g, nb ) ] );
+            double n2 = 0.0;
+            for( int k = 0; k < 3; ++k )
+            {
+              e[ k ] = ( cell_lower( g, k, nb[ k ] ) + 0.5 * g.h[ k ] ) - center[ k ];
+              n2 += e[ k ] * e[ k ];
+            }
+            const double weight = vdiv( 1.0, n2 );
+            for( int k = 0; k < 3; ++k )
+              e[ k ] *= weight;
+            wc = weight * ( colorNb - colorEn );
+          }
+          S.lsq[ s ][ 0 ] = e[ 0 ];
+          S.lsq[ s ][ 1 ] = e[ 1 ];
+          S.lsq[ s ][ 2 ] = e[ 2 ];
+          S.lsq[ s ][ 3 ] = wc;
+        }
+      }
+      // phase B: a lane owns the sums c = lane, lane + L, ... of ( AtA_00, AtA_01, AtA_02, AtA_11, AtA_12, AtA_22, Atb_0, Atb_1,
+      // Atb_2 ) and runs over the slots in order: AtA_ij += e_i e_j (outerProduct adds the product to a zero matrix first: the
+      // same value, see above), Atb_k += wc e_k.  The operands of sum c are entries ( ia, ib ) of the slot's record.
+      VOFX_LANES( G, L, lane )
+      {
+        double acc[ kOwn ];
+        int ia[ kOwn ], ib[ kOwn ];
+#pragma unroll
+        for( int q = 0; q < kOwn; ++q )
+        {
+          const int c = lane + q * L;
+          acc[ q ] = 0.0;
+          // c:  0 1 2 3 4 5 6 7 8  ->  ia: 0 0 0 1 1 2 3 3 3,  ib: 0 1 2 1 2 2 0 1 2
+          ia[ q ] = ( c < 3 ) ? 0 : ( ( c < 5 ) ? 1 : ( ( c < 6 ) ? 2 : 3 ) );
+          ib[ q ] = ( c < 3 ) ? c : ( ( c < 5 ) ? c - 2 : ( ( c < 6 ) ? 2 : c - 6 ) );
+          if( c >= 9 )
+            ia[ q ] = ib[ q ] = 0;
+        }
+#pragma unroll 2
+        for( int s = 0; s < 26; ++s )
+        {
+#pragma unroll
+          for( int q = 0; q < kOwn; ++q )
+            acc[ q ] += S.lsq[ s ][ ia[ q ] ] * S.lsq[ s ][ ib[ q ] ];
+        }
+#pragma unroll
+        for( int q = 0; q < kOwn; ++q )
+          if( lane + q * L < 9 )
+            S.sums[ lane + q * L ] = acc[ q ];
+      }
+      if( atWall )
+      {
+        // the ghosts of the wall faces follow in face order (:112-124): d = 2 ( face centre - cell centre ), colour 0.5
         VOFX_LANES( G, L, lane )
         {
-          const int s = round * L + lane;
-          bool valid = false;
-          double d[ 3 ] = { 0.0, 0.0, 0.0 }, colorDiff = 0.0;
-          if( s < 26 )
+#pragma unroll 1
+          for( int face = lane; face < 6; face += L )
           {
-            const int m = ( s < 13 ) ? s : s + 1;
-            const int nb[ 3 ] = { ijk[ 0 ] + ( m % 3 ) - 1, ijk[ 1 ] + ( ( m / 3 ) % 3 ) - 1, ijk[ 2 ] + ( m / 9 ) - 1 };
-            if( cell_exists( g, nb ) )
-            {
-              valid = true;
-              const double colorNb = clamp01( u[ cell_index( g, nb ) ] );
-              for( int k = 0; k < 3; ++k )
-                d[ k ] = ( cell_lower( g, k, nb[ k ] ) + 0.5 * g.h[ k ] ) - center[ k ];
-              colorDiff = colorNb - colorEn;
-            }
-          }
-          else if( s < 32 )
-          {
-            const int face = s - 26;
             int nb[ 3 ] = { ijk[ 0 ], ijk[ 1 ], ijk[ 2 ] };
             nb[ face >> 1 ] += ( face & 1 ) ? 1 : -1;
+            double e[ 3 ] = { 0.0, 0.0, 0.0 }, wc = 0.0;
             if( !in_domain( g, nb ) )
             {
-              valid = true;
+              double n2 = 0.0;
               for( int k = 0; k < 3; ++k )
               {
                 double fc = lower[ k ];
@@ -1130,47 +1183,35 @@ namespace vofx
                 }
                 else
                   fc += 0.5 * g.h[ k ];
-                d[ k ] = fc - center[ k ];
-                d[ k ] *= 2.0;
+                e[ k ] = fc - center[ k ];
+                e[ k ] *= 2.0;
+                n2 += e[ k ] * e[ k ];
               }
-              colorDiff = 0.5 - colorEn;
+              const double weight = vdiv( 1.0, n2 );
+              for( int k = 0; k < 3; ++k )
+                e[ k ] *= weight;
+              wc = weight * ( 0.5 - colorEn );
             }
-          }
-          S.lsValid[ lane ] = valid ? 1 : 0;
-          if( valid )
-          {
-            // ls_accumulate: weight = 1/|d|^2, d *= weight, AtA += d d^T, Atb += weight * colorDiff * d
-            double n2 = 0.0;
-            for( int k = 0; k < 3; ++k )
-              n2 += d[ k ] * d[ k ];
-            const double weight = vdiv( 1.0, n2 );
-            for( int k = 0; k < 3; ++k )
-              d[ k ] *= weight;
-            int c = 0;
-            for( int i = 0; i < 3; ++i )
-              for( int j = i; j < 3; ++j )
-              {
-                double mm = 0.0;          // outerProduct: axpy onto a zero matrix, geometry/utility.hh:161-169
-                mm += d[ i ] * d[ j ];
-                S.ls[ lane ][ c++ ] = mm;
-              }
-            const double w = weight * colorDiff;
-            for( int k = 0; k < 3; ++k )
-              S.ls[ lane ][ 6 + k ] = w * d[ k ];
+            S.lsq[ face ][ 0 ] = e[ 0 ];
+            S.lsq[ face ][ 1 ] = e[ 1 ];
+            S.lsq[ face ][ 2 ] = e[ 2 ];
+            S.lsq[ face ][ 3 ] = wc;
           }
         }
         VOFX_LANES( G, L, lane )
         {
+#pragma unroll
           for( int q = 0; q < kOwn; ++q )
           {
             const int c = lane + q * L;
             if( c < 9 )
             {
-              double a = ( round == 0 ) ? 0.0 : S.sums[ c ];
-              for( int j = 0; j < L; ++j )
-                if( S.lsValid[ j ] )
-                  a += S.ls[ j ][ c ];
-              S.sums[ c ] = a;
+              const int a = ( c < 3 ) ? 0 : ( ( c < 5 ) ? 1 : ( ( c < 6 ) ? 2 : 3 ) );
+              const int b = ( c < 3 ) ? c : ( ( c < 5 ) ? c - 2 : ( ( c < 6 ) ? 2 : c - 6 ) );
+              double acc = S.sums[ c ];
+              for( int face = 0; face < 6; ++face )
+                acc += S.lsq[ face ][ a ] * S.lsq[ face ][ b ];
+              S.sums[ c ] = acc;
             }
           }
         }

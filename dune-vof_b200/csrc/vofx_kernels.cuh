@@ -982,6 +982,16 @@ namespace vofx
     }
   }
 
+  // per band part (BandPart, vofx_types.cuh): its counter of serially located cells and its region of the serialCells array
+  __device__ __forceinline__ int *serial_locate_counter ( StepState *state, int part )
+  {
+    return part == 0 ? &state->serialLocate : &state->serialLocateMore[ part - 1 ];
+  }
+  __host__ __device__ __forceinline__ int serial_locate_offset ( int capacity, const BandPart &bp )
+  {
+    return bp.part * ( capacity / bp.parts + 1 );      // a part holds at most ceil( capacity / parts ) cells
+  }
+
   // R1 in 3D for the B200: L lanes per mixed cell (vofx_coop3d.cuh).  The stencil contributions, the faces of the cell
   // volume, the direction vectors and the per-bracket terms of the plane-constant solve are spread over the lanes;
   // the sweep topology comes from a table of the 96 generic height orders.  Cells with tied node heights (axis-aligned
@@ -994,19 +1004,21 @@ namespace vofx
                                                              StepState *state, int capacity, double *__restrict__ hs,
                                                              const coop::SweepTable *__restrict__ table, int *__restrict__ serialCells,
                                                              coop::RootTask *__restrict__ rootTasks, const int *__restrict__ order,
-                                                             unsigned char *__restrict__ costClass )
+                                                             unsigned char *__restrict__ costClass, BandPart bp )
   {
     pdl_prologue();
     constexpr int GROUPS = 16;          // 16 groups per block: 128 threads for L = 8, 64 for L = 4
     __shared__ coop::LocateScratch scratch[ GROUPS ];
     const int count = mixed_count( state, capacity );
+    int *serialCounter = serial_locate_counter( state, bp.part );
+    serialCells += serial_locate_offset( capacity, bp );
     const int lane = threadIdx.x % L;
     const int group = threadIdx.x / L;
     coop::Group G;
     G.lane = lane;
     G.mask = ( ( L == 32 ) ? 0xffffffffu : ( ( 1u << L ) - 1u ) ) << ( ( threadIdx.x & 31 ) - lane );
     coop::LocateScratch &S = scratch[ group ];
-    for( int idx = blockIdx.x * GROUPS + group; idx < count; idx += gridDim.x * GROUPS )
+    for( int idx = ( blockIdx.x * GROUPS + group ) * bp.parts + bp.part; idx < count; idx += gridDim.x * GROUPS * bp.parts )
     {
       const int c = mixedList[ order ? order[ idx ] : idx ];     // expensive cells first and together (k_cost_order)
       int ijk[ 3 ];
@@ -1059,7 +1071,7 @@ namespace vofx
         out[ 2 ] = normal[ 2 ];
         // the root tasks sit at the cell's position in the processing order: no counter shared by 1e5 cells
         if( !located )
-          serialCells[ atomicAdd( &state->serialLocate, 1 ) ] = c;
+          serialCells[ atomicAdd( serialCounter, 1 ) ] = c;
         else if( root.pending )
         {
           root.cell = c;
@@ -1076,12 +1088,13 @@ namespace vofx
 
   // Brent's method for the cells whose bracket k_youngs_coop3 has found: one thread per cell
   template< int DIM >
-  __global__ void __launch_bounds__( 128 ) k_locate_root3 ( StepState *state, int capacity, const coop::RootTask *__restrict__ rootTasks, double *__restrict__ hs )
+  __global__ void __launch_bounds__( 128 ) k_locate_root3 ( StepState *state, int capacity, const coop::RootTask *__restrict__ rootTasks, double *__restrict__ hs,
+                                                            BandPart bp )
   {
     pdl_prologue();
     const int n = mixed_count( state, capacity );
     int mine = 0;
-    for( int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x )
+    for( int t = ( blockIdx.x * blockDim.x + threadIdx.x ) * bp.parts + bp.part; t < n; t += gridDim.x * blockDim.x * bp.parts )
     {
       if( !rootTasks[ t ].pending )
         continue;
@@ -1100,10 +1113,11 @@ namespace vofx
   // plane-constant solve by the serial walk for the cells queued by k_youngs_coop3 (normal already in hs)
   template< int DIM >
   __global__ void __launch_bounds__( 64 ) k_locate_serial3 ( Grid g, const double *__restrict__ u, const StepState *state, double *__restrict__ hs,
-                                                              const int *__restrict__ serialCells )
+                                                              const int *__restrict__ serialCells, int capacity, BandPart bp )
   {
     pdl_prologue();
-    const int n = state->serialLocate;
+    const int n = *serial_locate_counter( const_cast< StepState * >( state ), bp.part );
+    serialCells += serial_locate_offset( capacity, bp );
     for( int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x )
     {
       const int c = serialCells[ t ];
@@ -1895,7 +1909,8 @@ namespace vofx
                                                               const unsigned char *__restrict__ flags, const int *__restrict__ mixedList,
                                                               StepState *state, int capacity, FluxRecord *__restrict__ records,
                                                               int *__restrict__ tasks, int taskCapacity, const coop::ClipCase *__restrict__ clipTable,
-                                                              const double *timeOverride, const double *dtOverride )
+                                                              const double *timeOverride, const double *dtOverride,
+                                                              const int *__restrict__ order, BandPart bp )
   {
     pdl_prologue();
     constexpr int DIM = 3, LANES = L, NFACES = 6;
@@ -1925,8 +1940,11 @@ namespace vofx
     FaceScratch &F = faceScratch[ group ];
     double dtMin = DBL_MAX;
 
-    for( int idx = blockIdx.x * GROUPS + group; idx < count; idx += gridDim.x * GROUPS )
+    for( int pos = ( blockIdx.x * GROUPS + group ) * bp.parts + bp.part; pos < count; pos += gridDim.x * GROUPS * bp.parts )
     {
+      // a band part takes the cells its plane-constant kernel took (positions of the processing order); the records stay
+      // at the cells' positions in the band list
+      const int idx = order ? order[ pos ] : pos;
       const int c = mixedList[ idx ];
       int ijk[ 3 ];
       cell_ijk( g, c, ijk );
@@ -2427,6 +2445,7 @@ namespace vofx
     state->taskCount = 0;
     state->serialCount = 0;
     state->serialLocate = 0;
+    state->serialLocateMore[ 0 ] = state->serialLocateMore[ 1 ] = state->serialLocateMore[ 2 ] = 0;
     state->rootCount = 0;
     state->slowFront = 0;
     state->normalBack = 0;
@@ -2439,6 +2458,7 @@ namespace vofx
     state->taskCount = 0;
     state->serialCount = 0;
     state->serialLocate = 0;
+    state->serialLocateMore[ 0 ] = state->serialLocateMore[ 1 ] = state->serialLocateMore[ 2 ] = 0;
     state->rootCount = 0;
     state->changedCount = 0;
     state->slowFront = 0;

@@ -97,10 +97,10 @@ namespace vofx
     void youngs3 ( int blocks, cudaStream_t s, Grid g, const double *u, const int *mixedList, const StepState *state, int capacity, double *hs );
     void cost_order ( int blocks, cudaStream_t s, const int *mixedList, StepState *state, int capacity, const unsigned char *costClass, int *order );
     void youngs_coop3 ( int lanes, int blocks, cudaStream_t s, Grid g, const double *u, const int *mixedList, StepState *state, int capacity, double *hs,
-                        const void *sweepTable, int *serialCells, void *rootTasks, int heightFunction , const int *order, unsigned char *costClass);
-    void locate_root3 ( int blocks, cudaStream_t s, StepState *state, int capacity, const void *rootTasks, double *hs );
+                        const void *sweepTable, int *serialCells, void *rootTasks, int heightFunction, const int *order, unsigned char *costClass, BandPart bp = BandPart() );
+    void locate_root3 ( int blocks, cudaStream_t s, StepState *state, int capacity, const void *rootTasks, double *hs, BandPart bp = BandPart() );
     size_t root_task_bytes ();
-    void locate_serial3 ( cudaStream_t s, Grid g, const double *u, const StepState *state, double *hs, const int *serialCells );
+    void locate_serial3 ( cudaStream_t s, Grid g, const double *u, const StepState *state, double *hs, const int *serialCells, int capacity, BandPart bp = BandPart() );
     int make_sweep_table ( void *host, size_t bytes );   // returns the number of cases (96) or -1
     size_t sweep_table_bytes ();
     void hf3 ( int blocks, cudaStream_t s, Grid g, const double *u, const int *mixedList, const StepState *state, int capacity, double *hs );
@@ -117,7 +117,9 @@ namespace vofx
                  StepState *state, int capacity, FluxRecord *records, const double *timeOverride, const double *dtOverride );
     void flux_cell3 ( int lanes, int blocks, cudaStream_t s, Grid g, const Velocity *velocity, const Velocity &velocityByValue, const double *hs, const unsigned char *flags, const int *mixedList,
                       StepState *state, int capacity, FluxRecord *records, int *tasks, int taskCapacity, const void *clipTable,
-                      const double *timeOverride, const double *dtOverride );
+                      const double *timeOverride, const double *dtOverride, const int *order = nullptr, BandPart bp = BandPart(), int withSerialClips = 1 );
+    void flux_clip_serial3 ( cudaStream_t s, Grid g, const Velocity *velocity, const double *hs, const unsigned char *flags, const int *mixedList,
+                             StepState *state, FluxRecord *records, int *tasks, int taskCapacity, const double *timeOverride, const double *dtOverride );
     size_t clip_table_bytes ();
     void make_clip_table ( void *host );   // clip_table_bytes(): 256 + 6561 entries of 64 bytes (coop::ClipCase)
     void test_locate3 ( int blocks, long long count, const double *lo, const double *h, const double *normal, const double *fraction, double *out );

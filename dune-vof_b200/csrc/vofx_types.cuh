@@ -29,7 +29,20 @@ namespace vofx
     int epoch;                  // number of the pass in flight (1, 2, ...): the stamp of the peer-memory signals of the distributed step
     int commError;              // a wait on a peer's signal timed out
     int pad;
+    int serialLocateMore[ 3 ];  // serialLocate of the band parts 1 .. kMaxBandParts - 1 (BandPart below; part 0 counts in serialLocate)
+    int pad2;
   };
+
+  // The band kernels of a pass (plane-constant solve, root search, fluxes) can run as `parts` independent chains on as many
+  // streams: chain p takes the positions p, p + parts, p + 2 parts, ... of the processing order.  A cell's fluxes need its own
+  // reconstruction only (owner-computes gather), so the chains meet again only before the update; the
+  // tail of one chain's kernel (latency-bound, a cell is ~70 k cycles of dependent work) is filled by the other chains.
+  constexpr int kMaxBandParts = 4;
+  struct BandPart
+  {
+    int part = 0, parts = 1;
+  };
+  static_assert( kMaxBandParts == 4, "StepState::serialLocateMore holds kMaxBandParts - 1 counters" );
 
   // ---- distributed step over peer-mapped memory (vofx_comm_*, include/vofx.h) ----------------------------------------
   constexpr int kMaxRanks = 16;
