@@ -290,8 +290,8 @@ def main():
         dist.all_gather_object(out, int(x))
         return out
 
-    def make_slab(n_global, h, layers=None, tr=transport):
-        slab = SlabAlgorithm(n_global, rank, world, CFL, EPS, ops.RECON_YOUNGS, h=h, device=local_rank,
+    def make_slab(n_global, h, layers=None, tr=transport, recon=ops.RECON_YOUNGS):
+        slab = SlabAlgorithm(n_global, rank, world, CFL, EPS, recon, h=h, device=local_rank,
                              overlap=os.environ.get("VOFX_NO_OVERLAP", "0") != "1", incremental=incremental, transport=tr, layers=layers)
         slab.set_velocity_builtin(ops.PROB_LEVEQUE)
         slab.grid.use_current_stream()
@@ -449,8 +449,9 @@ def main():
     workloads = {}
     multirank_parity = None
     if world > 1 and not args.no_extra_workloads:
-        def one_problem(tag, n_glob, hh):
+        def one_problem(tag, n_glob, hh, recon=ops.RECON_YOUNGS, steps=None):
             """one sphere in n_glob: even split -> per-layer cost from the initial flags -> cost-weighted split -> timed run"""
+            steps = steps or args.extra_steps
             res = {"grid": list(n_glob)}
             out = {}
             for mode in ("even", "balanced"):
@@ -460,7 +461,7 @@ def main():
                     if layers == out["even"]["layers"]:
                         res["balanced"] = dict(res["even"], note="the cost-weighted split equals the even one")
                         break
-                s2 = make_slab(n_glob, hh, layers=layers)
+                s2 = make_slab(n_glob, hh, layers=layers, recon=recon)
                 u2 = s2.color()
                 s2.grid.init(ops.PROB_LEVEQUE, out=u2)          # analytic initial data in global coordinates, halos included
                 torch.cuda.synchronize()
@@ -468,13 +469,13 @@ def main():
                     ops.FlagOperator(s2.grid, EPS)(u2, s2.alg.flags)
                     costs = s2.global_layer_costs()
                     out["_counts"] = split_by_cost(costs, world, min_layers=max(s2.exchanger.halo, 1))
-                ms2, _, st2 = timed_run(s2, u2, W, args.extra_steps)
+                ms2, _, st2 = timed_run(s2, u2, W, steps)
                 cells = 1
                 for x in n_glob:
                     cells *= x
-                entry = {"layers": list(s2.layer_counts), "ms_per_step": ms2 / args.extra_steps, "steps": args.extra_steps,
-                         "value": cells * args.extra_steps / (ms2 * 1e-3), "unit": "cell-steps/s",
-                         "value_per_gpu": cells * args.extra_steps / (ms2 * 1e-3) / world,
+                entry = {"layers": list(s2.layer_counts), "ms_per_step": ms2 / steps, "steps": steps,
+                         "value": cells * steps / (ms2 * 1e-3), "unit": "cell-steps/s",
+                         "value_per_gpu": cells * steps / (ms2 * 1e-3) / world,
                          "mixed_cells_per_rank": gather_ints(st2.mixed_cells), "time": st2.time}
                 out[mode] = entry
                 res[mode] = entry
@@ -484,6 +485,11 @@ def main():
         if N_SIDE % world == 0 and N_SIDE // world >= 4:
             workloads["c3_strong"] = dict(one_problem("c3_strong", (N_SIDE,) * 3, (1.0 / N_SIDE,) * 3),
                                           workload="configs[2] strong scaling: ONE 512^3 LeVeque sphere cut into z-slabs", scaling="strong")
+        if 256 % world == 0:
+            # fp64-bound: the band decides everything, so the cost-weighted split is the one that matters
+            workloads["c4"] = dict(one_problem("c4", (256,) * 3, (1.0 / 256,) * 3, recon=ops.RECON_SWARTZ, steps=20),
+                                   workload="configs[3]: ONE LeVeque sphere on 256^3, iterative Swartz reconstruction (maxIterations 10), z-slabs",
+                                   scaling="strong", one_gpu_reference="profiles/r2_configs.jsonl (tools/bench_configs.py, c4)")
         if world == 8:
             n5 = 2 * N_SIDE
             workloads["c5"] = dict(one_problem("c5", (n5, n5, n5), (1.0 / n5,) * 3),

@@ -139,6 +139,90 @@ namespace vofx
     VOFX_INLINE bool dirLess ( int lhs, int rhs ) { return faceOfEdge( lhs ) == faceOfEdge( reverseEdge( rhs ) ); }
   } // namespace cube
 
+  // ---- topology policies ------------------------------------------------------------------------------------------------
+  // The serial geometry below (clip walk, sweep, plane-constant solve) is written against a policy T: T = topo::Cube is the
+  // table above (cells of Cartesian grids, hexahedra, swept quadrilateral faces); topo::Tet is makePolyhedron( simplex ),
+  // 3d/polyhedron.hh:374-385; topo::Prism the swept triangle of upwindPolygon3d, 3d/upwindpolygon.hh:47-57.  A polytope
+  // keeps its nodes in a Hex (at most 8).  The derived look-ups of Tet and Prism are searches: they serve the unstructured
+  // path (vofx_mesh.cu), one thread per cell.
+  namespace topo
+  {
+    struct Cube
+    {
+      static constexpr int kNodes = 8, kEdges = 24, kFaces = 6;
+      VOFX_INLINE static int faceLen ( int ) { return 4; }
+      VOFX_INLINE static int edgeN0 ( int e ) { return cube::edgeN0( e ); }
+      VOFX_INLINE static int edgeN1 ( int e ) { return cube::edgeN1( e ); }
+      VOFX_INLINE static int faceEdge ( int f, int k ) { return cube::faceEdge( f, k ); }
+      VOFX_INLINE static int faceNode ( int f, int k ) { return cube::faceNode( f, k ); }
+      VOFX_INLINE static int faceOfEdge ( int e ) { return cube::faceOfEdge( e ); }
+      VOFX_INLINE static int outEdge ( int node, int k ) { return cube::outEdge( node, k ); }
+      VOFX_INLINE static int reverseEdge ( int e ) { return cube::reverseEdge( e ); }
+      VOFX_INLINE static int edgeId ( int a, int b ) { return cube::edgeId( a, b ); }
+      VOFX_INLINE static bool dirLess ( int lhs, int rhs ) { return cube::dirLess( lhs, rhs ); }
+    };
+
+    // the look-ups every policy derives from its edge and face tables
+    template< class B >
+    struct Derived : B
+    {
+      VOFX_INLINE static int faceNode ( int f, int k ) { return B::edgeN0( B::faceEdge( f, k ) ); }
+      VOFX_INLINE static int faceOfEdge ( int e )            // Polyhedron::attachedFaceToEdge: the first face holding the edge
+      {
+        for( int f = 0; f < B::kFaces; ++f )
+          for( int k = 0; k < B::faceLen( f ); ++k )
+            if( B::faceEdge( f, k ) == e )
+              return f;
+        return 7;
+      }
+      VOFX_INLINE static int outEdge ( int node, int which ) // Polyhedron::attachedEdgesToNode: edges leaving the node, in edge order
+      {
+        int c = 0;
+        for( int e = 0; e < B::kEdges; ++e )
+          if( B::edgeN0( e ) == node )
+          {
+            if( c == which )
+              return e;
+            ++c;
+          }
+        return 31;
+      }
+      VOFX_INLINE static int edgeId ( int a, int b )
+      {
+        for( int e = 0; e < B::kEdges; ++e )
+          if( B::edgeN0( e ) == a && B::edgeN1( e ) == b )
+            return e;
+        return -1;
+      }
+      VOFX_INLINE static int reverseEdge ( int e ) { const int r = edgeId( B::edgeN1( e ), B::edgeN0( e ) ); return r < 0 ? 31 : r; }
+      VOFX_INLINE static bool dirLess ( int lhs, int rhs ) { return faceOfEdge( lhs ) == faceOfEdge( reverseEdge( rhs ) ); }
+    };
+
+    struct TetTables
+    {
+      static constexpr int kNodes = 4, kEdges = 12, kFaces = 4;
+      VOFX_INLINE static int faceLen ( int ) { return 3; }
+      VOFX_INLINE static int edgeN0 ( int e ) { const signed char t[ 12 ] = { 0, 1, 0, 2, 1, 2, 0, 3, 1, 3, 3, 2 }; return t[ e ]; }
+      VOFX_INLINE static int edgeN1 ( int e ) { const signed char t[ 12 ] = { 1, 0, 2, 0, 2, 1, 3, 0, 3, 1, 2, 3 }; return t[ e ]; }
+      VOFX_INLINE static int faceEdge ( int f, int k ) { const signed char t[ 4 ][ 3 ] = { { 2, 5, 1 }, { 0, 8, 7 }, { 6, 10, 3 }, { 4, 11, 9 } }; return t[ f ][ k ]; }
+    };
+    using Tet = Derived< TetTables >;
+
+    struct PrismTables
+    {
+      static constexpr int kNodes = 6, kEdges = 18, kFaces = 5;
+      VOFX_INLINE static int faceLen ( int f ) { return f < 3 ? 4 : 3; }
+      VOFX_INLINE static int edgeN0 ( int e ) { const signed char t[ 18 ] = { 0, 1, 2, 0, 0, 1, 3, 3, 4, 3, 4, 5, 1, 2, 2, 4, 5, 5 }; return t[ e ]; }
+      VOFX_INLINE static int edgeN1 ( int e ) { const signed char t[ 18 ] = { 3, 4, 5, 1, 2, 2, 4, 5, 5, 0, 1, 2, 0, 0, 1, 3, 3, 4 }; return t[ e ]; }
+      VOFX_INLINE static int faceEdge ( int f, int k )
+      {
+        const signed char t[ 5 ][ 4 ] = { { 9, 3, 1, 15 }, { 0, 7, 11, 13 }, { 5, 2, 17, 10 }, { 4, 14, 12, 0 }, { 6, 8, 16, 0 } };
+        return t[ f ][ k ];
+      }
+    };
+    using Prism = Derived< PrismTables >;
+  } // namespace topo
+
   struct Hs3
   {
     double n[ 3 ];
@@ -194,27 +278,29 @@ namespace vofx
   }
 
   // Polyhedron::volume of an (unclipped) hexahedron, 3d/polyhedron.hh:317-324
+  template< class T = topo::Cube >
   VOFX_HD inline double hex_volume ( const Hex &c )
   {
     double vol = 0.0;
-    for( int f = 0; f < 6; ++f )
+    for( int f = 0; f < T::kFaces; ++f )
     {
       double center[ 3 ] = { 0.0, 0.0, 0.0 }, fn[ 3 ];
-      for( int k = 0; k < 4; ++k )
+      const int len = T::faceLen( f );
+      for( int k = 0; k < len; ++k )
       {
-        const double *x = c.x[ cube::faceNode( f, k ) ];
+        const double *x = c.x[ T::faceNode( f, k ) ];
         for( int d = 0; d < 3; ++d )
           center[ d ] += x[ d ];
       }
-      const double s = 1.0 / 4;
+      const double s = 1.0 / len;
       for( int d = 0; d < 3; ++d )
         center[ d ] *= s;
-      outer_normal3( c.x[ cube::faceNode( f, 0 ) ], c.x[ cube::faceNode( f, 1 ) ], c.x[ cube::faceNode( f, 2 ) ], fn );
+      outer_normal3( c.x[ T::faceNode( f, 0 ) ], c.x[ T::faceNode( f, 1 ) ], c.x[ T::faceNode( f, 2 ) ], fn );
       double fv = 0.0;
-      for( int k = 0; k < 4; ++k )
+      for( int k = 0; k < len; ++k )
       {
-        const int e = cube::faceEdge( f, k );
-        fv += face_edge_term( c.x[ cube::edgeN0( e ) ], c.x[ cube::edgeN1( e ) ], fn );
+        const int e = T::faceEdge( f, k );
+        fv += face_edge_term( c.x[ T::edgeN0( e ) ], c.x[ T::edgeN1( e ) ], fn );
       }
       vol += dot3( center, fn ) * fabs( fv / 2.0 );
     }
@@ -252,11 +338,12 @@ namespace vofx
   };
 
   // returns false for the trivial cases of :115-120 (empty result)
+  template< class T = topo::Cube >
   VOFX_HD inline bool clip_walk ( unsigned innerMask, unsigned boundaryMask, ClipTopo &t )
   {
     signed char p[ 8 ];
     int n = 0, onBoundary = 0;
-    for( int i = 0; i < 8; ++i )
+    for( int i = 0; i < T::kNodes; ++i )
     {
       if( innerMask & ( 1u << i ) )
       {
@@ -277,22 +364,22 @@ namespace vofx
 
     int nNew = 0;
     signed char cutNode[ 24 ];                 // new node id created on directed edge e, or -1 (std::map of :93-95)
-    for( int e = 0; e < 24; ++e )
+    for( int e = 0; e < T::kEdges; ++e )
       cutNode[ e ] = -1;
     signed char is0[ 16 ], is1[ 16 ];          // edges of the intersection face
     int nIF = 0;
 
-    for( int f = 0; f < 6; ++f )
+    for( int f = 0; f < T::kFaces; ++f )
     {
       signed char *n0 = t.fe0[ t.nFaces ], *n1 = t.fe1[ t.nFaces ];
       int nNF = 0;
       int lastIsId = -1;
 #define VOFX_FACE_EDGE( a_, b_ ) ( n0[ nNF ] = (signed char) ( a_ ), n1[ nNF ] = (signed char) ( b_ ), nNF++ )
 #define VOFX_CAP_EDGE( a_, b_ ) ( is0[ nIF ] = (signed char) ( a_ ), is1[ nIF ] = (signed char) ( b_ ), nIF++ )
-      for( int k = 0; k < 4; ++k )
+      for( int k = 0; k < T::faceLen( f ); ++k )
       {
-        const int edge = cube::faceEdge( f, k );
-        const int a = cube::edgeN0( edge ), b = cube::edgeN1( edge );
+        const int edge = T::faceEdge( f, k );
+        const int a = T::edgeN0( edge ), b = T::edgeN1( edge );
         const bool ia = innerMask & ( 1u << a ), ib = innerMask & ( 1u << b );
         if( ia && ib )
           VOFX_FACE_EDGE( p[ a ], p[ b ] );
@@ -318,7 +405,7 @@ namespace vofx
           }
           else
           {
-            int isNodeId = cutNode[ cube::reverseEdge( edge ) ];
+            int isNodeId = cutNode[ T::reverseEdge( edge ) ];
             if( isNodeId == -1 )
             {
               isNodeId = n + nNew;
@@ -426,10 +513,11 @@ namespace vofx
   }
 
   // classification of the nodes, 3d/intersect.hh:99-112
+  template< class T = topo::Cube >
   VOFX_HD inline void clip_classify ( const Hex &poly, const Hs3 &hs, unsigned &innerMask, unsigned &boundaryMask )
   {
     innerMask = boundaryMask = 0;
-    for( int i = 0; i < 8; ++i )
+    for( int i = 0; i < T::kNodes; ++i )
     {
       const double ls = level_set( hs, poly.x[ i ] );
       if( ls > -kEps )
@@ -442,14 +530,15 @@ namespace vofx
   }
 
   // volume of { hex } n { hs > 0 }: 3d/intersect.hh:72-263 + 3d/polyhedron.hh:317-324
+  template< class T = topo::Cube >
   VOFX_HD inline double clip_volume ( const Hex &poly, const Hs3 &hs )
   {
     if( !hs_valid( hs ) )
       return fabs( 0.0 / 3.0 );
     unsigned innerMask, boundaryMask;
-    clip_classify( poly, hs, innerMask, boundaryMask );
+    clip_classify< T >( poly, hs, innerMask, boundaryMask );
     ClipTopo t;
-    if( !clip_walk( innerMask, boundaryMask, t ) )
+    if( !clip_walk< T >( innerMask, boundaryMask, t ) )
       return fabs( 0.0 / 3.0 );
     double x[ 20 ][ 3 ];
     for( int k = 0; k < t.n; ++k )
@@ -508,6 +597,7 @@ namespace vofx
   // ---- G2: plane-constant solve -------------------------------------------------------------------------------------
 
   // rotateToReferenceFrame, 3d/rotation.hh:17-53: rotate so that the outer normal n becomes e_z
+  template< class T = topo::Cube >
   VOFX_HD inline void rotate_to_reference_frame ( const double *n, const Hex &cell, Hex &out )
   {
     if( n[ 0 ] == 0.0 && n[ 1 ] == 0.0 && n[ 2 ] == 1.0 )
@@ -535,7 +625,7 @@ namespace vofx
       R[ 2 ][ 1 ] = n[ 1 ];
       R[ 2 ][ 2 ] = n[ 2 ];
     }
-    for( int i = 0; i < 8; ++i )
+    for( int i = 0; i < T::kNodes; ++i )
       for( int r = 0; r < 3; ++r )
       {
         double y = 0.0;
@@ -552,11 +642,12 @@ namespace vofx
     signed char e[ 4 ];   // one spare slot: the reference reads one element past the end after an erase (see sweep_init)
   };
 
+  template< class T = topo::Cube >
   VOFX_INLINE void dirs_of_node ( int node, Dirs &d )
   {
     d.n = 3;
     for( int k = 0; k < 3; ++k )
-      d.e[ k ] = (signed char) cube::outEdge( node, k );
+      d.e[ k ] = (signed char) T::outEdge( node, k );
     d.e[ 3 ] = 0;
   }
 
@@ -569,12 +660,13 @@ namespace vofx
 
   // std::sort on fewer than 16 elements is libstdc++'s __insertion_sort; the comparator is cyclic (not a strict weak
   // ordering), so the exact algorithm is part of the specification
+  template< class T = topo::Cube >
   VOFX_HD inline void dirs_sort ( Dirs &d )
   {
     for( int i = 1; i < d.n; ++i )
     {
       const signed char val = d.e[ i ];
-      if( cube::dirLess( val, d.e[ 0 ] ) )
+      if( T::dirLess( val, d.e[ 0 ] ) )
       {
         for( int j = i; j > 0; --j )
           d.e[ j ] = d.e[ j - 1 ];
@@ -583,7 +675,7 @@ namespace vofx
       else
       {
         int j = i;
-        while( cube::dirLess( val, d.e[ j - 1 ] ) )
+        while( T::dirLess( val, d.e[ j - 1 ] ) )
         {
           d.e[ j ] = d.e[ j - 1 ];
           --j;
@@ -611,9 +703,10 @@ namespace vofx
   };
 
   // PolygonWithDirections::directionVector, 3d/polygonwithdirections.hh:64-74
+  template< class T = topo::Cube >
   VOFX_HD inline void direction_vector ( const Hex &P, int edge, double *dv )
   {
-    const int a = cube::edgeN0( edge ), b = cube::edgeN1( edge );
+    const int a = T::edgeN0( edge ), b = T::edgeN1( edge );
     for( int c = 0; c < 3; ++c )
       dv[ c ] = P.x[ b ][ c ] - P.x[ a ][ c ];
     const double norm = norm2( dv[ 0 ], dv[ 1 ] );
@@ -623,7 +716,7 @@ namespace vofx
 
   // PolygonWithDirections::initialize, 3d/polygonwithdirections.hh:76-174.  ids = node ids sorted by height, ds = sorted heights
   // POS = false: topology only (the cooperative path evaluates the positions itself); P may then be null
-  template< bool POS >
+  template< bool POS, class T = topo::Cube >
   VOFX_HD inline void sweep_init ( Sweep &s, const Hex *Pp, const int *ids, const double *ds )
   {
     s.nn = 0;
@@ -632,7 +725,7 @@ namespace vofx
     s.degenerate = false;
 
     int N = 1;
-    for( ; N < 8 && ds[ N ] == ds[ 0 ]; N++ )
+    for( ; N < T::kNodes && ds[ N ] == ds[ 0 ]; N++ )
       ;
 
     if( N == 1 )
@@ -643,8 +736,8 @@ namespace vofx
         s.py[ 0 ] = Pp->x[ ids[ 0 ] ][ 1 ];
       }
       s.nodeId[ 0 ] = (signed char) ids[ 0 ];
-      dirs_of_node( ids[ 0 ], s.dirs[ 0 ] );
-      dirs_sort( s.dirs[ 0 ] );
+      dirs_of_node< T >( ids[ 0 ], s.dirs[ 0 ] );
+      dirs_sort< T >( s.dirs[ 0 ] );
       s.nn = 1;
     }
     else if( N == 2 )
@@ -659,13 +752,13 @@ namespace vofx
         s.nodeId[ k ] = (signed char) ids[ k ];
       }
       Dirs d1, d2;
-      dirs_of_node( ids[ 0 ], d1 );
-      dirs_of_node( ids[ 1 ], d2 );
+      dirs_of_node< T >( ids[ 0 ], d1 );
+      dirs_of_node< T >( ids[ 1 ], d2 );
       // :107-114: both loops keep running after the erase; an index equal to the new size reads the stale copy of
       // the former last element that std::vector::erase leaves behind
       for( int i = 0; i < d1.n; ++i )
         for( int j = 0; j < d2.n; ++j )
-          if( d1.e[ i ] == cube::reverseEdge( d2.e[ j ] ) )
+          if( d1.e[ i ] == T::reverseEdge( d2.e[ j ] ) )
           {
             const signed char stale1 = d1.e[ d1.n - 1 ], stale2 = d2.e[ d2.n - 1 ];
             dirs_erase( d1, i );
@@ -673,8 +766,8 @@ namespace vofx
             d1.e[ d1.n ] = stale1;
             d2.e[ d2.n ] = stale2;
           }
-      dirs_sort( d1 );
-      dirs_sort( d2 );
+      dirs_sort< T >( d1 );
+      dirs_sort< T >( d2 );
       s.dirs[ 0 ] = d1;
       s.dirs[ 1 ] = d2;
       s.nn = 2;
@@ -685,22 +778,22 @@ namespace vofx
       for( int i = 0; i < N; ++i )
         lowMask |= 1u << ids[ i ];
       int found = -1;
-      for( int f = 0; f < 6 && found < 0; ++f )
+      for( int f = 0; f < T::kFaces && found < 0; ++f )
       {
         bool all = true;
-        for( int k = 0; k < 4; ++k )
-          all = all && ( lowMask & ( 1u << cube::faceNode( f, k ) ) );
+        for( int k = 0; k < T::faceLen( f ); ++k )
+          all = all && ( lowMask & ( 1u << T::faceNode( f, k ) ) );
         if( all )
           found = f;
       }
-      if( found < 0 || N > 4 )
+      if( found < 0 || N > T::faceLen( found ) )
       {
         s.degenerate = true;   // the reference indexes an empty / too short nodeIds_
         return;
       }
-      for( int k = 0; k < 4; ++k )
+      for( int k = 0; k < T::faceLen( found ); ++k )
       {
-        const int id = cube::faceNode( found, k );
+        const int id = T::faceNode( found, k );
         s.nodeId[ k ] = (signed char) id;
         if( POS )
         {
@@ -708,19 +801,19 @@ namespace vofx
           s.py[ k ] = Pp->x[ id ][ 1 ];
         }
       }
-      s.nn = 4;
+      s.nn = T::faceLen( found );
       for( int k = 0; k < N; ++k )
       {
         Dirs dd;
-        dirs_of_node( s.nodeId[ k ], dd );
+        dirs_of_node< T >( s.nodeId[ k ], dd );
         for( int j = 0; j < N; ++j )
           for( int i = 0; i < dd.n; ++i )
-            if( cube::edgeN1( dd.e[ i ] ) == s.nodeId[ j ] )
+            if( T::edgeN1( dd.e[ i ] ) == s.nodeId[ j ] )
             {
               dirs_erase( dd, i );
               --i;
             }
-        dirs_sort( dd );
+        dirs_sort< T >( dd );
         s.dirs[ k ] = dd;
       }
     }
@@ -735,13 +828,13 @@ namespace vofx
       for( int i = 0; i < s.nn; ++i )
       {
         const int j = ( i + 1 == s.nn ) ? 0 : i + 1;
-        const int e = cube::edgeId( s.nodeId[ j ], s.nodeId[ i ] );
+        const int e = T::edgeId( s.nodeId[ j ], s.nodeId[ i ] );
         if( e < 0 )
         {
           s.degenerate = true;   // reference: DUNE_THROW( InvalidStateException, "Edge was not found in any face." )
           return;
         }
-        s.corrFace[ s.nCF++ ] = (signed char) cube::faceOfEdge( e );
+        s.corrFace[ s.nCF++ ] = (signed char) T::faceOfEdge( e );
       }
       s.nEdges = s.nn;
     }
@@ -749,7 +842,7 @@ namespace vofx
 
   // PolygonWithDirections::evolveToNextPolygon, 3d/polygonwithdirections.hh:177-290
   // z: the eight node heights (P.x[ . ][ 2 ]); P only for POS = true
-  template< bool POS >
+  template< bool POS, class T = topo::Cube >
   VOFX_HD inline void sweep_evolve ( Sweep &s, const Hex *Pp, const double *z, double dk, double dk1, double h )
   {
     double nx[ kMaxSweep ], ny[ kMaxSweep ];
@@ -765,14 +858,14 @@ namespace vofx
       for( int i = 0; i < s.dirs[ n ].n; ++i )
       {
         const int dirEdge = s.dirs[ n ].e[ i ];
-        const int target = cube::edgeN1( dirEdge );
+        const int target = T::edgeN1( dirEdge );
         const double z1 = z[ target ];
 
         if( fabs( z1 - dk1 ) < 1e-10 )
         {
           if( nNew > 0 && target == nid[ nNew - 1 ] )
           {
-            s.corrFace[ s.nCF - 1 ] = (signed char) cube::faceOfEdge( dirEdge );
+            s.corrFace[ s.nCF - 1 ] = (signed char) T::faceOfEdge( dirEdge );
             continue;
           }
           if( nNew >= kMaxSweep )
@@ -793,14 +886,14 @@ namespace vofx
           dd.e[ 3 ] = 0;
           for( int a = 0; a < 3; ++a )
           {
-            const int e = cube::outEdge( target, a );
-            if( z[ cube::edgeN1( e ) ] > dk )
+            const int e = T::outEdge( target, a );
+            if( z[ T::edgeN1( e ) ] > dk )
               dd.e[ dd.n++ ] = (signed char) e;
           }
-          dirs_sort( dd );
+          dirs_sort< T >( dd );
           nd[ nNew ] = dd;
           nNew++;
-          s.corrFace[ s.nCF++ ] = (signed char) cube::faceOfEdge( dirEdge );
+          s.corrFace[ s.nCF++ ] = (signed char) T::faceOfEdge( dirEdge );
         }
         else if( z1 > dk1 )
         {
@@ -812,7 +905,7 @@ namespace vofx
           if( POS )
           {
             double dv[ 3 ];
-            direction_vector( *Pp, dirEdge, dv );
+            direction_vector< T >( *Pp, dirEdge, dv );
             const double f = vdiv( h, dv[ 2 ] );
             const double ax = dv[ 0 ] * f, ay = dv[ 1 ] * f;
             nx[ nNew ] = s.px[ n ] + ax;
@@ -824,7 +917,7 @@ namespace vofx
           nd[ nNew ].n = 1;
           nd[ nNew ].e[ 0 ] = (signed char) dirEdge;
           nNew++;
-          s.corrFace[ s.nCF++ ] = (signed char) cube::faceOfEdge( dirEdge );
+          s.corrFace[ s.nCF++ ] = (signed char) T::faceOfEdge( dirEdge );
         }
       }
 
@@ -846,7 +939,7 @@ namespace vofx
       Dirs &dd = nd[ a ];
       for( int i = 0; i < dd.n; ++i )
         for( int b = 0; b < nNew; ++b )
-          if( i >= 0 && cube::edgeN1( dd.e[ i ] ) == nid[ b ] )
+          if( i >= 0 && T::edgeN1( dd.e[ i ] ) == nid[ b ] )
           {
             dirs_erase( dd, i );
             --i;
@@ -862,8 +955,8 @@ namespace vofx
       {
         const int id0 = nid[ i ];
         const int id1 = nid[ ( i + 1 == nNew ) ? 0 : i + 1 ];
-        if( id0 != -1 && id1 != -1 && cube::edgeId( id0, id1 ) >= 0 )
-          s.corrFace[ i ] = (signed char) cube::faceOfEdge( cube::edgeId( id1, id0 ) );
+        if( id0 != -1 && id1 != -1 && T::edgeId( id0, id1 ) >= 0 )
+          s.corrFace[ i ] = (signed char) T::faceOfEdge( T::edgeId( id1, id0 ) );
       }
 
     s.nn = nNew;
@@ -890,6 +983,7 @@ namespace vofx
 
   // locateHalfSpace( Polyhedron, innerNormal, fraction ), geometry/algorithm.hh:119-236.  Returns the plane constant;
   // NaN where the reference's behaviour is undefined (it would read out of bounds or throw).
+  template< class T = topo::Cube >
   VOFX_HD inline double locate ( const Hex &cell, const double *innerNormal, double fraction )
   {
     double outerNormal[ 3 ];
@@ -899,15 +993,15 @@ namespace vofx
     fraction = ( fraction > 1.0 ) ? 1.0 : fraction;
     fraction = ( fraction < 0.0 ) ? 0.0 : fraction;
 
-    const double givenVolume = fraction * hex_volume( cell );
+    const double givenVolume = fraction * hex_volume< T >( cell );
 
     Hex P;
-    rotate_to_reference_frame( outerNormal, cell, P );
+    rotate_to_reference_frame< T >( outerNormal, cell, P );
 
     // node heights sorted by insertion sort (std::sort, N = 8 < 16; stable: ties keep ascending node id), :147-158
     int ids[ 8 ];
     double ds[ 8 ];
-    for( int i = 0; i < 8; ++i )
+    for( int i = 0; i < T::kNodes; ++i )
     {
       const double di = P.x[ i ][ 2 ];
       int j = i;
@@ -924,12 +1018,12 @@ namespace vofx
     double dU[ 8 ];
     int nU = 0;
     dU[ nU++ ] = ds[ 0 ];
-    for( int i = 1; i < 8; ++i )
+    for( int i = 1; i < T::kNodes; ++i )
       if( !( fabs( dU[ nU - 1 ] - ds[ i ] ) < 1e-10 ) )
         dU[ nU++ ] = ds[ i ];
 
     Sweep s;
-    sweep_init< true >( s, &P, ids, ds );
+    sweep_init< true, T >( s, &P, ids, ds );
     if( s.degenerate )
       return NAN;
 
@@ -945,14 +1039,14 @@ namespace vofx
           return NAN;   // reference: assert( !directions( n ).empty() ), then an out-of-range read
         const int epsn = s.dirs[ n ].n - 1;
         double v1[ 3 ], v2[ 3 ];
-        direction_vector( P, s.dirs[ n ].e[ epsn ], v1 );
-        direction_vector( P, s.dirs[ nxt ].e[ 0 ], v2 );
+        direction_vector< T >( P, s.dirs[ n ].e[ epsn ], v1 );
+        direction_vector< T >( P, s.dirs[ nxt ].e[ 0 ], v2 );
         A -= vdiv( v1[ 0 ] * v2[ 1 ] - v1[ 1 ] * v2[ 0 ], v1[ 2 ] * v2[ 2 ] );
         for( int l = 0; l < epsn; ++l )
         {
           double w1[ 3 ], w2[ 3 ];
-          direction_vector( P, s.dirs[ n ].e[ l ], w1 );
-          direction_vector( P, s.dirs[ n ].e[ l + 1 ], w2 );
+          direction_vector< T >( P, s.dirs[ n ].e[ l ], w1 );
+          direction_vector< T >( P, s.dirs[ n ].e[ l + 1 ], w2 );
           A -= vdiv( w1[ 0 ] * w2[ 1 ] - w1[ 1 ] * w2[ 0 ], w1[ 2 ] * w2[ 2 ] );
         }
       }
@@ -964,7 +1058,7 @@ namespace vofx
           return NAN;
         const int f = s.corrFace[ i ];
         double normal[ 3 ];
-        outer_normal3( P.x[ cube::faceNode( f, 0 ) ], P.x[ cube::faceNode( f, 1 ) ], P.x[ cube::faceNode( f, 2 ) ], normal );
+        outer_normal3( P.x[ T::faceNode( f, 0 ) ], P.x[ T::faceNode( f, 1 ) ], P.x[ T::faceNode( f, 2 ) ], normal );
         const double norm = norm2( normal[ 0 ], normal[ 1 ] );
         if( norm > 0 )
         {
@@ -1002,15 +1096,60 @@ namespace vofx
       else
       {
         double zs[ 8 ];
-        for( int i = 0; i < 8; ++i )
+        for( int i = 0; i < T::kNodes; ++i )
           zs[ i ] = P.x[ i ][ 2 ];
-        sweep_evolve< true >( s, &P, zs, dU[ k ], dU[ k + 1 ], h );
+        sweep_evolve< true, T >( s, &P, zs, dU[ k ], dU[ k + 1 ], h );
         if( s.degenerate )
           return NAN;
       }
       Vd_k = Vd_k1;
     }
     return dU[ nU - 1 ];
+  }
+
+  // ---- cells and intersections of unstructured 3D grids, given by their corners (vofx_mesh.cu) ---------------------------
+
+  // locateHalfSpace( makePolyhedron( geometry ), innerNormal, fraction ) for a tetrahedron (nc = 4, 3d/polyhedron.hh:374-385)
+  // or a hexahedron (nc = 8, :387-401); corners in DUNE corner order, [ nc ][ 3 ].  NaN for any other corner count
+  // (the reference throws InvalidStateException, "Invalid GeometryType.").
+  VOFX_HD inline double locate_corners ( const double *corners, int nc, const double *innerNormal, double fraction )
+  {
+    Hex cell;
+    for( int i = 0; i < nc && i < 8; ++i )
+      for( int d = 0; d < 3; ++d )
+        cell.x[ i ][ d ] = corners[ 3 * i + d ];
+    if( nc == 4 )
+      return locate< topo::Tet >( cell, innerNormal, fraction );
+    if( nc == 8 )
+      return locate< topo::Cube >( cell, innerNormal, fraction );
+    return NAN;
+  }
+
+  // truncVolume( upwindPolygon3d( iGeometry, v ), hs ), 3d/upwindpolygon.hh:24-74 + geometry/upwindpolygon.hh:58-62, for an
+  // intersection with nc = 3 (prism, :47-57) or nc = 4 (cube topology, :59-70) corners c[ nc ][ 3 ]
+  VOFX_HD inline double flux_corners ( const double *c, int nc, const double *v, const Hs3 &hs )
+  {
+    double e1[ 3 ], e2[ 3 ], cr[ 3 ];
+    for( int d = 0; d < 3; ++d )
+    {
+      e1[ d ] = c[ 3 + d ] - c[ d ];
+      e2[ d ] = c[ 6 + d ] - c[ d ];
+    }
+    cross3( e1, e2, cr );
+    const bool shiftedFirst = dot3( cr, v ) < 0.0;
+    Hex up;
+    for( int i = 0; i < nc && i < 4; ++i )
+      for( int d = 0; d < 3; ++d )
+      {
+        const double moved = c[ 3 * i + d ] - v[ d ];
+        up.x[ shiftedFirst ? i : i + nc ][ d ] = moved;
+        up.x[ shiftedFirst ? i + nc : i ][ d ] = c[ 3 * i + d ];
+      }
+    if( nc == 3 )
+      return clip_volume< topo::Prism >( up, hs );
+    if( nc == 4 )
+      return clip_volume< topo::Cube >( up, hs );
+    return NAN;
   }
 
   // ---- G6: interface polygon of a cell and its centroid ---------------------------------------------------------------

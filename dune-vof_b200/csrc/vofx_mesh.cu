@@ -1,9 +1,12 @@
-// vofx on unstructured 2D grids (triangles and quadrilaterals given as flattened arrays, include/vofx.h: vofx_mesh_desc):
-// kernels and the C ABI.  The arithmetic restates, operation for operation (vofx_math.cuh, -fmad=false),
+// vofx on unstructured grids given as flattened arrays (include/vofx.h: vofx_mesh_desc) -- triangles and quadrilaterals in 2D,
+// tetrahedra and hexahedra in 3D: kernels and the C ABI.  The arithmetic restates, operation for operation (vofx_math.cuh, -fmad=false),
 //   F1  flagging.hh:35-70
 //   R1  reconstruction/modifiedyoungs.hh:63-134 over the CSR vertex-neighbour stencil (stencil/vertexneighborsstencil.hh:52-94)
 //   G1  locateHalfSpace( Polygon ), geometry/algorithm.hh:68-111        (vofx_geom2d.cuh)
 //   E1  evolution/evolution.hh:58-145, G7 2d/upwindpolygon.hh:24-30
+//   3D: makePolyhedron( simplex / cube ), 3d/polyhedron.hh:366-404; G2 locateHalfSpace( Polyhedron ), geometry/algorithm.hh:119-236;
+//       G7 upwindPolygon3d for triangular and quadrilateral intersections, 3d/upwindpolygon.hh:24-74; G5 (vofx_geom3d.cuh: topology
+//       policies topo::Tet / topo::Prism / topo::Cube)
 // Layout: SoA device copies of the descriptor arrays; flags 1 B/cell; half-spaces (n, d) 24 B/cell; per-intersection flux
 // records (flux, v.N, direction) written by the mixed cells and GATHERED by every cell in the reference's accumulation
 // order (ascending index of the contributing mixed cell, its faces in order), so that no atomics touch the update and
@@ -19,6 +22,7 @@
 #include <cuda_runtime.h>
 
 #include "vofx_geom2d.cuh"
+#include "vofx_geom3d.cuh"
 
 namespace vofx
 {
@@ -40,7 +44,9 @@ namespace
 
   struct MeshDev
   {
+    int dim;
     int nCells, nFaces;
+    const int *faceCornerOffsets;    // 3D: corners of intersection s are faceCorners[ 3 * faceCornerOffsets[ s ] ... ]
     const int *cornerOffsets;
     const double *corners, *centers, *volumes;
     const int *faceOffsets, *faceNeighbor, *backSlot;
@@ -178,6 +184,145 @@ namespace
       hs[ 3 * c ] = nx;
       hs[ 3 * c + 1 ] = ny;
       hs[ 3 * c + 2 ] = dist;
+    }
+  }
+
+  // ---- 3D -----------------------------------------------------------------------------------------------------------------
+
+  __device__ __forceinline__ void ls_accumulate3 ( double *d, double colorDiff, double AtA[ 3 ][ 3 ], double *Atb )
+  {
+    double n2 = 0.0;
+#pragma unroll
+    for( int k = 0; k < 3; ++k )
+      n2 += d[ k ] * d[ k ];
+    const double weight = 1.0 / n2;
+#pragma unroll
+    for( int k = 0; k < 3; ++k )
+      d[ k ] *= weight;
+#pragma unroll
+    for( int i = 0; i < 3; ++i )
+#pragma unroll
+      for( int j = 0; j < 3; ++j )
+      {
+        double m = 0.0;          // outerProduct: axpy onto a zero matrix, geometry/utility.hh:161-169
+        m += d[ i ] * d[ j ];
+        AtA[ i ][ j ] += m;
+      }
+    const double w = weight * colorDiff;
+#pragma unroll
+    for( int k = 0; k < 3; ++k )
+      Atb[ k ] += w * d[ k ];
+  }
+
+  // FieldMatrix< double, 3, 3 >::solve of dune-common 2.6 (closed form; DESIGN.md "parity unpinned"), as the oracle's solve_small
+  __device__ __forceinline__ void solve3_plain ( const double M[ 3 ][ 3 ], const double *b, double *x )
+  {
+    const double t4 = M[ 0 ][ 0 ] * M[ 1 ][ 1 ];
+    const double t6 = M[ 0 ][ 0 ] * M[ 1 ][ 2 ];
+    const double t8 = M[ 0 ][ 1 ] * M[ 1 ][ 0 ];
+    const double t10 = M[ 0 ][ 2 ] * M[ 1 ][ 0 ];
+    const double t12 = M[ 0 ][ 1 ] * M[ 2 ][ 0 ];
+    const double t14 = M[ 0 ][ 2 ] * M[ 2 ][ 0 ];
+    const double d = ( t4 * M[ 2 ][ 2 ] - t6 * M[ 2 ][ 1 ] - t8 * M[ 2 ][ 2 ] + t10 * M[ 2 ][ 1 ] + t12 * M[ 1 ][ 2 ] - t14 * M[ 1 ][ 1 ] );
+    x[ 0 ] = ( b[ 0 ] * M[ 1 ][ 1 ] * M[ 2 ][ 2 ] - b[ 0 ] * M[ 2 ][ 1 ] * M[ 1 ][ 2 ]
+               - b[ 1 ] * M[ 0 ][ 1 ] * M[ 2 ][ 2 ] + b[ 1 ] * M[ 2 ][ 1 ] * M[ 0 ][ 2 ]
+               + b[ 2 ] * M[ 0 ][ 1 ] * M[ 1 ][ 2 ] - b[ 2 ] * M[ 1 ][ 1 ] * M[ 0 ][ 2 ] ) / d;
+    x[ 1 ] = ( M[ 0 ][ 0 ] * b[ 1 ] * M[ 2 ][ 2 ] - M[ 0 ][ 0 ] * b[ 2 ] * M[ 1 ][ 2 ]
+               - M[ 1 ][ 0 ] * b[ 0 ] * M[ 2 ][ 2 ] + M[ 1 ][ 0 ] * b[ 2 ] * M[ 0 ][ 2 ]
+               + M[ 2 ][ 0 ] * b[ 0 ] * M[ 1 ][ 2 ] - M[ 2 ][ 0 ] * b[ 1 ] * M[ 0 ][ 2 ] ) / d;
+    x[ 2 ] = ( M[ 0 ][ 0 ] * M[ 1 ][ 1 ] * b[ 2 ] - M[ 0 ][ 0 ] * M[ 2 ][ 1 ] * b[ 1 ]
+               - M[ 1 ][ 0 ] * M[ 0 ][ 1 ] * b[ 2 ] + M[ 1 ][ 0 ] * M[ 2 ][ 1 ] * b[ 0 ]
+               + M[ 2 ][ 0 ] * M[ 0 ][ 1 ] * b[ 1 ] - M[ 2 ][ 0 ] * M[ 1 ][ 1 ] * b[ 0 ] ) / d;
+  }
+
+  // applyLocal, modifiedyoungs.hh:90-134, on tetrahedra and hexahedra: one thread per mixed cell
+  __global__ void __launch_bounds__( 64 ) k_mesh_youngs3 ( MeshDev M, const double *__restrict__ u, const int *__restrict__ mixedList,
+                                                            const MeshState *state, double *__restrict__ hs )
+  {
+    const int count = state->mixedCount;
+    for( int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < count; idx += gridDim.x * blockDim.x )
+    {
+      const int c = mixedList[ idx ];
+      const double center[ 3 ] = { M.centers[ 3 * c ], M.centers[ 3 * c + 1 ], M.centers[ 3 * c + 2 ] };
+      const double colorEn = u[ c ];
+      double AtA[ 3 ][ 3 ] = { { 0.0, 0.0, 0.0 }, { 0.0, 0.0, 0.0 }, { 0.0, 0.0, 0.0 } }, Atb[ 3 ] = { 0.0, 0.0, 0.0 };
+      for( int s = M.stencilOffsets[ c ]; s < M.stencilOffsets[ c + 1 ]; ++s )
+      {
+        const int nb = M.stencil[ s ];
+        const double colorNb = clamp01( u[ nb ] );
+        double d[ 3 ];
+#pragma unroll
+        for( int k = 0; k < 3; ++k )
+          d[ k ] = M.centers[ 3 * nb + k ] - center[ k ];
+        ls_accumulate3( d, colorNb - colorEn, AtA, Atb );
+      }
+      for( int s = M.faceOffsets[ c ]; s < M.faceOffsets[ c + 1 ]; ++s )
+      {
+        if( M.faceNeighbor[ s ] >= 0 )
+          continue;
+        double d[ 3 ];
+#pragma unroll
+        for( int k = 0; k < 3; ++k )
+        {
+          d[ k ] = M.faceCenters[ 3 * s + k ] - center[ k ];
+          d[ k ] *= 2.0;
+        }
+        ls_accumulate3( d, 0.5 - colorEn, AtA, Atb );
+      }
+      double normal[ 3 ] = { 0.0, 0.0, 0.0 };
+      solve3_plain( AtA, Atb, normal );
+      const double n2 = dot3( normal, normal );
+      if( n2 < kEps )
+        continue;                       // the reconstruction stays the zero half-space, :128-129
+      const double nrm = sqrt( n2 );
+#pragma unroll
+      for( int k = 0; k < 3; ++k )
+        normal[ k ] = normal[ k ] / nrm;
+      const int b = M.cornerOffsets[ c ], nc = M.cornerOffsets[ c + 1 ] - b;
+      const double dist = locate_corners( M.corners + 3 * size_t( b ), nc, normal, colorEn );
+      hs[ 4 * c ] = normal[ 0 ];
+      hs[ 4 * c + 1 ] = normal[ 1 ];
+      hs[ 4 * c + 2 ] = normal[ 2 ];
+      hs[ 4 * c + 3 ] = dist;
+    }
+  }
+
+  // the per-intersection part of Evolution::applyLocal (evolution.hh:100-141) in 3D
+  __global__ void __launch_bounds__( 64 ) k_mesh_flux3 ( MeshDev M, const double *__restrict__ hs, const double *__restrict__ faceVelocity,
+                                                          const double *dtPtr, const int *__restrict__ mixedList, MeshState *state,
+                                                          double *__restrict__ recFlux, double *__restrict__ recVN, signed char *__restrict__ recDir )
+  {
+    const int count = state->mixedCount;
+    const double dt = *dtPtr;
+    for( int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < count; idx += gridDim.x * blockDim.x )
+    {
+      const int c = mixedList[ idx ];
+      const Hs3 rec = { { hs[ 4 * c ], hs[ 4 * c + 1 ], hs[ 4 * c + 2 ] }, hs[ 4 * c + 3 ] };
+      double sumFluxes = 0.0;
+      for( int s = M.faceOffsets[ c ]; s < M.faceOffsets[ c + 1 ]; ++s )
+      {
+        if( M.faceNeighbor[ s ] < 0 )
+          continue;
+        const double *n = M.faceUnit + 3 * size_t( s );
+        double v[ 3 ] = { faceVelocity[ 3 * size_t( s ) ], faceVelocity[ 3 * size_t( s ) + 1 ], faceVelocity[ 3 * size_t( s ) + 2 ] };
+        sumFluxes += M.faceVolumes[ s ] * fabs( dot3( n, v ) );
+#pragma unroll
+        for( int k = 0; k < 3; ++k )
+          v[ k ] *= dt;
+        const double vn = dot3( v, n );
+        double flux = 0.0;
+        if( vn > 0 )
+        {
+          const int fb = M.faceCornerOffsets[ s ], fnc = M.faceCornerOffsets[ s + 1 ] - fb;
+          flux = flux_corners( M.faceCorners + 3 * size_t( fb ), fnc, v, rec );
+        }
+        recFlux[ s ] = flux;
+        recVN[ s ] = dot3( v, M.faceInt + 3 * size_t( s ) );
+        recDir[ s ] = ( vn > 0 ) ? 1 : ( ( vn < 0 ) ? -1 : 0 );
+      }
+      const double est = M.volumes[ c ] / sumFluxes;
+      if( est >= 0.0 )
+        atomicMin( &state->dtEstBits, (unsigned long long) __double_as_longlong( est ) );
     }
   }
 
@@ -320,13 +465,13 @@ namespace
       const unsigned char flag = flags[ c ];
       const int begin = M.faceOffsets[ c ], end = M.faceOffsets[ c + 1 ];
       // contributors ( cell, slot in that cell ) sorted lexicographically; own entry ( c, -1 )
-      int key1[ 5 ], key2[ 5 ], n = 0;
+      int key1[ 7 ], key2[ 7 ], n = 0;     // the cell itself and at most six intersections (hexahedra)
       if( is_mixed( flag ) )
       {
         key1[ n ] = c;
         key2[ n++ ] = -1;
       }
-      for( int s = begin; s < end && n < 5; ++s )
+      for( int s = begin; s < end && n < 7; ++s )
       {
         const int nb = M.faceNeighbor[ s ];
         if( nb < 0 || !is_mixed( flags[ nb ] ) )
@@ -458,8 +603,11 @@ namespace
 
   int launchYoungs ( vofx_mesh *m, const double *u, double *hs )
   {
-    VOFX_MESH_CUDA( cudaMemsetAsync( hs, 0, sizeof( double ) * 3 * size_t( m->dev.nCells ), m->stream ) );   // reconstructions.clear(), :65
-    k_mesh_youngs<<< bandBlocks( m ), 128, 0, m->stream >>>( m->dev, u, m->mixedList, m->state, hs );
+    VOFX_MESH_CUDA( cudaMemsetAsync( hs, 0, sizeof( double ) * ( m->dev.dim + 1 ) * size_t( m->dev.nCells ), m->stream ) );   // reconstructions.clear(), :65
+    if( m->dev.dim == 3 )
+      k_mesh_youngs3<<< bandBlocks( m ) * 2, 64, 0, m->stream >>>( m->dev, u, m->mixedList, m->state, hs );
+    else
+      k_mesh_youngs<<< bandBlocks( m ), 128, 0, m->stream >>>( m->dev, u, m->mixedList, m->state, hs );
     m->launches += 1;
     VOFX_MESH_CUDA( cudaGetLastError() );
     return VOFX_OK;
@@ -467,6 +615,8 @@ namespace
 
   int launchSwartz ( vofx_mesh *m, const double *u, const unsigned char *flags, double *hs, int maxIterations )
   {
+    if( m->dev.dim != 2 )
+      return set_error( VOFX_ERR_ARGUMENT, "the Swartz reconstruction on unstructured grids is built for 2D meshes only" );
     k_mesh_swartz<<< bandBlocks( m ), 64, 0, m->stream >>>( m->dev, u, flags, m->mixedList, m->state, hs, maxIterations );
     m->launches += 1;
     VOFX_MESH_CUDA( cudaGetLastError() );
@@ -476,7 +626,10 @@ namespace
   template< bool FUSED >
   int launchEvolve ( vofx_mesh *m, const double *hs, const unsigned char *flags, const double *vel, const double *dtPtr, double *target )
   {
-    k_mesh_flux<<< bandBlocks( m ), 128, 0, m->stream >>>( m->dev, hs, vel, dtPtr, m->mixedList, m->state, m->recFlux, m->recVN, m->recDir );
+    if( m->dev.dim == 3 )
+      k_mesh_flux3<<< bandBlocks( m ) * 2, 64, 0, m->stream >>>( m->dev, hs, vel, dtPtr, m->mixedList, m->state, m->recFlux, m->recVN, m->recDir );
+    else
+      k_mesh_flux<<< bandBlocks( m ), 128, 0, m->stream >>>( m->dev, hs, vel, dtPtr, m->mixedList, m->state, m->recFlux, m->recVN, m->recDir );
     k_mesh_update< FUSED ><<< m->blocksCells, 256, 0, m->stream >>>( m->dev, flags, m->recFlux, m->recVN, m->recDir, target );
     m->launches += 2;
     VOFX_MESH_CUDA( cudaGetLastError() );
@@ -511,8 +664,11 @@ extern "C"
     if( !d || !out )
       return set_error( VOFX_ERR_ARGUMENT, "vofx_mesh_create: null argument" );
     *out = nullptr;
-    if( d->dim != 2 )
-      return set_error( VOFX_ERR_ARGUMENT, "vofx_mesh_create: only dim == 2 (triangles, quadrilaterals) is built" );
+    if( d->dim != 2 && d->dim != 3 )
+      return set_error( VOFX_ERR_ARGUMENT, "vofx_mesh_create: dim must be 2 (triangles, quadrilaterals) or 3 (tetrahedra, hexahedra)" );
+    const int dim = d->dim;
+    if( dim == 3 && !d->face_corner_offsets )
+      return set_error( VOFX_ERR_ARGUMENT, "vofx_mesh_create: a 3D mesh needs face_corner_offsets" );
     if( d->n_cells <= 0 || d->n_cells > 0x7fffffffLL )
       return set_error( VOFX_ERR_ARGUMENT, "vofx_mesh_create: n_cells out of range" );
     if( !d->corner_offsets || !d->corners || !d->centers || !d->volumes || !d->face_offsets || !d->face_neighbor || !d->face_corners
@@ -524,11 +680,11 @@ extern "C"
     for( int c = 0; c < n; ++c )
     {
       const int nc = d->corner_offsets[ c + 1 ] - d->corner_offsets[ c ];
-      if( nc != 3 && nc != 4 )
-        return set_error( VOFX_ERR_ARGUMENT, "vofx_mesh_create: Invalid GeometryType (cells must be triangles or quadrilaterals)" );
+      if( dim == 2 ? ( nc != 3 && nc != 4 ) : ( nc != 4 && nc != 8 ) )
+        return set_error( VOFX_ERR_ARGUMENT, "vofx_mesh_create: Invalid GeometryType (cells must be triangles or quadrilaterals in 2D, tetrahedra or hexahedra in 3D)" );
       const int nf = d->face_offsets[ c + 1 ] - d->face_offsets[ c ];
-      if( nf < 0 || nf > 4 )
-        return set_error( VOFX_ERR_ARGUMENT, "vofx_mesh_create: a cell has more than 4 intersections" );
+      if( nf < 0 || nf > ( dim == 2 ? 4 : 6 ) )
+        return set_error( VOFX_ERR_ARGUMENT, "vofx_mesh_create: a cell has too many intersections" );
       for( int s = d->face_offsets[ c ]; s < d->face_offsets[ c + 1 ]; ++s )
         if( d->face_neighbor[ s ] >= n || d->face_neighbor[ s ] == c )
           return set_error( VOFX_ERR_ARGUMENT, "vofx_mesh_create: face_neighbor out of range" );
@@ -542,6 +698,19 @@ extern "C"
       }
     }
     const int nFaces = d->face_offsets[ n ], nCorners = d->corner_offsets[ n ], nStencil = d->stencil_offsets[ n ];
+    int nFaceCorners = 2 * nFaces;
+    if( dim == 3 )
+    {
+      if( d->face_corner_offsets[ 0 ] != 0 )
+        return set_error( VOFX_ERR_ARGUMENT, "vofx_mesh_create: CSR offsets must start at 0" );
+      for( int s = 0; s < nFaces; ++s )
+      {
+        const int fnc = d->face_corner_offsets[ s + 1 ] - d->face_corner_offsets[ s ];
+        if( fnc != 3 && fnc != 4 )
+          return set_error( VOFX_ERR_ARGUMENT, "vofx_mesh_create: Invalid GeometryType (intersections must be triangles or quadrilaterals)" );
+      }
+      nFaceCorners = d->face_corner_offsets[ nFaces ];
+    }
 
     // for every intersection the slot of the same intersection seen from the outside cell
     std::vector< int > back( size_t( nFaces ), -1 );
@@ -558,6 +727,8 @@ extern "C"
             continue;
           if( first < 0 )
             first = t;
+          if( dim == 3 )
+            continue;                    // two cells of a conforming 3D mesh share at most one face
           const double *a = d->face_corners + 4 * size_t( s ), *b = d->face_corners + 4 * size_t( t );
           const bool same = a[ 0 ] == b[ 0 ] && a[ 1 ] == b[ 1 ] && a[ 2 ] == b[ 2 ] && a[ 3 ] == b[ 3 ];
           const bool swapped = a[ 0 ] == b[ 2 ] && a[ 1 ] == b[ 3 ] && a[ 2 ] == b[ 0 ] && a[ 3 ] == b[ 1 ];
@@ -577,8 +748,10 @@ extern "C"
     vofx_mesh *m = new vofx_mesh;
     m->device = current;
     MeshDev &D = m->dev;
+    D.dim = dim;
     D.nCells = n;
     D.nFaces = nFaces;
+    D.faceCornerOffsets = nullptr;
     cudaError_t e = cudaSuccess;
     auto up = [ & ] ( auto *&dst, const auto *src, size_t count ) {
       if( e != cudaSuccess )
@@ -590,16 +763,18 @@ extern "C"
       dst = p;
     };
     up( D.cornerOffsets, d->corner_offsets, size_t( n ) + 1 );
-    up( D.corners, d->corners, 2 * size_t( nCorners ) );
-    up( D.centers, d->centers, 2 * size_t( n ) );
+    up( D.corners, d->corners, size_t( dim ) * size_t( nCorners ) );
+    up( D.centers, d->centers, size_t( dim ) * size_t( n ) );
     up( D.volumes, d->volumes, size_t( n ) );
     up( D.faceOffsets, d->face_offsets, size_t( n ) + 1 );
     up( D.faceNeighbor, d->face_neighbor, size_t( nFaces ) );
     up( D.backSlot, back.data(), size_t( nFaces ) );
-    up( D.faceCorners, d->face_corners, 4 * size_t( nFaces ) );
-    up( D.faceCenters, d->face_centers, 2 * size_t( nFaces ) );
-    up( D.faceUnit, d->face_unit_normals, 2 * size_t( nFaces ) );
-    up( D.faceInt, d->face_int_normals, 2 * size_t( nFaces ) );
+    if( dim == 3 )
+      up( D.faceCornerOffsets, d->face_corner_offsets, size_t( nFaces ) + 1 );
+    up( D.faceCorners, d->face_corners, size_t( dim ) * size_t( nFaceCorners ) );
+    up( D.faceCenters, d->face_centers, size_t( dim ) * size_t( nFaces ) );
+    up( D.faceUnit, d->face_unit_normals, size_t( dim ) * size_t( nFaces ) );
+    up( D.faceInt, d->face_int_normals, size_t( dim ) * size_t( nFaces ) );
     up( D.faceVolumes, d->face_volumes, size_t( nFaces ) );
     up( D.stencilOffsets, d->stencil_offsets, size_t( n ) + 1 );
     up( D.stencil, d->stencil, size_t( nStencil ) );
@@ -613,9 +788,9 @@ extern "C"
     alloc( m->recVN, size_t( nFaces ) );
     alloc( m->recDir, size_t( nFaces ) );
     alloc( m->u, size_t( n ) );
-    alloc( m->hs, 3 * size_t( n ) );
+    alloc( m->hs, size_t( dim + 1 ) * size_t( n ) );
     alloc( m->upd, size_t( n ) );
-    alloc( m->vel, 2 * size_t( nFaces ) );
+    alloc( m->vel, size_t( dim ) * size_t( nFaces ) );
     alloc( m->flags, size_t( n ) );
     if( e == cudaSuccess )
       e = cudaStreamCreateWithFlags( &m->ownStream, cudaStreamNonBlocking );
@@ -767,7 +942,7 @@ extern "C"
     VOFX_MESH_CUDA( cudaMemcpyAsync( m->flags, flags, n, cudaMemcpyHostToDevice, m->stream ) );
     if( int rc = vofx_mesh_reconstruct( m, m->u, m->flags, m->hs ) )
       return rc;
-    VOFX_MESH_CUDA( cudaMemcpyAsync( hs, m->hs, 3 * n * sizeof( double ), cudaMemcpyDeviceToHost, m->stream ) );
+    VOFX_MESH_CUDA( cudaMemcpyAsync( hs, m->hs, size_t( m->dev.dim + 1 ) * n * sizeof( double ), cudaMemcpyDeviceToHost, m->stream ) );
     VOFX_MESH_CUDA( cudaStreamSynchronize( m->stream ) );
     m->colorSet = false;
     return VOFX_OK;
@@ -784,7 +959,7 @@ extern "C"
     VOFX_MESH_CUDA( cudaMemcpyAsync( m->flags, flags, n, cudaMemcpyHostToDevice, m->stream ) );
     if( int rc = vofx_mesh_reconstruct_swartz( m, m->u, m->flags, m->hs, maxIterations ) )
       return rc;
-    VOFX_MESH_CUDA( cudaMemcpyAsync( hs, m->hs, 3 * n * sizeof( double ), cudaMemcpyDeviceToHost, m->stream ) );
+    VOFX_MESH_CUDA( cudaMemcpyAsync( hs, m->hs, size_t( m->dev.dim + 1 ) * n * sizeof( double ), cudaMemcpyDeviceToHost, m->stream ) );
     VOFX_MESH_CUDA( cudaStreamSynchronize( m->stream ) );
     m->colorSet = false;
     return VOFX_OK;
@@ -797,9 +972,9 @@ extern "C"
     if( !hs || !flags || !vel || !update || !dtEst )
       return set_error( VOFX_ERR_ARGUMENT, "vofx_mesh_evolve_host: null argument" );
     const size_t n = size_t( m->dev.nCells ), nf = size_t( m->dev.nFaces );
-    VOFX_MESH_CUDA( cudaMemcpyAsync( m->hs, hs, 3 * n * sizeof( double ), cudaMemcpyHostToDevice, m->stream ) );
+    VOFX_MESH_CUDA( cudaMemcpyAsync( m->hs, hs, size_t( m->dev.dim + 1 ) * n * sizeof( double ), cudaMemcpyHostToDevice, m->stream ) );
     VOFX_MESH_CUDA( cudaMemcpyAsync( m->flags, flags, n, cudaMemcpyHostToDevice, m->stream ) );
-    VOFX_MESH_CUDA( cudaMemcpyAsync( m->vel, vel, 2 * nf * sizeof( double ), cudaMemcpyHostToDevice, m->stream ) );
+    VOFX_MESH_CUDA( cudaMemcpyAsync( m->vel, vel, size_t( m->dev.dim ) * nf * sizeof( double ), cudaMemcpyHostToDevice, m->stream ) );
     m->velocitySet = false;
     if( int rc = vofx_mesh_evolve( m, m->hs, m->flags, m->vel, dt, m->upd, dtEst ) )
       return rc;
@@ -826,7 +1001,7 @@ extern "C"
       return rc;
     if( !vel )
       return set_error( VOFX_ERR_ARGUMENT, "vofx_mesh_velocity_upload: null argument" );
-    VOFX_MESH_CUDA( cudaMemcpyAsync( m->vel, vel, 2 * size_t( m->dev.nFaces ) * sizeof( double ), cudaMemcpyHostToDevice, m->stream ) );
+    VOFX_MESH_CUDA( cudaMemcpyAsync( m->vel, vel, size_t( m->dev.dim ) * size_t( m->dev.nFaces ) * sizeof( double ), cudaMemcpyHostToDevice, m->stream ) );
     VOFX_MESH_CUDA( cudaStreamSynchronize( m->stream ) );
     m->velocitySet = true;
     return VOFX_OK;

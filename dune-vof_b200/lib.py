@@ -45,7 +45,7 @@ class MeshDesc(C.Structure):
                 ("centers", C.c_void_p), ("volumes", C.c_void_p), ("face_offsets", C.c_void_p), ("face_neighbor", C.c_void_p),
                 ("face_corners", C.c_void_p), ("face_centers", C.c_void_p), ("face_unit_normals", C.c_void_p),
                 ("face_int_normals", C.c_void_p), ("face_volumes", C.c_void_p), ("stencil_offsets", C.c_void_p),
-                ("stencil", C.c_void_p)]
+                ("stencil", C.c_void_p), ("face_corner_offsets", C.c_void_p)]
 
 
 class StepParams(C.Structure):

@@ -1,4 +1,5 @@
-"""Flattening of an unstructured 2D grid (triangles and quadrilaterals) into the arrays of `vofx_mesh_desc`.
+"""Flattening of an unstructured grid (2D: triangles and quadrilaterals; 3D: tetrahedra and hexahedra) into the arrays of
+`vofx_mesh_desc`.
 
 This is the host-side step `north_star` describes for unstructured grids ("flattens the mesh into device arrays ...
 CSR vertex-neighbour stencils"): what a DUNE adaptor does by walking `elements(gridView)` / `intersections(gridView,
@@ -10,6 +11,12 @@ Conventions (DUNE reference elements): triangle corners (v0, v1, v2), faces (v0,
 corners (v0, v1, v2, v3) with v2 above v0, faces (v0,v2), (v1,v3), (v0,v1), (v2,v3).  Intersections are stored in face
 order; `face_neighbor` is -1 on the domain boundary.  The vertex-neighbour stencil follows
 stencil/vertexneighborsstencil.hh:52-94: all cells sharing a vertex, ascending index, self excluded.
+
+3D (`flatten3`): tetrahedron corners (v0..v3), faces (v0,v1,v2), (v0,v1,v3), (v0,v2,v3), (v1,v2,v3); hexahedron corners
+v0..v7 (bit d of the corner number = upper side along axis d), faces x-, x+, y-, y+, z-, z+ with their corners in
+ascending corner number.  The library forms makePolyhedron( geometry ) (3d/polyhedron.hh:366-404) from the corners and
+upwindPolygon3d (3d/upwindpolygon.hh:24-74) from the intersection corners, so `face_corner_offsets` says how many
+corners (3 or 4) each intersection has.
 """
 from __future__ import annotations
 
@@ -40,6 +47,8 @@ class FlatMesh:
     face_volumes: np.ndarray        # f64 [nf]
     stencil_offsets: np.ndarray     # int32 [n_cells+1]
     stencil: np.ndarray             # int32
+    dim: int = 2
+    face_corner_offsets: np.ndarray = None   # int32 [nf+1], 3D only (2D: two corners per intersection)
 
     @property
     def n_faces(self) -> int:
@@ -50,6 +59,8 @@ class FlatMesh:
         """a flattened mesh stored field by field (tests/golden/mesh2d_*.npz)"""
         kw = {}
         for k in cls.__dataclass_fields__:
+            if prefix + k not in z:
+                continue                      # 2D files carry neither dim nor face_corner_offsets
             a = z[prefix + k]
             kw[k] = int(a) if a.ndim == 0 else np.ascontiguousarray(a)
         return cls(**kw)
@@ -122,6 +133,140 @@ def flatten(vertices, cells) -> FlatMesh:
                     c_(face_int_normals), c_(face_volumes), stencil_offsets, stencil)
 
 
+_TET_FACES = ((0, 1, 2), (0, 1, 3), (0, 2, 3), (1, 2, 3))
+_HEX_FACES = ((0, 2, 4, 6), (1, 3, 5, 7), (0, 1, 4, 5), (2, 3, 6, 7), (0, 1, 2, 3), (4, 5, 6, 7))
+
+
+def flatten3(vertices, cells) -> FlatMesh:
+    """vertices: (nv, 3) floats; cells: sequence of 4-tuples (tetrahedra) or 8-tuples (hexahedra with planar faces) of
+    vertex ids in DUNE corner order."""
+    vertices = np.ascontiguousarray(vertices, dtype=np.float64)
+    n_cells = len(cells)
+    corner_offsets = np.zeros(n_cells + 1, dtype=np.int32)
+    face_offsets = np.zeros(n_cells + 1, dtype=np.int32)
+    for c, vs in enumerate(cells):
+        if len(vs) not in (4, 8):
+            raise ValueError("only tetrahedra and hexahedra")
+        corner_offsets[c + 1] = corner_offsets[c] + len(vs)
+        face_offsets[c + 1] = face_offsets[c] + (4 if len(vs) == 4 else 6)
+    corner_vertex = np.fromiter((v for vs in cells for v in vs), dtype=np.int32, count=int(corner_offsets[-1]))
+    corners = vertices[corner_vertex]
+
+    centers = np.empty((n_cells, 3))
+    volumes = np.empty(n_cells)
+    face_cells = {}
+    face_local = []
+    for c, vs in enumerate(cells):
+        x = vertices[list(vs)]
+        centers[c] = x.sum(axis=0) / len(vs)
+        if len(vs) == 4:
+            volumes[c] = abs(np.linalg.det(np.stack([x[1] - x[0], x[2] - x[0], x[3] - x[0]]))) / 6.0
+        else:
+            # planar faces: the hexahedron is the union of six tetrahedra around its main diagonal
+            vol = 0.0
+            for a, b in ((1, 3), (3, 2), (2, 6), (6, 4), (4, 5), (5, 1)):
+                vol += abs(np.linalg.det(np.stack([x[a] - x[0], x[b] - x[0], x[7] - x[0]]))) / 6.0
+            volumes[c] = vol
+        for loc in (_TET_FACES if len(vs) == 4 else _HEX_FACES):
+            ids = tuple(vs[k] for k in loc)
+            face_cells.setdefault(tuple(sorted(ids)), []).append(c)
+            face_local.append((c, ids))
+
+    nf = len(face_local)
+    face_neighbor = np.full(nf, -1, dtype=np.int32)
+    face_corner_offsets = np.zeros(nf + 1, dtype=np.int32)
+    for s, (c, ids) in enumerate(face_local):
+        face_corner_offsets[s + 1] = face_corner_offsets[s] + len(ids)
+    face_corners = np.empty((int(face_corner_offsets[-1]), 3))
+    face_centers = np.empty((nf, 3))
+    face_volumes = np.empty(nf)
+    normals = np.empty((nf, 3))
+    for s, (c, ids) in enumerate(face_local):
+        owners = face_cells[tuple(sorted(ids))]
+        if len(owners) > 2:
+            raise ValueError("non-manifold face")
+        for o in owners:
+            if o != c:
+                face_neighbor[s] = o
+        x = vertices[list(ids)]
+        face_corners[face_corner_offsets[s]:face_corner_offsets[s + 1]] = x
+        face_centers[s] = x.sum(axis=0) / len(ids)
+        if len(ids) == 3:
+            cr = np.cross(x[1] - x[0], x[2] - x[0]) * 0.5
+        else:
+            cr = np.cross(x[3] - x[0], x[2] - x[1]) * 0.5      # half the cross product of the diagonals (corners 0,1,2,3 = 00,10,01,11)
+        face_volumes[s] = np.sqrt(cr @ cr)
+        n = cr / face_volumes[s]
+        if n @ (face_centers[s] - centers[c]) < 0:
+            n = -n
+        normals[s] = n
+    face_int_normals = normals * face_volumes[:, None]
+
+    vertex_cells = [[] for _ in range(len(vertices))]
+    for c, vs in enumerate(cells):
+        for v in vs:
+            vertex_cells[v].append(c)
+    stencil_offsets = np.zeros(n_cells + 1, dtype=np.int32)
+    entries = []
+    for c, vs in enumerate(cells):
+        nb = sorted({o for v in vs for o in vertex_cells[v] if o != c})
+        entries.extend(nb)
+        stencil_offsets[c + 1] = len(entries)
+    stencil = np.asarray(entries, dtype=np.int32)
+
+    c_ = np.ascontiguousarray
+    return FlatMesh(n_cells, len(vertices), corner_offsets, c_(corner_vertex), c_(corners), c_(centers), c_(volumes),
+                    face_offsets, face_neighbor, c_(face_corners), c_(face_centers), c_(normals),
+                    c_(face_int_normals), c_(face_volumes), stencil_offsets, stencil, 3, face_corner_offsets)
+
+
+def perturbed_cube(n: int, kind: str = "tet", seed: int = 0, jitter: float = 0.2):
+    """A conforming mesh of the unit cube from an n^3 lattice.  kind "tet": interior vertices moved by up to `jitter`·h, every
+    lattice cube split into six tetrahedra around its main diagonal (conforming across cubes); "hex": a rectilinear lattice
+    with seeded non-uniform spacings (planar faces); "mixed" is not offered: tetrahedra and hexahedra do not share faces.
+    Returns (vertices, cells)."""
+    rng = np.random.default_rng(seed)
+    h = 1.0 / n
+    if kind == "hex":
+        axes = []
+        for _ in range(3):
+            w = 1.0 + (rng.random(n) - 0.5) * 2.0 * jitter
+            x = np.concatenate([[0.0], np.cumsum(w)])
+            axes.append(x / x[-1])
+        vx, vy, vz = np.meshgrid(axes[0], axes[1], axes[2], indexing="ij")
+    else:
+        xs = np.arange(n + 1) * h
+        vx, vy, vz = np.meshgrid(xs, xs, xs, indexing="ij")
+    vid = lambda i, j, k: (k * (n + 1) + j) * (n + 1) + i
+    v = np.empty(((n + 1) ** 3, 3))
+    for k in range(n + 1):
+        for j in range(n + 1):
+            for i in range(n + 1):
+                v[vid(i, j, k)] = (vx[i, j, k], vy[i, j, k], vz[i, j, k])
+    if kind != "hex":
+        for k in range(1, n):
+            for j in range(1, n):
+                for i in range(1, n):
+                    v[vid(i, j, k)] += (rng.random(3) - 0.5) * 2.0 * jitter * h
+    cells = []
+    for k in range(n):
+        for j in range(n):
+            for i in range(n):
+                c = [vid(i + (q & 1), j + ((q >> 1) & 1), k + ((q >> 2) & 1)) for q in range(8)]
+                if kind == "hex":
+                    cells.append(tuple(c))
+                else:
+                    # Kuhn's subdivision: one tetrahedron per monotone path from corner 0 to corner 7
+                    # (positively oriented: makePolyhedron's simplex table then yields outer face normals)
+                    for a, b in ((1, 3), (3, 2), (2, 6), (6, 4), (4, 5), (5, 1)):
+                        t = (c[0], c[a], c[b], c[7])
+                        x = v[list(t)]
+                        if np.linalg.det(np.stack([x[1] - x[0], x[2] - x[0], x[3] - x[0]])) < 0:
+                            t = (c[0], c[b], c[a], c[7])
+                        cells.append(t)
+    return v, cells
+
+
 def perturbed_square(n: int, kind: str = "tri", seed: int = 0, jitter: float = 0.25):
     """A conforming mesh of the unit square from an n x n lattice whose interior vertices are moved by up to
     `jitter`·h: kind "tri" splits every quadrilateral into two triangles (alternating diagonals), "quad" keeps the
@@ -150,7 +295,7 @@ def perturbed_square(n: int, kind: str = "tri", seed: int = 0, jitter: float = 0
 
 
 class MeshOperators:
-    """dune-vof's FlagOperator / ModifiedYoungsReconstruction / Evolution on an unstructured 2D grid, computed on the GPU
+    """dune-vof's FlagOperator / ModifiedYoungsReconstruction / Evolution on an unstructured 2D or 3D grid, computed on the GPU
     through the C ABI (vofx_mesh_*, include/vofx.h).  Host numpy arrays in and out; `run` keeps the colour function on
     the device for a whole time loop (algorithm.hh:68-95).  There is no CPU fallback."""
 
@@ -161,10 +306,11 @@ class MeshOperators:
         self._C, self._lib, self.L = C, _lib, _lib.load()
         self.m = m
         a = lambda x: x.ctypes.data
-        self._desc = _lib.MeshDesc(2, m.n_cells, a(m.corner_offsets), a(m.corners), a(m.centers), a(m.volumes),
+        self._desc = _lib.MeshDesc(m.dim, m.n_cells, a(m.corner_offsets), a(m.corners), a(m.centers), a(m.volumes),
                                    a(m.face_offsets), a(m.face_neighbor), a(m.face_corners), a(m.face_centers),
                                    a(m.face_unit_normals), a(m.face_int_normals), a(m.face_volumes),
-                                   a(m.stencil_offsets), a(m.stencil))
+                                   a(m.stencil_offsets), a(m.stencil),
+                                   a(m.face_corner_offsets) if m.face_corner_offsets is not None else None)
         h = C.c_void_p()
         _lib.check(self.L.vofx_mesh_create(C.byref(self._desc), device, C.byref(h)))
         self._h = h
@@ -193,7 +339,7 @@ class MeshOperators:
     def youngs(self, u, flags):
         u = np.ascontiguousarray(u, dtype=np.float64)
         flags = np.ascontiguousarray(flags, dtype=np.uint8)
-        hs = np.empty((self.m.n_cells, 3))
+        hs = np.empty((self.m.n_cells, self.m.dim + 1))
         self._lib.check(self.L.vofx_mesh_reconstruct_host(self._h, u.ctypes.data, flags.ctypes.data, hs.ctypes.data))
         return hs
 

@@ -58,7 +58,8 @@ namespace Dune
       {
       public:
         using GridView = GV;
-        static_assert( GridView::dimension == 2, "the unstructured path is built for 2D grids" );
+        static constexpr int D = GridView::dimension;
+        static_assert( D == 2 || D == 3, "the unstructured path is built for 2D (triangles, quadrilaterals) and 3D (tetrahedra, hexahedra) grids" );
 
         explicit Context ( const GridView &gridView, int device = -1 )
         : gridView_( gridView )
@@ -84,17 +85,18 @@ namespace Dune
             faceOffsets[ i + 1 ] = faceOffsets[ i ] + nFaces[ i ];
           }
           const std::size_t nc = std::size_t( cornerOffsets[ n ] ), nf = std::size_t( faceOffsets[ n ] );
-          corners.resize( 2 * nc );
-          centers.resize( 2 * n );
+          corners.resize( D * nc );
+          centers.resize( D * n );
           volumes.resize( n );
           faceNeighbor.assign( nf, -1 );
-          faceCorners.resize( 4 * nf );
-          faceCenters.resize( 2 * nf );
-          faceUnitNormals.resize( 2 * nf );
-          faceIntNormals.resize( 2 * nf );
+          faceCornerOffsets.assign( nf + 1, 0 );
+          faceCorners.clear();
+          faceCenters.resize( D * nf );
+          faceUnitNormals.resize( D * nf );
+          faceIntNormals.resize( D * nf );
           faceVolumes.resize( nf );
 
-          std::vector< std::vector< std::int32_t > > cellsOfVertex( indexSet.size( 2 ) );
+          std::vector< std::vector< std::int32_t > > cellsOfVertex( indexSet.size( D ) );
           for( const auto &entity : elements( gridView_ ) )
           {
             const std::size_t i = indexSet.index( entity );
@@ -102,13 +104,13 @@ namespace Dune
             for( int k = 0; k < nCorners[ i ]; ++k )
             {
               const auto x = geometry.corner( k );
-              corners[ 2 * ( cornerOffsets[ i ] + k ) ] = x[ 0 ];
-              corners[ 2 * ( cornerOffsets[ i ] + k ) + 1 ] = x[ 1 ];
-              cellsOfVertex[ indexSet.subIndex( entity, k, 2 ) ].push_back( std::int32_t( i ) );
+              for( int d = 0; d < D; ++d )
+                corners[ D * ( cornerOffsets[ i ] + k ) + d ] = x[ d ];
+              cellsOfVertex[ indexSet.subIndex( entity, k, D ) ].push_back( std::int32_t( i ) );
             }
             const auto center = geometry.center();
-            centers[ 2 * i ] = center[ 0 ];
-            centers[ 2 * i + 1 ] = center[ 1 ];
+            for( int d = 0; d < D; ++d )
+              centers[ D * i + d ] = center[ d ];
             volumes[ i ] = geometry.volume();
             std::size_t s = std::size_t( faceOffsets[ i ] );
             for( const auto &intersection : intersections( gridView_, entity ) )
@@ -116,17 +118,26 @@ namespace Dune
               if( intersection.neighbor() )
                 faceNeighbor[ s ] = std::int32_t( indexSet.index( intersection.outside() ) );
               const auto ig = intersection.geometry();
-              const auto a = ig.corner( 0 ), b = ig.corner( 1 ), c = ig.center();
+              const auto c = ig.center();
               const auto un = intersection.centerUnitOuterNormal();
-              const typename std::decay_t< decltype( intersection ) >::LocalCoordinate local( 0.5 );   // refElement.position( 0, 0 )
+              // refElement.position( 0, 0 ): the centre of the intersection's reference element (evolution.hh:107-108)
+              typename std::decay_t< decltype( intersection ) >::LocalCoordinate local( 0.5 );
+              if( D == 3 && ig.corners() == 3 )
+                local = 1.0 / 3.0;
               const auto in = intersection.integrationOuterNormal( local );
-              for( int d = 0; d < 2; ++d )
+              const int nic = ig.corners();          // 2 in 2D; 3 (triangle) or 4 (quadrilateral) in 3D
+              faceCornerOffsets[ s + 1 ] = faceCornerOffsets[ s ] + nic;
+              for( int k = 0; k < nic; ++k )
               {
-                faceCorners[ 4 * s + d ] = a[ d ];
-                faceCorners[ 4 * s + 2 + d ] = b[ d ];
-                faceCenters[ 2 * s + d ] = c[ d ];
-                faceUnitNormals[ 2 * s + d ] = un[ d ];
-                faceIntNormals[ 2 * s + d ] = in[ d ];
+                const auto x = ig.corner( k );
+                for( int d = 0; d < D; ++d )
+                  faceCorners.push_back( x[ d ] );
+              }
+              for( int d = 0; d < D; ++d )
+              {
+                faceCenters[ D * s + d ] = c[ d ];
+                faceUnitNormals[ D * s + d ] = un[ d ];
+                faceIntNormals[ D * s + d ] = in[ d ];
               }
               faceVolumes[ s ] = ig.volume();
               ++s;
@@ -141,7 +152,7 @@ namespace Dune
             const std::size_t i = indexSet.index( entity );
             scratch.clear();
             for( int k = 0; k < nCorners[ i ]; ++k )
-              for( std::int32_t other : cellsOfVertex[ indexSet.subIndex( entity, k, 2 ) ] )
+              for( std::int32_t other : cellsOfVertex[ indexSet.subIndex( entity, k, D ) ] )
                 if( std::size_t( other ) != i )
                   scratch.push_back( other );
             std::sort( scratch.begin(), scratch.end() );
@@ -158,7 +169,7 @@ namespace Dune
           perCell_.shrink_to_fit();
 
           vofx_mesh_desc desc{};
-          desc.dim = 2;
+          desc.dim = D;
           desc.n_cells = std::int64_t( n );
           desc.corner_offsets = cornerOffsets.data();
           desc.corners = corners.data();
@@ -173,6 +184,7 @@ namespace Dune
           desc.face_volumes = faceVolumes.data();
           desc.stencil_offsets = stencilOffsets.data();
           desc.stencil = stencil.data();
+          desc.face_corner_offsets = faceCornerOffsets.data();
           check( vofx_mesh_create( &desc, device, &mesh_ ) );
         }
 
@@ -186,7 +198,7 @@ namespace Dune
         std::size_t faces () const { return faceVolumes.size(); }
 
         // the flattened grid (leaf-index order)
-        std::vector< std::int32_t > cornerOffsets, faceOffsets, faceNeighbor, stencilOffsets, stencil;
+        std::vector< std::int32_t > cornerOffsets, faceOffsets, faceNeighbor, faceCornerOffsets, stencilOffsets, stencil;
         std::vector< double > corners, centers, volumes, faceCorners, faceCenters, faceUnitNormals, faceIntNormals, faceVolumes;
         // staging
         std::vector< double > color, update, halfspaces, faceVelocity;
@@ -212,13 +224,13 @@ namespace Dune
         template< class ReconstructionSet >
         void gatherReconstructions ( const ReconstructionSet &recs )
         {
-          halfspaces.resize( 3 * size() );
+          halfspaces.resize( ( D + 1 ) * size() );
           std::size_t i = 0;
           for( auto it = recs.begin(); it != recs.end(); ++it, ++i )
           {
-            halfspaces[ 3 * i ] = it->innerNormal()[ 0 ];
-            halfspaces[ 3 * i + 1 ] = it->innerNormal()[ 1 ];
-            halfspaces[ 3 * i + 2 ] = it->boundary().distance();
+            for( int d = 0; d < D; ++d )
+              halfspaces[ ( D + 1 ) * i + d ] = it->innerNormal()[ d ];
+            halfspaces[ ( D + 1 ) * i + D ] = it->boundary().distance();
           }
         }
 
@@ -227,7 +239,7 @@ namespace Dune
         template< class Velocity >
         void sampleVelocity ( Velocity &velocity )
         {
-          faceVelocity.assign( 2 * faces(), 0.0 );
+          faceVelocity.assign( D * faces(), 0.0 );
           const auto &indexSet = gridView_.indexSet();
           for( const auto &entity : elements( gridView_ ) )
           {
@@ -235,11 +247,13 @@ namespace Dune
             for( const auto &intersection : intersections( gridView_, entity ) )
             {
               velocity.bind( intersection );
-              const typename std::decay_t< decltype( intersection ) >::LocalCoordinate local( 0.5 );
+              typename std::decay_t< decltype( intersection ) >::LocalCoordinate local( 0.5 );
+              if( D == 3 && intersection.geometry().corners() == 3 )
+                local = 1.0 / 3.0;             // refElement.position( 0, 0 ) of a triangle
               const auto v = velocity( local );
               velocity.unbind();
-              faceVelocity[ 2 * s ] = v[ 0 ];
-              faceVelocity[ 2 * s + 1 ] = v[ 1 ];
+              for( int d = 0; d < D; ++d )
+                faceVelocity[ D * s + d ] = v[ d ];
               ++s;
             }
           }
@@ -307,7 +321,7 @@ namespace Dune
           auto &c = *context_;
           c.gatherScalars( color, c.color );
           c.gatherFlags( flags );
-          c.halfspaces.resize( 3 * c.size() );
+          c.halfspaces.resize( ( Context< GV >::D + 1 ) * c.size() );
           check( vofx_mesh_reconstruct_host( c.mesh(), c.color.data(), c.flags.data(), c.halfspaces.data() ) );
           using HalfSpace = typename ReconstructionSet::DataType;
           using Coordinate = typename HalfSpace::Coordinate;
@@ -315,9 +329,10 @@ namespace Dune
           for( auto it = reconstructions.begin(); it != reconstructions.end(); ++it, ++i )
           {
             Coordinate normal;
-            normal[ 0 ] = c.halfspaces[ 3 * i ];
-            normal[ 1 ] = c.halfspaces[ 3 * i + 1 ];
-            *it = HalfSpace( normal, c.halfspaces[ 3 * i + 2 ] );
+            constexpr int D = Context< GV >::D;
+            for( int d = 0; d < D; ++d )
+              normal[ d ] = c.halfspaces[ ( D + 1 ) * i + d ];
+            *it = HalfSpace( normal, c.halfspaces[ ( D + 1 ) * i + D ] );
           }
         }
 
@@ -340,7 +355,7 @@ namespace Dune
           auto &c = *context_;
           c.gatherScalars( color, c.color );
           c.gatherFlags( flags );
-          c.halfspaces.resize( 3 * c.size() );
+          c.halfspaces.resize( ( Context< GV >::D + 1 ) * c.size() );
           check( vofx_mesh_reconstruct_swartz_host( c.mesh(), c.color.data(), c.flags.data(), c.halfspaces.data(), int( maxIterations_ ) ) );
           using HalfSpace = typename ReconstructionSet::DataType;
           using Coordinate = typename HalfSpace::Coordinate;
@@ -348,9 +363,10 @@ namespace Dune
           for( auto it = reconstructions.begin(); it != reconstructions.end(); ++it, ++i )
           {
             Coordinate normal;
-            normal[ 0 ] = c.halfspaces[ 3 * i ];
-            normal[ 1 ] = c.halfspaces[ 3 * i + 1 ];
-            *it = HalfSpace( normal, c.halfspaces[ 3 * i + 2 ] );
+            constexpr int D = Context< GV >::D;
+            for( int d = 0; d < D; ++d )
+              normal[ d ] = c.halfspaces[ ( D + 1 ) * i + d ];
+            *it = HalfSpace( normal, c.halfspaces[ ( D + 1 ) * i + D ] );
           }
         }
 

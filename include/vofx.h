@@ -346,10 +346,14 @@ int vofx_profile_read ( vofx_ctx *ctx, int max_entries, char *names, double *tot
  * Operators (same semantics and bits as the structured ones): flagging.hh:35-70, reconstruction/modifiedyoungs.hh:63-134
  * (height functions and HF curvature are Cartesian-only in the reference too), evolution/evolution.hh:58-145 with
  * 2d/upwindpolygon.hh:24-30.  The velocity is SAMPLED: one vector per intersection = what the reference's Velocity
- * returns for refElement.position( 0, 0 ) (velocity.hh:15-20, evolution.hh:107-108).  3D simplices are not built. */
+ * returns for refElement.position( 0, 0 ) (velocity.hh:15-20, evolution.hh:107-108).
+ * dim 3 (tetrahedra and hexahedra; "[2]" below reads "[3]"): the library forms makePolyhedron( geometry ) from the 4 or 8
+ * corners (3d/polyhedron.hh:366-404), locates with geometry/algorithm.hh:119-236 and clips upwindPolygon3d of the 3 or 4
+ * intersection corners (3d/upwindpolygon.hh:24-74: prism / cube topology); face_corner_offsets is then required.  The
+ * Swartz reconstruction on unstructured grids is 2D only. */
 typedef struct vofx_mesh_desc
 {
-  int32_t dim;                       /* 2 */
+  int32_t dim;                       /* 2 or 3 */
   int64_t n_cells;
   const int32_t *corner_offsets;     /* [n_cells + 1] */
   const double *corners;             /* [corner_offsets[n_cells]][2] */
@@ -364,6 +368,8 @@ typedef struct vofx_mesh_desc
   const double *face_volumes;        /* [n_faces] */
   const int32_t *stencil_offsets;    /* [n_cells + 1] */
   const int32_t *stencil;            /* [stencil_offsets[n_cells]] */
+  const int32_t *face_corner_offsets;/* dim 3: [n_faces + 1], intersection s has the corners face_corners[ face_corner_offsets[s] ... ][3];
+                                        dim 2: ignored (may be NULL), two corners per intersection */
 } vofx_mesh_desc;
 
 typedef struct vofx_mesh vofx_mesh;

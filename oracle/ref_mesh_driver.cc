@@ -1,9 +1,10 @@
 // TEST INFRASTRUCTURE ONLY (oracle/).  Not part of the product; the product never loads this.
 //
 // C-ABI harness around the UNMODIFIED reference headers (/root/reference/dune/vof/**) instantiated on the
-// unstructured 2D grid model oracle/shim/dune/grid/common/meshgrid.hh (triangles and quadrilaterals as flattened
-// arrays).  Built by oracle/Makefile into oracle/_ref/libvofrefmesh.so (git-ignored).  It pins
-// vo_mesh_* of oracle/vof_oracle.c and generates tests/golden/mesh2d_*.npz.
+// unstructured grid model oracle/shim/dune/grid/common/meshgrid.hh (flattened arrays): triangles and quadrilaterals
+// (MESHDIM 2, the default, symbols refmesh_*) or tetrahedra and hexahedra (-DMESHDIM=3, symbols refmesh3_*).  Built by
+// oracle/Makefile into oracle/_ref/libvofrefmesh.so and oracle/_ref/libvofrefmesh3.so (git-ignored).  It pins
+// vo_mesh_* of oracle/vof_oracle.c and generates tests/golden/mesh2d_*.npz / mesh3d_*.npz.
 //
 // The velocity is a SAMPLED field: one vector per intersection, evaluated by the caller at the intersection centre
 // (what Velocity< Problem, GridView >::operator() returns for refElement.position( 0, 0 ), velocity.hh:15-20,
@@ -15,7 +16,15 @@
 #include <string>
 #include <vector>
 
-#define GRIDDIM 2
+#ifndef MESHDIM
+#define MESHDIM 2
+#endif
+#define GRIDDIM MESHDIM
+#if MESHDIM == 2
+#define RM( name ) refmesh_##name
+#else
+#define RM( name ) refmesh3_##name
+#endif
 
 #include <dune/common/exceptions.hh>
 #include <dune/common/fmatrix.hh>
@@ -33,42 +42,54 @@
 #include <dune/vof/geometry/upwindpolygon.hh>
 #include <dune/vof/stencil/vertexneighborsstencil.hh>
 #include <dune/vof/reconstruction/modifiedyoungs.hh>
+#if MESHDIM == 2
 #include <dune/vof/reconstruction/modifiedswartz.hh>
+#endif
 
 namespace
 {
 
   thread_local std::string lastError;
 
+  constexpr int D = MESHDIM;
+  using Coord = Dune::FieldVector< double, D >;
+  using Entity = Dune::MeshEntityT< D >;
+  using Intersection = Dune::MeshIntersectionT< D >;
+
+  Coord coord ( const double *x )
+  {
+    Coord c;
+    for( int k = 0; k < D; ++k )
+      c[ k ] = x[ k ];
+    return c;
+  }
+
   struct SampledVelocity
   {
-    using Coord = Dune::FieldVector< double, 2 >;
     const double *samples;
-    const Dune::MeshIntersection *is = nullptr;
+    const Intersection *is = nullptr;
 
-    void bind ( const Dune::MeshIntersection &intersection ) { is = &intersection; }
+    void bind ( const Intersection &intersection ) { is = &intersection; }
     void unbind () { is = nullptr; }
-    Coord operator() ( const Dune::FieldVector< double, 1 > & ) const
-    {
-      return Coord( { samples[ 2 * is->slot ], samples[ 2 * is->slot + 1 ] } );
-    }
+    Coord operator() ( const Dune::FieldVector< double, D - 1 > & ) const { return coord( samples + D * is->slot ); }
   };
 
   struct Ctx
   {
-    using GridView = Dune::MeshGridView;
-    using Coord = Dune::FieldVector< double, 2 >;
+    using GridView = Dune::MeshGridViewT< D >;
     using Stencils = Dune::VoF::VertexNeighborsStencil< GridView >;
     using Color = Dune::VoF::ColorFunction< GridView >;
     using Flags = Dune::VoF::FlagSet< GridView >;
     using Recs = Dune::VoF::ReconstructionSet< GridView >;
     using Youngs = Dune::VoF::ModifiedYoungsReconstruction< GridView, Stencils >;
+#if MESHDIM == 2
     using Swartz = Dune::VoF::ModifiedSwartzReconstruction< GridView, Stencils, Youngs >;
+#endif
 
     // owned copies of the caller's arrays
-    std::vector< std::int32_t > cornerOffsets, cornerVertex, faceOffsets, faceNeighbor;
+    std::vector< std::int32_t > cornerOffsets, cornerVertex, faceOffsets, faceNeighbor, faceCornerOffsets;
     std::vector< double > corners, centers, volumes, faceCorners, faceCenters, faceUnitNormals, faceIntNormals, faceVolumes;
-    Dune::MeshGrid2 grid;
+    Dune::MeshGridT< D > grid;
     std::unique_ptr< GridView > gv;
     std::unique_ptr< Stencils > stencils;
 
@@ -84,7 +105,7 @@ namespace
     {
       auto it = recs.begin();
       for( std::size_t i = 0; i < cells(); ++i, ++it )
-        *it = Dune::VoF::HalfSpace< Coord >( Coord( { hs[ 3 * i ], hs[ 3 * i + 1 ] } ), hs[ 3 * i + 2 ] );
+        *it = Dune::VoF::HalfSpace< Coord >( coord( hs + ( D + 1 ) * i ), hs[ ( D + 1 ) * i + D ] );
     }
   };
 
@@ -113,28 +134,33 @@ namespace
 extern "C"
 {
 
-  const char *refmesh_last_error () { return lastError.c_str(); }
+  const char *RM( last_error ) () { return lastError.c_str(); }
 
-  void *refmesh_create ( std::int64_t nCells, std::int64_t nVertices, const std::int32_t *cornerOffsets, const std::int32_t *cornerVertex,
-                         const double *corners, const double *centers, const double *volumes, const std::int32_t *faceOffsets,
-                         const std::int32_t *faceNeighbor, const double *faceCorners, const double *faceCenters,
-                         const double *faceUnitNormals, const double *faceIntNormals, const double *faceVolumes )
+  // faceCornerOffsets: [faces + 1] positions in faceCorners (in corners, not doubles); null = two corners per intersection
+  void *RM( create ) ( std::int64_t nCells, std::int64_t nVertices, const std::int32_t *cornerOffsets, const std::int32_t *cornerVertex,
+                       const double *corners, const double *centers, const double *volumes, const std::int32_t *faceOffsets,
+                       const std::int32_t *faceNeighbor, const double *faceCorners, const double *faceCenters,
+                       const double *faceUnitNormals, const double *faceIntNormals, const double *faceVolumes,
+                       const std::int32_t *faceCornerOffsets )
   {
     auto *c = new Ctx;
     const std::size_t nCorners = std::size_t( cornerOffsets[ nCells ] ), nFaces = std::size_t( faceOffsets[ nCells ] );
     c->cornerOffsets.assign( cornerOffsets, cornerOffsets + nCells + 1 );
     c->cornerVertex.assign( cornerVertex, cornerVertex + nCorners );
-    c->corners.assign( corners, corners + 2 * nCorners );
-    c->centers.assign( centers, centers + 2 * nCells );
+    c->corners.assign( corners, corners + D * nCorners );
+    c->centers.assign( centers, centers + D * nCells );
     c->volumes.assign( volumes, volumes + nCells );
     c->faceOffsets.assign( faceOffsets, faceOffsets + nCells + 1 );
     c->faceNeighbor.assign( faceNeighbor, faceNeighbor + nFaces );
-    c->faceCorners.assign( faceCorners, faceCorners + 4 * nFaces );
-    c->faceCenters.assign( faceCenters, faceCenters + 2 * nFaces );
-    c->faceUnitNormals.assign( faceUnitNormals, faceUnitNormals + 2 * nFaces );
-    c->faceIntNormals.assign( faceIntNormals, faceIntNormals + 2 * nFaces );
+    if( faceCornerOffsets )
+      c->faceCornerOffsets.assign( faceCornerOffsets, faceCornerOffsets + nFaces + 1 );
+    const std::size_t nFaceCorners = faceCornerOffsets ? std::size_t( faceCornerOffsets[ nFaces ] ) : 2 * nFaces;
+    c->faceCorners.assign( faceCorners, faceCorners + D * nFaceCorners );
+    c->faceCenters.assign( faceCenters, faceCenters + D * nFaces );
+    c->faceUnitNormals.assign( faceUnitNormals, faceUnitNormals + D * nFaces );
+    c->faceIntNormals.assign( faceIntNormals, faceIntNormals + D * nFaces );
     c->faceVolumes.assign( faceVolumes, faceVolumes + nFaces );
-    Dune::MeshGrid2 &g = c->grid;
+    Dune::MeshGridT< D > &g = c->grid;
     g.nCells = nCells;
     g.nVertices = nVertices;
     g.cornerOffsets = c->cornerOffsets.data();
@@ -144,6 +170,7 @@ extern "C"
     g.volumes = c->volumes.data();
     g.faceOffsets = c->faceOffsets.data();
     g.faceNeighbor = c->faceNeighbor.data();
+    g.faceCornerOffsets = faceCornerOffsets ? c->faceCornerOffsets.data() : nullptr;
     g.faceCorners = c->faceCorners.data();
     g.faceCenters = c->faceCenters.data();
     g.faceUnitNormals = c->faceUnitNormals.data();
@@ -154,17 +181,17 @@ extern "C"
     return c;
   }
 
-  void refmesh_destroy ( void *handle ) { delete static_cast< Ctx * >( handle ); }
+  void RM( destroy ) ( void *handle ) { delete static_cast< Ctx * >( handle ); }
 
   // the reference's vertex-neighbour stencils as CSR (entries = cell indices in the order the reference stores them)
-  std::int64_t refmesh_stencil ( void *handle, std::int32_t *offsets, std::int32_t *entries, std::int64_t capacity )
+  std::int64_t RM( stencil ) ( void *handle, std::int32_t *offsets, std::int32_t *entries, std::int64_t capacity )
   {
     Ctx &ctx = *static_cast< Ctx * >( handle );
     std::int64_t k = 0;
     for( std::int64_t i = 0; i < ctx.grid.nCells; ++i )
     {
       offsets[ i ] = std::int32_t( k );
-      for( const auto &nb : ( *ctx.stencils )[ Dune::MeshEntity { &ctx.grid, i } ] )
+      for( const auto &nb : ( *ctx.stencils )[ Entity { &ctx.grid, i } ] )
       {
         if( k < capacity )
           entries[ k ] = std::int32_t( nb.idx );
@@ -176,7 +203,7 @@ extern "C"
   }
 
   // flagging.hh:35-70
-  int refmesh_flag ( void *handle, const double *u, double eps, std::uint8_t *flagsOut )
+  int RM( flag ) ( void *handle, const double *u, double eps, std::uint8_t *flagsOut )
   {
     return guarded( [ & ] {
       Ctx &ctx = *static_cast< Ctx * >( handle );
@@ -193,7 +220,7 @@ extern "C"
   }
 
   // reconstruction/modifiedyoungs.hh:63-76
-  int refmesh_youngs ( void *handle, const double *u, const std::uint8_t *flagsIn, double *hs )
+  int RM( youngs ) ( void *handle, const double *u, const std::uint8_t *flagsIn, double *hs )
   {
     return guarded( [ & ] {
       Ctx &ctx = *static_cast< Ctx * >( handle );
@@ -207,14 +234,15 @@ extern "C"
       auto it = recs.begin();
       for( std::size_t i = 0; i < ctx.cells(); ++i, ++it )
       {
-        hs[ 3 * i ] = it->innerNormal()[ 0 ];
-        hs[ 3 * i + 1 ] = it->innerNormal()[ 1 ];
-        hs[ 3 * i + 2 ] = it->boundary().distance();
+        for( int k = 0; k < D; ++k )
+          hs[ ( D + 1 ) * i + k ] = it->innerNormal()[ k ];
+        hs[ ( D + 1 ) * i + D ] = it->boundary().distance();
       }
       return 0;
     } );
   }
 
+#if MESHDIM == 2
   // reconstruction/modifiedswartz.hh:70-153 (2D), initialised by ModifiedYoungsReconstruction
   int refmesh_swartz ( void *handle, const double *u, const std::uint8_t *flagsIn, double *hs, int maxIterations )
   {
@@ -230,16 +258,18 @@ extern "C"
       auto it = recs.begin();
       for( std::size_t i = 0; i < ctx.cells(); ++i, ++it )
       {
-        hs[ 3 * i ] = it->innerNormal()[ 0 ];
-        hs[ 3 * i + 1 ] = it->innerNormal()[ 1 ];
-        hs[ 3 * i + 2 ] = it->boundary().distance();
+        for( int k = 0; k < D; ++k )
+          hs[ ( D + 1 ) * i + k ] = it->innerNormal()[ k ];
+        hs[ ( D + 1 ) * i + D ] = it->boundary().distance();
       }
       return 0;
     } );
   }
 
+#endif
+
   // evolution/evolution.hh:58-76 with one sampled velocity per intersection
-  int refmesh_evolve ( void *handle, const double *hs, const std::uint8_t *flagsIn, const double *faceVelocity, double dt,
+  int RM( evolve ) ( void *handle, const double *hs, const std::uint8_t *flagsIn, const double *faceVelocity, double dt,
                        double *updateOut, double *dtEst )
   {
     return guarded( [ & ] {
@@ -257,16 +287,16 @@ extern "C"
     } );
   }
 
-  // locateHalfSpace( Polygon, normal, fraction ), geometry/algorithm.hh:68-111, on one cell of the mesh
-  int refmesh_locate ( void *handle, std::int64_t cell, const double *normal, double fraction, double *out )
+  // locateHalfSpace( Polygon / Polyhedron, normal, fraction ), geometry/algorithm.hh:68-111 / :119-236, on one cell of the mesh
+  int RM( locate ) ( void *handle, std::int64_t cell, const double *normal, double fraction, double *out )
   {
     return guarded( [ & ] {
       Ctx &ctx = *static_cast< Ctx * >( handle );
-      const auto polygon = Dune::VoF::makePolytope( Dune::MeshEntity { &ctx.grid, cell }.geometry() );
-      const auto hs = Dune::VoF::locateHalfSpace( polygon, Ctx::Coord( { normal[ 0 ], normal[ 1 ] } ), fraction );
-      out[ 0 ] = hs.innerNormal()[ 0 ];
-      out[ 1 ] = hs.innerNormal()[ 1 ];
-      out[ 2 ] = hs.boundary().distance();
+      const auto polytope = Dune::VoF::makePolytope( Entity { &ctx.grid, cell }.geometry() );
+      const auto hs = Dune::VoF::locateHalfSpace( polytope, coord( normal ), fraction );
+      for( int k = 0; k < D; ++k )
+        out[ k ] = hs.innerNormal()[ k ];
+      out[ D ] = hs.boundary().distance();
       return 0;
     } );
   }

@@ -3120,8 +3120,19 @@ int vo_mesh_flag ( const vo_mesh *m, const double *u, double eps, uint8_t *flags
   return 0;
 }
 
+static int mesh_cell_polyhedron ( const vo_mesh *m, int64_t cell, vo_polyhedron *p );
+static int mesh_flux3 ( const double *c, int nc, const double *v, const double *hs, double *flux );
+static int mesh_dim ( const vo_mesh *m );
+
 int vo_mesh_locate ( const vo_mesh *m, int64_t cell, const double *normal, double fraction, double *out )
 {
+  if( mesh_dim( m ) == 3 )
+  {
+    vo_polyhedron ph;
+    if( mesh_cell_polyhedron( m, cell, &ph ) )
+      return 1;
+    return locate_3d( &ph, normal, fraction, out );
+  }
   vo_polygon p;
   if( mesh_cell_polygon( m, cell, &p ) )
     return 1;
@@ -3132,7 +3143,8 @@ int vo_mesh_locate ( const vo_mesh *m, int64_t cell, const double *normal, doubl
 /* applyLocal, modifiedyoungs.hh:90-134 */
 static int mesh_youngs_local ( const vo_mesh *m, const double *u, int64_t cell, double *hs )
 {
-  const double *center = m->centers + 2 * cell;
+  const int D = mesh_dim( m );
+  const double *center = m->centers + D * cell;
   const double colorEn = u[ cell ];
   double AtA[ 3 ][ 3 ] = { { 0, 0, 0 }, { 0, 0, 0 }, { 0, 0, 0 } };
   double Atb[ 3 ] = { 0, 0, 0 };
@@ -3141,34 +3153,40 @@ static int mesh_youngs_local ( const vo_mesh *m, const double *u, int64_t cell, 
   {
     const int64_t nb = m->stencil[ s ];
     const double colorNb = clampd( u[ nb ], 0.0, 1.0 );
-    double d[ 2 ] = { m->centers[ 2 * nb ] - center[ 0 ], m->centers[ 2 * nb + 1 ] - center[ 1 ] };
-    ls_accumulate( 2, d, colorNb - colorEn, AtA, Atb );
+    double d[ 3 ] = { 0, 0, 0 };
+    for( int k = 0; k < D; ++k )
+      d[ k ] = m->centers[ D * nb + k ] - center[ k ];
+    ls_accumulate( D, d, colorNb - colorEn, AtA, Atb );
   }
   for( int s = m->face_offsets[ cell ]; s < m->face_offsets[ cell + 1 ]; ++s )
   {
     if( m->face_neighbor[ s ] >= 0 )
       continue;
-    double d[ 2 ] = { m->face_centers[ 2 * s ] - center[ 0 ], m->face_centers[ 2 * s + 1 ] - center[ 1 ] };
-    d[ 0 ] *= 2.0;
-    d[ 1 ] *= 2.0;
-    ls_accumulate( 2, d, 0.5 - colorEn, AtA, Atb );
+    double d[ 3 ] = { 0, 0, 0 };
+    for( int k = 0; k < D; ++k )
+    {
+      d[ k ] = m->face_centers[ D * s + k ] - center[ k ];
+      d[ k ] *= 2.0;
+    }
+    ls_accumulate( D, d, 0.5 - colorEn, AtA, Atb );
   }
 
   double normal[ 3 ] = { 0, 0, 0 };
-  solve_small( 2, AtA, Atb, normal );
-  if( norm2n( normal, 2 ) < VO_EPS )
+  solve_small( D, AtA, Atb, normal );
+  if( norm2n( normal, D ) < VO_EPS )
     return 0;
-  const double nrm = normn( normal, 2 );
-  normal[ 0 ] /= nrm;
-  normal[ 1 ] /= nrm;
+  const double nrm = normn( normal, D );
+  for( int k = 0; k < D; ++k )
+    normal[ k ] /= nrm;
   return vo_mesh_locate( m, cell, normal, colorEn, hs );
 }
 
 int vo_mesh_youngs ( const vo_mesh *m, const double *u, const uint8_t *flags, double *hs )
 {
-  memset( hs, 0, sizeof( double ) * 3 * (size_t) m->n_cells );   /* reconstructions.clear(), :65 */
+  const int D = mesh_dim( m );
+  memset( hs, 0, sizeof( double ) * ( D + 1 ) * (size_t) m->n_cells );   /* reconstructions.clear(), :65 */
   for( int64_t c = 0; c < m->n_cells; ++c )
-    if( is_mixed( flags[ c ] ) && mesh_youngs_local( m, u, c, hs + 3 * c ) )
+    if( is_mixed( flags[ c ] ) && mesh_youngs_local( m, u, c, hs + ( D + 1 ) * c ) )
       return 1;
   return 0;
 }
@@ -3196,6 +3214,7 @@ static double mesh_flux ( const double *c0, const double *c1, const double *v, c
 
 int vo_mesh_evolve ( const vo_mesh *m, const double *hs, const uint8_t *flags, const double *face_velocity, double dt, double *update, double *dt_est )
 {
+  const int D = mesh_dim( m );
   double dtEst = DBL_MAX;
   memset( update, 0, sizeof( double ) * (size_t) m->n_cells );   /* update.clear(), :62 */
   for( int64_t c = 0; c < m->n_cells; ++c )
@@ -3209,33 +3228,164 @@ int vo_mesh_evolve ( const vo_mesh *m, const double *hs, const uint8_t *flags, c
       const int64_t nb = m->face_neighbor[ s ];
       if( nb < 0 )
         continue;
-      const double *outerNormal = m->face_unit_normals + 2 * s;
-      const double *intNormal = m->face_int_normals + 2 * s;
-      double v[ 2 ] = { face_velocity[ 2 * s ], face_velocity[ 2 * s + 1 ] };
-      sumFluxes += m->face_volumes[ s ] * fabs( dotn( outerNormal, v, 2 ) );
-      v[ 0 ] *= dt;
-      v[ 1 ] *= dt;
+      const double *outerNormal = m->face_unit_normals + D * s;
+      const double *intNormal = m->face_int_normals + D * s;
+      double v[ 3 ] = { 0, 0, 0 };
+      for( int k = 0; k < D; ++k )
+        v[ k ] = face_velocity[ D * s + k ];
+      sumFluxes += m->face_volumes[ s ] * fabs( dotn( outerNormal, v, D ) );
+      for( int k = 0; k < D; ++k )
+        v[ k ] *= dt;
       double flux = 0.0;
-      if( dotn( v, outerNormal, 2 ) > 0 )
+      if( dotn( v, outerNormal, D ) > 0 )
       {
-        flux = mesh_flux( m->face_corners + 4 * s, m->face_corners + 4 * s + 2, v, hs + 3 * c );
+        if( D == 2 )
+          flux = mesh_flux( m->face_corners + 4 * s, m->face_corners + 4 * s + 2, v, hs + 3 * c );
+        else if( mesh_flux3( m->face_corners + 3 * (size_t) m->face_corner_offsets[ s ], m->face_corner_offsets[ s + 1 ] - m->face_corner_offsets[ s ],
+                             v, hs + 4 * c, &flux ) )
+          return 1;
         update[ c ] -= flux / volume;
         if( flags[ nb ] == 3 )
-          update[ nb ] -= ( ( dotn( v, intNormal, 2 ) ) - flux ) / m->volumes[ nb ];
+          update[ nb ] -= ( ( dotn( v, intNormal, D ) ) - flux ) / m->volumes[ nb ];
         if( flags[ nb ] == 0 )
           update[ nb ] += flux / m->volumes[ nb ];
         if( is_mixed( flags[ nb ] ) )
           update[ nb ] += flux / m->volumes[ nb ];
       }
       if( flags[ nb ] == 3 )
-        if( dotn( v, outerNormal, 2 ) < 0 )
-          update[ c ] -= ( dotn( v, intNormal, 2 ) ) / volume;
+        if( dotn( v, outerNormal, D ) < 0 )
+          update[ c ] -= ( dotn( v, intNormal, D ) ) / volume;
     }
     const double est = volume / sumFluxes;
     dtEst = ( est < dtEst ) ? est : dtEst;
   }
   *dt_est = dtEst;
   return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Unstructured 3D meshes (tetrahedra and hexahedra): the same operators with makePolyhedron( geometry ),
+ * 3d/polyhedron.hh:366-404 (simplex and cube tables), locateHalfSpace( Polyhedron ), geometry/algorithm.hh:119-236, and
+ * upwindPolygon3d for triangular and quadrilateral intersections, 3d/upwindpolygon.hh:24-74.
+ * Pinned against oracle/_ref/libvofrefmesh3.so.
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* makePolyhedron( simplex ), 3d/polyhedron.hh:374-385 */
+static const int tet_edges[ 12 ][ 2 ] = {
+  { 0, 1 }, { 1, 0 }, { 0, 2 }, { 2, 0 }, { 1, 2 }, { 2, 1 }, { 0, 3 }, { 3, 0 }, { 1, 3 }, { 3, 1 }, { 3, 2 }, { 2, 3 }
+};
+static const int tet_faces[ 4 ][ 3 ] = { { 2, 5, 1 }, { 0, 8, 7 }, { 6, 10, 3 }, { 4, 11, 9 } };
+
+/* upwindPolygon3d( triangle ), 3d/upwindpolygon.hh:47-57: a prism of 6 nodes, 18 directed edges, 3 + 2 faces */
+static const int prism_edges[ 18 ][ 2 ] = {
+  { 0, 3 }, { 1, 4 }, { 2, 5 }, { 0, 1 }, { 0, 2 }, { 1, 2 }, { 3, 4 }, { 3, 5 }, { 4, 5 },
+  { 3, 0 }, { 4, 1 }, { 5, 2 }, { 1, 0 }, { 2, 0 }, { 2, 1 }, { 4, 3 }, { 5, 3 }, { 5, 4 }
+};
+static const int prism_face_len[ 5 ] = { 4, 4, 4, 3, 3 };
+static const int prism_faces[ 5 ][ 4 ] = { { 9, 3, 1, 15 }, { 0, 7, 11, 13 }, { 5, 2, 17, 10 }, { 4, 14, 12, 0 }, { 6, 8, 16, 0 } };
+
+static void make_tet_topology ( vo_polyhedron *p )
+{
+  p->nn = 4;
+  p->ne = 12;
+  p->nf = 4;
+  for( int i = 0; i < 12; ++i )
+  {
+    p->e[ i ][ 0 ] = tet_edges[ i ][ 0 ];
+    p->e[ i ][ 1 ] = tet_edges[ i ][ 1 ];
+  }
+  for( int f = 0; f < 4; ++f )
+  {
+    p->fne[ f ] = 3;
+    for( int i = 0; i < 3; ++i )
+      p->fe[ f ][ i ] = tet_faces[ f ][ i ];
+  }
+}
+
+static void make_prism_topology ( vo_polyhedron *p )
+{
+  p->nn = 6;
+  p->ne = 18;
+  p->nf = 5;
+  for( int i = 0; i < 18; ++i )
+  {
+    p->e[ i ][ 0 ] = prism_edges[ i ][ 0 ];
+    p->e[ i ][ 1 ] = prism_edges[ i ][ 1 ];
+  }
+  for( int f = 0; f < 5; ++f )
+  {
+    p->fne[ f ] = prism_face_len[ f ];
+    for( int i = 0; i < prism_face_len[ f ]; ++i )
+      p->fe[ f ][ i ] = prism_faces[ f ][ i ];
+  }
+}
+
+static int mesh_cell_polyhedron ( const vo_mesh *m, int64_t cell, vo_polyhedron *p )
+{
+  const int b = m->corner_offsets[ cell ], n = m->corner_offsets[ cell + 1 ] - b;
+  if( n == 4 )
+    make_tet_topology( p );
+  else if( n == 8 )
+    make_cube_topology( p );
+  else
+    return 1;                                 /* DUNE_THROW( InvalidStateException, "Invalid GeometryType." ) */
+  for( int i = 0; i < n; ++i )
+    for( int k = 0; k < 3; ++k )
+      p->x[ i ][ k ] = m->corners[ 3 * ( b + i ) + k ];
+  return 0;
+}
+
+/* truncVolume( upwindPolygon3d( iGeometry, v ), hs ) for an intersection with nc = 3 or 4 corners c */
+static int mesh_flux3 ( const double *c, int nc, const double *v, const double *hs, double *flux )
+{
+  double a[ 3 ], b[ 3 ], cr[ 3 ];
+  for( int k = 0; k < 3; ++k )
+  {
+    a[ k ] = c[ 3 + k ] - c[ k ];
+    b[ k ] = c[ 6 + k ] - c[ k ];
+  }
+  cross3( a, b, cr );
+  vo_polyhedron up, cl;
+  if( nc == 3 )
+    make_prism_topology( &up );
+  else if( nc == 4 )
+    make_cube_topology( &up );
+  else
+    return 1;
+  const int shiftedFirst = dotn( cr, v, 3 ) < 0.0;
+  for( int i = 0; i < nc; ++i )
+    for( int k = 0; k < 3; ++k )
+    {
+      const double moved = c[ 3 * i + k ] - v[ k ];
+      up.x[ shiftedFirst ? i : i + nc ][ k ] = moved;
+      up.x[ shiftedFirst ? i + nc : i ][ k ] = c[ 3 * i + k ];
+    }
+  polyhedron_clip( &up, hs, &cl );
+  *flux = polyhedron_volume( &cl );
+  return 0;
+}
+
+static int mesh_dim ( const vo_mesh *m ) { return m->dim == 3 ? 3 : 2; }
+
+/* the two primitives above on explicit corner lists (entry points for the tests of the device functions) */
+int vo_locate_corners ( int nc, const double *corners, const double *normal, double fraction, double *out )
+{
+  vo_polyhedron p;
+  if( nc == 4 )
+    make_tet_topology( &p );
+  else if( nc == 8 )
+    make_cube_topology( &p );
+  else
+    return 1;
+  for( int i = 0; i < nc; ++i )
+    for( int k = 0; k < 3; ++k )
+      p.x[ i ][ k ] = corners[ 3 * i + k ];
+  return locate_3d( &p, normal, fraction, out );
+}
+
+int vo_flux_corners ( int nc, const double *corners, const double *v, const double *hs, double *out )
+{
+  return mesh_flux3( corners, nc, v, hs, out );
 }
 
 /* R3 on a mesh: ModifiedSwartzReconstruction::applyLocal for 2D, reconstruction/modifiedswartz.hh:102-153 */

@@ -53,24 +53,27 @@ int vo_interface ( int dim, const double *lo, const double *h, const double *hs,
 double vo_brent_cubic ( double A, double B, double C, double target, double a, double b, double tol );
 double vo_det_cospi ( double s );
 
-/* ---- unstructured 2D meshes (triangles and quadrilaterals) as flattened arrays: the layout of include/vofx.h's
- *      vofx_mesh_desc.  All geometry of the grid (centres, volumes, normals) is DATA supplied by the grid side. ---- */
+/* ---- unstructured meshes as flattened arrays: triangles and quadrilaterals (dim 2), tetrahedra and hexahedra (dim 3);
+ *      the layout of include/vofx.h's vofx_mesh_desc.  All geometry of the grid (centres, volumes, normals) is DATA
+ *      supplied by the grid side; D below is dim. ---- */
 typedef struct
 {
   int64_t n_cells;
   const int32_t *corner_offsets;     /* [n_cells+1] */
-  const double *corners;             /* [..][2] cell corners in DUNE corner order */
-  const double *centers;             /* [n_cells][2] */
+  const double *corners;             /* [..][D] cell corners in DUNE corner order */
+  const double *centers;             /* [n_cells][D] */
   const double *volumes;             /* [n_cells] */
   const int32_t *face_offsets;       /* [n_cells+1] intersections in iteration order */
   const int32_t *face_neighbor;      /* outside cell or -1 */
-  const double *face_corners;        /* [..][2][2] */
+  const double *face_corners;        /* [..][2][2]; dim 3: 3 or 4 corners of D doubles per face */
   const double *face_centers;        /* [..][2] */
   const double *face_unit_normals;   /* [..][2] centerUnitOuterNormal */
   const double *face_int_normals;    /* [..][2] integrationOuterNormal at the centre */
   const double *face_volumes;        /* [..] */
   const int32_t *stencil_offsets;    /* [n_cells+1] CSR vertex-neighbour stencil, */
   const int32_t *stencil;            /*             ascending cell index, self excluded */
+  int32_t dim;                       /* 0 or 2: two dimensions; 3: three */
+  const int32_t *face_corner_offsets;/* dim 3: [n_faces+1] positions (in corners) in face_corners; dim 2: unused (2 each) */
 } vo_mesh;
 
 int vo_mesh_flag ( const vo_mesh *m, const double *u, double eps, uint8_t *flags );
@@ -78,6 +81,9 @@ int vo_mesh_youngs ( const vo_mesh *m, const double *u, const uint8_t *flags, do
 int vo_mesh_swartz ( const vo_mesh *m, const double *u, const uint8_t *flags, double *hs, int max_iterations );   /* 2D, modifiedswartz.hh:70-153 */
 int vo_mesh_evolve ( const vo_mesh *m, const double *hs, const uint8_t *flags, const double *face_velocity, double dt, double *update, double *dt_est );
 int vo_mesh_locate ( const vo_mesh *m, int64_t cell, const double *normal, double fraction, double *out );
+/* 3D primitives on explicit corner lists: cell with 4 (tetrahedron) or 8 (hexahedron) corners; intersection with 3 or 4 */
+int vo_locate_corners ( int nc, const double *corners, const double *normal, double fraction, double *out );
+int vo_flux_corners ( int nc, const double *corners, const double *v, const double *hs, double *out );
 
 #ifdef __cplusplus
 }

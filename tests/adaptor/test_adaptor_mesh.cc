@@ -249,7 +249,7 @@ int main ()
   grid.faceVolumes = A.faceVolumes.data();
   GV gv( grid );
 
-  vo_mesh om;
+  vo_mesh om{};     // dim 0 = two dimensions
   om.n_cells = std::int64_t( N );
   om.corner_offsets = A.cornerOffsets.data();
   om.corners = A.corners.data();

@@ -13,6 +13,22 @@ using namespace vofx;
 extern "C"
 {
 
+  // unstructured 3D grids: cells / intersections given by their corners (topology policies of vofx_geom3d.cuh)
+  int hg_locate_corners ( int nc, const double *corners, const double *normal, double fraction, double *out )
+  {
+    for( int k = 0; k < 3; ++k )
+      out[ k ] = normal[ k ];
+    out[ 3 ] = locate_corners( corners, nc, normal, fraction );
+    return 0;
+  }
+
+  int hg_flux_corners ( int nc, const double *corners, const double *v, const double *hs, double *out )
+  {
+    const Hs3 H = { { hs[ 0 ], hs[ 1 ], hs[ 2 ] }, hs[ 3 ] };
+    *out = flux_corners( corners, nc, v, H );
+    return 0;
+  }
+
   int hg_locate ( int dim, const double *lo, const double *h, const double *normal, double fraction, double *out )
   {
     if( dim == 2 )

@@ -268,3 +268,56 @@ def test_cooperative_swartz_bit_exact(hg, lanes):
             assert same_bits(rec, hs[c]), (n, problem, c, rec, hs[c])
         print(n, problem, "cooperative Swartz cells checked:", len(cells))
         og.close()
+
+
+def test_unstructured_3d_primitives_bit_exact(hg):
+    """the topology policies of vofx_geom3d.cuh (topo::Tet = makePolyhedron( simplex ), topo::Prism = upwindPolygon3d of a
+    triangle, topo::Cube) compiled for the host, against the oracle's general polyhedra: locateHalfSpace on tetrahedra and
+    boxes, truncVolume of swept triangles and quadrilaterals; random, axis-aligned and degenerate inputs"""
+    L = O.lib()
+    rng = np.random.default_rng(11)
+    checked = 0
+    for it in range(3000):
+        nc = 4 if it % 2 == 0 else 8
+        if nc == 4:
+            x = rng.random((4, 3)) * rng.choice([1.0, 0.01])
+            if np.linalg.det(np.stack([x[1] - x[0], x[2] - x[0], x[3] - x[0]])) < 0:
+                x[[1, 2]] = x[[2, 1]]
+            if it % 10 == 0:
+                x[:3, 2] = x[0, 2]              # a face at constant z: the N = 3 "face" start of the sweep
+        else:
+            lo, h = rng.random(3), rng.random(3) * 0.1 + 0.01
+            x = np.array([[lo[d] + ((i >> d) & 1) * h[d] for d in range(3)] for i in range(8)])
+        x = np.ascontiguousarray(x)
+        n = rng.normal(size=3)
+        if it % 7 == 0:
+            n[rng.integers(0, 3)] = 0
+        if it % 11 == 0:
+            n[:] = 0
+            n[rng.integers(0, 3)] = rng.choice([-1.0, 1.0])
+        n /= np.linalg.norm(n)
+        f = rng.random()
+        if it % 13 == 0:
+            f = float(rng.choice([0.0, 1.0, 1e-7, 1 - 1e-7, 0.5]))
+        o1, o2 = np.zeros(4), np.zeros(4)
+        rc = L.vo_locate_corners(nc, _d(x), _d(n), C.c_double(f), _d(o1))
+        hg.hg_locate_corners(nc, _d(x), _d(n), C.c_double(f), _d(o2))
+        if rc == 0 and not (np.isnan(o1[3]) and np.isnan(o2[3])):
+            assert np.array_equal(o1.view(np.uint64), o2.view(np.uint64)), (nc, it, o1, o2)
+            checked += 1
+        hs = np.array([n[0], n[1], n[2], o1[3] if rc == 0 and np.isfinite(o1[3]) else 0.0])
+        for fnc in (3, 4):
+            if fnc == 3:
+                c = np.ascontiguousarray(rng.random((3, 3)) * 0.1 + x[0])
+            else:
+                a, b = rng.random(3) * 0.1, rng.random(3) * 0.1
+                c = np.ascontiguousarray(np.array([x[0], x[0] + a, x[0] + b, x[0] + a + b]))
+            v = rng.normal(size=3) * 0.02
+            if it % 9 == 0:
+                v[rng.integers(0, 3)] = 0
+            q1, q2 = C.c_double(0), C.c_double(0)
+            L.vo_flux_corners(fnc, _d(c), _d(v), _d(hs), C.byref(q1))
+            hg.hg_flux_corners(fnc, _d(c), _d(v), _d(hs), C.byref(q2))
+            assert same_bits(q1.value, q2.value), (fnc, it, q1.value, q2.value)
+            checked += 1
+    assert checked > 8000

@@ -36,6 +36,22 @@ def test_unstructured_adaptor_binary():
         assert r.returncode == 0 and "ADAPTOR MESH TEST PASSED" in r.stdout, r.stdout + r.stderr
 
 
+def test_unstructured_adaptor_3d_binary():
+    """include/dune/vofx/unstructured.hh on a 3D grid view of tetrahedra (makePolyhedron simplex table, upwindPolygon3d prisms)"""
+    exe = os.path.join(ROOT, "tests", "adaptor", "test_adaptor_mesh3")
+    assert os.path.exists(exe), "tests/adaptor/test_adaptor_mesh3 is missing: run __graft_entry__.build()"
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    print(r.stdout)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "ADAPTOR MESH3 TEST PASSED" in r.stdout
+    assert "FAIL" not in r.stdout
+    ref = exe + "_ref"
+    if os.path.exists(ref):   # built only where /root/reference was mounted; travels to the GPU box as a binary
+        r = subprocess.run([ref], capture_output=True, text=True, timeout=600)
+        print(r.stdout)
+        assert r.returncode == 0 and "ADAPTOR MESH3 TEST PASSED" in r.stdout, r.stdout + r.stderr
+
+
 def test_adaptor_reference_containers_binary():
     """the same driver with the reference's own ColorFunction / FlagSet / ReconstructionSet (built where /root/reference is mounted)"""
     ref = os.path.join(ROOT, "tests", "adaptor", "test_adaptor_ref")

@@ -1,5 +1,5 @@
-"""Unstructured 2D meshes on the GPU (vofx_mesh_*, include/vofx.h) against the golden vectors of the unmodified reference
-and against the oracle on larger seeded meshes.  Bit-exact: flags, half-spaces, updates, dtEst, the device-resident loop."""
+"""Unstructured meshes on the GPU (vofx_mesh_*, include/vofx.h; 2D triangles / quadrilaterals, 3D tetrahedra / hexahedra)
+against the golden vectors of the unmodified reference and against the oracle on larger seeded meshes.  Bit-exact: flags, half-spaces, updates, dtEst, the device-resident loop."""
 import numpy as np
 import pytest
 
@@ -115,3 +115,61 @@ def test_descriptor_validation():
     L = lib.load()
     h = C.c_void_p()
     assert L.vofx_mesh_create(None, -1, C.byref(h)) != 0
+
+
+# ---- 3D: tetrahedra and hexahedra --------------------------------------------------------------------------------------------
+
+KINDS3 = ["tet", "hex"]
+
+
+@pytest.mark.parametrize("kind", KINDS3)
+def test_operators_match_golden_3d(kind):
+    z = golden(f"mesh3d_{kind}.npz")
+    m = mesh.FlatMesh.from_npz(z)
+    D = mesh.MeshOperators(m)
+    flags = D.flag(z["u"], float(z["eps"]))
+    assert np.array_equal(flags, z["flags"])
+    hs = D.youngs(z["u"], z["flags"])
+    assert hs.shape == (m.n_cells, 4)
+    assert n_mismatch(hs, z["halfspaces"]) == 0
+    upd, est = D.evolve(z["halfspaces"], z["flags"], z["velocity"], float(z["dt"]))
+    assert n_mismatch(upd, z["update"]) == 0
+    assert est == float(z["dt_est"])
+
+
+@pytest.mark.parametrize("kind", KINDS3)
+def test_resident_loop_matches_golden_3d(kind):
+    z = golden(f"mesh3d_{kind}.npz")
+    m = mesh.FlatMesh.from_npz(z)
+    D = mesh.MeshOperators(m)
+    u, t, dt = D.run(z["u_run"], z["velocity"], float(z["eps"]), float(z["cfl"]), int(z["passes"]))
+    assert n_mismatch(u, z["u_end"]) == 0
+    assert t == float(z["time_end"]) and dt == float(z["dt_end"])
+    assert abs(((u - z["u_run"]) * m.volumes).sum()) < 1e-15
+
+
+@pytest.mark.parametrize("kind,n,seed", [("tet", 14, 41), ("hex", 28, 42)])
+def test_larger_meshes_match_oracle_3d(kind, n, seed):
+    v, cells = mesh.perturbed_cube(n, kind, seed)
+    m = mesh.flatten3(v, cells)
+    O, D = meshlib.OracleMesh(m), mesh.MeshOperators(m)
+    u = meshlib.sphere_fractions(m, center=(0.5, 0.55, 0.45), radius=0.28, samples=60, seed=seed)
+    vel = meshlib.rotation_velocity3(m)
+    a = meshlib.run(O, m, u, vel, 1e-6, 0.5, 12)
+    b = D.run(u, vel, 1e-6, 0.5, 12)
+    assert n_mismatch(a[0], b[0]) == 0 and a[1:] == b[1:]
+    assert abs(((b[0] - u) * m.volumes).sum()) < 1e-14
+
+
+def test_3d_mesh_descriptor_validation_and_swartz_scope():
+    from dune_vof_b200 import lib
+    v, cells = mesh.perturbed_cube(3, "tet", 1)
+    m = mesh.flatten3(v, cells)
+    bad = mesh.FlatMesh(**{k: getattr(m, k) for k in m.__dataclass_fields__})
+    bad.face_corner_offsets = None                       # a 3D mesh needs the corner counts of its intersections
+    with pytest.raises(lib.VofxError):
+        mesh.MeshOperators(bad)
+    D = mesh.MeshOperators(m)
+    u = np.full(m.n_cells, 0.5)
+    with pytest.raises(lib.VofxError):                   # the Swartz reconstruction on meshes is 2D only
+        D.swartz(u, D.flag(u, 1e-6))

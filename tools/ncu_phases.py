@@ -50,9 +50,11 @@ def main():
     rows = list(csv.reader(io.StringIO(out)))
     head = rows[1]
     iA, iE, iN, iS = head.index("Address"), head.index("Instructions Executed"), head.index("# Samples"), head.index("Source")
+    iT = head.index("Thread Instructions Executed")
     base = int(rows[2][iA], 16)
     ex, sm = collections.Counter(), collections.Counter()
     fp = collections.Counter()
+    th = collections.Counter()
     for r in rows[2:]:
         if len(r) <= iN:
             continue
@@ -66,6 +68,7 @@ def main():
             key = chain[-1]
         n = int(r[iE] or 0)
         ex[key] += n
+        th[key] += int(r[iT] or 0)
         sm[key] += int(r[iN] or 0)
         toks = r[iS].split()
         if toks and toks[0].startswith("@"):
@@ -74,14 +77,14 @@ def main():
             fp[key] += n
     tot, tots = sum(ex.values()), sum(sm.values())
     if ranges:
-        print(f"{'phase':16s} {'executed':>12s} {'%':>6s} {'fp64 %':>7s} {'samples':>8s} {'%':>6s}")
+        print(f"{'phase':16s} {'executed':>12s} {'%':>6s} {'fp64 %':>7s} {'samples':>8s} {'%':>6s} {'thr/inst':>8s}")
         rest_e = rest_s = 0
         used = set()
         for name, lo, hi in ranges:
             keys = [k for k in ex if k[0] == fname and lo <= k[1] <= hi]
             used.update(keys)
-            e, s, f = sum(ex[k] for k in keys), sum(sm[k] for k in keys), sum(fp[k] for k in keys)
-            print(f"{name:16s} {e:12d} {100*e/tot:6.2f} {100*f/max(e,1):7.1f} {s:8d} {100*s/max(tots,1):6.2f}")
+            e, s, f, t = sum(ex[k] for k in keys), sum(sm[k] for k in keys), sum(fp[k] for k in keys), sum(th[k] for k in keys)
+            print(f"{name:16s} {e:12d} {100*e/tot:6.2f} {100*f/max(e,1):7.1f} {s:8d} {100*s/max(tots,1):6.2f} {t/max(e,1):8.1f}")
         others = collections.Counter()
         for k in ex:
             if k not in used:
