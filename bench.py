@@ -552,9 +552,9 @@ def main():
     try:
         summary = json.load(open(os.path.join(ROOT, "profiles", "r2_ncu_summary.json")))
         for nm, key in (("k_youngs", "k_youngs_coop3"), ("k_flux", "k_flux_cell3")):
-            if nm in sub and key in summary and "fp64_pipe_pct" in summary[key]:
+            if nm in sub and key in summary and summary[key].get("fp64_pipe_active_pct") is not None:
                 sub[nm]["bound"] = "fp64 latency"
-                sub[nm]["fp64_pipe_frac"] = summary[key]["fp64_pipe_pct"] / 100.0
+                sub[nm]["fp64_pipe_frac"] = summary[key]["fp64_pipe_active_pct"] / 100.0
                 sub[nm]["fp64_pipe_source"] = "profiles/r2_ncu_summary.json (static: ncu --set full capture of this workload)"
     except Exception:
         pass

@@ -212,7 +212,8 @@ namespace vofx
         for( int d = 0; d < 3; ++d )
           x3[ k ][ d ] = S.x[ d ][ r ];
       }
-      const double inv = vdiv( 1.0, (double) len );
+      // 1.0 / nodeIds_.size(): a face of a clipped hexahedron has 3 .. 7 nodes; the constants are the correctly rounded quotients
+      const double inv = ( len == 4 ) ? 1.0 / 4 : ( ( len == 3 ) ? 1.0 / 3 : ( ( len == 5 ) ? 1.0 / 5 : ( ( len == 6 ) ? 1.0 / 6 : vdiv( 1.0, (double) len ) ) ) );
       for( int d = 0; d < 3; ++d )
         center[ d ] *= inv;
       outer_normal3( x3[ 0 ], x3[ 1 ], x3[ 2 ], fn );

@@ -53,6 +53,8 @@ def main():
     iT = head.index("Thread Instructions Executed")
     base = int(rows[2][iA], 16)
     ex, sm = collections.Counter(), collections.Counter()
+    stall_cols = [(i, h) for i, h in enumerate(head) if h.startswith("stall_") and "Not Issued" not in h]
+    stalls = collections.defaultdict(collections.Counter)
     fp = collections.Counter()
     th = collections.Counter()
     for r in rows[2:]:
@@ -69,6 +71,9 @@ def main():
         n = int(r[iE] or 0)
         ex[key] += n
         th[key] += int(r[iT] or 0)
+        for i, h in stall_cols:
+            if i < len(r) and r[i]:
+                stalls[key][h[6:]] += int(r[i] or 0)
         sm[key] += int(r[iN] or 0)
         toks = r[iS].split()
         if toks and toks[0].startswith("@"):
@@ -84,7 +89,11 @@ def main():
             keys = [k for k in ex if k[0] == fname and lo <= k[1] <= hi]
             used.update(keys)
             e, s, f, t = sum(ex[k] for k in keys), sum(sm[k] for k in keys), sum(fp[k] for k in keys), sum(th[k] for k in keys)
-            print(f"{name:16s} {e:12d} {100*e/tot:6.2f} {100*f/max(e,1):7.1f} {s:8d} {100*s/max(tots,1):6.2f} {t/max(e,1):8.1f}")
+            st = collections.Counter()
+            for k in keys:
+                st.update(stalls[k])
+            top = " ".join(f"{n}:{100*v/max(s,1):.0f}%" for n, v in st.most_common(3))
+            print(f"{name:16s} {e:12d} {100*e/tot:6.2f} {100*f/max(e,1):7.1f} {s:8d} {100*s/max(tots,1):6.2f} {t/max(e,1):8.1f}  {top}")
         others = collections.Counter()
         for k in ex:
             if k not in used:

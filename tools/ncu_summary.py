@@ -1,9 +1,11 @@
 """Summarise `ncu --set full` reports (one kernel launch each) into profiles/<tag>_ncu_summary.json and
 profiles/<tag>_ncu_<kernel>_details.txt.
 
-    python tools/ncu_summary.py gpurun_out/r1g_ r1
+    python tools/ncu_summary.py gpurun_out/r1g_ r1 [OUTDIR]
 
-reads gpurun_out/r1g_<kernel>.ncu-rep for every kernel found.  The numbers bench.py's roofline.traffic cites come from here.
+reads gpurun_out/r1g_<kernel>.ncu-rep for every kernel found and writes into OUTDIR (default profiles/; on the GPU box the
+directory under gpurun_out/ that travels back, so that the reports themselves - tens of MB - need not).  An existing
+summary in OUTDIR is extended.  The numbers bench.py's roofline.traffic cites come from here.
 """
 import csv
 import glob
@@ -38,7 +40,10 @@ def num(d, k):
 def main():
     prefix, tag = sys.argv[1], sys.argv[2]
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outdir = sys.argv[3] if len(sys.argv) > 3 else os.path.join(root, "profiles")
     summary = {}
+    if os.path.exists(os.path.join(outdir, f"{tag}_ncu_summary.json")):
+        summary = json.load(open(os.path.join(outdir, f"{tag}_ncu_summary.json")))
     for rep in sorted(glob.glob(prefix + "*.ncu-rep")):
         kernel = os.path.basename(rep)[len(os.path.basename(prefix)):-len(".ncu-rep")]
         d = raw(rep)
@@ -62,9 +67,9 @@ def main():
             "stall_cycles_per_issue": top,
         }
         details = subprocess.run(["ncu", "-i", rep, "--page", "details"], capture_output=True, text=True).stdout
-        with open(os.path.join(root, "profiles", f"{tag}_ncu_{kernel}_details.txt"), "w") as f:
+        with open(os.path.join(outdir, f"{tag}_ncu_{kernel}_details.txt"), "w") as f:
             f.write(details)
-    with open(os.path.join(root, "profiles", f"{tag}_ncu_summary.json"), "w") as f:
+    with open(os.path.join(outdir, f"{tag}_ncu_summary.json"), "w") as f:
         json.dump(summary, f, indent=1)
     print(json.dumps({k: {"us": v["duration_us"], "dram": v["dram_bytes_total"]} for k, v in summary.items()}))
 
