@@ -166,7 +166,11 @@ def cpu_reference_run(passes, warm, sizes=(96, CPU_SAMPLE_N)):
             "sample": f"{kind} timed at " + " and ".join(f"{smp['n']}^3" for smp in samples) + f" ({passes} loop passes after {warm} warm-up "
                       f"passes each, sphere in LeVeque field, Young's); per-phase fit seconds = a*cells + b*mixed evaluated at "
                       f"{N_SIDE}^3 cells / {target_mixed:.0f} mixed cells (the reference needs >= 624 B/cell: {N_SIDE}^3 does not fit a host)",
-            "host_cores_available": os.cpu_count(), "seconds": time.perf_counter() - t_begin,
+            "host_cores_available": os.cpu_count(),
+            "threads_note": "the reference's path is single-threaded (no OpenMP / TBB; its parallelism is one MPI rank per core, and MPI is not in "
+                            "this image): 1 core is what it can use here.  value x host cores would be the ceiling of an ideal MPI run",
+            "ideal_all_cores_ceiling": value * (os.cpu_count() or 1),
+            "seconds": time.perf_counter() - t_begin,
             "equivalent_seconds_per_step_on_bench_grid": step_seconds, "bench_grid_mixed_cells_assumed": target_mixed,
             "fit": fit, "samples": samples}
     return value, info
@@ -404,6 +408,26 @@ def main():
                "d2h_bytes_per_step": int(d2h.value), "steps": KE, "ms_per_step": 1e3 * wall / KE,
                "api": "vofx_step_host: pinned host colour function in (whole array H2D, dense flags), updated in place on the host from "
                       "the (cell, value) pairs of the cells the step changed (sparse D2H) + loop state"}
+        # the call example/vof.cc makes: Algorithm::operator()( uh, start, end ) (algorithm.hh:54-103) = the host colour function
+        # up once, the loop passes on the device-resident copy, the colour function back for the data writer.  Reported next to
+        # the per-step figure above (which copies the whole array every step, what an operator-by-operator driver pays).
+        try:
+            KA = 100
+            t0 = time.perf_counter()
+            vlib.check(L.vofx_color_upload(grid._ctx, C.c_void_p(host_u.data_ptr())))
+            vlib.check(L.vofx_step_begin(grid._ctx, C.c_double(state.time), C.c_double(state.dt)))
+            for _ in range(KA):
+                vlib.check(L.vofx_step_resident(grid._ctx, C.byref(p)))
+            vlib.check(L.vofx_color_download(grid._ctx, C.c_void_p(host_u.data_ptr()), None))
+            torch.cuda.synchronize()
+            wall_a = time.perf_counter() - t0
+            e2e["algorithm_call"] = {"value": total_cells * KA / wall_a, "unit": "cell-steps/s", "passes_per_call": KA,
+                                     "ms_per_step": 1e3 * wall_a / KA, "h2d_bytes_per_call": 8 * grid.cells, "d2h_bytes_per_call": 8 * grid.cells,
+                                     "api": "vofx_color_upload (pinned host colour function, whole array) + vofx_step_begin + 100 x vofx_step_resident "
+                                            "(eager launches, incremental flagging) + vofx_color_download, all inside the timed region: what "
+                                            "Dune::VoFx::Algorithm::operator() does between two writes of the data writer"}
+        except Exception as exc:
+            e2e["algorithm_call"] = {"error": repr(exc)}
         drop(slab)
     else:
         # every rank: H2D of its owned slab from pinned host memory, one loop pass on a caller-owned device tensor (NCCL halo
