@@ -46,6 +46,8 @@ extern "C" {
  *   VOFX_FLUX_BLOCKS_PER_SM, VOFX_UPDATE_BLOCKS_PER_SM = n   grids of the 3D flux / update kernels (default 8)
  *   VOFX_SWZ_BLOCKS_PER_SM, VOFX_SWZ_OTHER_BLOCKS_PER_SM = n   grids of the batched Swartz kernels (default 80 / 48)
  *   VOFX_NO_COST_ORDER  = 1   process the band in list order instead of last step's expensive cells first
+ *   VOFX_BAND_PARTS     = 1 .. 4   chains ( plane-constant solve -> root search -> fluxes ) a 3D Young's / height-function pass runs
+ *                                  on as many streams (default 2; joined before the update)
  *   VOFX_PDL            = 1   launch the kernels of a pass with programmatic dependent launch (measured slower: off by default)
  *   VOFX_NO_GRAPH       = 1   vofx_mesh_run issues its kernels one by one instead of replaying a CUDA graph
  * None of them changes a result. */
