@@ -46,11 +46,14 @@ namespace vofx
     if( !hs_valid( hs ) )
       return;
     const int n = p.n;
+    // the level set of a vertex enters two edges: evaluated once (the reference evaluates it per edge, same value)
+    double first = 0.0, l0 = 0.0;
     for( int i = 0; i < n; ++i )
     {
       const int j = ( i + 1 == n ) ? 0 : i + 1;
-      const double l0 = level_set( hs, p.x[ i ], p.y[ i ] );
-      const double l1 = level_set( hs, p.x[ j ], p.y[ j ] );
+      if( i == 0 )
+        first = l0 = level_set( hs, p.x[ 0 ], p.y[ 0 ] );
+      const double l1 = ( j == 0 ) ? first : level_set( hs, p.x[ j ], p.y[ j ] );
       if( l0 > 0.0 )
       {
         out.x[ out.n ] = p.x[ i ];
@@ -59,8 +62,8 @@ namespace vofx
       }
       if( ( l0 > 0.0 ) != ( l1 > 0.0 ) )
       {
-        const double a = -l1 / ( l0 - l1 );
-        const double b = l0 / ( l0 - l1 );
+        double a = -l1, b = l0;
+        vdiv2( a, b, l0 - l1 );          // -l1 / ( l0 - l1 ), l0 / ( l0 - l1 ): one reciprocal, the IEEE quotients
         double cx = 0.0, cy = 0.0;
         cx += a * p.x[ i ]; cx += b * p.x[ j ];
         cy += a * p.y[ i ]; cy += b * p.y[ j ];
@@ -68,6 +71,7 @@ namespace vofx
         out.y[ out.n ] = cy;
         out.n++;
       }
+      l0 = l1;
     }
   }
 
@@ -76,7 +80,15 @@ namespace vofx
   {
     Poly2 c;
     poly_clip( p, hs, c );
-    return poly_volume( c ) / poly_volume( p );
+    return vdiv( poly_volume( c ), poly_volume( p ) );
+  }
+
+  // the same with the volume of p already known (the plane-constant solve evaluates it for ~15 planes through one cell)
+  VOFX_HD inline double volume_fraction ( const Poly2 &p, double volumeOfP, const Hs2 &hs )
+  {
+    Poly2 c;
+    poly_clip( p, hs, c );
+    return vdiv( poly_volume( c ), volumeOfP );
   }
 
   // makePolygon of a quadrilateral cell, 2d/polygon.hh:230-241: corners 0,1,3,2; upper corner = lower + h
@@ -93,11 +105,11 @@ namespace vofx
   struct VfResidual2
   {
     const Poly2 *p;
-    double nx, ny, fraction;
+    double nx, ny, fraction, volume;
     VOFX_HD double operator() ( double dist ) const
     {
       const Hs2 hs = { nx, ny, dist };
-      return volume_fraction( *p, hs ) - fraction;
+      return volume_fraction( *p, volume, hs ) - fraction;
     }
   };
 
@@ -107,11 +119,12 @@ namespace vofx
   {
     double pMin = 0.0, pMax = 0.0;
     double volMin = -DBL_MAX, volMax = DBL_MAX;
+    const double cellVolume = poly_volume( polygon );
     for( int i = 0; i < polygon.n; ++i )
     {
       const double dist = -( dot2( nx, ny, polygon.x[ i ], polygon.y[ i ] ) );
       const Hs2 hs = { nx, ny, dist };
-      const double volume = volume_fraction( polygon, hs );
+      const double volume = volume_fraction( polygon, cellVolume, hs );
       if( ( volume <= volMax ) && ( volume >= fraction ) )
       {
         pMax = dist;
@@ -129,7 +142,7 @@ namespace vofx
       return pMax;
     if( volMin == volMax )
       return pMin;
-    const VfResidual2 f = { &polygon, nx, ny, fraction };
+    const VfResidual2 f = { &polygon, nx, ny, fraction, cellVolume };
     return brent( f, pMin, pMax, 1e-12 );
   }
 

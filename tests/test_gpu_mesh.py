@@ -173,3 +173,28 @@ def test_3d_mesh_descriptor_validation_and_swartz_scope():
     u = np.full(m.n_cells, 0.5)
     with pytest.raises(lib.VofxError):                   # the Swartz reconstruction on meshes is 2D only
         D.swartz(u, D.flag(u, 1e-6))
+
+
+@pytest.mark.parametrize("kind", KINDS3)
+def test_edge_cases_3d(kind):
+    """uniform, full, empty and NaN colour functions, zero velocity, a colour function slightly outside [0, 1]"""
+    v, cells = mesh.perturbed_cube(5, kind, 7)
+    m = mesh.flatten3(v, cells)
+    O, D = meshlib.OracleMesh(m), mesh.MeshOperators(m)
+    vel = meshlib.rotation_velocity3(m)
+    rng = np.random.default_rng(3)
+    over = np.clip(meshlib.sphere_fractions(m, samples=40) + (rng.random(m.n_cells) - 0.5) * 4e-3, -2e-3, 1.002)
+    for u in (np.zeros(m.n_cells), np.ones(m.n_cells), np.full(m.n_cells, 0.5), np.full(m.n_cells, np.nan), over):
+        fo, fd = O.flag(u, 1e-6), D.flag(u, 1e-6)
+        assert np.array_equal(fo, fd)
+        ho, hd = O.youngs(u, fo), D.youngs(u, fd)
+        assert n_mismatch(ho, hd) == 0
+        uo, eo = O.evolve(ho, fo, vel, 0.02)
+        ud, ed = D.evolve(hd, fd, vel, 0.02)
+        assert n_mismatch(uo, ud) == 0 and eo == ed
+    u = meshlib.sphere_fractions(m, samples=40)
+    f = O.flag(u, 1e-6)
+    h = O.youngs(u, f)
+    uo, eo = O.evolve(h, f, np.zeros_like(vel), 0.02)
+    ud, ed = D.evolve(h, f, np.zeros_like(vel), 0.02)
+    assert n_mismatch(uo, ud) == 0 and eo == ed == np.finfo(np.float64).max
