@@ -428,6 +428,25 @@ def main():
                                             "Dune::VoFx::Algorithm::operator() does between two writes of the data writer"}
         except Exception as exc:
             e2e["algorithm_call"] = {"error": repr(exc)}
+        # a driver that keeps the colour function on the host and declares what it changed there between two passes
+        # (nothing, in a plain time loop): vofx_step_host_sparse uploads only declared cells and writes the changed cells back
+        try:
+            vlib.check(L.vofx_step_host_sparse(grid._ctx, C.byref(p), C.c_void_p(host_u.data_ptr()), None, None, 0))   # first call: whole array up
+            torch.cuda.synchronize()
+            KS = 50
+            t0 = time.perf_counter()
+            for _ in range(KS):
+                vlib.check(L.vofx_step_host_sparse(grid._ctx, C.byref(p), C.c_void_p(host_u.data_ptr()), None, None, 0))
+            torch.cuda.synchronize()
+            wall_s = time.perf_counter() - t0
+            vlib.check(L.vofx_host_transfer_bytes(grid._ctx, C.byref(h2d), C.byref(d2h)))
+            e2e["host_sparse"] = {"value": total_cells * KS / wall_s, "unit": "cell-steps/s", "steps": KS, "ms_per_step": 1e3 * wall_s / KS,
+                                  "h2d_bytes_per_step": int(h2d.value), "d2h_bytes_per_step": int(d2h.value),
+                                  "api": "vofx_step_host_sparse with an empty list of touched cells: the host colour function is current after "
+                                         "every pass (changed (cell, value) pairs device -> host), nothing goes host -> device because the "
+                                         "caller declares that it changed nothing"}
+        except Exception as exc:
+            e2e["host_sparse"] = {"error": repr(exc)}
         drop(slab)
     else:
         # every rank: H2D of its owned slab from pinned host memory, one loop pass on a caller-owned device tensor (NCCL halo

@@ -113,6 +113,7 @@ namespace vofx
     void finalize ( cudaStream_t s, StepState *state, double cfl ) { pdl( k_finalize, 1, 1, s, state, cfl ); }
     void reset_counters ( cudaStream_t s, StepState *state ) { k_reset_counters<<< 1, 1, 0, s >>>( state ); }
     void axpy ( int blocks, cudaStream_t s, long long n, double *u, double a, const double *x ) { k_axpy<<< blocks, 256, 0, s >>>( n, u, a, x ); }
+    void scatter_values ( int blocks, cudaStream_t s, long long n, const int *idx, const double *val, double *u ) { k_scatter_values<<< blocks, 256, 0, s >>>( n, idx, val, u ); }
     void init ( int dim, int blocks, cudaStream_t s, Grid g, Indicator I, double *u )
     {
       if( dim == 2 )
@@ -160,6 +161,7 @@ namespace vofx
       preload_one( k_comm_flux_done );
       preload_one( k_halo_push );
       preload_one( k_axpy );
+      preload_one( k_scatter_values );
       preload_one( k_init< 2 > );
       preload_one( k_init< 3 > );
     }

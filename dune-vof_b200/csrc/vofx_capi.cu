@@ -83,6 +83,10 @@ struct vofx_ctx
   int changedCapacity = 0;
   bool trackChanges = false;
   long long lastH2D = 0, lastD2H = 0;   // bytes moved by the last vofx_step_host call
+  const double *hostMirrorOf = nullptr; // host array whose current content the device mirror dU holds (vofx_step_host_sparse)
+  int *touchedIdx = nullptr;            // cells the caller changed on the host since the last call, and their values
+  double *touchedVal = nullptr;
+  size_t touchedCap = 0, touchedValCap = 0;
   // incremental flagging (vofx_set_incremental_flagging): one mark per aligned 32-cell row segment, and the arrays the
   // last finished pass ran on (the flags / band list are only reusable for exactly those)
   unsigned char *marks = nullptr;
@@ -404,6 +408,8 @@ namespace
   }
 
   int readState ( vofx_ctx *ctx, StepState &s );
+  static const int32_t kFullUploadCell = 0;
+  static const int32_t *const kFullUpload = &kFullUploadCell;     // sentinel of stepHostImpl: upload the whole array
 
   int launchReconstruct ( vofx_ctx *ctx, int kind, const double *u, const unsigned char *flags, double *hs, int maxIterations )
   {
@@ -900,6 +906,8 @@ extern "C"
     cudaFree( ctx->clipTable );
     cudaFree( ctx->sweepTable );
     cudaFree( ctx->serialCells );
+    cudaFree( ctx->touchedIdx );
+    cudaFree( ctx->touchedVal );
     cudaFree( ctx->rootTasks );
     cudaFree( ctx->diagScratch );
     cudaFree( ctx->costClass );
@@ -1624,6 +1632,7 @@ extern "C"
       return fail( VOFX_ERR_ARGUMENT, "null argument" );
     const size_t N = (size_t) ctx->grid.cells;
     int rc = ensureMirrors( ctx );
+    ctx->hostMirrorOf = nullptr;
     rc = rc ? rc : stageIn( ctx, ctx->dU, u, N * sizeof( double ) );
     rc = rc ? rc : vofx_flag( ctx, ctx->dU, eps, ctx->dFlags );
     return rc ? rc : stageOut( ctx, flags, ctx->dFlags, N );
@@ -1635,6 +1644,7 @@ extern "C"
       return fail( VOFX_ERR_ARGUMENT, "null argument" );
     const size_t N = (size_t) ctx->grid.cells;
     int rc = ensureMirrors( ctx );
+    ctx->hostMirrorOf = nullptr;
     rc = rc ? rc : stageIn( ctx, ctx->dU, u, N * sizeof( double ) );
     rc = rc ? rc : stageIn( ctx, ctx->dFlags, flags, N );
     rc = rc ? rc : vofx_reconstruct( ctx, kind, ctx->dU, ctx->dFlags, ctx->dHs, max_iterations );
@@ -1662,6 +1672,7 @@ extern "C"
     int rc = ensureMirrors( ctx );
     rc = rc ? rc : ensureDevice( ctx->dKappa, N );
     rc = rc ? rc : ensureDevice( ctx->dValid, N );
+    ctx->hostMirrorOf = nullptr;
     rc = rc ? rc : stageIn( ctx, ctx->dU, u, N * sizeof( double ) );
     rc = rc ? rc : stageIn( ctx, ctx->dHs, halfspaces, N * ( ctx->desc.dim + 1 ) * sizeof( double ) );
     rc = rc ? rc : stageIn( ctx, ctx->dFlags, flags, N );
@@ -1685,11 +1696,15 @@ extern "C"
     return rc ? rc : stageOut( ctx, kappa, ctx->dKappa, N * sizeof( double ) );
   }
 
-  int vofx_step_host ( vofx_ctx *ctx, const vofx_step_params *p, double *u, uint8_t *flags )
+  // touched == nullptr: the whole host colour function goes host -> device.  Otherwise the device mirror of the previous
+  // vofx_step_host* call on this array is current except for the nTouched cells the caller lists (it changed them on the
+  // host since that call): only those values are uploaded, and flags are maintained incrementally
+  static int stepHostImpl ( vofx_ctx *ctx, const vofx_step_params *p, double *u, uint8_t *flags, const int32_t *touched, int64_t nTouched )
   {
-    if( !ctx || !p || !u )
+    if( !ctx || !p || !u || ( nTouched > 0 && !touched ) || nTouched < 0 )
       return fail( VOFX_ERR_ARGUMENT, "null argument" );
     const size_t N = (size_t) ctx->grid.cells;
+    const bool sparse = touched != kFullUpload && ctx->hostMirrorOf == u;     // else: first call on this array, or the mirror was used otherwise
     int rc = ensureMirrors( ctx );
     if( !rc && p->with_curvature )
       rc = ensureDevice( ctx->dKappa, N );
@@ -1704,14 +1719,57 @@ extern "C"
     }
     if( rc )
       return rc;
-    // u may be caller-pinned memory: copy directly, no staging copy
-    VOFX_CUDA( cudaMemcpyAsync( ctx->dU, u, N * sizeof( double ), cudaMemcpyHostToDevice, ctx->stream ) );
-    ctx->lastH2D = (long long) ( N * sizeof( double ) );
+    if( !sparse )
+    {
+      // u may be caller-pinned memory: copy directly, no staging copy
+      VOFX_CUDA( cudaMemcpyAsync( ctx->dU, u, N * sizeof( double ), cudaMemcpyHostToDevice, ctx->stream ) );
+      ctx->lastH2D = (long long) ( N * sizeof( double ) );
+      ctx->primedU = nullptr;       // the caller's colour function was copied in again: dense flags
+      ctx->primedFlags = nullptr;
+    }
+    else
+    {
+      ctx->lastH2D = 0;
+      if( nTouched > 0 )
+      {
+        // ( index, value ) pairs through the pinned staging buffer, scattered by a kernel; a cell the caller changed may
+        // change flags anywhere near it: the next pass flags densely (incremental flagging only covers the band's own writes)
+        const size_t bytes = (size_t) nTouched * ( sizeof( int ) + sizeof( double ) ) + 16;
+        rc = ensurePinned( ctx, bytes );
+        rc = rc ? rc : growDevice( ctx->touchedIdx, ctx->touchedCap, (size_t) nTouched );
+        rc = rc ? rc : growDevice( ctx->touchedVal, ctx->touchedValCap, (size_t) nTouched );
+        if( rc )
+          return rc;
+        VOFX_CUDA( cudaStreamSynchronize( ctx->stream ) );     // the staging buffer may still feed the previous call's copies
+        double *hostVal = static_cast< double * >( ctx->pinned );
+        int *hostIdx = reinterpret_cast< int * >( hostVal + nTouched );
+        for( int64_t i = 0; i < nTouched; ++i )
+        {
+          if( touched[ i ] < 0 || (size_t) touched[ i ] >= N )
+            return fail( VOFX_ERR_ARGUMENT, "vofx_step_host_sparse: touched cell out of range" );
+          hostIdx[ i ] = touched[ i ];
+          hostVal[ i ] = u[ touched[ i ] ];
+        }
+        VOFX_CUDA( cudaMemcpyAsync( ctx->touchedVal, hostVal, (size_t) nTouched * sizeof( double ), cudaMemcpyHostToDevice, ctx->stream ) );
+        VOFX_CUDA( cudaMemcpyAsync( ctx->touchedIdx, hostIdx, (size_t) nTouched * sizeof( int ), cudaMemcpyHostToDevice, ctx->stream ) );
+        launch::scatter_values( gridBlocks( ctx, nTouched, 256, 8 ), ctx->stream, nTouched, ctx->touchedIdx, ctx->touchedVal, ctx->dU );
+        ctx->launches++;
+        VOFX_CUDA( cudaGetLastError() );
+        ctx->lastH2D = (long long) ( nTouched * ( sizeof( int ) + sizeof( double ) ) );
+        ctx->primedU = nullptr;
+        ctx->primedFlags = nullptr;
+      }
+      else if( !ctx->incremental )
+      {
+        rc = vofx_set_incremental_flagging( ctx, 1 );       // nothing but the passes changes the mirror: re-flag the band's neighbourhood only
+        if( rc )
+          return rc;
+      }
+    }
     ctx->lastD2H = (long long) sizeof( StepState ) + ( flags ? (long long) N : 0 );
     const bool tracking = ctx->trackChanges;
     ctx->trackChanges = true;
-    ctx->primedU = nullptr;       // the caller's colour function was copied in again: dense flags
-    ctx->primedFlags = nullptr;
+    ctx->hostMirrorOf = nullptr;  // until this call has brought the host array up to date
     rc = vofx_step( ctx, p, ctx->dU, ctx->dFlags, ctx->dHs, ctx->dKappa );
     ctx->trackChanges = tracking;
     if( rc )
@@ -1728,8 +1786,10 @@ extern "C"
       VOFX_CUDA( cudaMemcpyAsync( u, ctx->dU, N * sizeof( double ), cudaMemcpyDeviceToHost, ctx->stream ) );
       VOFX_CUDA( cudaStreamSynchronize( ctx->stream ) );
       ctx->lastD2H += (long long) ( N * sizeof( double ) );
+      ctx->hostMirrorOf = u;
       return VOFX_OK;
     }
+    ctx->hostMirrorOf = u;
     if( n == 0 )
       return VOFX_OK;
     ctx->lastD2H += (long long) ( n * ( sizeof( int ) + sizeof( double ) ) );
@@ -1748,6 +1808,17 @@ extern "C"
     for( size_t i = 0; i < n; ++i )
       u[ hostIdx[ i ] ] = hostVal[ i ];
     return VOFX_OK;
+  }
+
+  int vofx_step_host ( vofx_ctx *ctx, const vofx_step_params *p, double *u, uint8_t *flags )
+  {
+    return stepHostImpl( ctx, p, u, flags, kFullUpload, 0 );
+  }
+
+  int vofx_step_host_sparse ( vofx_ctx *ctx, const vofx_step_params *p, double *u, uint8_t *flags, const int32_t *touched, int64_t n_touched )
+  {
+    static const int32_t none = 0;
+    return stepHostImpl( ctx, p, u, flags, ( n_touched == 0 && !touched ) ? &none : touched, n_touched );
   }
 
   // Sparse write-back for drivers that run the pass themselves (slab decomposition): vofx_track_changes( 1 ) makes every
@@ -1825,6 +1896,7 @@ extern "C"
     int rc = ensureMirrors( ctx );
     if( rc )
       return rc;
+    ctx->hostMirrorOf = nullptr;
     VOFX_CUDA( cudaMemcpyAsync( ctx->dU, u, (size_t) ctx->grid.cells * sizeof( double ), cudaMemcpyHostToDevice, ctx->stream ) );
     VOFX_CUDA( cudaStreamSynchronize( ctx->stream ) );
     ctx->primedU = nullptr;
@@ -1911,6 +1983,7 @@ extern "C"
     std::fclose( f );
     if( !ok || tooLong )
       return fail( VOFX_ERR_ARGUMENT, std::string( path ) + " does not hold a time and one double per owned cell of this context" );
+    ctx->hostMirrorOf = nullptr;
     VOFX_CUDA( cudaMemcpyAsync( ctx->dU + first, ctx->pinned, n * sizeof( double ), cudaMemcpyHostToDevice, ctx->stream ) );
     VOFX_CUDA( cudaStreamSynchronize( ctx->stream ) );
     ctx->primedU = nullptr;       // new colour values: the next pass flags densely
@@ -1928,6 +2001,7 @@ extern "C"
     // the mirror is only written by the loop passes and by vofx_color_upload: flags are maintained incrementally
     if( !rc && !ctx->incremental )
       rc = vofx_set_incremental_flagging( ctx, 1 );
+    ctx->hostMirrorOf = nullptr;
     return rc ? rc : vofx_step( ctx, p, ctx->dU, ctx->dFlags, ctx->dHs, ctx->dKappa );
   }
 
@@ -2139,6 +2213,7 @@ extern "C"
   {
     if( !ctx || ensureMirrors( ctx ) )
       return nullptr;
+    ctx->hostMirrorOf = nullptr;     // the caller may write through the pointer
     return ctx->dU;
   }
 
@@ -2187,6 +2262,7 @@ extern "C"
       rc = vofx_set_incremental_flagging( ctx, 1 );
     if( rc )
       return rc;
+    ctx->hostMirrorOf = nullptr;
     double *u = ctx->dU;
     unsigned char *flags = ctx->dFlags;
     if( phase == 0 )

@@ -2530,6 +2530,13 @@ namespace vofx
       u[ i ] += a * x[ i ];
   }
 
+  // vofx_step_host_sparse: the cells the caller changed on the host since the previous call, written into the device mirror
+  static __global__ void __launch_bounds__( 256 ) k_scatter_values ( long long n, const int *__restrict__ idx, const double *__restrict__ val, double *__restrict__ u )
+  {
+    for( long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x; i < n; i += (long long) gridDim.x * blockDim.x )
+      u[ idx[ i ] ] = val[ i ];
+  }
+
 } // namespace vofx
 
 namespace vofx

@@ -68,6 +68,7 @@ namespace vofx
     void finalize ( cudaStream_t s, StepState *state, double cfl );
     void reset_counters ( cudaStream_t s, StepState *state );
     void axpy ( int blocks, cudaStream_t s, long long n, double *u, double a, const double *x );
+    void scatter_values ( int blocks, cudaStream_t s, long long n, const int *idx, const double *val, double *u );
     void init ( int dim, int blocks, cudaStream_t s, Grid g, Indicator I, double *u );
     void test_face_velocity ( cudaStream_t s, Grid g, const Velocity *velocity, double time, long long cell, int face, double *out );
 

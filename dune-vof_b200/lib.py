@@ -23,7 +23,7 @@ SYMBOLS = [
     "vofx_velocity_set_component", "vofx_velocity_set_factor", "vofx_velocity_set_faces", "vofx_velocity_builtin", "vofx_face_velocity",
     "vofx_flag", "vofx_reconstruct", "vofx_evolve", "vofx_axpy", "vofx_curvature", "vofx_curvature_swartz", "vofx_curvature_swartz_host", "vofx_step_begin", "vofx_set_incremental_flagging", "vofx_step",
     "vofx_step_state", "vofx_band_list_fetch", "vofx_step_counters", "vofx_step_local", "vofx_step_phase", "vofx_step_finish", "vofx_dt_est_device", "vofx_flag_host",
-    "vofx_reconstruct_host", "vofx_evolve_host", "vofx_curvature_host", "vofx_step_host", "vofx_host_transfer_bytes", "vofx_track_changes", "vofx_changed_fetch", "vofx_color_upload",
+    "vofx_reconstruct_host", "vofx_evolve_host", "vofx_curvature_host", "vofx_step_host", "vofx_step_host_sparse", "vofx_host_transfer_bytes", "vofx_track_changes", "vofx_changed_fetch", "vofx_color_upload",
     "vofx_step_resident", "vofx_color_download", "vofx_checkpoint_name", "vofx_checkpoint_write", "vofx_checkpoint_read", "vofx_comm_export", "vofx_comm_connect", "vofx_comm_connect_local", "vofx_comm_disconnect",
     "vofx_color_device", "vofx_flags_device", "vofx_halfspaces_device", "vofx_halo_push", "vofx_step_distributed", "vofx_step_distributed_phase", "vofx_band_list_fetch_in_flight",
     "vofx_velocity_set_band_faces", "vofx_diagnostics", "vofx_interface", "vofx_interface_host", "vofx_interface_fetch", "vofx_init", "vofx_init_circle", "vofx_l1error_circle", "vofx_l1error_circle_device",
@@ -122,6 +122,7 @@ def load():
     L.vofx_evolve_host.argtypes = [vp, dp, bp, C.c_double, C.c_double, dp, C.POINTER(C.c_double)]
     L.vofx_curvature_host.argtypes = [vp, dp, dp, bp, dp, bp]
     L.vofx_step_host.argtypes = [vp, C.POINTER(StepParams), dp, bp]
+    L.vofx_step_host_sparse.argtypes = [vp, C.POINTER(StepParams), dp, bp, vp, C.c_int64]
     L.vofx_track_changes.argtypes = [vp, C.c_int]
     L.vofx_changed_fetch.argtypes = [vp, dp, C.c_int64, C.POINTER(C.c_int64)]
     L.vofx_host_transfer_bytes.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]

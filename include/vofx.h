@@ -199,6 +199,14 @@ int vofx_curvature_swartz ( vofx_ctx *ctx, const double *halfspaces, const uint8
 int vofx_curvature_swartz_host ( vofx_ctx *ctx, const double *halfspaces, const uint8_t *flags, double *kappa );
 /* one full loop pass on a host colour function: H2D u, step, D2H u (and flags if non-NULL) */
 int vofx_step_host ( vofx_ctx *ctx, const vofx_step_params *params, double *u, uint8_t *flags );
+/* The same pass for a driver that keeps its colour function on the HOST and says what it did to it: `touched` lists the
+ * n_touched cells (storage indices) the caller has changed in `u` since the previous vofx_step_host / vofx_step_host_sparse
+ * call on the same array (none for a plain time loop; boundary or source cells otherwise).  The device mirror left by that
+ * call is then current elsewhere: only the listed values cross PCIe host -> device, and, as in vofx_step_host, only the
+ * (cell, new value) pairs of the cells the update changed come back.  The first call on an array, or a call after the
+ * mirror was used by another entry point, uploads the whole array.  With n_touched == 0 flags are maintained incrementally
+ * (vofx_set_incremental_flagging); otherwise the pass flags densely. */
+int vofx_step_host_sparse ( vofx_ctx *ctx, const vofx_step_params *params, double *u, uint8_t *flags, const int32_t *touched, int64_t n_touched );
 /* bytes the last vofx_step_host call moved across PCIe: the whole colour function host->device; device->host only the
  * (cell, new value) pairs of the cells the update touched (mixed cells and their face neighbours) plus the loop state */
 int vofx_host_transfer_bytes ( const vofx_ctx *ctx, int64_t *h2d_bytes, int64_t *d2h_bytes );

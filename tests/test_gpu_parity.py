@@ -530,3 +530,61 @@ def test_checkpoint_binarywriter_format(vofx, tmp_path):
     assert L.vofx_checkpoint_read(gb._ctx, str(tmp_path / "short.bin").encode(), C.byref(t2)) != 0
     ga.close()
     gb.close()
+
+
+def test_step_host_sparse_matches_full_upload(vofx):
+    """vofx_step_host_sparse: a host colour function whose changes the caller declares.  Plain loop (nothing touched): the host
+    array after every pass is bit-identical to vofx_step_host's, with no host -> device colour traffic after the first call;
+    then the caller overwrites a few cells on the host and lists them; then it uses another entry point in between (the mirror
+    is dropped and the whole array goes up again)."""
+    import numpy as np
+    from dune_vof_b200 import lib as vlib
+    L = vlib.load()
+    n = (48, 40, 56)
+    N = n[0] * n[1] * n[2]
+    p = vlib.StepParams(vofx.RECON_YOUNGS, 10, 1e-6, 0.5, 0)
+
+    def make():
+        g = vofx.CartesianGrid(n)
+        g.set_velocity_builtin(vofx.PROB_LEVEQUE)
+        u = g.init(vofx.PROB_LEVEQUE).cpu().numpy().copy()
+        vlib.check(L.vofx_step_begin(g._ctx, 0.0, 0.0))
+        return g, np.ascontiguousarray(u)
+
+    ga, ua = make()
+    gb, ub = make()
+    h2d, d2h = C.c_int64(0), C.c_int64(0)
+    rng = np.random.default_rng(9)
+    for k in range(14):
+        touched = None
+        if k in (5, 9):
+            # the caller edits its host array: a few cells near the interface and a few far away
+            cells = rng.integers(0, N, 40).astype(np.int32)
+            vals = rng.random(40)
+            ua[cells] = vals
+            ub[cells] = vals
+            touched = np.ascontiguousarray(cells)
+        if k == 11:
+            # another entry point uses the context's mirror in between
+            f = np.empty(N, dtype=np.uint8)
+            vlib.check(L.vofx_flag_host(gb._ctx, _p(ub), 1e-6, _p(f)))
+        vlib.check(L.vofx_step_host(ga._ctx, C.byref(p), _p(ua), None))
+        vlib.check(L.vofx_step_host_sparse(gb._ctx, C.byref(p), _p(ub), None, _p(touched) if touched is not None else None,
+                                           0 if touched is None else len(touched)))
+        vlib.check(L.vofx_host_transfer_bytes(gb._ctx, C.byref(h2d), C.byref(d2h)))
+        assert n_mismatch(ua, ub) == 0, k
+        if k == 0 or k == 11:
+            assert h2d.value == 8 * N                      # first call / dropped mirror: the whole array
+        elif touched is not None:
+            assert h2d.value == 12 * len(touched)
+        else:
+            assert h2d.value == 0
+        assert 0 < d2h.value < 8 * N
+    ta, tb = C.c_double(), C.c_double()
+    da, db = C.c_double(), C.c_double()
+    e, m = C.c_double(), C.c_int64()
+    vlib.check(L.vofx_step_state(ga._ctx, C.byref(ta), C.byref(da), C.byref(e), C.byref(m)))
+    vlib.check(L.vofx_step_state(gb._ctx, C.byref(tb), C.byref(db), C.byref(e), C.byref(m)))
+    assert ta.value == tb.value and da.value == db.value
+    ga.close()
+    gb.close()
