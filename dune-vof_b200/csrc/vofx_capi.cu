@@ -408,8 +408,6 @@ namespace
   }
 
   int readState ( vofx_ctx *ctx, StepState &s );
-  static const int32_t kFullUploadCell = 0;
-  static const int32_t *const kFullUpload = &kFullUploadCell;     // sentinel of stepHostImpl: upload the whole array
 
   int launchReconstruct ( vofx_ctx *ctx, int kind, const double *u, const unsigned char *flags, double *hs, int maxIterations )
   {
@@ -1696,15 +1694,15 @@ extern "C"
     return rc ? rc : stageOut( ctx, kappa, ctx->dKappa, N * sizeof( double ) );
   }
 
-  // touched == nullptr: the whole host colour function goes host -> device.  Otherwise the device mirror of the previous
+  // !declared: the whole host colour function goes host -> device.  Otherwise the device mirror of the previous
   // vofx_step_host* call on this array is current except for the nTouched cells the caller lists (it changed them on the
   // host since that call): only those values are uploaded, and flags are maintained incrementally
-  static int stepHostImpl ( vofx_ctx *ctx, const vofx_step_params *p, double *u, uint8_t *flags, const int32_t *touched, int64_t nTouched )
+  static int stepHostImpl ( vofx_ctx *ctx, const vofx_step_params *p, double *u, uint8_t *flags, bool declared, const int32_t *touched, int64_t nTouched )
   {
     if( !ctx || !p || !u || ( nTouched > 0 && !touched ) || nTouched < 0 )
       return fail( VOFX_ERR_ARGUMENT, "null argument" );
     const size_t N = (size_t) ctx->grid.cells;
-    const bool sparse = touched != kFullUpload && ctx->hostMirrorOf == u;     // else: first call on this array, or the mirror was used otherwise
+    const bool sparse = declared && ctx->hostMirrorOf == u;     // else: first call on this array, or the mirror was used otherwise
     int rc = ensureMirrors( ctx );
     if( !rc && p->with_curvature )
       rc = ensureDevice( ctx->dKappa, N );
@@ -1812,13 +1810,12 @@ extern "C"
 
   int vofx_step_host ( vofx_ctx *ctx, const vofx_step_params *p, double *u, uint8_t *flags )
   {
-    return stepHostImpl( ctx, p, u, flags, kFullUpload, 0 );
+    return stepHostImpl( ctx, p, u, flags, false, nullptr, 0 );
   }
 
   int vofx_step_host_sparse ( vofx_ctx *ctx, const vofx_step_params *p, double *u, uint8_t *flags, const int32_t *touched, int64_t n_touched )
   {
-    static const int32_t none = 0;
-    return stepHostImpl( ctx, p, u, flags, ( n_touched == 0 && !touched ) ? &none : touched, n_touched );
+    return stepHostImpl( ctx, p, u, flags, true, touched, n_touched );
   }
 
   // Sparse write-back for drivers that run the pass themselves (slab decomposition): vofx_track_changes( 1 ) makes every
