@@ -108,8 +108,11 @@ namespace vofx
       else
         k_curvature_average< 3 ><<< blocks, 128, 0, s >>>( g, flags, mixedList, slot, state, capacity, curv1, ok1, kappa, valid );
     }
-    void cost_order ( int blocks, cudaStream_t s, const int *mixedList, StepState *state, int capacity, const unsigned char *costClass, int *order )
-    { pdl( k_cost_order, blocks, 256, s, mixedList, state, capacity, costClass, order ); }
+    void cost_order ( int blocks, cudaStream_t s, const int *mixedList, StepState *state, int capacity, const unsigned char *costClass, int *order, int parts )
+    {
+      pdl( k_cost_hist, blocks, 256, s, mixedList, state, capacity, costClass, parts );
+      pdl( k_cost_order, blocks, 256, s, mixedList, state, capacity, costClass, order, parts );
+    }
     void finalize ( cudaStream_t s, StepState *state, double cfl ) { pdl( k_finalize, 1, 1, s, state, cfl ); }
     void reset_counters ( cudaStream_t s, StepState *state ) { k_reset_counters<<< 1, 1, 0, s >>>( state ); }
     void axpy ( int blocks, cudaStream_t s, long long n, double *u, double a, const double *x ) { k_axpy<<< blocks, 256, 0, s >>>( n, u, a, x ); }
@@ -153,6 +156,7 @@ namespace vofx
       preload_one( k_curvature_local< 3 > );
       preload_one( k_curvature_average< 2 > );
       preload_one( k_curvature_average< 3 > );
+      preload_one( k_cost_hist );
       preload_one( k_cost_order );
       preload_one( k_finalize );
       preload_one( k_reset_counters );

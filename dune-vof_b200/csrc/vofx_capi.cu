@@ -431,6 +431,7 @@ namespace
       if( ordered )
       {
         launch::cost_order( ctx->numSMs * 2, ctx->stream, ctx->mixedList, ctx->state, ctx->capacity, ctx->costClass, ctx->order );
+        ctx->launches++;       // k_cost_hist + k_cost_order
         int rco = checkLaunch( ctx, "k_cost_order" );
         if( rco )
           return rco;
@@ -564,7 +565,8 @@ namespace
     const bool ordered = ctx->costOrder && ctx->order && ctx->costClass;
     if( ordered )
     {
-      launch::cost_order( ctx->numSMs * 2, ctx->stream, ctx->mixedList, ctx->state, ctx->capacity, ctx->costClass, ctx->order );
+      launch::cost_order( ctx->numSMs * 2, ctx->stream, ctx->mixedList, ctx->state, ctx->capacity, ctx->costClass, ctx->order, parts );
+      ctx->launches++;         // k_cost_hist + k_cost_order
       int rc = checkLaunch( ctx, "k_cost_order" );
       if( rc )
         return rc;
@@ -584,7 +586,7 @@ namespace
       launch::locate_root3( ( ctx->numSMs * 8 + parts - 1 ) / parts, s, ctx->state, ctx->capacity, ctx->rootTasks, hs, bp );
       launch::locate_serial3( s, g, u, ctx->state, hs, ctx->serialCells, ctx->capacity, bp );
       launch::flux_cell3( ctx->fluxLanes, ( ctx->numSMs * ctx->fluxBlocksPerSM + parts - 1 ) / parts, s, g, ctx->velDev, ctx->velHost, hs, flags, ctx->mixedList, ctx->state,
-                          ctx->capacity, ctx->records, ctx->tasks, ctx->taskCapacity, ctx->clipTable, nullptr, nullptr, order, bp, 0 );
+                          ctx->capacity, ctx->records, ctx->tasks, ctx->taskCapacity, ctx->clipTable, nullptr, nullptr, nullptr, bp, 0 );
       ctx->launches += 4;
       VOFX_CUDA( cudaGetLastError() );
       VOFX_CUDA( cudaEventRecord( ctx->evBandJoin[ q ], s ) );

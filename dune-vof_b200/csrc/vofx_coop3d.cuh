@@ -850,9 +850,9 @@ namespace vofx
         }
       }
       const bool walking = ( C == nullptr );
-      // cost class for the scheduling of the next step: 2 the topology is walked on lane 0, 1 six or seven brackets, 0 otherwise
+      // cost class for the scheduling of the next step: 7 the topology is walked on lane 0, else the bracket the solve ends in
       if( cost )
-        *cost = walking ? 2 : ( nU >= 7 ? 1 : 0 );
+        *cost = walking ? 7 : ( nU >= 2 ? ( nU - 2 < 6 ? nU - 2 : 6 ) : 0 );
 #if defined( __CUDA_ARCH__ ) && defined( VOFX_COUNT_WALKS )
       if( G.lane == 0 )
       {
@@ -1005,8 +1005,8 @@ namespace vofx
         const double hk = dU[ k + 1 ] - dU[ k ];
         Cubic V = { A, Bc, Cc, 0.0 };
         const double Vd_k1 = Vd_k + V( hk );
-        if( cost && !walking && ( fabs( Vd_k1 - givenVolume ) < 1e-14 || Vd_k1 > givenVolume ) && k < 5 )
-          *cost = 0;
+        if( cost && !walking && ( fabs( Vd_k1 - givenVolume ) < 1e-14 || Vd_k1 > givenVolume ) )
+          *cost = k < 6 ? k : 6;
         if( fabs( Vd_k1 - givenVolume ) < 1e-14 )
         {
 #if defined( __CUDA_ARCH__ ) && defined( VOFX_COUNT_WALKS )

@@ -1018,9 +1018,16 @@ namespace vofx
     G.lane = lane;
     G.mask = ( ( L == 32 ) ? 0xffffffffu : ( ( 1u << L ) - 1u ) ) << ( ( threadIdx.x & 31 ) - lane );
     coop::LocateScratch &S = scratch[ group ];
-    for( int idx = ( blockIdx.x * GROUPS + group ) * bp.parts + bp.part; idx < count; idx += gridDim.x * GROUPS * bp.parts )
+    // part p owns the band-list entries p, p + parts, ...; in the order array they follow the entries of the parts before it,
+    // sorted by last step's cost class (k_cost_order): cells of one class share a warp
+    const int nMine = ( count - bp.part + bp.parts - 1 ) / bp.parts;
+    int orderBase = 0;
+    for( int q = 0; q < bp.part; ++q )
+      orderBase += ( count - q + bp.parts - 1 ) / bp.parts;
+    for( int mine = blockIdx.x * GROUPS + group; mine < nMine; mine += gridDim.x * GROUPS )
     {
-      const int c = mixedList[ order ? order[ idx ] : idx ];     // expensive cells first and together (k_cost_order)
+      const int idx = order ? order[ orderBase + mine ] : mine * bp.parts + bp.part;   // position in the band list
+      const int c = mixedList[ idx ];
       int ijk[ 3 ];
       cell_ijk( g, c, ijk );
       const double colorEn = u[ c ];
@@ -1949,9 +1956,9 @@ namespace vofx
 
     for( int pos = ( blockIdx.x * GROUPS + group ) * bp.parts + bp.part; pos < count; pos += gridDim.x * GROUPS * bp.parts )
     {
-      // a band part takes the cells its plane-constant kernel took (positions of the processing order); the records stay
-      // at the cells' positions in the band list
-      const int idx = order ? order[ pos ] : pos;
+      // a band part takes the band-list entries its plane-constant kernel took ( part, part + parts, ... ) in list order:
+      // neighbours in the list are neighbours in space with the same outflow faces, which keeps the warp's four cells in step
+      const int idx = pos;
       const int c = mixedList[ idx ];
       int ijk[ 3 ];
       cell_ijk( g, c, ijk );
@@ -2456,6 +2463,8 @@ namespace vofx
     state->rootCount = 0;
     state->slowFront = 0;
     state->normalBack = 0;
+    for( int c = 0; c < 32; ++c )
+      state->costHist[ c ] = state->costFill[ c ] = 0;
   }
 
   static __global__ void k_reset_counters ( StepState *state )
@@ -2470,55 +2479,89 @@ namespace vofx
     state->changedCount = 0;
     state->slowFront = 0;
     state->normalBack = 0;
+    for( int c = 0; c < 32; ++c )
+      state->costHist[ c ] = state->costFill[ c ] = 0;
     state->dtEst = DBL_MAX;
   }
 
-  // Processing order of the band for the plane-constant kernel: the cells that were expensive in the previous step (walk on
-  // lane 0 for tied node heights, or all brackets of a nearly full cell; costClass written by k_youngs_coop3) first and
-  // together - eight cells share a warp, and one straggler sets the pace of its warp.  A pure permutation of the band list:
-  // no result depends on it.
-  static __global__ void __launch_bounds__( 256 ) k_cost_order ( const int *__restrict__ mixedList, StepState *state, int capacity,
-                                                                  const unsigned char *__restrict__ costClass, int *__restrict__ order )
+  // Processing order of the band for the plane-constant kernel.  The kernel writes a cost class per cell (costClass: the
+  // bracket 0 .. 6 its plane-constant solve ended in, 7 if lane 0 walked the topology for tied node heights); the next step
+  // sorts the band list by that class, expensive first (a counting sort: k_cost_hist, then k_cost_order places the entries
+  // behind the prefix of the histogram).  Eight cells share a warp and leave the bracket loop one by one: with cells of one
+  // class per warp the lanes of finished cells no longer idle (the bracket phases ran at 13 .. 21 of 32 lanes).  Temporal
+  // coherence does the prediction; a pure permutation of the band list: no result depends on it.
+  // Band parts (BandPart): part p owns the list entries p, p + parts, ...; the order array holds part 0's entries first, each
+  // part's entries sorted by class.  bucket = part * 8 + class.
+  static __global__ void __launch_bounds__( 256 ) k_cost_hist ( const int *__restrict__ mixedList, StepState *state, int capacity,
+                                                                 const unsigned char *__restrict__ costClass, int parts )
   {
     pdl_prologue();
-    __shared__ int warpSlow[ 8 ], warpNormal[ 8 ], baseSlow, baseNormal;
+    __shared__ int hist[ 32 ];
+    if( threadIdx.x < 32 )
+      hist[ threadIdx.x ] = 0;
+    __syncthreads();
+    const int count = mixed_count( state, capacity );
+    for( int idx = blockIdx.x * 256 + threadIdx.x; idx < count; idx += gridDim.x * 256 )
+      atomicAdd( &hist[ ( idx % parts ) * 8 + ( costClass[ mixedList[ idx ] ] & 7 ) ], 1 );
+    __syncthreads();
+    if( threadIdx.x < 32 && hist[ threadIdx.x ] )
+      atomicAdd( &state->costHist[ threadIdx.x ], hist[ threadIdx.x ] );
+  }
+
+  static __global__ void __launch_bounds__( 256 ) k_cost_order ( const int *__restrict__ mixedList, StepState *state, int capacity,
+                                                                  const unsigned char *__restrict__ costClass, int *__restrict__ order, int parts )
+  {
+    pdl_prologue();
+    __shared__ int warpCount[ 32 ][ 8 ], tileBase[ 32 ], start[ 32 ];
     const int count = mixed_count( state, capacity );
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if( threadIdx.x == 0 )
+    {
+      // part by part; within a part class 7 first, class 0 last
+      int at = 0;
+      for( int p = 0; p < 4; ++p )
+        for( int c = 7; c >= 0; --c )
+        {
+          start[ p * 8 + c ] = at;
+          at += state->costHist[ p * 8 + c ];
+        }
+    }
+    __syncthreads();
+    const int nBuckets = parts * 8;
     const int rounded = ( count + 255 ) & ~255;
     for( int first = blockIdx.x * 256; first < rounded; first += gridDim.x * 256 )
     {
       const int idx = first + threadIdx.x;
       const bool valid = idx < count;
-      const bool slow = valid && costClass[ mixedList[ idx ] ] != 0;
-      const unsigned slowBallot = __ballot_sync( 0xffffffffu, slow );
-      const unsigned normalBallot = __ballot_sync( 0xffffffffu, valid && !slow );
-      if( lane == 0 )
-      {
-        warpSlow[ warp ] = __popc( slowBallot );
-        warpNormal[ warp ] = __popc( normalBallot );
-      }
+      const int bucket = valid ? ( idx % parts ) * 8 + ( costClass[ mixedList[ idx ] ] & 7 ) : 32 + warp;   // padding lanes: a bucket of their own
+      warpCount[ threadIdx.x >> 3 ][ threadIdx.x & 7 ] = 0;
       __syncthreads();
-      if( threadIdx.x == 0 )
+      // the lanes of a warp that share a bucket find each other in one instruction
+      const unsigned peers = __match_any_sync( 0xffffffffu, bucket );
+      const int below = __popc( peers & ( ( 1u << lane ) - 1u ) );
+      if( valid && below == 0 )
+        warpCount[ bucket ][ warp ] = __popc( peers );
+      __syncthreads();
+      if( threadIdx.x < nBuckets )
       {
-        // one pair of atomics per 256 entries; the warps' shares become exclusive prefixes
-        int nSlow = 0, nNormal = 0;
+        // one atomic per bucket and 256 entries; the warps' shares become exclusive prefixes
+        const int b = threadIdx.x;
+        int n = 0;
         for( int w = 0; w < 8; ++w )
         {
-          const int a = warpSlow[ w ], b = warpNormal[ w ];
-          warpSlow[ w ] = nSlow;
-          warpNormal[ w ] = nNormal;
-          nSlow += a;
-          nNormal += b;
+          const int a = warpCount[ b ][ w ];
+          warpCount[ b ][ w ] = n;
+          n += a;
         }
-        baseSlow = nSlow ? atomicAdd( &state->slowFront, nSlow ) : 0;
-        baseNormal = nNormal ? atomicAdd( &state->normalBack, nNormal ) : 0;
+        tileBase[ b ] = n ? atomicAdd( &state->costFill[ b ], n ) : 0;
       }
       __syncthreads();
-      const unsigned below = ( 1u << lane ) - 1u;
-      if( slow )
-        order[ baseSlow + warpSlow[ warp ] + __popc( slowBallot & below ) ] = idx;
-      else if( valid )
-        order[ count - 1 - ( baseNormal + warpNormal[ warp ] + __popc( normalBallot & below ) ) ] = idx;
+      if( valid )
+      {
+        const int pos = start[ bucket ] + tileBase[ bucket ] + warpCount[ bucket ][ warp ] + below;
+        if( pos < count )                // the histogram and the classes were read from the same arrays: always true
+          order[ pos ] = idx;
+      }
       __syncthreads();
     }
   }

@@ -96,7 +96,7 @@ namespace vofx
 
     // k_recon3d.cu, k_swartz3d.cu, k_flux3d.cu
     void youngs3 ( int blocks, cudaStream_t s, Grid g, const double *u, const int *mixedList, const StepState *state, int capacity, double *hs );
-    void cost_order ( int blocks, cudaStream_t s, const int *mixedList, StepState *state, int capacity, const unsigned char *costClass, int *order );
+    void cost_order ( int blocks, cudaStream_t s, const int *mixedList, StepState *state, int capacity, const unsigned char *costClass, int *order, int parts = 1 );
     void youngs_coop3 ( int lanes, int blocks, cudaStream_t s, Grid g, const double *u, const int *mixedList, StepState *state, int capacity, double *hs,
                         const void *sweepTable, int *serialCells, void *rootTasks, int heightFunction, const int *order, unsigned char *costClass, BandPart bp = BandPart() );
     void locate_root3 ( int blocks, cudaStream_t s, StepState *state, int capacity, const void *rootTasks, double *hs, BandPart bp = BandPart() );

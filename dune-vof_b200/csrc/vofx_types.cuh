@@ -31,6 +31,8 @@ namespace vofx
     int pad;
     int serialLocateMore[ 3 ];  // serialLocate of the band parts 1 .. kMaxBandParts - 1 (BandPart below; part 0 counts in serialLocate)
     int pad2;
+    int costHist[ 32 ];         // k_cost_hist: band cells per ( band part, cost class of the previous step: 0 .. 6 = bracket the solve ended in, 7 = walked )
+    int costFill[ 32 ];         // k_cost_order: entries of each bucket placed so far
   };
 
   // The band kernels of a pass (plane-constant solve, root search, fluxes) can run as `parts` independent chains on as many
