@@ -24,7 +24,7 @@ namespace vofx
     // all iterations of the batched Swartz reconstruction (4 kernels each) after the setup; `counter` is zeroed by the caller
     void swartz_batched3 ( int lanes, int sms, cudaStream_t s, Grid g, const double *u, const unsigned char *flags, const int *mixedList, StepState *state,
                            int capacity, double *hs, int maxIterations, const void *sweepTable, void *cells, void *tasks, int *counter,
-                           int cellCapacity, int taskCapacity )
+                           int cellCapacity, int taskCapacity, int *order, int *sort )
     {
       const coop::SweepTable *T = (const coop::SweepTable *) sweepTable;
       SwzCell *C = (SwzCell *) cells;
@@ -36,11 +36,22 @@ namespace vofx
       static const int otherBlocks = std::getenv( "VOFX_SWZ_OTHER_BLOCKS_PER_SM" ) ? std::atoi( std::getenv( "VOFX_SWZ_OTHER_BLOCKS_PER_SM" ) ) : 48;
       for( int it = 0; it < maxIterations; ++it )
       {
+        // the active tasks, sorted by the bracket of their last solve: order[ 0 .. sort[ 32 ] )
+        const int *nActive = counter;
+        const int *ord = nullptr;
+        if( order && sort )
+        {
+          cudaMemsetAsync( sort, 0, 64 * sizeof( int ), s );
+          k_swz_hist<<< sms * 2, 256, 0, s >>>( C, K, counter, sort );
+          k_swz_order<<< sms * 2, 256, 0, s >>>( C, K, counter, sort, order );
+          nActive = sort + 32;
+          ord = order;
+        }
         if( lanes == 8 )
-          k_swz_locate< 8 ><<< sms * 8, 128, 0, s >>>( g, u, C, K, counter, T );
+          k_swz_locate< 8 ><<< sms * 8, 128, 0, s >>>( g, u, C, K, nActive, T, ord );
         else
-          k_swz_locate< 4 ><<< sms * locateBlocks, 64, 0, s >>>( g, u, C, K, counter, T );
-        k_swz_centroid< 3 ><<< sms * otherBlocks, 64, 0, s >>>( g, u, C, K, counter );
+          k_swz_locate< 4 ><<< sms * locateBlocks, 64, 0, s >>>( g, u, C, K, nActive, T, ord );
+        k_swz_centroid< 3 ><<< sms * otherBlocks, 64, 0, s >>>( g, u, C, K, nActive, ord );
         if( lanes == 8 )
           k_swz_normal< 8 ><<< sms * 8, 64, 0, s >>>( g, u, C, K, state, capacity, T );
         else

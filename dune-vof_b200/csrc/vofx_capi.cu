@@ -68,6 +68,9 @@ struct vofx_ctx
   size_t swzCellCount = 0;          // cells the buffers hold
   size_t swzHint = 0;               // band length of the last pass the host has seen (readState)
   int *swzCounter = nullptr;
+  int *swzOrder = nullptr, *swzSort = nullptr;   // per iteration: active tasks sorted by class, and the sort's counters (64 ints)
+  size_t swzOrderCap = 0;
+  bool swzSortTasks = true;                      // VOFX_SWZ_NO_SORT=1 switches the per-iteration task sort off
   // interface extraction (vofx_interface): grow-only scratch
   int *ifBlockSums = nullptr, *ifCells = nullptr, *ifNverts = nullptr, *ifOffsets = nullptr;
   long long *ifTotal = nullptr;
@@ -492,6 +495,8 @@ namespace
               int rcs = growDevice( ctx->swzCells, ctx->swzCellCap, cellsWanted * launch::swz_cell_bytes() + 16 );
               rcs = rcs ? rcs : growDevice( ctx->swzTasks, ctx->swzTaskCap, cellsWanted * 27 * launch::swz_task_bytes() + 16 );
               rcs = rcs ? rcs : ensureDevice( ctx->swzCounter, (size_t) 1 );
+              rcs = rcs ? rcs : growDevice( ctx->swzOrder, ctx->swzOrderCap, cellsWanted * 27 + 16 );
+              rcs = rcs ? rcs : ensureDevice( ctx->swzSort, (size_t) 64 );
               if( rcs )
                 return rcs;
               ctx->swzCellCount = cellsWanted;
@@ -502,8 +507,9 @@ namespace
           VOFX_CUDA( cudaMemsetAsync( ctx->swzCounter, 0, sizeof( int ), ctx->stream ) );
           profBegin( ctx );
           launch::swartz_batched3( lanes, ctx->numSMs, ctx->stream, g, u, flags, ctx->mixedList, ctx->state, ctx->capacity, hs, maxIterations, ctx->sweepTable,
-                                   ctx->swzCells, ctx->swzTasks, ctx->swzCounter, (int) ctx->swzCellCount, (int) ( ctx->swzCellCount * 27 ) );
-          ctx->launches += 4 * maxIterations;
+                                   ctx->swzCells, ctx->swzTasks, ctx->swzCounter, (int) ctx->swzCellCount, (int) ( ctx->swzCellCount * 27 ),
+                                   ctx->swzSortTasks ? ctx->swzOrder : nullptr, ctx->swzSortTasks ? ctx->swzSort : nullptr );
+          ctx->launches += ( ctx->swzSortTasks ? 6 : 4 ) * maxIterations;
         }
       }
       rc = checkLaunch( ctx, "k_swartz" );
@@ -868,6 +874,8 @@ extern "C"
         ctx->fluxLanes = ( std::atoi( env ) == 4 ) ? 4 : 8;
       if( const char *env = std::getenv( "VOFX_BAND_PARTS" ) )
         ctx->bandParts = std::atoi( env ) < 1 ? 1 : ( std::atoi( env ) > kMaxBandParts ? kMaxBandParts : std::atoi( env ) );
+      if( std::getenv( "VOFX_SWZ_NO_SORT" ) )
+        ctx->swzSortTasks = false;
       if( std::getenv( "VOFX_NO_COST_ORDER" ) )
         ctx->costOrder = false;
       if( const char *env = std::getenv( "VOFX_FLUX_BLOCKS_PER_SM" ) )
@@ -932,6 +940,8 @@ extern "C"
     cudaFree( ctx->swzCells );
     cudaFree( ctx->swzTasks );
     cudaFree( ctx->swzCounter );
+    cudaFree( ctx->swzOrder );
+    cudaFree( ctx->swzSort );
     cudaFree( ctx->ifBlockSums );
     cudaFree( ctx->ifCells );
     cudaFree( ctx->ifNverts );

@@ -1407,7 +1407,8 @@ namespace vofx
     double cen[ 3 ];
     int owner;                        // index into the mixed list / SwzCell array
     int which;                        // 0: the cell itself, a > 0: its (a-1)-th mixed neighbour
-    int state, pad;
+    int state;
+    int cls;                          // bracket the last plane-constant solve of this task ended in (7: walked on lane 0): sort key of the next iteration
   };
 
   template< int DIM_ >
@@ -1462,6 +1463,7 @@ namespace vofx
       {
         tasks[ base + a ].owner = p;
         tasks[ base + a ].which = a;
+        tasks[ base + a ].cls = 0;
       }
     }
   }
@@ -1478,23 +1480,99 @@ namespace vofx
     }
   }
 
+  // Every iteration the tasks of the still-active cells are counting-sorted by the bracket their last solve ended in (the
+  // same idea as k_cost_order: the eight tasks of a warp of k_swz_locate leave the bracket loop together, and the tasks of
+  // converged cells no longer occupy lanes of k_swz_locate / k_swz_centroid).  sort[ 0 .. 15 ] histogram, [ 16 .. 31 ] fill
+  // counters, [ 32 ] number of active tasks; bucket 8 = inactive.
+  __device__ __forceinline__ int swz_task_bucket ( const SwzCell *cells, const SwzTask &T ) { return cells[ T.owner ].active ? ( T.cls & 7 ) : 8; }
+
+  static __global__ void __launch_bounds__( 256 ) k_swz_hist ( const SwzCell *__restrict__ cells, const SwzTask *__restrict__ tasks, const int *taskCounter, int *sort )
+  {
+    __shared__ int hist[ 16 ];
+    if( threadIdx.x < 16 )
+      hist[ threadIdx.x ] = 0;
+    __syncthreads();
+    const int nTasks = *taskCounter;
+    for( int t = blockIdx.x * 256 + threadIdx.x; t < nTasks; t += gridDim.x * 256 )
+      atomicAdd( &hist[ swz_task_bucket( cells, tasks[ t ] ) ], 1 );
+    __syncthreads();
+    if( threadIdx.x < 16 && hist[ threadIdx.x ] )
+      atomicAdd( &sort[ threadIdx.x ], hist[ threadIdx.x ] );
+  }
+
+  static __global__ void __launch_bounds__( 256 ) k_swz_order ( const SwzCell *__restrict__ cells, const SwzTask *__restrict__ tasks, const int *taskCounter, int *sort,
+                                                                 int *__restrict__ order )
+  {
+    __shared__ int warpCount[ 16 ][ 8 ], tileBase[ 16 ], start[ 16 ];
+    const int nTasks = *taskCounter;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if( threadIdx.x == 0 )
+    {
+      int at = 0;
+      for( int c = 7; c >= 0; --c )      // expensive first; the inactive tasks behind all active ones
+      {
+        start[ c ] = at;
+        at += sort[ c ];
+      }
+      start[ 8 ] = at;
+      if( blockIdx.x == 0 )
+        sort[ 32 ] = at;                 // active tasks: the grid-stride loops of this iteration's kernels end here
+    }
+    __syncthreads();
+    const int rounded = ( nTasks + 255 ) & ~255;
+    for( int first = blockIdx.x * 256; first < rounded; first += gridDim.x * 256 )
+    {
+      const int t = first + threadIdx.x;
+      const bool valid = t < nTasks;
+      const int bucket = valid ? swz_task_bucket( cells, tasks[ t ] ) : 16 + warp;
+      if( threadIdx.x < 128 )
+        warpCount[ threadIdx.x >> 3 ][ threadIdx.x & 7 ] = 0;
+      __syncthreads();
+      const unsigned peers = __match_any_sync( 0xffffffffu, bucket );
+      const int below = __popc( peers & ( ( 1u << lane ) - 1u ) );
+      if( valid && below == 0 )
+        warpCount[ bucket ][ warp ] = __popc( peers );
+      __syncthreads();
+      if( threadIdx.x < 9 )
+      {
+        const int b = threadIdx.x;
+        int n = 0;
+        for( int w = 0; w < 8; ++w )
+        {
+          const int a = warpCount[ b ][ w ];
+          warpCount[ b ][ w ] = n;
+          n += a;
+        }
+        tileBase[ b ] = n ? atomicAdd( &sort[ 16 + b ], n ) : 0;
+      }
+      __syncthreads();
+      if( valid )
+      {
+        const int pos = start[ bucket ] + tileBase[ bucket ] + warpCount[ bucket ][ warp ] + below;
+        if( pos < nTasks )
+          order[ pos ] = t;
+      }
+      __syncthreads();
+    }
+  }
+
   template< int L >
   __global__ void __launch_bounds__( 16 * L, VOFX_YOUNGS_THREADS_PER_SM / ( 16 * L ) ) k_swz_locate ( Grid g, const double *__restrict__ u, const SwzCell *__restrict__ cells,
                                                                                                         SwzTask *__restrict__ tasks, const int *taskCounter,
-                                                                                                        const coop::SweepTable *__restrict__ table )
+                                                                                                        const coop::SweepTable *__restrict__ table, const int *__restrict__ order )
   {
     constexpr int GROUPS = 16;
     __shared__ coop::LocateScratch scratch[ GROUPS ];
-    const int nTasks = *taskCounter;
+    const int nTasks = *taskCounter;     // with `order`: the tasks of the still-active cells, sorted by class (k_swz_order)
     const int lane = threadIdx.x % L;
     const int group = threadIdx.x / L;
     coop::Group G;
     G.lane = lane;
     G.mask = ( ( 1u << L ) - 1u ) << ( ( threadIdx.x & 31 ) - lane );
     coop::LocateScratch &S = scratch[ group ];
-    for( int t = blockIdx.x * GROUPS + group; t < nTasks; t += gridDim.x * GROUPS )
+    for( int q = blockIdx.x * GROUPS + group; q < nTasks; q += gridDim.x * GROUPS )
     {
-      SwzTask &T = tasks[ t ];
+      SwzTask &T = tasks[ order ? order[ q ] : q ];
       const SwzCell &C = cells[ T.owner ];
       if( !C.active )
         continue;
@@ -1506,12 +1584,14 @@ namespace vofx
       coop::RootTask root;
       root.pending = 0;
       double dist = 0.0;
-      const bool ok = coop::locate_coop< L >( G, S, *table, lo, g.h, normal, color, dist, &root );
+      int cost = 0;
+      const bool ok = coop::locate_coop< L >( G, S, *table, lo, g.h, normal, color, dist, &root, &cost );
       if( lane == 0 )
       {
         T.state = !ok ? 2 : ( root.pending ? 1 : 0 );
         T.dist = dist;
         T.root = root;
+        T.cls = cost;
       }
       G.sync();
     }
@@ -1519,12 +1599,12 @@ namespace vofx
 
   template< int DIM_ >
   __global__ void __launch_bounds__( 64 ) k_swz_centroid ( Grid g, const double *__restrict__ u, const SwzCell *__restrict__ cells, SwzTask *__restrict__ tasks,
-                                                            const int *taskCounter )
+                                                            const int *taskCounter, const int *__restrict__ order )
   {
     const int nTasks = *taskCounter;
-    for( int t = blockIdx.x * blockDim.x + threadIdx.x; t < nTasks; t += gridDim.x * blockDim.x )
+    for( int q = blockIdx.x * blockDim.x + threadIdx.x; q < nTasks; q += gridDim.x * blockDim.x )
     {
-      SwzTask &T = tasks[ t ];
+      SwzTask &T = tasks[ order ? order[ q ] : q ];
       const SwzCell &C = cells[ T.owner ];
       if( !C.active )
         continue;

@@ -45,6 +45,7 @@ extern "C" {
  *   VOFX_YOUNGS_BLOCKS_PER_SM = n   grid of the 3D plane-constant kernel in 64-thread blocks per SM (default 60)
  *   VOFX_FLUX_BLOCKS_PER_SM, VOFX_UPDATE_BLOCKS_PER_SM = n   grids of the 3D flux / update kernels (default 8)
  *   VOFX_SWZ_BLOCKS_PER_SM, VOFX_SWZ_OTHER_BLOCKS_PER_SM = n   grids of the batched Swartz kernels (default 80 / 48)
+ *   VOFX_SWZ_NO_SORT    = 1   batched 3D Swartz: do not sort the (cell, neighbour) tasks by last iteration's bracket
  *   VOFX_NO_COST_ORDER  = 1   process the band in list order instead of last step's expensive cells first
  *   VOFX_BAND_PARTS     = 1 .. 4   chains ( plane-constant solve -> root search -> fluxes ) a 3D Young's / height-function pass runs
  *                                  on as many streams (default 2; joined before the update)
