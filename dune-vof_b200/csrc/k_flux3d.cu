@@ -11,12 +11,12 @@ namespace vofx
     { k_flux< 3 ><<< blocks, 128, 0, s >>>( g, velocity, hs, flags, mixedList, state, capacity, records, timeOverride, dtOverride ); }
     void flux_cell3 ( int lanes, int blocks, cudaStream_t s, Grid g, const Velocity *velocity, const Velocity &velocityByValue, const double *hs, const unsigned char *flags, const int *mixedList,
                       StepState *state, int capacity, FluxRecord *records, int *tasks, int taskCapacity, const void *clipTable,
-                      const double *timeOverride, const double *dtOverride, const int *order, BandPart bp, int withSerialClips )
+                      const double *timeOverride, const double *dtOverride, BandPart bp, int withSerialClips )
     {
       if( lanes == 4 )
-        pdl( k_flux_cell3< 3, 4 >, blocks * 2, 64, s, g, velocityByValue, hs, flags, mixedList, state, capacity, records, tasks, taskCapacity, (const coop::ClipCase *) clipTable, timeOverride, dtOverride, order, bp );
+        pdl( k_flux_cell3< 3, 4 >, blocks * 2, 64, s, g, velocityByValue, hs, flags, mixedList, state, capacity, records, tasks, taskCapacity, (const coop::ClipCase *) clipTable, timeOverride, dtOverride, bp );
       else
-        pdl( k_flux_cell3< 3, 8 >, blocks, 128, s, g, velocityByValue, hs, flags, mixedList, state, capacity, records, tasks, taskCapacity, (const coop::ClipCase *) clipTable, timeOverride, dtOverride, order, bp );
+        pdl( k_flux_cell3< 3, 8 >, blocks, 128, s, g, velocityByValue, hs, flags, mixedList, state, capacity, records, tasks, taskCapacity, (const coop::ClipCase *) clipTable, timeOverride, dtOverride, bp );
       if( withSerialClips )
         flux_clip_serial3( s, g, velocity, hs, flags, mixedList, state, records, tasks, taskCapacity, timeOverride, dtOverride );
     }

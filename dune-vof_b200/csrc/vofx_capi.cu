@@ -592,7 +592,7 @@ namespace
       launch::locate_root3( ( ctx->numSMs * 8 + parts - 1 ) / parts, s, ctx->state, ctx->capacity, ctx->rootTasks, hs, bp );
       launch::locate_serial3( s, g, u, ctx->state, hs, ctx->serialCells, ctx->capacity, bp );
       launch::flux_cell3( ctx->fluxLanes, ( ctx->numSMs * ctx->fluxBlocksPerSM + parts - 1 ) / parts, s, g, ctx->velDev, ctx->velHost, hs, flags, ctx->mixedList, ctx->state,
-                          ctx->capacity, ctx->records, ctx->tasks, ctx->taskCapacity, ctx->clipTable, nullptr, nullptr, nullptr, bp, 0 );
+                          ctx->capacity, ctx->records, ctx->tasks, ctx->taskCapacity, ctx->clipTable, nullptr, nullptr, bp, 0 );
       ctx->launches += 4;
       VOFX_CUDA( cudaGetLastError() );
       VOFX_CUDA( cudaEventRecord( ctx->evBandJoin[ q ], s ) );

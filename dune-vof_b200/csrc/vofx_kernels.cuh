@@ -1076,7 +1076,7 @@ namespace vofx
         out[ 0 ] = normal[ 0 ];
         out[ 1 ] = normal[ 1 ];
         out[ 2 ] = normal[ 2 ];
-        // the root tasks sit at the cell's position in the processing order: no counter shared by 1e5 cells
+        // the root tasks sit at the cell's position in the band list: no counter shared by 1e5 cells
         if( !located )
           serialCells[ atomicAdd( serialCounter, 1 ) ] = c;
         else if( root.pending )
@@ -2003,8 +2003,7 @@ namespace vofx
                                                               const unsigned char *__restrict__ flags, const int *__restrict__ mixedList,
                                                               StepState *state, int capacity, FluxRecord *__restrict__ records,
                                                               int *__restrict__ tasks, int taskCapacity, const coop::ClipCase *__restrict__ clipTable,
-                                                              const double *timeOverride, const double *dtOverride,
-                                                              const int *__restrict__ order, BandPart bp )
+                                                              const double *timeOverride, const double *dtOverride, BandPart bp )
   {
     pdl_prologue();
     constexpr int DIM = 3, LANES = L, NFACES = 6;
@@ -2541,8 +2540,6 @@ namespace vofx
     state->serialLocate = 0;
     state->serialLocateMore[ 0 ] = state->serialLocateMore[ 1 ] = state->serialLocateMore[ 2 ] = 0;
     state->rootCount = 0;
-    state->slowFront = 0;
-    state->normalBack = 0;
     for( int c = 0; c < 32; ++c )
       state->costHist[ c ] = state->costFill[ c ] = 0;
   }
@@ -2557,8 +2554,6 @@ namespace vofx
     state->serialLocateMore[ 0 ] = state->serialLocateMore[ 1 ] = state->serialLocateMore[ 2 ] = 0;
     state->rootCount = 0;
     state->changedCount = 0;
-    state->slowFront = 0;
-    state->normalBack = 0;
     for( int c = 0; c < 32; ++c )
       state->costHist[ c ] = state->costFill[ c ] = 0;
     state->dtEst = DBL_MAX;

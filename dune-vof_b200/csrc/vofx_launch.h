@@ -118,7 +118,7 @@ namespace vofx
                  StepState *state, int capacity, FluxRecord *records, const double *timeOverride, const double *dtOverride );
     void flux_cell3 ( int lanes, int blocks, cudaStream_t s, Grid g, const Velocity *velocity, const Velocity &velocityByValue, const double *hs, const unsigned char *flags, const int *mixedList,
                       StepState *state, int capacity, FluxRecord *records, int *tasks, int taskCapacity, const void *clipTable,
-                      const double *timeOverride, const double *dtOverride, const int *order = nullptr, BandPart bp = BandPart(), int withSerialClips = 1 );
+                      const double *timeOverride, const double *dtOverride, BandPart bp = BandPart(), int withSerialClips = 1 );
     void flux_clip_serial3 ( cudaStream_t s, Grid g, const Velocity *velocity, const double *hs, const unsigned char *flags, const int *mixedList,
                              StepState *state, FluxRecord *records, int *tasks, int taskCapacity, const double *timeOverride, const double *dtOverride );
     size_t clip_table_bytes ();

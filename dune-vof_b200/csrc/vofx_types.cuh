@@ -22,8 +22,7 @@ namespace vofx
     int rootCount;              // mixed cells whose bracket is found and whose root search is left to k_locate_root3
     int changedCount;           // entries of the changed-cell list of the current step (host-buffer variant: sparse write-back)
     int changedCountLast;
-    int slowFront;              // k_cost_order: expensive cells placed from the front of the processing order ...
-    int normalBack;             // ... the others from the back
+    int unused0, unused1;
     int overflowLast;           // the last finished pass overflowed the mixed list: it was a no-op (time and u unchanged)
     int segCount;               // incremental flagging: marked row segments of this pass (k_scan_marks -> k_flag_segments)
     int epoch;                  // number of the pass in flight (1, 2, ...): the stamp of the peer-memory signals of the distributed step
