@@ -24,12 +24,12 @@ namespace vofx
     // all iterations of the batched Swartz reconstruction (4 kernels each) after the setup; `counter` is zeroed by the caller
     void swartz_batched3 ( int lanes, int sms, cudaStream_t s, Grid g, const double *u, const unsigned char *flags, const int *mixedList, StepState *state,
                            int capacity, double *hs, int maxIterations, const void *sweepTable, void *cells, void *tasks, int *counter,
-                           int cellCapacity, int taskCapacity, int *order, int *sort )
+                           int cellCapacity, int taskCapacity, int *order, int *sort, int *cellList, int *listCount )
     {
       const coop::SweepTable *T = (const coop::SweepTable *) sweepTable;
       SwzCell *C = (SwzCell *) cells;
       SwzTask *K = (SwzTask *) tasks;
-      k_swz_setup< 3 ><<< sms * 8, 128, 0, s >>>( g, flags, mixedList, state, capacity, hs, C, K, counter, cellCapacity, taskCapacity );
+      k_swz_setup< 3 ><<< sms * 8, 128, 0, s >>>( g, flags, mixedList, state, capacity, hs, C, K, counter, cellCapacity, taskCapacity, cellList, listCount );
       // grid-stride kernels over the (cell, neighbour) tasks: grids well beyond the resident blocks balance the waves
       // (256^3, ms per step: 16 blocks/SM 9.75, 40 8.99, 80 8.72)
       static const int locateBlocks = std::getenv( "VOFX_SWZ_BLOCKS_PER_SM" ) ? std::atoi( std::getenv( "VOFX_SWZ_BLOCKS_PER_SM" ) ) : 80;
@@ -53,10 +53,10 @@ namespace vofx
           k_swz_locate< 4 ><<< sms * locateBlocks, 64, 0, s >>>( g, u, C, K, nActive, T, ord );
         k_swz_centroid< 3 ><<< sms * otherBlocks, 64, 0, s >>>( g, u, C, K, nActive, ord );
         if( lanes == 8 )
-          k_swz_normal< 8 ><<< sms * 8, 64, 0, s >>>( g, u, C, K, state, capacity, T );
+          k_swz_normal< 8 ><<< sms * 8, 64, 0, s >>>( g, u, C, K, state, capacity, T, cellList, listCount, it, cellCapacity );
         else
-          k_swz_normal< 4 ><<< sms * otherBlocks, 32, 0, s >>>( g, u, C, K, state, capacity, T );
-        k_swz_finish< 3 ><<< sms * 8, 64, 0, s >>>( g, u, C, state, capacity, hs, maxIterations );
+          k_swz_normal< 4 ><<< sms * otherBlocks, 32, 0, s >>>( g, u, C, K, state, capacity, T, cellList, listCount, it, cellCapacity );
+        k_swz_finish< 3 ><<< sms * 8, 64, 0, s >>>( g, u, C, state, capacity, hs, maxIterations, cellList, listCount, it, cellCapacity );
       }
     }
     // forces the (lazily loaded) kernels of this translation unit into the context: a first launch loads its kernel, which

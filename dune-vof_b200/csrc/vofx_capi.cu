@@ -70,6 +70,8 @@ struct vofx_ctx
   int *swzCounter = nullptr;
   int *swzOrder = nullptr, *swzSort = nullptr;   // per iteration: active tasks sorted by class, and the sort's counters (64 ints)
   size_t swzOrderCap = 0;
+  int *swzCellList = nullptr, *swzListCount = nullptr;   // the cells still iterating: two lists of swzCellCount entries, and their lengths
+  size_t swzCellListCap = 0;
   bool swzSortTasks = true;                      // VOFX_SWZ_NO_SORT=1 switches the per-iteration task sort off
   // interface extraction (vofx_interface): grow-only scratch
   int *ifBlockSums = nullptr, *ifCells = nullptr, *ifNverts = nullptr, *ifOffsets = nullptr;
@@ -497,6 +499,8 @@ namespace
               rcs = rcs ? rcs : ensureDevice( ctx->swzCounter, (size_t) 1 );
               rcs = rcs ? rcs : growDevice( ctx->swzOrder, ctx->swzOrderCap, cellsWanted * 27 + 16 );
               rcs = rcs ? rcs : ensureDevice( ctx->swzSort, (size_t) 64 );
+              rcs = rcs ? rcs : growDevice( ctx->swzCellList, ctx->swzCellListCap, 2 * cellsWanted + 16 );
+              rcs = rcs ? rcs : ensureDevice( ctx->swzListCount, (size_t) 4 );
               if( rcs )
                 return rcs;
               ctx->swzCellCount = cellsWanted;
@@ -508,7 +512,8 @@ namespace
           profBegin( ctx );
           launch::swartz_batched3( lanes, ctx->numSMs, ctx->stream, g, u, flags, ctx->mixedList, ctx->state, ctx->capacity, hs, maxIterations, ctx->sweepTable,
                                    ctx->swzCells, ctx->swzTasks, ctx->swzCounter, (int) ctx->swzCellCount, (int) ( ctx->swzCellCount * 27 ),
-                                   ctx->swzSortTasks ? ctx->swzOrder : nullptr, ctx->swzSortTasks ? ctx->swzSort : nullptr );
+                                   ctx->swzSortTasks ? ctx->swzOrder : nullptr, ctx->swzSortTasks ? ctx->swzSort : nullptr,
+                                   ctx->swzSortTasks ? ctx->swzCellList : nullptr, ctx->swzSortTasks ? ctx->swzListCount : nullptr );
           ctx->launches += ( ctx->swzSortTasks ? 6 : 4 ) * maxIterations;
         }
       }
@@ -941,6 +946,8 @@ extern "C"
     cudaFree( ctx->swzTasks );
     cudaFree( ctx->swzCounter );
     cudaFree( ctx->swzOrder );
+    cudaFree( ctx->swzCellList );
+    cudaFree( ctx->swzListCount );
     cudaFree( ctx->swzSort );
     cudaFree( ctx->ifBlockSums );
     cudaFree( ctx->ifCells );

@@ -1415,9 +1415,15 @@ namespace vofx
   __global__ void __launch_bounds__( 128 ) k_swz_setup ( Grid g, const unsigned char *__restrict__ flags, const int *__restrict__ mixedList,
                                                           StepState *state, int capacity, const double *__restrict__ hs,
                                                           SwzCell *__restrict__ cells, SwzTask *__restrict__ tasks, int *taskCounter,
-                                                          int cellCapacity, int taskCapacity )
+                                                          int cellCapacity, int taskCapacity, int *__restrict__ cellList, int *listCount )
   {
     const int count = mixed_count( state, capacity );
+    // the cells still iterating, as a list per iteration (k_swz_finish fills the next one): list 0 = every cell of the band
+    if( cellList && blockIdx.x == 0 && threadIdx.x == 0 )
+    {
+      listCount[ 0 ] = ( count > cellCapacity ) ? 0 : count;
+      listCount[ 1 ] = 0;
+    }
     // the buffers are sized by the host from the band of an earlier pass (no read-back per pass, the pass stays
     // graph-capturable): a band that outgrew them turns the pass into a no-op and the host sees the overflow at its next
     // read of the loop state (and enlarges the buffers)
@@ -1433,6 +1439,8 @@ namespace vofx
       int ijk[ 3 ];
       cell_ijk( g, c, ijk );
       SwzCell &C = cells[ p ];
+      if( cellList )
+        cellList[ p ] = p;
       int n = 0;
       for( int s = 0; s < 26; ++s )
       {
@@ -1644,20 +1652,26 @@ namespace vofx
 
   template< int L >
   __global__ void __launch_bounds__( 8 * L ) k_swz_normal ( Grid g, const double *__restrict__ u, SwzCell *__restrict__ cells, const SwzTask *__restrict__ tasks,
-                                                             const StepState *state, int capacity, const coop::SweepTable *__restrict__ table )
+                                                             const StepState *state, int capacity, const coop::SweepTable *__restrict__ table,
+                                                             const int *__restrict__ cellList, int *listCount, int iteration, int cellCapacity )
   {
     constexpr int GROUPS = 8;
     __shared__ SwzNormalScratch scratch[ GROUPS ];
-    const int count = mixed_count( state, capacity );
+    // cellList: the cells still iterating (list iteration & 1, written by the previous iteration's k_swz_finish); the other
+    // list is emptied here for this iteration's k_swz_finish
+    const int *list = cellList ? cellList + ( iteration & 1 ) * cellCapacity : nullptr;
+    const int count = list ? listCount[ iteration & 1 ] : mixed_count( state, capacity );
+    if( list && blockIdx.x == 0 && threadIdx.x == 0 )
+      listCount[ ( iteration & 1 ) ^ 1 ] = 0;
     const int lane = threadIdx.x % L;
     const int group = threadIdx.x / L;
     coop::Group G;
     G.lane = lane;
     G.mask = ( ( 1u << L ) - 1u ) << ( ( threadIdx.x & 31 ) - lane );
     SwzNormalScratch &S = scratch[ group ];
-    for( int p = blockIdx.x * GROUPS + group; p < count; p += gridDim.x * GROUPS )
+    for( int q = blockIdx.x * GROUPS + group; q < count; q += gridDim.x * GROUPS )
     {
-      SwzCell &C = cells[ p ];
+      SwzCell &C = cells[ list ? list[ q ] : q ];
       if( !C.active )
         continue;
       const int nNb = C.nNb;
@@ -1748,11 +1762,15 @@ namespace vofx
 
   template< int DIM_ >
   __global__ void __launch_bounds__( 64 ) k_swz_finish ( Grid g, const double *__restrict__ u, SwzCell *__restrict__ cells, const StepState *state, int capacity,
-                                                          double *__restrict__ hs, int maxIterations )
+                                                          double *__restrict__ hs, int maxIterations, int *__restrict__ cellList, int *listCount, int iteration,
+                                                          int cellCapacity )
   {
-    const int count = mixed_count( state, capacity );
-    for( int p = blockIdx.x * blockDim.x + threadIdx.x; p < count; p += gridDim.x * blockDim.x )
+    const int *list = cellList ? cellList + ( iteration & 1 ) * cellCapacity : nullptr;
+    int *next = cellList ? cellList + ( ( iteration & 1 ) ^ 1 ) * cellCapacity : nullptr;
+    const int count = list ? listCount[ iteration & 1 ] : mixed_count( state, capacity );
+    for( int q = blockIdx.x * blockDim.x + threadIdx.x; q < count; q += gridDim.x * blockDim.x )
     {
+      const int p = list ? list[ q ] : q;
       SwzCell &C = cells[ p ];
       if( !C.active )
         continue;
@@ -1783,6 +1801,8 @@ namespace vofx
       const int it = C.iterations + 1;
       C.iterations = it;
       C.active = ( residuum > 1e-12 && it < maxIterations ) ? 1 : 0;
+      if( next && C.active )
+        next[ atomicAdd( &listCount[ ( iteration & 1 ) ^ 1 ], 1 ) ] = p;
     }
   }
 

@@ -113,7 +113,7 @@ namespace vofx
     size_t swz_task_bytes ();
     void swartz_batched3 ( int lanes, int sms, cudaStream_t s, Grid g, const double *u, const unsigned char *flags, const int *mixedList, StepState *state,
                            int capacity, double *hs, int maxIterations, const void *sweepTable, void *cells, void *tasks, int *counter,
-                           int cellCapacity, int taskCapacity, int *order = nullptr, int *sort = nullptr );
+                           int cellCapacity, int taskCapacity, int *order = nullptr, int *sort = nullptr, int *cellList = nullptr, int *listCount = nullptr );
     void flux3 ( int blocks, cudaStream_t s, Grid g, const Velocity *velocity, const double *hs, const unsigned char *flags, const int *mixedList,
                  StepState *state, int capacity, FluxRecord *records, const double *timeOverride, const double *dtOverride );
     void flux_cell3 ( int lanes, int blocks, cudaStream_t s, Grid g, const Velocity *velocity, const Velocity &velocityByValue, const double *hs, const unsigned char *flags, const int *mixedList,
