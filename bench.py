@@ -601,9 +601,21 @@ def main():
                 sub[nm]["fp64_pipe_source"] = "profiles/r2_ncu_summary.json (static: ncu --set full capture of this workload)"
     except Exception:
         pass
+    # DRAM traffic of one step from the committed ncu captures of this workload (static, per launch; the band kernels run as
+    # two chains, a capture is one chain): far below the algorithmic 17 B/cell because the dense passes are gone
+    traffic, traffic_note = None, "not captured in this run; per-kernel dram bytes of the ncu captures are under profiles/"
+    try:
+        summary = json.load(open(os.path.join(ROOT, "profiles", "r2_ncu_summary.json")))
+        per_step = {"k_flag_segments": 1, "k_youngs_coop3": 2, "k_locate_root3": 2, "k_flux_cell3": 2, "k_update": 1}
+        if world == 1 and incremental and all(k in summary for k in per_step):
+            traffic = float(sum(summary[k]["dram_bytes_total"] * n for k, n in per_step.items()))
+            traffic_note = ("static: dram__bytes_read.sum + dram__bytes_write.sum of the committed ncu --set full captures of this workload "
+                            "(profiles/r2_ncu_summary.json), summed over the launches of one step (two band chains); not measured in this run")
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": "whole step (SURVEY.md 8(d): cell-steps/s per GPU x 17 B against the measured HBM peak)",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "traffic_note": "not captured in this run; per-kernel dram bytes of the ncu captures are under profiles/",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_note": traffic_note,
                 "algorithmic_bytes_per_cell_step": SURVEY_BYTES_PER_CELL_STEP,
                 "algorithmic_bytes_per_step_per_gpu": SURVEY_BYTES_PER_CELL_STEP * cells_per_gpu,
                 "peak_source": peak_src, "ms_per_step": step_ms,
